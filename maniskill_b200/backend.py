@@ -1,0 +1,186 @@
+"""ctypes binding of libb200sim.so (include/b200sim.h) -- the object ManiSkill-side code talks to instead of
+``sapien.physx.PhysxGpuSystem`` (mani_skill/envs/scene.py:40-66, 379-380, 950-986).
+
+There is NO CPU path: constructing a :class:`World` without the compiled CUDA library or without a CUDA device
+raises.  The exposed buffers are torch CUDA tensors that alias the device state, exactly like
+``px.cuda_rigid_body_data.torch()`` (mani_skill/utils/structs/base.py:262-270).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .model import B2SModelStruct, CompiledModel
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200sim.so")
+
+BUF_RIGID, BUF_ROOT_POSE, BUF_QPOS, BUF_QVEL, BUF_QF, BUF_TARGET_QPOS, BUF_TARGET_QVEL, BUF_QACC, BUF_LINK = [1 << i for i in range(9)]
+BUF_ALL = 0xFFFFFFFF
+BUF_APPLY_ALL = BUF_RIGID | BUF_ROOT_POSE | BUF_QPOS | BUF_QVEL | BUF_QF | BUF_TARGET_QPOS | BUF_TARGET_QVEL
+
+
+class B2SBufferTable(C.Structure):
+    _fields_ = [("rigid_body_data", C.c_void_p), ("qpos", C.c_void_p), ("qvel", C.c_void_p), ("qacc", C.c_void_p),
+                ("qf", C.c_void_p), ("target_qpos", C.c_void_p), ("target_qvel", C.c_void_p), ("n_rows", C.c_int32),
+                ("max_dof", C.c_int32), ("contact_count", C.c_void_p), ("overflow_flag", C.c_void_p)]
+
+
+class B2SCameraDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("near_", C.c_float), ("far_", C.c_float), ("mount_row", C.c_int32),
+                ("local_pose", C.c_float * 7)]
+
+
+class B2SVisualTable(C.Structure):
+    _fields_ = [("n_visual", C.c_int32), ("type", C.c_void_p), ("row", C.c_void_p), ("pose", C.c_void_p), ("size", C.c_void_p),
+                ("hull", C.c_void_p), ("color", C.c_void_p), ("seg_id", C.c_void_p), ("hidden", C.c_void_p), ("n_tri", C.c_int32),
+                ("hull_tri_offset", C.c_void_p), ("hull_tris", C.c_void_p)]
+
+
+class B2SRenderTargets(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("position_seg", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libb200sim.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(b200sim has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.b2s_last_error.restype = C.c_char_p
+    lib.b2s_world_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+    lib.b2s_world_destroy.argtypes = [C.c_uint64]
+    lib.b2s_world_buffers.argtypes = [C.c_uint64, C.POINTER(B2SBufferTable)]
+    lib.b2s_step.argtypes = [C.c_uint64, C.c_int32, C.c_uint32, C.c_void_p]
+    lib.b2s_apply.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
+    lib.b2s_fetch.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
+    lib.b2s_update_kinematics.argtypes = [C.c_uint64, C.c_void_p]
+    lib.b2s_contact_query_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+    lib.b2s_contact_query_run.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.b2s_camera_group_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(B2SRenderTargets)]
+    lib.b2s_render.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["b2s_last_error", "b2s_version", "b2s_world_create", "b2s_world_destroy", "b2s_world_buffers", "b2s_step",
+                    "b2s_apply", "b2s_fetch", "b2s_update_kinematics", "b2s_contact_query_create", "b2s_contact_query_run",
+                    "b2s_camera_group_create", "b2s_render"]
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can alias library-owned device memory (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+        self._owner = owner
+
+
+def _as_tensor(ptr, shape, typestr, owner, device):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr, owner), device=device)
+
+
+def _check(lib, code):
+    if code != 0:
+        raise RuntimeError(f"b200sim error {code}: {lib.b2s_last_error().decode()}")
+
+
+class World:
+    """One batched world on one GPU (the PhysxGpuSystem + all sub-scenes of the reference)."""
+
+    def __init__(self, cm: CompiledModel, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200sim needs a CUDA device (B200); there is no CPU path")
+        self.lib = load_library()
+        self.cm = cm
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._struct = cm.struct()
+        h = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.b2s_world_create(C.addressof(self._struct), self.device.index, C.byref(h)))
+        self.h = h
+        tab = B2SBufferTable()
+        _check(self.lib, self.lib.b2s_world_buffers(self.h, C.byref(tab)))
+        s = cm.scalars
+        self.n_envs, self.n_rows, self.n_link, self.n_fb, self.n_art = s["n_envs"], tab.n_rows, s["n_link"], s["n_fb"], s["n_art"]
+        self.max_dof = max(tab.max_dof, 1)
+        N = self.n_envs
+        f4 = "<f4"
+        self.rigid_body_data = _as_tensor(tab.rigid_body_data, (N * self.n_rows, 13), f4, self, self.device)
+        shape_q = (N * max(self.n_art, 1), self.max_dof)
+        self.qpos = _as_tensor(tab.qpos, shape_q, f4, self, self.device)
+        self.qvel = _as_tensor(tab.qvel, shape_q, f4, self, self.device)
+        self.qacc = _as_tensor(tab.qacc, shape_q, f4, self, self.device)
+        self.qf = _as_tensor(tab.qf, shape_q, f4, self, self.device)
+        self.target_qpos = _as_tensor(tab.target_qpos, shape_q, f4, self, self.device)
+        self.target_qvel = _as_tensor(tab.target_qvel, shape_q, f4, self, self.device)
+        self.contact_count = _as_tensor(tab.contact_count, (N,), "<i4", self, self.device)
+        self.overflow_flag = _as_tensor(tab.overflow_flag, (1,), "<i4", self, self.device)
+        self._queries = {}
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ stream
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ px.* entry points
+    def step(self, substeps: int = 1, fetch_mask: int = 0):
+        _check(self.lib, self.lib.b2s_step(self.h, substeps, fetch_mask, self._stream()))
+        self.kernel_launches += 1
+
+    def apply(self, mask: int = BUF_APPLY_ALL):
+        _check(self.lib, self.lib.b2s_apply(self.h, mask, self._stream()))
+        self.kernel_launches += 1
+
+    def fetch(self, mask: int = BUF_ALL):
+        _check(self.lib, self.lib.b2s_fetch(self.h, mask, self._stream()))
+        self.kernel_launches += 1
+
+    def update_kinematics(self):
+        _check(self.lib, self.lib.b2s_update_kinematics(self.h, self._stream()))
+        self.kernel_launches += 1
+
+    def body_view(self):
+        """[n_envs, n_rows, 13] view of rigid_body_data."""
+        return self.rigid_body_data.view(self.n_envs, self.n_rows, 13)
+
+    def create_contact_query(self, row_pairs):
+        key = tuple(map(tuple, row_pairs))
+        if key not in self._queries:
+            rows = np.ascontiguousarray(np.asarray(row_pairs, dtype=np.int32).reshape(-1))
+            q = C.c_uint64(0)
+            _check(self.lib, self.lib.b2s_contact_query_create(self.h, rows.ctypes.data_as(C.c_void_p), len(row_pairs), C.byref(q)))
+            out = torch.zeros((self.n_envs, len(row_pairs), 3), dtype=torch.float32, device=self.device)
+            self._queries[key] = (q, out)
+        return key
+
+    def query_contact_impulses(self, key):
+        q, out = self._queries[key]
+        _check(self.lib, self.lib.b2s_contact_query_run(self.h, q, C.c_void_p(out.data_ptr()), self._stream()))
+        self.kernel_launches += 1
+        return out
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            torch.cuda.synchronize(self.device)
+            self.lib.b2s_world_destroy(self.h)
+            self.h = C.c_uint64(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

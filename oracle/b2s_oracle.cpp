@@ -202,17 +202,10 @@ static void step_env(Oracle& O, Env& E) {
     // implicit PD drive (docs/source/user_guide/concepts/controllers.md:134; articulation_joint.py:187-195)
     R kp = O.dof_drive[4 * i], kd = O.dof_drive[4 * i + 1], fl = O.dof_drive[4 * i + 2];
     R damp = O.dof_passive[4 * i], armature = O.dof_passive[4 * i + 2];
-    R e_tau = kp * (E.tq[i] - E.q[i]) + kd * (E.tqd[i] - E.qd[i]);
-    R t, a_imp;
-    if (std::fabs(e_tau) > fl) {
-      t = e_tau > 0 ? fl : -fl;
-      a_imp = 0;
-    } else {
-      t = kp * (E.tq[i] - E.q[i] - dt * E.qd[i]) + kd * (E.tqd[i] - E.qd[i]);
-      a_imp = dt * kd + dt * dt * kp;
-    }
-    tau[i] = t + E.qf[i] - damp * E.qd[i];
-    arm[i] = armature + a_imp + dt * damp;
+    (void)fl;
+    // first pass: every drive implicit.  tau = kp (tq - q - dt qd) + kd (tqd - qd), joint-space diagonal += dt kd + dt^2 kp
+    tau[i] = kp * (E.tq[i] - E.q[i] - dt * E.qd[i]) + kd * (E.tqd[i] - E.qd[i]) + E.qf[i] - damp * E.qd[i];
+    arm[i] = armature + dt * kd + dt * dt * kp + dt * damp;
   }
   // ------------------------------------------------------------ 2. collision detection
   const int ns = m.n_shape;
@@ -296,32 +289,53 @@ static void step_env(Oracle& O, Env& E) {
     n_points += n;
   }
   // ------------------------------------------------------------ 3. ABA (Featherstone RBDA table 7.1) in sub-scene axes
-  std::vector<M6> IAa(IA);
-  std::vector<V6> pAa(pA);
-  for (int i = nd - 1; i >= 0; i--) {
-    U[i] = IAa[i] * S[i];
-    R D = dot6(S[i], U[i]) + arm[i];
-    Dinv[i] = R(1) / D;
-    u[i] = tau[i] - dot6(S[i], pAa[i]);
-    int p = O.dof_parent[i];
-    if (p >= 0) {
-      M6 Ia = IAa[i];
-      for (int r = 0; r < 6; r++)
-        for (int c = 0; c < 6; c++) Ia.m[r][c] -= U[i].v[r] * U[i].v[c] * Dinv[i];
-      V6 pa = pAa[i] + Ia * cvp[i] + U[i] * (u[i] * Dinv[i]);
-      for (int r = 0; r < 6; r++) {
-        for (int c = 0; c < 6; c++) IAa[p].m[r][c] += Ia.m[r][c];
-        pAa[p].v[r] += pa.v[r];
-      }
-    }
-  }
+  // Drives are implicit springs with a force limit (PhysxArticulationJoint.set_drive_properties(force_limit=...),
+  // mani_skill/agents/controllers/pd_joint_pos.py:38-52).  Pass 0 treats every drive implicitly; a drive whose
+  // implicit force would exceed its limit is re-run as a constant force at the limit (pass 1).
+  std::vector<M6> IAa;
+  std::vector<V6> pAa;
   std::vector<V6> acc(nd);
   std::vector<R> qdd(nd);
-  for (int i = 0; i < nd; i++) {
-    int p = O.dof_parent[i];
-    V6 ap = (p >= 0 ? acc[p] : V6()) + cvp[i];
-    qdd[i] = (u[i] - dot6(U[i], ap)) * Dinv[i];
-    acc[i] = ap + S[i] * qdd[i];
+  for (int pass = 0; pass < 2; pass++) {
+    IAa = IA;
+    pAa = pA;
+    for (int i = nd - 1; i >= 0; i--) {
+      U[i] = IAa[i] * S[i];
+      R D = dot6(S[i], U[i]) + arm[i];
+      Dinv[i] = R(1) / D;
+      u[i] = tau[i] - dot6(S[i], pAa[i]);
+      int p = O.dof_parent[i];
+      if (p >= 0) {
+        M6 Ia = IAa[i];
+        for (int r = 0; r < 6; r++)
+          for (int c = 0; c < 6; c++) Ia.m[r][c] -= U[i].v[r] * U[i].v[c] * Dinv[i];
+        V6 pa = pAa[i] + Ia * cvp[i] + U[i] * (u[i] * Dinv[i]);
+        for (int r = 0; r < 6; r++) {
+          for (int c = 0; c < 6; c++) IAa[p].m[r][c] += Ia.m[r][c];
+          pAa[p].v[r] += pa.v[r];
+        }
+      }
+    }
+    for (int i = 0; i < nd; i++) {
+      int p = O.dof_parent[i];
+      V6 ap = (p >= 0 ? acc[p] : V6()) + cvp[i];
+      qdd[i] = (u[i] - dot6(U[i], ap)) * Dinv[i];
+      acc[i] = ap + S[i] * qdd[i];
+    }
+    if (pass == 1) break;
+    bool any_sat = false;
+    for (int i = 0; i < nd; i++) {
+      R kp = O.dof_drive[4 * i], kd = O.dof_drive[4 * i + 1], fl = O.dof_drive[4 * i + 2];
+      R damp = O.dof_passive[4 * i], armature = O.dof_passive[4 * i + 2];
+      R qd1 = E.qd[i] + dt * qdd[i];
+      R f = kp * (E.tq[i] - E.q[i] - dt * qd1) + kd * (E.tqd[i] - qd1);
+      if (std::fabs(f) > fl) {
+        any_sat = true;
+        tau[i] = (f > 0 ? fl : -fl) + E.qf[i] - damp * E.qd[i];
+        arm[i] = armature + dt * damp;
+      }
+    }
+    if (!any_sat) break;
   }
   // M~^-1 columns: unit joint torque, zero velocity / bias
   std::vector<R> Minv(nd * nd, 0);

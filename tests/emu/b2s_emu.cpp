@@ -1,0 +1,61 @@
+// TEST TOOL ONLY: compiles the device per-env code (maniskill_b200/csrc/*.cuh, all __host__ __device__) for the host
+// and loops it over envs, so the CUDA kernel's logic can be compared with the oracle on a machine without a GPU.
+// Never loaded by the product; maniskill_b200.backend only loads libb200sim.so and raises when no GPU is present.
+#include <stdio.h>
+
+#include "../../maniskill_b200/csrc/b2s_world.inl"
+
+namespace {
+struct HostMem {
+  static void* alloc(size_t n) { return malloc(n); }
+  static void upload(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+  static void zero(void* d, size_t n) { memset(d, 0, n); }
+  static void release(void* p) { free(p); }
+};
+typedef b2s::WorldT<HostMem> World;
+}  // namespace
+
+extern "C" {
+void* emu_create(const B2SModel* m) {
+  World* w = new World();
+  const char* err = w->build(*m);
+  if (err) { fprintf(stderr, "emu_create: %s\n", err); delete w; return nullptr; }
+  return w;
+}
+void emu_destroy(void* h) { World* w = (World*)h; w->release(); delete w; }
+void emu_step(void* h, int substeps, unsigned fetch_mask) {
+  World* w = (World*)h;
+  for (int e = 0; e < w->M.n_envs; e++) {
+    if (w->caps == 0) b2s::step_env<b2s::CapsS>(w->M, w->S, e, substeps, fetch_mask);
+    else b2s::step_env<b2s::CapsL>(w->M, w->S, e, substeps, fetch_mask);
+  }
+}
+void emu_apply(void* h, unsigned mask) {
+  World* w = (World*)h;
+  for (int e = 0; e < w->M.n_envs; e++) b2s::apply_env(w->M, w->S, e, mask);
+}
+void emu_fetch(void* h, unsigned mask) {
+  World* w = (World*)h;
+  for (int e = 0; e < w->M.n_envs; e++) {
+    if (w->caps == 0) b2s::fetch_env<b2s::CapsS>(w->M, w->S, e, mask);
+    else b2s::fetch_env<b2s::CapsL>(w->M, w->S, e, mask);
+  }
+}
+// raw pointers to the exposed (AoS) buffers, host memory here
+float* emu_buffer(void* h, int which) {
+  World* w = (World*)h;
+  switch (which) {
+    case 0: return w->S.body_data;
+    case 1: return w->S.xq;
+    case 2: return w->S.xqd;
+    case 3: return w->S.xqacc;
+    case 4: return w->S.xqf;
+    case 5: return w->S.xtq;
+    case 6: return w->S.xtqd;
+    case 7: return w->S.man;
+  }
+  return nullptr;
+}
+int* emu_man_count(void* h) { return ((World*)h)->S.man_count; }
+int emu_overflow(void* h) { return *((World*)h)->S.overflow; }
+}

@@ -1,0 +1,97 @@
+"""Shared seeded scenarios for the parity tests (oracle vs host emulation vs CUDA through the C-ABI)."""
+import numpy as np
+
+from maniskill_b200.scenes import PANDA_REST_QPOS, pick_cube_scene
+
+
+def pick_cube_random_actions(n_envs, n_substeps=100, seed=0, action_every=5):
+    """Yields (step, target_qpos or None). PickCube reset state + random joint-delta targets, like the benchmark's
+    random actions (mani_skill/examples/benchmarking/gpu_sim.py:97-108)."""
+    rng = np.random.RandomState(seed)
+    q0 = PANDA_REST_QPOS + rng.normal(0, 0.02, (n_envs, 9))
+    q0[:, 7:] = 0.04
+    cube = np.zeros((n_envs, 13))
+    cube[:, 0:2] = rng.uniform(-0.1, 0.1, (n_envs, 2))
+    cube[:, 2] = 0.02
+    yaw = rng.uniform(0, 2 * np.pi, n_envs)
+    cube[:, 3] = np.cos(yaw / 2)
+    cube[:, 6] = np.sin(yaw / 2)
+    deltas = [rng.uniform(-0.1, 0.1, (n_envs, 9)) for _ in range(n_substeps // action_every + 1)]
+    grip = [rng.uniform(-0.01, 0.04, (n_envs, 1)) for _ in range(n_substeps // action_every + 1)]
+    return q0, cube, deltas, grip
+
+
+def run_pick_cube(world_kind, cm, n_substeps=100, seed=0, device=None):
+    """Runs the scenario on 'oracle32' / 'oracle64' / 'emu' / 'cuda'; returns dict of final numpy arrays."""
+    N = cm.scalars["n_envs"]
+    q0, cube, deltas, grip = pick_cube_random_actions(N, n_substeps, seed)
+    cube_fb = cm.actor_fb["cube"]
+    n_link = cm.scalars["n_link"]
+    if world_kind.startswith("oracle"):
+        from oracle.oracle import OracleWorld
+        w = OracleWorld(cm, "f32" if world_kind == "oracle32" else "f64")
+        w.set_joint("qpos", q0)
+        w.set_joint("target_qpos", q0)
+        b = w.get_bodies()
+        b[:, cube_fb] = cube
+        w.set_bodies(b)
+        for s in range(n_substeps):
+            if s % 5 == 0:
+                tq = w.get_joint("qpos") + deltas[s // 5]
+                tq[:, 7:] = grip[s // 5]
+                w.set_joint("target_qpos", tq)
+            w.step(1)
+        return dict(qpos=w.get_joint("qpos"), qvel=w.get_joint("qvel"), body=w.rigid_body_data(), world=w)
+    if world_kind == "emu":
+        from emu import EmuWorld
+        w = EmuWorld(cm)
+        w.qpos[:] = q0
+        w.target_qpos[:] = q0
+        w.rigid_body_data[:, n_link + cube_fb] = cube
+        w.apply()
+        for s in range(n_substeps):
+            if s % 5 == 0:
+                w.fetch(4)
+                tq = w.qpos.astype(np.float64) + deltas[s // 5]
+                tq[:, 7:] = grip[s // 5]
+                w.target_qpos[:] = tq
+                w.apply(32)
+            w.step(1, 0)
+        w.fetch()
+        return dict(qpos=w.qpos.astype(np.float64), qvel=w.qvel.astype(np.float64), body=w.rigid_body_data.astype(np.float64), world=w)
+    if world_kind == "cuda":
+        import torch
+        from maniskill_b200.backend import BUF_ALL, World
+        w = World(cm, device)
+        dev = w.device
+        w.qpos[:] = torch.tensor(q0, dtype=torch.float32, device=dev)
+        w.target_qpos[:] = w.qpos
+        w.body_view()[:, n_link + cube_fb] = torch.tensor(cube, dtype=torch.float32, device=dev)
+        w.apply()
+        for s in range(n_substeps):
+            if s % 5 == 0:
+                w.fetch(4)
+                tq = w.qpos.double() + torch.tensor(deltas[s // 5], device=dev)
+                tq[:, 7:] = torch.tensor(grip[s // 5], device=dev)
+                w.target_qpos[:] = tq.float()
+                w.apply(32)
+            w.step(1, 0)
+        w.fetch(BUF_ALL)
+        torch.cuda.synchronize()
+        return dict(qpos=w.qpos.double().cpu().numpy(), qvel=w.qvel.double().cpu().numpy(),
+                    body=w.body_view().double().cpu().numpy(), world=w)
+    raise ValueError(world_kind)
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor), elementwise"""
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def rel_err_vec(a, b, floor):
+    """max over vectors (last axis) of ||a-b|| / max(||b||, floor): error relative to the magnitude of the quantity
+    (a position, a unit quaternion, a joint vector), not to each component -- a 1e-7 absolute wobble of a quaternion
+    component that happens to be 1e-3 is float32 rounding, not a 1e-4 relative error of the pose."""
+    d = np.linalg.norm(a - b, axis=-1)
+    n = np.maximum(np.linalg.norm(b, axis=-1), floor)
+    return float(np.max(d / n))
