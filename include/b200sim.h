@@ -142,6 +142,7 @@ typedef struct B2SModel {
   /* ---- hulls ---- */
   const int32_t* hull_offset;  /* [n_hull+1] */
   const float* hull_verts;     /* [n_hull_verts*3] */
+  const float* hull_aabb;      /* [n_hull*6] local box (centre, half extents) of each hull, broadphase only */
   /* ---- broadphase candidates ---- */
   const int32_t* pair_a;
   const int32_t* pair_b;

@@ -1,0 +1,236 @@
+"""Robot agents + joint-space controllers -- host-side mirror of mani_skill/agents/base_agent.py:46,
+mani_skill/agents/controllers/pd_joint_pos.py (PDJointPosController / PDJointPosMimicController) and
+mani_skill/agents/robots/panda/panda.py (Panda).  Same action layout, bounds, scaling and mimic rule as the
+reference; the output of ``set_action`` is written straight into the backend's ``target_qpos`` buffer
+(articulation.py:873-896) and picked up by the fused substep kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import utils as U
+from .structs import Articulation, Pose
+
+
+class PDJointPosController:
+    """pd_joint_pos.py:15-101.  ``lower/upper`` None => joint limits, ``use_delta`` => target = qpos + action."""
+    sets_target_qpos = True
+    sets_target_qvel = False
+
+    def __init__(self, articulation: Articulation, joint_names: List[str], lower, upper, use_delta=False, use_target=False,
+                 normalize_action=True):
+        self.articulation = articulation
+        self.scene = articulation.scene
+        self.device = self.scene.device
+        self.joint_names = joint_names
+        self.active_joint_indices = torch.tensor([articulation.dof_names.index(n) for n in joint_names], dtype=torch.int64, device=self.device)
+        self.use_delta, self.use_target, self.normalize_action = use_delta, use_target, normalize_action
+        lim = articulation.qlimits[0, self.active_joint_indices].cpu().numpy().copy()
+        if lower is not None:
+            lim[:, 0] = lower
+        if upper is not None:
+            lim[:, 1] = upper
+        self._set_bounds(lim)
+        self._target_qpos = None
+        self._start_qpos = None
+
+    def _set_bounds(self, lim):
+        self.action_low = torch.tensor(lim[:, 0], dtype=torch.float32, device=self.device)
+        self.action_high = torch.tensor(lim[:, 1], dtype=torch.float32, device=self.device)
+        self.action_dim = lim.shape[0]
+
+    @property
+    def qpos(self):
+        return self.articulation.qpos[..., self.active_joint_indices]
+
+    def reset(self, env_idx=None):
+        q = self.qpos.clone()
+        if self._target_qpos is None or env_idx is None:
+            self._start_qpos, self._target_qpos = q.clone(), q.clone()
+        else:
+            self._start_qpos[env_idx] = q[env_idx]
+            self._target_qpos[env_idx] = q[env_idx]
+
+    def _preprocess_action(self, action):
+        if self.normalize_action:
+            action = U.clip_and_scale_action(action, self.action_low, self.action_high)
+        return action
+
+    def set_drive_targets(self, targets):
+        self.articulation.set_joint_drive_targets(targets, self.active_joint_indices)
+
+    def set_action(self, action):
+        action = self._preprocess_action(action)
+        self._start_qpos = self.qpos
+        if self.use_delta:
+            self._target_qpos = (self._target_qpos if self.use_target else self._start_qpos) + action
+        else:
+            self._target_qpos = torch.broadcast_to(action, self._start_qpos.shape).clone()
+        self.set_drive_targets(self._target_qpos)
+
+    def get_state(self):
+        return {"target_qpos": self._target_qpos} if self.use_target else {}
+
+
+class PDJointPosMimicController(PDJointPosController):
+    """pd_joint_pos.py:129-237: one action per control joint, mimic joints copy multiplier*q + offset."""
+
+    def __init__(self, articulation, joint_names, lower, upper, mimic: Dict[str, dict], **kw):
+        super().__init__(articulation, joint_names, lower, upper, **kw)
+        mimic_idx, ctrl_idx = [], []
+        for mimic_name, data in mimic.items():
+            mimic_idx.append(joint_names.index(mimic_name))
+            ctrl_idx.append(joint_names.index(data["joint"]))
+        self.mimic_joint_indices = torch.tensor(mimic_idx, dtype=torch.int64, device=self.device)
+        self.mimic_control_joint_indices = torch.tensor(ctrl_idx, dtype=torch.int64, device=self.device)
+        self.control_joint_indices = torch.unique(self.mimic_control_joint_indices)
+        self._multiplier = torch.tensor([d.get("multiplier", 1.0) for d in mimic.values()], dtype=torch.float32, device=self.device)
+        self._offset = torch.tensor([d.get("offset", 0.0) for d in mimic.values()], dtype=torch.float32, device=self.device)
+        lim = np.stack([self.action_low.cpu().numpy(), self.action_high.cpu().numpy()], 1)[self.control_joint_indices.cpu().numpy()]
+        self._set_bounds(lim)
+
+    def set_action(self, action):
+        action = self._preprocess_action(action)
+        self._start_qpos = self.qpos
+        self._target_qpos = self._target_qpos.clone()
+        if self.use_delta:
+            base = self._target_qpos if self.use_target else self._start_qpos
+            self._target_qpos[:, self.control_joint_indices] = base[:, self.control_joint_indices] + action
+        else:
+            self._target_qpos[:, self.control_joint_indices] = action
+        self._target_qpos[:, self.mimic_joint_indices] = (
+            self._target_qpos[:, self.mimic_control_joint_indices] * self._multiplier[None, :] + self._offset[None, :])
+        self.set_drive_targets(self._target_qpos)
+
+
+class CombinedController:
+    """base_controller.py:305-347 `DictController` with balanced action concatenation."""
+
+    def __init__(self, controllers: Dict[str, PDJointPosController]):
+        self.controllers = controllers
+        self.action_mapping = {}
+        d = 0
+        for k, c in controllers.items():
+            self.action_mapping[k] = (d, d + c.action_dim)
+            d += c.action_dim
+        self.action_dim = d
+
+    def reset(self, env_idx=None):
+        for c in self.controllers.values():
+            c.reset(env_idx)
+
+    def set_action(self, action):
+        for k, c in self.controllers.items():
+            a, b = self.action_mapping[k]
+            c.set_action(action[:, a:b])
+
+    def get_state(self):
+        out = {}
+        for k, c in self.controllers.items():
+            s = c.get_state()
+            if s:
+                out[k] = s
+        return out
+
+
+class Panda:
+    """mani_skill/agents/robots/panda/panda.py:16-269 (uid 'panda'; PandaWristCam = panda_v3 urdf)."""
+    uid = "panda"
+    arm_joint_names = [f"panda_joint{i}" for i in range(1, 8)]
+    gripper_joint_names = ["panda_finger_joint1", "panda_finger_joint2"]
+    ee_link_name = "panda_hand_tcp"
+    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_joint_target_delta_pos")
+
+    def __init__(self, scene, name="panda"):
+        self.scene = scene
+        self.device = scene.device
+        self.robot: Articulation = scene.articulations[name]
+        lm = self.robot.links_map
+        self.finger1_link = lm["panda_leftfinger"]
+        self.finger2_link = lm["panda_rightfinger"]
+        self.tcp = lm[self.ee_link_name]
+        self.controller = None
+        self.control_mode = None
+
+    def set_control_mode(self, control_mode: Optional[str] = None):
+        if control_mode is None:
+            control_mode = self.SUPPORTED_CONTROL_MODES[0]  # first key of the controller dict (panda.py:187-190)
+        if control_mode not in self.SUPPORTED_CONTROL_MODES:
+            raise NotImplementedError(f"control mode {control_mode} is not available in this build "
+                                      f"(supported: {self.SUPPORTED_CONTROL_MODES})")
+        self.control_mode = control_mode
+        gripper = PDJointPosMimicController(self.robot, self.gripper_joint_names, -0.01, 0.04,
+                                            mimic={"panda_finger_joint2": {"joint": "panda_finger_joint1"}})
+        if control_mode == "pd_joint_delta_pos":
+            arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
+        elif control_mode == "pd_joint_target_delta_pos":
+            arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True, use_target=True)
+        else:
+            arm = PDJointPosController(self.robot, self.arm_joint_names, None, None, normalize_action=False)
+        self.controller = CombinedController(dict(arm=arm, gripper=gripper))
+
+    def action_bounds(self):
+        lows, highs = [], []
+        for c in self.controller.controllers.values():
+            if c.normalize_action:
+                lows.append(-np.ones(c.action_dim, dtype=np.float32))
+                highs.append(np.ones(c.action_dim, dtype=np.float32))
+            else:
+                lows.append(c.action_low.cpu().numpy())
+                highs.append(c.action_high.cpu().numpy())
+        return np.concatenate(lows), np.concatenate(highs)
+
+    def reset(self, init_qpos=None):
+        """base_agent.py:300-320: zero velocity / force, optional qpos."""
+        if init_qpos is not None:
+            self.robot.set_qpos(init_qpos)
+        self.robot.set_qvel(torch.zeros(self.robot.dof, device=self.device))
+        self.robot.set_qf(torch.zeros(self.robot.dof, device=self.device))
+
+    def controller_reset(self, env_idx=None):
+        self.controller.reset(env_idx)
+        # the drive keeps holding the reset configuration until the first action (controller.reset -> targets = qpos)
+        full = self.robot.qpos.clone()
+        rows = self.robot._rows if env_idx is None else self.robot._rows[env_idx]
+        self.scene.world.target_qpos[rows, :self.robot.dof] = full if env_idx is None else full[env_idx]
+        self.scene._dirty |= self.scene.BUF_TARGET_QPOS
+        self.scene._gpu_apply_all()
+
+    def set_action(self, action):
+        self.controller.set_action(action)
+
+    def get_proprioception(self):
+        obs = dict(qpos=self.robot.get_qpos(), qvel=self.robot.get_qvel())
+        cs = self.controller.get_state()
+        if cs:
+            obs["controller"] = cs
+        return obs
+
+    def is_grasping(self, obj, min_force=0.5, max_angle=85):
+        """panda.py:237-265."""
+        l_f = self.scene.get_pairwise_contact_forces(self.finger1_link, obj)
+        r_f = self.scene.get_pairwise_contact_forces(self.finger2_link, obj)
+        lforce = torch.linalg.norm(l_f, axis=1)
+        rforce = torch.linalg.norm(r_f, axis=1)
+        ldirection = self.finger1_link.pose.to_transformation_matrix()[..., :3, 1]
+        rdirection = -self.finger2_link.pose.to_transformation_matrix()[..., :3, 1]
+        langle = U.compute_angle_between(ldirection, l_f)
+        rangle = U.compute_angle_between(rdirection, r_f)
+        lflag = torch.logical_and(lforce >= min_force, torch.rad2deg(langle) <= max_angle)
+        rflag = torch.logical_and(rforce >= min_force, torch.rad2deg(rangle) <= max_angle)
+        return torch.logical_and(lflag, rflag)
+
+    def is_static(self, threshold: float = 0.2):
+        qvel = self.robot.get_qvel()[..., :-2]
+        return torch.max(torch.abs(qvel), 1)[0] <= threshold
+
+    @property
+    def tcp_pose(self) -> Pose:
+        return self.tcp.pose
+
+    @property
+    def tcp_pos(self):
+        return self.tcp.pose.p

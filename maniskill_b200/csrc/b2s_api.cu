@@ -58,11 +58,11 @@ World* get(uint64_t h) {
   return it == g_worlds.end() ? nullptr : it->second;
 }
 
-template <class C>
+template <class C, int ND>
 __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState S, int substeps, unsigned fetch_mask) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
-  b2s::step_env<C>(M, S, env, substeps, fetch_mask);
+  b2s::step_env<C, ND>(M, S, env, substeps, fetch_mask);
 }
 
 template <class C>
@@ -174,8 +174,9 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->caps == 0) step_kernel<b2s::CapsS><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
-  else step_kernel<b2s::CapsL><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else step_kernel<b2s::CapsL, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
   CK(cudaGetLastError());
   return B2S_OK;
 }

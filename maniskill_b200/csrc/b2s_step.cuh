@@ -35,6 +35,7 @@ struct DevModel {
   const float *shape_pose, *shape_size, *shape_mu, *shape_bound, *shape_patch;
   const int* hull_offset;
   const float* hull_verts;
+  const float* hull_aabb;
   const int *pair_a, *pair_b;
   // per-env overrides, SoA [slot][n_envs]
   const float *ov_shape_size, *ov_shape_pose, *ov_shape_bound, *ov_fb_mass;
@@ -132,10 +133,12 @@ B2S_HDN void fk(const DevModel& M, Lane<C>& L) {
   }
 }
 
-template <class C>
+// ND > 0 fixes the dof count at compile time (loops over joints unroll, the velocity vectors live in registers);
+// ND == 0 reads it from the model.
+template <class C, int ND>
 B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   const int N = M.n_envs;
-  const int nd = M.n_dof;
+  const int nd = ND > 0 ? ND : M.n_dof;
   const float dt = M.dt;
   const v3 grav = mk3(M.gx, M.gy, M.gz);
   // ---------------------------------------------------------------- 1. FK + spatial quantities + drive
@@ -240,6 +243,28 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       v3 dd = bc[a] - bc[b];
       float rr = br[a] + br[b] + margin;
       if (dot(dd, dd) > rr * rr) continue;
+      // bounding sphere of one against the oriented box of the other (both ways): a table-sized box has a huge
+      // bounding sphere, this keeps GJK for the pairs that are really close.  Conservative => results unchanged.
+      bool cull = false;
+      for (int w = 0; w < 2 && !cull; w++) {
+        int sb = w == 0 ? b : a, ss = w == 0 ? a : b;
+        int tbx = M.shape_type[sb];
+        v3 cl = mk3(0, 0, 0), hl;
+        if (tbx == SH_BOX) hl = Ssize[sb];
+        else if (tbx == SH_SPHERE) hl = mk3(Ssize[sb].x, Ssize[sb].x, Ssize[sb].x);
+        else if (tbx == SH_CAPSULE) hl = mk3(Ssize[sb].x + Ssize[sb].y, Ssize[sb].x, Ssize[sb].x);
+        else {
+          const float* bx = M.hull_aabb + 6 * M.shape_hull[sb];
+          cl = mk3(bx[0], bx[1], bx[2]);
+          hl = mk3(bx[3], bx[4], bx[5]);
+        }
+        q4 qi = mkq(SX[sb].q.w, -SX[sb].q.x, -SX[sb].q.y, -SX[sb].q.z);
+        v3 pl = qrot(qi, bc[ss] - SX[sb].p) - cl;
+        v3 ex = mk3(fmaxf(fabsf(pl.x) - hl.x, 0.f), fmaxf(fabsf(pl.y) - hl.y, 0.f), fmaxf(fabsf(pl.z) - hl.z, 0.f));
+        float lim = br[ss] + margin;
+        if (dot(ex, ex) > lim * lim) cull = true;
+      }
+      if (cull) continue;
     }
     WShape WA, WB;
     WA.type = ta; WA.X = SX[a]; WA.R = qmat(SX[a].q); WA.size = Ssize[a]; WA.verts = nullptr; WA.nverts = 0;
@@ -772,12 +797,12 @@ B2S_HDN inline void apply_env(const DevModel& M, const DevState& St, int env, un
   }
 }
 
-template <class C>
+template <class C, int ND>
 B2S_HDN void step_env(const DevModel& M, const DevState& St, int env, int substeps, unsigned fetch_mask) {
   Lane<C> L;
   load_lane<C>(M, St, env, L);
   int ovf = 0;
-  for (int s = 0; s < substeps; s++) substep<C>(M, L, env, &ovf);
+  for (int s = 0; s < substeps; s++) substep<C, ND>(M, L, env, &ovf);
   if (ovf) *St.overflow = 1;
   store_lane<C>(M, St, env, L);
   if (fetch_mask) {

@@ -79,6 +79,7 @@ struct WorldT {
     M.shape_mu = up(m.shape_mu, m.n_shape); M.shape_bound = up(m.shape_bound, m.n_shape * 4);
     M.shape_patch = up(m.shape_patch, m.n_shape);
     M.hull_offset = up(m.hull_offset, m.n_hull + 1); M.hull_verts = up(m.hull_verts, (size_t)m.n_hull_verts * 3);
+    M.hull_aabb = up(m.hull_aabb, (size_t)m.n_hull * 6);
     M.pair_a = up(m.pair_a, m.n_pair); M.pair_b = up(m.pair_b, m.n_pair);
     M.ov_shape_size = up_soa(m.ov_shape_size, (size_t)m.n_ov_shape * 3, N);
     M.ov_shape_pose = up_soa(m.ov_shape_pose, (size_t)m.n_ov_shape * 7, N);

@@ -1,0 +1,5 @@
+from ..registration import register_env
+from .base_env import BaseEnv
+from .pick_cube import PickCubeEnv
+
+register_env("PickCube-v1", max_episode_steps=50)(PickCubeEnv)

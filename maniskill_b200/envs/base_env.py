@@ -1,0 +1,384 @@
+"""BaseEnv -- host-side mirror of mani_skill/envs/sapien_env.py:45 (``BaseEnv``) and mani_skill/envs/scene.py:40
+(``ManiSkillScene``) for the hot path: same public method names, argument meaning and return structure
+(``reset(seed, options) -> (obs, info)``, ``step(action) -> (obs, reward, terminated, truncated, info)``), same
+seeding scheme (main RNG 2022+i, per-episode RNG, ``torch.random.fork_rng`` + ``manual_seed(episode_seed[0])``,
+sapien_env.py:321,857-1021), same partial-reset semantics through ``scene._reset_mask`` and the same 5-substep
+control loop (sapien_env.py:1073-1132) -- executed by ONE fused kernel launch instead of 5 ``px.step()`` calls.
+
+The backend is ``maniskill_b200.backend.World`` (CUDA, no CPU path).  Tests may inject another object with the same
+interface through ``world_factory`` (tests/ only).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .. import utils as U
+from ..backend import (BUF_ALL, BUF_APPLY_ALL, BUF_QF, BUF_QPOS, BUF_QVEL, BUF_RIGID, BUF_ROOT_POSE, BUF_TARGET_QPOS,
+                       BUF_TARGET_QVEL)
+from ..model import CompiledModel, SceneDesc, SimParams
+from ..structs import Actor, Articulation, Pose
+
+
+class Scene:
+    """What ``env.scene`` is in the reference (ManiSkillScene): owns the physics world + named actors/articulations."""
+    BUF_RIGID, BUF_ROOT_POSE, BUF_QPOS, BUF_QVEL, BUF_QF, BUF_TARGET_QPOS, BUF_TARGET_QVEL = (
+        BUF_RIGID, BUF_ROOT_POSE, BUF_QPOS, BUF_QVEL, BUF_QF, BUF_TARGET_QPOS, BUF_TARGET_QVEL)
+
+    def __init__(self, world, cm: CompiledModel, desc: SceneDesc):
+        self.world = world
+        self.px = world
+        self.cm = cm
+        self.num_envs = world.n_envs
+        self.device = world.device
+        self.timestep = cm.scalars["dt"]
+        self._reset_mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self._dirty = 0
+        self.actors: Dict[str, Actor] = {}
+        self.articulations: Dict[str, Articulation] = {}
+        n_link = cm.scalars["n_link"]
+        for act in desc.actors:
+            if act.body_type == "static":
+                continue
+            a = Actor(self, act.name, cm.actor_rows[act.name], act.body_type, cm.actor_fb[act.name],
+                      Pose.create(act.initial_pose, self.device))
+            a.hidden = act.hidden
+            self.actors[act.name] = a
+        for art in desc.articulations:
+            ai = cm.art_index[art.name]
+            d0, d1 = cm.art_dof_start[ai], cm.art_dof_start[ai + 1]
+            qlim = cm.arrays["dof_limit"].reshape(-1, 2)[d0:d1]
+            self.articulations[art.name] = Articulation(self, art.name, ai, cm.link_rows[art.name], cm.dof_names[art.name], qlim)
+        self._query_cache = {}
+
+    # ---- mani_skill/envs/scene.py:379-380
+    def step(self, substeps=1, fetch_mask=0):
+        self.world.step(substeps, fetch_mask)
+
+    # ---- mani_skill/envs/scene.py:950-986
+    def _gpu_apply_all(self):
+        if self._dirty:
+            self.world.apply(self._dirty)
+            self._dirty = 0
+
+    def _gpu_fetch_all(self):
+        self.world.fetch(BUF_ALL)
+
+    # ---- mani_skill/envs/scene.py:741-801
+    def get_pairwise_contact_impulses(self, obj1, obj2):
+        key = (obj1.row, obj2.row)
+        if key not in self._query_cache:
+            self._query_cache[key] = self.world.create_contact_query([key])
+        return self.world.query_contact_impulses(self._query_cache[key])[:, 0]
+
+    def get_pairwise_contact_forces(self, obj1, obj2):
+        return self.get_pairwise_contact_impulses(obj1, obj2) / self.timestep
+
+    def get_sim_state(self):
+        state = {"actors": {}, "articulations": {}}
+        for k, a in self.actors.items():
+            if a.px_body_type == "static":
+                continue
+            state["actors"][k] = a.get_state()
+        for k, a in self.articulations.items():
+            state["articulations"][k] = a.get_state()
+        return state
+
+    def set_sim_state(self, state, env_idx=None):
+        for k, s in state["actors"].items():
+            self.actors[k].set_state(s, env_idx)
+        for k, s in state["articulations"].items():
+            self.articulations[k].set_state(s, env_idx)
+
+
+class BaseEnv:
+    """Mirror of mani_skill.envs.sapien_env.BaseEnv for GPU simulation (num_envs >= 1, sim_backend physx_cuda)."""
+
+    SUPPORTED_OBS_MODES = ("none", "state", "state_dict", "rgb", "depth", "segmentation", "rgbd", "rgb+depth",
+                           "rgb+depth+segmentation", "state+rgb+depth", "sensor_data")
+    SUPPORTED_REWARD_MODES = ("normalized_dense", "dense", "sparse", "none")
+    max_episode_steps: Optional[int] = None
+
+    def __init__(self, num_envs: int = 1, obs_mode: Optional[str] = None, reward_mode: Optional[str] = None,
+                 control_mode: Optional[str] = None, sim_config: Optional[dict] = None, device: Union[str, torch.device, None] = None,
+                 world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None):
+        self.num_envs = num_envs
+        self._obs_mode = "state" if obs_mode is None else obs_mode
+        if self._obs_mode not in self.SUPPORTED_OBS_MODES:
+            raise NotImplementedError(f"Unsupported obs mode: {self._obs_mode}. Must be one of {self.SUPPORTED_OBS_MODES}")
+        self._reward_mode = "normalized_dense" if reward_mode is None else reward_mode
+        if self._reward_mode not in self.SUPPORTED_REWARD_MODES:
+            raise NotImplementedError(f"Unsupported reward mode: {self._reward_mode}")
+        self.sim_params = SimParams(**(sim_config or {}))
+        self._sim_freq, self._control_freq = self.sim_params.sim_freq, self.sim_params.control_freq
+        if self._sim_freq % self._control_freq != 0:
+            raise ValueError("sim_freq must be divisible by control_freq")  # sapien_env.py:279-283 warns; we are strict
+        self._sim_steps_per_control = self._sim_freq // self._control_freq
+        self._world_factory = world_factory
+        self._requested_device = device
+        self._main_seed = None
+        self._episode_seed = np.zeros(num_envs, dtype=np.int64)
+        self._batched_main_rng = None
+        self._batched_episode_rng = None
+        self._episode_rng = None
+        self._enhanced_determinism = False
+        self._sensor_overrides = sensor_configs or {}
+        self._visual = any(k in self._obs_mode for k in ("rgb", "depth", "segmentation", "sensor_data"))
+        if enable_cameras is not None:
+            self._visual = self._visual or enable_cameras
+        # ---- build the scene (sapien_env.py:725-770 `_reconfigure`)
+        self.scene_desc = SceneDesc(num_envs, self.sim_params)
+        self._load_agent_desc()
+        self._load_scene_desc()
+        self.cm = self.scene_desc.compile()
+        if world_factory is None:
+            from ..backend import World
+            world = World(self.cm, device)
+        else:
+            world = world_factory(self.cm)
+        self.scene = Scene(world, self.cm, self.scene_desc)
+        self.device = self.scene.device
+        self._elapsed_steps = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
+        self._hidden_objects = []
+        self._after_build()
+        self.agent.set_control_mode(control_mode)
+        self.single_action_space_low, self.single_action_space_high = self.agent.action_bounds()
+        self.action_dim = self.single_action_space_low.shape[0]
+        self._sensors = self._setup_sensors() if self._visual else {}
+        self._last_obs = None
+        # sapien_env.py:321-327: main RNG seeds 2022+i, first reset
+        self._set_main_rng([2022 + i for i in range(num_envs)])
+        self._elapsed_steps[:] = 0
+        self.reset(seed=[2022 + i for i in range(num_envs)])
+
+    # ------------------------------------------------------------------ task hooks (same names as the reference)
+    def _load_agent_desc(self):
+        raise NotImplementedError
+
+    def _load_scene_desc(self):
+        raise NotImplementedError
+
+    def _after_build(self):
+        raise NotImplementedError
+
+    def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
+        pass
+
+    def evaluate(self) -> dict:
+        return {}
+
+    def _get_obs_extra(self, info: dict) -> dict:
+        return {}
+
+    def compute_dense_reward(self, obs, action, info):
+        raise NotImplementedError
+
+    def compute_normalized_dense_reward(self, obs, action, info):
+        raise NotImplementedError
+
+    def compute_sparse_reward(self, obs, action, info):
+        if "success" in info:
+            if "fail" in info:
+                return info["success"].float() - info["fail"].float()
+            return info["success"].float()
+        return torch.zeros(self.num_envs, device=self.device)
+
+    def _setup_sensors(self):
+        return {}
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def obs_mode(self):
+        return self._obs_mode
+
+    @property
+    def elapsed_steps(self):
+        return self._elapsed_steps
+
+    @property
+    def control_freq(self):
+        return self._control_freq
+
+    @property
+    def sim_freq(self):
+        return self._sim_freq
+
+    @property
+    def gpu_sim_enabled(self):
+        return True
+
+    # ------------------------------------------------------------------ RNG (sapien_env.py:980-1021)
+    def _set_main_rng(self, seed):
+        if seed is None:
+            if self._main_seed is not None:
+                return
+            seed = np.random.RandomState().randint(2**31, size=(self.num_envs,))
+        if not np.iterable(seed):
+            seed = [seed]
+        self._main_seed = list(seed)
+        self._main_rng = np.random.RandomState(self._main_seed[0])
+        if len(self._main_seed) == 1 and self.num_envs > 1:
+            self._main_seed = self._main_seed + np.random.RandomState(self._main_seed[0]).randint(2**31, size=(self.num_envs - 1,)).tolist()
+        self._batched_main_rng = U.BatchedRNG.from_seeds(self._main_seed)
+
+    def _set_episode_rng(self, seed, env_idx):
+        if seed is not None or self._enhanced_determinism:
+            env_idx_np = env_idx.cpu().numpy() if isinstance(env_idx, torch.Tensor) else np.asarray(env_idx)
+            if seed is None:
+                self._episode_seed[env_idx_np] = self._batched_main_rng[env_idx_np].randint(2**31)
+            else:
+                if not np.iterable(seed):
+                    seed = [seed]
+                self._episode_seed = np.asarray(seed, dtype=np.int64)
+                if len(self._episode_seed) == 1 and self.num_envs > 1:
+                    self._episode_seed = np.concatenate((self._episode_seed, np.random.RandomState(self._episode_seed[0]).randint(2**31, size=(self.num_envs - 1,))))
+            if seed is not None or self._batched_episode_rng is None:
+                self._batched_episode_rng = U.BatchedRNG.from_seeds(self._episode_seed)
+            else:
+                self._batched_episode_rng[env_idx_np] = U.BatchedRNG.from_seeds(self._episode_seed[env_idx_np])
+            self._episode_rng = self._batched_episode_rng[0]
+
+    # ------------------------------------------------------------------ reset (sapien_env.py:857-978)
+    def reset(self, seed: Union[None, int, Sequence[int]] = None, options: Optional[dict] = None):
+        options = dict() if options is None else options
+        if "env_idx" in options:
+            env_idx = U.to_tensor(options["env_idx"], self.device, dtype=torch.int64).long()
+        else:
+            env_idx = torch.arange(0, self.num_envs, device=self.device)
+        self._set_main_rng(seed)
+        self._set_episode_rng(seed, env_idx)
+        self.scene._reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self.scene._reset_mask[env_idx] = True
+        self._elapsed_steps[env_idx] = 0
+        self._clear_sim_state()
+        self.agent.reset()
+        if "reset_to_env_states" in options:
+            self.set_state_dict(options["reset_to_env_states"]["env_states"], env_idx)
+        else:
+            if seed is not None or self._enhanced_determinism:
+                with torch.random.fork_rng(devices=[self.device] if self.device.type == "cuda" else []):
+                    torch.manual_seed(int(self._episode_seed[0]))
+                    self._initialize_episode(env_idx, options)
+            else:
+                self._initialize_episode(env_idx, options)
+        self.scene._reset_mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        # sapien_env.py:956-960: apply everything, refresh link poses, fetch
+        self.scene._gpu_apply_all()
+        self.scene._gpu_fetch_all()
+        self.agent.controller_reset(env_idx)
+        info = self.get_info()
+        obs = self.get_obs(info)
+        info["reconfigure"] = False
+        self._last_obs = obs
+        return obs, info
+
+    def _clear_sim_state(self):
+        """sapien_env.py:1023-1036: zero the velocities of the sub-scenes being reset."""
+        for actor in self.scene.actors.values():
+            if actor.px_body_type == "dynamic":
+                actor.set_linear_velocity(torch.zeros(3, device=self.device))
+                actor.set_angular_velocity(torch.zeros(3, device=self.device))
+        for art in self.scene.articulations.values():
+            art.set_qvel(torch.zeros(art.dof, device=self.device))
+        self.scene._gpu_apply_all()
+
+    # ------------------------------------------------------------------ step (sapien_env.py:1042-1132)
+    def step(self, action):
+        action = self._step_action(action)
+        self._elapsed_steps += 1
+        info = self.get_info()
+        obs = self.get_obs(info)
+        reward = self.get_reward(obs=obs, action=action, info=info)
+        if "success" in info:
+            terminated = torch.logical_or(info["success"], info["fail"]) if "fail" in info else info["success"].clone()
+        else:
+            terminated = info["fail"].clone() if "fail" in info else torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        self._last_obs = obs
+        return obs, reward, terminated, torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+
+    def _step_action(self, action):
+        if action is not None:
+            if isinstance(action, np.ndarray):
+                action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+            elif isinstance(action, torch.Tensor):
+                action = action.to(self.device)
+            else:
+                raise TypeError(type(action))
+            if action.shape == (self.action_dim,):
+                action = action[None]
+            self.agent.set_action(action)
+            self.scene._gpu_apply_all()  # px.gpu_apply_articulation_target_position (sapien_env.py:1118-1121)
+        self._before_control_step()
+        # `for _ in range(self._sim_steps_per_control): scene.step()` + `_gpu_fetch_all()` as one fused launch
+        self.scene.step(self._sim_steps_per_control, BUF_ALL)
+        self._after_control_step()
+        return action
+
+    def _before_control_step(self):
+        pass
+
+    def _after_control_step(self):
+        pass
+
+    # ------------------------------------------------------------------ obs / info / reward (sapien_env.py:501-700)
+    def get_info(self):
+        info = dict(elapsed_steps=self._elapsed_steps.clone())
+        info.update(self.evaluate())
+        return info
+
+    def _get_obs_agent(self):
+        return self.agent.get_proprioception()
+
+    def _get_obs_state_dict(self, info):
+        return dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
+
+    def get_obs(self, info=None):
+        if info is None:
+            info = self.get_info()
+        if self._obs_mode == "none":
+            return dict()
+        if self._obs_mode == "state":
+            return U.flatten_state_dict(self._get_obs_state_dict(info))
+        if self._obs_mode == "state_dict":
+            return self._get_obs_state_dict(info)
+        # visual modes (sapien_env.py:535-625): agent + extra (+ state when requested) + sensor data / params
+        obs = dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
+        if self._obs_mode.startswith("state+"):
+            obs["state"] = U.flatten_state_dict(self._get_obs_state_dict(info))
+        obs["sensor_param"] = self.get_sensor_params()
+        obs["sensor_data"] = self._get_obs_sensor_data()
+        return obs
+
+    def _get_obs_sensor_data(self):
+        raise NotImplementedError("this task has no sensors")
+
+    def get_sensor_params(self):
+        return {}
+
+    def get_reward(self, obs, action, info):
+        if self._reward_mode == "sparse":
+            return self.compute_sparse_reward(obs, action, info)
+        if self._reward_mode == "dense":
+            return self.compute_dense_reward(obs, action, info)
+        if self._reward_mode == "normalized_dense":
+            return self.compute_normalized_dense_reward(obs, action, info)
+        return torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ state (sapien_env.py:1272-1325)
+    def get_state_dict(self):
+        return self.scene.get_sim_state()
+
+    def set_state_dict(self, state, env_idx=None):
+        self.scene.set_sim_state(state, env_idx)
+        self.scene._gpu_apply_all()
+        self.scene._gpu_fetch_all()
+
+    def get_state(self):
+        return U.flatten_state_dict(self.get_state_dict())
+
+    def close(self):
+        w = getattr(self.scene, "world", None)
+        if w is not None and hasattr(w, "close"):
+            w.close()

@@ -1,0 +1,116 @@
+"""PickCube-v1 -- mirror of mani_skill/envs/tasks/tabletop/pick_cube.py:33-191 on the b200sim backend.
+
+Scene, randomisation (same torch.rand call order under the same seed), observation layout (42-dim state), success
+test and dense reward are restated line by line from the reference task; the scene prototype comes from
+maniskill_b200/scenes.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import utils as U
+from ..agents import Panda
+from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..model import SHAPE_BOX, SHAPE_SPHERE, ActorRec, ShapeRec, pose7
+from ..structs import Pose
+from .base_env import BaseEnv
+
+
+class PickCubeEnv(BaseEnv):
+    max_episode_steps = 50  # @register_env("PickCube-v1", max_episode_steps=50)
+    goal_thresh = 0.025
+    cube_half_size = 0.02
+    cube_spawn_half_size = 0.1
+    cube_spawn_center = (0, 0)
+    max_goal_height = 0.3
+    sensor_cam_eye_pos = [0.3, 0, 0.6]
+    sensor_cam_target_pos = [-0.1, 0, 0.1]
+
+    def __init__(self, *args, robot_uids="panda", robot_init_qpos_noise=0.02, **kwargs):
+        if robot_uids != "panda":
+            raise NotImplementedError("PickCube-v1 on b200sim ships the default 'panda' robot")
+        self.robot_uids = robot_uids
+        self.robot_init_qpos_noise = robot_init_qpos_noise
+        super().__init__(*args, **kwargs)
+
+    # ---- pick_cube.py:79-104
+    def _load_agent_desc(self):
+        self.scene_desc.add_articulation(panda_articulation("panda", "panda_v2", (-0.615, 0, 0)))
+
+    def _load_scene_desc(self):
+        add_table_scene(self.scene_desc)
+        self.scene_desc.add_actor(ActorRec("cube", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([self.cube_half_size] * 3), color=(1, 0, 0, 1))],
+                                           pose7([0, 0, self.cube_half_size])))
+        self.scene_desc.add_actor(ActorRec("goal_site", "kinematic",
+                                           [ShapeRec(SHAPE_SPHERE, pose7(), np.array([self.goal_thresh, 0, 0]), color=(0, 1, 0, 1), collide=False)],
+                                           pose7(), hidden=True))
+
+    def _after_build(self):
+        self.agent = Panda(self.scene, "panda")
+        self.table = self.scene.actors["table-workspace"]
+        self.cube = self.scene.actors["cube"]
+        self.goal_site = self.scene.actors["goal_site"]
+        self._hidden_objects.append(self.goal_site)
+
+    # ---- pick_cube.py:66-71
+    def _sensor_configs(self):
+        return [dict(uid="base_camera", pose=U.look_at(self.sensor_cam_eye_pos, self.sensor_cam_target_pos), width=128, height=128,
+                     fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
+
+    # ---- table/scene_builder.py:68-103 + pick_cube.py:106-130
+    def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
+        b = len(env_idx)
+        dev = self.device
+        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
+        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
+        qpos[:, -2:] = 0.04
+        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
+        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        xyz = torch.zeros((b, 3), device=dev)
+        xyz[:, :2] = torch.rand((b, 2), device=dev) * self.cube_spawn_half_size * 2 - self.cube_spawn_half_size
+        xyz[:, 0] += self.cube_spawn_center[0]
+        xyz[:, 1] += self.cube_spawn_center[1]
+        xyz[:, 2] = self.cube_half_size
+        qs = U.random_quaternions(b, device=dev, lock_x=True, lock_y=True)
+        self.cube.set_pose(Pose.create_from_pq(xyz, qs))
+        goal_xyz = torch.zeros((b, 3), device=dev)
+        goal_xyz[:, :2] = torch.rand((b, 2), device=dev) * self.cube_spawn_half_size * 2 - self.cube_spawn_half_size
+        goal_xyz[:, 0] += self.cube_spawn_center[0]
+        goal_xyz[:, 1] += self.cube_spawn_center[1]
+        goal_xyz[:, 2] = torch.rand((b,), device=dev) * self.max_goal_height + xyz[:, 2]
+        self.goal_site.set_pose(Pose.create_from_pq(goal_xyz, device=dev))
+
+    # ---- pick_cube.py:132-145
+    def _get_obs_extra(self, info: dict):
+        obs = dict(is_grasped=info["is_grasped"], tcp_pose=self.agent.tcp_pose.raw_pose, goal_pos=self.goal_site.pose.p)
+        if "state" in self.obs_mode:
+            obs.update(obj_pose=self.cube.pose.raw_pose, tcp_to_obj_pos=self.cube.pose.p - self.agent.tcp_pose.p,
+                       obj_to_goal_pos=self.goal_site.pose.p - self.cube.pose.p)
+        return obs
+
+    # ---- pick_cube.py:147-159
+    def evaluate(self):
+        is_obj_placed = torch.linalg.norm(self.goal_site.pose.p - self.cube.pose.p, axis=1) <= self.goal_thresh
+        is_grasped = self.agent.is_grasping(self.cube)
+        is_robot_static = self.agent.is_static(0.2)
+        return {"success": is_obj_placed & is_robot_static, "is_obj_placed": is_obj_placed,
+                "is_robot_static": is_robot_static, "is_grasped": is_grasped}
+
+    # ---- pick_cube.py:161-191
+    def compute_dense_reward(self, obs, action, info):
+        tcp_to_obj_dist = torch.linalg.norm(self.cube.pose.p - self.agent.tcp_pose.p, axis=1)
+        reward = 1 - torch.tanh(5 * tcp_to_obj_dist)
+        is_grasped = info["is_grasped"]
+        reward = reward + is_grasped
+        obj_to_goal_dist = torch.linalg.norm(self.goal_site.pose.p - self.cube.pose.p, axis=1)
+        place_reward = 1 - torch.tanh(5 * obj_to_goal_dist)
+        reward = reward + place_reward * is_grasped
+        qvel = self.agent.robot.get_qvel()[..., :-2]
+        static_reward = 1 - torch.tanh(5 * torch.linalg.norm(qvel, axis=1))
+        reward = reward + static_reward * info["is_obj_placed"]
+        reward[info["success"]] = 5
+        return reward
+
+    def compute_normalized_dense_reward(self, obs, action, info):
+        return self.compute_dense_reward(obs=obs, action=action, info=info) / 5

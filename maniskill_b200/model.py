@@ -256,7 +256,7 @@ class B2SModelStruct(C.Structure):
         ("fb_init_pose", _F), ("fb_ov", _I),
         ("shape_type", _I), ("shape_owner_kind", _I), ("shape_owner", _I), ("shape_row", _I), ("shape_pose", _F),
         ("shape_size", _F), ("shape_hull", _I), ("shape_mu", _F), ("shape_bound", _F), ("shape_ov", _I), ("shape_patch", _F),
-        ("hull_offset", _I), ("hull_verts", _F),
+        ("hull_offset", _I), ("hull_verts", _F), ("hull_aabb", _F),
         ("pair_a", _I), ("pair_b", _I),
         ("ov_shape_size", _F), ("ov_shape_pose", _F), ("ov_shape_bound", _F), ("ov_fb_mass", _F),
     ]
@@ -505,7 +505,7 @@ class SceneDesc:
                 shapes.append(dict(rec=s, owner_kind=OWNER_BODY, owner=b, row=n_link + b, art=-1, link=-1, seg=seg, hidden=act.hidden))
         n_fb = len(fb_type)
         # ---- shapes -> tables (collision shapes only); visuals recorded for the renderer
-        hull_offset, hull_verts = [0], []
+        hull_offset, hull_verts, hull_aabb = [0], [], []
         st, sok, so, srow, spose, ssize, shull, smu, sbound, sov, spatch = [], [], [], [], [], [], [], [], [], [], []
         ov_size, ov_pose, ov_bound = [], [], []
         col_meta = []
@@ -516,6 +516,8 @@ class SceneDesc:
                 hull_id = len(hull_offset) - 1
                 hull_verts.extend(np.asarray(rec.vertices, dtype=np.float32).tolist())
                 hull_offset.append(len(hull_verts))
+                hv_ = np.asarray(rec.vertices, dtype=np.float64)
+                hull_aabb.append(np.concatenate([(hv_.max(0) + hv_.min(0)) / 2, (hv_.max(0) - hv_.min(0)) / 2]))
                 cm.hull_tris.append(np.asarray(rec.triangles, dtype=np.int32))
             if rec.visual:
                 cm.visuals.append(dict(type=rec.type, row=sh["row"], pose=rec.pose, size=rec.size, hull=hull_id,
@@ -604,7 +606,7 @@ class SceneDesc:
         A["shape_type"] = i32(st); A["shape_owner_kind"] = i32(sok); A["shape_owner"] = i32(so); A["shape_row"] = i32(srow)
         A["shape_pose"] = f32(spose).reshape(-1); A["shape_size"] = f32(ssize).reshape(-1); A["shape_hull"] = i32(shull)
         A["shape_mu"] = f32(smu); A["shape_bound"] = f32(sbound).reshape(-1); A["shape_ov"] = i32(sov); A["shape_patch"] = f32(spatch)
-        A["hull_offset"] = i32(hull_offset); A["hull_verts"] = f32(hull_verts).reshape(-1)
+        A["hull_offset"] = i32(hull_offset); A["hull_verts"] = f32(hull_verts).reshape(-1); A["hull_aabb"] = f32(hull_aabb).reshape(-1)
         A["pair_a"] = i32(pair_a); A["pair_b"] = i32(pair_b)
         A["ov_shape_size"] = f32(np.stack(ov_size, 1) if ov_size else np.zeros(0)).reshape(-1)
         A["ov_shape_pose"] = f32(np.stack(ov_pose, 1) if ov_pose else np.zeros(0)).reshape(-1)

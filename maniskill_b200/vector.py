@@ -1,0 +1,54 @@
+"""ManiSkillVectorEnv -- mirror of mani_skill/vector/wrappers/gymnasium.py:18-199 together with the TimeLimit
+truncation the registry adds (mani_skill/utils/registration.py:127-170): auto-reset of finished sub-scenes via the
+partial reset ``reset(options={"env_idx": ...})``, ``final_info`` / ``final_observation`` bookkeeping."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class ManiSkillVectorEnv:
+    def __init__(self, env, auto_reset: bool = True, ignore_terminations: bool = False, max_episode_steps: Optional[int] = None):
+        self._env = env
+        self.num_envs = env.num_envs
+        self.auto_reset = auto_reset
+        self.ignore_terminations = ignore_terminations
+        self.max_episode_steps = max_episode_steps if max_episode_steps is not None else env.max_episode_steps
+        self.device = env.device
+
+    @property
+    def base_env(self):
+        return self._env
+
+    @property
+    def unwrapped(self):
+        return self._env
+
+    def reset(self, *, seed=None, options=None):
+        return self._env.reset(seed=seed, options=dict() if options is None else options)
+
+    def step(self, actions):
+        obs, rew, terminations, truncations, infos = self._env.step(actions)
+        if self.max_episode_steps is not None:
+            # TimeLimitWrapper.step (registration.py:160-168)
+            truncations = self._env.elapsed_steps >= self.max_episode_steps
+        else:
+            truncations = torch.zeros_like(terminations)
+        if self.ignore_terminations:
+            terminations = torch.zeros_like(terminations)
+        dones = torch.logical_or(terminations, truncations)
+        if dones.any() and self.auto_reset:
+            final_obs = obs if isinstance(obs, dict) else obs.clone()
+            env_idx = torch.arange(0, self.num_envs, device=self.device)[dones]
+            final_info = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in infos.items()}
+            obs, infos = self.reset(options=dict(env_idx=env_idx))
+            infos["final_info"] = final_info
+            infos["_final_info"] = dones
+            infos["final_observation"] = final_obs
+            infos["_final_observation"] = dones
+            infos["_elapsed_steps"] = dones
+        return obs, rew, terminations, truncations, infos
+
+    def close(self):
+        self._env.close()

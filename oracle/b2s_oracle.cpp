@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../include/b200sim.h"
@@ -84,7 +85,7 @@ enum { ROW_CONTACT_N = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_EQ = 3 };
 
 struct Row {
   int type;
-  std::vector<R> J, B;  // articulation part over the env's dof vector
+  R J[32], B[32];       // articulation part over the env's dof vector (n_dof <= 32)
   bool has_art;
   int fb[2];            // free body per side or -1
   V3 lin[2], ang[2];    // jacobian of each free-body side (already signed)
@@ -127,7 +128,7 @@ struct Oracle {
   std::vector<uint32_t> dof_anc_mask;
   std::vector<float> dof_T0, dof_axis, dof_mass, dof_com, dof_inertia, dof_gravity, dof_limit, dof_drive, dof_passive,
       link_offset, art_root_pose, eq_param, fb_mass, fb_com, fb_inertia, fb_damping, fb_gravity, fb_init_pose, shape_pose,
-      shape_size, shape_mu, shape_bound, hull_verts, shape_patch;
+      shape_size, shape_mu, shape_bound, hull_verts, shape_patch, hull_aabb;
   std::vector<Env> envs;
   int overflow;
 };
@@ -390,10 +391,11 @@ static void step_env(Oracle& O, Env& E) {
   }
   // ------------------------------------------------------------ 4. rows
   std::vector<Row> rows;
+  rows.reserve(96);
   auto finish_row = [&](Row& r) {
     R d = 0;
     if (r.has_art) {
-      r.B.assign(nd, 0);
+      for (int i = 0; i < nd; i++) r.B[i] = 0;
       for (int i = 0; i < nd; i++) {
         R s = 0;
         for (int j = 0; j < nd; j++) s += Minv[i * nd + j] * r.J[j];
@@ -432,7 +434,7 @@ static void step_env(Oracle& O, Env& E) {
     int a = O.eq_dof[2 * e], b = O.eq_dof[2 * e + 1];
     R mult = O.eq_param[4 * e], off = O.eq_param[4 * e + 1], k = O.eq_param[4 * e + 2];
     r.has_art = true;
-    r.J.assign(nd, 0);
+    for (int j = 0; j < nd; j++) r.J[j] = 0;
     r.J[b] = 1;
     r.J[a] = -mult;
     r.s0 = E.q[b] - mult * E.q[a] - off;
@@ -446,7 +448,7 @@ static void step_env(Oracle& O, Env& E) {
     if (lo > R(-1e29) && E.q[i] - lo < limit_margin) {
       Row r = blank_row(ROW_LIMIT);
       r.has_art = true;
-      r.J.assign(nd, 0);
+      for (int j = 0; j < nd; j++) r.J[j] = 0;
       r.J[i] = 1;
       r.s0 = E.q[i] - lo;
       finish_row(r);
@@ -455,7 +457,7 @@ static void step_env(Oracle& O, Env& E) {
     if (hi < R(1e29) && hi - E.q[i] < limit_margin) {
       Row r = blank_row(ROW_LIMIT);
       r.has_art = true;
-      r.J.assign(nd, 0);
+      for (int j = 0; j < nd; j++) r.J[j] = 0;
       r.J[i] = -1;
       r.s0 = hi - E.q[i];
       finish_row(r);
@@ -467,7 +469,7 @@ static void step_env(Oracle& O, Env& E) {
   auto contact_row = [&](int type, int sa, int sb, V3 pt, V3 dir, bool angular_only) {
     Row r = blank_row(type);
     r.dir = dir;
-    r.J.assign(nd, 0);
+    for (int j = 0; j < nd; j++) r.J[j] = 0;
     int sh[2] = {sa, sb};
     for (int sde = 0; sde < 2; sde++) {
       R sg = sde == 0 ? R(1) : R(-1);
@@ -667,7 +669,7 @@ void* b2o_create(const B2SModel* mp) {
   cp(O->shape_pose, m.shape_pose, m.n_shape * 7); cp(O->shape_size, m.shape_size, m.n_shape * 3);
   cp(O->shape_hull, m.shape_hull, m.n_shape); cp(O->shape_mu, m.shape_mu, m.n_shape); cp(O->shape_bound, m.shape_bound, m.n_shape * 4);
   cp(O->shape_ov, m.shape_ov, m.n_shape); cp(O->shape_patch, m.shape_patch, m.n_shape);
-  cp(O->hull_offset, m.hull_offset, m.n_hull + 1); cp(O->hull_verts, m.hull_verts, m.n_hull_verts * 3);
+  cp(O->hull_offset, m.hull_offset, m.n_hull + 1); cp(O->hull_verts, m.hull_verts, m.n_hull_verts * 3); cp(O->hull_aabb, m.hull_aabb, m.n_hull * 6);
   cp(O->pair_a, m.pair_a, m.n_pair); cp(O->pair_b, m.pair_b, m.n_pair);
   O->envs.resize(m.n_envs);
   for (int e = 0; e < m.n_envs; e++) {
@@ -782,6 +784,19 @@ void b2o_step_range(void* h, int substeps, int env_begin, int env_end) {
   Oracle* O = (Oracle*)h;
   for (int s = 0; s < substeps; s++)
     for (int e = env_begin; e < env_end; e++) step_env(*O, O->envs[e]);
+}
+
+// all envs, `nthreads` std::threads each owning a contiguous slice (CPU baseline timing)
+void b2o_step_mt(void* h, int substeps, int nthreads) {
+  Oracle* O = (Oracle*)h;
+  int n = O->m.n_envs;
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    int lo = (int)((long long)n * t / nthreads), hi = (int)((long long)n * (t + 1) / nthreads);
+    if (hi > lo) th.emplace_back([=]() { for (int s = 0; s < substeps; s++) for (int e = lo; e < hi; e++) step_env(*O, O->envs[e]); });
+  }
+  for (auto& t : th) t.join();
 }
 
 int b2o_contact_count(void* h, int env) { return (int)((Oracle*)h)->envs[env].contacts.size(); }

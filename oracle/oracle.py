@@ -15,9 +15,8 @@ _D = C.POINTER(C.c_double)
 
 def build(force=False):
     """Compile the two oracle builds (float32 / float64) with the committed Makefile."""
-    need = force or not all(os.path.exists(os.path.join(_DIR, f"libb2s_oracle_{p}.so")) for p in ("f32", "f64"))
-    if need:
-        subprocess.check_call(["make", "-C", _DIR, "-s"] + (["-B"] if force else []))
+    # make tracks the dependencies (sources + include/b200sim.h); a no-op when everything is up to date
+    subprocess.check_call(["make", "-C", _DIR, "-s"] + (["-B"] if force else []))
 
 
 _libs = {}
@@ -39,6 +38,7 @@ def _lib(precision):
         lib.b2o_get_links.argtypes = [C.c_void_p, _D]
         lib.b2o_step.argtypes = [C.c_void_p, C.c_int]
         lib.b2o_step_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.b2o_step_mt.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.b2o_contact_count.argtypes = [C.c_void_p, C.c_int]
         lib.b2o_get_contacts.argtypes = [C.c_void_p, C.c_int, _D]
         lib.b2o_pair_impulse.argtypes = [C.c_void_p, C.c_int, C.c_int, _D]
@@ -104,6 +104,9 @@ class OracleWorld:
 
     def step_range(self, substeps, lo, hi):
         self.lib.b2o_step_range(self.h, substeps, lo, hi)
+
+    def step_mt(self, substeps, nthreads):
+        self.lib.b2o_step_mt(self.h, substeps, nthreads)
 
     def contacts(self, env=0):
         n = self.lib.b2o_contact_count(self.h, env)

@@ -26,8 +26,9 @@ void emu_destroy(void* h) { World* w = (World*)h; w->release(); delete w; }
 void emu_step(void* h, int substeps, unsigned fetch_mask) {
   World* w = (World*)h;
   for (int e = 0; e < w->M.n_envs; e++) {
-    if (w->caps == 0) b2s::step_env<b2s::CapsS>(w->M, w->S, e, substeps, fetch_mask);
-    else b2s::step_env<b2s::CapsL>(w->M, w->S, e, substeps, fetch_mask);
+    if (w->caps == 0 && w->M.n_dof == 9) b2s::step_env<b2s::CapsS, 9>(w->M, w->S, e, substeps, fetch_mask);
+    else if (w->caps == 0) b2s::step_env<b2s::CapsS, 0>(w->M, w->S, e, substeps, fetch_mask);
+    else b2s::step_env<b2s::CapsL, 0>(w->M, w->S, e, substeps, fetch_mask);
   }
 }
 void emu_apply(void* h, unsigned mask) {

@@ -14,7 +14,8 @@ BUF_ALL = 0xFFFFFFFF
 def _build():
     so = os.path.join(_DIR, "libb2s_emu.so")
     srcs = [os.path.join(_DIR, "b2s_emu.cpp")] + [os.path.join(_DIR, "../../maniskill_b200/csrc", f) for f in
-                                                   ("b2s_math.cuh", "b2s_collide.cuh", "b2s_step.cuh", "b2s_world.inl")]
+                                                   ("b2s_math.cuh", "b2s_collide.cuh", "b2s_step.cuh", "b2s_world.inl",
+                                                    "../../include/b200sim.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-x", "c++", "-o", so, srcs[0]])
     return so

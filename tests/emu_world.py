@@ -1,0 +1,55 @@
+"""TEST DOUBLE: maniskill_b200.backend.World's interface on top of the host emulation (tests/emu), with CPU torch
+tensors aliasing the emulated buffers.  Lets the host logic (BaseEnv, controllers, obs/reward, partial reset) be
+tested on a machine without a GPU; the product never uses it."""
+import numpy as np
+import torch
+
+from emu import BUF_ALL, EmuWorld
+
+
+class EmuBackendWorld:
+    def __init__(self, cm):
+        self.cm = cm
+        self._w = EmuWorld(cm)
+        w = self._w
+        self.device = torch.device("cpu")
+        self.n_envs, self.n_rows, self.n_link = w.n_envs, w.n_rows, w.n_link
+        s = cm.scalars
+        self.n_art, self.n_fb = s["n_art"], s["n_fb"]
+        self.max_dof = max(s["max_dof_per_art"], 1)
+        self.rigid_body_data = torch.from_numpy(w.rigid_body_data.reshape(-1, 13))
+        self.qpos, self.qvel, self.qacc, self.qf = [torch.from_numpy(a) for a in (w.qpos, w.qvel, w.qacc, w.qf)]
+        self.target_qpos, self.target_qvel = torch.from_numpy(w.target_qpos), torch.from_numpy(w.target_qvel)
+        self._queries = {}
+        self.kernel_launches = 0
+
+    def body_view(self):
+        return self.rigid_body_data.view(self.n_envs, self.n_rows, 13)
+
+    def step(self, substeps=1, fetch_mask=0):
+        self._w.step(substeps, fetch_mask)
+
+    def apply(self, mask):
+        self._w.apply(mask)
+
+    def fetch(self, mask=BUF_ALL):
+        self._w.fetch(mask)
+
+    def update_kinematics(self):
+        self._w.fetch(1 << 8)
+
+    def create_contact_query(self, row_pairs):
+        key = tuple(map(tuple, row_pairs))
+        self._queries[key] = list(key)
+        return key
+
+    def query_contact_impulses(self, key):
+        out = np.stack([self._w.pair_impulse(a, b) for a, b in self._queries[key]], axis=1)
+        return torch.from_numpy(out.astype(np.float32))
+
+    @property
+    def overflow_flag(self):
+        return torch.tensor([self._w.overflow()])
+
+    def close(self):
+        pass
