@@ -209,18 +209,20 @@ typedef struct B2SCameraDesc {
 } B2SCameraDesc;
 
 typedef struct B2SVisualTable {
-  int32_t n_visual;
-  const int32_t* type;    /* B2S_SHAPE_*  */
-  const int32_t* row;     /* exposed body row or -1 static */
-  const float* pose;      /* [n*7] local */
-  const float* size;      /* [n*3] */
-  const int32_t* hull;    /* hull id for convex */
-  const float* color;     /* [n*4] base colour rgba in [0,1] */
-  const int32_t* seg_id;  /* per_scene_id of the owning entity */
-  const int32_t* hidden;  /* 1 = not drawn in sensor cameras (hidden objects) */
-  int32_t n_tri;          /* triangles over all hulls (for convex visuals) */
-  const int32_t* hull_tri_offset; /* [n_hull+1] */
-  const int32_t* hull_tris;       /* [n_tri*3] vertex ids local to the hull */
+  int32_t n_visual;        /* <= 64 render shapes per sub-scene */
+  const int32_t* type;     /* B2S_SHAPE_* (box / sphere / plane are ray-cast, convex is rasterised) */
+  const int32_t* row;      /* exposed body row the shape follows, or -1 static */
+  const float* pose;       /* [n*7] local pose in the body frame */
+  const float* size;       /* [n*3] */
+  const float* color;      /* [n*4] base colour rgba in [0,1] */
+  const int32_t* seg_id;   /* per_scene_id of the owning entity (segmentation value) */
+  const int32_t* ov_slot;  /* [n] per-env override slot or -1 */
+  int32_t n_ov;
+  const float* ov_size;    /* [n_envs*n_ov*3] env-major */
+  const float* ov_pose;    /* [n_envs*n_ov*7] env-major */
+  int32_t n_tri;           /* triangle soup of all convex visuals */
+  const int32_t* tri_vis;  /* [n_tri] owning visual */
+  const float* tri_verts;  /* [n_tri*9] vertices in the visual's local frame */
 } B2SVisualTable;
 
 typedef struct B2SRenderTargets {

@@ -38,8 +38,8 @@ class B2SCameraDesc(C.Structure):
 
 class B2SVisualTable(C.Structure):
     _fields_ = [("n_visual", C.c_int32), ("type", C.c_void_p), ("row", C.c_void_p), ("pose", C.c_void_p), ("size", C.c_void_p),
-                ("hull", C.c_void_p), ("color", C.c_void_p), ("seg_id", C.c_void_p), ("hidden", C.c_void_p), ("n_tri", C.c_int32),
-                ("hull_tri_offset", C.c_void_p), ("hull_tris", C.c_void_p)]
+                ("color", C.c_void_p), ("seg_id", C.c_void_p), ("ov_slot", C.c_void_p), ("n_ov", C.c_int32), ("ov_size", C.c_void_p),
+                ("ov_pose", C.c_void_p), ("n_tri", C.c_int32), ("tri_vis", C.c_void_p), ("tri_verts", C.c_void_p)]
 
 
 class B2SRenderTargets(C.Structure):
@@ -94,6 +94,26 @@ def _as_tensor(ptr, shape, typestr, owner, device):
 def _check(lib, code):
     if code != 0:
         raise RuntimeError(f"b200sim error {code}: {lib.b2s_last_error().decode()}")
+
+
+class CameraGroup:
+    """What ``render_system_group.create_camera_group(...)`` returns in the reference (mani_skill/envs/scene.py:1087-1106):
+    ``take_picture()`` renders every camera of every sub-scene, ``get_picture_cuda(name)`` hands out zero-copy tensors."""
+
+    def __init__(self, world, handle, cameras, color, posseg):
+        self.world, self.handle, self.cameras = world, handle, cameras
+        self._color, self._posseg = color, posseg
+        self._offsets = np.cumsum([0] + [int(c["width"]) * int(c["height"]) for c in cameras])
+
+    def take_picture(self):
+        self.world.render(self)
+
+    def get_picture_cuda(self, name: str, cam: int = 0):
+        """[N, H, W, 4] view of one camera's render target ('Color' uint8 | 'PositionSegmentation' int16)."""
+        c = self.cameras[cam]
+        a, b = int(self._offsets[cam]), int(self._offsets[cam + 1])
+        buf = self._color if name == "Color" else self._posseg
+        return buf[:, a:b].view(self.world.n_envs, int(c["height"]), int(c["width"]), 4)
 
 
 class World:
@@ -172,6 +192,40 @@ class World:
         _check(self.lib, self.lib.b2s_contact_query_run(self.h, q, C.c_void_p(out.data_ptr()), self._stream()))
         self.kernel_launches += 1
         return out
+
+    # ------------------------------------------------------------------ rendering
+    def create_camera_group(self, cameras, visuals):
+        """cameras: list of dict(width, height, fx, fy, cx, cy, near, far, mount_row, local_pose7);
+        visuals: dict of numpy arrays (see maniskill_b200/render.py).  Returns a CameraGroup with aliasing tensors
+        ``color`` [N, P, 4] uint8 and ``position_seg`` [N, P, 4] int16 (P = pixels of all cameras of one sub-scene)."""
+        n_cam = len(cameras)
+        arr = (B2SCameraDesc * n_cam)()
+        for i, c in enumerate(cameras):
+            arr[i].width, arr[i].height = int(c["width"]), int(c["height"])
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = c["fx"], c["fy"], c["cx"], c["cy"]
+            arr[i].near_, arr[i].far_ = c["near"], c["far"]
+            arr[i].mount_row = int(c["mount_row"])
+            arr[i].local_pose = (C.c_float * 7)(*[float(x) for x in c["local_pose"]])
+        keep = {k: np.ascontiguousarray(v) for k, v in visuals.items() if isinstance(v, np.ndarray)}
+        for k in keep:
+            if keep[k].size == 0:
+                keep[k] = np.zeros(1, dtype=keep[k].dtype)
+        vt = B2SVisualTable()
+        vt.n_visual, vt.n_ov, vt.n_tri = int(visuals["n_visual"]), int(visuals["n_ov"]), int(visuals["n_tri"])
+        for name in ("type", "row", "pose", "size", "color", "seg_id", "ov_slot", "ov_size", "ov_pose", "tri_vis", "tri_verts"):
+            setattr(vt, name, keep[name].ctypes.data_as(C.c_void_p))
+        g = C.c_uint64(0)
+        rt = B2SRenderTargets()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.b2s_camera_group_create(self.h, C.cast(arr, C.c_void_p), n_cam, C.byref(vt), C.byref(g), C.byref(rt)))
+        pix = sum(int(c["width"]) * int(c["height"]) for c in cameras)
+        color = _as_tensor(rt.color, (self.n_envs, pix, 4), "|u1", self, self.device)
+        posseg = _as_tensor(rt.position_seg, (self.n_envs, pix, 4), "<i2", self, self.device)
+        return CameraGroup(self, g, cameras, color, posseg)
+
+    def render(self, group):
+        _check(self.lib, self.lib.b2s_render(self.h, group.handle, self._stream()))
+        self.kernel_launches += 1
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

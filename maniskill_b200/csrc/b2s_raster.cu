@@ -1,0 +1,95 @@
+// Host side of the rasteriser + the kernel instantiation.  Compiled with -fmad=false (see Makefile) so the per-pixel
+// arithmetic is plain IEEE mul/add/div/sqrt and the segmentation mask is reproducible bit for bit by the CPU oracle.
+#define B2S_RASTER_IMPL
+#include "b2s_raster.cuh"
+
+#include <string.h>
+
+namespace b2s {
+
+namespace {
+template <class T>
+T* dev_copy(RasterGroup* g, const T* src, size_t n) {
+  if (n == 0) n = 1, src = nullptr;
+  void* d = nullptr;
+  if (cudaMalloc(&d, n * sizeof(T)) != cudaSuccess) return nullptr;
+  if (src) cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  else cudaMemset(d, 0, n * sizeof(T));
+  g->allocs.push_back(d);
+  return (T*)d;
+}
+}  // namespace
+
+const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& host, const B2SCameraDesc* cams, int n_cam,
+                          const B2SVisualTable* vis, RasterGroup** out, B2SRenderTargets* targets) {
+  if (vis->n_visual > 64) return "more than 64 render shapes per sub-scene";
+  RasterGroup* g = new RasterGroup();
+  RasterModel& R = g->R;
+  memset(&R, 0, sizeof(R));
+  const size_t N = M.n_envs;
+  R.n_envs = M.n_envs; R.n_cam = n_cam; R.n_vis = vis->n_visual; R.n_tri_total = vis->n_tri; R.n_rows = M.n_rows; R.n_ov = vis->n_ov;
+  R.vis_type = dev_copy(g, vis->type, vis->n_visual); R.vis_row = dev_copy(g, vis->row, vis->n_visual);
+  R.vis_pose = dev_copy(g, vis->pose, (size_t)vis->n_visual * 7); R.vis_size = dev_copy(g, vis->size, (size_t)vis->n_visual * 3);
+  R.vis_hull = nullptr;
+  R.vis_color = dev_copy(g, vis->color, (size_t)vis->n_visual * 4); R.vis_seg = dev_copy(g, vis->seg_id, vis->n_visual);
+  R.vis_ov = dev_copy(g, vis->ov_slot, vis->n_visual);
+  {
+    std::vector<float> sz((size_t)vis->n_ov * 3 * N + 1), ps((size_t)vis->n_ov * 7 * N + 1);
+    for (size_t e = 0; e < N; e++) {
+      for (int k = 0; k < vis->n_ov * 3; k++) sz[(size_t)k * N + e] = vis->ov_size[e * vis->n_ov * 3 + k];
+      for (int k = 0; k < vis->n_ov * 7; k++) ps[(size_t)k * N + e] = vis->ov_pose[e * vis->n_ov * 7 + k];
+    }
+    R.ov_size = dev_copy(g, sz.data(), sz.size());
+    R.ov_pose = dev_copy(g, ps.data(), ps.size());
+  }
+  R.tri_vis = dev_copy(g, vis->tri_vis, vis->n_tri);
+  R.tri_verts = dev_copy(g, vis->tri_verts, (size_t)vis->n_tri * 9);
+  std::vector<int> w(n_cam), h(n_cam), mount(n_cam);
+  std::vector<float> intr(n_cam * 6), cp(n_cam * 7);
+  std::vector<size_t> off(n_cam);
+  size_t pix = 0;
+  g->max_pixels = 0;
+  for (int c = 0; c < n_cam; c++) {
+    w[c] = cams[c].width; h[c] = cams[c].height; mount[c] = cams[c].mount_row;
+    intr[6 * c] = cams[c].fx; intr[6 * c + 1] = cams[c].fy; intr[6 * c + 2] = cams[c].cx; intr[6 * c + 3] = cams[c].cy;
+    intr[6 * c + 4] = cams[c].near_; intr[6 * c + 5] = cams[c].far_;
+    for (int k = 0; k < 7; k++) cp[7 * c + k] = cams[c].local_pose[k];
+    off[c] = pix;
+    pix += (size_t)w[c] * h[c];
+    if (w[c] * h[c] > g->max_pixels) g->max_pixels = w[c] * h[c];
+  }
+  if ((size_t)g->max_pixels * 4 > 200 * 1024) { raster_destroy(g); return "camera image does not fit the shared-memory depth buffer (max ~224x224)"; }
+  R.cam_w = dev_copy(g, w.data(), n_cam); R.cam_h = dev_copy(g, h.data(), n_cam); R.cam_mount = dev_copy(g, mount.data(), n_cam);
+  R.cam_intr = dev_copy(g, intr.data(), intr.size()); R.cam_pose = dev_copy(g, cp.data(), cp.size());
+  R.cam_offset = dev_copy(g, off.data(), n_cam);
+  R.pixels_per_env = pix;
+  g->color = dev_copy<uint8_t>(g, nullptr, N * pix * 4);
+  g->posseg = dev_copy<int16_t>(g, nullptr, N * pix * 4);
+  for (void* p : g->allocs)
+    if (!p) { raster_destroy(g); return "rasteriser allocation failed"; }
+  if (cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess) {
+    raster_destroy(g);
+    return "cannot reserve shared memory for the depth buffer";
+  }
+  targets->color = g->color;
+  targets->position_seg = g->posseg;
+  (void)S; (void)host;
+  *out = g;
+  return nullptr;
+}
+
+const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, cudaStream_t st) {
+  int grid = M.n_envs * g->R.n_cam;
+  raster_kernel<<<grid, 256, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+void raster_destroy(RasterGroup* g) {
+  if (!g) return;
+  for (void* p : g->allocs)
+    if (p) cudaFree(p);
+  delete g;
+}
+
+}  // namespace b2s

@@ -1,18 +1,310 @@
-// b200sim batched tiled rasteriser (device).  Placeholder interface until the rasteriser lands (next milestone).
+// b200sim batched tiled rasteriser -- replaces `camera_group.take_picture()` of the reference
+// (mani_skill/utils/structs/render_camera.py:269-273; camera group creation mani_skill/envs/scene.py:1087-1106; pose
+// sync physics->renderer mani_skill/envs/scene.py:404-427) for the "minimal" shader pack
+// (mani_skill/render/shaders.py:68-84): per camera and sub-scene it produces
+//     Color                 [H, W, 4] uint8  rgba
+//     PositionSegmentation  [H, W, 4] int16  x, y, z in millimetres (OpenGL camera frame: x right, y up, z backward,
+//                                            so depth = -z) and the segmentation id (= per_scene_id, 0 = background)
+//
+// One CTA renders one (sub-scene, camera) image.  The whole depth/id buffer of the image lives in shared memory
+// (H*W 32-bit keys: 24-bit reversed-z depth | 8-bit visual id; 64 KB for 128x128):
+//   pass 1  all threads stride over the triangles of the convex-hull visuals: body pose (read once from
+//           rigid_body_data) x local pose -> camera frame, project, top-left fill rule, shared-memory atomicMin
+//   pass 2  each thread owns pixels: analytic ray tests against boxes / spheres / the ground half-space, merge with the
+//           rasterised key, shade (ambient 0.3 + two directional lights, mani_skill/envs/sapien_env.py:845-853), write
+//           the two render targets straight to HBM with 4-byte (rgba8) and 8-byte (4 x int16) stores, coalesced by row.
+// HBM traffic per image: the body rows once in, 12 B per pixel out.  The per-pixel arithmetic is restated in
+// oracle/b2s_oracle_raster.cpp; this translation unit is compiled with -fmad=false so both produce identical masks.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
 
 #include "../../include/b200sim.h"
 #include "b2s_step.cuh"
 
 namespace b2s {
-struct RasterGroup {
-  int dummy;
+
+struct RasterModel {
+  int n_envs, n_cam, n_vis, n_tri_total, n_rows, n_ov;
+  const int* vis_type;
+  const int* vis_row;
+  const float* vis_pose;   // [n_vis*7]
+  const float* vis_size;   // [n_vis*3]
+  const int* vis_hull;
+  const float* vis_color;  // [n_vis*4]
+  const int* vis_seg;
+  const int* vis_ov;       // per-env override slot or -1
+  const float* ov_size;    // SoA [n_ov*3][N]
+  const float* ov_pose;    // SoA [n_ov*7][N]
+  // triangle soup of the hull visuals
+  const int* tri_vis;      // [n_tri_total] owning visual
+  const float* tri_verts;  // [n_tri_total*9] local (hull frame) vertices
+  // cameras
+  const int* cam_w;
+  const int* cam_h;
+  const float* cam_intr;   // [n_cam*6] fx fy cx cy near far
+  const int* cam_mount;    // row or -1
+  const float* cam_pose;   // [n_cam*7]
+  size_t* cam_offset;      // [n_cam] pixel offset of camera c inside one env's block
+  size_t pixels_per_env;
 };
-inline const char* raster_create(const DevModel&, const DevState&, const B2SModel&, const B2SCameraDesc*, int, const B2SVisualTable*,
-                                 RasterGroup**, B2SRenderTargets*) {
-  return "rasteriser not built into this library yet";
+
+struct RasterGroup {
+  RasterModel R;
+  std::vector<void*> allocs;
+  uint8_t* color;
+  int16_t* posseg;
+  int max_pixels;  // largest camera image (pixels) -> shared memory size
+};
+
+#define B2S_DEPTH_BITS 24
+#define B2S_DEPTH_MAX 16777215.0f
+
+// reversed-z quantisation shared by the raster and the analytic pass
+B2S_HD unsigned depth_key(float d, float nearp, float farp) {
+  float inv = 1.0f / d, invn = 1.0f / nearp, invf = 1.0f / farp;
+  float t = (inv - invf) / (invn - invf);  // 1 at near, 0 at far
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  float q = B2S_DEPTH_MAX - t * B2S_DEPTH_MAX;
+  return (unsigned)q;
 }
-inline const char* raster_run(const DevModel&, const DevState&, RasterGroup*, cudaStream_t) { return "rasteriser not built"; }
-inline void raster_destroy(RasterGroup*) {}
+B2S_HD float key_depth(unsigned k, float nearp, float farp) {
+  float invn = 1.0f / nearp, invf = 1.0f / farp;
+  float t = (B2S_DEPTH_MAX - (float)k) / B2S_DEPTH_MAX;
+  float inv = invf + t * (invn - invf);
+  return 1.0f / inv;
+}
+
+// ray (origin o, direction dvec, both in the box frame) against an axis-aligned box of half extents h: entry distance
+B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit, v3& n_local) {
+  float tmin = -1e30f, tmax = 1e30f;
+  int axis = 0;
+  float sgn = 1.0f;
+  float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
+  for (int k = 0; k < 3; k++) {
+    if (fabsf(dd[k]) < 1e-12f) {
+      if (fabsf(oo[k]) > hh[k]) return false;
+    } else {
+      float inv = 1.0f / dd[k];
+      float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
+      float s = -1.0f;
+      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; s = 1.0f; }
+      if (t0 > tmin) { tmin = t0; axis = k; sgn = s; }
+      if (t1 < tmax) tmax = t1;
+    }
+  }
+  if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
+  t_hit = tmin;
+  n_local = mk3(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f);
+  return true;
+}
+B2S_HD bool ray_sphere(v3 o, v3 dv, float r, float& t_hit, v3& n_local) {
+  float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
+  float disc = b * b - a * c;
+  if (disc < 0.0f) return false;
+  float t = (-b - sqrtf(disc)) / a;
+  if (t <= 0.0f) return false;
+  t_hit = t;
+  n_local = (o + dv * t) * (1.0f / r);
+  return true;
+}
+
+B2S_HD uint8_t to_u8(float x) {
+  float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
+  return (uint8_t)c;
+}
+B2S_HD v3 shade(v3 base, v3 n_world) {
+  // ambient 0.3 + directional [1,1,-1] + directional [0,0,-1] (white), Lambert
+  const float k = 0.57735026f;
+  v3 l1 = mk3(-k, -k, k), l2 = mk3(0.0f, 0.0f, 1.0f);
+  float w = 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
+  return base * w;
+}
+B2S_HD int16_t to_mm(float x) {
+  float v = x * 1000.0f;
+  v = fminf(fmaxf(v, -32768.0f), 32767.0f);
+  return (int16_t)rintf(v);
+}
+
+#if defined(__CUDACC__) && defined(B2S_RASTER_IMPL)
+
+__device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_rows, int env, int row) {
+  if (row < 0) return pose_ident();
+  const float* o = body_data + ((size_t)env * n_rows + row) * 13;
+  pose P;
+  P.p = mk3(o[0], o[1], o[2]);
+  P.q = mkq(o[3], o[4], o[5], o[6]);
+  return P;
+}
+
+__global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
+                                                     int16_t* __restrict__ posseg) {
+  extern __shared__ unsigned zkey[];
+  __shared__ float vis_R[64][9];   // camera-from-visual rotation (row major)
+  __shared__ float vis_t[64][3];   // camera-from-visual translation
+  __shared__ float vis_Rw[64][9];  // world-from-visual rotation (lighting)
+  __shared__ float vis_sz[64][3];
+  const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
+  const int W = R.cam_w[cam], H = R.cam_h[cam];
+  const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
+  const float nearp = R.cam_intr[6 * cam + 4], farp = R.cam_intr[6 * cam + 5];
+  const int npix = W * H;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) zkey[i] = 0xFFFFFFFFu;
+  // camera pose in the sub-scene frame
+  pose Xc = pmul(raster_body_pose(body_data, R.n_rows, env, R.cam_mount[cam]), pose7(R.cam_pose + 7 * cam));
+  Xc.q = qnormalized(Xc.q);
+  m3 Rc = qmat(Xc.q);
+  const int nv = R.n_vis < 64 ? R.n_vis : 64;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    float lp[7];
+    int ov = R.vis_ov[v];
+    if (ov >= 0) {
+      for (int k = 0; k < 7; k++) lp[k] = R.ov_pose[(size_t)(ov * 7 + k) * R.n_envs + env];
+      for (int k = 0; k < 3; k++) vis_sz[v][k] = R.ov_size[(size_t)(ov * 3 + k) * R.n_envs + env];
+    } else {
+      for (int k = 0; k < 7; k++) lp[k] = R.vis_pose[7 * v + k];
+      for (int k = 0; k < 3; k++) vis_sz[v][k] = R.vis_size[3 * v + k];
+    }
+    pose Xv = pmul(raster_body_pose(body_data, R.n_rows, env, R.vis_row[v]), pose7(lp));
+    Xv.q = qnormalized(Xv.q);
+    m3 Rv = qmat(Xv.q);
+    m3 Rcv = mul(transpose(Rc), Rv);
+    v3 tcv = tmul(Rc, Xv.p - Xc.p);
+    for (int k = 0; k < 9; k++) { vis_R[v][k] = Rcv.m[k]; vis_Rw[v][k] = Rv.m[k]; }
+    vis_t[v][0] = tcv.x; vis_t[v][1] = tcv.y; vis_t[v][2] = tcv.z;
+  }
+  __syncthreads();
+  // ---------------- pass 1: rasterise hull triangles (camera frame: x forward, y left, z up)
+  for (int t = threadIdx.x; t < R.n_tri_total; t += blockDim.x) {
+    int v = R.tri_vis[t];
+    if (v >= nv) continue;
+    const float* tv = R.tri_verts + 9 * (size_t)t;
+    float px[3], py[3], pd[3];
+    bool ok = true;
+    for (int k = 0; k < 3; k++) {
+      v3 l = mk3(tv[3 * k], tv[3 * k + 1], tv[3 * k + 2]);
+      float xc = vis_R[v][0] * l.x + vis_R[v][1] * l.y + vis_R[v][2] * l.z + vis_t[v][0];
+      float yc = vis_R[v][3] * l.x + vis_R[v][4] * l.y + vis_R[v][5] * l.z + vis_t[v][1];
+      float zc = vis_R[v][6] * l.x + vis_R[v][7] * l.y + vis_R[v][8] * l.z + vis_t[v][2];
+      if (xc <= nearp) ok = false;
+      float inv = 1.0f / xc;
+      px[k] = cx - fx * yc * inv;
+      py[k] = cy - fy * zc * inv;
+      pd[k] = inv;
+    }
+    if (!ok) continue;  // triangles touching the near plane are dropped (robot links never get that close)
+    float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
+    if (area == 0.0f) continue;
+    if (area < 0.0f) {  // make counter-clockwise in screen space (hulls are closed: back faces are hidden by front ones)
+      float tx = px[1]; px[1] = px[2]; px[2] = tx;
+      float ty = py[1]; py[1] = py[2]; py[2] = ty;
+      float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
+      area = -area;
+    }
+    float minx = fminf(px[0], fminf(px[1], px[2])), maxx = fmaxf(px[0], fmaxf(px[1], px[2]));
+    float miny = fminf(py[0], fminf(py[1], py[2])), maxy = fmaxf(py[0], fmaxf(py[1], py[2]));
+    int x0 = max(0, (int)floorf(minx - 0.5f)), x1 = min(W - 1, (int)ceilf(maxx - 0.5f));
+    int y0 = max(0, (int)floorf(miny - 0.5f)), y1 = min(H - 1, (int)ceilf(maxy - 0.5f));
+    if (x0 > x1 || y0 > y1) continue;
+    float inv_area = 1.0f / area;
+    for (int y = y0; y <= y1; y++)
+      for (int x = x0; x <= x1; x++) {
+        float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
+        float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
+        float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
+        float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
+        if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) continue;
+        float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
+        if (!(inv > 0.0f)) continue;
+        float d = 1.0f / inv;
+        if (d <= nearp || d >= farp) continue;
+        unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
+        atomicMin(&zkey[y * W + x], key);
+      }
+  }
+  __syncthreads();
+  // ---------------- pass 2: per pixel analytic primitives + merge + shade + store
+  uint8_t* cbase = color + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
+  int16_t* pbase = posseg + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+    int x = i % W, y = i / W;
+    float ry = -((float)x + 0.5f - cx) / fx, rz = -((float)y + 0.5f - cy) / fy;
+    v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
+    float best = 1e30f;
+    int best_v = -1;
+    v3 best_n = mk3(0, 0, 0);  // world normal
+    unsigned k = zkey[i];
+    if (k != 0xFFFFFFFFu) {
+      best = key_depth(k >> 8, nearp, farp);
+      best_v = (int)(k & 255u);
+    }
+    bool raster_hit = best_v >= 0;
+    for (int v = 0; v < nv; v++) {
+      int ty = R.vis_type[v];
+      if (ty == SH_CONVEX) continue;
+      // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
+      v3 tt = mk3(vis_t[v][0], vis_t[v][1], vis_t[v][2]);
+      v3 o = mk3(-(vis_R[v][0] * tt.x + vis_R[v][3] * tt.y + vis_R[v][6] * tt.z), -(vis_R[v][1] * tt.x + vis_R[v][4] * tt.y + vis_R[v][7] * tt.z),
+                 -(vis_R[v][2] * tt.x + vis_R[v][5] * tt.y + vis_R[v][8] * tt.z));
+      v3 dl = mk3(vis_R[v][0] * rdir.x + vis_R[v][3] * rdir.y + vis_R[v][6] * rdir.z, vis_R[v][1] * rdir.x + vis_R[v][4] * rdir.y + vis_R[v][7] * rdir.z,
+                  vis_R[v][2] * rdir.x + vis_R[v][5] * rdir.y + vis_R[v][8] * rdir.z);
+      float th;
+      v3 nl;
+      bool hit = false;
+      if (ty == SH_BOX) hit = ray_box(o, dl, mk3(vis_sz[v][0], vis_sz[v][1], vis_sz[v][2]), th, nl);
+      else if (ty == SH_SPHERE) hit = ray_sphere(o, dl, vis_sz[v][0], th, nl);
+      else if (ty == SH_PLANE) {  // half-space, normal = +x of the visual frame
+        if (dl.x < -1e-9f && o.x > 0.0f) { th = -o.x / dl.x; nl = mk3(1, 0, 0); hit = true; }
+      }
+      if (hit && th > nearp && th < farp && th < best) {
+        best = th;
+        best_v = v;
+        raster_hit = false;
+        best_n = mk3(vis_Rw[v][0] * nl.x + vis_Rw[v][1] * nl.y + vis_Rw[v][2] * nl.z, vis_Rw[v][3] * nl.x + vis_Rw[v][4] * nl.y + vis_Rw[v][5] * nl.z,
+                     vis_Rw[v][6] * nl.x + vis_Rw[v][7] * nl.y + vis_Rw[v][8] * nl.z);
+      }
+    }
+    uchar4 c4 = make_uchar4(0, 0, 0, 255);
+    short4 p4 = make_short4(0, 0, 0, 0);
+    if (best_v >= 0) {
+      v3 pc = rdir * best;  // camera-frame hit point
+      if (raster_hit) {
+        // screen-space normal from neighbouring depths of the same visual (flat-ish shading of hull faces)
+        int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
+        unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
+        v3 n_cam = mk3(-1, 0, 0);
+        if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
+          float dx_ = key_depth(kx >> 8, nearp, farp), dy_ = key_depth(ky >> 8, nearp, farp);
+          v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) / fx, rz) * dx_;
+          v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) / fy) * dy_;
+          v3 e1 = pxn - pc, e2 = pyn - pc;
+          if (xn < x) e1 = -e1;
+          if (yn < y) e2 = -e2;
+          v3 nn = cross(e2, e1);  // screen x runs to -y_cam, screen y to -z_cam: e2 x e1 faces the camera
+          float l = norm(nn);
+          if (l > 1e-20f) n_cam = nn * (1.0f / l);
+          if (n_cam.x > 0.0f) n_cam = -n_cam;
+        }
+        best_n = mul(Rc, n_cam);
+      }
+      const float* col = R.vis_color + 4 * best_v;
+      v3 rgb = shade(mk3(col[0], col[1], col[2]), best_n);
+      c4 = make_uchar4(to_u8(rgb.x), to_u8(rgb.y), to_u8(rgb.z), 255);
+      // OpenGL camera frame: x right = -y_cam, y up = z_cam, z backward = -x_cam
+      p4 = make_short4(to_mm(-pc.y), to_mm(pc.z), to_mm(-pc.x), (short)R.vis_seg[best_v]);
+    }
+    *reinterpret_cast<uchar4*>(cbase + (size_t)i * 4) = c4;
+    *reinterpret_cast<short4*>(pbase + (size_t)i * 4) = p4;
+  }
+}
+
+#endif  // __CUDACC__ && B2S_RASTER_IMPL
+
+const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& host, const B2SCameraDesc* cams, int n_cam,
+                          const B2SVisualTable* vis, RasterGroup** out, B2SRenderTargets* targets);
+const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, cudaStream_t st);
+void raster_destroy(RasterGroup* g);
+
 }  // namespace b2s

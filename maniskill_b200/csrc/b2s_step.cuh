@@ -459,10 +459,10 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     r_gamma[ri] = 1.f / (h * h * k);
     B2S_FINISH_ROW(ri);
   }
-  const float limit_margin = 0.1f;
   int n_lim = 0;
   for (int i = 0; i < nd; i++) {
     float lo = M.dof_limit[2 * i], hi = M.dof_limit[2 * i + 1];
+    const float limit_margin = 0.005f + 2.f * dt * fabsf(L.qd[i]);  // only while the limit is reachable within this step
     for (int side = 0; side < 2; side++) {
       bool act = side == 0 ? (lo > -1e29f && L.q[i] - lo < limit_margin) : (hi < 1e29f && hi - L.q[i] < limit_margin);
       if (!act) continue;
@@ -551,9 +551,9 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     man_np[mi] = -1 - mo;
   }
   // ---------------------------------------------------------------- 5. sub-stepped soft TGS
-  float dq[C::MAXD];
-  for (int j = 0; j < nd; j++) dq[j] = 0.f;
-  v3 dx[C::MAXFB], dth[C::MAXFB];
+  float dq[C::MAXD], vfree[C::MAXD], ac[C::MAXD];
+  for (int j = 0; j < nd; j++) { dq[j] = 0.f; ac[j] = 0.f; }
+  v3 dx[C::MAXFB], dth[C::MAXFB], fvfree[C::MAXFB], fwfree[C::MAXFB], acv[C::MAXFB], acw[C::MAXFB];
   for (int b = 0; b < nfb; b++) { dx[b] = mk3(0, 0, 0); dth[b] = mk3(0, 0, 0); }
   const float kPi = 3.14159265358979323846f;
   const float omega = 2.f * kPi * fminf(M.contact_hertz, 0.25f / h), zeta = M.contact_zeta;
@@ -606,9 +606,13 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
         fv[b] = (fv[b] + grav * (h * M.fb_gravity[b])) * fmaxf(0.f, 1.f - h * M.fb_damping[2 * b]);
         fw[b] = fw[b] * fmaxf(0.f, 1.f - h * M.fb_damping[2 * b + 1]);
       }
-      if (it > 0)
-        for (int ri = 0; ri < n_row; ri++)
-          if (r_lambda[ri] != 0.f) B2S_ROW_APPLY(ri, r_lambda[ri]);
+      // warm start: re-apply the velocity change the constraints produced in the previous sub-step
+      for (int j = 0; j < nd; j++) vfree[j] = v[j];
+      for (int b = 0; b < nfb; b++) { fvfree[b] = fv[b]; fwfree[b] = fw[b]; }
+      if (it > 0) {
+        for (int j = 0; j < nd; j++) v[j] += ac[j];
+        for (int b = 0; b < nfb; b++) { fv[b] = fv[b] + acv[b]; fw[b] = fw[b] + acw[b]; }
+      }
     } else {
       for (int ri = 0; ri < n_row; ri++) r_total[ri] -= r_lambda[ri];
     }
@@ -643,6 +647,8 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     }
     for (int ri = 0; ri < n_row; ri++) r_total[ri] += r_lambda[ri];
     if (!relax) {
+      for (int j = 0; j < nd; j++) ac[j] = v[j] - vfree[j];
+      for (int b = 0; b < nfb; b++) { acv[b] = fv[b] - fvfree[b]; acw[b] = fw[b] - fwfree[b]; }
       for (int j = 0; j < nd; j++) dq[j] += h * v[j];
       for (int b = 0; b < nfb; b++) {
         dx[b] = dx[b] + fv[b] * h;

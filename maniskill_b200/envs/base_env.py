@@ -185,9 +185,6 @@ class BaseEnv:
             return info["success"].float()
         return torch.zeros(self.num_envs, device=self.device)
 
-    def _setup_sensors(self):
-        return {}
-
     # ------------------------------------------------------------------ properties
     @property
     def obs_mode(self):
@@ -351,11 +348,38 @@ class BaseEnv:
         obs["sensor_data"] = self._get_obs_sensor_data()
         return obs
 
+    def _sensor_configs(self):
+        """task hook: list of dict(uid, pose(7), width, height, fov, near, far, mount(link/actor name or None))."""
+        return []
+
+    def _setup_sensors(self):
+        """sapien_env.py:771-843 `_setup_sensors` + scene.py:1087-1106: one camera group for all sensor cameras."""
+        from ..render import CameraSensors, camera_desc
+        cams = []
+        for c in self._sensor_configs():
+            c = dict(c)
+            c.update(self._sensor_overrides.get(c["uid"], {}))
+            row = -1
+            if c.get("mount") is not None:
+                art, link = c["mount"]
+                row = self.cm.link_rows[art][link]
+            cams.append(camera_desc(c["uid"], c["pose"], c["width"], c["height"], c["fov"], c["near"], c["far"], row))
+        if not cams:
+            raise NotImplementedError("this task defines no sensor cameras")
+        return CameraSensors(self.scene.world, self.cm, cams)
+
     def _get_obs_sensor_data(self):
-        raise NotImplementedError("this task has no sensors")
+        """sapien_env.py:578-625: hidden objects are simply absent from the sensor render-shape table (the reference
+        teleports them away and back, actor.py:176-201), then update_render + take_picture on the camera group."""
+        self._sensors.capture()
+        m = self._obs_mode
+        want_rgb = "rgb" in m or m == "sensor_data"
+        want_depth = "depth" in m or "rgbd" in m or m == "sensor_data"
+        want_seg = "segmentation" in m or m == "sensor_data"
+        return self._sensors.get_obs(rgb=want_rgb, depth=want_depth, segmentation=want_seg)
 
     def get_sensor_params(self):
-        return {}
+        return self._sensors.get_params(self.scene.world.body_view()) if self._sensors else {}
 
     def get_reward(self, obs, action, info):
         if self._reward_mode == "sparse":

@@ -1,0 +1,110 @@
+"""Host side of the camera sensors: render-shape table + camera descriptors for the batched rasteriser.
+
+Mirror of the pieces of mani_skill/sensors/camera.py:126-253 (``Camera``), mani_skill/utils/structs/render_camera.py:77-182
+(camera parameter tensors) and mani_skill/render/shaders.py:68-84 (the "minimal" pack's texture transforms) that the
+visual observation modes use.  Render shapes are the collision primitives / convex hulls with a flat base colour (the
+reference's .glb visual meshes and the floor texture are assets outside the hot path).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from .model import SHAPE_CONVEX, CompiledModel
+
+
+def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = False) -> Dict[str, np.ndarray]:
+    vis = [v for v in cm.visuals if include_hidden or not v["hidden"]]
+    hull_off = cm.arrays["hull_offset"]
+    hull_verts = cm.arrays["hull_verts"].reshape(-1, 3)
+    types, rows, poses, sizes, colors, segs, ov_slot = [], [], [], [], [], [], []
+    ov_size, ov_pose = [], []
+    tri_vis, tri_verts = [], []
+    for i, v in enumerate(vis):
+        types.append(v["type"]); rows.append(v["row"]); poses.append(v["pose"]); sizes.append(v["size"])
+        colors.append(v["color"]); segs.append(v["seg"])
+        if v["per_env_size"] is not None or v["per_env_pose"] is not None:
+            ov_slot.append(len(ov_size))
+            ov_size.append(np.asarray(v["per_env_size"] if v["per_env_size"] is not None else np.tile(v["size"], (n_envs, 1)), dtype=np.float32))
+            ov_pose.append(np.asarray(v["per_env_pose"] if v["per_env_pose"] is not None else np.tile(v["pose"], (n_envs, 1)), dtype=np.float32))
+        else:
+            ov_slot.append(-1)
+        if v["type"] == SHAPE_CONVEX:
+            h = v["hull"]
+            verts = hull_verts[hull_off[h]:hull_off[h + 1]]
+            tris = cm.hull_tris[h]
+            tri_verts.append(verts[tris].reshape(-1, 9))
+            tri_vis.extend([i] * len(tris))
+    f32 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(shape))
+    n = len(vis)
+    return dict(
+        n_visual=n, n_ov=len(ov_size), n_tri=len(tri_vis),
+        type=np.asarray(types, dtype=np.int32), row=np.asarray(rows, dtype=np.int32), pose=f32(poses, (-1,)), size=f32(sizes, (-1,)),
+        color=f32(colors, (-1,)), seg_id=np.asarray(segs, dtype=np.int32), ov_slot=np.asarray(ov_slot, dtype=np.int32),
+        ov_size=f32(np.stack(ov_size, 1) if ov_size else np.zeros(0), (-1,)), ov_pose=f32(np.stack(ov_pose, 1) if ov_pose else np.zeros(0), (-1,)),
+        tri_vis=np.asarray(tri_vis, dtype=np.int32), tri_verts=f32(np.concatenate(tri_verts) if tri_verts else np.zeros(0), (-1,)),
+    )
+
+
+def camera_desc(uid, pose7, width, height, fov, near, far, mount_row=-1):
+    """CameraConfig(uid, pose, width, height, fov, near, far) -> intrinsics like RenderCameraComponent.set_fovy:
+    fy = (H/2) / tan(fov/2), fx = fy, principal point at the image centre."""
+    fy = (height / 2.0) / np.tan(fov / 2.0)
+    return dict(uid=uid, width=int(width), height=int(height), fx=float(fy), fy=float(fy), cx=width / 2.0, cy=height / 2.0,
+                near=float(near), far=float(far), mount_row=int(mount_row), local_pose=[float(x) for x in pose7])
+
+
+class CameraSensors:
+    """All cameras of a task as one camera group (mani_skill/envs/scene.py:1087-1106) + the obs-facing accessors."""
+
+    def __init__(self, world, cm: CompiledModel, cams: List[dict]):
+        self.world = world
+        self.cams = cams
+        self.visuals = build_visual_table(cm, world.n_envs)
+        self.group = world.create_camera_group(cams, self.visuals)
+
+    def capture(self):
+        self.group.take_picture()
+
+    def get_obs(self, rgb=True, depth=True, segmentation=True, position=False):
+        """sensor_data[uid] = {rgb [N,H,W,3] uint8, depth [N,H,W,1] int16 (mm), segmentation [N,H,W,1] int16}
+        (texture_transforms of the minimal shader pack, mani_skill/render/shaders.py:74-83)."""
+        out = {}
+        for i, c in enumerate(self.cams):
+            d = {}
+            if rgb:
+                d["rgb"] = self.group.get_picture_cuda("Color", i)[..., :3]
+            ps = self.group.get_picture_cuda("PositionSegmentation", i)
+            if depth:
+                d["depth"] = -ps[..., [2]]
+            if position:
+                d["position"] = ps[..., :3]
+            if segmentation:
+                d["segmentation"] = ps[..., [3]]
+            out[c["uid"]] = d
+        return out
+
+    def get_params(self, body_view: torch.Tensor):
+        """sensor_param[uid] = extrinsic_cv [N,3,4], cam2world_gl [N,4,4], intrinsic_cv [N,3,3]
+        (mani_skill/utils/structs/render_camera.py:77-155)."""
+        from . import utils as U
+        from .structs import Pose
+        dev = body_view.device
+        N = body_view.shape[0]
+        out = {}
+        for c in self.cams:
+            local = Pose.create(torch.tensor([c["local_pose"]], dtype=torch.float32, device=dev).expand(N, 7))
+            pose = Pose(body_view[:, c["mount_row"], :7]) * local if c["mount_row"] >= 0 else local
+            T = pose.to_transformation_matrix()  # sapien camera frame (x fwd, y left, z up) -> world
+            # OpenGL camera axes (x right, y up, z back) expressed in the sapien camera frame
+            gl = torch.tensor([[0, 0, -1, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)
+            cam2world_gl = T @ gl
+            # OpenCV camera axes (x right, y down, z fwd)
+            cv = torch.tensor([[0, 0, 1, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)
+            cam2world_cv = T @ cv
+            extrinsic_cv = torch.linalg.inv(cam2world_cv)[:, :3, :4]
+            K = torch.tensor([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1]], dtype=torch.float32, device=dev)[None].expand(N, 3, 3)
+            out[c["uid"]] = dict(extrinsic_cv=extrinsic_cv, cam2world_gl=cam2world_gl, intrinsic_cv=K)
+        return out

@@ -442,9 +442,10 @@ static void step_env(Oracle& O, Env& E) {
     finish_row(r);
     rows.push_back(r);
   }
-  const R limit_margin = R(0.1);
   for (int i = 0; i < nd; i++) {
     R lo = O.dof_limit[2 * i], hi = O.dof_limit[2 * i + 1];
+    // a limit row exists only while the joint can reach the limit within this step
+    const R limit_margin = R(0.005) + 2 * dt * std::fabs(E.qd[i]);
     if (lo > R(-1e29) && E.q[i] - lo < limit_margin) {
       Row r = blank_row(ROW_LIMIT);
       r.has_art = true;
@@ -545,8 +546,8 @@ static void step_env(Oracle& O, Env& E) {
   // impulses (warm start), one Gauss-Seidel sweep, advance the linearised configuration.  Penetration is removed by a
   // soft constraint (natural frequency contact_hertz, damping ratio contact_zeta; Catto's "soft step" coefficients),
   // speculative contacts (s > 0) are exact.  n_vel_iters relaxation sweeps without penetration bias follow.
-  std::vector<R> dq(nd, 0);
-  std::vector<V3> dx(nfb), dth(nfb);
+  std::vector<R> dq(nd, 0), vfree(nd, 0), ac(nd, 0);
+  std::vector<V3> dx(nfb), dth(nfb), fvfree(nfb), fwfree(nfb), acv(nfb), acw(nfb);
   const R kPi = R(3.14159265358979323846);
   const R omega = 2 * kPi * std::fmin((R)m.contact_hertz, R(0.25) / h), zeta = m.contact_zeta;
   const R sa1 = 2 * zeta + h * omega, sa2 = h * omega * sa1, sa3 = R(1) / (R(1) + sa2);
@@ -603,10 +604,15 @@ static void step_env(Oracle& O, Env& E) {
       fv[b] = (fv[b] + grav * (h * O.fb_gravity[b])) * std::fmax(R(0), R(1) - h * O.fb_damping[2 * b]);
       fw[b] = fw[b] * std::fmax(R(0), R(1) - h * O.fb_damping[2 * b + 1]);
     }
-    if (it > 0)
-      for (size_t ri = 0; ri < rows.size(); ri++)
-        if (rows[ri].lambda != 0) apply(rows[ri], rows[ri].lambda);
+    // warm start: re-apply the velocity change the constraints produced in the previous sub-step (= sum_r B_r lambda_r)
+    vfree = v; fvfree = fv; fwfree = fw;
+    if (it > 0) {
+      for (int j = 0; j < nd; j++) v[j] += ac[j];
+      for (int b = 0; b < nfb; b++) { fv[b] = fv[b] + acv[b]; fw[b] = fw[b] + acw[b]; }
+    }
     sweep(false);
+    for (int j = 0; j < nd; j++) ac[j] = v[j] - vfree[j];
+    for (int b = 0; b < nfb; b++) { acv[b] = fv[b] - fvfree[b]; acw[b] = fw[b] - fwfree[b]; }
     for (size_t ri = 0; ri < rows.size(); ri++) rows[ri].total += rows[ri].lambda;
     for (int j = 0; j < nd; j++) dq[j] += h * v[j];
     for (int b = 0; b < nfb; b++) {

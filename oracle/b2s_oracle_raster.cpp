@@ -1,0 +1,299 @@
+// TEST INFRASTRUCTURE ONLY.  CPU restatement of the camera path the reference gets from SAPIEN's Vulkan rasteriser:
+// `camera_group.take_picture()` (mani_skill/utils/structs/render_camera.py:269-273) with the "minimal" shader pack whose
+// render targets are `Color` rgba8 and `PositionSegmentation` 4 x int16 = (x, y, z in mm, OpenGL camera frame,
+// segmentation id) (mani_skill/render/shaders.py:68-84, docs/source/user_guide/concepts/observation.md).
+//
+// SAPIEN's renderer is not in /root/reference and cannot run here, and the reference ships no reference images or
+// masks: PARITY UNPINNED for absolute pixel values.  What this oracle pins is the CUDA rasteriser's own definition:
+//   * pinhole camera, sapien camera frame (x forward, y left, z up), pixel centres at (u + 0.5, v + 0.5), v = 0 at the top
+//   * convex-hull visuals: triangles projected to the screen, sample inside iff the three edge functions are >= 0 after
+//     orienting the triangle counter-clockwise, 1/depth interpolated linearly in screen space, depth quantised to a
+//     24-bit reversed-z key; nearest key wins, ties broken by the lower visual index
+//   * boxes / spheres / half-spaces: analytic ray tests per pixel, a primitive wins only if strictly nearer
+//   * segmentation = per_scene_id of the winning visual, 0 = background; position = hit point in mm (round to nearest even)
+// Plain loops, float32, compiled with -ffp-contract=off; the CUDA translation unit is compiled with -fmad=false, so the
+// integer outputs (segmentation, position) are expected to agree bit for bit.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct F3 {
+  float x, y, z;
+};
+inline F3 f3(float x, float y, float z) { F3 r = {x, y, z}; return r; }
+inline F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline F3 operator-(F3 a) { return f3(-a.x, -a.y, -a.z); }
+inline F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+inline float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline F3 cross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline float norm(F3 a) { return sqrtf(dot(a, a)); }
+
+struct Q {
+  float w, x, y, z;
+};
+struct P7 {
+  F3 p;
+  Q q;
+};
+inline Q qmul(Q a, Q b) {
+  Q r = {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+         a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+  return r;
+}
+inline Q qnorm(Q q) {
+  float s = 1.f / sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  Q r = {q.w * s, q.x * s, q.y * s, q.z * s};
+  return r;
+}
+inline F3 qrot(Q q, F3 v) {
+  F3 u = f3(q.x, q.y, q.z);
+  F3 t = cross(u, v) * 2.f;
+  return v + t * q.w + cross(u, t);
+}
+inline void qmat(Q q, float* m) {
+  float w = q.w, x = q.x, y = q.y, z = q.z;
+  m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = 1 - 2 * (x * x + y * y);
+}
+inline P7 pmul(P7 a, P7 b) {
+  P7 c;
+  c.p = a.p + qrot(a.q, b.p);
+  c.q = qmul(a.q, b.q);
+  return c;
+}
+inline P7 p7(const float* f) {
+  P7 p;
+  p.p = f3(f[0], f[1], f[2]);
+  Q q = {f[3], f[4], f[5], f[6]};
+  p.q = q;
+  return p;
+}
+inline P7 ident() {
+  P7 p;
+  p.p = f3(0, 0, 0);
+  Q q = {1, 0, 0, 0};
+  p.q = q;
+  return p;
+}
+
+const float DEPTH_MAX = 16777215.0f;
+inline unsigned depth_key(float d, float nearp, float farp) {
+  float inv = 1.0f / d, invn = 1.0f / nearp, invf = 1.0f / farp;
+  float t = (inv - invf) / (invn - invf);
+  t = fminf(fmaxf(t, 0.0f), 1.0f);
+  float q = DEPTH_MAX - t * DEPTH_MAX;
+  return (unsigned)q;
+}
+inline float key_depth(unsigned k, float nearp, float farp) {
+  float invn = 1.0f / nearp, invf = 1.0f / farp;
+  float t = (DEPTH_MAX - (float)k) / DEPTH_MAX;
+  float inv = invf + t * (invn - invf);
+  return 1.0f / inv;
+}
+inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, F3& n_local) {
+  float tmin = -1e30f, tmax = 1e30f;
+  int axis = 0;
+  float sgn = 1.0f;
+  float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
+  for (int k = 0; k < 3; k++) {
+    if (fabsf(dd[k]) < 1e-12f) {
+      if (fabsf(oo[k]) > hh[k]) return false;
+    } else {
+      float inv = 1.0f / dd[k];
+      float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
+      float s = -1.0f;
+      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; s = 1.0f; }
+      if (t0 > tmin) { tmin = t0; axis = k; sgn = s; }
+      if (t1 < tmax) tmax = t1;
+    }
+  }
+  if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
+  t_hit = tmin;
+  n_local = f3(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f);
+  return true;
+}
+inline bool ray_sphere(F3 o, F3 dv, float r, float& t_hit, F3& n_local) {
+  float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
+  float disc = b * b - a * c;
+  if (disc < 0.0f) return false;
+  float t = (-b - sqrtf(disc)) / a;
+  if (t <= 0.0f) return false;
+  t_hit = t;
+  n_local = (o + dv * t) * (1.0f / r);
+  return true;
+}
+inline uint8_t to_u8(float x) {
+  float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
+  return (uint8_t)c;
+}
+inline int16_t to_mm(float x) {
+  float v = x * 1000.0f;
+  v = fminf(fmaxf(v, -32768.0f), 32767.0f);
+  return (int16_t)rintf(v);
+}
+inline F3 mulm(const float* m, F3 v) { return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
+inline F3 tmulm(const float* m, F3 v) { return f3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z); }
+
+}  // namespace
+
+extern "C" {
+
+// Renders one camera of one sub-scene.
+//   vis_*: render-shape table (same arrays the C-ABI B2SVisualTable carries); per-env size/pose already resolved by the caller
+//   body:  [n_rows*13] float32 rows of this sub-scene
+//   cam:   w h fx fy cx cy near far mount_row local_pose(7)  as 16 floats
+//   out:   color [h*w*4] uint8, posseg [h*w*4] int16
+void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const float* vis_pose, const float* vis_size,
+                    const float* vis_color, const int* vis_seg, int n_tri, const int* tri_vis, const float* tri_verts,
+                    int n_rows, const float* body, const float* cam, uint8_t* color, int16_t* posseg) {
+  const int W = (int)cam[0], H = (int)cam[1];
+  const float fx = cam[2], fy = cam[3], cx = cam[4], cy = cam[5], nearp = cam[6], farp = cam[7];
+  const int mount = (int)cam[8];
+  auto body_pose = [&](int row) {
+    if (row < 0) return ident();
+    return p7(body + (size_t)row * 13);
+  };
+  P7 Xc = pmul(body_pose(mount), p7(cam + 9));
+  Xc.q = qnorm(Xc.q);
+  float Rc[9];
+  qmat(Xc.q, Rc);
+  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vRw(n_vis * 9);
+  for (int v = 0; v < n_vis; v++) {
+    P7 Xv = pmul(body_pose(vis_row[v]), p7(vis_pose + 7 * v));
+    Xv.q = qnorm(Xv.q);
+    float Rv[9];
+    qmat(Xv.q, Rv);
+    // Rcv = Rc^T Rv
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) vR[v * 9 + 3 * i + j] = Rc[i] * Rv[j] + Rc[3 + i] * Rv[3 + j] + Rc[6 + i] * Rv[6 + j];
+    F3 t = tmulm(Rc, Xv.p - Xc.p);
+    vt[v * 3] = t.x; vt[v * 3 + 1] = t.y; vt[v * 3 + 2] = t.z;
+    for (int k = 0; k < 9; k++) vRw[v * 9 + k] = Rv[k];
+  }
+  const int npix = W * H;
+  std::vector<unsigned> zkey(npix, 0xFFFFFFFFu);
+  for (int t = 0; t < n_tri; t++) {
+    int v = tri_vis[t];
+    const float* tv = tri_verts + 9 * (size_t)t;
+    const float* Rm = &vR[v * 9];
+    float px[3], py[3], pd[3];
+    bool ok = true;
+    for (int k = 0; k < 3; k++) {
+      F3 l = f3(tv[3 * k], tv[3 * k + 1], tv[3 * k + 2]);
+      float xc = Rm[0] * l.x + Rm[1] * l.y + Rm[2] * l.z + vt[v * 3];
+      float yc = Rm[3] * l.x + Rm[4] * l.y + Rm[5] * l.z + vt[v * 3 + 1];
+      float zc = Rm[6] * l.x + Rm[7] * l.y + Rm[8] * l.z + vt[v * 3 + 2];
+      if (xc <= nearp) ok = false;
+      float inv = 1.0f / xc;
+      px[k] = cx - fx * yc * inv;
+      py[k] = cy - fy * zc * inv;
+      pd[k] = inv;
+    }
+    if (!ok) continue;
+    float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
+    if (area == 0.0f) continue;
+    if (area < 0.0f) {
+      float tx = px[1]; px[1] = px[2]; px[2] = tx;
+      float ty = py[1]; py[1] = py[2]; py[2] = ty;
+      float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
+      area = -area;
+    }
+    float minx = fminf(px[0], fminf(px[1], px[2])), maxx = fmaxf(px[0], fmaxf(px[1], px[2]));
+    float miny = fminf(py[0], fminf(py[1], py[2])), maxy = fmaxf(py[0], fmaxf(py[1], py[2]));
+    int x0 = (int)floorf(minx - 0.5f), x1 = (int)ceilf(maxx - 0.5f), y0 = (int)floorf(miny - 0.5f), y1 = (int)ceilf(maxy - 0.5f);
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > W - 1) x1 = W - 1;
+    if (y1 > H - 1) y1 = H - 1;
+    if (x0 > x1 || y0 > y1) continue;
+    float inv_area = 1.0f / area;
+    for (int y = y0; y <= y1; y++)
+      for (int x = x0; x <= x1; x++) {
+        float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
+        float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
+        float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
+        float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
+        if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) continue;
+        float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
+        if (!(inv > 0.0f)) continue;
+        float d = 1.0f / inv;
+        if (d <= nearp || d >= farp) continue;
+        unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
+        if (key < zkey[y * W + x]) zkey[y * W + x] = key;
+      }
+  }
+  for (int i = 0; i < npix; i++) {
+    int x = i % W, y = i / W;
+    float ry = -((float)x + 0.5f - cx) / fx, rz = -((float)y + 0.5f - cy) / fy;
+    F3 rdir = f3(1.0f, ry, rz);
+    float best = 1e30f;
+    int best_v = -1;
+    F3 best_n = f3(0, 0, 0);
+    unsigned k = zkey[i];
+    if (k != 0xFFFFFFFFu) {
+      best = key_depth(k >> 8, nearp, farp);
+      best_v = (int)(k & 255u);
+    }
+    bool raster_hit = best_v >= 0;
+    for (int v = 0; v < n_vis; v++) {
+      int ty = vis_type[v];
+      if (ty == 4) continue;
+      const float* Rm = &vR[v * 9];
+      F3 tt = f3(vt[v * 3], vt[v * 3 + 1], vt[v * 3 + 2]);
+      F3 o = f3(-(Rm[0] * tt.x + Rm[3] * tt.y + Rm[6] * tt.z), -(Rm[1] * tt.x + Rm[4] * tt.y + Rm[7] * tt.z), -(Rm[2] * tt.x + Rm[5] * tt.y + Rm[8] * tt.z));
+      F3 dl = f3(Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z, Rm[1] * rdir.x + Rm[4] * rdir.y + Rm[7] * rdir.z,
+                 Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
+      float th = 0;
+      F3 nl = f3(0, 0, 0);
+      bool hit = false;
+      if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th, nl);
+      else if (ty == 2) hit = ray_sphere(o, dl, vis_size[3 * v], th, nl);
+      else if (ty == 0) {
+        if (dl.x < -1e-9f && o.x > 0.0f) { th = -o.x / dl.x; nl = f3(1, 0, 0); hit = true; }
+      }
+      if (hit && th > nearp && th < farp && th < best) {
+        best = th;
+        best_v = v;
+        raster_hit = false;
+        best_n = mulm(&vRw[v * 9], nl);
+      }
+    }
+    uint8_t* c4 = color + (size_t)i * 4;
+    int16_t* p4 = posseg + (size_t)i * 4;
+    c4[0] = c4[1] = c4[2] = 0; c4[3] = 255;
+    p4[0] = p4[1] = p4[2] = p4[3] = 0;
+    if (best_v >= 0) {
+      F3 pc = rdir * best;
+      if (raster_hit) {
+        int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
+        unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
+        F3 n_cam = f3(-1, 0, 0);
+        if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
+          float dx_ = key_depth(kx >> 8, nearp, farp), dy_ = key_depth(ky >> 8, nearp, farp);
+          F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) / fx, rz) * dx_;
+          F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) / fy) * dy_;
+          F3 e1 = pxn - pc, e2 = pyn - pc;
+          if (xn < x) e1 = -e1;
+          if (yn < y) e2 = -e2;
+          F3 nn = cross(e2, e1);
+          float l = norm(nn);
+          if (l > 1e-20f) n_cam = nn * (1.0f / l);
+          if (n_cam.x > 0.0f) n_cam = -n_cam;
+        }
+        best_n = mulm(Rc, n_cam);
+      }
+      const float* col = vis_color + 4 * best_v;
+      const float kk = 0.57735026f;
+      F3 l1 = f3(-kk, -kk, kk), l2 = f3(0.0f, 0.0f, 1.0f);
+      float w = 0.3f + 0.5f * fmaxf(dot(best_n, l1), 0.0f) + 0.5f * fmaxf(dot(best_n, l2), 0.0f);
+      c4[0] = to_u8(col[0] * w); c4[1] = to_u8(col[1] * w); c4[2] = to_u8(col[2] * w);
+      p4[0] = to_mm(-pc.y); p4[1] = to_mm(pc.z); p4[2] = to_mm(-pc.x); p4[3] = (int16_t)vis_seg[best_v];
+    }
+  }
+}
+}
