@@ -68,8 +68,14 @@ class Pose:
         return Pose(self.raw_pose[i] if self.raw_pose[i].dim() == 2 else self.raw_pose[i][None])
 
     def __mul__(self, other: "Pose") -> "Pose":
-        p = self.p + U.quat_apply(self.q, other.p)
-        q = U.quat_mul(self.q, other.q)
+        a, b = self.raw_pose, other.raw_pose
+        if b.shape[0] == 1 and a.shape[0] > 1:
+            b = b.expand(a.shape[0], 7)
+        elif a.shape[0] == 1 and b.shape[0] > 1:
+            a = a.expand(b.shape[0], 7)
+        p = a[..., :3] + U.quat_apply(a[..., 3:], b[..., :3])
+        q = U.quat_mul(a[..., 3:], b[..., 3:])
+        q = torch.where(q[..., :1] < 0, -q, q)  # quaternion_multiply standardises to a non-negative real part (pose.py:199)
         return Pose(torch.hstack([p, q]))
 
     def inv(self) -> "Pose":

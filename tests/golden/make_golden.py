@@ -1,0 +1,199 @@
+#!/usr/bin/env python
+"""Generates tests/golden/host_golden.npz by running the REFERENCE's own Python functions (imported from the read-only
+checkout at /root/reference) on seeded inputs.  The reference package cannot be imported as a whole here (sapien,
+gymnasium, ... are not installed), so the needed files are loaded one by one with stub modules standing in for the absent
+third-party packages; only pure torch/numpy code paths of the reference execute.
+
+    python tests/golden/make_golden.py          (run in the build container; the .npz is committed)
+
+Covered reference functions (file:line):
+  mani_skill/utils/geometry/rotation_conversions.py  quaternion_raw_multiply, quaternion_apply, quaternion_to_matrix,
+                                                     matrix_to_quaternion, euler_angles_to_matrix
+  mani_skill/envs/utils/randomization/pose.py:13-34  random_quaternions
+  mani_skill/utils/gym_utils.py:104-108              clip_and_scale_action
+  mani_skill/utils/common.py:195-262, 300-304        flatten_state_dict, compute_angle_between
+  mani_skill/utils/sapien_utils.py:317-366           look_at
+  mani_skill/utils/structs/pose.py                   Pose.__mul__, Pose.inv, Pose.to_transformation_matrix
+  mani_skill/envs/tasks/tabletop/pick_cube.py:132-191  _get_obs_extra, evaluate (success logic), compute_dense_reward
+  mani_skill/agents/robots/panda/panda.py:237-269    is_grasping, is_static
+"""
+import importlib.util
+import os
+import sys
+import types
+from types import SimpleNamespace
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_golden.npz")
+
+
+def stub(name, **attrs):
+    m = MagicMock(name=name)
+    m.__name__ = name
+    m.__path__ = []
+    m.__all__ = []
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def pkg(name):
+    m = types.ModuleType(name)
+    m.__path__ = []
+    sys.modules[name] = m
+    parent, _, child = name.rpartition(".")
+    if parent:
+        setattr(sys.modules[parent], child, m)
+    return m
+
+
+def load(modname, rel):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    parent, _, child = modname.rpartition(".")
+    spec.loader.exec_module(mod)
+    if parent in sys.modules:
+        setattr(sys.modules[parent], child, mod)
+    return mod
+
+
+def main():
+    class FakeSapienPose:  # only used in isinstance checks
+        pass
+
+    for n in ["sapien", "sapien.physx", "sapien.render", "sapien.wrapper", "sapien.wrapper.urdf_loader", "sapien.utils", "gymnasium",
+              "gymnasium.spaces", "transforms3d", "transforms3d.euler", "transforms3d.quaternions"]:
+        stub(n)
+    sys.modules["sapien"].Pose = FakeSapienPose
+    sys.modules["gymnasium"].__version__ = "0.29.1"
+    for p in ["mani_skill", "mani_skill.utils", "mani_skill.utils.geometry", "mani_skill.utils.structs", "mani_skill.envs",
+              "mani_skill.envs.utils", "mani_skill.envs.tasks", "mani_skill.envs.tasks.tabletop", "mani_skill.agents",
+              "mani_skill.agents.robots", "mani_skill.agents.robots.panda", "mani_skill.vector", "mani_skill.vector.wrappers"]:
+        pkg(p)
+    sys.modules["mani_skill"].PACKAGE_ASSET_DIR = "/nonexistent"
+    stub("mani_skill.utils.logging_utils")
+    stub("mani_skill.vector.wrappers.gymnasium")
+    stub("mani_skill.render", SAPIEN_RENDER_SYSTEM="3.0")
+    rc = load("mani_skill.utils.geometry.rotation_conversions", "mani_skill/utils/geometry/rotation_conversions.py")
+    load("mani_skill.utils.structs.types", "mani_skill/utils/structs/types.py")
+    common = load("mani_skill.utils.common", "mani_skill/utils/common.py")
+    gym_utils = load("mani_skill.utils.gym_utils", "mani_skill/utils/gym_utils.py")
+    pose_mod = load("mani_skill.utils.structs.pose", "mani_skill/utils/structs/pose.py")
+    sapien_utils = load("mani_skill.utils.sapien_utils", "mani_skill/utils/sapien_utils.py")
+    rnd = pkg("mani_skill.envs.utils.randomization")
+    rpose = load("mani_skill.envs.utils.randomization.pose", "mani_skill/envs/utils/randomization/pose.py")
+    rnd.random_quaternions = rpose.random_quaternions
+    Pose = pose_mod.Pose
+    G = {}
+    g = torch.Generator().manual_seed(20240922)
+    # ---- rotations
+    qa = torch.nn.functional.normalize(torch.randn(32, 4, generator=g), dim=-1)
+    qb = torch.nn.functional.normalize(torch.randn(32, 4, generator=g), dim=-1)
+    v = torch.randn(32, 3, generator=g)
+    G["rot_qa"], G["rot_qb"], G["rot_v"] = qa, qb, v
+    G["rot_qmul"] = rc.quaternion_raw_multiply(qa, qb)
+    G["rot_qapply"] = rc.quaternion_apply(qa, v)
+    G["rot_q2m"] = rc.quaternion_to_matrix(qa)
+    G["rot_m2q"] = rc.matrix_to_quaternion(rc.quaternion_to_matrix(qa))
+    eul = torch.rand(32, 3, generator=g) * 6.28
+    G["rot_euler"] = eul
+    G["rot_euler_xyz_m"] = rc.euler_angles_to_matrix(eul, "XYZ")
+    # ---- random_quaternions under a fixed global seed (CPU generator)
+    torch.manual_seed(777)
+    G["randq_lockxy"] = rpose.random_quaternions(16, lock_x=True, lock_y=True)
+    torch.manual_seed(778)
+    G["randq_free"] = rpose.random_quaternions(16)
+    # ---- clip_and_scale_action
+    a = torch.randn(8, 7, generator=g) * 1.5
+    low, high = torch.full((7,), -0.1), torch.full((7,), 0.1)
+    G["cs_action"], G["cs_low"], G["cs_high"] = a, low, high
+    G["cs_out"] = gym_utils.clip_and_scale_action(a, low, high)
+    G["cs_out_grip"] = gym_utils.clip_and_scale_action(a[:, :1], torch.tensor([-0.01]), torch.tensor([0.04]))
+    # ---- flatten_state_dict / compute_angle_between
+    d = dict(agent=dict(qpos=torch.randn(4, 9, generator=g), qvel=torch.randn(4, 9, generator=g)),
+             extra=dict(is_grasped=torch.tensor([True, False, True, False]), tcp_pose=torch.randn(4, 7, generator=g), goal_pos=torch.randn(4, 3, generator=g)))
+    G["fl_qpos"], G["fl_qvel"], G["fl_isg"], G["fl_tcp"], G["fl_goal"] = d["agent"]["qpos"], d["agent"]["qvel"], d["extra"]["is_grasped"], d["extra"]["tcp_pose"], d["extra"]["goal_pos"]
+    G["fl_out"] = common.flatten_state_dict(d, use_torch=True)
+    x1, x2 = torch.randn(16, 3, generator=g), torch.randn(16, 3, generator=g)
+    x2[3] = 0
+    G["ang_x1"], G["ang_x2"] = x1, x2
+    G["ang_out"] = common.compute_angle_between(x1, x2)
+    # ---- look_at (PickCube sensor + human cameras, PegInsertion base camera)
+    for name, eye, tgt in [("pick_sensor", [0.3, 0, 0.6], [-0.1, 0, 0.1]), ("pick_human", [0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), ("peg_sensor", [0, -0.3, 0.2], [0, 0, 0.1])]:
+        G["lookat_" + name] = sapien_utils.look_at(eye, tgt).raw_pose[0]
+    # ---- Pose algebra
+    pa = Pose.create_from_pq(torch.randn(8, 3, generator=g), qa[:8])
+    pb = Pose.create_from_pq(torch.randn(8, 3, generator=g), qb[:8])
+    G["pose_a"], G["pose_b"] = pa.raw_pose, pb.raw_pose
+    G["pose_mul"] = (pa * pb).raw_pose
+    G["pose_inv"] = pa.inv().raw_pose
+    G["pose_mat"] = pa.to_transformation_matrix()
+    # ---- PickCube task logic on synthetic states
+    stub("mani_skill.agents.robots", SO100=object, Fetch=object, Panda=object, WidowXAI=object, XArm6Robotiq=object)
+    sapien_env = stub("mani_skill.envs.sapien_env")
+    sapien_env.BaseEnv = type("BaseEnv", (), {})
+    stub("mani_skill.sensors")
+    stub("mani_skill.sensors.camera")
+    stub("mani_skill.utils.building")
+    reg = stub("mani_skill.utils.registration")
+    reg.register_env = lambda *a, **k: (lambda cls: cls)
+    stub("mani_skill.utils.scene_builder")
+    stub("mani_skill.utils.scene_builder.table")
+    load("mani_skill.envs.tasks.tabletop.pick_cube_cfgs", "mani_skill/envs/tasks/tabletop/pick_cube_cfgs.py")
+    pc = load("mani_skill.envs.tasks.tabletop.pick_cube", "mani_skill/envs/tasks/tabletop/pick_cube.py")
+    n = 12
+    cube_p = torch.randn(n, 3, generator=g) * 0.1
+    goal_p = cube_p + torch.randn(n, 3, generator=g) * 0.03
+    goal_p[:3] = cube_p[:3] + 0.001
+    tcp_raw = torch.hstack([cube_p + torch.randn(n, 3, generator=g) * 0.05, qa[:n]])
+    cube_raw = torch.hstack([cube_p, qb[:n]])
+    qvel = torch.randn(n, 9, generator=g) * 0.3
+    qvel[:2] *= 0.01
+    is_grasped = torch.tensor([True, False] * (n // 2))
+    is_static = torch.max(torch.abs(qvel[:, :-2]), 1)[0] <= 0.2
+    fake = SimpleNamespace(
+        cube=SimpleNamespace(pose=Pose.create(cube_raw)), goal_site=SimpleNamespace(pose=Pose.create_from_pq(goal_p)),
+        agent=SimpleNamespace(tcp_pose=Pose.create(tcp_raw), robot=SimpleNamespace(get_qvel=lambda: qvel),
+                              is_grasping=lambda obj: is_grasped, is_static=lambda thr: is_static),
+        goal_thresh=0.025, robot_uids="panda", obs_mode="state")
+    info = pc.PickCubeEnv.evaluate(fake)
+    fake.compute_dense_reward = lambda obs, action, info: pc.PickCubeEnv.compute_dense_reward(fake, obs, action, info)
+    G["pc_cube"], G["pc_goal"], G["pc_tcp"], G["pc_qvel"], G["pc_is_grasped"] = cube_raw, goal_p, tcp_raw, qvel, is_grasped
+    G["pc_success"], G["pc_is_obj_placed"], G["pc_is_robot_static"] = info["success"], info["is_obj_placed"], info["is_robot_static"]
+    G["pc_reward"] = pc.PickCubeEnv.compute_dense_reward(fake, None, None, info)
+    G["pc_reward_norm"] = pc.PickCubeEnv.compute_normalized_dense_reward(fake, None, None, info)
+    extra = pc.PickCubeEnv._get_obs_extra(fake, info)
+    G["pc_extra_flat"] = common.flatten_state_dict(extra, use_torch=True)
+    # ---- Panda.is_grasping / is_static
+    base_agent = stub("mani_skill.agents.base_agent")
+    base_agent.BaseAgent = type("BaseAgent", (), {})
+    base_agent.Keyframe = lambda **k: SimpleNamespace(**k)
+    stub("mani_skill.agents.controllers")
+    regs = stub("mani_skill.agents.registration")
+    regs.register_agent = lambda *a, **k: (lambda cls: cls)
+    stub("mani_skill.utils.structs.actor")
+    sys.modules["sapien"].Pose = lambda *a, **k: None
+    panda = load("mani_skill.agents.robots.panda.panda", "mani_skill/agents/robots/panda/panda.py")
+    lf = torch.randn(n, 3, generator=g) * 3
+    rf = torch.randn(n, 3, generator=g) * 3
+    lf[:2] = 0
+    f1 = Pose.create_from_pq(torch.randn(n, 3, generator=g), qa[8:8 + n])
+    f2 = Pose.create_from_pq(torch.randn(n, 3, generator=g), qb[8:8 + n])
+    fl1, fl2 = SimpleNamespace(pose=f1), SimpleNamespace(pose=f2)
+    fake_agent = SimpleNamespace(finger1_link=fl1, finger2_link=fl2, robot=SimpleNamespace(get_qvel=lambda: qvel),
+                                 scene=SimpleNamespace(get_pairwise_contact_forces=lambda a, b: lf if a is fl1 else rf))
+    G["pg_lforce"], G["pg_rforce"], G["pg_f1"], G["pg_f2"] = lf, rf, f1.raw_pose, f2.raw_pose
+    G["pg_is_grasping"] = panda.Panda.is_grasping(fake_agent, None)
+    G["pg_is_static"] = panda.Panda.is_static(fake_agent, 0.2)
+    np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
+    print("wrote", OUT, len(G), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU: the host-side mirror against golden vectors produced by the REFERENCE's own functions
+(tests/golden/make_golden.py, run in the build container where /root/reference exists; the .npz is committed)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from maniskill_b200 import utils as U
+from maniskill_b200.structs import Pose
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_golden.npz"))
+T = lambda k: torch.from_numpy(G[k])
+
+
+def close(a, b, tol=1e-6):
+    a = a.numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    assert np.allclose(a, b, atol=tol, rtol=tol), np.abs(a - b).max()
+
+
+def test_rotation_conversions():
+    qa, qb, v = T("rot_qa"), T("rot_qb"), T("rot_v")
+    close(U.quat_mul(qa, qb), G["rot_qmul"])
+    close(U.quat_apply(qa, v), G["rot_qapply"])
+    close(U.quat_to_matrix(qa), G["rot_q2m"])
+    close(U.matrix_to_quat(U.quat_to_matrix(qa)), G["rot_m2q"])
+    close(U.euler_xyz_to_matrix(T("rot_euler")), G["rot_euler_xyz_m"])
+
+
+def test_random_quaternions_same_stream():
+    torch.manual_seed(777)
+    close(U.random_quaternions(16, lock_x=True, lock_y=True), G["randq_lockxy"])
+    torch.manual_seed(778)
+    got = U.random_quaternions(16).numpy()
+    ref = G["randq_free"]
+    assert np.allclose(np.minimum(np.abs(got - ref).max(1), np.abs(got + ref).max(1)), 0, atol=1e-6)
+
+
+def test_clip_and_scale_action():
+    close(U.clip_and_scale_action(T("cs_action"), T("cs_low"), T("cs_high")), G["cs_out"])
+    close(U.clip_and_scale_action(T("cs_action")[:, :1], torch.tensor([-0.01]), torch.tensor([0.04])), G["cs_out_grip"])
+
+
+def test_flatten_and_angle():
+    d = dict(agent=dict(qpos=T("fl_qpos"), qvel=T("fl_qvel")), extra=dict(is_grasped=T("fl_isg"), tcp_pose=T("fl_tcp"), goal_pos=T("fl_goal")))
+    out = U.flatten_state_dict(d)
+    assert out.dtype == torch.float32
+    close(out, G["fl_out"])
+    close(U.compute_angle_between(T("ang_x1"), T("ang_x2")), G["ang_out"])
+
+
+def test_look_at():
+    for name, eye, tgt in [("pick_sensor", [0.3, 0, 0.6], [-0.1, 0, 0.1]), ("pick_human", [0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), ("peg_sensor", [0, -0.3, 0.2], [0, 0, 0.1])]:
+        close(U.look_at(eye, tgt), G["lookat_" + name], 1e-6)
+
+
+def test_pose_algebra():
+    a, b = Pose(T("pose_a")), Pose(T("pose_b"))
+    close((a * b).raw_pose, G["pose_mul"])
+    close(a.inv().raw_pose, G["pose_inv"])
+    close(a.to_transformation_matrix(), G["pose_mat"])
+
+
+def _fake_pick_cube():
+    from maniskill_b200.envs.pick_cube import PickCubeEnv
+    qvel = T("pc_qvel")
+    isg = T("pc_is_grasped")
+    agent = SimpleNamespace(tcp_pose=Pose(T("pc_tcp")), robot=SimpleNamespace(get_qvel=lambda: qvel),
+                            is_grasping=lambda obj: isg, is_static=lambda thr: torch.max(torch.abs(qvel[:, :-2]), 1)[0] <= thr)
+    fake = SimpleNamespace(cube=SimpleNamespace(pose=Pose(T("pc_cube"))), goal_site=SimpleNamespace(pose=Pose(torch.hstack([T("pc_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(len(qvel), 4)]))),
+                           agent=agent, goal_thresh=0.025, obs_mode="state")
+    return PickCubeEnv, fake
+
+
+def test_pick_cube_evaluate_reward_obs():
+    cls, fake = _fake_pick_cube()
+    info = cls.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["pc_success"])
+    assert np.array_equal(info["is_obj_placed"].numpy(), G["pc_is_obj_placed"])
+    assert np.array_equal(info["is_robot_static"].numpy(), G["pc_is_robot_static"])
+    close(cls.compute_dense_reward(fake, None, None, info), G["pc_reward"])
+    fake.compute_dense_reward = lambda obs, action, info: cls.compute_dense_reward(fake, obs, action, info)
+    close(cls.compute_normalized_dense_reward(fake, None, None, info), G["pc_reward_norm"])
+    close(U.flatten_state_dict(cls._get_obs_extra(fake, info)), G["pc_extra_flat"])
+
+
+def test_panda_is_grasping_and_static():
+    from maniskill_b200.agents import Panda
+    lf, rf = T("pg_lforce"), T("pg_rforce")
+    f1, f2 = SimpleNamespace(pose=Pose(T("pg_f1"))), SimpleNamespace(pose=Pose(T("pg_f2")))
+    qvel = T("pc_qvel")
+    fake = SimpleNamespace(finger1_link=f1, finger2_link=f2, robot=SimpleNamespace(get_qvel=lambda: qvel),
+                           scene=SimpleNamespace(get_pairwise_contact_forces=lambda a, b: lf if a is f1 else rf))
+    assert np.array_equal(Panda.is_grasping(fake, None).numpy(), G["pg_is_grasping"])
+    assert np.array_equal(Panda.is_static(fake, 0.2).numpy(), G["pg_is_static"])
