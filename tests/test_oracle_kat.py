@@ -1,0 +1,156 @@
+"""CPU: known-answer tests that pin the oracle (PhysX is absent, so the physics restatement is
+anchored on analytic results instead of golden vectors)."""
+import numpy as np
+import pytest
+
+from maniskill_b200.model import (SHAPE_BOX, SHAPE_PLANE, SHAPE_SPHERE, ActorRec, ArticulationRec, SceneDesc, ShapeRec, SimParams, pose7)
+from oracle.oracle import OracleWorld, collide
+
+DT = 0.01
+G = 9.81
+
+
+def link(name, parent, jtype, p, axis, mass, com=(0, 0, 0), inertia=(1e-3, 1e-3, 1e-3, 0, 0, 0), lower=-1e30, upper=1e30):
+    return dict(name=name, parent=parent, mass=mass, com=list(com), inertia=list(inertia), collisions=[],
+                joint=dict(name=name + "_joint", type=jtype, p=list(p), q=[1, 0, 0, 0], axis=list(axis), lower=lower, upper=upper,
+                           effort=0, damping=0, friction=0))
+
+
+def root_link():
+    return dict(name="base", parent=-1, mass=1.0, com=[0, 0, 0], inertia=[1, 1, 1, 0, 0, 0], collisions=[],
+                joint=dict(name="", type="fixed", p=[0, 0, 0], q=[1, 0, 0, 0], axis=[1, 0, 0], lower=0, upper=0, effort=0, damping=0, friction=0))
+
+
+def ground(scene, mu=0.3):
+    scene.add_actor(ActorRec("ground", "static", [ShapeRec(SHAPE_PLANE, pose7([0, 0, 0], [0.7071068, 0, -0.7071068, 0]), mu=mu)], pose7()))
+
+
+def test_free_fall_matches_substepped_euler():
+    s = SceneDesc(1, SimParams())
+    s.add_actor(ActorRec("ball", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([0.05, 0, 0]))], pose7([0, 0, 10.0]), angular_damping=0.0))
+    w = OracleWorld(s.compile(), "f64")
+    n = 50
+    w.step(n)
+    b = w.get_bodies()[0, 0]
+    assert b[9] == pytest.approx(-G * DT * n, rel=1e-6)  # model tables are float32 (dt, g)
+    # positions integrate the velocity of each of the 15 sub-steps (h = dt/15): per step dx = dt v + g dt^2 (15+1)/(2*15)
+    assert b[2] == pytest.approx(10.0 - G * DT * DT * (n * (n - 1) / 2 + n * 16 / 30), rel=1e-6)
+
+
+def test_pd_drive_is_the_implicit_recurrence():
+    m, kp, kd = 2.0, 1e3, 1e2
+    robot = dict(name="slider", links=[root_link(), link("mass", 0, "prismatic", (0, 0, 0), (1, 0, 0), m)], disabled_collision_pairs=[])
+    s = SceneDesc(1, SimParams())
+    s.add_articulation(ArticulationRec("slider", robot, pose7(), drive={"mass_joint": (kp, kd, 1e10)}))
+    w = OracleWorld(s.compile(), "f64")
+    w.set_joint("target_qpos", [[0.3]])
+    q, v = 0.0, 0.0
+    for _ in range(60):
+        w.step(1)
+        v_new = (m * v + DT * (kp * (0.3 - q))) / (m + DT * kd + DT * DT * kp)  # implicit spring-damper, target velocity 0
+        q += DT * v + (v_new - v) * DT * 16 / 30  # the acceleration is applied over 15 sub-steps
+        v = v_new
+        assert w.get_joint("qpos")[0, 0] == pytest.approx(q, abs=1e-6)
+    assert abs(q - 0.3) < 0.02
+
+
+def test_drive_force_limit_caps_acceleration():
+    m, fl = 2.0, 5.0
+    robot = dict(name="slider", links=[root_link(), link("mass", 0, "prismatic", (0, 0, 0), (1, 0, 0), m)], disabled_collision_pairs=[])
+    s = SceneDesc(1, SimParams())
+    s.add_articulation(ArticulationRec("slider", robot, pose7(), drive={"mass_joint": (1e3, 1e2, fl)}))
+    w = OracleWorld(s.compile(), "f64")
+    w.set_joint("target_qpos", [[10.0]])
+    w.step(10)
+    assert w.get_joint("qvel")[0, 0] == pytest.approx(fl / m * DT * 10, rel=1e-6)
+
+
+def test_pendulum_period_and_energy():
+    L, m = 0.5, 1.0
+    I = 1e-4
+    robot = dict(name="pend", links=[root_link(), link("bob", 0, "revolute", (0, 0, 0), (0, 1, 0), m, com=(0, 0, -L), inertia=(I, I, I, 0, 0, 0))],
+                 disabled_collision_pairs=[])
+    s = SceneDesc(1, SimParams(sim_freq=1000))
+    s.add_articulation(ArticulationRec("pend", robot, pose7(), disable_gravity=False))
+    w = OracleWorld(s.compile(), "f64")
+    th0 = 0.1
+    w.set_joint("qpos", [[th0]])
+    qs = []
+    for _ in range(3000):
+        w.step(1)
+        qs.append(w.get_joint("qpos")[0, 0])
+    qs = np.array(qs)
+    zc = np.where((qs[:-1] > 0) & (qs[1:] <= 0))[0]
+    period = (zc[1] - zc[0]) * 1e-3
+    analytic = 2 * np.pi * np.sqrt((I + m * L * L) / (m * G * L))
+    assert period == pytest.approx(analytic, rel=5e-3)
+    assert np.abs(qs).max() == pytest.approx(th0, rel=2e-2)  # semi-implicit Euler: bounded energy error
+
+
+def test_box_rests_on_plane_and_weighs_mg():
+    s = SceneDesc(1, SimParams())
+    ground(s)
+    s.add_actor(ActorRec("box", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([0.05, 0.05, 0.05]))], pose7([0, 0, 0.05])))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    w.step(200)
+    b = w.get_bodies()[0, 0]
+    assert abs(b[2] - 0.05) < 1e-3 and np.abs(b[:2]).max() < 1e-5 and np.abs(b[7:]).max() < 1e-2
+    mass = 1000 * 0.1**3
+    imp = w.pair_impulse(cm.actor_rows["box"], -1)
+    assert imp[0, 2] == pytest.approx(mass * G * DT, rel=1e-3)
+
+
+@pytest.mark.parametrize("angle_deg,slides", [(10.0, False), (25.0, True)])
+def test_coulomb_threshold(angle_deg, slides):
+    """mu = 0.3 on both -> combined 0.3: tan(16.7 deg) = 0.3.  Tilt gravity instead of the plane."""
+    th = np.deg2rad(angle_deg)
+    s = SceneDesc(1, SimParams(gravity=(G * np.sin(th), 0, -G * np.cos(th))))
+    ground(s)
+    s.add_actor(ActorRec("box", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([0.05, 0.05, 0.02]))], pose7([0, 0, 0.02])))
+    w = OracleWorld(s.compile(), "f64")
+    w.step(100)
+    b = w.get_bodies()[0, 0]
+    if slides:
+        a = G * (np.sin(th) - 0.3 * np.cos(th))
+        assert b[7] == pytest.approx(a * 1.0, rel=0.05)
+    else:
+        assert abs(b[0]) < 1e-3 and abs(b[7]) < 1e-3
+
+
+def test_momentum_is_conserved_in_a_collision():
+    s = SceneDesc(1, SimParams(gravity=(0, 0, 0)))
+    for i, (x, vx) in enumerate([(-0.2, 1.0), (0.2, -0.5)]):
+        s.add_actor(ActorRec(f"ball{i}", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([0.05, 0, 0]), density=1000 * (1 + i))],
+                             pose7([x, 0, 0]), angular_damping=0.0))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    b = w.get_bodies()
+    b[0, 0, 7], b[0, 1, 7] = 1.0, -0.5
+    w.set_bodies(b)
+    masses = cm.arrays["fb_mass"]
+    p0 = masses[0] * 1.0 + masses[1] * -0.5
+    w.step(60)
+    b = w.get_bodies()[0]
+    assert masses[0] * b[0, 7] + masses[1] * b[1, 7] == pytest.approx(p0, rel=1e-6)
+    assert b[0, 7] <= b[1, 7] + 1e-6  # they no longer approach (restitution 0)
+
+
+def test_narrowphase_known_answers():
+    box = dict(type=SHAPE_BOX, pose=[0, 0, 0.049, 1, 0, 0, 0], size=[0.05, 0.05, 0.05])
+    plane = dict(type=SHAPE_PLANE, pose=[0, 0, 0, 0.7071068, 0, -0.7071068, 0])
+    c = collide(box, plane)
+    assert len(c) == 4 and np.allclose(c[:, 6], -0.001, atol=1e-7) and np.allclose(c[:, 3:6], [0, 0, 1], atol=1e-6)
+    b2 = dict(type=SHAPE_BOX, pose=[0, 0, 0.1 + 0.002, 1, 0, 0, 0], size=[0.05, 0.05, 0.05])
+    b1 = dict(type=SHAPE_BOX, pose=[0, 0, 0, 1, 0, 0, 0], size=[0.05, 0.05, 0.05])
+    c = collide(b2, b1)
+    assert len(c) == 4 and np.allclose(c[:, 6], 0.002, atol=1e-6) and np.allclose(c[:, 3:6], [0, 0, 1], atol=1e-6)
+    sph_a = dict(type=SHAPE_SPHERE, pose=[0.0, 0, 0, 1, 0, 0, 0], size=[0.05, 0, 0])
+    sph_b = dict(type=SHAPE_SPHERE, pose=[0.12, 0, 0, 1, 0, 0, 0], size=[0.05, 0, 0])
+    c = collide(sph_a, sph_b)
+    assert len(c) == 1 and c[0, 6] == pytest.approx(0.02, abs=1e-6) and np.allclose(c[0, 3:6], [-1, 0, 0], atol=1e-6)
+    # GJK/EPA: an octahedron hull penetrating a box by 5 mm along z
+    octa = np.array([[0.05, 0, 0], [-0.05, 0, 0], [0, 0.05, 0], [0, -0.05, 0], [0, 0, 0.05], [0, 0, -0.05]], dtype=np.float32)
+    hull = dict(type=4, pose=[0, 0, 0.095, 1, 0, 0, 0], size=[0, 0, 0], verts=octa)
+    c = collide(hull, b1)
+    assert len(c) == 1 and c[0, 6] == pytest.approx(-0.005, abs=1e-5) and np.allclose(c[0, 3:6], [0, 0, 1], atol=1e-4)
