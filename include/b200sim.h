@@ -234,6 +234,49 @@ int32_t b2s_camera_group_create(uint64_t world, const B2SCameraDesc* cams, int32
                                 uint64_t* group, B2SRenderTargets* out);
 int32_t b2s_render(uint64_t world, uint64_t group, void* stream);
 
+/*
+ * Fused control step for the pick-and-place task family (PickCube-v1): what BaseEnv.step() does between receiving the
+ * action and returning (obs, reward, terminated, truncated, info) -- envs/sapien_env.py:1042-1132 -- as three launches:
+ *   1. joint-space controller: clip/scale the normalised action, delta or absolute targets, mimic joints
+ *      (agents/controllers/pd_joint_pos.py:76-93,207-228, utils/gym_utils.py:104-108) -> target_qpos
+ *   2. `substeps` physics steps + fetch (b2s_step)
+ *   3. epilogue: is_grasped from the finger/object contact impulses (agents/robots/panda/panda.py:237-265), is_obj_placed,
+ *      is_robot_static, success (envs/tasks/tabletop/pick_cube.py:147-159), dense reward (:161-191), flattened state
+ *      observation (:132-145 + agents/base_agent.py:339-347), elapsed_steps += 1, truncation (utils/registration.py:160-168)
+ * The python path (maniskill_b200/envs) computes the same values with torch ops and is kept as the checked fallback.
+ */
+typedef struct B2SJointController {
+  int32_t n_action;             /* action width */
+  const int32_t* dof_action;    /* [n_dof] action column driving this dof, or -1 (target untouched) */
+  const int32_t* dof_use_delta; /* [n_dof] 1: target = qpos + scaled action, 0: target = scaled action */
+  const int32_t* dof_normalize; /* [n_dof] 1: clip to [-1,1] and scale into [low, high] */
+  const float* dof_low;         /* [n_dof] */
+  const float* dof_high;        /* [n_dof] */
+} B2SJointController;
+
+typedef struct B2SPickTask {
+  int32_t tcp_row, obj_row, goal_row, lfinger_row, rfinger_row; /* exposed body rows */
+  float goal_thresh;     /* pick_cube.py:43 */
+  float min_force;       /* panda.py:237 (0.5 N) */
+  float max_angle_deg;   /* panda.py:237 (85) */
+  float static_thresh;   /* pick_cube.py:154 (0.2) */
+  int32_t n_static_dof;  /* leading dofs checked by is_static / static reward (qvel[..., :-2]) */
+  int32_t max_episode_steps;
+  int32_t normalized_reward; /* 1: reward / 5 */
+} B2SPickTask;
+
+typedef struct B2SPickOutputs {
+  float* obs;          /* [n_envs, 2*n_dof + 24] : qpos, qvel, is_grasped, tcp_pose7, goal_pos3, obj_pose7, tcp_to_obj3, obj_to_goal3 */
+  float* reward;       /* [n_envs] */
+  uint8_t* flags;      /* [n_envs, 6] : success, is_obj_placed, is_robot_static, is_grasped, terminated, truncated */
+  int32_t* elapsed;    /* [n_envs] in/out */
+} B2SPickOutputs;
+
+int32_t b2s_pick_task_create(uint64_t world, const B2SJointController* ctrl, const B2SPickTask* task, uint64_t* handle);
+/* actions: device [n_envs, n_action] float32, or NULL to step without a new action */
+int32_t b2s_pick_task_step(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

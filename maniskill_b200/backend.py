@@ -46,6 +46,21 @@ class B2SRenderTargets(C.Structure):
     _fields_ = [("color", C.c_void_p), ("position_seg", C.c_void_p)]
 
 
+class B2SJointController(C.Structure):
+    _fields_ = [("n_action", C.c_int32), ("dof_action", C.c_void_p), ("dof_use_delta", C.c_void_p), ("dof_normalize", C.c_void_p),
+                ("dof_low", C.c_void_p), ("dof_high", C.c_void_p)]
+
+
+class B2SPickTask(C.Structure):
+    _fields_ = [("tcp_row", C.c_int32), ("obj_row", C.c_int32), ("goal_row", C.c_int32), ("lfinger_row", C.c_int32), ("rfinger_row", C.c_int32),
+                ("goal_thresh", C.c_float), ("min_force", C.c_float), ("max_angle_deg", C.c_float), ("static_thresh", C.c_float),
+                ("n_static_dof", C.c_int32), ("max_episode_steps", C.c_int32), ("normalized_reward", C.c_int32)]
+
+
+class B2SPickOutputs(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p), ("elapsed", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -70,13 +85,15 @@ def load_library():
     lib.b2s_contact_query_run.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.b2s_camera_group_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(B2SRenderTargets)]
     lib.b2s_render.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.b2s_pick_task_create.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.b2s_pick_task_step.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["b2s_last_error", "b2s_version", "b2s_world_create", "b2s_world_destroy", "b2s_world_buffers", "b2s_step",
                     "b2s_apply", "b2s_fetch", "b2s_update_kinematics", "b2s_contact_query_create", "b2s_contact_query_run",
-                    "b2s_camera_group_create", "b2s_render"]
+                    "b2s_camera_group_create", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step"]
 
 
 class _DevArray:
@@ -192,6 +209,28 @@ class World:
         _check(self.lib, self.lib.b2s_contact_query_run(self.h, q, C.c_void_p(out.data_ptr()), self._stream()))
         self.kernel_launches += 1
         return out
+
+    # ------------------------------------------------------------------ fused control step (pick task family)
+    def create_pick_task(self, dof_action, dof_use_delta, dof_normalize, dof_low, dof_high, n_action, rows: dict, goal_thresh,
+                         n_static_dof, max_episode_steps, normalized_reward=True, min_force=0.5, max_angle_deg=85.0, static_thresh=0.2):
+        ctrl = B2SJointController()
+        keep = [np.ascontiguousarray(np.asarray(dof_action, dtype=np.int32)), np.ascontiguousarray(np.asarray(dof_use_delta, dtype=np.int32)),
+                np.ascontiguousarray(np.asarray(dof_normalize, dtype=np.int32)), np.ascontiguousarray(np.asarray(dof_low, dtype=np.float32)),
+                np.ascontiguousarray(np.asarray(dof_high, dtype=np.float32))]
+        ctrl.n_action = int(n_action)
+        ctrl.dof_action, ctrl.dof_use_delta, ctrl.dof_normalize, ctrl.dof_low, ctrl.dof_high = [a.ctypes.data_as(C.c_void_p) for a in keep]
+        task = B2SPickTask(int(rows["tcp"]), int(rows["obj"]), int(rows["goal"]), int(rows["lfinger"]), int(rows["rfinger"]), float(goal_thresh),
+                           float(min_force), float(max_angle_deg), float(static_thresh), int(n_static_dof), int(max_episode_steps or 0),
+                           1 if normalized_reward else 0)
+        h = C.c_uint64(0)
+        _check(self.lib, self.lib.b2s_pick_task_create(self.h, C.byref(ctrl), C.byref(task), C.byref(h)))
+        return h
+
+    def pick_task_step(self, handle, actions, substeps, obs, reward, flags, elapsed):
+        out = B2SPickOutputs(obs.data_ptr(), reward.data_ptr(), flags.data_ptr(), elapsed.data_ptr())
+        a = C.c_void_p(actions.data_ptr()) if actions is not None else None
+        _check(self.lib, self.lib.b2s_pick_task_step(self.h, handle, a, int(substeps), C.byref(out), self._stream()))
+        self.kernel_launches += 3 if actions is not None else 2
 
     # ------------------------------------------------------------------ rendering
     def create_camera_group(self, cameras, visuals):

@@ -42,10 +42,18 @@ struct Query {
   int* rows_dev;
 };
 
+struct PickTaskDev {
+  int n_action;
+  int *dof_action, *dof_use_delta, *dof_normalize;
+  float *dof_low, *dof_high;
+  B2SPickTask task;
+};
+
 struct World : b2s::WorldT<DevMem> {
   int device;
   std::vector<Query> queries;
   std::vector<b2s::RasterGroup*> groups;
+  std::vector<PickTaskDev> pick_tasks;
 };
 
 std::mutex g_mu;
@@ -96,6 +104,111 @@ __global__ void query_kernel(b2s::DevModel M, b2s::DevState S, const int* rows, 
     float* w = out + ((size_t)env * nq + q) * 3;
     w[0] = sx; w[1] = sy; w[2] = sz;
   }
+}
+
+// ---- fused control step, launch 1: joint-space controller (pd_joint_pos.py:76-93,207-228; gym_utils.py:104-108).
+// Reads the internal qpos, writes the internal target (what the substep kernel consumes) and the exposed target_qpos.
+__global__ void controller_kernel(b2s::DevModel M, b2s::DevState S, PickTaskDev T, const float* __restrict__ actions) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  const size_t N = M.n_envs;
+  const int md = M.max_dof_per_art;
+  for (int a = 0; a < M.n_art; a++) {
+    int d0 = M.art_dof_start[a], d1 = M.art_dof_start[a + 1];
+    for (int i = d0; i < d1; i++) {
+      int col = T.dof_action[i];
+      if (col < 0) continue;
+      float act = actions[(size_t)env * T.n_action + col];
+      if (T.dof_normalize[i]) {
+        act = fminf(fmaxf(act, -1.f), 1.f);
+        float lo = T.dof_low[i], hi = T.dof_high[i];
+        act = 0.5f * (hi + lo) + 0.5f * (hi - lo) * act;
+      }
+      float tq = T.dof_use_delta[i] ? S.q[i * N + env] + act : act;
+      S.tq[i * N + env] = tq;
+      S.xtq[((size_t)env * M.n_art + a) * md + i - d0] = tq;
+    }
+  }
+}
+
+// ---- fused control step, launch 3: evaluate + reward + observation of the pick task (pick_cube.py:132-191,
+// panda.py:237-269, base_agent.py:339-347).  Reads the freshly fetched exposed buffers, so the python path sees the same data.
+__global__ void pick_epilogue_kernel(b2s::DevModel M, b2s::DevState S, PickTaskDev T, float* __restrict__ obs, float* __restrict__ reward,
+                                     uint8_t* __restrict__ flags, int* __restrict__ elapsed) {
+  using namespace b2s;
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  const size_t N = M.n_envs;
+  const B2SPickTask& K = T.task;
+  const int nr = M.n_rows, nd = M.n_dof, md = M.max_dof_per_art;
+  const float* body = S.body_data + (size_t)env * nr * 13;
+  const float* tcp = body + K.tcp_row * 13;
+  const float* obj = body + K.obj_row * 13;
+  const float* goal = body + K.goal_row * 13;
+  // contact forces finger <-> object (sum of patch impulses / dt, acting on the finger)
+  v3 lf = mk3(0, 0, 0), rf = mk3(0, 0, 0);
+  int nm = S.man_count[env];
+  for (int m = 0; m < nm; m++) {
+    const float* o = S.man + (size_t)(m * 8) * N + env;
+    int a = (int)o[0], b = (int)o[N];
+    v3 imp = mk3(o[2 * N], o[3 * N], o[4 * N]);
+    if (a == K.lfinger_row && b == K.obj_row) lf = lf + imp;
+    else if (a == K.obj_row && b == K.lfinger_row) lf = lf - imp;
+    if (a == K.rfinger_row && b == K.obj_row) rf = rf + imp;
+    else if (a == K.obj_row && b == K.rfinger_row) rf = rf - imp;
+  }
+  float inv_dt = 1.f / M.dt;
+  lf = lf * inv_dt;
+  rf = rf * inv_dt;
+  float lforce = norm(lf), rforce = norm(rf);
+  const float* l13 = body + K.lfinger_row * 13;
+  const float* r13 = body + K.rfinger_row * 13;
+  v3 ldir = col(qmat(mkq(l13[3], l13[4], l13[5], l13[6])), 1);
+  v3 rdir = -col(qmat(mkq(r13[3], r13[4], r13[5], r13[6])), 1);
+  // common.compute_angle_between: normalise (zero stays zero), clip, acos
+  v3 lfn = lforce < 1e-6f ? mk3(0, 0, 0) : lf * (1.f / lforce), rfn = rforce < 1e-6f ? mk3(0, 0, 0) : rf * (1.f / rforce);
+  float ldn = norm(ldir), rdn = norm(rdir);
+  v3 ldu = ldn < 1e-6f ? mk3(0, 0, 0) : ldir * (1.f / ldn), rdu = rdn < 1e-6f ? mk3(0, 0, 0) : rdir * (1.f / rdn);
+  const float rad2deg = 57.29577951308232f;
+  float langle = acosf(fminf(fmaxf(dot(ldu, lfn), -1.f), 1.f)) * rad2deg;
+  float rangle = acosf(fminf(fmaxf(dot(rdu, rfn), -1.f), 1.f)) * rad2deg;
+  bool is_grasped = (lforce >= K.min_force && langle <= K.max_angle_deg) && (rforce >= K.min_force && rangle <= K.max_angle_deg);
+  v3 tcp_p = mk3(tcp[0], tcp[1], tcp[2]), obj_p = mk3(obj[0], obj[1], obj[2]), goal_p = mk3(goal[0], goal[1], goal[2]);
+  float obj_to_goal = norm(goal_p - obj_p);
+  bool is_obj_placed = obj_to_goal <= K.goal_thresh;
+  const float* qv = S.xqd + (size_t)env * M.n_art * md;  // articulation 0 = the robot
+  const float* qp = S.xq + (size_t)env * M.n_art * md;
+  float vmax = 0.f, vsq = 0.f;
+  for (int i = 0; i < K.n_static_dof; i++) { vmax = fmaxf(vmax, fabsf(qv[i])); vsq += qv[i] * qv[i]; }
+  bool is_static = vmax <= K.static_thresh;
+  bool success = is_obj_placed && is_static;
+  // dense reward (pick_cube.py:161-191)
+  float tcp_to_obj = norm(obj_p - tcp_p);
+  float r = 1.f - tanhf(5.f * tcp_to_obj);
+  r += is_grasped ? 1.f : 0.f;
+  r += (1.f - tanhf(5.f * obj_to_goal)) * (is_grasped ? 1.f : 0.f);
+  r += (1.f - tanhf(5.f * sqrtf(vsq))) * (is_obj_placed ? 1.f : 0.f);
+  if (success) r = 5.f;
+  if (K.normalized_reward) r = r / 5.f;
+  reward[env] = r;
+  int el = elapsed[env] + 1;
+  elapsed[env] = el;
+  uint8_t* f = flags + (size_t)env * 6;
+  f[0] = success; f[1] = is_obj_placed; f[2] = is_static; f[3] = is_grasped; f[4] = success;
+  f[5] = (K.max_episode_steps > 0 && el >= K.max_episode_steps) ? 1 : 0;
+  // observation: qpos, qvel, is_grasped, tcp_pose, goal_pos, obj_pose, tcp_to_obj_pos, obj_to_goal_pos
+  int d0 = M.art_dof_start[0], d1 = M.art_dof_start[1], nq = d1 - d0;
+  float* o = obs + (size_t)env * (2 * nq + 24);
+  for (int i = 0; i < nq; i++) { o[i] = qp[i]; o[nq + i] = qv[i]; }
+  o += 2 * nq;
+  o[0] = is_grasped ? 1.f : 0.f;
+  for (int k = 0; k < 7; k++) o[1 + k] = tcp[k];
+  for (int k = 0; k < 3; k++) o[8 + k] = goal[k];
+  for (int k = 0; k < 7; k++) o[11 + k] = obj[k];
+  v3 t2o = obj_p - tcp_p, o2g = goal_p - obj_p;
+  o[18] = t2o.x; o[19] = t2o.y; o[20] = t2o.z;
+  o[21] = o2g.x; o[22] = o2g.y; o[23] = o2g.z;
+  (void)nd;
 }
 
 }  // namespace
@@ -245,6 +358,42 @@ int32_t b2s_render(uint64_t world, uint64_t group, void* stream) {
   if (!w || group < 1 || group > w->groups.size()) return fail(B2S_ERR_INVALID, "bad camera group");
   const char* err = b2s::raster_run(w->M, w->S, w->groups[group - 1], (cudaStream_t)stream);
   if (err) return fail(B2S_ERR_CUDA, "%s", err);
+  return B2S_OK;
+}
+
+int32_t b2s_pick_task_create(uint64_t world, const B2SJointController* c, const B2SPickTask* task, uint64_t* handle) {
+  World* w = get(world);
+  if (!w || !c || !task || !handle) return fail(B2S_ERR_INVALID, "bad pick task");
+  int nd = w->M.n_dof, nr = w->M.n_rows;
+  const int rows[5] = {task->tcp_row, task->obj_row, task->goal_row, task->lfinger_row, task->rfinger_row};
+  for (int r : rows)
+    if (r < 0 || r >= nr) return fail(B2S_ERR_INVALID, "pick task row out of range");
+  if (w->M.n_art < 1 || task->n_static_dof > w->M.max_dof_per_art) return fail(B2S_ERR_INVALID, "pick task needs the robot as articulation 0");
+  PickTaskDev T;
+  T.n_action = c->n_action;
+  T.task = *task;
+  T.dof_action = (int*)w->up(c->dof_action, nd); T.dof_use_delta = (int*)w->up(c->dof_use_delta, nd);
+  T.dof_normalize = (int*)w->up(c->dof_normalize, nd);
+  T.dof_low = (float*)w->up(c->dof_low, nd); T.dof_high = (float*)w->up(c->dof_high, nd);
+  if (!T.dof_action || !T.dof_use_delta || !T.dof_normalize || !T.dof_low || !T.dof_high) return fail(B2S_ERR_CUDA, "allocation failed");
+  w->pick_tasks.push_back(T);
+  *handle = w->pick_tasks.size();
+  return B2S_OK;
+}
+
+int32_t b2s_pick_task_step(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
+                           void* stream) {
+  World* w = get(world);
+  if (!w || handle < 1 || handle > w->pick_tasks.size() || !out || !out->obs || !out->reward || !out->flags || !out->elapsed)
+    return fail(B2S_ERR_INVALID, "bad pick task step");
+  const PickTaskDev& T = w->pick_tasks[handle - 1];
+  cudaStream_t st = (cudaStream_t)stream;
+  int N = w->M.n_envs;
+  if (actions_dev) controller_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, actions_dev);
+  int32_t rc = b2s_step(world, substeps, 0xFFFFFFFFu, stream);
+  if (rc != B2S_OK) return rc;
+  pick_epilogue_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->reward, out->flags, out->elapsed);
+  CK(cudaGetLastError());
   return B2S_OK;
 }
 

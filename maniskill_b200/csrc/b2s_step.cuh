@@ -265,6 +265,32 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
         if (dot(ex, ex) > lim * lim) cull = true;
       }
       if (cull) continue;
+      // oriented box against oriented box on the six face axes (a lower bound of the true distance): robot links
+      // hovering a few centimetres above the table stop here instead of running GJK on 64-vertex hulls
+      {
+        v3 cA = mk3(0, 0, 0), hA, cB = mk3(0, 0, 0), hB;
+        if (ta == SH_BOX) hA = Ssize[a];
+        else if (ta == SH_SPHERE) hA = mk3(Ssize[a].x, Ssize[a].x, Ssize[a].x);
+        else if (ta == SH_CAPSULE) hA = mk3(Ssize[a].x + Ssize[a].y, Ssize[a].x, Ssize[a].x);
+        else { const float* bx = M.hull_aabb + 6 * M.shape_hull[a]; cA = mk3(bx[0], bx[1], bx[2]); hA = mk3(bx[3], bx[4], bx[5]); }
+        if (tb == SH_BOX) hB = Ssize[b];
+        else if (tb == SH_SPHERE) hB = mk3(Ssize[b].x, Ssize[b].x, Ssize[b].x);
+        else if (tb == SH_CAPSULE) hB = mk3(Ssize[b].x + Ssize[b].y, Ssize[b].x, Ssize[b].x);
+        else { const float* bx = M.hull_aabb + 6 * M.shape_hull[b]; cB = mk3(bx[0], bx[1], bx[2]); hB = mk3(bx[3], bx[4], bx[5]); }
+        m3 RA = qmat(SX[a].q), RB = qmat(SX[b].q);
+        v3 dAB = (SX[b].p + mul(RB, cB)) - (SX[a].p + mul(RA, cA));
+        float hAa[3] = {hA.x, hA.y, hA.z}, hBa[3] = {hB.x, hB.y, hB.z};
+        float sepmax = -1e30f;
+        for (int i = 0; i < 3; i++) {
+          v3 ax = col(RA, i);
+          float rB = hBa[0] * fabsf(dot(ax, col(RB, 0))) + hBa[1] * fabsf(dot(ax, col(RB, 1))) + hBa[2] * fabsf(dot(ax, col(RB, 2)));
+          sepmax = fmaxf(sepmax, fabsf(dot(ax, dAB)) - hAa[i] - rB);
+          v3 bxs = col(RB, i);
+          float rA = hAa[0] * fabsf(dot(bxs, col(RA, 0))) + hAa[1] * fabsf(dot(bxs, col(RA, 1))) + hAa[2] * fabsf(dot(bxs, col(RA, 2)));
+          sepmax = fmaxf(sepmax, fabsf(dot(bxs, dAB)) - hBa[i] - rA);
+        }
+        if (sepmax > margin + 1e-5f) continue;
+      }
     }
     WShape WA, WB;
     WA.type = ta; WA.X = SX[a]; WA.R = qmat(SX[a].q); WA.size = Ssize[a]; WA.verts = nullptr; WA.nverts = 0;

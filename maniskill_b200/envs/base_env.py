@@ -103,7 +103,7 @@ class BaseEnv:
 
     def __init__(self, num_envs: int = 1, obs_mode: Optional[str] = None, reward_mode: Optional[str] = None,
                  control_mode: Optional[str] = None, sim_config: Optional[dict] = None, device: Union[str, torch.device, None] = None,
-                 world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None):
+                 world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True):
         self.num_envs = num_envs
         self._obs_mode = "state" if obs_mode is None else obs_mode
         if self._obs_mode not in self.SUPPORTED_OBS_MODES:
@@ -148,6 +148,9 @@ class BaseEnv:
         self.action_dim = self.single_action_space_low.shape[0]
         self._sensors = self._setup_sensors() if self._visual else {}
         self._last_obs = None
+        self._fused = None
+        if fused and world_factory is None and self._obs_mode == "state":
+            self._fused = self._setup_fused_step()
         # sapien_env.py:321-327: main RNG seeds 2022+i, first reset
         self._set_main_rng([2022 + i for i in range(num_envs)])
         self._elapsed_steps[:] = 0
@@ -283,6 +286,8 @@ class BaseEnv:
 
     # ------------------------------------------------------------------ step (sapien_env.py:1042-1132)
     def step(self, action):
+        if self._fused is not None:
+            return self._step_fused(action)
         action = self._step_action(action)
         self._elapsed_steps += 1
         info = self.get_info()
@@ -294,6 +299,30 @@ class BaseEnv:
             terminated = info["fail"].clone() if "fail" in info else torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self._last_obs = obs
         return obs, reward, terminated, torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+
+    def _setup_fused_step(self):
+        """task hook: return a fused-step handle (backend.create_pick_task) or None to use the torch path."""
+        return None
+
+    def _step_fused(self, action):
+        """One C-ABI call = controller + substeps + evaluate/reward/obs kernels (include/b200sim.h b2s_pick_task_step);
+        produces exactly what the torch path below produces (tests/test_gpu_env.py::test_fused_step_matches_python_path)."""
+        if action is not None:
+            if isinstance(action, np.ndarray):
+                action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+            elif not isinstance(action, torch.Tensor):
+                raise TypeError(type(action))
+            action = action.to(device=self.device, dtype=torch.float32)
+            if action.shape == (self.action_dim,):
+                action = action[None]
+            action = action.contiguous()
+        f = self._fused
+        self.scene.world.pick_task_step(f["handle"], action, self._sim_steps_per_control, f["obs"], f["reward"], f["flags"], self._elapsed_steps)
+        fl = f["flags"]
+        info = dict(elapsed_steps=self._elapsed_steps.clone(), success=fl[:, 0], is_obj_placed=fl[:, 1], is_robot_static=fl[:, 2], is_grasped=fl[:, 3])
+        obs = f["obs"]
+        self._last_obs = obs
+        return obs, f["reward"], fl[:, 4].clone(), torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
 
     def _step_action(self, action):
         if action is not None:

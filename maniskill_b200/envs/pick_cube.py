@@ -53,6 +53,37 @@ class PickCubeEnv(BaseEnv):
         self.goal_site = self.scene.actors["goal_site"]
         self._hidden_objects.append(self.goal_site)
 
+    def _setup_fused_step(self):
+        """Fused controller + physics + evaluate/reward/obs (include/b200sim.h b2s_pick_task_*), pd_joint_delta_pos / pd_joint_pos."""
+        if self.agent.control_mode not in ("pd_joint_delta_pos", "pd_joint_pos"):
+            return None
+        nd = self.agent.robot.dof
+        dof_action = -np.ones(nd, dtype=np.int32)
+        use_delta, normalize = np.zeros(nd, dtype=np.int32), np.zeros(nd, dtype=np.int32)
+        low, high = np.zeros(nd, dtype=np.float32), np.zeros(nd, dtype=np.float32)
+        col = 0
+        for name, c in self.agent.controller.controllers.items():
+            joints = c.active_joint_indices.cpu().numpy()
+            if name == "gripper":  # mimic controller: one action column drives both fingers
+                for j in joints:
+                    dof_action[j], use_delta[j], normalize[j] = col, 0, 1
+                    low[j], high[j] = float(c.action_low[0]), float(c.action_high[0])
+                col += 1
+            else:
+                for k, j in enumerate(joints):
+                    dof_action[j], use_delta[j], normalize[j] = col + k, int(c.use_delta), int(c.normalize_action)
+                    low[j], high[j] = float(c.action_low[k]), float(c.action_high[k])
+                col += len(joints)
+        rows = dict(tcp=self.agent.tcp.row, obj=self.cube.row, goal=self.goal_site.row, lfinger=self.agent.finger1_link.row, rfinger=self.agent.finger2_link.row)
+        w = self.scene.world
+        handle = w.create_pick_task(dof_action, use_delta, normalize, low, high, col, rows, self.goal_thresh, nd - 2, 0,
+                                    normalized_reward=self._reward_mode == "normalized_dense")
+        if self._reward_mode not in ("normalized_dense", "dense"):
+            return None
+        N = self.num_envs
+        return dict(handle=handle, obs=torch.zeros((N, 2 * nd + 24), dtype=torch.float32, device=self.device),
+                    reward=torch.zeros(N, dtype=torch.float32, device=self.device), flags=torch.zeros((N, 6), dtype=torch.bool, device=self.device))
+
     # ---- pick_cube.py:66-71
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at(self.sensor_cam_eye_pos, self.sensor_cam_target_pos), width=128, height=128,
