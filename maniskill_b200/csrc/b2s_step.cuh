@@ -308,6 +308,32 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     CPoint out[4];
     int n = collide_pair(WA, WB, margin, out);
     if (n == 0) continue;
+    // patches of the same two bodies with (nearly) the same normal are one friction patch (4 finger boxes on the table
+    // give 4 points + 3 friction rows, not 16 + 12)
+    int merge = -1;
+    for (int mi = 0; mi < n_man; mi++) {
+      int qa = man_sa[mi], qb = man_sb[mi];
+      if (M.shape_owner_kind[qa] == M.shape_owner_kind[a] && M.shape_owner[qa] == M.shape_owner[a] &&
+          M.shape_owner_kind[qb] == M.shape_owner_kind[b] && M.shape_owner[qb] == M.shape_owner[b] &&
+          M.shape_row[qa] == M.shape_row[a] && M.shape_row[qb] == M.shape_row[b] && dot(man_n[mi], out[0].n) > 0.995f) {
+        merge = mi;
+        break;
+      }
+    }
+    if (merge >= 0) {
+      v3 cp[8];
+      float cs[8];
+      int nc = 0;
+      for (int i = 0; i < man_np[merge]; i++) { cp[nc] = man_p[merge][i]; cs[nc] = man_s[merge][i]; nc++; }
+      for (int i = 0; i < n; i++) { cp[nc] = out[i].p; cs[nc] = out[i].sep - M.rest_offset; nc++; }
+      int keep[4];
+      int k = reduce4(nc, cp, cs, keep);
+      n_points += k - man_np[merge];
+      man_np[merge] = k;
+      for (int i = 0; i < k; i++) { man_p[merge][i] = cp[keep[i]]; man_s[merge][i] = cs[keep[i]]; }
+      man_patch[merge] = fmaxf(man_patch[merge], fmaxf(M.shape_patch[a], M.shape_patch[b]));
+      continue;
+    }
     if (n_man >= max_man || n_points + n > max_cp) { *overflow = 1; continue; }
     man_sa[n_man] = a; man_sb[n_man] = b; man_np[n_man] = n; man_n[n_man] = out[0].n;
     for (int i = 0; i < n; i++) { man_p[n_man][i] = out[i].p; man_s[n_man][i] = out[i].sep - M.rest_offset; }

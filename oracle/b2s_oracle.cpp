@@ -280,6 +280,33 @@ static void step_env(Oracle& O, Env& E) {
     Contact out[4];
     int n = collide_pair(W[a], W[b], margin, out);
     if (n == 0) continue;
+    // Patches of the same two bodies with (nearly) the same normal are one friction patch: the four collision boxes of a
+    // Panda finger lying on the table give 4 points + 3 friction rows, not 16 + 12.
+    int merge = -1;
+    for (size_t mi = 0; mi < mans.size(); mi++) {
+      const Manifold& Q = mans[mi];
+      if (O.shape_owner_kind[Q.sa] == O.shape_owner_kind[a] && O.shape_owner[Q.sa] == O.shape_owner[a] &&
+          O.shape_owner_kind[Q.sb] == O.shape_owner_kind[b] && O.shape_owner[Q.sb] == O.shape_owner[b] &&
+          O.shape_row[Q.sa] == O.shape_row[a] && O.shape_row[Q.sb] == O.shape_row[b] && dot(Q.n, out[0].n) > R(0.995)) {
+        merge = (int)mi;
+        break;
+      }
+    }
+    if (merge >= 0) {
+      Manifold& Q = mans[merge];
+      V3 cp[8];
+      R cs[8];
+      int nc = 0;
+      for (int i = 0; i < Q.npts; i++) { cp[nc] = Q.p[i]; cs[nc] = Q.sep[i]; nc++; }
+      for (int i = 0; i < n; i++) { cp[nc] = out[i].p; cs[nc] = out[i].sep - m.rest_offset; nc++; }
+      int keep[4];
+      int k = reduce4(nc, cp, cs, keep);
+      n_points += k - Q.npts;
+      Q.npts = k;
+      for (int i = 0; i < k; i++) { Q.p[i] = cp[keep[i]]; Q.sep[i] = cs[keep[i]]; }
+      Q.patch = std::fmax(Q.patch, (R)std::fmax(O.shape_patch[a], O.shape_patch[b]));
+      continue;
+    }
     if ((int)mans.size() >= m.max_manifolds || n_points + n > m.max_contacts) { O.overflow = 1; continue; }
     Manifold M;
     M.sa = a; M.sb = b; M.npts = n; M.n = out[0].n;

@@ -3,16 +3,18 @@ usage: ncu_lines.py <ncu-rep> <libb200sim.so> <kernel regex> [topN]"""
 import csv, re, subprocess, sys, os, tempfile, collections
 rep, so, kre = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sel = sys.argv[5] if len(sys.argv) > 5 else "CapsILi12ELi4ELi32ELi1EEELi9E"  # mangled-name fragment choosing the instantiation
 tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {os.path.abspath(so)} >/dev/null", shell=True, check=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(f"nvdisasm --print-line-info -c {tmp}/{cubin}", shell=True, capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(f"nvdisasm --print-line-info -c {tmp}/{cubin}", shell=True, capture_output=True, text=True).stdout.splitlines()
 # map offset -> (file,line) for the first section whose name matches
 line_of = {}
 cur = None; insec = False
 for l in dis:
     if l.startswith("\t.section\t.text."):
-        insec = re.search(kre, l) is not None and "Caps" in l and "Li12" in l
+        insec = re.search(kre, l) is not None and (sel in l)
         cur = None
     if not insec: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
