@@ -287,9 +287,19 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
-  else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
-  else step_kernel<b2s::CapsL, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  // Lanes per warp.  Measured on B200 at 4096 envs (bench.py, ms per control step): 32 lanes 3.38, 16 lanes 3.76,
+  // 8 lanes 4.27, 4 lanes 5.16 -- spreading the envs over more, partially filled warps shortens the divergent union of
+  // control flow per warp but several warps per SM then stream different parts of the ~0.5 MB kernel through the
+  // instruction caches, which costs more.  Full warps it is; B2S_LANES overrides for experiments.
+  int lanes = 32;
+  {
+    static int forced = getenv("B2S_LANES") ? atoi(getenv("B2S_LANES")) : 0;
+    if (forced > 0 && forced <= 32) lanes = forced;
+  }
+  int grid = (N + lanes - 1) / lanes;
+  if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else step_kernel<b2s::CapsL, 0><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
   CK(cudaGetLastError());
   return B2S_OK;
 }

@@ -14,6 +14,14 @@
 #pragma once
 #include "b2s_collide.cuh"
 
+// loops with large bodies stay rolled: the kernel is instruction-fetch sensitive (one warp per SM streams the whole
+// substep through the instruction caches), the small inner loops (dot products over the dofs) are the ones worth unrolling
+#if defined(__CUDACC__)
+#define B2S_NO_UNROLL _Pragma("unroll 1")
+#else
+#define B2S_NO_UNROLL
+#endif
+
 namespace b2s {
 
 struct DevModel {
@@ -150,6 +158,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   v6 fextW[C::MAXD];
   pose* X = L.X;
   v6* V = L.V;
+  B2S_NO_UNROLL
   for (int i = 0; i < nd; i++) {
     int p = M.dof_parent[i], a = M.dof_art[i];
     pose Xp = p >= 0 ? X[p] : L.root[a];
@@ -190,6 +199,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   float br[C::MAXSH], bv[C::MAXSH];
   pose SX[C::MAXSH];
   v3 Ssize[C::MAXSH];
+  B2S_NO_UNROLL
   for (int s = 0; s < ns; s++) {
     int kind = M.shape_owner_kind[s], ow = M.shape_owner[s];
     pose own;
@@ -229,6 +239,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   const float margin_cap = 2.f * M.contact_offset;
   const int max_man = M.max_manifolds < C::MAXMAN ? M.max_manifolds : C::MAXMAN;
   const int max_cp = M.max_contacts < C::MAXCP ? M.max_contacts : C::MAXCP;
+  B2S_NO_UNROLL
   for (int k = 0; k < M.n_pair; k++) {
     int a = M.pair_a[k], b = M.pair_b[k];
     const float margin = fminf(margin_cap, M.margin_min + 2.f * dt * (bv[a] + bv[b]));
@@ -347,10 +358,12 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   // force would exceed its limit is re-run as a constant force at the limit (pass 1, rare).
   float qdd[C::MAXD];
   for (int pass = 0; pass < 2; pass++) {
+    B2S_NO_UNROLL
     for (int i = 0; i < nd; i++) {
       spatial_inertia(IA[i], M.dof_mass[i], cW[i], IwW[i]);
       pA[i] = crf(V[i], m6mul(IA[i], V[i])) - fextW[i];
     }
+    B2S_NO_UNROLL
     for (int i = nd - 1; i >= 0; i--) {
       U[i] = m6mul(IA[i], S[i]);
       float D = dot6(S[i], U[i]) + arm[i];
@@ -368,6 +381,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     }
     {
       v6 acc[C::MAXD];
+      B2S_NO_UNROLL
       for (int i = 0; i < nd; i++) {
         int p = M.dof_parent[i];
         v6 ap = (p >= 0 ? acc[p] : zero6()) + cvp[i];
@@ -392,6 +406,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   }
   float Minv[C::MAXD * C::MAXD];
   for (int i = 0; i < nd * nd; i++) Minv[i] = 0.f;
+  B2S_NO_UNROLL
   for (int j = 0; j < nd; j++) {
     float uu[C::MAXD];
     for (int i = 0; i < nd; i++) uu[i] = 0.f;
@@ -404,6 +419,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       p = M.dof_parent[p];
     }
     v6 aa[C::MAXD];
+    B2S_NO_UNROLL
     for (int i = 0; i < nd; i++) {
       if (M.dof_art[i] != M.dof_art[j]) continue;
       int pi = M.dof_parent[i];
@@ -512,9 +528,11 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     B2S_FINISH_ROW(ri);
   }
   int n_lim = 0;
+  B2S_NO_UNROLL
   for (int i = 0; i < nd; i++) {
     float lo = M.dof_limit[2 * i], hi = M.dof_limit[2 * i + 1];
     const float limit_margin = 0.005f + 2.f * dt * fabsf(L.qd[i]);  // only while the limit is reachable within this step
+    B2S_NO_UNROLL
     for (int side = 0; side < 2; side++) {
       bool act = side == 0 ? (lo > -1e29f && L.q[i] - lo < limit_margin) : (hi < 1e29f && hi - L.q[i] < limit_margin);
       if (!act) continue;
@@ -531,6 +549,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     }
   }
   L.n_man = 0;
+  B2S_NO_UNROLL
   for (int mi = 0; mi < n_man; mi++) {
     v3 n = man_n[mi];
     v3 t1 = fabsf(n.x) < 0.57735f ? normalized(cross(n, mk3(1, 0, 0))) : normalized(cross(n, mk3(0, 1, 0)));
@@ -550,6 +569,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       if (M.shape_owner_kind[sh[sde]] == OWNER_LINK && M.shape_owner[sh[sde]] >= 0) any_art = true;
     int nrows_needed = np + 2 + (rad > 0.f ? 1 : 0);
     if (n_row + nrows_needed > C::MAXROW || (any_art && n_ar + nrows_needed > C::MAXAR)) { *overflow = 1; continue; }
+    B2S_NO_UNROLL
     for (int k = 0; k < nrows_needed; k++) {
       int ri = n_row++;
       bool is_n = k < np;
@@ -669,29 +689,48 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       for (int ri = 0; ri < n_row; ri++) r_total[ri] -= r_lambda[ri];
     }
     for (int ri = 0; ri < n_row; ri++) {
-      float jv;
-      B2S_ROW_JV(ri, v, fv, fw, jv);
+      // J.v (velocity error) and J.dq (position error of the row) in one pass: two independent accumulation chains
+      // and one read of the row
+      float jv = 0.f, sd = 0.f;
+      if (r_art[ri] >= 0) {
+        const float* J_ = JB[r_art[ri]];
+        for (int j_ = 0; j_ < nd; j_++) {
+          float Jj = J_[j_];
+          jv += Jj * v[j_];
+          sd += Jj * dq[j_];
+        }
+      }
+      if (r_fb0[ri] >= 0) {
+        int b_ = r_fb0[ri];
+        v3 lin_ = r_angonly[ri] ? mk3(0, 0, 0) : r_dir[ri];
+        jv += dot(lin_, fv[b_]) + dot(r_ang0[ri], fw[b_]);
+        sd += dot(lin_, dx[b_]) + dot(r_ang0[ri], dth[b_]);
+      }
+      if (r_fb1[ri] >= 0) {
+        int b_ = r_fb1[ri];
+        v3 lin_ = r_angonly[ri] ? mk3(0, 0, 0) : -r_dir[ri];
+        jv += dot(lin_, fv[b_]) + dot(r_ang1[ri], fw[b_]);
+        sd += dot(lin_, dx[b_]) + dot(r_ang1[ri], dth[b_]);
+      }
       float nl;
-      if (r_type[ri] == ROW_FRICTION) {
+      const float lam = r_lambda[ri];
+      const int ty = r_type[ri];
+      if (ty == ROW_FRICTION) {
         float nsum = 0.f;
         for (int k = 0; k < r_ncount[ri]; k++) nsum += r_lambda[r_nrow[ri] + k];
         float lim = r_mu[ri] * nsum;
-        nl = fmaxf(-lim, fminf(lim, r_lambda[ri] - jv * r_dinv[ri]));
-      } else if (r_type[ri] == ROW_EQ) {
-        float sd;
-        B2S_ROW_JV(ri, dq, dx, dth, sd);
+        nl = fmaxf(-lim, fminf(lim, lam - jv * r_dinv[ri]));
+      } else if (ty == ROW_EQ) {
         float s = r_s0[ri] + sd;
         float bias = relax ? 0.f : s / h;
-        nl = r_lambda[ri] - (jv + bias + r_gamma[ri] * r_lambda[ri]) * r_dinv[ri];
+        nl = lam - (jv + bias + r_gamma[ri] * lam) * r_dinv[ri];
       } else {
-        float sd;
-        B2S_ROW_JV(ri, dq, dx, dth, sd);
         float s = r_s0[ri] + sd;
         float bias, ms = 1.f, is = 0.f;
         if (s > 0.f) bias = s / h;
         else if (relax) bias = 0.f;
         else { bias = fmaxf(soft_rate * s, -M.max_depen_vel); ms = soft_mass; is = soft_imp; }
-        nl = fmaxf(0.f, r_lambda[ri] - r_dinv[ri] * ms * (jv + bias) - is * r_lambda[ri]);
+        nl = fmaxf(0.f, lam - r_dinv[ri] * ms * (jv + bias) - is * lam);
       }
       float dl = nl - r_lambda[ri];
       r_lambda[ri] = nl;
