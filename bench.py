@@ -138,7 +138,8 @@ def run_gpu(args):
     venv = ms.ManiSkillVectorEnv(env, auto_reset=not args.no_auto_reset)
     world = env.scene.world
     A = env.action_dim
-    obs, _ = venv.reset(seed=2022)
+    from maniskill_b200.dist import ObsGather, shard_seeds
+    obs, _ = venv.reset(seed=shard_seeds(2022, n_envs * world_size, rank, world_size))  # seeds keep the global env id
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
@@ -148,14 +149,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_buf = None
-    if args.gather_obs and world_size > 1:
-        gather_buf = torch.empty((world_size * n_envs, obs.shape[1]), dtype=obs.dtype, device=dev)
+    gather_buf = ObsGather(n_envs, obs.shape[1], obs.dtype, dev) if (args.gather_obs and world_size > 1) else None
 
     def one_step(actions):
         o, r, te, tr, info = venv.step(actions)
         if gather_buf is not None:
-            dist.all_gather_into_tensor(gather_buf, o)
+            gather_buf(o)
         return o, r, te, tr
 
     # ---------------- warm-up

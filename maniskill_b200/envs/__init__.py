@@ -3,3 +3,6 @@ from .base_env import BaseEnv
 from .pick_cube import PickCubeEnv
 
 register_env("PickCube-v1", max_episode_steps=50)(PickCubeEnv)
+from .peg_insertion_side import PegInsertionSideEnv
+
+register_env("PegInsertionSide-v1", max_episode_steps=100)(PegInsertionSideEnv)

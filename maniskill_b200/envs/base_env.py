@@ -128,6 +128,10 @@ class BaseEnv:
         self._visual = any(k in self._obs_mode for k in ("rgb", "depth", "segmentation", "sensor_data"))
         if enable_cameras is not None:
             self._visual = self._visual or enable_cameras
+        # sapien_env.py:321-327 + 899-907: the first reset seeds main/episode RNG with 2022+i BEFORE `_load_scene` runs, so
+        # tasks can draw per-env geometry from `_batched_episode_rng` while building (peg_insertion_side.py:114-120)
+        self._set_main_rng([2022 + i for i in range(num_envs)])
+        self._set_episode_rng([2022 + i for i in range(num_envs)], np.arange(num_envs))
         # ---- build the scene (sapien_env.py:725-770 `_reconfigure`)
         self.scene_desc = SceneDesc(num_envs, self.sim_params)
         self._load_agent_desc()

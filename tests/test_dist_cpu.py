@@ -1,0 +1,66 @@
+"""CPU: the N>1 path (env sharding + observation all-gather) with world_size-2 gloo processes on the emulated backend."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from maniskill_b200.dist import shard_range, shard_seeds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_exactly():
+    for total in (7, 8, 4096, 16384):
+        for g in (1, 2, 3, 8):
+            blocks = [shard_range(total, r, g) for r in range(g)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(g - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_seeds(2022, 8, 1, 2) == [2026, 2027, 2028, 2029]
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _worker(rank, world_size, port, q):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    import maniskill_b200 as ms
+    from emu_world import EmuBackendWorld
+    from maniskill_b200.dist import ObsGather
+    n_local = 2
+    env = ms.make("PickCube-v1", num_envs=n_local, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=shard_seeds(2022, n_local * world_size, rank, world_size))
+    gather = ObsGather(n_local, obs.shape[1])
+    a = torch.full((n_local, 8), 0.1 * (rank + 1))
+    obs, rew, *_ = env.step(a)
+    full = gather(obs).clone()
+    # every rank must hold every rank's block, in rank order
+    mine = full[rank * n_local:(rank + 1) * n_local]
+    ok = torch.equal(mine, obs) and full.shape == (n_local * world_size, obs.shape[1])
+    blocks = [torch.empty_like(obs) for _ in range(world_size)]
+    dist.all_gather(blocks, obs)
+    ok = ok and torch.equal(torch.cat(blocks), full)
+    q.put((rank, bool(ok), float(full.abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_obs_all_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert abs(res[0][2] - res[1][2]) < 1e-3  # both ranks see the same gathered batch
