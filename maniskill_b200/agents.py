@@ -234,3 +234,112 @@ class Panda:
     @property
     def tcp_pos(self):
         return self.tcp.pose.p
+
+
+class PDBaseForwardVelController:
+    """mani_skill/agents/controllers/pd_base_vel.py:39-73: action = (forward velocity, yaw rate) in the robot frame ->
+    velocity drive targets of the three virtual base joints (x, y, yaw)."""
+    sets_target_qpos = False
+    sets_target_qvel = True
+    normalize_action = True
+    use_target = False
+
+    def __init__(self, articulation: Articulation, joint_names: List[str], lower, upper):
+        self.articulation = articulation
+        self.scene = articulation.scene
+        self.device = self.scene.device
+        self.active_joint_indices = torch.tensor([articulation.dof_names.index(n) for n in joint_names], dtype=torch.int64, device=self.device)
+        self.action_low = torch.tensor(np.broadcast_to(lower, 2).astype(np.float32), device=self.device)
+        self.action_high = torch.tensor(np.broadcast_to(upper, 2).astype(np.float32), device=self.device)
+        self.action_dim = 2
+
+    @property
+    def qpos(self):
+        return self.articulation.qpos[..., self.active_joint_indices]
+
+    def reset(self, env_idx=None):
+        pass
+
+    def set_action(self, action):
+        action = U.clip_and_scale_action(action, self.action_low, self.action_high)
+        ori = self.qpos[:, 2]
+        c, s = torch.cos(ori), torch.sin(ori)
+        vel = torch.stack([c * action[:, 0], s * action[:, 0]], 1)  # rot(ori) @ (forward, 0)
+        self.articulation.set_joint_drive_velocity_targets(torch.hstack([vel, action[:, 1:]]), self.active_joint_indices)
+
+    def get_state(self):
+        return {}
+
+
+class Fetch:
+    """mani_skill/agents/robots/fetch/fetch.py:26-410 (uid 'fetch'): 7-dof arm, mimic gripper, head/torso, velocity-driven base."""
+    uid = "fetch"
+    arm_joint_names = ["shoulder_pan_joint", "shoulder_lift_joint", "upperarm_roll_joint", "elbow_flex_joint", "forearm_roll_joint",
+                       "wrist_flex_joint", "wrist_roll_joint"]
+    gripper_joint_names = ["l_gripper_finger_joint", "r_gripper_finger_joint"]
+    body_joint_names = ["head_pan_joint", "head_tilt_joint", "torso_lift_joint"]
+    base_joint_names = ["root_x_axis_joint", "root_y_axis_joint", "root_z_rotation_joint"]
+    ee_link_name = "gripper_link"
+    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos")
+
+    def __init__(self, scene, name="fetch"):
+        self.scene = scene
+        self.device = scene.device
+        self.robot: Articulation = scene.articulations[name]
+        lm = self.robot.links_map
+        self.finger1_link, self.finger2_link = lm["l_gripper_finger_link"], lm["r_gripper_finger_link"]
+        self.tcp = lm[self.ee_link_name]
+        self.base_link = lm["base_link"]
+        self.controller = None
+        self.control_mode = None
+
+    def set_control_mode(self, control_mode: Optional[str] = None):
+        if control_mode is None:
+            control_mode = self.SUPPORTED_CONTROL_MODES[0]
+        if control_mode not in self.SUPPORTED_CONTROL_MODES:
+            raise NotImplementedError(f"control mode {control_mode} is not available in this build (supported: {self.SUPPORTED_CONTROL_MODES})")
+        self.control_mode = control_mode
+        if control_mode == "pd_joint_delta_pos":
+            arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
+        else:
+            arm = PDJointPosController(self.robot, self.arm_joint_names, None, None, normalize_action=False)
+        gripper = PDJointPosMimicController(self.robot, self.gripper_joint_names, -0.01, 0.05,
+                                            mimic={"r_gripper_finger_joint": {"joint": "l_gripper_finger_joint"}})
+        body = PDJointPosController(self.robot, self.body_joint_names, -0.1, 0.1, use_delta=True)
+        base = PDBaseForwardVelController(self.robot, self.base_joint_names, [-1, -3.14], [1, 3.14])
+        self.controller = CombinedController(dict(arm=arm, gripper=gripper, body=body, base=base))
+
+    action_bounds = Panda.action_bounds
+    reset = Panda.reset
+    set_action = Panda.set_action
+    get_proprioception = Panda.get_proprioception
+
+    def controller_reset(self, env_idx=None):
+        Panda.controller_reset(self, env_idx)
+        rows = self.robot._rows if env_idx is None else self.robot._rows[env_idx]
+        self.scene.world.target_qvel[rows, :self.robot.dof] = 0.0
+        self.scene._dirty |= self.scene.BUF_TARGET_QVEL
+        self.scene._gpu_apply_all()
+
+    def is_grasping(self, obj, min_force=0.5, max_angle=85):
+        """fetch.py:338-368 (finger opening directions are mirrored with respect to the Panda)."""
+        l_f = self.scene.get_pairwise_contact_forces(self.finger1_link, obj)
+        r_f = self.scene.get_pairwise_contact_forces(self.finger2_link, obj)
+        ldirection = -self.finger1_link.pose.to_transformation_matrix()[..., :3, 1]
+        rdirection = self.finger2_link.pose.to_transformation_matrix()[..., :3, 1]
+        lflag = torch.logical_and(torch.linalg.norm(l_f, axis=1) >= min_force, torch.rad2deg(U.compute_angle_between(ldirection, l_f)) <= max_angle)
+        rflag = torch.logical_and(torch.linalg.norm(r_f, axis=1) >= min_force, torch.rad2deg(U.compute_angle_between(rdirection, r_f)) <= max_angle)
+        return torch.logical_and(lflag, rflag)
+
+    def is_static(self, threshold: float = 0.2, base_threshold: float = 0.05):
+        """fetch.py:370-375 (the reference orders qvel base-first; here the joints are selected by name)."""
+        names = self.robot.dof_names
+        base = torch.tensor([names.index(n) for n in self.base_joint_names], device=self.device)
+        fingers = set(self.gripper_joint_names) | set(self.base_joint_names)
+        body = torch.tensor([i for i, n in enumerate(names) if n not in fingers], device=self.device)
+        qv = self.robot.get_qvel()
+        return torch.all(qv[:, body] <= threshold, dim=1) & torch.all(qv[:, base] <= base_threshold, dim=1)
+
+    @property
+    def tcp_pose(self) -> Pose:
+        return self.tcp.pose

@@ -139,6 +139,24 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
   return P;
 }
 
+#define B2S_MAX_BIG_TRIS 384
+
+// one coverage + depth sample: edge functions at the pixel centre, 1/depth interpolated in screen space, atomicMin on the key
+__device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int y, const float* px, const float* py, const float* pd, float inv_area,
+                                              int v, float nearp, float farp) {
+  float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
+  float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
+  float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
+  float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
+  if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) return;
+  float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
+  if (!(inv > 0.0f)) return;
+  float d = 1.0f / inv;
+  if (d <= nearp || d >= farp) return;
+  unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
+  atomicMin(&zkey[y * W + x], key);
+}
+
 __global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
                                                      int16_t* __restrict__ posseg) {
   extern __shared__ unsigned zkey[];
@@ -146,6 +164,13 @@ __global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float*
   __shared__ float vis_t[64][3];   // camera-from-visual translation
   __shared__ float vis_Rw[64][9];  // world-from-visual rotation (lighting)
   __shared__ float vis_sz[64][3];
+  __shared__ int vis_rect[64][4];  // conservative screen rectangle (x0, x1, y0, y1) of the ray-cast primitives
+  __shared__ int vis_kind[64];
+  __shared__ float vis_o[64][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
+  __shared__ float big_tri[B2S_MAX_BIG_TRIS][10];
+  __shared__ int big_box[B2S_MAX_BIG_TRIS][5];
+  __shared__ int n_big;
+  if (threadIdx.x == 0) n_big = 0;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
@@ -174,6 +199,30 @@ __global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float*
     v3 tcv = tmul(Rc, Xv.p - Xc.p);
     for (int k = 0; k < 9; k++) { vis_R[v][k] = Rcv.m[k]; vis_Rw[v][k] = Rv.m[k]; }
     vis_t[v][0] = tcv.x; vis_t[v][1] = tcv.y; vis_t[v][2] = tcv.z;
+    vis_o[v][0] = -(Rcv.m[0] * tcv.x + Rcv.m[3] * tcv.y + Rcv.m[6] * tcv.z);
+    vis_o[v][1] = -(Rcv.m[1] * tcv.x + Rcv.m[4] * tcv.y + Rcv.m[7] * tcv.z);
+    vis_o[v][2] = -(Rcv.m[2] * tcv.x + Rcv.m[5] * tcv.y + Rcv.m[8] * tcv.z);
+    // screen rectangle that surely contains the primitive (whole image when it reaches behind the near plane)
+    int rx0 = 0, rx1 = W - 1, ry0 = 0, ry1 = H - 1;
+    int ty = R.vis_type[v];
+    vis_kind[v] = ty;
+    if (ty == SH_BOX || ty == SH_SPHERE) {
+      float hx = vis_sz[v][0], hy = ty == SH_BOX ? vis_sz[v][1] : vis_sz[v][0], hz = ty == SH_BOX ? vis_sz[v][2] : vis_sz[v][0];
+      float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+      bool behind = false;
+      for (int c = 0; c < 8; c++) {
+        v3 l = mk3((c & 1) ? hx : -hx, (c & 2) ? hy : -hy, (c & 4) ? hz : -hz);
+        v3 pc = mul(Rcv, l) + tcv;
+        if (pc.x <= nearp) { behind = true; break; }
+        float u = cx - fx * pc.y / pc.x, w = cy - fy * pc.z / pc.x;
+        mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w);
+      }
+      if (!behind) {
+        rx0 = max(0, (int)floorf(mnx) - 1); rx1 = min(W - 1, (int)ceilf(mxx) + 1);
+        ry0 = max(0, (int)floorf(mny) - 1); ry1 = min(H - 1, (int)ceilf(mxy) + 1);
+      }
+    }
+    vis_rect[v][0] = rx0; vis_rect[v][1] = rx1; vis_rect[v][2] = ry0; vis_rect[v][3] = ry1;
   }
   __syncthreads();
   // ---------------- pass 1: rasterise hull triangles (camera frame: x forward, y left, z up)
@@ -209,27 +258,49 @@ __global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float*
     int y0 = max(0, (int)floorf(miny - 0.5f)), y1 = min(H - 1, (int)ceilf(maxy - 0.5f));
     if (x0 > x1 || y0 > y1) continue;
     float inv_area = 1.0f / area;
-    for (int y = y0; y <= y1; y++)
-      for (int x = x0; x <= x1; x++) {
-        float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
-        float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
-        float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
-        float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
-        if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) continue;
-        float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
-        if (!(inv > 0.0f)) continue;
-        float d = 1.0f / inv;
-        if (d <= nearp || d >= farp) continue;
-        unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
-        atomicMin(&zkey[y * W + x], key);
+    const int bw = x1 - x0 + 1, cnt = bw * (y1 - y0 + 1);
+    if (cnt > 48) {
+      // large on-screen triangle (close-up views of the wrist camera): hand it to the whole CTA instead of one thread
+      int slot = atomicAdd(&n_big, 1);
+      if (slot < B2S_MAX_BIG_TRIS) {
+        float* o = big_tri[slot];
+        o[0] = px[0]; o[1] = px[1]; o[2] = px[2]; o[3] = py[0]; o[4] = py[1]; o[5] = py[2];
+        o[6] = pd[0]; o[7] = pd[1]; o[8] = pd[2]; o[9] = inv_area;
+        big_box[slot][0] = x0; big_box[slot][1] = y0; big_box[slot][2] = bw; big_box[slot][3] = cnt; big_box[slot][4] = v;
+        continue;
       }
+    }
+    for (int y = y0; y <= y1; y++)
+      for (int x = x0; x <= x1; x++) raster_sample(zkey, W, x, y, px, py, pd, inv_area, v, nearp, farp);
+  }
+  __syncthreads();
+  {
+    const int nb = n_big < B2S_MAX_BIG_TRIS ? n_big : B2S_MAX_BIG_TRIS;
+    for (int b = 0; b < nb; b++) {
+      const float* o = big_tri[b];
+      const int x0 = big_box[b][0], y0 = big_box[b][1], bw = big_box[b][2], cnt = big_box[b][3], v = big_box[b][4];
+      for (int p = threadIdx.x; p < cnt; p += blockDim.x) raster_sample(zkey, W, x0 + p % bw, y0 + p / bw, o, o + 3, o + 6, o[9], v, nearp, farp);
+    }
   }
   __syncthreads();
   // ---------------- pass 2: per pixel analytic primitives + merge + shade + store
   uint8_t* cbase = color + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
   int16_t* pbase = posseg + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
-  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-    int x = i % W, y = i / W;
+  // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel).  With W dividing blockDim the
+  // column of a thread is fixed, so the set of ray-cast primitives whose screen rectangle covers that column is one
+  // 64-bit mask computed once per column.
+  int x = threadIdx.x % W, y = threadIdx.x / W;
+  const int step_x = blockDim.x % W, step_y = blockDim.x / W;
+  int mask_x = -1;
+  unsigned long long xmask = 0ull;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x, x += step_x, y += step_y) {
+    if (x >= W) { x -= W; y++; }
+    if (x != mask_x) {
+      xmask = 0ull;
+      for (int v = 0; v < nv; v++)
+        if (vis_kind[v] != SH_CONVEX && x >= vis_rect[v][0] && x <= vis_rect[v][1]) xmask |= 1ull << v;
+      mask_x = x;
+    }
     float ry = -((float)x + 0.5f - cx) / fx, rz = -((float)y + 0.5f - cy) / fy;
     v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
     float best = 1e30f;
@@ -241,13 +312,12 @@ __global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float*
       best_v = (int)(k & 255u);
     }
     bool raster_hit = best_v >= 0;
-    for (int v = 0; v < nv; v++) {
-      int ty = R.vis_type[v];
-      if (ty == SH_CONVEX) continue;
+    for (unsigned long long m = xmask; m != 0ull; m &= m - 1ull) {
+      const int v = __ffsll((long long)m) - 1;
+      if (y < vis_rect[v][2] || y > vis_rect[v][3]) continue;
+      const int ty = vis_kind[v];
       // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
-      v3 tt = mk3(vis_t[v][0], vis_t[v][1], vis_t[v][2]);
-      v3 o = mk3(-(vis_R[v][0] * tt.x + vis_R[v][3] * tt.y + vis_R[v][6] * tt.z), -(vis_R[v][1] * tt.x + vis_R[v][4] * tt.y + vis_R[v][7] * tt.z),
-                 -(vis_R[v][2] * tt.x + vis_R[v][5] * tt.y + vis_R[v][8] * tt.z));
+      v3 o = mk3(vis_o[v][0], vis_o[v][1], vis_o[v][2]);
       v3 dl = mk3(vis_R[v][0] * rdir.x + vis_R[v][3] * rdir.y + vis_R[v][6] * rdir.z, vis_R[v][1] * rdir.x + vis_R[v][4] * rdir.y + vis_R[v][7] * rdir.z,
                   vis_R[v][2] * rdir.x + vis_R[v][5] * rdir.y + vis_R[v][8] * rdir.z);
       float th;

@@ -6,3 +6,6 @@ register_env("PickCube-v1", max_episode_steps=50)(PickCubeEnv)
 from .peg_insertion_side import PegInsertionSideEnv
 
 register_env("PegInsertionSide-v1", max_episode_steps=100)(PegInsertionSideEnv)
+from .open_cabinet_drawer import OpenCabinetDrawerEnv
+
+register_env("OpenCabinetDrawer-v1", max_episode_steps=100)(OpenCabinetDrawerEnv)

@@ -97,3 +97,49 @@ def test_unsupported_modes_raise():
         ms.make("PickCube-v1", num_envs=1, obs_mode="pointcloud", world_factory=EmuBackendWorld)
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_delta_pose", world_factory=EmuBackendWorld)
+
+
+def test_peg_insertion_side_heterogeneous_envs():
+    """tests/test_sim_state.py:53-65 analogue + per-env geometry (peg_insertion_side.py:114-120)."""
+    env = ms.make("PegInsertionSide-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert obs.shape == (3, 9 + 9 + 7 + 7 + 3 + 7 + 1)
+    hs = env.peg_half_sizes
+    assert (hs[:, 0] >= 0.085).all() and (hs[:, 0] <= 0.125).all() and (hs[:, 1] >= 0.015).all() and (hs[:, 1] <= 0.025).all()
+    assert len(torch.unique(hs[:, 0])) == 3  # every env has its own peg
+    # same draws as the reference: RandomState(2022 + i).uniform(0.085, 0.125) is the first draw of env i
+    assert np.allclose(hs[:, 0].numpy(), [np.random.RandomState(2022 + i).uniform(0.085, 0.125) for i in range(3)], atol=1e-7)
+    for _ in range(20):
+        obs, r, te, tr, info = env.step(torch.zeros(3, 8))
+    # pegs lie flat on the table: z = radius (within the soft-contact sag)
+    assert torch.allclose(env.peg.pose.p[:, 2], hs[:, 1], atol=1.5e-3)
+    assert not info["success"].any() and torch.isfinite(r).all()
+    # goal geometry helper: the hole frame sits at the box centre plus the per-env offset
+    assert torch.allclose((env.box.pose.inv() * env.box_hole_pose).p[:, 0], torch.zeros(3), atol=1e-6)
+
+
+def test_open_cabinet_drawer_standin():
+    env = ms.make("OpenCabinetDrawer-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert env.action_dim == 13 and obs.shape == (2, 15 + 15 + 7 + 3 + 1 + 3)
+    q = env.agent.robot.qpos
+    names = env.agent.robot.dof_names
+    d = torch.sqrt(q[:, names.index("root_x_axis_joint")] ** 2 + q[:, names.index("root_y_axis_joint")] ** 2)
+    assert ((d >= 1.6 - 1e-4) & (d <= 1.8 + 1e-4)).all()  # robot 1.6-1.8 m from the cabinet (open_cabinet_drawer.py:262-267)
+    r0 = env.step(torch.zeros(2, 13))[1]
+    # pull the target drawer open with a generalised force: reward goes up, open_enough / success flip
+    qf = torch.zeros(2, env.cabinet.dof)
+    qf[torch.arange(2), env._target_dof] = 40.0
+    env.cabinet.set_qf(qf)
+    env.scene._gpu_apply_all()
+    for _ in range(40):
+        obs, r, te, tr, info = env.step(torch.zeros(2, 13))
+    assert (env._target_joint_qpos() > 0.25).all() and info["open_enough"].all()
+    assert (r > r0).all()
+    env.cabinet.set_qf(torch.zeros(2, env.cabinet.dof))
+    env.scene._gpu_apply_all()
+    for _ in range(10):
+        obs, r, te, tr, info = env.step(torch.zeros(2, 13))
+    assert info["success"].all() and torch.allclose(r, torch.ones(2))
+    # the goal marker follows the handle of the chosen drawer (:294-305)
+    assert torch.allclose(env.handle_link_goal.pose.p, info["handle_link_pos"], atol=1e-5)

@@ -55,3 +55,36 @@ def test_depth_of_table_top_is_analytic():
     centre = d[63:65, 63:65].mean()
     assert abs(centre - t * 1000) < 15, (centre, t * 1000)
     env.close()
+
+
+def test_peg_insertion_rgbd_two_cameras_heterogeneous_envs():
+    """BASELINE.json configs[2]: PegInsertionSide-v1 with 128x128 RGBD, base + wrist camera, per-env peg/box geometry."""
+    import maniskill_b200 as ms
+    from oracle import raster
+    n = 5
+    env = ms.make("PegInsertionSide-v1", num_envs=n, obs_mode="rgbd")
+    obs, _ = env.reset(seed=1)
+    g = torch.Generator(device=env.device).manual_seed(0)
+    for _ in range(3):
+        obs, rew, term, trunc, info = env.step(2 * torch.rand((n, 8), device=env.device, generator=g) - 1)
+    assert set(obs["sensor_data"].keys()) == {"base_camera", "hand_camera"}
+    for cam in ("base_camera", "hand_camera"):
+        assert obs["sensor_data"][cam]["rgb"].shape == (n, 128, 128, 3)
+        assert obs["sensor_data"][cam]["depth"].shape == (n, 128, 128, 1)
+        assert "segmentation" not in obs["sensor_data"][cam]
+    assert obs["extra"]["tcp_pose"].shape == (n, 7) and torch.isfinite(rew).all()
+    torch.cuda.synchronize()
+    body = env.scene.world.body_view().cpu().numpy()
+    ref = raster.render(env._sensors.visuals, env._sensors.cams, body)
+    grp = env._sensors.group
+    for i, (color, posseg) in enumerate(ref):
+        ps = grp.get_picture_cuda("PositionSegmentation", i).cpu().numpy()
+        col = grp.get_picture_cuda("Color", i).cpu().numpy()
+        assert np.array_equal(ps[..., 3], posseg[..., 3]), f"camera {i}: {(ps[..., 3] != posseg[..., 3]).sum()} seg pixels differ"
+        assert np.array_equal(ps[..., :3], posseg[..., :3])
+        assert np.abs(col.astype(int) - color.astype(int)).max() <= 1
+    # pegs have different lengths in different envs, and the peg is visible from the base camera
+    peg_seg = env.cm.actor_seg_id["peg"]
+    counts = [(grp.get_picture_cuda("PositionSegmentation", 0)[e, ..., 3] == peg_seg).sum().item() for e in range(n)]
+    assert min(counts) > 0
+    env.close()
