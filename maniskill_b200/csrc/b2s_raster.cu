@@ -3,6 +3,7 @@
 #define B2S_RASTER_IMPL
 #include "b2s_raster.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace b2s {
@@ -80,7 +81,9 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
 
 const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, cudaStream_t st) {
   int grid = M.n_envs * g->R.n_cam;
-  raster_kernel<<<grid, 256, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg);
+  // 512 threads = 16 warps per image: two images per SM (shared-memory bound) then keep 32 warps in flight
+  static int threads = getenv("B2S_RASTER_THREADS") ? atoi(getenv("B2S_RASTER_THREADS")) : 512;
+  raster_kernel<<<grid, threads, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -157,7 +157,7 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
   atomicMin(&zkey[y * W + x], key);
 }
 
-__global__ void __launch_bounds__(256) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
+__global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
                                                      int16_t* __restrict__ posseg) {
   extern __shared__ unsigned zkey[];
   __shared__ float vis_R[64][9];   // camera-from-visual rotation (row major)
