@@ -25,6 +25,29 @@ BYTES_PHYSICS_PER_ENV_SUBSTEP = 3696
 BYTES_IO_PER_ENV_STEP = 213
 
 
+def usable_cores():
+    """Host cores this process may actually use: min(os.cpu_count, scheduler affinity, cgroup cpu quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -83,11 +106,12 @@ def cpu_oracle_throughput(n_envs, control_steps, substeps=5, seed=0):
     mani_skill/examples/benchmarking/gpu_sim.py:72-84).  Returns (env-steps/s, cores, seconds)."""
     from oracle import oracle as _o
     _o.build()
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per = max(n_envs // cores, 1)
-    start_at = time.time() + 4.0 + 0.05 * per  # imports + world construction + warm-up happen before this instant
+    start_at = time.time() + 8.0 + 0.05 * per + 0.05 * cores  # imports + world construction + warm-up happen before this instant
+    env_ = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), str(per), str(control_steps), str(seed + i),
-                               repr(start_at)], stdout=subprocess.PIPE, text=True) for i in range(cores)]
+                               repr(start_at)], stdout=subprocess.PIPE, text=True, env=env_) for i in range(cores)]
     times = [float(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
     dt = max(times)
     return per * cores * control_steps / dt, cores, dt
@@ -99,8 +123,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sample_envs = 32 * cores
+    cores = usable_cores()
+    sample_envs = 64 * cores
     # warm-up + K steps, each step = one control step of the bounded sample
     v, cores, dt = cpu_oracle_throughput(sample_envs, max(args.steps, 1))
     line = {
@@ -169,11 +193,13 @@ def run_gpu(args):
     with ClockSampler(local_rank) as clocks:
         barrier()
         t_wall0 = time.perf_counter()
+        torch.cuda.nvtx.range_push("timed")  # ncu --nvtx --nvtx-include "timed/" captures exactly these launches
         for i in range(args.steps):
             flush.fill_(float(i))  # evict L2 between timed iterations
             ev0[i].record()
             one_step(actions_all[i])
             ev1[i].record()
+        torch.cuda.nvtx.range_pop()
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = world.kernel_launches - launches0
@@ -240,12 +266,47 @@ def run_gpu(args):
                      "traffic": args.traffic_bytes, "peak_source": peak_src, "kernel": "step_kernel (5 fused substeps)",
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_per_launch},
     }
+    # ---------------- supplementary: the RGBD half of BASELINE.json's metric (PickCube-v1 state+rgb+depth, one 128x128 camera)
+    extra = None
+    if not args.no_rgbd:
+        env.close()
+        n_v = args.num_envs
+        env_v = ms.make("PickCube-v1", num_envs=n_v, obs_mode="state+rgb+depth", device=dev)
+        venv_v = ms.ManiSkillVectorEnv(env_v)
+        venv_v.reset(seed=shard_seeds(2022, n_v * world_size, rank, world_size))
+        for _ in range(3):
+            venv_v.step(2 * torch.rand((n_v, A), device=dev, generator=gen) - 1)
+        barrier()
+        kv = 20
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(kv):
+            venv_v.step(2 * torch.rand((n_v, A), device=dev, generator=gen) - 1)
+        r1.record()
+        barrier()
+        t_v = torch.tensor([r0.elapsed_time(r1) / 1e3], dtype=torch.float64, device=dev)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(kv):
+            env_v._sensors.capture()
+        q1.record()
+        torch.cuda.synchronize()
+        raster_ms = q0.elapsed_time(q1) / kv
+        if world_size > 1:
+            dist.all_reduce(t_v, op=dist.ReduceOp.MAX)
+        px_bytes = n_v * 128 * 128 * 12  # Color rgba8 + PositionSegmentation 4 x int16 actually written per image
+        extra = {"workload": f"PickCube-v1 num_envs={n_v}/GPU obs_mode=state+rgb+depth (1 camera 128x128), {kv} steps, no L2 flush",
+                 "env_steps_per_s": n_v * world_size * kv / float(t_v.item()), "ms_per_step": float(t_v.item()) / kv * 1e3,
+                 "raster_kernel_ms": raster_ms, "raster_write_GBps": px_bytes / (raster_ms * 1e-3) / 1e9,
+                 "raster_frac_of_hbm_peak": px_bytes / (raster_ms * 1e-3) / 1e9 / peak}
+        env = env_v
+    line["state_rgbd"] = extra
     if rank == 0:
         if not args.no_cpu_baseline and world_size == 1:
-            cores = os.cpu_count() or 1
-            v, cores, dt = cpu_oracle_throughput(16 * cores, 20)
+            cores = usable_cores()
+            v, cores, dt = cpu_oracle_throughput(64 * cores, 40)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{16 * cores} envs x 20 control steps (5 substeps each) of the same workload, CPU oracle f32, "
+                                    "sample": f"{64 * cores} envs x 40 control steps (5 substeps each) of the same workload, CPU oracle f32, "
                                               f"{cores} threads, {dt:.1f}s"}
         else:
             line["cpu_baseline"] = None
@@ -265,6 +326,7 @@ def main():
     ap.add_argument("--gather-obs", action="store_true", help="all-gather the flattened observation across ranks (NCCL)")
     ap.add_argument("--no-auto-reset", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rgbd", action="store_true", help="skip the supplementary state+RGBD measurement")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
     args = ap.parse_args()
     if args.impl == "reference":
