@@ -12,6 +12,7 @@
 
 #include "b2s_raster.cuh"
 #include "b2s_world.inl"
+#include "b2s_solve.cuh"
 
 namespace {
 
@@ -71,6 +72,35 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   b2s::step_env<C, ND>(M, S, env, substeps, fetch_mask);
+}
+
+// ---- split substep: phase A (one lane per sub-scene, same code as the fused kernel up to the assembled rows) ...
+template <class C, int ND>
+__global__ void __launch_bounds__(32) prep_kernel(b2s::DevModel M, b2s::DevState S) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  b2s::prep_env<C, ND>(M, S, env);
+}
+
+// ---- ... and phase B: L lanes per sub-scene run the Gauss-Seidel sweeps and integrate (b2s_solve.cuh)
+#define B2S_SOLVE_L 4
+#define B2S_SOLVE_THREADS 128
+template <int NUQ>
+__global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel M, b2s::DevState S) {
+  constexpr int MR = b2s::CapsS::MAXROW;
+  constexpr int EPB = B2S_SOLVE_THREADS / B2S_SOLVE_L;  // sub-scenes per block
+  __shared__ float s_lam[EPB][MR];
+  __shared__ float s_tot[EPB][MR];
+  __shared__ float s_stage[EPB][2 * NUQ];
+  const int g = threadIdx.x / B2S_SOLVE_L, lane = threadIdx.x % B2S_SOLVE_L;
+  const int env = blockIdx.x * EPB + g;
+  const bool valid = env < M.n_envs;
+  int n_row = valid ? S.sol_nrow[env] : 0;
+  // the row loop bound must be uniform over the warp (the group reduction uses full-warp shuffles)
+  int nmax = n_row;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  b2s::solve_env<B2S_SOLVE_L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lam[g], s_tot[g], s_stage[g]);
 }
 
 template <class C>
@@ -295,6 +325,21 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   {
     static int forced = getenv("B2S_LANES") ? atoi(getenv("B2S_LANES")) : 0;
     if (forced > 0 && forced <= 32) lanes = forced;
+  }
+  // Split substep (phase A rows -> phase B group solve); the unified velocity vector must fit B2S_NU_MAX slots.
+  static int split_mode = getenv("B2S_SPLIT") ? atoi(getenv("B2S_SPLIT")) : 0;
+  if (split_mode && w->M.n_u <= 28) {
+    const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
+    for (int sidx = 0; sidx < substeps; sidx++) {
+      if (w->caps == 0 && w->M.n_dof == 9) prep_kernel<b2s::CapsS, 9><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0) prep_kernel<b2s::CapsS, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      else prep_kernel<b2s::CapsL, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      if (w->M.n_u <= 16) solve_kernel<16><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
+      else solve_kernel<28><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
+    }
+    CK(cudaGetLastError());
+    if (fetch_mask) return b2s_fetch(world, fetch_mask, stream);
+    return B2S_OK;
   }
   int grid = (N + lanes - 1) / lanes;
   if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);

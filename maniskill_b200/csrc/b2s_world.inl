@@ -72,6 +72,14 @@ struct WorldT {
     M.fb_type = up(m.fb_type, m.n_fb); M.fb_mass = up(m.fb_mass, m.n_fb); M.fb_com = up(m.fb_com, m.n_fb * 3);
     M.fb_inertia = up(m.fb_inertia, m.n_fb * 6); M.fb_damping = up(m.fb_damping, m.n_fb * 2);
     M.fb_gravity = up(m.fb_gravity, m.n_fb); M.fb_ov = up(m.fb_ov, m.n_fb);
+    {
+      std::vector<int> slot(m.n_fb > 0 ? m.n_fb : 1, -1);
+      int nu = nd;
+      for (int b = 0; b < m.n_fb; b++)
+        if (m.fb_type[b] == 0) { slot[b] = nu; nu += 6; }
+      M.fb_slot = up(slot.data(), m.n_fb);
+      M.n_u = nu;
+    }
     M.shape_type = up(m.shape_type, m.n_shape); M.shape_owner_kind = up(m.shape_owner_kind, m.n_shape);
     M.shape_owner = up(m.shape_owner, m.n_shape); M.shape_row = up(m.shape_row, m.n_shape);
     M.shape_hull = up(m.shape_hull, m.n_shape); M.shape_ov = up(m.shape_ov, m.n_shape);
@@ -104,6 +112,9 @@ struct WorldT {
     }
     S.man = zeros<float>((size_t)Caps<12, 4, 32, 1>::MAXMAN * 8 * N);
     S.man_count = zeros<int>(N);
+    S.sol_rows = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * (M.n_u <= 16 ? 44 : 68));
+    S.sol_nrow = zeros<int>(N);
+    S.sol_qdd = zeros<float>((size_t)nd * N);
     S.overflow = zeros<int>(1);
     S.body_data = zeros<float>(N * M.n_rows * 13);
     size_t nq = N * m.n_art * (m.max_dof_per_art > 0 ? m.max_dof_per_art : 1);

@@ -4,6 +4,7 @@
 #include <stdio.h>
 
 #include "../../maniskill_b200/csrc/b2s_world.inl"
+#include "../../maniskill_b200/csrc/b2s_solve.cuh"
 
 namespace {
 struct HostMem {
@@ -29,6 +30,26 @@ void emu_step(void* h, int substeps, unsigned fetch_mask) {
     if (w->caps == 0 && w->M.n_dof == 9) b2s::step_env<b2s::CapsS, 9>(w->M, w->S, e, substeps, fetch_mask);
     else if (w->caps == 0) b2s::step_env<b2s::CapsS, 0>(w->M, w->S, e, substeps, fetch_mask);
     else b2s::step_env<b2s::CapsL, 0>(w->M, w->S, e, substeps, fetch_mask);
+  }
+}
+// split substep (phase A: rows, phase B: group solve with L = 1), what the CUDA library runs with L = 4
+void emu_step_split(void* h, int substeps, unsigned fetch_mask) {
+  World* w = (World*)h;
+  const int MR = b2s::CapsS::MAXROW;
+  float lam[MR], tot[MR], stage[2 * 28];
+  for (int s = 0; s < substeps; s++)
+    for (int e = 0; e < w->M.n_envs; e++) {
+      if (w->caps == 0 && w->M.n_dof == 9) b2s::prep_env<b2s::CapsS, 9>(w->M, w->S, e);
+      else if (w->caps == 0) b2s::prep_env<b2s::CapsS, 0>(w->M, w->S, e);
+      else b2s::prep_env<b2s::CapsL, 0>(w->M, w->S, e);
+      if (w->M.n_u <= 16) b2s::solve_env<1, 16, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
+      else b2s::solve_env<1, 28, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
+    }
+  if (fetch_mask) {
+    for (int e = 0; e < w->M.n_envs; e++) {
+      if (w->caps == 0) b2s::fetch_env<b2s::CapsS>(w->M, w->S, e, fetch_mask);
+      else b2s::fetch_env<b2s::CapsL>(w->M, w->S, e, fetch_mask);
+    }
   }
 }
 void emu_apply(void* h, unsigned mask) {
