@@ -327,7 +327,7 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
     if (forced > 0 && forced <= 32) lanes = forced;
   }
   // Split substep (phase A rows -> phase B group solve); the unified velocity vector must fit B2S_NU_MAX slots.
-  static int split_mode = getenv("B2S_SPLIT") ? atoi(getenv("B2S_SPLIT")) : 0;
+  static int split_mode = getenv("B2S_SPLIT") ? atoi(getenv("B2S_SPLIT")) : 1;  // measured 2.45 vs 3.29 ms per control step (4096 envs)
   if (split_mode && w->M.n_u <= 28) {
     const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
     for (int sidx = 0; sidx < substeps; sidx++) {
