@@ -331,9 +331,10 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   if (split_mode && w->M.n_u <= 28) {
     const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
     for (int sidx = 0; sidx < substeps; sidx++) {
-      if (w->caps == 0 && w->M.n_dof == 9) prep_kernel<b2s::CapsS, 9><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0) prep_kernel<b2s::CapsS, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
-      else prep_kernel<b2s::CapsL, 0><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      const int pg = (N + lanes - 1) / lanes;
+      if (w->caps == 0 && w->M.n_dof == 9) prep_kernel<b2s::CapsS, 9><<<pg, lanes, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0) prep_kernel<b2s::CapsS, 0><<<pg, lanes, 0, st>>>(w->M, w->S);
+      else prep_kernel<b2s::CapsL, 0><<<pg, lanes, 0, st>>>(w->M, w->S);
       if (w->M.n_u <= 16) solve_kernel<16><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
       else solve_kernel<28><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
     }
