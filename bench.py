@@ -124,7 +124,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = usable_cores()
-    sample_envs = 64 * cores
+    sample_envs = 256 * cores
     # warm-up + K steps, each step = one control step of the bounded sample
     v, cores, dt = cpu_oracle_throughput(sample_envs, max(args.steps, 1))
     line = {
@@ -134,7 +134,7 @@ def run_reference(args):
         "config": {"workload": "PickCube-v1 num_envs=4096/GPU state-only (configs[1]); CPU arm runs a bounded sample",
                    "sample_envs": sample_envs, "substeps_per_step": 5},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_envs} envs x {args.steps} control steps (5 substeps each), CPU oracle f32, {cores} threads"},
+                         "sample": f"{sample_envs} envs x {args.steps} control steps (5 substeps each), CPU oracle f32, {cores} worker processes"},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -304,10 +304,10 @@ def run_gpu(args):
     if rank == 0:
         if not args.no_cpu_baseline and world_size == 1:
             cores = usable_cores()
-            v, cores, dt = cpu_oracle_throughput(64 * cores, 40)
+            v, cores, dt = cpu_oracle_throughput(256 * cores, 100)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{64 * cores} envs x 40 control steps (5 substeps each) of the same workload, CPU oracle f32, "
-                                              f"{cores} threads, {dt:.1f}s"}
+                                    "sample": f"{256 * cores} envs x 100 control steps (5 substeps each) of the same workload, CPU oracle f32, "
+                                              f"{cores} worker processes (usable cores), {dt:.1f}s wall"}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
