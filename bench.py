@@ -263,7 +263,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": args.traffic_bytes, "peak_source": peak_src, "kernel": "b2s_step: 5 substeps = 5 x (prep_kernel + solve_kernel) + fetch_kernel",
+                     "traffic": args.traffic_bytes, "peak_source": peak_src, "kernel": "b2s_step: 5 substeps x (kin + collide + manifest + rowfill + solve kernels) + fetch_kernel",
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_per_launch},
     }
     # ---------------- supplementary: the RGBD half of BASELINE.json's metric (PickCube-v1 state+rgb+depth, one 128x128 camera)

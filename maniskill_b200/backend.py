@@ -173,10 +173,16 @@ class World:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _step_launches(self, substeps, fetch_mask):
+        """Kernels one b2s_step launches (csrc/b2s_api.cu): kin, collide, manifest, rowfill, solve per substep + the fetch."""
+        if os.environ.get("B2S_FUSED", "0") not in ("", "0"):
+            return 1
+        return 5 * int(substeps) + (1 if fetch_mask else 0)
+
     # ------------------------------------------------------------------ px.* entry points
     def step(self, substeps: int = 1, fetch_mask: int = 0):
         _check(self.lib, self.lib.b2s_step(self.h, substeps, fetch_mask, self._stream()))
-        self.kernel_launches += 1
+        self.kernel_launches += self._step_launches(substeps, fetch_mask)
 
     def apply(self, mask: int = BUF_APPLY_ALL):
         _check(self.lib, self.lib.b2s_apply(self.h, mask, self._stream()))
@@ -230,7 +236,7 @@ class World:
         out = B2SPickOutputs(obs.data_ptr(), reward.data_ptr(), flags.data_ptr(), elapsed.data_ptr())
         a = C.c_void_p(actions.data_ptr()) if actions is not None else None
         _check(self.lib, self.lib.b2s_pick_task_step(self.h, handle, a, int(substeps), C.byref(out), self._stream()))
-        self.kernel_launches += 3 if actions is not None else 2
+        self.kernel_launches += (2 if actions is not None else 1) + self._step_launches(substeps, BUF_ALL)
 
     # ------------------------------------------------------------------ rendering
     def create_camera_group(self, cameras, visuals):

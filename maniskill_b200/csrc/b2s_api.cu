@@ -1,9 +1,9 @@
 // libb200sim.so -- C-ABI (include/b200sim.h) over the sm_100a kernels.
 //
-// Launch geometry for the fused substep kernel: one lane per sub-scene, 32-lane CTAs so that n_envs = 4096 spreads as
-// 128 CTAs over the 148 SMs (one resident warp per SM; the per-lane scratch of a substep is several KB, so residency
-// is bounded by local memory traffic, not by warps).  State is env-major SoA so every global access of a warp is one
-// fully-coalesced 128 B line per slot.
+// b2s_step launches the pipelined substep (b2s_pipe.cuh, b2s_solve.cuh): per physics substep kin -> collide -> manifest ->
+// rowfill -> solve, each at its own width (lane per sub-scene / per candidate pair / per row / 4 lanes per sub-scene), exchanging
+// L2-resident env-major struct-of-arrays buffers.  State is env-major SoA so a warp's access to a slot is one coalesced line.
+// B2S_FUSED=1 selects the single-kernel form (one lane per sub-scene, everything in per-lane scratch) kept for comparison.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
@@ -12,7 +12,7 @@
 
 #include "b2s_raster.cuh"
 #include "b2s_world.inl"
-#include "b2s_solve.cuh"
+#include "b2s_pipe.cuh"
 
 namespace {
 
@@ -74,25 +74,16 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
   b2s::step_env<C, ND>(M, S, env, substeps, fetch_mask);
 }
 
-// ---- split substep: phase A (one lane per sub-scene, same code as the fused kernel up to the assembled rows) ...
-template <class C, int ND>
-__global__ void __launch_bounds__(32) prep_kernel(b2s::DevModel M, b2s::DevState S) {
-  int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= M.n_envs) return;
-  b2s::prep_env<C, ND>(M, S, env);
-}
-
-// ---- ... and phase B: L lanes per sub-scene run the Gauss-Seidel sweeps and integrate (b2s_solve.cuh)
-#define B2S_SOLVE_L 4
+// ---- phase B: L lanes per sub-scene run the Gauss-Seidel sweeps and integrate (b2s_solve.cuh)
 #define B2S_SOLVE_THREADS 128
-template <int NUQ>
+template <int NUQ, int L>
 __global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel M, b2s::DevState S) {
   constexpr int MR = b2s::CapsS::MAXROW;
-  constexpr int EPB = B2S_SOLVE_THREADS / B2S_SOLVE_L;  // sub-scenes per block
+  constexpr int EPB = B2S_SOLVE_THREADS / L;  // sub-scenes per block
   __shared__ float s_lam[EPB][MR];
   __shared__ float s_tot[EPB][MR];
   __shared__ float s_stage[EPB][2 * NUQ];
-  const int g = threadIdx.x / B2S_SOLVE_L, lane = threadIdx.x % B2S_SOLVE_L;
+  const int g = threadIdx.x / L, lane = threadIdx.x % L;
   const int env = blockIdx.x * EPB + g;
   const bool valid = env < M.n_envs;
   int n_row = valid ? S.sol_nrow[env] : 0;
@@ -100,7 +91,55 @@ __global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel 
   int nmax = n_row;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-  b2s::solve_env<B2S_SOLVE_L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lam[g], s_tot[g], s_stage[g]);
+  b2s::solve_env<L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lam[g], s_tot[g], s_stage[g]);
+}
+
+// Lanes per sub-scene in phase B.  Every sub-scene is resident at once, so the launch lasts as long as the slowest one: what counts
+// is the dependent chain of a row visit.  Measured on B200 (PickCube-v1, ms per control step, 4096 / 16384 envs): 4 lanes
+// 0.93 / 1.78, 8 lanes 0.93 / 1.82, 16 lanes 1.00 / 2.21; one lane per sub-scene with instruction-level parallelism instead of
+// shuffles was 1.4 / 2.2.  B2S_SOLVE_L (4, 8, 16) overrides for experiments.
+static void launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st) {
+  static int forced = getenv("B2S_SOLVE_L") ? atoi(getenv("B2S_SOLVE_L")) : 0;
+  const int N = M.n_envs;
+  const int L = (M.n_u <= 16 && (forced == 8 || forced == 16)) ? forced : 4;
+  const int epb = B2S_SOLVE_THREADS / L;
+  const int grid = (N + epb - 1) / epb;
+  if (M.n_u > 16) solve_kernel<28, 4><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  else if (L == 16) solve_kernel<16, 16><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  else if (L == 8) solve_kernel<16, 8><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  else solve_kernel<16, 4><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+}
+
+// ---- pipelined phase A (b2s_pipe.cuh): kin (lane per sub-scene) -> collide (lane per candidate pair x sub-scene) ->
+// manifest (lane per sub-scene) -> rowfill (lane per row x sub-scene); phase B is the solve_kernel above
+template <class C, int ND>
+__global__ void __launch_bounds__(32) kin_kernel(b2s::DevModel M, b2s::DevState S) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  b2s::kin_env<C, ND>(M, S, env);
+}
+
+#define B2S_COLLIDE_THREADS 64
+__global__ void __launch_bounds__(B2S_COLLIDE_THREADS) collide_kernel(b2s::DevModel M, b2s::DevState S) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  b2s::collide_env(M, S, env, blockIdx.y);
+}
+
+template <class C>
+__global__ void __launch_bounds__(64) manifest_kernel(b2s::DevModel M, b2s::DevState S) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  b2s::manifest_env<C>(M, S, env);
+}
+
+template <class C, int ND, int NUQ>
+__global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevState S) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  const int r = blockIdx.y;
+  if (r >= S.sol_nrow[env]) return;
+  b2s::rowfill_env<C, ND, NUQ>(M, S, env, r);
 }
 
 template <class C>
@@ -317,35 +356,36 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
-  // Lanes per warp.  Measured on B200 at 4096 envs (bench.py, ms per control step): 32 lanes 3.38, 16 lanes 3.76,
-  // 8 lanes 4.27, 4 lanes 5.16 -- spreading the envs over more, partially filled warps shortens the divergent union of
-  // control flow per warp but several warps per SM then stream different parts of the ~0.5 MB kernel through the
-  // instruction caches, which costs more.  Full warps it is; B2S_LANES overrides for experiments.
-  int lanes = 32;
-  {
-    static int forced = getenv("B2S_LANES") ? atoi(getenv("B2S_LANES")) : 0;
-    if (forced > 0 && forced <= 32) lanes = forced;
-  }
-  // Split substep (phase A rows -> phase B group solve); the unified velocity vector must fit B2S_NU_MAX slots.
-  static int split_mode = getenv("B2S_SPLIT") ? atoi(getenv("B2S_SPLIT")) : 1;  // measured 2.45 vs 3.29 ms per control step (4096 envs)
-  if (split_mode && w->M.n_u <= 28) {
-    const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
+  static int fused = getenv("B2S_FUSED") ? atoi(getenv("B2S_FUSED")) : 0;
+  if (!fused && w->M.n_u <= 28) {
+    const int MR = b2s::CapsS::MAXROW;
     for (int sidx = 0; sidx < substeps; sidx++) {
-      const int pg = (N + lanes - 1) / lanes;
-      if (w->caps == 0 && w->M.n_dof == 9) prep_kernel<b2s::CapsS, 9><<<pg, lanes, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0) prep_kernel<b2s::CapsS, 0><<<pg, lanes, 0, st>>>(w->M, w->S);
-      else prep_kernel<b2s::CapsL, 0><<<pg, lanes, 0, st>>>(w->M, w->S);
-      if (w->M.n_u <= 16) solve_kernel<16><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
-      else solve_kernel<28><<<(N + epb - 1) / epb, B2S_SOLVE_THREADS, 0, st>>>(w->M, w->S);
+      const int pg = (N + 31) / 32;
+      if (w->caps == 0 && w->M.n_dof == 9) kin_kernel<b2s::CapsS, 9><<<pg, 32, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0) kin_kernel<b2s::CapsS, 0><<<pg, 32, 0, st>>>(w->M, w->S);
+      else kin_kernel<b2s::CapsL, 0><<<pg, 32, 0, st>>>(w->M, w->S);
+      if (w->M.n_pair > 0)
+        collide_kernel<<<dim3((N + B2S_COLLIDE_THREADS - 1) / B2S_COLLIDE_THREADS, w->M.n_pair), B2S_COLLIDE_THREADS, 0, st>>>(w->M, w->S);
+      if (w->caps == 0) manifest_kernel<b2s::CapsS><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      else manifest_kernel<b2s::CapsL><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      const dim3 rg((N + 127) / 128, MR);
+      if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 9, 16><<<rg, 128, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0) rowfill_kernel<b2s::CapsS, 0, 28><<<rg, 128, 0, st>>>(w->M, w->S);
+      else if (w->M.n_u <= 16) rowfill_kernel<b2s::CapsL, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
+      else rowfill_kernel<b2s::CapsL, 0, 28><<<rg, 128, 0, st>>>(w->M, w->S);
+      launch_solve(w->M, w->S, st);
     }
     CK(cudaGetLastError());
     if (fetch_mask) return b2s_fetch(world, fetch_mask, stream);
     return B2S_OK;
   }
-  int grid = (N + lanes - 1) / lanes;
-  if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
-  else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
-  else step_kernel<b2s::CapsL, 0><<<grid, lanes, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  // single-kernel form: one lane per sub-scene, 32-lane CTAs (fewer lanes per warp measured slower: the ~0.5 MB kernel thrashes
+  // the instruction caches when several warps per SM run different phases)
+  int grid = (N + 31) / 32;
+  if (w->caps == 0 && w->M.n_dof == 9) step_kernel<b2s::CapsS, 9><<<grid, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<grid, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
+  else step_kernel<b2s::CapsL, 0><<<grid, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
   CK(cudaGetLastError());
   return B2S_OK;
 }

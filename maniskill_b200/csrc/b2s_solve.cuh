@@ -1,6 +1,6 @@
-// b200sim split substep, phase B: the sub-stepped soft TGS solve + integration of one sub-scene by a GROUP of L lanes.
+// b200sim pipelined substep, phase B: the sub-stepped soft TGS solve + integration of one sub-scene by a GROUP of L lanes.
 //
-// Phase A (b2s_step.cuh, `substep<..., SPLIT=true>`, one lane per sub-scene) leaves, per sub-scene, a table of constraint rows in a
+// Phase A (b2s_pipe.cuh: kin -> collide -> manifest -> rowfill) leaves, per sub-scene, a table of constraint rows in a
 // unified layout: the generalised velocity of the sub-scene is one vector u[NUQ] = [joint velocities (n_dof) | per DYNAMIC free
 // body: linear(3) angular(3)] (NUQ = 16 or 28 slots), and every row is two dense NUQ-vectors (Jacobian Ju, response
 // Bu = M~^-1 Ju^T) plus 12 scalars (16-byte aligned records of 176 or 272 bytes).  Phase B runs the 15 + 1 Gauss-Seidel sweeps
@@ -53,6 +53,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
   const float omega = 2.f * kPi * fminf(M.contact_hertz, 0.25f / h), zeta = M.contact_zeta;
   const float sa1 = 2.f * zeta + h * omega, sa2 = h * omega * sa1, sa3 = 1.f / (1.f + sa2);
   const float soft_rate = omega / sa1, soft_mass = sa2 * sa3, soft_imp = sa3;
+  const float inv_h = 1.f / h, max_depen = M.max_depen_vel;
   const int n_row = valid ? St.sol_nrow[env] : 0;
   const float* rows = St.sol_rows + (size_t)(valid ? env : 0) * MAXROW * RF;
   float u[SL], du[SL], uf[SL], ac[SL], af[SL], dm[SL];
@@ -104,6 +105,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       for (int k = 0; k < 5; k++) scn[k] = rows[2 * NUQ + k];
       scn[5] = rows[2 * NUQ + 8];
     }
+#pragma unroll 2
     for (int r = 0; r < nrow_max; r++) {
       const bool act = r < n_row;
       float Jc[SL], Bc[SL], sc[6];
@@ -119,43 +121,45 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
         for (int k = 0; k < 5; k++) scn[k] = Rn[2 * NUQ + k];
         scn[5] = Rn[2 * NUQ + 8];
       }
-      float jv = 0.f, sd = 0.f;
-      if (act) {
-#pragma unroll
-        for (int k = 0; k < SL; k++) {
-          jv += Jc[k] * u[k];
-          sd += Jc[k] * du[k];
-        }
-      }
-      jv = group_sum<L>(jv);
-      sd = group_sum<L>(sd);
-      if (!act) continue;
-      const float dinv = sc[0], gamma = sc[1], s0 = sc[2], mu = sc[3];
+      // branch-free row visit (the lanes of a warp hold rows of different types).  Loads from the impulse table first: they do
+      // not depend on the reduction.  Friction bound = mu x (sum of the <= 4 normal impulses of the patch).
       const int meta = as_int(sc[4]);
-      jv += sc[5];  // constant contribution of kinematic bodies
       const int ty = meta & 0xff;
-      const float lamr = lam[r];
-      float nl;
-      if (ty == ROW_FRICTION) {
-        const int nrow = (meta >> 8) & 0xff, ncount = (meta >> 16) & 0xff;
-        float nsum = 0.f;
-        for (int k = 0; k < ncount; k++) nsum += lam[nrow + k];
-        const float lim = mu * nsum;
-        nl = fmaxf(-lim, fminf(lim, lamr - jv * dinv));
-      } else if (ty == ROW_EQ) {
-        const float s = s0 + sd;
-        const float bias = relax ? 0.f : s / h;
-        nl = lamr - (jv + bias + gamma * lamr) * dinv;
-      } else {
-        const float s = s0 + sd;
-        float bias, ms = 1.f, is = 0.f;
-        if (s > 0.f) bias = s / h;
-        else if (relax) bias = 0.f;
-        else { bias = fmaxf(soft_rate * s, -M.max_depen_vel); ms = soft_mass; is = soft_imp; }
-        nl = fmaxf(0.f, lamr - dinv * ms * (jv + bias) - is * lamr);
+      const bool fric = ty == ROW_FRICTION, eq = ty == ROW_EQ;
+      const int nrow = (meta >> 8) & 0xff, ncount = fric ? (meta >> 16) & 0xff : 0;
+      float nsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int rk = nrow + k < MAXROW ? nrow + k : MAXROW - 1;
+        const float lk = lam[rk];
+        nsum += k < ncount ? lk : 0.f;
       }
-      const float dl = nl - lamr;
-      lam[r] = nl;  // every lane of the group writes the same value
+      const float lamr = lam[act ? r : 0];
+      float jp[2] = {0.f, 0.f}, sp[2] = {0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < SL; k++) {
+        jp[k & 1] += Jc[k] * u[k];
+        sp[k & 1] += Jc[k] * du[k];
+      }
+      const float jv = group_sum<L>(jp[0] + jp[1]) + sc[5];  // + constant contribution of kinematic bodies
+      const float sep = sc[2] + group_sum<L>(sp[0] + sp[1]);
+      const float dinv = sc[0], gamma = sc[1], mu = sc[3];
+      // nl = clamp(lamr - dinv * ms * (jv + bias) - c * lamr, lo, hi)
+      //   contact / limit: open (sep > 0): exact bias sep/h; else soft constraint during the position sweeps, no bias in the relaxation
+      //   tendon: bias sep/h (position sweeps), regularised by gamma;   friction: no bias, box bound
+      const bool open = sep > 0.f;
+      const float sh = sep * inv_h;
+      const float bias_c = open ? sh : (relax ? 0.f : fmaxf(soft_rate * sep, -max_depen));
+      const float bias = fric ? 0.f : (eq ? (relax ? 0.f : sh) : bias_c);
+      const bool use_soft = !fric && !eq && !open && !relax;
+      const float ms = use_soft ? soft_mass : 1.f;
+      const float c = eq ? gamma * dinv : (use_soft ? soft_imp : 0.f);
+      const float lim = mu * nsum;
+      const float lo = fric ? -lim : (eq ? -3.0e38f : 0.f), hi = fric ? lim : 3.0e38f;
+      float nl = lamr - dinv * ms * (jv + bias) - c * lamr;
+      nl = fminf(fmaxf(nl, lo), hi);
+      const float dl = act ? nl - lamr : 0.f;
+      if (act) lam[r] = nl;  // every lane of the group writes the same value
 #pragma unroll
       for (int k = 0; k < SL; k++) u[k] += Bc[k] * dl;
     }
@@ -176,14 +180,15 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     stage[NUQ + k * L + lane] = du[k];
   }
   group_sync();
-  if (!valid || lane != 0) return;
-  for (int i = 0; i < nd; i++) {
+  if (!valid) return;
+  // the lanes of the group share the export: joints and bodies strided by lane, patch impulses by output slot
+  for (int i = lane; i < nd; i += L) {
     const float v1 = stage[i], qd0 = St.qd[i * N + env];
     St.qacc[i * N + env] = (v1 - qd0) / dt;
     St.q[i * N + env] += stage[NUQ + i];
     St.qd[i * N + env] = v1;
   }
-  for (int b = 0; b < nfb; b++) {
+  for (int b = lane; b < nfb; b += L) {
     const int o_ = M.fb_slot[b];
     if (o_ < 0) continue;
     float f[7];
@@ -202,11 +207,12 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     const float o[13] = {pn.x, pn.y, pn.z, qn.w, qn.x, qn.y, qn.z, sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
     for (int k = 0; k < 13; k++) St.fb[(size_t)(b * 13 + k) * N + env] = o[k];
   }
-  // contact patch impulses: sum over the rows of a patch of (row direction x impulse accumulated over the step)
+  // contact patch impulses: sum over the rows of a patch of (row direction x impulse accumulated over the step); a lane owns the
+  // output slots congruent to it, so the accumulation order per slot is the row order
   for (int r = 0; r < n_row; r++) {
     const float* Sc = rows + (size_t)r * RF + 2 * NUQ;
     const int slot = ((as_int(Sc[4]) >> 24) & 0xff) - 1;
-    if (slot < 0) continue;
+    if (slot < 0 || slot % L != lane) continue;
     float* o = St.man + (size_t)(slot * 8) * N + env;
     const float t = tot[r];
     o[2 * N] += Sc[5] * t; o[3 * N] += Sc[6] * t; o[4 * N] += Sc[7] * t;

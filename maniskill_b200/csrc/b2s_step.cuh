@@ -62,10 +62,18 @@ struct DevState {
   // exposed env-major AoS buffers (the reference's px.cuda_* layout)
   float* body_data;                      // [n_envs, n_rows, 13]
   float *xq, *xqd, *xqacc, *xqf, *xtq, *xtqd;  // [n_envs*n_art, max_dof_per_art]
-  // split-substep exchange (phase A -> phase B, b2s_solve.cuh)
-  float* sol_rows;                       // [n_envs, MAXROW, 64] unified constraint rows
+  // pipelined substep exchange, phase A -> phase B (b2s_pipe.cuh -> b2s_solve.cuh)
+  float* sol_rows;                       // [n_envs, MAXROW, 44 | 68] unified constraint rows (AoS)
   int* sol_nrow;                         // [n_envs]
   float* sol_qdd;                        // [n_dof][n_envs] free joint accelerations
+  // pipelined substep exchange (b2s_pipe.cuh), SoA [slot][n_envs] unless noted
+  float* kin_link;                       // [n_dof*19]  joint frame pose, spatial velocity, motion axis
+  float* kin_minv;                       // [n_dof*n_dof]  M~^-1
+  float* kin_fb;                         // [n_fb*13]  world com, 1/m, world inverse inertia
+  int* col_n;                            // [n_pair]  contact points of a candidate pair (valid where the hit bit is set)
+  unsigned* col_mask;                    // [ceil(n_pair/32)]  hit bitmap over the candidate pairs
+  float* col_data;                       // [n_pair*19]  normal, 4 x (point, separation)
+  float* row_desc;                       // [n_envs, MAXROW, 16]  row descriptors (AoS)
 };
 
 enum { OWNER_STATIC = 0, OWNER_LINK = 1, OWNER_BODY = 2 };
@@ -149,9 +157,8 @@ B2S_HDN void fk(const DevModel& M, Lane<C>& L) {
 
 // ND > 0 fixes the dof count at compile time (loops over joints unroll, the velocity vectors live in registers);
 // ND == 0 reads it from the model.
-// SPLIT: stop after the constraint rows are assembled and hand them to phase B (b2s_solve.cuh) through `St`.
-template <class C, int ND, bool SPLIT = false>
-B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow, const DevState* St = nullptr) {
+template <class C, int ND>
+B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   const int N = M.n_envs;
   const int nd = ND > 0 ? ND : M.n_dof;
   const float dt = M.dt;
@@ -629,54 +636,6 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow, cons
     // remember which output slot this manifold uses (mi may differ from mo if rows overflowed)
     man_np[mi] = -1 - mo;
   }
-  if (SPLIT) {
-    // unified rows: u = [joint velocities | per DYNAMIC free body linear(3) angular(3)]; NUQ slots (16 or 28),
-    // 2*NUQ + 12 floats per row (see b2s_solve.cuh).  Kinematic bodies only contribute a constant to the row velocity.
-    const int NUQ = M.n_u <= 16 ? 16 : 28, RF = 2 * NUQ + 12;
-    float* rows = St->sol_rows + (size_t)env * C::MAXROW * RF;
-    for (int ri = 0; ri < n_row; ri++) {
-      float* R = rows + (size_t)ri * RF;
-      for (int k = 0; k < 2 * NUQ; k++) R[k] = 0.f;
-      float ckin = 0.f;
-      if (r_art[ri] >= 0) {
-        const float* J_ = JB[r_art[ri]];
-        for (int j = 0; j < nd; j++) { R[j] = J_[j]; R[NUQ + j] = J_[C::MAXD + j]; }
-      }
-      for (int sde = 0; sde < 2; sde++) {
-        int b_ = sde == 0 ? r_fb0[ri] : r_fb1[ri];
-        if (b_ < 0) continue;
-        v3 lin_ = r_angonly[ri] ? mk3(0, 0, 0) : (sde == 0 ? r_dir[ri] : -r_dir[ri]);
-        v3 ang_ = sde == 0 ? r_ang0[ri] : r_ang1[ri];
-        v3 Ba_ = sde == 0 ? r_Bang0[ri] : r_Bang1[ri];
-        int o_ = M.fb_slot[b_];
-        if (o_ < 0) { ckin += dot(lin_, L.fbv[b_]) + dot(ang_, L.fbw[b_]); continue; }
-        v3 Bl_ = lin_ * finvm[b_];
-        R[o_] = lin_.x; R[o_ + 1] = lin_.y; R[o_ + 2] = lin_.z; R[o_ + 3] = ang_.x; R[o_ + 4] = ang_.y; R[o_ + 5] = ang_.z;
-        R[NUQ + o_] = Bl_.x; R[NUQ + o_ + 1] = Bl_.y; R[NUQ + o_ + 2] = Bl_.z;
-        R[NUQ + o_ + 3] = Ba_.x; R[NUQ + o_ + 4] = Ba_.y; R[NUQ + o_ + 5] = Ba_.z;
-      }
-      float* Sc = R + 2 * NUQ;
-      Sc[0] = r_dinv[ri]; Sc[1] = r_gamma[ri]; Sc[2] = r_s0[ri]; Sc[3] = r_mu[ri];
-      int slot_ = r_man[ri] >= 0 ? -1 - man_np[r_man[ri]] : -1;
-      int meta_ = (r_type[ri] & 0xff) | ((r_nrow[ri] < 0 ? 0 : r_nrow[ri]) << 8) | ((r_ncount[ri] & 0xff) << 16) | (((slot_ + 1) & 0xff) << 24);
-      union { int i; float f; } cv_;
-      cv_.i = meta_;
-      Sc[4] = cv_.f;
-      Sc[5] = r_dir[ri].x; Sc[6] = r_dir[ri].y; Sc[7] = r_dir[ri].z;
-      Sc[8] = ckin; Sc[9] = 0.f; Sc[10] = 0.f; Sc[11] = 0.f;
-    }
-    St->sol_nrow[env] = n_row;
-    const size_t Nn = M.n_envs;
-    for (int j = 0; j < nd; j++) St->sol_qdd[j * Nn + env] = qdd[j];
-    St->man_count[env] = L.n_man;
-    for (int m_ = 0; m_ < L.n_man; m_++) {
-      float* o = St->man + (size_t)(m_ * 8) * Nn + env;
-      o[0] = (float)L.man_rowA[m_]; o[Nn] = (float)L.man_rowB[m_];
-      o[2 * Nn] = 0.f; o[3 * Nn] = 0.f; o[4 * Nn] = 0.f;
-      o[5 * Nn] = (float)L.man_npts[m_]; o[6 * Nn] = L.man_sep[m_];
-    }
-    return;
-  }
   // ---------------------------------------------------------------- 5. sub-stepped soft TGS
   float dq[C::MAXD], vfree[C::MAXD], ac[C::MAXD];
   for (int j = 0; j < nd; j++) { dq[j] = 0.f; ac[j] = 0.f; }
@@ -961,16 +920,6 @@ B2S_HDN void step_env(const DevModel& M, const DevState& St, int env, int subste
     fk<C>(M, L);
     fetch_lane<C>(M, St, env, L, fetch_mask);
   }
-}
-
-// phase A of the split substep: everything up to the assembled constraint rows (state is only read)
-template <class C, int ND>
-B2S_HDN void prep_env(const DevModel& M, const DevState& St, int env) {
-  Lane<C> L;
-  load_lane<C>(M, St, env, L);
-  int ovf = 0;
-  substep<C, ND, true>(M, L, env, &ovf, &St);
-  if (ovf) *St.overflow = 1;
 }
 
 template <class C>

@@ -115,6 +115,13 @@ struct WorldT {
     S.sol_rows = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * (M.n_u <= 16 ? 44 : 68));
     S.sol_nrow = zeros<int>(N);
     S.sol_qdd = zeros<float>((size_t)nd * N);
+    S.kin_link = zeros<float>((size_t)nd * 19 * N);
+    S.kin_minv = zeros<float>((size_t)nd * nd * N);
+    S.kin_fb = zeros<float>((size_t)m.n_fb * 13 * N);
+    S.col_n = zeros<int>((size_t)m.n_pair * N);
+    S.col_mask = zeros<unsigned>((size_t)((m.n_pair + 31) / 32) * N);
+    S.col_data = zeros<float>((size_t)m.n_pair * 19 * N);
+    S.row_desc = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * 16);
     S.overflow = zeros<int>(1);
     S.body_data = zeros<float>(N * M.n_rows * 13);
     size_t nq = N * m.n_art * (m.max_dof_per_art > 0 ? m.max_dof_per_art : 1);

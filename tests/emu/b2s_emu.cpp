@@ -4,7 +4,7 @@
 #include <stdio.h>
 
 #include "../../maniskill_b200/csrc/b2s_world.inl"
-#include "../../maniskill_b200/csrc/b2s_solve.cuh"
+#include "../../maniskill_b200/csrc/b2s_pipe.cuh"
 
 namespace {
 struct HostMem {
@@ -15,6 +15,20 @@ struct HostMem {
 };
 typedef b2s::WorldT<HostMem> World;
 }  // namespace
+
+// pipelined substep (kin -> collide per pair -> manifest -> rowfill per row -> group solve with L = 1), what the CUDA library runs
+template <class C, int ND, int NUQ>
+static void pipe_substep(World* w) {
+  const int MR = b2s::CapsS::MAXROW;
+  float lam[MR], tot[MR], stage[2 * 28];
+  for (int e = 0; e < w->M.n_envs; e++) {
+    b2s::kin_env<C, ND>(w->M, w->S, e);
+    for (int k = 0; k < w->M.n_pair; k++) b2s::collide_env(w->M, w->S, e, k);
+    b2s::manifest_env<C>(w->M, w->S, e);
+    for (int r = 0; r < w->S.sol_nrow[e]; r++) b2s::rowfill_env<C, ND, NUQ>(w->M, w->S, e, r);
+    b2s::solve_env<1, NUQ, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
+  }
+}
 
 extern "C" {
 void* emu_create(const B2SModel* m) {
@@ -32,19 +46,16 @@ void emu_step(void* h, int substeps, unsigned fetch_mask) {
     else b2s::step_env<b2s::CapsL, 0>(w->M, w->S, e, substeps, fetch_mask);
   }
 }
-// split substep (phase A: rows, phase B: group solve with L = 1), what the CUDA library runs with L = 4
-void emu_step_split(void* h, int substeps, unsigned fetch_mask) {
+void emu_step_pipe(void* h, int substeps, unsigned fetch_mask) {
   World* w = (World*)h;
-  const int MR = b2s::CapsS::MAXROW;
-  float lam[MR], tot[MR], stage[2 * 28];
-  for (int s = 0; s < substeps; s++)
-    for (int e = 0; e < w->M.n_envs; e++) {
-      if (w->caps == 0 && w->M.n_dof == 9) b2s::prep_env<b2s::CapsS, 9>(w->M, w->S, e);
-      else if (w->caps == 0) b2s::prep_env<b2s::CapsS, 0>(w->M, w->S, e);
-      else b2s::prep_env<b2s::CapsL, 0>(w->M, w->S, e);
-      if (w->M.n_u <= 16) b2s::solve_env<1, 16, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
-      else b2s::solve_env<1, 28, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
-    }
+  for (int s = 0; s < substeps; s++) {
+    const bool small_u = w->M.n_u <= 16;
+    if (w->caps == 0 && w->M.n_dof == 9 && small_u) pipe_substep<b2s::CapsS, 9, 16>(w);
+    else if (w->caps == 0 && small_u) pipe_substep<b2s::CapsS, 0, 16>(w);
+    else if (w->caps == 0) pipe_substep<b2s::CapsS, 0, 28>(w);
+    else if (small_u) pipe_substep<b2s::CapsL, 0, 16>(w);
+    else pipe_substep<b2s::CapsL, 0, 28>(w);
+  }
   if (fetch_mask) {
     for (int e = 0; e < w->M.n_envs; e++) {
       if (w->caps == 0) b2s::fetch_env<b2s::CapsS>(w->M, w->S, e, fetch_mask);
@@ -81,3 +92,4 @@ float* emu_buffer(void* h, int which) {
 int* emu_man_count(void* h) { return ((World*)h)->S.man_count; }
 int emu_overflow(void* h) { return *((World*)h)->S.overflow; }
 }
+extern "C" int* emu_nrow(void* h) { return ((World*)h)->S.sol_nrow; }

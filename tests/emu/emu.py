@@ -14,7 +14,7 @@ BUF_ALL = 0xFFFFFFFF
 def _build():
     so = os.path.join(_DIR, "libb2s_emu.so")
     srcs = [os.path.join(_DIR, "b2s_emu.cpp")] + [os.path.join(_DIR, "../../maniskill_b200/csrc", f) for f in
-                                                   ("b2s_math.cuh", "b2s_collide.cuh", "b2s_step.cuh", "b2s_solve.cuh", "b2s_world.inl",
+                                                   ("b2s_math.cuh", "b2s_collide.cuh", "b2s_step.cuh", "b2s_solve.cuh", "b2s_pipe.cuh", "b2s_world.inl",
                                                     "../../include/b200sim.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-x", "c++", "-o", so, srcs[0]])
@@ -32,7 +32,7 @@ def lib():
         _lib.emu_create.argtypes = [C.c_void_p]
         _lib.emu_destroy.argtypes = [C.c_void_p]
         _lib.emu_step.argtypes = [C.c_void_p, C.c_int, C.c_uint]
-        _lib.emu_step_split.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+        _lib.emu_step_pipe.argtypes = [C.c_void_p, C.c_int, C.c_uint]
         _lib.emu_apply.argtypes = [C.c_void_p, C.c_uint]
         _lib.emu_fetch.argtypes = [C.c_void_p, C.c_uint]
         _lib.emu_buffer.restype = C.POINTER(C.c_float)
@@ -63,10 +63,12 @@ class EmuWorld:
         self.man_count = np.ctypeslib.as_array(lib().emu_man_count(self.h), shape=(N,))
         lib().emu_fetch(self.h, BUF_ALL)
 
-    split = False  # True: run the two-phase substep (what the CUDA library does), False: the single fused function
+    # True: the pipelined substep (kin -> collide -> manifest -> rowfill -> solve) the CUDA library runs; False: the single-lane
+    # fused substep (B2S_FUSED=1 in the library)
+    split = True
 
     def step(self, substeps=1, fetch_mask=BUF_ALL):
-        (lib().emu_step_split if self.split else lib().emu_step)(self.h, substeps, fetch_mask)
+        (lib().emu_step_pipe if self.split else lib().emu_step)(self.h, substeps, fetch_mask)
 
     def apply(self, mask=BUF_ALL & ~BUF_LINK):
         lib().emu_apply(self.h, mask)

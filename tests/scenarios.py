@@ -21,7 +21,7 @@ def pick_cube_random_actions(n_envs, n_substeps=100, seed=0, action_every=5):
     return q0, cube, deltas, grip
 
 
-def run_pick_cube(world_kind, cm, n_substeps=100, seed=0, device=None):
+def run_pick_cube(world_kind, cm, n_substeps=100, seed=0, device=None, emu_mode=1):
     """Runs the scenario on 'oracle32' / 'oracle64' / 'emu' / 'cuda'; returns dict of final numpy arrays."""
     N = cm.scalars["n_envs"]
     q0, cube, deltas, grip = pick_cube_random_actions(N, n_substeps, seed)
@@ -45,6 +45,7 @@ def run_pick_cube(world_kind, cm, n_substeps=100, seed=0, device=None):
     if world_kind == "emu":
         from emu import EmuWorld
         w = EmuWorld(cm)
+        w.split = bool(emu_mode)  # 0 single-lane fused substep, 1 pipelined substep (the CUDA library's default)
         w.qpos[:] = q0
         w.target_qpos[:] = q0
         w.rigid_body_data[:, n_link + cube_fb] = cube

@@ -1,15 +1,17 @@
 """CPU: the device per-env code compiled for the host (tests/emu) against the oracle -- proves the kernel logic
 is the restated algorithm before any GPU time is spent. Both are float32 with contraction off => bit-level agreement."""
 import numpy as np
+import pytest
 
 from scenarios import run_pick_cube
 
 
-def test_emu_matches_oracle_f32_pick_cube():
+@pytest.mark.parametrize("emu_mode", [0, 1], ids=["fused", "pipelined"])
+def test_emu_matches_oracle_f32_pick_cube(emu_mode):
     from maniskill_b200.scenes import pick_cube_scene
     cm = pick_cube_scene(6).compile()
     ref = run_pick_cube("oracle32", cm, 100)
-    got = run_pick_cube("emu", cm, 100)
+    got = run_pick_cube("emu", cm, 100, emu_mode=emu_mode)
     assert np.abs(got["qpos"] - ref["qpos"]).max() < 1e-6
     assert np.abs(got["body"] - ref["body"]).max() < 1e-5
     rows = cm.link_rows["panda"]
