@@ -52,6 +52,9 @@ struct PickTaskDev {
 
 struct World : b2s::WorldT<DevMem> {
   int device;
+  // the dynamics half of kin (ABA, M~^-1) runs on a side stream while collide + manifest run on the caller's stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<Query> queries;
   std::vector<b2s::RasterGroup*> groups;
   std::vector<PickTaskDev> pick_tasks;
@@ -112,11 +115,11 @@ static void launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStr
 
 // ---- pipelined phase A (b2s_pipe.cuh): kin (lane per sub-scene) -> collide (lane per candidate pair x sub-scene) ->
 // manifest (lane per sub-scene) -> rowfill (lane per row x sub-scene); phase B is the solve_kernel above
-template <class C, int ND>
+template <class C, int ND, int PART>
 __global__ void __launch_bounds__(32) kin_kernel(b2s::DevModel M, b2s::DevState S) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
-  b2s::kin_env<C, ND>(M, S, env);
+  b2s::kin_env<C, ND, PART>(M, S, env);
 }
 
 #define B2S_COLLIDE_THREADS 64
@@ -330,6 +333,9 @@ int32_t b2s_world_destroy(uint64_t world) {
   }
   cudaSetDevice(w->device);
   cudaDeviceSynchronize();
+  if (w->side) cudaStreamDestroy(w->side);
+  if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+  if (w->ev_join) cudaEventDestroy(w->ev_join);
   for (auto& q : w->queries) cudaFree(q.rows_dev);
   for (auto* g : w->groups) b2s::raster_destroy(g);
   w->release();
@@ -359,15 +365,36 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   static int fused = getenv("B2S_FUSED") ? atoi(getenv("B2S_FUSED")) : 0;
   if (!fused && w->M.n_u <= 28) {
     const int MR = b2s::CapsS::MAXROW;
+    static int overlap_on = getenv("B2S_OVERLAP") ? atoi(getenv("B2S_OVERLAP")) : 1;
+    if (overlap_on && !w->side) {
+      CK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
+    }
+    const bool overlap = overlap_on != 0;
     for (int sidx = 0; sidx < substeps; sidx++) {
       const int pg = (N + 31) / 32;
-      if (w->caps == 0 && w->M.n_dof == 9) kin_kernel<b2s::CapsS, 9><<<pg, 32, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0) kin_kernel<b2s::CapsS, 0><<<pg, 32, 0, st>>>(w->M, w->S);
-      else kin_kernel<b2s::CapsL, 0><<<pg, 32, 0, st>>>(w->M, w->S);
+#define B2S_KIN(PART_, STREAM_)                                                                                  \
+  {                                                                                                              \
+    if (w->caps == 0 && w->M.n_dof == 9) kin_kernel<b2s::CapsS, 9, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);   \
+    else if (w->caps == 0) kin_kernel<b2s::CapsS, 0, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);                 \
+    else kin_kernel<b2s::CapsL, 0, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);                                   \
+  }
+      if (overlap) {
+        B2S_KIN(1, st)
+        CK(cudaEventRecord(w->ev_fork, st));
+        CK(cudaStreamWaitEvent(w->side, w->ev_fork, 0));
+        B2S_KIN(2, w->side)
+        CK(cudaEventRecord(w->ev_join, w->side));
+      } else {
+        B2S_KIN(0, st)
+      }
+#undef B2S_KIN
       if (w->M.n_pair > 0)
         collide_kernel<<<dim3((N + B2S_COLLIDE_THREADS - 1) / B2S_COLLIDE_THREADS, w->M.n_pair), B2S_COLLIDE_THREADS, 0, st>>>(w->M, w->S);
       if (w->caps == 0) manifest_kernel<b2s::CapsS><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
       else manifest_kernel<b2s::CapsL><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      if (overlap) CK(cudaStreamWaitEvent(st, w->ev_join, 0));
       const dim3 rg((N + 127) / 128, MR);
       if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 9, 16><<<rg, 128, 0, st>>>(w->M, w->S);
       else if (w->caps == 0 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);

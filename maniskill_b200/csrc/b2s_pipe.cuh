@@ -29,7 +29,9 @@ B2S_HD float int_as_float(int i) {
 }
 
 // ------------------------------------------------------------------------------------------------ kin
-template <class C, int ND>
+// PART 0: everything.  The library runs it as two kernels so that the dynamics overlap the collision pass: PART 1 = forward
+// kinematics only (joint frames, velocities, motion axes -> kin_link; clears the hit bitmap), PART 2 = the rest (reloads kin_link).
+template <class C, int ND, int PART = 0>
 B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
   const size_t N = M.n_envs;
   const int nd = ND > 0 ? ND : M.n_dof;
@@ -55,22 +57,36 @@ B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
   v6 fextW[C::MAXD];
   B2S_NO_UNROLL
   for (int i = 0; i < nd; i++) {
-    int p = M.dof_parent[i], a = M.dof_art[i];
-    pose Xp = p >= 0 ? X[p] : root[a];
-    pose Xj = pmul(Xp, pose7(M.dof_T0 + 7 * i));
-    v3 ax = mk3(M.dof_axis[3 * i], M.dof_axis[3 * i + 1], M.dof_axis[3 * i + 2]);
-    pose mo = pose_ident();
-    bool rev = M.dof_type[i] == 0;
-    if (rev) mo.q = qaxis_angle(ax, q[i]);
-    else mo.p = ax * q[i];
-    X[i] = pmul(Xj, mo);
-    X[i].q = qnormalized(X[i].q);
-    v3 aw = qrot(Xj.q, ax);
-    v3 Oa = root[a].p;
-    S[i] = rev ? mk6(aw, cross(X[i].p - Oa, aw)) : mk6(mk3(0, 0, 0), aw);
-    v6 Vp = p >= 0 ? V[p] : zero6();
+    const int p = M.dof_parent[i], a = M.dof_art[i];
+    const v3 Oa = root[a].p;
+    float* o = St.kin_link + (size_t)(i * B2S_KL) * N + env;
+    if (PART != 2) {
+      pose Xp = p >= 0 ? X[p] : root[a];
+      pose Xj = pmul(Xp, pose7(M.dof_T0 + 7 * i));
+      v3 ax = mk3(M.dof_axis[3 * i], M.dof_axis[3 * i + 1], M.dof_axis[3 * i + 2]);
+      pose mo = pose_ident();
+      bool rev = M.dof_type[i] == 0;
+      if (rev) mo.q = qaxis_angle(ax, q[i]);
+      else mo.p = ax * q[i];
+      X[i] = pmul(Xj, mo);
+      X[i].q = qnormalized(X[i].q);
+      v3 aw = qrot(Xj.q, ax);
+      S[i] = rev ? mk6(aw, cross(X[i].p - Oa, aw)) : mk6(mk3(0, 0, 0), aw);
+      v6 Vp = p >= 0 ? V[p] : zero6();
+      V[i] = Vp + S[i] * qd[i];
+      const float w[B2S_KL] = {X[i].p.x, X[i].p.y, X[i].p.z, X[i].q.w, X[i].q.x, X[i].q.y, X[i].q.z,
+                               V[i].a.x, V[i].a.y, V[i].a.z, V[i].l.x, V[i].l.y, V[i].l.z,
+                               S[i].a.x, S[i].a.y, S[i].a.z, S[i].l.x, S[i].l.y, S[i].l.z};
+      for (int k = 0; k < B2S_KL; k++) o[k * N] = w[k];
+    } else {
+      float w[B2S_KL];
+      for (int k = 0; k < B2S_KL; k++) w[k] = o[k * N];
+      X[i] = pose7(w);
+      V[i] = mk6(mk3(w[7], w[8], w[9]), mk3(w[10], w[11], w[12]));
+      S[i] = mk6(mk3(w[13], w[14], w[15]), mk3(w[16], w[17], w[18]));
+    }
+    if (PART == 1) continue;
     v6 vj = S[i] * qd[i];
-    V[i] = Vp + vj;
     cvp[i] = crm(V[i], vj);
     m3 Rm = qmat(X[i].q);
     v3 com = mk3(M.dof_com[3 * i], M.dof_com[3 * i + 1], M.dof_com[3 * i + 2]);
@@ -86,12 +102,10 @@ B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
     float damp = M.dof_passive[4 * i], armature = M.dof_passive[4 * i + 2];
     tau[i] = kp * (tq[i] - q[i] - dt * qd[i]) + kd * (tqd[i] - qd[i]) + qf[i] - damp * qd[i];
     arm[i] = armature + dt * kd + dt * dt * kp + dt * damp;
-    float* o = St.kin_link + (size_t)(i * B2S_KL) * N + env;
-    const float w[B2S_KL] = {X[i].p.x, X[i].p.y, X[i].p.z, X[i].q.w, X[i].q.x, X[i].q.y, X[i].q.z,
-                             V[i].a.x, V[i].a.y, V[i].a.z, V[i].l.x, V[i].l.y, V[i].l.z,
-                             S[i].a.x, S[i].a.y, S[i].a.z, S[i].l.x, S[i].l.y, S[i].l.z};
-    for (int k = 0; k < B2S_KL; k++) o[k * N] = w[k];
   }
+  if (PART != 2)
+    for (int kw = 0; kw < (M.n_pair + 31) >> 5; kw++) St.col_mask[(size_t)kw * N + env] = 0u;
+  if (PART == 1) return;
   // ABA with the implicit drive in the joint diagonal; second pass for force-limited drives (see substep, part 3)
   float qdd[C::MAXD];
   for (int pass = 0; pass < 2; pass++) {
@@ -168,7 +182,6 @@ B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
       St.kin_minv[(size_t)(i * nd + j) * N + env] = qd2;
     }
   }
-  for (int kw = 0; kw < (M.n_pair + 31) >> 5; kw++) St.col_mask[(size_t)kw * N + env] = 0u;
   // free bodies: world centre of mass, inverse mass, world inverse inertia (zero for kinematic bodies)
   for (int b = 0; b < M.n_fb; b++) {
     int ov = M.fb_ov[b];
@@ -491,7 +504,7 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
       v3 pt = is_n ? man_p[mi][k] : cen;
       v3 dir = is_n ? n : (k == np ? t1 : (k == np + 1 ? t2 : n));
       if (is_n) {
-        B2S_DESC(ri, ROW_CONTACT_N, 0, 0, mo, sides, 0, pt, dir, man_s[mi][k], 0.f, 0.f, -1, 0.f, -1, 0.f);
+        B2S_DESC(ri, ROW_CONTACT_N | (k == 0 ? ROW_PATCH_START : 0), 0, 0, mo, sides, 0, pt, dir, man_s[mi][k], 0.f, 0.f, -1, 0.f, -1, 0.f);
       } else {
         B2S_DESC(ri, ROW_FRICTION, first, np, tors ? -1 : mo, sides, tors ? 1 : 0, pt, dir, 0.f, tors ? man_mu[mi] * rad : man_mu[mi], 0.f, -1, 0.f,
                  -1, 0.f);
@@ -520,7 +533,7 @@ B2S_HDN void rowfill_env(const DevModel& M, const DevState& St, int env, int r) 
   float* R = St.sol_rows + ((size_t)env * C::MAXROW + r) * RF;
   const int meta = as_int(D[0]), sides = as_int(D[1]);
   const bool tors = (as_int(D[2]) & 1) != 0;
-  const int ty = meta & 0xff;
+  const int ty = meta & 0x0f;
   const v3 pt = mk3(D[3], D[4], D[5]), dir = mk3(D[6], D[7], D[8]);
   const float gamma = D[11];
   float J[JD];

@@ -105,6 +105,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       for (int k = 0; k < 5; k++) scn[k] = rows[2 * NUQ + k];
       scn[5] = rows[2 * NUQ + 8];
     }
+    float pn_sum = 0.f;
 #pragma unroll 2
     for (int r = 0; r < nrow_max; r++) {
       const bool act = r < n_row;
@@ -121,19 +122,12 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
         for (int k = 0; k < 5; k++) scn[k] = Rn[2 * NUQ + k];
         scn[5] = Rn[2 * NUQ + 8];
       }
-      // branch-free row visit (the lanes of a warp hold rows of different types).  Loads from the impulse table first: they do
-      // not depend on the reduction.  Friction bound = mu x (sum of the <= 4 normal impulses of the patch).
+      // branch-free row visit (the lanes of a warp hold rows of different types).  The friction bound mu x (sum of the normal
+      // impulses of the patch) comes from a running sum: the normal rows of a patch directly precede its friction rows.
       const int meta = as_int(sc[4]);
-      const int ty = meta & 0xff;
+      const int ty = meta & 0x0f;
       const bool fric = ty == ROW_FRICTION, eq = ty == ROW_EQ;
-      const int nrow = (meta >> 8) & 0xff, ncount = fric ? (meta >> 16) & 0xff : 0;
-      float nsum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int rk = nrow + k < MAXROW ? nrow + k : MAXROW - 1;
-        const float lk = lam[rk];
-        nsum += k < ncount ? lk : 0.f;
-      }
+      if (meta & ROW_PATCH_START) pn_sum = 0.f;
       const float lamr = lam[act ? r : 0];
       float jp[2] = {0.f, 0.f}, sp[2] = {0.f, 0.f};
 #pragma unroll
@@ -154,12 +148,13 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       const bool use_soft = !fric && !eq && !open && !relax;
       const float ms = use_soft ? soft_mass : 1.f;
       const float c = eq ? gamma * dinv : (use_soft ? soft_imp : 0.f);
-      const float lim = mu * nsum;
+      const float lim = mu * pn_sum;
       const float lo = fric ? -lim : (eq ? -3.0e38f : 0.f), hi = fric ? lim : 3.0e38f;
       float nl = lamr - dinv * ms * (jv + bias) - c * lamr;
       nl = fminf(fmaxf(nl, lo), hi);
       const float dl = act ? nl - lamr : 0.f;
       if (act) lam[r] = nl;  // every lane of the group writes the same value
+      if (ty == ROW_CONTACT_N) pn_sum += nl;
 #pragma unroll
       for (int k = 0; k < SL; k++) u[k] += Bc[k] * dl;
     }

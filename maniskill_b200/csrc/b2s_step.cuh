@@ -77,7 +77,7 @@ struct DevState {
 };
 
 enum { OWNER_STATIC = 0, OWNER_LINK = 1, OWNER_BODY = 2 };
-enum { ROW_CONTACT_N = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_EQ = 3 };
+enum { ROW_CONTACT_N = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_EQ = 3, ROW_PATCH_START = 0x10 /* flag: first normal row of a patch */ };
 enum {
   BUF_RIGID = 1u << 0, BUF_ROOT_POSE = 1u << 1, BUF_QPOS = 1u << 2, BUF_QVEL = 1u << 3, BUF_QF = 1u << 4,
   BUF_TARGET_QPOS = 1u << 5, BUF_TARGET_QVEL = 1u << 6, BUF_QACC = 1u << 7, BUF_LINK = 1u << 8

@@ -22,7 +22,8 @@ for N in [int(a) for a in (sys.argv[1:] or ["1024", "4096", "16384"])]:
         w.step(5, BUF_ALL)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    iters = 20
+    iters = 60
+    torch.manual_seed(0)
     ev[0].record()
     for i in range(iters):
         w.target_qpos[:] = w.qpos + 0.1 * (2 * torch.rand_like(w.qpos) - 1)
