@@ -77,14 +77,18 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
   b2s::step_env<C, ND>(M, S, env, substeps, fetch_mask);
 }
 
-// ---- phase B: L lanes per sub-scene run the Gauss-Seidel sweeps and integrate (b2s_solve.cuh)
+// ---- phase B: 4 lanes per sub-scene run the Gauss-Seidel sweeps and integrate (b2s_solve.cuh).  Every sub-scene is resident at
+// once, so the launch lasts as long as the slowest one: what counts is the dependent chain of a row visit.  Measured on B200
+// (PickCube-v1, ms per control step, 4096 / 16384 envs): 4 lanes 0.93 / 1.78, 8 lanes 0.93 / 1.82, 16 lanes 1.00 / 2.21; one lane
+// per sub-scene with instruction-level parallelism instead of shuffles 1.4 / 2.2.
+#define B2S_SOLVE_L 4
 #define B2S_SOLVE_THREADS 128
-template <int NUQ, int L>
+template <int NUQ>
 __global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel M, b2s::DevState S) {
+  constexpr int L = B2S_SOLVE_L;
   constexpr int MR = b2s::CapsS::MAXROW;
   constexpr int EPB = B2S_SOLVE_THREADS / L;  // sub-scenes per block
-  __shared__ float s_lam[EPB][MR];
-  __shared__ float s_tot[EPB][MR];
+  __shared__ b2s::LamTot s_lt[EPB][MR];
   __shared__ float s_stage[EPB][2 * NUQ];
   const int g = threadIdx.x / L, lane = threadIdx.x % L;
   const int env = blockIdx.x * EPB + g;
@@ -94,23 +98,15 @@ __global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel 
   int nmax = n_row;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-  b2s::solve_env<L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lam[g], s_tot[g], s_stage[g]);
+  b2s::solve_env<L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lt[g], s_stage[g]);
 }
 
-// Lanes per sub-scene in phase B.  Every sub-scene is resident at once, so the launch lasts as long as the slowest one: what counts
-// is the dependent chain of a row visit.  Measured on B200 (PickCube-v1, ms per control step, 4096 / 16384 envs): 4 lanes
-// 0.93 / 1.78, 8 lanes 0.93 / 1.82, 16 lanes 1.00 / 2.21; one lane per sub-scene with instruction-level parallelism instead of
-// shuffles was 1.4 / 2.2.  B2S_SOLVE_L (4, 8, 16) overrides for experiments.
 static void launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st) {
-  static int forced = getenv("B2S_SOLVE_L") ? atoi(getenv("B2S_SOLVE_L")) : 0;
   const int N = M.n_envs;
-  const int L = (M.n_u <= 16 && (forced == 8 || forced == 16)) ? forced : 4;
-  const int epb = B2S_SOLVE_THREADS / L;
+  const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
   const int grid = (N + epb - 1) / epb;
-  if (M.n_u > 16) solve_kernel<28, 4><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
-  else if (L == 16) solve_kernel<16, 16><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
-  else if (L == 8) solve_kernel<16, 8><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
-  else solve_kernel<16, 4><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  if (M.n_u > 16) solve_kernel<32><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  else solve_kernel<16><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
 }
 
 // ---- pipelined phase A (b2s_pipe.cuh): kin (lane per sub-scene) -> collide (lane per candidate pair x sub-scene) ->
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevS
   if (env >= M.n_envs) return;
   const int r = blockIdx.y;
   if (r >= S.sol_nrow[env]) return;
-  b2s::rowfill_env<C, ND, NUQ>(M, S, env, r);
+  b2s::rowfill_env<C, ND, NUQ, B2S_SOLVE_L>(M, S, env, r);
 }
 
 template <class C>
@@ -363,7 +359,7 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
   static int fused = getenv("B2S_FUSED") ? atoi(getenv("B2S_FUSED")) : 0;
-  if (!fused && w->M.n_u <= 28) {
+  if (!fused && w->M.n_u <= 32) {
     const int MR = b2s::CapsS::MAXROW;
     static int overlap_on = getenv("B2S_OVERLAP") ? atoi(getenv("B2S_OVERLAP")) : 1;
     if (overlap_on && !w->side) {
@@ -398,9 +394,9 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
       const dim3 rg((N + 127) / 128, MR);
       if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 9, 16><<<rg, 128, 0, st>>>(w->M, w->S);
       else if (w->caps == 0 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0) rowfill_kernel<b2s::CapsS, 0, 28><<<rg, 128, 0, st>>>(w->M, w->S);
+      else if (w->caps == 0) rowfill_kernel<b2s::CapsS, 0, 32><<<rg, 128, 0, st>>>(w->M, w->S);
       else if (w->M.n_u <= 16) rowfill_kernel<b2s::CapsL, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
-      else rowfill_kernel<b2s::CapsL, 0, 28><<<rg, 128, 0, st>>>(w->M, w->S);
+      else rowfill_kernel<b2s::CapsL, 0, 32><<<rg, 128, 0, st>>>(w->M, w->S);
       launch_solve(w->M, w->S, st);
     }
     CK(cudaGetLastError());

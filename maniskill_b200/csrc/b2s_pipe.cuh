@@ -523,7 +523,8 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
 
 // ------------------------------------------------------------------------------------------------ rowfill
 // row r of sub-scene env: descriptor -> unified row record (J_u | B_u | 12 scalars), see b2s_solve.cuh
-template <class C, int ND, int NUQ>
+// L = lanes per sub-scene of the solve that will read the record (fixes the lane-major order of the two vectors, b2s_solve.cuh)
+template <class C, int ND, int NUQ, int L>
 B2S_HDN void rowfill_env(const DevModel& M, const DevState& St, int env, int r) {
   constexpr int RF = 2 * NUQ + B2S_ROW_SCALARS;
   constexpr int JD = ND > 0 ? ND : C::MAXD;
@@ -584,8 +585,8 @@ B2S_HDN void rowfill_env(const DevModel& M, const DevState& St, int env, int r) 
 #pragma unroll
         for (int j = 0; j < JD; j++)
           if (j < nd) s += St.kin_minv[(size_t)(i * nd + j) * N + env] * J[j];
-        R[i] = J[i];
-        R[(NUQ + i)] = s;
+        R[row_pos<L, NUQ>(i)] = J[i];
+        R[NUQ + row_pos<L, NUQ>(i)] = s;
         d += J[i] * s;  // effective mass of the articulation block, summed in joint order like the fused substep
       }
     }
@@ -614,12 +615,12 @@ B2S_HDN void rowfill_env(const DevModel& M, const DevState& St, int env, int r) 
     }
     const float jl[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z}, bl[6] = {Bl.x, Bl.y, Bl.z, Ba.x, Ba.y, Ba.z};
 #pragma unroll
-    for (int k = 0; k < 6; k++) { R[(o + k)] = jl[k]; R[(NUQ + o + k)] = bl[k]; }
+    for (int k = 0; k < 6; k++) { R[row_pos<L, NUQ>(o + k)] = jl[k]; R[NUQ + row_pos<L, NUQ>(o + k)] = bl[k]; }
   }
   float* Sc = R + 2 * NUQ;
-  const float sc[12] = {(d + gamma) > 1e-12f ? 1.f / (d + gamma) : 0.f, gamma, D[9], D[10], D[0], dir.x, dir.y, dir.z, ckin, 0.f, 0.f, 0.f};
+  const float sc[12] = {(d + gamma) > 1e-12f ? 1.f / (d + gamma) : 0.f, gamma, D[9], D[10], D[0], ckin, 0.f, 0.f, dir.x, dir.y, dir.z, 0.f};
 #pragma unroll
-  for (int k = 0; k < 9; k++) Sc[k] = sc[k];
+  for (int k = 0; k < 12; k++) Sc[k] = sc[k];
 }
 
 }  // namespace b2s

@@ -39,10 +39,44 @@ B2S_HD void group_sync() {
 #endif
 }
 
+// Position of slot s of the unified vector inside a row record: lane-major, so that the SL slots of a lane are contiguous and a
+// lane fetches its slice of J (and of B) with 16-byte loads.  Identity for L = 1 (host emulation).
+template <int L, int NUQ>
+B2S_HD int row_pos(int s) {
+  return (s % L) * (NUQ / L) + s / L;
+}
+
+// n consecutive floats (n % 4 == 0 and 16-byte aligned on the device)
+template <int n>
+B2S_HD void load_vec(const float* p, float* out) {
+#if defined(__CUDA_ARCH__)
+  if (n % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < n / 4; k++) {
+      const float4 v = *reinterpret_cast<const float4*>(p + 4 * k);
+      out[4 * k] = v.x; out[4 * k + 1] = v.y; out[4 * k + 2] = v.z; out[4 * k + 3] = v.w;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < n; k++) out[k] = p[k];
+}
+
+// Row record (RF = 2 NUQ + 12 floats, 16-byte aligned): J (lane-major) | B (lane-major) | dinv gamma s0 mu | meta ckin 0 0 | dir(3) 0
+struct alignas(8) LamTot {
+  float lam, tot;  // impulse of a row, its accumulation over the step
+};
+
+#define B2S_SC_META 4
+#define B2S_SC_CKIN 5
+#define B2S_SC_DIR 8
+
 // One sub-scene, executed by the L lanes of its group (lane = 0..L-1).  `valid` is false for padding groups past n_envs (they only
-// take part in the shuffles).  lam / tot / stage are group-private scratch (shared memory on the device).
+// take part in the shuffles).  lamtot (impulse, accumulated impulse pairs) / stage are group-private scratch (shared memory on the
+// device).
 template <int L, int NUQ, int MAXROW>
-B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane, bool valid, int nrow_max, float* lam, float* tot, float* stage) {
+B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane, bool valid, int nrow_max, LamTot* lamtot, float* stage) {
   constexpr int SL = NUQ / L;                       // slots per lane
   constexpr int RF = 2 * NUQ + B2S_ROW_SCALARS;     // floats per row record
   const size_t N = M.n_envs;
@@ -81,8 +115,9 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       }
     }
   }
-  for (int r = lane; r < n_row; r += L) { lam[r] = 0.f; tot[r] = 0.f; }
+  for (int r = lane; r < n_row; r += L) { lamtot[r].lam = 0.f; lamtot[r].tot = 0.f; }
   group_sync();
+  const float* myJ = rows + lane * SL;        // this lane's slice of J; its slice of B is NUQ floats further
   for (int it = 0; it < npos + M.n_vel_iters; it++) {
     const bool relax = it >= npos;
     if (!relax) {
@@ -92,74 +127,77 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
         uf[k] = u[k];
         if (it > 0) u[k] += ac[k];
       }
-    } else {
-      for (int r = lane; r < n_row; r += L) tot[r] -= lam[r];
-      group_sync();
     }
-    // software pipeline: the Jacobian slice, the response slice and the scalars of row r+1 are in flight while row r is reduced
-    float Jn[SL], Bn[SL], scn[6];
-    if (n_row > 0) {
-#pragma unroll
-      for (int k = 0; k < SL; k++) { Jn[k] = rows[k * L + lane]; Bn[k] = rows[NUQ + k * L + lane]; }
-#pragma unroll
-      for (int k = 0; k < 5; k++) scn[k] = rows[2 * NUQ + k];
-      scn[5] = rows[2 * NUQ + 8];
-    }
+    // Software pipeline over two register sets (A: even rows, B: odd rows): the Jacobian slice, the response slice and the scalars
+    // of the next row are in flight while the current one is reduced.  Fetches are unconditional (index clamped to the last row).
+    float JA[SL], BA[SL], scA[4], mcA[2], JB[SL], BB[SL], scB[4], mcB[2];
+    const int r_last = n_row > 0 ? n_row - 1 : 0;
+#define B2S_FETCH_ROW(rr, J_, B_, sc_, mc_)                                      \
+  {                                                                              \
+    const int rc_ = (rr) < r_last ? (rr) : r_last;                               \
+    const float* Rn_ = myJ + (size_t)rc_ * RF;                                   \
+    load_vec<SL>(Rn_, J_);                                                       \
+    load_vec<SL>(Rn_ + NUQ, B_);                                                 \
+    const float* Sn_ = rows + (size_t)rc_ * RF + 2 * NUQ;                        \
+    load_vec<4>(Sn_, sc_);                                                       \
+    mc_[0] = Sn_[B2S_SC_META]; mc_[1] = Sn_[B2S_SC_CKIN];                        \
+  }
+    // Branch-free row visit (the lanes of a warp hold rows of different types).  The friction bound mu x (sum of the normal
+    // impulses of the patch) comes from a running sum: the normal rows of a patch directly precede its friction rows.
+    //   nl = clamp(lamr - dinv * ms * (jv + bias) - c * lamr, lo, hi)
+    //   contact / limit: open (sep > 0): exact bias sep/h; else soft constraint during the position sweeps, no bias in the relaxation
+    //   tendon: bias sep/h (position sweeps), regularised by gamma;   friction: no bias, box bound
+    // Impulse and its accumulation over the step (position sweeps add the sub-step impulse, the relaxation its correction) are
+    // one 8-byte pair; every lane of the group writes the same pair.
+#define B2S_VISIT_ROW(rr, J_, B_, sc_, mc_)                                                          \
+  {                                                                                                  \
+    const bool act_ = (rr) < n_row;                                                                  \
+    const int meta_ = as_int(mc_[0]);                                                                \
+    const int ty_ = meta_ & 0x0f;                                                                    \
+    const bool fric_ = ty_ == ROW_FRICTION, eq_ = ty_ == ROW_EQ;                                     \
+    if (meta_ & ROW_PATCH_START) pn_sum = 0.f;                                                       \
+    LamTot* lt_ = lamtot + (act_ ? (rr) : 0);                                                        \
+    const LamTot lt0_ = *lt_;                                                                        \
+    const float lamr_ = lt0_.lam;                                                                    \
+    float jp_[2] = {0.f, 0.f}, sp_[2] = {0.f, 0.f};                                                  \
+    _Pragma("unroll") for (int k = 0; k < SL; k++) {                                                 \
+      jp_[k & 1] += J_[k] * u[k];                                                                    \
+      sp_[k & 1] += J_[k] * du[k];                                                                   \
+    }                                                                                                \
+    const float jv_ = group_sum<L>(jp_[0] + jp_[1]) + mc_[1];                                        \
+    const float sep_ = sc_[2] + group_sum<L>(sp_[0] + sp_[1]);                                       \
+    const float dinv_ = sc_[0];                                                                      \
+    const bool open_ = sep_ > 0.f;                                                                   \
+    const float sh_ = sep_ * inv_h;                                                                  \
+    const float bias_c_ = open_ ? sh_ : (relax ? 0.f : fmaxf(soft_rate * sep_, -max_depen));         \
+    const float bias_ = fric_ ? 0.f : (eq_ ? (relax ? 0.f : sh_) : bias_c_);                         \
+    const bool use_soft_ = !fric_ && !eq_ && !open_ && !relax;                                       \
+    const float ms_ = use_soft_ ? soft_mass : 1.f;                                                   \
+    const float c_ = eq_ ? sc_[1] * dinv_ : (use_soft_ ? soft_imp : 0.f);                            \
+    const float lim_ = sc_[3] * pn_sum;                                                              \
+    const float lo_ = fric_ ? -lim_ : (eq_ ? -3.0e38f : 0.f), hi_ = fric_ ? lim_ : 3.0e38f;          \
+    float nl_ = lamr_ - dinv_ * ms_ * (jv_ + bias_) - c_ * lamr_;                                    \
+    nl_ = fminf(fmaxf(nl_, lo_), hi_);                                                               \
+    const float dl_ = act_ ? nl_ - lamr_ : 0.f;                                                      \
+    if (act_) {                                                                                      \
+      LamTot lt1_;                                                                                   \
+      lt1_.lam = nl_; lt1_.tot = lt0_.tot + (relax ? dl_ : nl_);                                     \
+      *lt_ = lt1_;                                                                                   \
+    }                                                                                                \
+    if (ty_ == ROW_CONTACT_N) pn_sum += nl_;                                                         \
+    _Pragma("unroll") for (int k = 0; k < SL; k++) u[k] += B_[k] * dl_;                              \
+  }
     float pn_sum = 0.f;
-#pragma unroll 2
-    for (int r = 0; r < nrow_max; r++) {
-      const bool act = r < n_row;
-      float Jc[SL], Bc[SL], sc[6];
-#pragma unroll
-      for (int k = 0; k < SL; k++) { Jc[k] = Jn[k]; Bc[k] = Bn[k]; }
-#pragma unroll
-      for (int k = 0; k < 6; k++) sc[k] = scn[k];
-      if (r + 1 < n_row) {
-        const float* Rn = rows + (size_t)(r + 1) * RF;
-#pragma unroll
-        for (int k = 0; k < SL; k++) { Jn[k] = Rn[k * L + lane]; Bn[k] = Rn[NUQ + k * L + lane]; }
-#pragma unroll
-        for (int k = 0; k < 5; k++) scn[k] = Rn[2 * NUQ + k];
-        scn[5] = Rn[2 * NUQ + 8];
-      }
-      // branch-free row visit (the lanes of a warp hold rows of different types).  The friction bound mu x (sum of the normal
-      // impulses of the patch) comes from a running sum: the normal rows of a patch directly precede its friction rows.
-      const int meta = as_int(sc[4]);
-      const int ty = meta & 0x0f;
-      const bool fric = ty == ROW_FRICTION, eq = ty == ROW_EQ;
-      if (meta & ROW_PATCH_START) pn_sum = 0.f;
-      const float lamr = lam[act ? r : 0];
-      float jp[2] = {0.f, 0.f}, sp[2] = {0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < SL; k++) {
-        jp[k & 1] += Jc[k] * u[k];
-        sp[k & 1] += Jc[k] * du[k];
-      }
-      const float jv = group_sum<L>(jp[0] + jp[1]) + sc[5];  // + constant contribution of kinematic bodies
-      const float sep = sc[2] + group_sum<L>(sp[0] + sp[1]);
-      const float dinv = sc[0], gamma = sc[1], mu = sc[3];
-      // nl = clamp(lamr - dinv * ms * (jv + bias) - c * lamr, lo, hi)
-      //   contact / limit: open (sep > 0): exact bias sep/h; else soft constraint during the position sweeps, no bias in the relaxation
-      //   tendon: bias sep/h (position sweeps), regularised by gamma;   friction: no bias, box bound
-      const bool open = sep > 0.f;
-      const float sh = sep * inv_h;
-      const float bias_c = open ? sh : (relax ? 0.f : fmaxf(soft_rate * sep, -max_depen));
-      const float bias = fric ? 0.f : (eq ? (relax ? 0.f : sh) : bias_c);
-      const bool use_soft = !fric && !eq && !open && !relax;
-      const float ms = use_soft ? soft_mass : 1.f;
-      const float c = eq ? gamma * dinv : (use_soft ? soft_imp : 0.f);
-      const float lim = mu * pn_sum;
-      const float lo = fric ? -lim : (eq ? -3.0e38f : 0.f), hi = fric ? lim : 3.0e38f;
-      float nl = lamr - dinv * ms * (jv + bias) - c * lamr;
-      nl = fminf(fmaxf(nl, lo), hi);
-      const float dl = act ? nl - lamr : 0.f;
-      if (act) lam[r] = nl;  // every lane of the group writes the same value
-      if (ty == ROW_CONTACT_N) pn_sum += nl;
-#pragma unroll
-      for (int k = 0; k < SL; k++) u[k] += Bc[k] * dl;
+    B2S_FETCH_ROW(0, JA, BA, scA, mcA)
+    B2S_NO_UNROLL
+    for (int r = 0; r < nrow_max; r += 2) {
+      B2S_FETCH_ROW(r + 1, JB, BB, scB, mcB)
+      B2S_VISIT_ROW(r, JA, BA, scA, mcA)
+      B2S_FETCH_ROW(r + 2, JA, BA, scA, mcA)
+      B2S_VISIT_ROW(r + 1, JB, BB, scB, mcB)
     }
-    group_sync();
-    for (int r = lane; r < n_row; r += L) tot[r] += lam[r];
+#undef B2S_FETCH_ROW
+#undef B2S_VISIT_ROW
     if (!relax) {
 #pragma unroll
       for (int k = 0; k < SL; k++) {
@@ -168,7 +206,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       }
     }
   }
-  // ---- integrate + export (the first lane of the group; the vector is gathered through the staging area)
+  // ---- integrate + export (the vector is gathered through the staging area)
 #pragma unroll
   for (int k = 0; k < SL; k++) {
     stage[k * L + lane] = u[k];
@@ -203,14 +241,28 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     for (int k = 0; k < 13; k++) St.fb[(size_t)(b * 13 + k) * N + env] = o[k];
   }
   // contact patch impulses: sum over the rows of a patch of (row direction x impulse accumulated over the step); a lane owns the
-  // output slots congruent to it, so the accumulation order per slot is the row order
-  for (int r = 0; r < n_row; r++) {
-    const float* Sc = rows + (size_t)r * RF + 2 * NUQ;
-    const int slot = ((as_int(Sc[4]) >> 24) & 0xff) - 1;
-    if (slot < 0 || slot % L != lane) continue;
-    float* o = St.man + (size_t)(slot * 8) * N + env;
-    const float t = tot[r];
-    o[2 * N] += Sc[5] * t; o[3 * N] += Sc[6] * t; o[4 * N] += Sc[7] * t;
+  // output slots congruent to it (the rows of a slot are consecutive), so the accumulation order per slot is the row order
+  int cur = -1;
+  v3 acc = mk3(0, 0, 0);
+  for (int r = 0; r <= n_row; r++) {
+    int slot = -1;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < n_row) {
+      const float* Sc = rows + (size_t)r * RF + 2 * NUQ;
+      slot = ((as_int(Sc[B2S_SC_META]) >> 24) & 0xff) - 1;
+      if (slot >= 0 && slot % L == lane) load_vec<4>(Sc + B2S_SC_DIR, d);
+      else slot = -1;
+    }
+    if (slot != cur && cur >= 0) {
+      float* o = St.man + (size_t)(cur * 8) * N + env;
+      o[2 * N] = acc.x; o[3 * N] = acc.y; o[4 * N] = acc.z;
+      acc = mk3(0, 0, 0);
+    }
+    if (slot >= 0) {
+      const float t = lamtot[r].tot;
+      acc = acc + mk3(d[0], d[1], d[2]) * t;
+    }
+    cur = slot;
   }
 }
 

@@ -112,7 +112,7 @@ struct WorldT {
     }
     S.man = zeros<float>((size_t)Caps<12, 4, 32, 1>::MAXMAN * 8 * N);
     S.man_count = zeros<int>(N);
-    S.sol_rows = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * (M.n_u <= 16 ? 44 : 68));
+    S.sol_rows = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * (M.n_u <= 16 ? 44 : 76));
     S.sol_nrow = zeros<int>(N);
     S.sol_qdd = zeros<float>((size_t)nd * N);
     S.kin_link = zeros<float>((size_t)nd * 19 * N);

@@ -20,13 +20,14 @@ typedef b2s::WorldT<HostMem> World;
 template <class C, int ND, int NUQ>
 static void pipe_substep(World* w) {
   const int MR = b2s::CapsS::MAXROW;
-  float lam[MR], tot[MR], stage[2 * 28];
+  b2s::LamTot lamtot[MR];
+  float stage[2 * 32];
   for (int e = 0; e < w->M.n_envs; e++) {
     b2s::kin_env<C, ND>(w->M, w->S, e);
     for (int k = 0; k < w->M.n_pair; k++) b2s::collide_env(w->M, w->S, e, k);
     b2s::manifest_env<C>(w->M, w->S, e);
-    for (int r = 0; r < w->S.sol_nrow[e]; r++) b2s::rowfill_env<C, ND, NUQ>(w->M, w->S, e, r);
-    b2s::solve_env<1, NUQ, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lam, tot, stage);
+    for (int r = 0; r < w->S.sol_nrow[e]; r++) b2s::rowfill_env<C, ND, NUQ, 1>(w->M, w->S, e, r);
+    b2s::solve_env<1, NUQ, MR>(w->M, w->S, e, 0, true, w->S.sol_nrow[e], lamtot, stage);
   }
 }
 
@@ -52,9 +53,9 @@ void emu_step_pipe(void* h, int substeps, unsigned fetch_mask) {
     const bool small_u = w->M.n_u <= 16;
     if (w->caps == 0 && w->M.n_dof == 9 && small_u) pipe_substep<b2s::CapsS, 9, 16>(w);
     else if (w->caps == 0 && small_u) pipe_substep<b2s::CapsS, 0, 16>(w);
-    else if (w->caps == 0) pipe_substep<b2s::CapsS, 0, 28>(w);
+    else if (w->caps == 0) pipe_substep<b2s::CapsS, 0, 32>(w);
     else if (small_u) pipe_substep<b2s::CapsL, 0, 16>(w);
-    else pipe_substep<b2s::CapsL, 0, 28>(w);
+    else pipe_substep<b2s::CapsL, 0, 32>(w);
   }
   if (fetch_mask) {
     for (int e = 0; e < w->M.n_envs; e++) {
