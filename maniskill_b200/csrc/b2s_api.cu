@@ -55,6 +55,9 @@ struct World : b2s::WorldT<DevMem> {
   // the dynamics half of kin (ABA, M~^-1) runs on a side stream while collide + manifest run on the caller's stream
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // captured control steps, keyed by (substeps, fetch_mask); `cap` is the stream they are captured on
+  cudaStream_t cap = nullptr;
+  std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::vector<Query> queries;
   std::vector<b2s::RasterGroup*> groups;
   std::vector<PickTaskDev> pick_tasks;
@@ -329,6 +332,8 @@ int32_t b2s_world_destroy(uint64_t world) {
   }
   cudaSetDevice(w->device);
   cudaDeviceSynchronize();
+  for (auto& kv : w->graphs) cudaGraphExecDestroy(kv.second);
+  if (w->cap) cudaStreamDestroy(w->cap);
   if (w->side) cudaStreamDestroy(w->side);
   if (w->ev_fork) cudaEventDestroy(w->ev_fork);
   if (w->ev_join) cudaEventDestroy(w->ev_join);
@@ -352,12 +357,10 @@ int32_t b2s_world_buffers(uint64_t world, B2SBufferTable* out) {
   return B2S_OK;
 }
 
-int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* stream) {
-  World* w = get(world);
-  if (!w) return fail(B2S_ERR_INVALID, "unknown world");
-  if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
-  int N = w->M.n_envs;
-  cudaStream_t st = (cudaStream_t)stream;
+// Enqueues the kernels of `substeps` physics substeps (+ the fetch) on `st`.  The dynamics half of kin runs on the world's side
+// stream between a fork and a join event; under stream capture the same calls become the dependency edges of the graph.
+static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_t st) {
+  const int N = w->M.n_envs;
   static int fused = getenv("B2S_FUSED") ? atoi(getenv("B2S_FUSED")) : 0;
   if (!fused && w->M.n_u <= 32) {
     const int MR = b2s::CapsS::MAXROW;
@@ -399,8 +402,11 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
       else rowfill_kernel<b2s::CapsL, 0, 32><<<rg, 128, 0, st>>>(w->M, w->S);
       launch_solve(w->M, w->S, st);
     }
+    if (fetch_mask) {
+      if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, fetch_mask);
+      else fetch_kernel<b2s::CapsL><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, fetch_mask);
+    }
     CK(cudaGetLastError());
-    if (fetch_mask) return b2s_fetch(world, fetch_mask, stream);
     return B2S_OK;
   }
   // single-kernel form: one lane per sub-scene, 32-lane CTAs (fewer lanes per warp measured slower: the ~0.5 MB kernel thrashes
@@ -410,6 +416,36 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   else if (w->caps == 0) step_kernel<b2s::CapsS, 0><<<grid, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
   else step_kernel<b2s::CapsL, 0><<<grid, 32, 0, st>>>(w->M, w->S, substeps, fetch_mask);
   CK(cudaGetLastError());
+  return B2S_OK;
+}
+
+// The launch sequence of a control step (5 x 6 kernels + fetch) never changes for a world: it is captured once per
+// (substeps, fetch_mask) into a CUDA graph on an internal stream and replayed on the caller's stream with one launch.
+// B2S_GRAPH=0 issues the kernels directly.
+int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* stream) {
+  World* w = get(world);
+  if (!w) return fail(B2S_ERR_INVALID, "unknown world");
+  if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  static int graph_on = getenv("B2S_GRAPH") ? atoi(getenv("B2S_GRAPH")) : 1;
+  if (!graph_on) return enqueue_step(w, substeps, fetch_mask, st);
+  const uint64_t key = ((uint64_t)(uint32_t)substeps << 32) | fetch_mask;
+  auto it = w->graphs.find(key);
+  if (it == w->graphs.end()) {
+    if (!w->cap) CK(cudaStreamCreateWithFlags(&w->cap, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(w->cap, cudaStreamCaptureModeRelaxed));
+    int rc = enqueue_step(w, substeps, fetch_mask, w->cap);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(w->cap, &g);
+    if (rc != B2S_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+    cudaGraphExec_t ex = nullptr;
+    e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+    it = w->graphs.emplace(key, ex).first;
+  }
+  CK(cudaGraphLaunch(it->second, st));
   return B2S_OK;
 }
 
