@@ -19,13 +19,64 @@ namespace b2s {
 
 #define B2S_KL 19  // kin_link floats per joint: X(7) V(ang3, lin3) S(ang3, lin3)
 #define B2S_KF 13  // kin_fb floats per free body: com(3) 1/m fIinv(9)
-#define B2S_CD 19  // col_data floats per candidate pair: normal(3), 4 x (point(3), separation)
+#define B2S_CD 20  // col_data floats per candidate pair: point count, normal(3), 4 x (point(3), separation)
 #define B2S_RD 16  // row descriptor floats: meta sides flags pt(3) dir(3) s0 mu gamma dofA coefA dofB coefB
 
 B2S_HD float int_as_float(int i) {
   union { int i; float f; } c;
   c.i = i;
   return c.f;
+}
+
+// 64-byte row descriptor (manifest / kin -> rowfill), written with four 16-byte stores
+B2S_HD void emit_desc(float* RD, int ri, int ty, int nrow, int ncount, int slot, int sides, int flags, v3 pt, v3 dir, float s0, float mu,
+                      float gamma, int dA, float cA, int dB, float cB) {
+  struct alignas(16) f4 { float x, y, z, w; };
+  f4* D = reinterpret_cast<f4*>(RD + (size_t)ri * B2S_RD);
+  f4 a, b, c, d;
+  a.x = int_as_float((ty & 0xff) | (nrow << 8) | ((ncount & 0xff) << 16) | (((slot + 1) & 0xff) << 24));
+  a.y = int_as_float(sides); a.z = int_as_float(flags); a.w = pt.x;
+  b.x = pt.y; b.y = pt.z; b.z = dir.x; b.w = dir.y;
+  c.x = dir.z; c.y = s0; c.z = mu; c.w = gamma;
+  d.x = int_as_float(dA); d.y = cA; d.z = int_as_float(dB); d.w = cB;
+  D[0] = a; D[1] = b; D[2] = c; D[3] = d;
+}
+
+// The rows that do not depend on the collision pass -- tendon couplings and the joint limits that can be reached within this step --
+// are emitted by the FK kernel, which holds q and qd in registers; manifest appends the contact rows after them.
+template <class C>
+B2S_HD void emit_joint_rows(const DevModel& M, const DevState& St, int env, const float* q, const float* qd, int nd) {
+  const size_t N = M.n_envs;
+  const float dt = M.dt, h = dt / M.n_pos_iters;
+  float* RD = St.row_desc + (size_t)env * C::MAXROW * B2S_RD;
+  const v3 zero3 = mk3(0, 0, 0);
+  int n_row = 0, ovf = 0;
+  for (int e = 0; e < M.n_eq && e < C::MAXEQ; e++) {
+    if (n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; break; }
+    const int ri = n_row++;
+    const int a = M.eq_dof[2 * e], b = M.eq_dof[2 * e + 1];
+    const float mult = M.eq_param[4 * e], off = M.eq_param[4 * e + 1], kk = M.eq_param[4 * e + 2];
+    emit_desc(RD, ri, ROW_EQ, 0, 0, -1, 0, 0, zero3, zero3, q[b] - mult * q[a] - off, 0.f, 1.f / (h * h * kk), b, 1.f, a, -mult);
+  }
+  int n_lim = 0;
+  B2S_NO_UNROLL
+  for (int i = 0; i < nd; i++) {
+    const float lo = M.dof_limit[2 * i], hi = M.dof_limit[2 * i + 1];
+    const float qi = q[i];
+    const float limit_margin = 0.005f + 2.f * dt * fabsf(qd[i]);  // only while the limit is reachable within this step
+    B2S_NO_UNROLL
+    for (int side = 0; side < 2; side++) {
+      const bool act = side == 0 ? (lo > -1e29f && qi - lo < limit_margin) : (hi < 1e29f && hi - qi < limit_margin);
+      if (!act) continue;
+      if (n_lim >= C::MAXLIM || n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; continue; }
+      n_lim++;
+      const int ri = n_row++;
+      emit_desc(RD, ri, ROW_LIMIT, 0, 0, -1, 0, 0, zero3, zero3, side == 0 ? qi - lo : hi - qi, 0.f, 0.f, i, side == 0 ? 1.f : -1.f, -1, 0.f);
+    }
+  }
+  St.sol_nrow[env] = n_row;  // manifest continues from here
+  if (ovf) *St.overflow = 1;
+  (void)N;
 }
 
 // ------------------------------------------------------------------------------------------------ kin
@@ -103,8 +154,10 @@ B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
     tau[i] = kp * (tq[i] - q[i] - dt * qd[i]) + kd * (tqd[i] - qd[i]) + qf[i] - damp * qd[i];
     arm[i] = armature + dt * kd + dt * dt * kp + dt * damp;
   }
-  if (PART != 2)
+  if (PART != 2) {
     for (int kw = 0; kw < (M.n_pair + 31) >> 5; kw++) St.col_mask[(size_t)kw * N + env] = 0u;
+    emit_joint_rows<C>(M, St, env, q, qd, nd);
+  }
   if (PART == 1) return;
   // ABA with the implicit drive in the joint diagonal; second pass for force-limited drives (see substep, part 3)
   float qdd[C::MAXD];
@@ -285,7 +338,6 @@ B2S_HDN inline void shape_obb(const DevModel& M, int s, const PlacedShape& P, v3
 // candidate pair k of sub-scene env -> col_n / col_data
 B2S_HDN inline void collide_env(const DevModel& M, const DevState& St, int env, int k) {
   const size_t N = M.n_envs;
-  int* out_n = St.col_n + (size_t)k * N + env;
   const int a = M.pair_a[k], b = M.pair_b[k];
   PlacedShape A, B;
   place_shape(M, St, env, a, A);
@@ -348,7 +400,6 @@ B2S_HDN inline void collide_env(const DevModel& M, const DevState& St, int env, 
   CPoint out[4];
   const int n = collide_pair(WA, WB, margin, out);
   if (n == 0) return;
-  *out_n = n;
   // hit bitmap of the sub-scene (cleared by kin): the manifest pass visits the set bits in candidate order
 #if defined(__CUDA_ARCH__)
   atomicOr(St.col_mask + (size_t)(k >> 5) * N + env, 1u << (k & 31));
@@ -356,9 +407,9 @@ B2S_HDN inline void collide_env(const DevModel& M, const DevState& St, int env, 
   St.col_mask[(size_t)(k >> 5) * N + env] |= 1u << (k & 31);
 #endif
   float* o = St.col_data + (size_t)(k * B2S_CD) * N + env;
-  o[0] = out[0].n.x; o[N] = out[0].n.y; o[2 * N] = out[0].n.z;
+  o[0] = (float)n; o[N] = out[0].n.x; o[2 * N] = out[0].n.y; o[3 * N] = out[0].n.z;
   for (int i = 0; i < n; i++) {
-    float* w = o + (size_t)(3 + 4 * i) * N;
+    float* w = o + (size_t)(4 + 4 * i) * N;
     w[0] = out[i].p.x; w[N] = out[i].p.y; w[2 * N] = out[i].p.z; w[3 * N] = out[i].sep;
   }
 }
@@ -386,16 +437,20 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
 #else
     for (unsigned t = (bits & (0u - bits)) >> 1; t; t >>= 1) k++;
 #endif
-    const int n = St.col_n[(size_t)k * N + env];
     const int a = M.pair_a[k], b = M.pair_b[k];
+    // the whole record of the pair is fetched at once (one round trip to L2), the point count selects what is used
     const float* o = St.col_data + (size_t)(k * B2S_CD) * N + env;
-    const v3 nrm = mk3(o[0], o[N], o[2 * N]);
+    float cd[B2S_CD];
+#pragma unroll
+    for (int i = 0; i < B2S_CD; i++) cd[i] = o[(size_t)i * N];
+    const int n = (int)cd[0];
+    const v3 nrm = mk3(cd[1], cd[2], cd[3]);
     v3 op[4];
     float os[4];
-    for (int i = 0; i < n; i++) {
-      const float* w = o + (size_t)(3 + 4 * i) * N;
-      op[i] = mk3(w[0], w[N], w[2 * N]);
-      os[i] = w[3 * N] - M.rest_offset;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      op[i] = mk3(cd[4 + 4 * i], cd[5 + 4 * i], cd[6 + 4 * i]);
+      os[i] = cd[7 + 4 * i] - M.rest_offset;
     }
     // patches of the same two bodies with (nearly) the same normal are one friction patch
     int merge = -1;
@@ -431,44 +486,9 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
     n_points += n;
   }
   // ---- row descriptors
-  int n_row = 0, n_ar = 0;
+  // the joint rows (tendons, reachable limits) are already there (emit_joint_rows, FK kernel); all of them touch the articulation
+  int n_row = St.sol_nrow[env], n_ar = n_row;
   float* RD = St.row_desc + (size_t)env * C::MAXROW * B2S_RD;
-  const float h = dt / M.n_pos_iters;
-#define B2S_DESC(ri, ty, nrow_, ncount_, slot_, sides_, flags_, pt_, dir_, s0_, mu_, gamma_, dA_, cA_, dB_, cB_)                     \
-  {                                                                                                                                   \
-    float* D_ = RD + (size_t)(ri) * B2S_RD;                                                                                           \
-    D_[0] = int_as_float(((ty)&0xff) | ((nrow_) << 8) | (((ncount_)&0xff) << 16) | ((((slot_) + 1) & 0xff) << 24));                    \
-    D_[1] = int_as_float(sides_); D_[2] = int_as_float(flags_);                                                                       \
-    D_[3] = (pt_).x; D_[4] = (pt_).y; D_[5] = (pt_).z; D_[6] = (dir_).x; D_[7] = (dir_).y; D_[8] = (dir_).z;                           \
-    D_[9] = s0_; D_[10] = mu_; D_[11] = gamma_; D_[12] = int_as_float(dA_); D_[13] = cA_; D_[14] = int_as_float(dB_); D_[15] = cB_;   \
-  }
-  const v3 zero3 = mk3(0, 0, 0);
-  for (int e = 0; e < M.n_eq && e < C::MAXEQ; e++) {
-    if (n_ar >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; break; }
-    int ri = n_row++;
-    n_ar++;
-    int a = M.eq_dof[2 * e], b = M.eq_dof[2 * e + 1];
-    float mult = M.eq_param[4 * e], off = M.eq_param[4 * e + 1], kk = M.eq_param[4 * e + 2];
-    float s0 = St.q[b * N + env] - mult * St.q[a * N + env] - off;
-    B2S_DESC(ri, ROW_EQ, 0, 0, -1, 0, 0, zero3, zero3, s0, 0.f, 1.f / (h * h * kk), b, 1.f, a, -mult);
-  }
-  int n_lim = 0;
-  B2S_NO_UNROLL
-  for (int i = 0; i < nd; i++) {
-    float lo = M.dof_limit[2 * i], hi = M.dof_limit[2 * i + 1];
-    const float qi = St.q[i * N + env];
-    const float limit_margin = 0.005f + 2.f * dt * fabsf(St.qd[i * N + env]);  // only while the limit is reachable within this step
-    B2S_NO_UNROLL
-    for (int side = 0; side < 2; side++) {
-      bool act = side == 0 ? (lo > -1e29f && qi - lo < limit_margin) : (hi < 1e29f && hi - qi < limit_margin);
-      if (!act) continue;
-      if (n_lim >= C::MAXLIM || n_ar >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; continue; }
-      n_lim++;
-      int ri = n_row++;
-      n_ar++;
-      B2S_DESC(ri, ROW_LIMIT, 0, 0, -1, 0, 0, zero3, zero3, side == 0 ? qi - lo : hi - qi, 0.f, 0.f, i, side == 0 ? 1.f : -1.f, -1, 0.f);
-    }
-  }
   int n_out = 0;
   B2S_NO_UNROLL
   for (int mi = 0; mi < n_man; mi++) {
@@ -504,10 +524,10 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
       v3 pt = is_n ? man_p[mi][k] : cen;
       v3 dir = is_n ? n : (k == np ? t1 : (k == np + 1 ? t2 : n));
       if (is_n) {
-        B2S_DESC(ri, ROW_CONTACT_N | (k == 0 ? ROW_PATCH_START : 0), 0, 0, mo, sides, 0, pt, dir, man_s[mi][k], 0.f, 0.f, -1, 0.f, -1, 0.f);
+        emit_desc(RD, ri, ROW_CONTACT_N | (k == 0 ? ROW_PATCH_START : 0), 0, 0, mo, sides, 0, pt, dir, man_s[mi][k], 0.f, 0.f, -1, 0.f, -1, 0.f);
       } else {
-        B2S_DESC(ri, ROW_FRICTION, first, np, tors ? -1 : mo, sides, tors ? 1 : 0, pt, dir, 0.f, tors ? man_mu[mi] * rad : man_mu[mi], 0.f, -1, 0.f,
-                 -1, 0.f);
+        emit_desc(RD, ri, ROW_FRICTION, first, np, tors ? -1 : mo, sides, tors ? 1 : 0, pt, dir, 0.f, tors ? man_mu[mi] * rad : man_mu[mi], 0.f, -1, 0.f,
+                  -1, 0.f);
       }
     }
     float* o = St.man + (size_t)(mo * 8) * N + env;
@@ -515,7 +535,6 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
     o[2 * N] = 0.f; o[3 * N] = 0.f; o[4 * N] = 0.f;
     o[5 * N] = (float)np; o[6 * N] = minsep;
   }
-#undef B2S_DESC
   St.sol_nrow[env] = n_row;
   St.man_count[env] = n_out;
   if (ovf) *St.overflow = 1;

@@ -70,9 +70,8 @@ struct DevState {
   float* kin_link;                       // [n_dof*19]  joint frame pose, spatial velocity, motion axis
   float* kin_minv;                       // [n_dof*n_dof]  M~^-1
   float* kin_fb;                         // [n_fb*13]  world com, 1/m, world inverse inertia
-  int* col_n;                            // [n_pair]  contact points of a candidate pair (valid where the hit bit is set)
   unsigned* col_mask;                    // [ceil(n_pair/32)]  hit bitmap over the candidate pairs
-  float* col_data;                       // [n_pair*19]  normal, 4 x (point, separation)
+  float* col_data;                       // [n_pair*20]  point count, normal, 4 x (point, separation); valid where the hit bit is set
   float* row_desc;                       // [n_envs, MAXROW, 16]  row descriptors (AoS)
 };
 

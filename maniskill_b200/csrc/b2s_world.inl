@@ -118,9 +118,8 @@ struct WorldT {
     S.kin_link = zeros<float>((size_t)nd * 19 * N);
     S.kin_minv = zeros<float>((size_t)nd * nd * N);
     S.kin_fb = zeros<float>((size_t)m.n_fb * 13 * N);
-    S.col_n = zeros<int>((size_t)m.n_pair * N);
     S.col_mask = zeros<unsigned>((size_t)((m.n_pair + 31) / 32) * N);
-    S.col_data = zeros<float>((size_t)m.n_pair * 19 * N);
+    S.col_data = zeros<float>((size_t)m.n_pair * 20 * N);
     S.row_desc = zeros<float>(N * (size_t)Caps<12, 4, 32, 1>::MAXROW * 16);
     S.overflow = zeros<int>(1);
     S.body_data = zeros<float>(N * M.n_rows * 13);
