@@ -84,13 +84,11 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
 // once, so the launch lasts as long as the slowest one: what counts is the dependent chain of a row visit.  Measured on B200
 // (PickCube-v1, ms per control step, 4096 / 16384 envs): 4 lanes 0.93 / 1.78, 8 lanes 0.93 / 1.82, 16 lanes 1.00 / 2.21; one lane
 // per sub-scene with instruction-level parallelism instead of shuffles 1.4 / 2.2.
-#define B2S_SOLVE_L 4
-#define B2S_SOLVE_THREADS 128
-template <int NUQ>
-__global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel M, b2s::DevState S) {
-  constexpr int L = B2S_SOLVE_L;
+#define B2S_SOLVE_EPB 32  // sub-scenes per block
+template <int NUQ, int L>
+__global__ void __launch_bounds__(B2S_SOLVE_EPB * L) solve_kernel(b2s::DevModel M, b2s::DevState S) {
   constexpr int MR = b2s::CapsS::MAXROW;
-  constexpr int EPB = B2S_SOLVE_THREADS / L;  // sub-scenes per block
+  constexpr int EPB = B2S_SOLVE_EPB;
   __shared__ b2s::LamTot s_lt[EPB][MR];
   __shared__ float s_stage[EPB][2 * NUQ];
   const int g = threadIdx.x / L, lane = threadIdx.x % L;
@@ -104,12 +102,21 @@ __global__ void __launch_bounds__(B2S_SOLVE_THREADS) solve_kernel(b2s::DevModel 
   b2s::solve_env<L, NUQ, MR>(M, S, env, lane, valid, nmax, s_lt[g], s_stage[g]);
 }
 
+static int solve_lanes() {
+  static int forced = getenv("B2S_SOLVE_L") ? atoi(getenv("B2S_SOLVE_L")) : 0;
+  return forced == 2 ? 2 : 4;
+}
 static void launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st) {
   const int N = M.n_envs;
-  const int epb = B2S_SOLVE_THREADS / B2S_SOLVE_L;
-  const int grid = (N + epb - 1) / epb;
-  if (M.n_u > 16) solve_kernel<32><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
-  else solve_kernel<16><<<grid, B2S_SOLVE_THREADS, 0, st>>>(M, S);
+  const int L = solve_lanes();
+  const int grid = (N + B2S_SOLVE_EPB - 1) / B2S_SOLVE_EPB;
+  if (L == 2) {
+    if (M.n_u > 16) solve_kernel<32, 2><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
+    else solve_kernel<16, 2><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
+  } else {
+    if (M.n_u > 16) solve_kernel<32, 4><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
+    else solve_kernel<16, 4><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
+  }
 }
 
 // ---- pipelined phase A (b2s_pipe.cuh): kin (lane per sub-scene) -> collide (lane per candidate pair x sub-scene) ->
@@ -135,13 +142,13 @@ __global__ void __launch_bounds__(64) manifest_kernel(b2s::DevModel M, b2s::DevS
   b2s::manifest_env<C>(M, S, env);
 }
 
-template <class C, int ND, int NUQ>
+template <class C, int ND, int NUQ, int L>
 __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevState S) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   const int r = blockIdx.y;
   if (r >= S.sol_nrow[env]) return;
-  b2s::rowfill_env<C, ND, NUQ, B2S_SOLVE_L>(M, S, env, r);
+  b2s::rowfill_env<C, ND, NUQ, L>(M, S, env, r);
 }
 
 template <class C>
@@ -395,11 +402,17 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
       else manifest_kernel<b2s::CapsL><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
       if (overlap) CK(cudaStreamWaitEvent(st, w->ev_join, 0));
       const dim3 rg((N + 127) / 128, MR);
-      if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 9, 16><<<rg, 128, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0 && w->M.n_u <= 16) rowfill_kernel<b2s::CapsS, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
-      else if (w->caps == 0) rowfill_kernel<b2s::CapsS, 0, 32><<<rg, 128, 0, st>>>(w->M, w->S);
-      else if (w->M.n_u <= 16) rowfill_kernel<b2s::CapsL, 0, 16><<<rg, 128, 0, st>>>(w->M, w->S);
-      else rowfill_kernel<b2s::CapsL, 0, 32><<<rg, 128, 0, st>>>(w->M, w->S);
+#define B2S_ROWFILL(C_, ND_, NUQ_)                                                                  \
+  {                                                                                                \
+    if (solve_lanes() == 2) rowfill_kernel<C_, ND_, NUQ_, 2><<<rg, 128, 0, st>>>(w->M, w->S);      \
+    else rowfill_kernel<C_, ND_, NUQ_, 4><<<rg, 128, 0, st>>>(w->M, w->S);                         \
+  }
+      if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 9, 16)
+      else if (w->caps == 0 && w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 0, 16)
+      else if (w->caps == 0) B2S_ROWFILL(b2s::CapsS, 0, 32)
+      else if (w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsL, 0, 16)
+      else B2S_ROWFILL(b2s::CapsL, 0, 32)
+#undef B2S_ROWFILL
       launch_solve(w->M, w->S, st);
     }
     if (fetch_mask) {

@@ -138,6 +138,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     const float* Rn_ = myJ + (size_t)rc_ * RF;                                   \
     load_vec<SL>(Rn_, J_);                                                       \
     load_vec<SL>(Rn_ + NUQ, B_);                                                 \
+    if ((rr) >= n_row) { _Pragma("unroll") for (int k = 0; k < SL; k++) B_[k] = 0.f; }  \
     const float* Sn_ = rows + (size_t)rc_ * RF + 2 * NUQ;                        \
     load_vec<4>(Sn_, sc_);                                                       \
     mc_[0] = Sn_[B2S_SC_META]; mc_[1] = Sn_[B2S_SC_CKIN];                        \
@@ -164,7 +165,7 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
       jp_[k & 1] += J_[k] * u[k];                                                                    \
       sp_[k & 1] += J_[k] * du[k];                                                                   \
     }                                                                                                \
-    const float jv_ = group_sum<L>(jp_[0] + jp_[1]) + mc_[1];                                        \
+    const float jvr_ = group_sum<L>(jp_[0] + jp_[1]);  /* critical chain: u -> dot -> reduce -> update -> u */                  \
     const float sep_ = sc_[2] + group_sum<L>(sp_[0] + sp_[1]);                                       \
     const float dinv_ = sc_[0];                                                                      \
     const bool open_ = sep_ > 0.f;                                                                   \
@@ -172,20 +173,23 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     const float bias_c_ = open_ ? sh_ : (relax ? 0.f : fmaxf(soft_rate * sep_, -max_depen));         \
     const float bias_ = fric_ ? 0.f : (eq_ ? (relax ? 0.f : sh_) : bias_c_);                         \
     const bool use_soft_ = !fric_ && !eq_ && !open_ && !relax;                                       \
-    const float ms_ = use_soft_ ? soft_mass : 1.f;                                                   \
+    const float dm_ = use_soft_ ? dinv_ * soft_mass : dinv_;                                         \
     const float c_ = eq_ ? sc_[1] * dinv_ : (use_soft_ ? soft_imp : 0.f);                            \
     const float lim_ = sc_[3] * pn_sum;                                                              \
     const float lo_ = fric_ ? -lim_ : (eq_ ? -3.0e38f : 0.f), hi_ = fric_ ? lim_ : 3.0e38f;          \
-    float nl_ = lamr_ - dinv_ * ms_ * (jv_ + bias_) - c_ * lamr_;                                    \
+    /* everything that does not depend on the reduced dot product is folded beforehand: nl = t - dm * (jv + bk) */ \
+    const float bk_ = bias_ + mc_[1];               /* bias + constant contribution of kinematic bodies */ \
+    const float t_ = lamr_ - c_ * lamr_;                                                             \
+    float nl_ = t_ - dm_ * (jvr_ + bk_);                                                             \
     nl_ = fminf(fmaxf(nl_, lo_), hi_);                                                               \
-    const float dl_ = act_ ? nl_ - lamr_ : 0.f;                                                      \
+    const float dl_ = nl_ - lamr_;                                                                   \
     if (act_) {                                                                                      \
       LamTot lt1_;                                                                                   \
       lt1_.lam = nl_; lt1_.tot = lt0_.tot + (relax ? dl_ : nl_);                                     \
       *lt_ = lt1_;                                                                                   \
     }                                                                                                \
     if (ty_ == ROW_CONTACT_N) pn_sum += nl_;                                                         \
-    _Pragma("unroll") for (int k = 0; k < SL; k++) u[k] += B_[k] * dl_;                              \
+    _Pragma("unroll") for (int k = 0; k < SL; k++) u[k] += B_[k] * dl_;  /* B_ is zero for padding rows */  \
   }
     float pn_sum = 0.f;
     B2S_FETCH_ROW(0, JA, BA, scA, mcA)

@@ -78,11 +78,11 @@ class CameraSensors:
                 d["rgb"] = self.group.get_picture_cuda("Color", i)[..., :3]
             ps = self.group.get_picture_cuda("PositionSegmentation", i)
             if depth:
-                d["depth"] = -ps[..., [2]]
+                d["depth"] = -ps[..., 2:3]  # strided elementwise negation; a slice, not a gather
             if position:
                 d["position"] = ps[..., :3]
             if segmentation:
-                d["segmentation"] = ps[..., [3]]
+                d["segmentation"] = ps[..., 3:4]  # a view of the render target
             out[c["uid"]] = d
         return out
 
