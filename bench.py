@@ -203,7 +203,8 @@ def run_gpu(args):
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = world.kernel_launches - launches0
-    t_dev = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / 1e3
+    step_ms = sorted(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t_dev = sum(step_ms) / 1e3
     # ---------------- timed: end to end through the public API with host buffers ("e2e")
     h_actions = torch.empty((n_envs, A), dtype=torch.float32).pin_memory()
     h_obs = torch.empty(tuple(obs.shape), dtype=torch.float32).pin_memory()
@@ -257,7 +258,8 @@ def run_gpu(args):
         "config": {"workload": f"PickCube-v1 num_envs={n_envs}/GPU state-only, sim_freq=100 control_freq=20 (5 substeps/step), "
                                "15 position + 1 velocity iterations, pd_joint_delta_pos, auto-reset on (BASELINE.json configs[1])",
                    "num_envs_total": total_envs, "substeps_per_s": value * substeps, "l2": "256 MiB write between timed steps",
-                   "obs_all_gather": bool(gather_buf is not None), "wall_s": t_wall},
+                   "obs_all_gather": bool(gather_buf is not None), "wall_s": t_wall,
+                   "step_ms_median_rank0": step_ms[len(step_ms) // 2], "step_ms_max_rank0": step_ms[-1]},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n_envs * A * 4,
                 "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel())},
         "gpu_launches": int(launches),

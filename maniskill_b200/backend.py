@@ -174,7 +174,8 @@ class World:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _step_launches(self, substeps, fetch_mask):
-        """Kernels one b2s_step launches (csrc/b2s_api.cu): kin (2 launches), collide, manifest, rowfill, solve per substep + the fetch."""
+        """Kernels one b2s_step launches (csrc/b2s_api.cu): kin x2, collide, manifest, rowfill, solve per substep + the fetch
+        (replayed as one CUDA graph); B2S_FUSED=1 selects the single-lane kernel."""
         if os.environ.get("B2S_FUSED", "0") not in ("", "0"):
             return 1
         return 6 * int(substeps) + (1 if fetch_mask else 0)
