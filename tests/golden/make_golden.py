@@ -16,6 +16,10 @@ Covered reference functions (file:line):
   mani_skill/utils/structs/pose.py                   Pose.__mul__, Pose.inv, Pose.to_transformation_matrix
   mani_skill/envs/tasks/tabletop/pick_cube.py:132-191  _get_obs_extra, evaluate (success logic), compute_dense_reward
   mani_skill/agents/robots/panda/panda.py:237-269    is_grasping, is_static
+  mani_skill/envs/tasks/tabletop/peg_insertion_side.py:250-360  peg_head_pose / box_hole_pose / goal_pose, has_peg_inserted,
+                                                     evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358  handle_link_positions, evaluate, _get_obs_extra,
+                                                     compute_dense_reward
 """
 import importlib.util
 import os
@@ -170,6 +174,88 @@ def main():
     G["pc_reward_norm"] = pc.PickCubeEnv.compute_normalized_dense_reward(fake, None, None, info)
     extra = pc.PickCubeEnv._get_obs_extra(fake, info)
     G["pc_extra_flat"] = common.flatten_state_dict(extra, use_torch=True)
+    # ---- PegInsertionSide task logic on synthetic states (peg near / inside / far from the hole, grasped or not)
+    class SapienPose:  # stands in for sapien.Pose in `tgt_gripper_pose * sapien.Pose([-0.06, 0, 0])`
+        def __init__(self, p=(0, 0, 0), q=(1, 0, 0, 0)):
+            self.p, self.q = np.asarray(p, dtype=np.float32), np.asarray(q, dtype=np.float32)
+
+    sys.modules["sapien"].Pose = SapienPose
+    stub("mani_skill.utils.building.actors")
+    sys.modules["mani_skill.agents.robots.panda"].PandaWristCam = object
+    stub("mani_skill.envs.scene")
+    sys.modules["mani_skill.utils.structs"].Pose = Pose
+    sys.modules["mani_skill.utils.structs"].Actor = object
+    sys.modules["mani_skill.envs.utils"].randomization = sys.modules["mani_skill.envs.utils.randomization"]
+    sys.modules["mani_skill.utils"].common = common
+    sys.modules["mani_skill.utils"].sapien_utils = sapien_utils
+    peg_mod = load("mani_skill.envs.tasks.tabletop.peg_insertion_side", "mani_skill/envs/tasks/tabletop/peg_insertion_side.py")
+    PE = peg_mod.PegInsertionSideEnv
+    m = 16
+    lengths = 0.085 + 0.04 * torch.rand(m, generator=g)
+    radii = 0.015 + 0.01 * torch.rand(m, generator=g)
+    peg_half = torch.stack([lengths, radii, radii], 1)
+    box_raw = torch.hstack([torch.randn(m, 3, generator=g) * 0.1, torch.nn.functional.normalize(torch.randn(m, 4, generator=g), dim=-1)])
+    hole_off = torch.hstack([torch.zeros(m, 1), 0.02 * torch.randn(m, 2, generator=g)])
+    box_hole_offsets = Pose.create_from_pq(p=hole_off)
+    peg_head_offsets = Pose.create_from_pq(p=torch.hstack([lengths[:, None], torch.zeros(m, 2)]))
+    hole_radii = radii + 0.003
+    goal = Pose.create(box_raw) * box_hole_offsets * peg_head_offsets.inv()
+    # envs 0-3: peg exactly at the goal (inserted); 4-7: slightly off (pre-inserted / close); the rest: anywhere
+    pert = torch.randn(m, 3, generator=g) * 0.1
+    pert[:4] = 0
+    pert[4:8] = torch.randn(4, 3, generator=g) * 0.004
+    peg_raw = goal.raw_pose.clone()
+    peg_raw[:, :3] += pert
+    peg_raw[8:, 3:] = torch.nn.functional.normalize(torch.randn(m - 8, 4, generator=g), dim=-1)
+    tcp_raw2 = torch.hstack([peg_raw[:, :3] + torch.randn(m, 3, generator=g) * 0.05, qa[:m]])
+    peg_grasped = torch.tensor([True, True, False, True] * (m // 4))
+    fake_peg = SimpleNamespace(
+        peg=SimpleNamespace(pose=Pose.create(peg_raw)), box=SimpleNamespace(pose=Pose.create(box_raw)), peg_head_offsets=peg_head_offsets,
+        box_hole_offsets=box_hole_offsets, box_hole_radii=hole_radii, peg_half_sizes=peg_half,
+        agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(tcp_raw2)), is_grasping=lambda obj, max_angle=None: peg_grasped),
+        obs_mode_struct=SimpleNamespace(use_state=True))
+    fake_peg.peg_head_pose = PE.peg_head_pose.fget(fake_peg)
+    fake_peg.box_hole_pose = PE.box_hole_pose.fget(fake_peg)
+    fake_peg.goal_pose = PE.goal_pose.fget(fake_peg)
+    fake_peg.has_peg_inserted = lambda: PE.has_peg_inserted(fake_peg)
+    pinfo = PE.evaluate(fake_peg)
+    G["peg_peg"], G["peg_box"], G["peg_tcp"], G["peg_half"], G["peg_hole_off"], G["peg_hole_radii"], G["peg_grasped"] = \
+        peg_raw, box_raw, tcp_raw2, peg_half, hole_off, hole_radii, peg_grasped
+    G["peg_head_pose"], G["peg_box_hole_pose"], G["peg_goal_pose"] = fake_peg.peg_head_pose.raw_pose, fake_peg.box_hole_pose.raw_pose, fake_peg.goal_pose.raw_pose
+    G["peg_success"], G["peg_head_at_hole"] = pinfo["success"], pinfo["peg_head_pos_at_hole"]
+    G["peg_reward"] = PE.compute_dense_reward(fake_peg, None, None, pinfo)
+    G["peg_extra_flat"] = common.flatten_state_dict(PE._get_obs_extra(fake_peg, pinfo), use_torch=True)
+    # ---- OpenCabinetDrawer task logic on synthetic states (drawer closed / partly open / open enough, handle moving or still)
+    for n_ in ["trimesh", "mani_skill.utils.building.articulations", "mani_skill.utils.building.ground", "mani_skill.utils.io_utils"]:
+        stub(n_)
+    pkg("mani_skill.envs.tasks.mobile_manipulation")
+    import pathlib
+    sys.modules["mani_skill"].PACKAGE_ASSET_DIR = pathlib.Path("/nonexistent")
+    stub("mani_skill.utils.geometry.bounding_cylinder")
+    geo = load("mani_skill.utils.geometry.geometry", "mani_skill/utils/geometry/geometry.py")
+    sys.modules["mani_skill.utils.structs"].Articulation = object
+    sys.modules["mani_skill.utils.structs"].Link = object
+    cab_mod = load("mani_skill.envs.tasks.mobile_manipulation.open_cabinet_drawer", "mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py")
+    CE = cab_mod.OpenCabinetDrawerEnv
+    m = 12
+    target_qpos = 0.2 + 0.2 * torch.rand(m, generator=g)
+    joint_qpos = target_qpos * torch.tensor([0.0, 0.0005, 0.3, 0.95, 1.0, 1.05, 1.2, 0.5, 1.1, 0.0, 1.3, 0.999])
+    handle_pose = Pose.create_from_pq(torch.randn(m, 3, generator=g) * 0.3, torch.nn.functional.normalize(torch.randn(m, 4, generator=g), dim=-1))
+    handle_local = torch.randn(m, 3, generator=g) * 0.1
+    ang_v = torch.randn(m, 3, generator=g) * 0.8
+    lin_v = torch.randn(m, 3, generator=g) * 0.08
+    tcp3 = Pose.create_from_pq(torch.randn(m, 3, generator=g) * 0.3, qa[:m])
+    fake_cab = SimpleNamespace(
+        handle_link=SimpleNamespace(joint=SimpleNamespace(qpos=joint_qpos), pose=handle_pose, angular_velocity=ang_v, linear_velocity=lin_v),
+        handle_link_pos=handle_local, target_qpos=target_qpos, device=torch.device("cpu"), obs_mode="state",
+        agent=SimpleNamespace(tcp=SimpleNamespace(pose=tcp3)))
+    fake_cab.handle_link_positions = lambda env_idx=None: CE.handle_link_positions(fake_cab, env_idx)
+    cinfo = CE.evaluate(fake_cab)
+    G["cab_target_qpos"], G["cab_joint_qpos"], G["cab_handle_pose"], G["cab_handle_local"], G["cab_ang_v"], G["cab_lin_v"], G["cab_tcp"] = \
+        target_qpos, joint_qpos, handle_pose.raw_pose, handle_local, ang_v, lin_v, tcp3.raw_pose
+    G["cab_success"], G["cab_open_enough"], G["cab_handle_link_pos"] = cinfo["success"], cinfo["open_enough"], cinfo["handle_link_pos"]
+    G["cab_reward"] = CE.compute_dense_reward(fake_cab, None, None, cinfo)
+    G["cab_extra_flat"] = common.flatten_state_dict(CE._get_obs_extra(fake_cab, cinfo), use_torch=True)
     # ---- Panda.is_grasping / is_static
     base_agent = stub("mani_skill.agents.base_agent")
     base_agent.BaseAgent = type("BaseAgent", (), {})

@@ -94,3 +94,51 @@ def test_panda_is_grasping_and_static():
                            scene=SimpleNamespace(get_pairwise_contact_forces=lambda a, b: lf if a is f1 else rf))
     assert np.array_equal(Panda.is_grasping(fake, None).numpy(), G["pg_is_grasping"])
     assert np.array_equal(Panda.is_static(fake, 0.2).numpy(), G["pg_is_static"])
+
+
+def _fake_peg():
+    from maniskill_b200.envs.peg_insertion_side import PegInsertionSideEnv as PE
+    m = len(G["peg_grasped"])
+    grasped = T("peg_grasped")
+    hole_off = Pose(torch.hstack([T("peg_hole_off"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    half = T("peg_half")
+    head_off = Pose(torch.hstack([half[:, :1], torch.zeros(m, 2), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(peg=SimpleNamespace(pose=Pose(T("peg_peg"))), box=SimpleNamespace(pose=Pose(T("peg_box"))), peg_head_offsets=head_off,
+                           box_hole_offsets=hole_off, box_hole_radii=T("peg_hole_radii"), peg_half_sizes=half, obs_mode="state", device=torch.device("cpu"),
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("peg_tcp"))), is_grasping=lambda obj, max_angle=None: grasped))
+    fake.peg_head_pose = PE.peg_head_pose.fget(fake)
+    fake.box_hole_pose = PE.box_hole_pose.fget(fake)
+    fake.goal_pose = PE.goal_pose.fget(fake)
+    fake.has_peg_inserted = lambda: PE.has_peg_inserted(fake)
+    return PE, fake
+
+
+def test_peg_insertion_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/peg_insertion_side.py:250-360 run by the reference's own code on the same synthetic states."""
+    PE, fake = _fake_peg()
+    close(fake.peg_head_pose.raw_pose, G["peg_head_pose"])
+    close(fake.box_hole_pose.raw_pose, G["peg_box_hole_pose"])
+    close(fake.goal_pose.raw_pose, G["peg_goal_pose"], 2e-6)
+    info = PE.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["peg_success"])
+    assert G["peg_success"][:4].all() and not G["peg_success"].all()  # the fixture holds inserted and not-inserted pegs
+    close(info["peg_head_pos_at_hole"], G["peg_head_at_hole"], 2e-6)
+    close(PE.compute_dense_reward(fake, None, None, info), G["peg_reward"], 2e-5)
+    close(U.flatten_state_dict(PE._get_obs_extra(fake, info)), G["peg_extra_flat"], 2e-6)
+
+
+def test_open_cabinet_drawer_evaluate_reward_obs():
+    """mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358 run by the reference's own code."""
+    from maniskill_b200.envs.open_cabinet_drawer import OpenCabinetDrawerEnv as CE
+    jq = T("cab_joint_qpos")
+    fake = SimpleNamespace(handle_link=SimpleNamespace(pose=Pose(T("cab_handle_pose")), angular_velocity=T("cab_ang_v"), linear_velocity=T("cab_lin_v")),
+                           handle_link_pos=T("cab_handle_local"), target_qpos=T("cab_target_qpos"), obs_mode="state", device=torch.device("cpu"),
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("cab_tcp")))), _target_joint_qpos=lambda: jq)
+    fake.handle_link_positions = lambda env_idx=None: CE.handle_link_positions(fake, env_idx)
+    info = CE.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["cab_success"])
+    assert np.array_equal(info["open_enough"].numpy(), G["cab_open_enough"])
+    assert G["cab_open_enough"].any() and not G["cab_open_enough"].all()
+    close(info["handle_link_pos"], G["cab_handle_link_pos"], 2e-6)
+    close(CE.compute_dense_reward(fake, None, None, info), G["cab_reward"], 2e-6)
+    close(U.flatten_state_dict(CE._get_obs_extra(fake, info)), G["cab_extra_flat"], 2e-6)
