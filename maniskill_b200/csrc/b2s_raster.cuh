@@ -62,18 +62,30 @@ struct RasterGroup {
 #define B2S_DEPTH_BITS 24
 #define B2S_DEPTH_MAX 16777215.0f
 
-// reversed-z quantisation shared by the raster and the analytic pass
-B2S_HD unsigned depth_key(float d, float nearp, float farp) {
-  float inv = 1.0f / d, invn = 1.0f / nearp, invf = 1.0f / farp;
-  float t = (inv - invf) / (invn - invf);  // 1 at near, 0 at far
+// Reversed-z quantisation shared by the raster and the analytic pass, on 1/depth.  The constants of a camera are computed once
+// (DepthMap), a sample costs no division: the key comes from the interpolated 1/depth directly, the near/far test is done on it.
+struct DepthMap {
+  float invn, invf, range, scale, inv_max;  // 1/near, 1/far, invn - invf, 1 / range, 1 / B2S_DEPTH_MAX
+};
+B2S_HD DepthMap depth_map(float nearp, float farp) {
+  DepthMap m;
+  m.invn = 1.0f / nearp;
+  m.invf = 1.0f / farp;
+  m.range = m.invn - m.invf;
+  m.scale = 1.0f / m.range;
+  m.inv_max = 1.0f / B2S_DEPTH_MAX;
+  return m;
+}
+B2S_HD bool inv_depth_in_range(float inv, const DepthMap& m) { return inv < m.invn && inv > m.invf; }
+B2S_HD unsigned depth_key_inv(float inv, const DepthMap& m) {
+  float t = (inv - m.invf) * m.scale;  // 1 at near, 0 at far
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   float q = B2S_DEPTH_MAX - t * B2S_DEPTH_MAX;
   return (unsigned)q;
 }
-B2S_HD float key_depth(unsigned k, float nearp, float farp) {
-  float invn = 1.0f / nearp, invf = 1.0f / farp;
-  float t = (B2S_DEPTH_MAX - (float)k) / B2S_DEPTH_MAX;
-  float inv = invf + t * (invn - invf);
+B2S_HD float key_depth(unsigned k, const DepthMap& m) {
+  float t = (B2S_DEPTH_MAX - (float)k) * m.inv_max;
+  float inv = m.invf + t * m.range;
   return 1.0f / inv;
 }
 
@@ -143,17 +155,15 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
 
 // one coverage + depth sample: edge functions at the pixel centre, 1/depth interpolated in screen space, atomicMin on the key
 __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int y, const float* px, const float* py, const float* pd, float inv_area,
-                                              int v, float nearp, float farp) {
+                                              int v, const DepthMap& dm) {
   float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
   float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
   float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
   float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
   if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) return;
   float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
-  if (!(inv > 0.0f)) return;
-  float d = 1.0f / inv;
-  if (d <= nearp || d >= farp) return;
-  unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
+  if (!inv_depth_in_range(inv, dm)) return;
+  unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
   atomicMin(&zkey[y * W + x], key);
 }
 
@@ -175,6 +185,8 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
   const float nearp = R.cam_intr[6 * cam + 4], farp = R.cam_intr[6 * cam + 5];
+  const DepthMap dm = depth_map(nearp, farp);
+  const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
   const int npix = W * H;
   for (int i = threadIdx.x; i < npix; i += blockDim.x) zkey[i] = 0xFFFFFFFFu;
   // camera pose in the sub-scene frame
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
       }
     }
     for (int y = y0; y <= y1; y++)
-      for (int x = x0; x <= x1; x++) raster_sample(zkey, W, x, y, px, py, pd, inv_area, v, nearp, farp);
+      for (int x = x0; x <= x1; x++) raster_sample(zkey, W, x, y, px, py, pd, inv_area, v, dm);
   }
   __syncthreads();
   {
@@ -279,7 +291,14 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
     for (int b = 0; b < nb; b++) {
       const float* o = big_tri[b];
       const int x0 = big_box[b][0], y0 = big_box[b][1], bw = big_box[b][2], cnt = big_box[b][3], v = big_box[b][4];
-      for (int p = threadIdx.x; p < cnt; p += blockDim.x) raster_sample(zkey, W, x0 + p % bw, y0 + p / bw, o, o + 3, o + 6, o[9], v, nearp, farp);
+      // pixel walk over the bounding box without a division per sample: (xx, yy) advance by blockDim incrementally
+      int yy = threadIdx.x / bw, xx = threadIdx.x - yy * bw;
+      const int sy_ = blockDim.x / bw, sx_ = blockDim.x - sy_ * bw;
+      for (int p = threadIdx.x; p < cnt; p += blockDim.x) {
+        raster_sample(zkey, W, x0 + xx, y0 + yy, o, o + 3, o + 6, o[9], v, dm);
+        xx += sx_; yy += sy_;
+        if (xx >= bw) { xx -= bw; yy++; }
+      }
     }
   }
   __syncthreads();
@@ -301,14 +320,14 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
         if (vis_kind[v] != SH_CONVEX && x >= vis_rect[v][0] && x <= vis_rect[v][1]) xmask |= 1ull << v;
       mask_x = x;
     }
-    float ry = -((float)x + 0.5f - cx) / fx, rz = -((float)y + 0.5f - cy) / fy;
+    float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
     v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
     float best = 1e30f;
     int best_v = -1;
     v3 best_n = mk3(0, 0, 0);  // world normal
     unsigned k = zkey[i];
     if (k != 0xFFFFFFFFu) {
-      best = key_depth(k >> 8, nearp, farp);
+      best = key_depth(k >> 8, dm);
       best_v = (int)(k & 255u);
     }
     bool raster_hit = best_v >= 0;
@@ -346,9 +365,9 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
         unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
         v3 n_cam = mk3(-1, 0, 0);
         if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
-          float dx_ = key_depth(kx >> 8, nearp, farp), dy_ = key_depth(ky >> 8, nearp, farp);
-          v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) / fx, rz) * dx_;
-          v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) / fy) * dy_;
+          float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
+          v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
+          v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
           v3 e1 = pxn - pc, e2 = pyn - pc;
           if (xn < x) e1 = -e1;
           if (yn < y) e2 = -e2;

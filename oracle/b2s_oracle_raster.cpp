@@ -82,17 +82,29 @@ inline P7 ident() {
 }
 
 const float DEPTH_MAX = 16777215.0f;
-inline unsigned depth_key(float d, float nearp, float farp) {
-  float inv = 1.0f / d, invn = 1.0f / nearp, invf = 1.0f / farp;
-  float t = (inv - invf) / (invn - invf);
+// reversed-z quantisation on 1/depth; per-camera constants computed once (maniskill_b200/csrc/b2s_raster.cuh DepthMap)
+struct DepthMap {
+  float invn, invf, range, scale, inv_max;
+};
+inline DepthMap depth_map(float nearp, float farp) {
+  DepthMap m;
+  m.invn = 1.0f / nearp;
+  m.invf = 1.0f / farp;
+  m.range = m.invn - m.invf;
+  m.scale = 1.0f / m.range;
+  m.inv_max = 1.0f / DEPTH_MAX;
+  return m;
+}
+inline bool inv_depth_in_range(float inv, const DepthMap& m) { return inv < m.invn && inv > m.invf; }
+inline unsigned depth_key_inv(float inv, const DepthMap& m) {
+  float t = (inv - m.invf) * m.scale;
   t = fminf(fmaxf(t, 0.0f), 1.0f);
   float q = DEPTH_MAX - t * DEPTH_MAX;
   return (unsigned)q;
 }
-inline float key_depth(unsigned k, float nearp, float farp) {
-  float invn = 1.0f / nearp, invf = 1.0f / farp;
-  float t = (DEPTH_MAX - (float)k) / DEPTH_MAX;
-  float inv = invf + t * (invn - invf);
+inline float key_depth(unsigned k, const DepthMap& m) {
+  float t = (DEPTH_MAX - (float)k) * m.inv_max;
+  float inv = m.invf + t * m.range;
   return 1.0f / inv;
 }
 inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, F3& n_local) {
@@ -153,6 +165,8 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
                     int n_rows, const float* body, const float* cam, uint8_t* color, int16_t* posseg) {
   const int W = (int)cam[0], H = (int)cam[1];
   const float fx = cam[2], fy = cam[3], cx = cam[4], cy = cam[5], nearp = cam[6], farp = cam[7];
+  const DepthMap dm = depth_map(nearp, farp);
+  const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
   const int mount = (int)cam[8];
   auto body_pose = [&](int row) {
     if (row < 0) return ident();
@@ -220,23 +234,21 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
         float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
         if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) continue;
         float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
-        if (!(inv > 0.0f)) continue;
-        float d = 1.0f / inv;
-        if (d <= nearp || d >= farp) continue;
-        unsigned key = (depth_key(d, nearp, farp) << 8) | (unsigned)v;
+        if (!inv_depth_in_range(inv, dm)) continue;
+        unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
         if (key < zkey[y * W + x]) zkey[y * W + x] = key;
       }
   }
   for (int i = 0; i < npix; i++) {
     int x = i % W, y = i / W;
-    float ry = -((float)x + 0.5f - cx) / fx, rz = -((float)y + 0.5f - cy) / fy;
+    float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
     F3 rdir = f3(1.0f, ry, rz);
     float best = 1e30f;
     int best_v = -1;
     F3 best_n = f3(0, 0, 0);
     unsigned k = zkey[i];
     if (k != 0xFFFFFFFFu) {
-      best = key_depth(k >> 8, nearp, farp);
+      best = key_depth(k >> 8, dm);
       best_v = (int)(k & 255u);
     }
     bool raster_hit = best_v >= 0;
@@ -274,9 +286,9 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
         unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
         F3 n_cam = f3(-1, 0, 0);
         if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
-          float dx_ = key_depth(kx >> 8, nearp, farp), dy_ = key_depth(ky >> 8, nearp, farp);
-          F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) / fx, rz) * dx_;
-          F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) / fy) * dy_;
+          float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
+          F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
+          F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
           F3 e1 = pxn - pc, e2 = pyn - pc;
           if (xn < x) e1 = -e1;
           if (yn < y) e2 = -e2;
