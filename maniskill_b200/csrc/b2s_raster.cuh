@@ -257,13 +257,13 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
     }
     if (!ok) continue;  // triangles touching the near plane are dropped (robot links never get that close)
     float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
-    if (area == 0.0f) continue;
-    if (area < 0.0f) {  // make counter-clockwise in screen space (hulls are closed: back faces are hidden by front ones)
-      float tx = px[1]; px[1] = px[2]; px[2] = tx;
-      float ty = py[1]; py[1] = py[2]; py[2] = ty;
-      float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
-      area = -area;
-    }
+    // hull triangles are wound outwards (render.py build_visual_table): with screen x to the right and y down a front face has
+    // negative area; back faces are culled (hulls are closed: they are hidden by the front faces), front faces made counter-clockwise
+    if (!(area < 0.0f)) continue;
+    float tx = px[1]; px[1] = px[2]; px[2] = tx;
+    float ty = py[1]; py[1] = py[2]; py[2] = ty;
+    float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
+    area = -area;
     float minx = fminf(px[0], fminf(px[1], px[2])), maxx = fmaxf(px[0], fmaxf(px[1], px[2]));
     float miny = fminf(py[0], fminf(py[1], py[2])), maxy = fmaxf(py[0], fmaxf(py[1], py[2]));
     int x0 = max(0, (int)floorf(minx - 0.5f)), x1 = min(W - 1, (int)ceilf(maxx - 0.5f));

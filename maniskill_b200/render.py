@@ -35,7 +35,12 @@ def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = Fa
             h = v["hull"]
             verts = hull_verts[hull_off[h]:hull_off[h + 1]]
             tris = cm.hull_tris[h]
-            tri_verts.append(verts[tris].reshape(-1, 9))
+            tv = verts[tris].astype(np.float64)  # [n_tri, 3, 3]
+            # outward winding (normal away from the hull centre): the rasteriser culls back faces by the sign of the screen area
+            nrm = np.cross(tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0])
+            inward = np.einsum("ij,ij->i", nrm, tv.mean(1) - verts.mean(0)) < 0
+            tv[inward] = tv[inward][:, [0, 2, 1]]
+            tri_verts.append(tv.astype(np.float32).reshape(-1, 9))
             tri_vis.extend([i] * len(tris))
     f32 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(shape))
     n = len(vis)

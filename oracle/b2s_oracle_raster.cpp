@@ -210,13 +210,13 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
     }
     if (!ok) continue;
     float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
-    if (area == 0.0f) continue;
-    if (area < 0.0f) {
-      float tx = px[1]; px[1] = px[2]; px[2] = tx;
-      float ty = py[1]; py[1] = py[2]; py[2] = ty;
-      float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
-      area = -area;
-    }
+    // hull triangles are wound outwards (render.py build_visual_table): with screen x to the right and y down a front face has
+    // negative area; back faces are culled (hulls are closed: they are hidden by the front faces), front faces made counter-clockwise
+    if (!(area < 0.0f)) continue;
+    float tx = px[1]; px[1] = px[2]; px[2] = tx;
+    float ty = py[1]; py[1] = py[2]; py[2] = ty;
+    float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
+    area = -area;
     float minx = fminf(px[0], fminf(px[1], px[2])), maxx = fmaxf(px[0], fmaxf(px[1], px[2]));
     float miny = fminf(py[0], fminf(py[1], py[2])), maxy = fmaxf(py[0], fmaxf(py[1], py[2]));
     int x0 = (int)floorf(minx - 0.5f), x1 = (int)ceilf(maxx - 0.5f), y0 = (int)floorf(miny - 0.5f), y1 = (int)ceilf(maxy - 0.5f);
