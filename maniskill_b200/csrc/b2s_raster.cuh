@@ -151,7 +151,9 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
   return P;
 }
 
-#define B2S_MAX_BIG_TRIS 384
+#define B2S_MAX_BIG_TRIS 512
+#define B2S_BIG_TRI_PIXELS 24     // bounding boxes above this many pixels leave the one-thread path
+#define B2S_HUGE_TRI_PIXELS 2048  // ... and above this many are shared by the whole CTA instead of one warp
 
 // one coverage + depth sample: edge functions at the pixel centre, 1/depth interpolated in screen space, atomicMin on the key
 __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int y, const float* px, const float* py, const float* pd, float inv_area,
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
   __shared__ int vis_kind[64];
   __shared__ float vis_o[64][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
   __shared__ float big_tri[B2S_MAX_BIG_TRIS][10];
-  __shared__ int big_box[B2S_MAX_BIG_TRIS][5];
+  __shared__ int big_box[B2S_MAX_BIG_TRIS][7];  // x0 y0 width count visual, walk step (x, y) of the unit that rasterises it
   __shared__ int n_big;
   if (threadIdx.x == 0) n_big = 0;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
@@ -271,14 +273,18 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
     if (x0 > x1 || y0 > y1) continue;
     float inv_area = 1.0f / area;
     const int bw = x1 - x0 + 1, cnt = bw * (y1 - y0 + 1);
-    if (cnt > 48) {
-      // large on-screen triangle (close-up views of the wrist camera): hand it to the whole CTA instead of one thread
+    if (cnt > B2S_BIG_TRI_PIXELS) {
+      // larger on-screen triangle: queued and rasterised by a whole warp (by the whole CTA when huge: close-ups of the wrist camera)
+      // so that the one-thread path stays short and balanced
       int slot = atomicAdd(&n_big, 1);
       if (slot < B2S_MAX_BIG_TRIS) {
         float* o = big_tri[slot];
         o[0] = px[0]; o[1] = px[1]; o[2] = px[2]; o[3] = py[0]; o[4] = py[1]; o[5] = py[2];
         o[6] = pd[0]; o[7] = pd[1]; o[8] = pd[2]; o[9] = inv_area;
+        const int stride = cnt > B2S_HUGE_TRI_PIXELS ? (int)blockDim.x : 32;  // pixels between two samples of one lane
+        const int sy_ = stride / bw;
         big_box[slot][0] = x0; big_box[slot][1] = y0; big_box[slot][2] = bw; big_box[slot][3] = cnt; big_box[slot][4] = v;
+        big_box[slot][5] = stride - sy_ * bw; big_box[slot][6] = sy_;
         continue;
       }
     }
@@ -287,17 +293,23 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
   }
   __syncthreads();
   {
+    // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride`
+    // pixels, (xx, yy) follow incrementally with the precomputed (stride % width, stride / width)
     const int nb = n_big < B2S_MAX_BIG_TRIS ? n_big : B2S_MAX_BIG_TRIS;
-    for (int b = 0; b < nb; b++) {
-      const float* o = big_tri[b];
-      const int x0 = big_box[b][0], y0 = big_box[b][1], bw = big_box[b][2], cnt = big_box[b][3], v = big_box[b][4];
-      // pixel walk over the bounding box without a division per sample: (xx, yy) advance by blockDim incrementally
-      int yy = threadIdx.x / bw, xx = threadIdx.x - yy * bw;
-      const int sy_ = blockDim.x / bw, sx_ = blockDim.x - sy_ * bw;
-      for (int p = threadIdx.x; p < cnt; p += blockDim.x) {
-        raster_sample(zkey, W, x0 + xx, y0 + yy, o, o + 3, o + 6, o[9], v, dm);
-        xx += sx_; yy += sy_;
-        if (xx >= bw) { xx -= bw; yy++; }
+    const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int pass = 0; pass < 2; pass++) {  // 0: warp-sized triangles, one warp each; 1: huge ones, all threads
+      for (int b = pass == 0 ? warp : 0; b < nb; b += pass == 0 ? n_warp : 1) {
+        const int cnt = big_box[b][3];
+        if ((cnt > B2S_HUGE_TRI_PIXELS) != (pass == 1)) continue;
+        const float* o = big_tri[b];
+        const int x0 = big_box[b][0], y0 = big_box[b][1], bw = big_box[b][2], v = big_box[b][4], sx_ = big_box[b][5], sy_ = big_box[b][6];
+        const int first = pass == 0 ? lane : (int)threadIdx.x, stride = pass == 0 ? 32 : (int)blockDim.x;
+        int yy = first / bw, xx = first - yy * bw;
+        for (int p = first; p < cnt; p += stride) {
+          raster_sample(zkey, W, x0 + xx, y0 + yy, o, o + 3, o + 6, o[9], v, dm);
+          xx += sx_; yy += sy_;
+          if (xx >= bw) { xx -= bw; yy++; }
+        }
       }
     }
   }
