@@ -96,3 +96,44 @@ def rel_err_vec(a, b, floor):
     d = np.linalg.norm(a - b, axis=-1)
     n = np.maximum(np.linalg.norm(b, axis=-1), floor)
     return float(np.max(d / n))
+
+
+def run_task_vs_oracle(task, steps, n, world_factory=None, seed=4):
+    """Steps a registered task with seeded random actions on the product backend (CUDA through the C-ABI; or the host emulation when
+    `world_factory` is given) and the CPU oracle started from the same state and fed the same drive targets.  Returns
+    (max |qpos error|, max |position error|, overflow flag of the backend)."""
+    import torch
+
+    import maniskill_b200 as ms
+    from oracle.oracle import OracleWorld
+    kw = dict(device="cpu", world_factory=world_factory) if world_factory is not None else {}
+    env = ms.make(task, num_envs=n, obs_mode="state", **kw)
+    obs, _ = env.reset(seed=seed)
+    w, cm = env.scene.world, env.cm
+    n_art, n_link = cm.scalars["n_art"], cm.scalars["n_link"]
+    o = OracleWorld(cm, "f32")
+
+    def joint_state(t):  # exposed [N*n_art, max_dof] -> oracle [N, n_dof]
+        t = t.double().cpu().numpy().reshape(n, n_art, -1)
+        return np.concatenate([t[:, a, :cm.art_dof_start[a + 1] - cm.art_dof_start[a]] for a in range(n_art)], axis=1)
+
+    for name, buf in (("qpos", w.qpos), ("qvel", w.qvel), ("target_qpos", w.target_qpos), ("target_qvel", w.target_qvel)):
+        o.set_joint(name, joint_state(buf))
+    body = w.body_view().double().cpu().numpy()
+    o.set_bodies(body[:, n_link:])
+    o.set_roots(np.stack([body[:, cm.arrays["art_link_start"][a], :7] for a in range(n_art)], axis=1))
+    g = torch.Generator(device=env.device).manual_seed(0)
+    for _ in range(steps):
+        a = 2 * torch.rand((n, env.action_dim), device=env.device, generator=g) - 1
+        obs, rew, term, trunc, info = env.step(a)
+        o.set_joint("target_qpos", joint_state(w.target_qpos))
+        o.set_joint("target_qvel", joint_state(w.target_qvel))
+        if task == "OpenCabinetDrawer-v1":  # the goal marker is re-posed by the task every step
+            o.set_bodies(w.body_view().double().cpu().numpy()[:, n_link:])
+        o.step(5)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    err_q = float(np.abs(joint_state(w.qpos) - o.get_joint("qpos")).max())
+    err_p = float(np.abs(w.body_view().double().cpu().numpy()[..., :3] - o.rigid_body_data()[..., :3]).max())
+    overflow = int(w.overflow_flag.item())
+    env.close()
+    return err_q, err_p, overflow

@@ -95,41 +95,7 @@ def test_fused_step_matches_python_path():
 def test_other_tasks_match_oracle(task, steps):
     """Heterogeneous per-env geometry (peg) and the two-articulation / 17-dof configuration (Fetch + cabinet, the large
     kernel instantiation) against the CPU oracle started from the same state."""
-    import maniskill_b200 as ms
-    from oracle.oracle import OracleWorld
-    n = 16
-    env = ms.make(task, num_envs=n, obs_mode="state")
-    obs, _ = env.reset(seed=4)
-    w, cm = env.scene.world, env.cm
-    nd = cm.scalars["n_dof"]
-    o = OracleWorld(cm, "f32")
-
-    def joint_state(t):  # exposed [N*n_art, max_dof] -> oracle [N, n_dof]
-        t = t.double().cpu().numpy().reshape(n, cm.scalars["n_art"], -1)
-        return np.concatenate([t[:, a, :cm.art_dof_start[a + 1] - cm.art_dof_start[a]] for a in range(cm.scalars["n_art"])], axis=1)
-
-    o.set_joint("qpos", joint_state(w.qpos))
-    o.set_joint("qvel", joint_state(w.qvel))
-    o.set_joint("target_qpos", joint_state(w.target_qpos))
-    o.set_joint("target_qvel", joint_state(w.target_qvel))
-    body = w.body_view().double().cpu().numpy()
-    o.set_bodies(body[:, cm.scalars["n_link"]:])
-    roots = np.stack([body[:, cm.arrays["art_link_start"][a], :7] for a in range(cm.scalars["n_art"])], axis=1)
-    o.set_roots(roots)
-    g = torch.Generator(device=env.device).manual_seed(0)
-    for _ in range(steps):
-        a = 2 * torch.rand((n, env.action_dim), device=env.device, generator=g) - 1
-        obs, rew, term, trunc, info = env.step(a)
-        o.set_joint("target_qpos", joint_state(w.target_qpos))
-        o.set_joint("target_qvel", joint_state(w.target_qvel))
-        o.set_bodies(np.concatenate([o.get_bodies()[:, :0], w.body_view().double().cpu().numpy()[:, cm.scalars["n_link"]:]], axis=1)
-                     if task == "OpenCabinetDrawer-v1" else o.get_bodies())  # the goal marker is re-posed by the task every step
-        o.step(5)
-    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
-    err_q = np.abs(joint_state(w.qpos) - o.get_joint("qpos")).max()
-    ref = o.rigid_body_data()
-    got = w.body_view().double().cpu().numpy()
-    err_p = np.abs(got[..., :3] - ref[..., :3]).max()
+    from scenarios import run_task_vs_oracle
+    err_q, err_p, overflow = run_task_vs_oracle(task, steps, 16)
     assert err_q < 1e-4 and err_p < 1e-4, (err_q, err_p)
-    assert int(w.overflow_flag.item()) == 0
-    env.close()
+    assert overflow == 0
