@@ -20,7 +20,7 @@
  *   b2s_contact_query_run     px.gpu_query_contact_pair_impulses(query)                         envs/scene.py:776-781
  *   b2s_camera_group_create   RenderSystemGroup.create_camera_group(cameras, texture_names)     envs/scene.py:1087-1106
  *   b2s_render                camera_group.take_picture() (+ set_cuda_poses / update_render)    utils/structs/render_camera.py:269-273, envs/scene.py:404-427
- *   b2s_env_step_fused        BaseEnv.step() for the PickCube-v1 family (controller + 5 substeps + evaluate + obs +
+ *   b2s_pick_task_create/step BaseEnv.step() for the PickCube-v1 family (controller + 5 substeps + evaluate + obs +
  *                             reward) as one launch sequence                                   envs/sapien_env.py:1042-1132
  *
  * Memory: all device buffers are owned by the world (cudaMalloc at create); b2s_world_buffers() hands out
