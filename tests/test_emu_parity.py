@@ -30,3 +30,52 @@ def test_emu_other_tasks_match_oracle(task, steps):
     err_q, err_p, overflow = run_task_vs_oracle(task, steps, 3, world_factory=EmuBackendWorld)
     assert err_q < 1e-5 and err_p < 1e-5, (err_q, err_p)
     assert overflow == 0
+
+
+def _edge_scenes():
+    """Degenerate model shapes the pipeline has to take without special cases: no articulation at all (0 dofs), an articulation
+    and nothing to collide with (0 candidate pairs, 0 bodies), bodies that only meet each other (no static geometry)."""
+    from test_oracle_kat import ground, link, root_link
+    from maniskill_b200.model import SHAPE_BOX, SHAPE_SPHERE, ActorRec, ArticulationRec, SceneDesc, ShapeRec, SimParams, pose7
+    n = 3
+    s1 = SceneDesc(n, SimParams())
+    ground(s1)
+    s1.add_actor(ActorRec("box", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([0.05, 0.04, 0.03]))], pose7([0, 0, 0.2], [0.9238795, 0.3826834, 0, 0])))
+    s1.add_actor(ActorRec("ball", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([0.04, 0, 0]))], pose7([0.01, 0.0, 0.5])))
+    robot = dict(name="arm", links=[root_link(), link("l1", 0, "revolute", (0, 0, 1.0), (0, 1, 0), 1.0, com=(0.2, 0, 0)),
+                                    link("l2", 1, "prismatic", (0.4, 0, 0), (1, 0, 0), 0.5, lower=-0.05, upper=0.05)], disabled_collision_pairs=[])
+    s2 = SceneDesc(n, SimParams())
+    s2.add_articulation(ArticulationRec("arm", robot, pose7(), drive={"l1_joint": (50.0, 5.0, 1e10)}))
+    s3 = SceneDesc(n, SimParams(gravity=(0, 0, 0)))
+    for i, x in enumerate((-0.2, 0.2)):
+        s3.add_actor(ActorRec(f"ball{i}", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([0.05, 0, 0]))], pose7([x, 0.01 * i, 0]), angular_damping=0.0))
+    return [("bodies-only", s1, 120), ("articulation-only", s2, 120), ("two-bodies-no-static", s3, 80)]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2], ids=["bodies-only", "articulation-only", "two-bodies-no-static"])
+def test_emu_edge_models_match_oracle(idx):
+    from emu import EmuWorld
+    from oracle.oracle import OracleWorld
+    name, scene, n_sub = _edge_scenes()[idx]
+    cm = scene.compile()
+    o, e = OracleWorld(cm, "f32"), EmuWorld(cm)
+    nl = cm.scalars["n_link"]
+    if idx == 1:
+        tq = np.tile(np.array([[0.4, 0.02]]), (cm.scalars["n_envs"], 1))
+        o.set_joint("target_qpos", tq)
+        e.target_qpos[:] = tq
+        e.apply(32)
+    if idx == 2:  # head-on approach
+        b = o.get_bodies()
+        b[:, 0, 7], b[:, 1, 7] = 1.0, -0.5
+        o.set_bodies(b)
+        e.rigid_body_data[:, nl:] = b
+        e.apply()
+    o.step(n_sub)
+    e.step(n_sub)
+    ref, got = o.rigid_body_data(), e.rigid_body_data.astype(np.float64)
+    assert np.isfinite(got).all()
+    assert np.abs(got[..., :7] - ref[..., :7]).max() < 2e-5, np.abs(got[..., :7] - ref[..., :7]).max()
+    if cm.scalars["n_dof"]:
+        assert np.abs(e.qpos.astype(np.float64) - o.get_joint("qpos")).max() < 2e-5
+    assert e.overflow() == 0

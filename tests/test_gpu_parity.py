@@ -58,3 +58,41 @@ def test_contact_query_matches_oracle(cm):
     assert np.abs(imp - ref_imp).max() < 1e-4 * max(1.0, np.abs(ref_imp).max())
     # the cube rests on the table in most envs: vertical impulse = m g dt
     assert np.median(np.abs(ref_imp[:, 2, 2])) == pytest.approx(0.064 * 9.81 * 0.01, rel=0.05)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2], ids=["bodies-only", "articulation-only", "two-bodies-no-static"])
+def test_edge_models_vs_oracle(idx):
+    """Degenerate model shapes through the C-ABI: 0 dofs, 0 candidate pairs / 0 bodies, bodies without static geometry
+    (the scenes of tests/test_emu_parity.py::test_emu_edge_models_match_oracle)."""
+    import torch
+
+    from maniskill_b200.backend import BUF_ALL, World
+    from oracle.oracle import OracleWorld
+    from test_emu_parity import _edge_scenes
+    name, scene, n_sub = _edge_scenes()[idx]
+    cm = scene.compile()
+    o, w = OracleWorld(cm, "f32"), World(cm)
+    nl = cm.scalars["n_link"]
+    if idx == 1:
+        tq = np.tile(np.array([[0.4, 0.02]]), (cm.scalars["n_envs"], 1))
+        o.set_joint("target_qpos", tq)
+        w.target_qpos[:] = torch.tensor(tq, dtype=torch.float32, device=w.device)
+        w.apply(32)
+    if idx == 2:
+        b = o.get_bodies()
+        b[:, 0, 7], b[:, 1, 7] = 1.0, -0.5
+        o.set_bodies(b)
+        w.body_view()[:, nl:] = torch.tensor(b, dtype=torch.float32, device=w.device)
+        w.apply()
+    o.step(n_sub)
+    for _ in range(n_sub // 5):
+        w.step(5, 0)
+    w.fetch(BUF_ALL)
+    torch.cuda.synchronize()
+    ref, got = o.rigid_body_data(), w.body_view().double().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got[..., :7] - ref[..., :7]).max() < 1e-4, np.abs(got[..., :7] - ref[..., :7]).max()
+    if cm.scalars["n_dof"]:
+        assert np.abs(w.qpos.double().cpu().numpy() - o.get_joint("qpos")).max() < 1e-4
+    assert int(w.overflow_flag.item()) == 0
+    w.close()
