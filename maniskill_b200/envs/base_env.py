@@ -117,6 +117,7 @@ class BaseEnv:
             raise ValueError("sim_freq must be divisible by control_freq")  # sapien_env.py:279-283 warns; we are strict
         self._sim_steps_per_control = self._sim_freq // self._control_freq
         self._world_factory = world_factory
+        self._state_version = 0
         self._requested_device = device
         self._main_seed = None
         self._episode_seed = np.zeros(num_envs, dtype=np.int64)
@@ -253,6 +254,7 @@ class BaseEnv:
             env_idx = torch.arange(0, self.num_envs, device=self.device)
         self._set_main_rng(seed)
         self._set_episode_rng(seed, env_idx)
+        self._state_version += 1  # invalidates per-state caches of derived poses (tasks may memoise them between fetches)
         self.scene._reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.scene._reset_mask[env_idx] = True
         self._elapsed_steps[env_idx] = 0
@@ -294,6 +296,7 @@ class BaseEnv:
             return self._step_fused(action)
         action = self._step_action(action)
         self._elapsed_steps += 1
+        self._state_version += 1
         info = self.get_info()
         obs = self.get_obs(info)
         reward = self.get_reward(obs=obs, action=action, info=info)
@@ -431,6 +434,7 @@ class BaseEnv:
         self.scene.set_sim_state(state, env_idx)
         self.scene._gpu_apply_all()
         self.scene._gpu_fetch_all()
+        self._state_version += 1
 
     def get_state(self):
         return U.flatten_state_dict(self.get_state_dict())

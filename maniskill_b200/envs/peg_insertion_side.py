@@ -123,18 +123,30 @@ class PegInsertionSideEnv(BaseEnv):
         self.agent.robot.set_qpos(torch.tensor(q, dtype=torch.float32, device=dev))
         self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
 
-    # ---- :251-287
+    # ---- :251-287.  The three derived poses are used by evaluate, the observation and the reward of the same step: computed once per
+    # simulation state (the reference recomputes them on every access and notes they could be cached, :262-266).
+    def _memo(self, name, fn):
+        version = getattr(self, "_state_version", None)
+        if version is None:
+            return fn()
+        cache = self.__dict__.setdefault("_pose_cache", {})
+        hit = cache.get(name)
+        if hit is None or hit[0] != version:
+            hit = (version, fn())
+            cache[name] = hit
+        return hit[1]
+
     @property
     def peg_head_pose(self):
-        return self.peg.pose * self.peg_head_offsets
+        return PegInsertionSideEnv._memo(self, "peg_head", lambda: self.peg.pose * self.peg_head_offsets)
 
     @property
     def box_hole_pose(self):
-        return self.box.pose * self.box_hole_offsets
+        return PegInsertionSideEnv._memo(self, "box_hole", lambda: self.box.pose * self.box_hole_offsets)
 
     @property
     def goal_pose(self):
-        return self.box.pose * self.box_hole_offsets * self.peg_head_offsets.inv()
+        return PegInsertionSideEnv._memo(self, "goal", lambda: self.box_hole_pose * self.peg_head_offsets.inv())
 
     def has_peg_inserted(self):
         p = (self.box_hole_pose.inv() * self.peg_head_pose).p
@@ -157,7 +169,9 @@ class PegInsertionSideEnv(BaseEnv):
     # ---- :289-360
     def compute_dense_reward(self, obs, action, info):
         gripper_pos = self.agent.tcp.pose.p
-        tgt = self.peg.pose * Pose.create(pose7([-0.06, 0, 0]), self.device)
+        if getattr(self, "_grasp_offset", None) is None:
+            self._grasp_offset = Pose.create(pose7([-0.06, 0, 0]), self.device)
+        tgt = self.peg.pose * self._grasp_offset
         gripper_to_peg_dist = torch.linalg.norm(gripper_pos - tgt.p, axis=1)
         reaching_reward = 1 - torch.tanh(4.0 * gripper_to_peg_dist)
         is_grasped = self.agent.is_grasping(self.peg, max_angle=20)

@@ -84,11 +84,14 @@ class Pose:
 
     def to_transformation_matrix(self) -> torch.Tensor:
         n = self.raw_pose.shape[0]
-        T = torch.zeros((n, 4, 4), device=self.device)
-        T[:, :3, :3] = U.quat_to_matrix(self.q)
-        T[:, :3, 3] = self.p
-        T[:, 3, 3] = 1
-        return T
+        top = torch.cat([U.quat_to_matrix(self.q), self.p.unsqueeze(-1)], dim=2)  # [n, 3, 4]
+        key = (self.device, top.dtype)
+        if key not in _LAST_ROW:
+            _LAST_ROW[key] = torch.tensor([[[0.0, 0.0, 0.0, 1.0]]], device=self.device, dtype=top.dtype)
+        return torch.cat([top, _LAST_ROW[key].expand(n, 1, 4)], dim=1)
+
+
+_LAST_ROW = {}
 
 
 class _BodyView:
