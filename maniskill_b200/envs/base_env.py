@@ -35,6 +35,7 @@ class Scene:
         self.device = world.device
         self.timestep = cm.scalars["dt"]
         self._reset_mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self._reset_all = True  # python-side knowledge that the mask is all-true: setters then skip the boolean gather (a device sync)
         self._dirty = 0
         self.actors: Dict[str, Actor] = {}
         self.articulations: Dict[str, Articulation] = {}
@@ -257,6 +258,7 @@ class BaseEnv:
         self._state_version += 1  # invalidates per-state caches of derived poses (tasks may memoise them between fetches)
         self.scene._reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.scene._reset_mask[env_idx] = True
+        self.scene._reset_all = False
         self._elapsed_steps[env_idx] = 0
         self._clear_sim_state()
         self.agent.reset()
@@ -270,6 +272,7 @@ class BaseEnv:
             else:
                 self._initialize_episode(env_idx, options)
         self.scene._reset_mask = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        self.scene._reset_all = True
         # sapien_env.py:956-960: apply everything, refresh link poses, fetch
         self.scene._gpu_apply_all()
         self.scene._gpu_fetch_all()

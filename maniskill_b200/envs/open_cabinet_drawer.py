@@ -171,10 +171,10 @@ class OpenCabinetDrawerEnv(BaseEnv):
         reaching_reward = 1 - torch.tanh(5 * tcp_to_handle_dist)
         amount_to_open_left = torch.div(self.target_qpos - self._target_joint_qpos(), self.target_qpos)
         open_reward = 2 * (1 - amount_to_open_left)
-        reaching_reward[amount_to_open_left < 0.999] = 2
-        open_reward[info["open_enough"]] = 3
+        reaching_reward = torch.where(amount_to_open_left < 0.999, 2.0, reaching_reward)  # masked assignment without the nonzero() sync
+        open_reward = torch.where(info["open_enough"], 3.0, open_reward)
         reward = reaching_reward + open_reward
-        reward[info["success"]] = 5.0
+        reward = torch.where(info["success"], 5.0, reward)
         return reward
 
     def compute_normalized_dense_reward(self, obs, action, info):

@@ -187,7 +187,7 @@ class PegInsertionSideEnv(BaseEnv):
         inside = self.box_hole_pose.inv() * self.peg_head_pose
         insertion_reward = 5 * (1 - torch.tanh(5.0 * torch.linalg.norm(inside.p, axis=1)))
         reward = reward + insertion_reward * (is_grasped & pre_inserted)
-        reward[info["success"]] = 10
+        reward = torch.where(info["success"], 10.0, reward)  # masked assignment without the nonzero() sync
         return reward
 
     def compute_normalized_dense_reward(self, obs, action, info):

@@ -140,7 +140,7 @@ class PickCubeEnv(BaseEnv):
         qvel = self.agent.robot.get_qvel()[..., :-2]
         static_reward = 1 - torch.tanh(5 * torch.linalg.norm(qvel, axis=1))
         reward = reward + static_reward * info["is_obj_placed"]
-        reward[info["success"]] = 5
+        reward = torch.where(info["success"], 5.0, reward)  # masked assignment without the nonzero() sync
         return reward
 
     def compute_normalized_dense_reward(self, obs, action, info):

@@ -94,6 +94,11 @@ class Pose:
 _LAST_ROW = {}
 
 
+def _sel(scene, idx):
+    """idx[scene._reset_mask] without the boolean gather (and its device sync) when every sub-scene is selected."""
+    return idx if getattr(scene, "_reset_all", False) else idx[scene._reset_mask]
+
+
 class _BodyView:
     """Rows of rigid_body_data belonging to one named body across all sub-scenes."""
 
@@ -143,21 +148,21 @@ class Actor(_BodyView):
 
     def set_pose(self, pose):
         pose = Pose.create(pose, self.scene.device)
-        mask = self.scene._reset_mask
+        rows = _sel(self.scene, self._idx)
         raw = pose.raw_pose
         if raw.shape[0] == 1:
-            raw = raw.expand(int(mask.sum().item()) if mask.dtype == torch.bool else len(mask), 7)
-        self._data[self._idx[mask], :7] = raw
+            raw = raw.expand(rows.shape[0], 7)
+        self._data[rows, :7] = raw
         self.scene._dirty |= self.scene.BUF_RIGID
 
     def set_linear_velocity(self, v):
         v = U.to_tensor(v, self.scene.device)
-        self._data[self._idx[self.scene._reset_mask], 7:10] = v
+        self._data[_sel(self.scene, self._idx), 7:10] = v
         self.scene._dirty |= self.scene.BUF_RIGID
 
     def set_angular_velocity(self, v):
         v = U.to_tensor(v, self.scene.device)
-        self._data[self._idx[self.scene._reset_mask], 10:13] = v
+        self._data[_sel(self.scene, self._idx), 10:13] = v
         self.scene._dirty |= self.scene.BUF_RIGID
 
     def get_state(self):
@@ -210,7 +215,7 @@ class Articulation:
         return self.qlimits
 
     def _masked_rows(self):
-        return self._rows[self.scene._reset_mask]
+        return _sel(self.scene, self._rows)
 
     def set_qpos(self, q):
         q = U.to_tensor(q, self.scene.device)
@@ -229,12 +234,12 @@ class Articulation:
 
     def set_joint_drive_targets(self, targets, joint_indices):
         """articulation.py:873-896: write px.cuda_articulation_target_qpos[gx[mask], gy[mask]]."""
-        rows = self._rows[self.scene._reset_mask]
+        rows = _sel(self.scene, self._rows)
         self.scene.world.target_qpos[rows[:, None], joint_indices[None, :]] = targets
         self.scene._dirty |= self.scene.BUF_TARGET_QPOS
 
     def set_joint_drive_velocity_targets(self, targets, joint_indices):
-        rows = self._rows[self.scene._reset_mask]
+        rows = _sel(self.scene, self._rows)
         self.scene.world.target_qvel[rows[:, None], joint_indices[None, :]] = targets
         self.scene._dirty |= self.scene.BUF_TARGET_QVEL
 
@@ -244,7 +249,7 @@ class Articulation:
 
     def set_pose(self, pose):
         pose = Pose.create(pose, self.scene.device)
-        rows = self.root._idx[self.scene._reset_mask]
+        rows = _sel(self.scene, self.root._idx)
         self.scene.world.rigid_body_data[rows, :7] = pose.raw_pose
         self.scene._dirty |= self.scene.BUF_ROOT_POSE
 
