@@ -10,6 +10,7 @@ interface through ``world_factory`` (tests/ only).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Sequence, Union
 
 import numpy as np
@@ -155,7 +156,10 @@ class BaseEnv:
         self._sensors = self._setup_sensors() if self._visual else {}
         self._last_obs = None
         self._fused = None
-        if fused and world_factory is None and self._obs_mode == "state":
+        # the fused control step serves the flat-state observation directly; tasks that can rebuild their observation dict from the
+        # fused state vector (`_obs_from_fused`) use it under the visual modes too (B2S_FUSED_VISUAL=0 keeps the torch path there)
+        fused_visual = self._visual and hasattr(self, "_obs_from_fused") and os.environ.get("B2S_FUSED_VISUAL", "0") not in ("", "0")
+        if fused and world_factory is None and (self._obs_mode == "state" or fused_visual):
             self._fused = self._setup_fused_step()
         # sapien_env.py:321-327: main RNG seeds 2022+i, first reset
         self._set_main_rng([2022 + i for i in range(num_envs)])
@@ -330,7 +334,7 @@ class BaseEnv:
         self.scene.world.pick_task_step(f["handle"], action, self._sim_steps_per_control, f["obs"], f["reward"], f["flags"], self._elapsed_steps)
         fl = f["flags"]
         info = dict(elapsed_steps=self._elapsed_steps.clone(), success=fl[:, 0], is_obj_placed=fl[:, 1], is_robot_static=fl[:, 2], is_grasped=fl[:, 3])
-        obs = f["obs"]
+        obs = f["obs"] if self._obs_mode == "state" else self._visual_obs_from_fused(f["obs"], info)
         self._last_obs = obs
         return obs, f["reward"], fl[:, 4].clone(), torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
 
@@ -383,6 +387,15 @@ class BaseEnv:
         obs = dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
         if self._obs_mode.startswith("state+"):
             obs["state"] = U.flatten_state_dict(self._get_obs_state_dict(info))
+        obs["sensor_param"] = self.get_sensor_params()
+        obs["sensor_data"] = self._get_obs_sensor_data()
+        return obs
+
+    def _visual_obs_from_fused(self, vec, info):
+        """Visual-mode observation (same structure as `get_obs`) with the agent / extra entries taken from the fused state vector."""
+        obs = self._obs_from_fused(vec, info)
+        if self._obs_mode.startswith("state+"):
+            obs["state"] = vec
         obs["sensor_param"] = self.get_sensor_params()
         obs["sensor_data"] = self._get_obs_sensor_data()
         return obs

@@ -120,6 +120,16 @@ class PickCubeEnv(BaseEnv):
                        obj_to_goal_pos=self.goal_site.pose.p - self.cube.pose.p)
         return obs
 
+    def _obs_from_fused(self, vec, info):
+        """agent + extra of `get_obs` as views of the fused state vector [qpos | qvel | is_grasped, tcp_pose(7), goal_pos(3), obj_pose(7),
+        tcp_to_obj_pos(3), obj_to_goal_pos(3)] (the order `_get_obs_state_dict` flattens to; pick_epilogue_kernel writes it)."""
+        nd = self.agent.robot.dof
+        o = 2 * nd
+        extra = dict(is_grasped=info["is_grasped"], tcp_pose=vec[:, o + 1:o + 8], goal_pos=vec[:, o + 8:o + 11])
+        if "state" in self.obs_mode:
+            extra.update(obj_pose=vec[:, o + 11:o + 18], tcp_to_obj_pos=vec[:, o + 18:o + 21], obj_to_goal_pos=vec[:, o + 21:o + 24])
+        return dict(agent=dict(qpos=vec[:, :nd], qvel=vec[:, nd:o]), extra=extra)
+
     # ---- pick_cube.py:147-159
     def evaluate(self):
         is_obj_placed = torch.linalg.norm(self.goal_site.pose.p - self.cube.pose.p, axis=1) <= self.goal_thresh

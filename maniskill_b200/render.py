@@ -94,22 +94,34 @@ class CameraSensors:
     def get_params(self, body_view: torch.Tensor):
         """sensor_param[uid] = extrinsic_cv [N,3,4], cam2world_gl [N,4,4], intrinsic_cv [N,3,3]
         (mani_skill/utils/structs/render_camera.py:77-155)."""
-        from . import utils as U
         from .structs import Pose
         dev = body_view.device
         N = body_view.shape[0]
+        cache = self.__dict__.setdefault("_param_cache", {})
         out = {}
         for c in self.cams:
-            local = Pose.create(torch.tensor([c["local_pose"]], dtype=torch.float32, device=dev).expand(N, 7))
-            pose = Pose(body_view[:, c["mount_row"], :7]) * local if c["mount_row"] >= 0 else local
+            uid = c["uid"]
+            if uid not in cache:  # per-camera constants, and the whole entry for cameras that are not mounted on a moving body
+                cache[uid] = dict(
+                    local=Pose.create(torch.tensor([c["local_pose"]], dtype=torch.float32, device=dev).expand(N, 7)),
+                    # OpenGL camera axes (x right, y up, z back) / OpenCV axes (x right, y down, z fwd) in the sapien camera frame
+                    gl=torch.tensor([[0, 0, -1, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev),
+                    cv=torch.tensor([[0, 0, 1, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev),
+                    K=torch.tensor([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1]], dtype=torch.float32, device=dev)[None].expand(N, 3, 3),
+                    static=None)
+            k = cache[uid]
+            if k["static"] is not None:
+                out[uid] = dict(k["static"])
+                continue
+            pose = Pose(body_view[:, c["mount_row"], :7]) * k["local"] if c["mount_row"] >= 0 else k["local"]
             T = pose.to_transformation_matrix()  # sapien camera frame (x fwd, y left, z up) -> world
-            # OpenGL camera axes (x right, y up, z back) expressed in the sapien camera frame
-            gl = torch.tensor([[0, 0, -1, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)
-            cam2world_gl = T @ gl
-            # OpenCV camera axes (x right, y down, z fwd)
-            cv = torch.tensor([[0, 0, 1, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32, device=dev)
-            cam2world_cv = T @ cv
-            extrinsic_cv = torch.linalg.inv(cam2world_cv)[:, :3, :4]
-            K = torch.tensor([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1]], dtype=torch.float32, device=dev)[None].expand(N, 3, 3)
-            out[c["uid"]] = dict(extrinsic_cv=extrinsic_cv, cam2world_gl=cam2world_gl, intrinsic_cv=K)
+            cam2world_gl = T @ k["gl"]
+            cam2world_cv = T @ k["cv"]
+            # inverse of a rigid transform: [R^T | -R^T t]
+            Rt = cam2world_cv[:, :3, :3].transpose(1, 2)
+            extrinsic_cv = torch.cat([Rt, -(Rt @ cam2world_cv[:, :3, 3:4])], dim=2)
+            entry = dict(extrinsic_cv=extrinsic_cv, cam2world_gl=cam2world_gl, intrinsic_cv=k["K"])
+            if c["mount_row"] < 0:
+                k["static"] = entry
+            out[uid] = dict(entry)
         return out

@@ -143,3 +143,28 @@ def test_open_cabinet_drawer_standin():
     assert info["success"].all() and torch.allclose(r, torch.ones(2))
     # the goal marker follows the handle of the chosen drawer (:294-305)
     assert torch.allclose(env.handle_link_goal.pose.p, info["handle_link_pos"], atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["state_dict", "rgbd-like"])
+def test_pick_cube_obs_from_fused_vector_matches_obs_dict(mode):
+    """`_obs_from_fused` (used when the fused control step serves a visual observation mode) rebuilds exactly the agent / extra
+    entries `get_obs` produces, from the flattened state vector."""
+    from maniskill_b200 import utils as U
+    env = ms.make("PickCube-v1", num_envs=5, obs_mode="state_dict", device="cpu", world_factory=EmuBackendWorld)
+    env.reset(seed=2)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        env.step(2 * torch.rand((5, env.action_dim), generator=g) - 1)
+    info = env.get_info()
+    ref = env._get_obs_state_dict(info)
+    vec = U.flatten_state_dict(ref)
+    if mode != "state_dict":
+        env._obs_mode = "rgbd"  # extra drops the privileged entries (pick_cube.py:132-145)
+        ref = dict(agent=env._get_obs_agent(), extra=env._get_obs_extra(info))
+        assert "obj_pose" not in ref["extra"]
+    got = env._obs_from_fused(vec, info)
+    assert set(got.keys()) == set(ref.keys())
+    for grp in ref:
+        assert set(got[grp].keys()) == set(ref[grp].keys()), grp
+        for k in ref[grp]:
+            assert got[grp][k].dtype == ref[grp][k].dtype and torch.equal(got[grp][k], ref[grp][k]), (grp, k)

@@ -91,6 +91,38 @@ def test_fused_step_matches_python_path():
     e2.close()
 
 
+def test_fused_step_serves_visual_obs_modes(monkeypatch):
+    """With B2S_FUSED_VISUAL=1 the fused control step also runs under the visual observation modes: same observation dict (agent,
+    extra, state, sensor data bit for bit) as the torch path."""
+    import maniskill_b200 as ms
+    n = 16
+    monkeypatch.setenv("B2S_FUSED_VISUAL", "1")
+    e1 = ms.make("PickCube-v1", num_envs=n, obs_mode="state+rgb+depth", fused=True)
+    e2 = ms.make("PickCube-v1", num_envs=n, obs_mode="state+rgb+depth", fused=False)
+    assert e1._fused is not None and e2._fused is None
+    e1.reset(seed=5)
+    e2.reset(seed=5)
+    g = torch.Generator(device=e1.device).manual_seed(1)
+    for i in range(12):
+        a = 2 * torch.rand((n, 8), device=e1.device, generator=g) - 1
+        o1, r1, t1, _, i1 = e1.step(a)
+        o2, r2, t2, _, i2 = e2.step(a)
+        assert set(o1.keys()) == set(o2.keys()) == {"agent", "extra", "state", "sensor_param", "sensor_data"}
+        assert torch.allclose(o1["state"], o2["state"], atol=2e-5)
+        for grp in ("agent", "extra"):
+            assert set(o1[grp].keys()) == set(o2[grp].keys())
+            for k in o1[grp]:
+                assert o1[grp][k].dtype == o2[grp][k].dtype and torch.allclose(o1[grp][k].float(), o2[grp][k].float(), atol=2e-5), (grp, k)
+        for k in ("rgb", "depth"):
+            d = (o1["sensor_data"]["base_camera"][k].int() - o2["sensor_data"]["base_camera"][k].int()).abs()
+            assert (d > 1).float().mean() < 1e-3, k  # the two envs' physics agree to ~1e-5: a handful of edge pixels may flip
+        for k in o1["sensor_param"]["base_camera"]:
+            assert torch.allclose(o1["sensor_param"]["base_camera"][k], o2["sensor_param"]["base_camera"][k], atol=1e-5)
+        assert torch.allclose(r1, r2, atol=2e-5) and torch.equal(t1, t2)
+    e1.close()
+    e2.close()
+
+
 @pytest.mark.parametrize("task,steps", [("PegInsertionSide-v1", 8), ("OpenCabinetDrawer-v1", 6)])
 def test_other_tasks_match_oracle(task, steps):
     """Heterogeneous per-env geometry (peg) and the two-articulation / 17-dof configuration (Fetch + cabinet, the large
