@@ -329,7 +329,10 @@ def main():
     ap.add_argument("--no-auto-reset", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rgbd", action="store_true", help="skip the supplementary state+RGBD measurement")
-    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    ap.add_argument("--traffic-bytes", type=float, default=110.1e6,
+                    help="dram bytes read + written by one b2s_step (5 substeps): sum over its six kernels of dram__bytes_read.sum + "
+                         "dram__bytes_write.sum from the committed per-kernel `ncu --set full` captures (cold caches per kernel, i.e. an upper "
+                         "bound for the graph replay where the exchange buffers stay in L2): profiles/r01_pipeline_kernels_ncu_summary.md")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

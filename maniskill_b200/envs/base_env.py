@@ -157,8 +157,8 @@ class BaseEnv:
         self._last_obs = None
         self._fused = None
         # the fused control step serves the flat-state observation directly; tasks that can rebuild their observation dict from the
-        # fused state vector (`_obs_from_fused`) use it under the visual modes too (B2S_FUSED_VISUAL=0 keeps the torch path there)
-        fused_visual = self._visual and hasattr(self, "_obs_from_fused") and os.environ.get("B2S_FUSED_VISUAL", "0") not in ("", "0")
+        # fused state vector (`_obs_from_fused`) use it under the visual modes too (B2S_FUSED_VISUAL=0 keeps the torch path there; tests/test_gpu_env.py compares the two)
+        fused_visual = self._visual and hasattr(self, "_obs_from_fused") and os.environ.get("B2S_FUSED_VISUAL", "1") not in ("", "0")
         if fused and world_factory is None and (self._obs_mode == "state" or fused_visual):
             self._fused = self._setup_fused_step()
         # sapien_env.py:321-327: main RNG seeds 2022+i, first reset

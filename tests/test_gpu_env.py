@@ -92,8 +92,8 @@ def test_fused_step_matches_python_path():
 
 
 def test_fused_step_serves_visual_obs_modes(monkeypatch):
-    """With B2S_FUSED_VISUAL=1 the fused control step also runs under the visual observation modes: same observation dict (agent,
-    extra, state, sensor data bit for bit) as the torch path."""
+    """The fused control step also runs under the visual observation modes (default; B2S_FUSED_VISUAL=0 turns it off): same
+    observation dict (agent, extra, state, sensor data) as the torch path."""
     import maniskill_b200 as ms
     n = 16
     monkeypatch.setenv("B2S_FUSED_VISUAL", "1")
