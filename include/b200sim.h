@@ -18,6 +18,8 @@
  *   b2s_update_kinematics     px.gpu_update_articulation_kinematics()                           envs/scene.py:947, envs/sapien_env.py:958
  *   b2s_contact_query_create  px.gpu_create_contact_pair_impulse_query(body_pairs)              envs/scene.py:761-775
  *   b2s_contact_query_run     px.gpu_query_contact_pair_impulses(query)                         envs/scene.py:776-781
+ *                             (row b = B2S_ANY_BODY: px.gpu_create_contact_body_impulse_query /
+ *                             px.gpu_query_contact_body_impulses, the net impulse on body a)         utils/structs/base.py:116-136, articulation.py:441-462
  *   b2s_camera_group_create   RenderSystemGroup.create_camera_group(cameras, texture_names)     envs/scene.py:1087-1106
  *   b2s_render                camera_group.take_picture() (+ set_cuda_poses / update_render)    utils/structs/render_camera.py:269-273, envs/scene.py:404-427
  *   b2s_pick_task_create/step BaseEnv.step() for the PickCube-v1 family (controller + 5 substeps + evaluate + obs +
@@ -196,7 +198,9 @@ int32_t b2s_fetch(uint64_t world, uint32_t mask, void* stream);
 int32_t b2s_update_kinematics(uint64_t world, void* stream);
 
 /* Sum of last-substep solver contact impulses (sub-scene frame) between exposed body rows a and b, acting on a.
- * rows: [n_query*2] per-env row ids.  out: device [n_envs, n_query, 3]. */
+ * rows: [n_query*2] per-env row ids (-1 = the static geometry; b = B2S_ANY_BODY sums over every body touching a: the net
+ * contact impulse on a).  out: device [n_envs, n_query, 3]. */
+#define B2S_ANY_BODY (-2)
 int32_t b2s_contact_query_create(uint64_t world, const int32_t* rows, int32_t n_query, uint64_t* query);
 int32_t b2s_contact_query_run(uint64_t world, uint64_t query, float* out_dev, void* stream);
 

@@ -133,6 +133,9 @@ class CameraGroup:
         return buf[:, a:b].view(self.world.n_envs, int(c["height"]), int(c["width"]), 4)
 
 
+ANY_BODY = -2  # include/b200sim.h B2S_ANY_BODY: second row of a contact query = every body (net impulse on the first)
+
+
 class World:
     """One batched world on one GPU (the PhysxGpuSystem + all sub-scenes of the reference)."""
 

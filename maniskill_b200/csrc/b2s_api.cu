@@ -176,7 +176,8 @@ __global__ void query_kernel(b2s::DevModel M, b2s::DevState S, const int* rows, 
     for (int m = 0; m < nm; m++) {
       const float* o = S.man + (size_t)(m * 8) * N + env;
       int a = (int)o[0], b = (int)o[N];
-      float sg = (a == ra && b == rb) ? 1.f : ((a == rb && b == ra) ? -1.f : 0.f);
+      const bool any = rb == B2S_ANY_BODY;  // net impulse on ra: every patch that has ra on one side
+      float sg = (a == ra && (any || b == rb)) ? 1.f : ((b == ra && (any || a == rb)) ? -1.f : 0.f);
       sx += sg * o[2 * N]; sy += sg * o[3 * N]; sz += sg * o[4 * N];
     }
     float* w = out + ((size_t)env * nq + q) * 3;

@@ -78,6 +78,16 @@ class Scene:
     def get_pairwise_contact_forces(self, obj1, obj2):
         return self.get_pairwise_contact_impulses(obj1, obj2) / self.timestep
 
+    # ---- mani_skill/utils/structs/base.py:116-136 (px.gpu_create_contact_body_impulse_query / gpu_query_contact_body_impulses)
+    def get_net_contact_impulses(self, obj):
+        key = (obj.row, -2)  # backend.ANY_BODY
+        if key not in self._query_cache:
+            self._query_cache[key] = self.world.create_contact_query([key])
+        return self.world.query_contact_impulses(self._query_cache[key])[:, 0]
+
+    def get_net_contact_forces(self, obj):
+        return self.get_net_contact_impulses(obj) / self.timestep
+
     def get_sim_state(self):
         state = {"actors": {}, "articulations": {}}
         for k, a in self.actors.items():

@@ -127,6 +127,13 @@ class _BodyView:
     def angular_velocity(self):
         return self._data[self._idx, 10:13]
 
+    def get_net_contact_impulses(self):
+        """base.py:116-136: net contact impulse on this body over the last substep (sub-scene frame)."""
+        return self.scene.get_net_contact_impulses(self)
+
+    def get_net_contact_forces(self):
+        return self.scene.get_net_contact_forces(self)
+
     def get_linear_velocity(self):
         return self.linear_velocity
 

@@ -849,8 +849,9 @@ void b2o_pair_impulse(void* h, int rowA, int rowB, double* out) {
   for (int e = 0; e < O->m.n_envs; e++) {
     V3 s;
     for (const ContactOut& c : O->envs[e].contacts) {
-      if (c.rowA == rowA && c.rowB == rowB) s = s + c.impulse;
-      else if (c.rowA == rowB && c.rowB == rowA) s = s - c.impulse;
+      const bool any = rowB == -2;  // B2S_ANY_BODY: net impulse on rowA
+      if (c.rowA == rowA && (any || c.rowB == rowB)) s = s + c.impulse;
+      else if (c.rowB == rowA && (any || c.rowA == rowB)) s = s - c.impulse;
     }
     out[3 * e] = s.x; out[3 * e + 1] = s.y; out[3 * e + 2] = s.z;
   }

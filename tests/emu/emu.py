@@ -82,9 +82,10 @@ class EmuWorld:
             for m in range(self.man_count[e]):
                 ra, rb = int(self.man[m * 8, e]), int(self.man[m * 8 + 1, e])
                 imp = self.man[m * 8 + 2:m * 8 + 5, e]
-                if ra == row_a and rb == row_b:
+                any_body = row_b == -2  # B2S_ANY_BODY
+                if ra == row_a and (any_body or rb == row_b):
                     out[e] += imp
-                elif ra == row_b and rb == row_a:
+                elif rb == row_a and (any_body or ra == row_b):
                     out[e] -= imp
         return out
 

@@ -168,3 +168,19 @@ def test_pick_cube_obs_from_fused_vector_matches_obs_dict(mode):
         assert set(got[grp].keys()) == set(ref[grp].keys()), grp
         for k in ref[grp]:
             assert got[grp][k].dtype == ref[grp][k].dtype and torch.equal(got[grp][k], ref[grp][k]), (grp, k)
+
+
+def test_net_contact_force_on_resting_cube_is_its_weight():
+    """Body-net impulse query (base.py:116-136): a cube at rest on the table feels m g from the table and nothing else; the net
+    query equals the sum of the pairwise queries against everything the cube touches."""
+    env = ms.make("PickCube-v1", num_envs=3, obs_mode="state", device="cpu", world_factory=EmuBackendWorld)
+    env.reset(seed=0)
+    for _ in range(10):
+        env.step(torch.zeros(3, env.action_dim))
+    f = env.cube.get_net_contact_forces()
+    mass = 1000 * 0.04**3  # density x volume of the 4 cm cube (pick_cube.py:77-84)
+    assert f.shape == (3, 3)
+    assert torch.allclose(f[:, 2], torch.full((3,), mass * 9.81), rtol=2e-2)
+    assert f[:, :2].abs().max() < 1e-2
+    table = env.scene.actors["table-workspace"]
+    assert torch.allclose(f, env.scene.get_pairwise_contact_forces(env.cube, table), atol=1e-6)

@@ -47,14 +47,18 @@ def test_contact_query_matches_oracle(cm):
     rows = cm.link_rows["panda"]
     cube = cm.actor_rows["cube"]
     table = cm.actor_rows["table-workspace"]
-    key = w.create_contact_query([(rows["panda_leftfinger"], cube), (rows["panda_rightfinger"], cube), (cube, table)])
+    from maniskill_b200.backend import ANY_BODY
+    key = w.create_contact_query([(rows["panda_leftfinger"], cube), (rows["panda_rightfinger"], cube), (cube, table), (cube, ANY_BODY),
+                                  (rows["panda_link7"], ANY_BODY)])
     import torch
     imp = w.query_contact_impulses(key)
     torch.cuda.synchronize()
     imp = imp.cpu().numpy()
     o = ref["world"]
     ref_imp = np.stack([o.pair_impulse(rows["panda_leftfinger"], cube), o.pair_impulse(rows["panda_rightfinger"], cube),
-                        o.pair_impulse(cube, table)], axis=1)
+                        o.pair_impulse(cube, table), o.pair_impulse(cube, ANY_BODY), o.pair_impulse(rows["panda_link7"], ANY_BODY)], axis=1)
+    # the body-net query (px.gpu_query_contact_body_impulses) is the sum of the pairwise ones over everything the body touches
+    assert np.abs(ref_imp[:, 3] - (ref_imp[:, 2] - ref_imp[:, 0] - ref_imp[:, 1])).max() < 1e-5
     assert np.abs(imp - ref_imp).max() < 1e-4 * max(1.0, np.abs(ref_imp).max())
     # the cube rests on the table in most envs: vertical impulse = m g dt
     assert np.median(np.abs(ref_imp[:, 2, 2])) == pytest.approx(0.064 * 9.81 * 0.01, rel=0.05)
