@@ -26,6 +26,10 @@ struct CPoint {
   float sep;
 };
 
+// Keeps <= 4 of n candidate points: the deepest one, then the points that spread the support polygon most, where a candidate
+// pays for lying above the deepest one: every length is reduced by (B2S_REDUCE4_LAMBDA x height above the deepest point), so the
+// near-contact set is preferred over far speculative points (a many-vertex hull resting on a facet keeps that facet).
+#define B2S_REDUCE4_LAMBDA 20
 B2S_HD int reduce4(int n, const v3* p, const float* d, int* keep) {
   if (n <= 4) {
     for (int i = 0; i < n; i++) keep[i] = i;
@@ -33,30 +37,36 @@ B2S_HD int reduce4(int n, const v3* p, const float* d, int* keep) {
   }
   int i0 = 0;
   for (int i = 1; i < n; i++)
-    if (d[i] < d[i0]) i0 = i;
+    if (d[i] < d[i0] - 1e-6f) i0 = i;  // ties (symmetric features) go to the lower index
+  const float lam2 = (float)(B2S_REDUCE4_LAMBDA * B2S_REDUCE4_LAMBDA);
   int i1 = -1;
-  float best = -1.f;
+  float best = -1e30f;
   for (int i = 0; i < n; i++) {
     if (i == i0) continue;
     v3 e = p[i] - p[i0];
-    float v = dot(e, e);
-    if (v > best) { best = v; i1 = i; }
+    float h = d[i] - d[i0];
+    float v = dot(e, e) - lam2 * h * h;
+    if (v > best + 1e-4f * fabsf(best) + 1e-12f) { best = v; i1 = i; }
   }
   int i2 = -1;
-  best = -1.f;
+  best = -1e30f;
+  const v3 base = p[i1] - p[i0];
+  const float base2 = dot(base, base);
   for (int i = 0; i < n; i++) {
     if (i == i0 || i == i1) continue;
-    v3 c = cross(p[i1] - p[i0], p[i] - p[i0]);
-    float v = dot(c, c);
-    if (v > best) { best = v; i2 = i; }
+    v3 c = cross(base, p[i] - p[i0]);
+    float h = d[i] - d[i0];
+    float v = dot(c, c) - base2 * lam2 * h * h;  // (triangle height)^2 - (lambda h)^2, times base^2
+    if (v > best + 1e-4f * fabsf(best) + 1e-12f) { best = v; i2 = i; }
   }
   int i3 = -1;
-  best = -1.f;
+  best = -1e30f;
   for (int i = 0; i < n; i++) {
     if (i == i0 || i == i1 || i == i2) continue;
     v3 e0 = p[i] - p[i0], e1 = p[i] - p[i1], e2 = p[i] - p[i2];
-    float v = fminf(dot(e0, e0), fminf(dot(e1, e1), dot(e2, e2)));
-    if (v > best) { best = v; i3 = i; }
+    float h = d[i] - d[i0];
+    float v = fminf(dot(e0, e0), fminf(dot(e1, e1), dot(e2, e2))) - lam2 * h * h;
+    if (v > best + 1e-4f * fabsf(best) + 1e-12f) { best = v; i3 = i; }
   }
   keep[0] = i0; keep[1] = i1; keep[2] = i2; keep[3] = i3;
   return 4;
@@ -552,6 +562,52 @@ B2S_HDN inline int collide_convex_generic(const WShape& A, const WShape& B, floa
   return 1;
 }
 
+// Convex mesh (vertex cloud H) against a box Bx: a multi-point patch around the single GJK / EPA contact.  PhysX accumulates up to
+// four points of a pair over frames (persistent manifold); this path is stateless, so the patch is generated at once: every hull
+// vertex within `margin` of the box's supporting plane along the contact normal, whose foot point lies on the box, is a candidate
+// (separation measured along the normal); reduce4 keeps the deepest one and the spread of the near-contact set.  The normal and the
+// first candidate are the GJK / EPA result, so a vertex-less contact (edge against edge) degrades to the single point.
+B2S_HDN inline int hull_box_patch(const WShape& H, const WShape& Bx, v3 n_out, bool hull_is_a, const CPoint& c0, float margin, CPoint* out) {
+  const v3 nbh = hull_is_a ? n_out : -n_out;  // from the box towards the hull
+  const float hb[3] = {Bx.size.x, Bx.size.y, Bx.size.z};
+  float smax = dot(Bx.X.p, nbh);
+  for (int k = 0; k < 3; k++) smax += hb[k] * fabsf(dot(col(Bx.R, k), nbh));
+  v3 cand[65];
+  float dist[65];
+  int m = 0;
+  cand[m] = c0.p; dist[m] = c0.sep; m++;
+  const float tol = 1e-3f;
+  for (int i = 0; i < H.nverts && m < 65; i++) {
+    v3 l = mk3(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2]);
+    v3 vw = H.X.p + mul(H.R, l);
+    float sp = dot(vw, nbh) - smax;
+    if (!(sp < margin)) continue;
+    v3 q = vw - nbh * sp;  // foot point on the supporting plane
+    v3 rel = q - Bx.X.p;
+    bool inside = true;
+    for (int k = 0; k < 3; k++)
+      if (fabsf(dot(col(Bx.R, k), rel)) > hb[k] + tol) inside = false;
+    if (!inside) continue;
+    v3 cp = vw - nbh * (sp * 0.5f);
+    v3 dc = cp - c0.p;
+    if (dot(dc, dc) < 1e-6f) {  // the GJK / EPA point itself (within 1 mm): keep one of the two, the vertex
+      cand[0] = cp; dist[0] = sp;
+      continue;
+    }
+    cand[m] = cp;
+    dist[m] = sp;
+    m++;
+  }
+  int keep[4];
+  int k = reduce4(m, cand, dist, keep);
+  for (int i = 0; i < k; i++) {
+    out[i].p = cand[keep[i]];
+    out[i].n = n_out;
+    out[i].sep = dist[keep[i]];
+  }
+  return k;
+}
+
 B2S_HDN inline int collide_pair(const WShape& a, const WShape& b, float margin, CPoint* out) {
   if (a.type == SH_PLANE && b.type == SH_PLANE) return 0;
   if (b.type == SH_PLANE) return collide_plane_any(a, b, margin, out);
@@ -561,7 +617,16 @@ B2S_HDN inline int collide_pair(const WShape& a, const WShape& b, float margin, 
     return k;
   }
   if (a.type == SH_BOX && b.type == SH_BOX) return collide_box_box(a, b, margin, out);
-  return collide_convex_generic(a, b, margin, out);
+  int k = collide_convex_generic(a, b, margin, out);
+  if (k == 1 && a.type == SH_CONVEX && b.type == SH_BOX) {
+    CPoint c0 = out[0];
+    return hull_box_patch(a, b, c0.n, true, c0, margin, out);
+  }
+  if (k == 1 && a.type == SH_BOX && b.type == SH_CONVEX) {
+    CPoint c0 = out[0];
+    return hull_box_patch(b, a, c0.n, false, c0, margin, out);
+  }
+  return k;
 }
 
 }  // namespace b2s

@@ -119,6 +119,24 @@ def hull_mass(verts, tris, density):
     return density * vol, com, I
 
 
+def cylinder_shape(radius, half_length, pose=None, segments=24, **kw):
+    """`add_cylinder_collision(radius, half_length)` (mani_skill/utils/building/actor_builder.py:104-116; axis = local x): like
+    SAPIEN/PhysX, a cylinder is a cooked convex mesh -- here a `segments`-sided prism handled by the convex paths (plane: vertex
+    tests, box: GJK/EPA + vertex patch); mass properties come from the polyhedron.  Returns a ShapeRec (keyword arguments are
+    passed on: mu, density, groups, color ...)."""
+    from scipy.spatial import ConvexHull
+    ang = 2 * np.pi * (np.arange(segments) + 0.5) / segments
+    ring = np.stack([np.cos(ang), np.sin(ang)], 1) * radius
+    verts = np.concatenate([np.concatenate([np.full((segments, 1), sx * half_length), ring], 1) for sx in (-1.0, 1.0)])
+    hull = ConvexHull(verts)
+    tris = hull.simplices.copy()
+    # outward winding (hull_mass sums signed tetrahedra): flip the facets whose vertex order disagrees with the facet normal
+    n = np.cross(verts[tris[:, 1]] - verts[tris[:, 0]], verts[tris[:, 2]] - verts[tris[:, 0]])
+    flip = np.einsum("ij,ij->i", n, hull.equations[:, :3]) < 0
+    tris[flip] = tris[flip][:, [0, 2, 1]]
+    return ShapeRec(SHAPE_CONVEX, pose7() if pose is None else pose, np.zeros(3), vertices=verts, triangles=tris, **kw)
+
+
 def rotate_inertia(I, R):
     return R @ I @ R.T
 

@@ -33,6 +33,10 @@ struct WShape {  // shape placed in the sub-scene frame
 
 // ---------------------------------------------------------------- manifold reduction
 // keep <=4 of n candidate points: deepest, farthest from it, largest triangle, farthest from that triangle.
+// Keeps <= 4 of n candidate points: the deepest one, then the points that spread the support polygon most, where a candidate
+// pays for lying above the deepest one: every length is reduced by (REDUCE4_LAMBDA x height above the deepest point), so the
+// near-contact set is preferred over far speculative points (a many-vertex hull resting on a facet keeps that facet).
+#define REDUCE4_LAMBDA 20
 static inline int reduce4(int n, const V3* p, const R* d, int* keep) {
   if (n <= 4) {
     for (int i = 0; i < n; i++) keep[i] = i;
@@ -40,30 +44,36 @@ static inline int reduce4(int n, const V3* p, const R* d, int* keep) {
   }
   int i0 = 0;
   for (int i = 1; i < n; i++)
-    if (d[i] < d[i0]) i0 = i;
+    if (d[i] < d[i0] - R(1e-6)) i0 = i;  // ties (symmetric features) go to the lower index
+  const R lam2 = (R)(REDUCE4_LAMBDA * REDUCE4_LAMBDA);
   int i1 = -1;
-  R best = -1;
+  R best = (R)-1e30;
   for (int i = 0; i < n; i++) {
     if (i == i0) continue;
     V3 e = p[i] - p[i0];
-    R v = dot(e, e);
-    if (v > best) { best = v; i1 = i; }
+    R h = d[i] - d[i0];
+    R v = dot(e, e) - lam2 * h * h;
+    if (v > best + R(1e-4) * std::fabs(best) + R(1e-12)) { best = v; i1 = i; }
   }
   int i2 = -1;
-  best = -1;
+  best = (R)-1e30;
+  const V3 base = p[i1] - p[i0];
+  const R base2 = dot(base, base);
   for (int i = 0; i < n; i++) {
     if (i == i0 || i == i1) continue;
-    V3 c = cross(p[i1] - p[i0], p[i] - p[i0]);
-    R v = dot(c, c);
-    if (v > best) { best = v; i2 = i; }
+    V3 c = cross(base, p[i] - p[i0]);
+    R h = d[i] - d[i0];
+    R v = dot(c, c) - base2 * lam2 * h * h;  // (triangle height)^2 - (lambda h)^2, times base^2
+    if (v > best + R(1e-4) * std::fabs(best) + R(1e-12)) { best = v; i2 = i; }
   }
   int i3 = -1;
-  best = -1;
+  best = (R)-1e30;
   for (int i = 0; i < n; i++) {
     if (i == i0 || i == i1 || i == i2) continue;
     V3 e0 = p[i] - p[i0], e1 = p[i] - p[i1], e2 = p[i] - p[i2];
-    R v = std::fmin(dot(e0, e0), std::fmin(dot(e1, e1), dot(e2, e2)));
-    if (v > best) { best = v; i3 = i; }
+    R h = d[i] - d[i0];
+    R v = std::fmin(dot(e0, e0), std::fmin(dot(e1, e1), dot(e2, e2))) - lam2 * h * h;
+    if (v > best + R(1e-4) * std::fabs(best) + R(1e-12)) { best = v; i3 = i; }
   }
   keep[0] = i0; keep[1] = i1; keep[2] = i2; keep[3] = i3;
   return 4;
@@ -591,6 +601,52 @@ static inline int collide_convex_generic(const WShape& A, const WShape& B, R mar
   return 1;
 }
 
+// Convex mesh (vertex cloud H) against a box Bx: a multi-point patch around the single GJK / EPA contact.  PhysX accumulates up to
+// four points of a pair over frames (persistent manifold); this path is stateless, so the patch is generated at once: every hull
+// vertex within `margin` of the box's supporting plane along the contact normal, whose foot point lies on the box, is a candidate
+// (separation measured along the normal); reduce4 keeps the deepest one and the spread of the near-contact set.  The normal and the
+// first candidate are the GJK / EPA result, so a vertex-less contact (edge against edge) degrades to the single point.
+static inline int hull_box_patch(const WShape& H, const WShape& Bx, V3 n_out, bool hull_is_a, const Contact& c0, R margin, Contact* out) {
+  const V3 nbh = hull_is_a ? n_out : -n_out;  // from the box towards the hull
+  const R hb[3] = {Bx.size.x, Bx.size.y, Bx.size.z};
+  R smax = dot(Bx.X.p, nbh);
+  for (int k = 0; k < 3; k++) smax += hb[k] * std::fabs(dot(Bx.Rm.col(k), nbh));
+  V3 cand[65];
+  R dist[65];
+  int m = 0;
+  cand[m] = c0.p; dist[m] = c0.sep; m++;
+  const R tol = R(1e-3);
+  for (int i = 0; i < H.nverts && m < 65; i++) {
+    V3 l(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2]);
+    V3 vw = H.X.p + H.Rm * l;
+    R sp = dot(vw, nbh) - smax;
+    if (!(sp < margin)) continue;
+    V3 q = vw - nbh * sp;  // foot point on the supporting plane
+    V3 rel = q - Bx.X.p;
+    bool inside = true;
+    for (int k = 0; k < 3; k++)
+      if (std::fabs(dot(Bx.Rm.col(k), rel)) > hb[k] + tol) inside = false;
+    if (!inside) continue;
+    V3 cp = vw - nbh * (sp * R(0.5));
+    V3 dc = cp - c0.p;
+    if (dot(dc, dc) < R(1e-6)) {  // the GJK / EPA point itself (within 1 mm): keep one of the two, the vertex
+      cand[0] = cp; dist[0] = sp;
+      continue;
+    }
+    cand[m] = cp;
+    dist[m] = sp;
+    m++;
+  }
+  int keep[4];
+  int k = reduce4(m, cand, dist, keep);
+  for (int i = 0; i < k; i++) {
+    out[i].p = cand[keep[i]];
+    out[i].n = n_out;
+    out[i].sep = dist[keep[i]];
+  }
+  return k;
+}
+
 // dispatch; out normals point from shape b towards shape a
 static inline int collide_pair(const WShape& a, const WShape& b, R margin, Contact* out) {
   if (a.type == SHAPE_PLANE && b.type == SHAPE_PLANE) return 0;
@@ -601,5 +657,14 @@ static inline int collide_pair(const WShape& a, const WShape& b, R margin, Conta
     return k;
   }
   if (a.type == SHAPE_BOX && b.type == SHAPE_BOX) return collide_box_box(a, b, margin, out);
-  return collide_convex_generic(a, b, margin, out);
+  int k = collide_convex_generic(a, b, margin, out);
+  if (k == 1 && a.type == SHAPE_CONVEX && b.type == SHAPE_BOX) {
+    Contact c0 = out[0];
+    return hull_box_patch(a, b, c0.n, true, c0, margin, out);
+  }
+  if (k == 1 && a.type == SHAPE_BOX && b.type == SHAPE_CONVEX) {
+    Contact c0 = out[0];
+    return hull_box_patch(b, a, c0.n, false, c0, margin, out);
+  }
+  return k;
 }

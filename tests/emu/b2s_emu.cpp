@@ -94,3 +94,20 @@ int* emu_man_count(void* h) { return ((World*)h)->S.man_count; }
 int emu_overflow(void* h) { return *((World*)h)->S.overflow; }
 }
 extern "C" int* emu_nrow(void* h) { return ((World*)h)->S.sol_nrow; }
+// stand-alone narrowphase probe (device collide_pair compiled for the host), same arguments as the oracle's b2o_collide
+extern "C" int emu_collide(int ta, const double* pa, const double* sa, const float* va, int nva, int tb, const double* pb, const double* sb,
+                           const float* vb, int nvb, double margin, double* out) {
+  using namespace b2s;
+  WShape A, B;
+  A.type = ta; A.X.p = mk3((float)pa[0], (float)pa[1], (float)pa[2]); A.X.q = qnormalized(mkq((float)pa[3], (float)pa[4], (float)pa[5], (float)pa[6]));
+  A.R = qmat(A.X.q); A.size = mk3((float)sa[0], (float)sa[1], (float)sa[2]); A.verts = va; A.nverts = nva;
+  B.type = tb; B.X.p = mk3((float)pb[0], (float)pb[1], (float)pb[2]); B.X.q = qnormalized(mkq((float)pb[3], (float)pb[4], (float)pb[5], (float)pb[6]));
+  B.R = qmat(B.X.q); B.size = mk3((float)sb[0], (float)sb[1], (float)sb[2]); B.verts = vb; B.nverts = nvb;
+  CPoint c[4];
+  int n = collide_pair(A, B, (float)margin, c);
+  for (int i = 0; i < n; i++) {
+    out[7 * i] = c[i].p.x; out[7 * i + 1] = c[i].p.y; out[7 * i + 2] = c[i].p.z;
+    out[7 * i + 3] = c[i].n.x; out[7 * i + 4] = c[i].n.y; out[7 * i + 5] = c[i].n.z; out[7 * i + 6] = c[i].sep;
+  }
+  return n;
+}

@@ -154,3 +154,31 @@ def test_narrowphase_known_answers():
     hull = dict(type=4, pose=[0, 0, 0.095, 1, 0, 0, 0], size=[0, 0, 0], verts=octa)
     c = collide(hull, b1)
     assert len(c) == 1 and c[0, 6] == pytest.approx(-0.005, abs=1e-5) and np.allclose(c[0, 3:6], [0, 0, 1], atol=1e-4)
+
+
+@pytest.mark.parametrize("support,tilt", [("plane", False), ("box", False), ("box", True)])
+def test_cooked_cylinder_rests_on_a_facet_and_weighs_mg(support, tilt):
+    """add_cylinder_collision (actor_builder.py:104-116) = a cooked convex prism, axis local x.  A 48-vertex hull resting on the
+    ground plane (vertex tests) or on a box (GJK/EPA + the hull-vertex patch) must stay put for hundreds of steps and load its
+    support with exactly m g dt: the regression for the near-contact manifold selection (reduce4) and hull_box_patch."""
+    from maniskill_b200.model import cylinder_shape
+    r, hl = 0.03, 0.05
+    shape = cylinder_shape(r, hl, density=1000.0)
+    m, c, I = shape.mass_props()
+    assert len(shape.vertices) == 48 and np.abs(c).max() < 1e-9
+    assert m == pytest.approx(1000.0 * np.pi * r * r * 2 * hl, rel=0.02)
+    assert I[0, 0] == pytest.approx(0.5 * m * r * r, rel=0.03) and I[1, 1] == pytest.approx(m * (r * r / 4 + (2 * hl) ** 2 / 12), rel=0.03)
+    s = SceneDesc(1, SimParams())
+    if support == "plane":
+        ground(s)
+    else:
+        s.add_actor(ActorRec("slab", "static", [ShapeRec(SHAPE_BOX, pose7(), np.array([1.0, 1.0, 0.1]))], pose7([0, 0, -0.1])))
+    q = [0.9659258, 0, 0.2588190, 0] if tilt else [1, 0, 0, 0]  # 30 degrees about y: lands on the rim of an end cap first
+    s.add_actor(ActorRec("cyl", "dynamic", [shape], pose7([0, 0, r + 0.04], q)))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    w.step(600)
+    b = w.get_bodies()[0, 0]
+    assert abs(b[2] - r * np.cos(np.pi / 24)) < 1e-3, b[:3]        # lies on a facet of the prism
+    assert np.abs(b[7:10]).max() < 5e-3 and np.abs(b[10:13]).max() < 5e-2
+    assert w.pair_impulse(cm.actor_rows["cyl"], -1)[0, 2] == pytest.approx(m * G * DT, rel=1e-2)
