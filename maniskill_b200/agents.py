@@ -106,6 +106,93 @@ class PDJointPosMimicController(PDJointPosController):
         self.set_drive_targets(self._target_qpos)
 
 
+class PDEEPosController(PDJointPosController):
+    """pd_ee_pose.py:25-146, GPU-simulation semantics: frame "root_translation", delta actions.  Without a virtual target the
+    (clipped and scaled) action IS the end-effector displacement in the root frame and goes straight into one damped least-squares
+    IK step; with `use_target` the displacement is applied to the previous target pose and the IK step closes the gap between
+    that target and the current end-effector pose (pd_ee_pose.py:101-133, utils/kinematics.py:197-260)."""
+    pos_only = True
+
+    def __init__(self, articulation: Articulation, joint_names: List[str], pos_lower, pos_upper, robot: dict, ee_link: str,
+                 rot_lower=None, rot_upper=None, use_delta=True, use_target=False, normalize_action=True,
+                 solver_config: Optional[dict] = None):
+        from .kinematics import Kinematics
+        if not use_delta:
+            raise NotImplementedError("absolute end-effector targets (pd_ee_pose) are not available in this build")
+        super().__init__(articulation, joint_names, None, None, use_delta=use_delta, use_target=use_target, normalize_action=normalize_action)
+        self.kinematics = Kinematics(robot, ee_link, articulation.dof_names, joint_names, self.device)
+        self.ee_link = articulation.links_map[ee_link]
+        self.root_link = articulation.root
+        self.solver_config = dict(type="levenberg_marquardt", alpha=1.0) if solver_config is None else solver_config
+        low = np.broadcast_to(np.float32(pos_lower), 3)
+        high = np.broadcast_to(np.float32(pos_upper), 3)
+        self.rot_lower = rot_lower
+        if not self.pos_only:
+            low = np.hstack([low, np.broadcast_to(np.float32(rot_lower), 3)])
+            high = np.hstack([high, np.broadcast_to(np.float32(rot_upper), 3)])
+        self._set_bounds(np.stack([low, high], 1))
+        self._target_pose = None
+
+    @property
+    def ee_pose_at_base(self) -> Pose:
+        return self.root_link.pose.inv() * self.ee_link.pose
+
+    def reset(self, env_idx=None):
+        super().reset(env_idx)
+        if self.use_target:
+            cur = self.ee_pose_at_base.raw_pose
+            if self._target_pose is None or env_idx is None:
+                self._target_pose = Pose(cur.clone())
+            else:
+                self._target_pose.raw_pose[env_idx] = cur[env_idx]
+
+    def compute_target_pose(self, prev: Pose, action) -> Pose:
+        """pd_ee_pose.py:85-99 with frame root_translation: keep the rotation, translate in the root frame."""
+        return Pose(torch.hstack([prev.p + action[:, :3], prev.q]))
+
+    def _delta_from_target(self, target: Pose, current: Pose):
+        """utils/kinematics.py:218-241: translation difference and XYZ Euler angles of target.q * current.q^-1."""
+        dq = U.quat_mul(target.q, U.quat_conj(current.q))
+        dq = torch.where(dq[..., :1] < 0, -dq, dq)
+        return torch.hstack([target.p - current.p, U.matrix_to_euler_xyz(U.quat_to_matrix(dq))])
+
+    def set_action(self, action):
+        action = self._preprocess_action(action)
+        self._start_qpos = self.qpos
+        if self.use_target:
+            self._target_pose = self.compute_target_pose(self._target_pose, action)
+            delta = self._delta_from_target(self._target_pose, self.ee_pose_at_base)
+        else:
+            delta = torch.hstack([action, torch.zeros((action.shape[0], 3), device=self.device)]) if self.pos_only else action
+        self._target_qpos = self.kinematics.compute_ik(delta, self.articulation.get_qpos(), self.solver_config)
+        self.set_drive_targets(self._target_qpos)
+
+    def get_state(self):
+        return {"target_pose": self._target_pose.raw_pose} if self.use_target else {}
+
+
+class PDEEPoseController(PDEEPosController):
+    """pd_ee_pose.py:203-263, frame "root_translation:root_aligned_body_rotation": the last three action entries are a rotation
+    vector-like increment (clipped by norm, scaled by `rot_lower` exactly as pd_ee_pose.py:229-239 does), applied as XYZ Euler
+    angles in the root frame."""
+    pos_only = False
+
+    def _preprocess_action(self, action):
+        if not self.normalize_action:
+            return action
+        pos = U.clip_and_scale_action(action[:, :3], self.action_low[:3], self.action_high[:3])
+        rot = action[:, 3:]
+        norm = torch.linalg.norm(rot, dim=1, keepdim=True)
+        rot = torch.where(norm > 1, rot / norm.clamp(min=1e-12), rot) * float(np.broadcast_to(self.rot_lower, 3)[0])
+        return torch.hstack([pos, rot])
+
+    def compute_target_pose(self, prev: Pose, action) -> Pose:
+        dq = U.matrix_to_quat(U.euler_xyz_to_matrix(action[:, 3:6]))
+        q = U.quat_mul(dq, prev.q)
+        q = torch.where(q[..., :1] < 0, -q, q)
+        return Pose(torch.hstack([prev.p + action[:, :3], q]))
+
+
 class CombinedController:
     """base_controller.py:305-347 `DictController` with balanced action concatenation."""
 
@@ -142,7 +229,9 @@ class Panda:
     arm_joint_names = [f"panda_joint{i}" for i in range(1, 8)]
     gripper_joint_names = ["panda_finger_joint1", "panda_finger_joint2"]
     ee_link_name = "panda_hand_tcp"
-    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_joint_target_delta_pos")
+    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_joint_target_delta_pos", "pd_ee_delta_pos", "pd_ee_delta_pose",
+                               "pd_ee_target_delta_pos", "pd_ee_target_delta_pose")
+    robot_asset = "panda_v2"
 
     def __init__(self, scene, name="panda"):
         self.scene = scene
@@ -164,7 +253,12 @@ class Panda:
         self.control_mode = control_mode
         gripper = PDJointPosMimicController(self.robot, self.gripper_joint_names, -0.01, 0.04,
                                             mimic={"panda_finger_joint2": {"joint": "panda_finger_joint1"}})
-        if control_mode == "pd_joint_delta_pos":
+        if control_mode.startswith("pd_ee_"):  # panda.py:103-141: pos +-0.1, rot +-0.1, ee link panda_hand_tcp
+            from .model import load_robot
+            cls = PDEEPoseController if control_mode.endswith("pose") else PDEEPosController
+            arm = cls(self.robot, self.arm_joint_names, -0.1, 0.1, load_robot(self.robot_asset), self.ee_link_name, rot_lower=-0.1, rot_upper=0.1,
+                      use_target="target" in control_mode)
+        elif control_mode == "pd_joint_delta_pos":
             arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
         elif control_mode == "pd_joint_target_delta_pos":
             arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True, use_target=True)

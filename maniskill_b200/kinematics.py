@@ -1,0 +1,118 @@
+"""Batched forward kinematics, geometric Jacobian and the one-step damped least-squares IK of the end-effector controllers.
+
+Host-side mirror of mani_skill/agents/controllers/utils/kinematics.py (`Kinematics`, GPU branch :197-275): the reference builds a
+`pytorch_kinematics` serial chain from the URDF, takes `chain.jacobian(q)` (6 x n: linear rows first, then angular, expressed in
+the root frame) and solves  (J^T J + 1e-4 I) dq = J^T delta_pose  (Levenberg-Marquardt, one iteration) or `pinv(J) delta_pose`.
+Here the chain comes from the baked robot description (tools/bake_assets.py) and everything is plain batched torch.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import utils as U
+
+
+class SerialChain:
+    """Root link -> `end_link` of a baked robot (maniskill_b200/assets/robots/*.json): fixed and 1-dof joints, wxyz quaternions."""
+
+    def __init__(self, robot: dict, end_link: str, device, dtype=torch.float32):
+        names = [l["name"] for l in robot["links"]]
+        if end_link not in names:
+            raise KeyError(end_link)
+        chain = []
+        i = names.index(end_link)
+        while i >= 0:
+            chain.append(i)
+            i = robot["links"][i]["parent"]
+        chain.reverse()
+        self.link_names = [names[i] for i in chain]
+        self.joint_names: List[str] = []   # the moving joints along the chain, root first
+        self._origin_p, self._origin_q, self._axis, self._kind = [], [], [], []
+        for i in chain[1:]:  # the root link has no joint
+            j = robot["links"][i]["joint"]
+            self._origin_p.append(j["p"])
+            self._origin_q.append(j["q"])
+            self._axis.append(j["axis"])
+            kind = {"fixed": 0, "revolute": 1, "continuous": 1, "prismatic": 2}[j["type"]]
+            self._kind.append(kind)
+            if kind:
+                self.joint_names.append(j["name"])
+        t = lambda a: torch.tensor(a, dtype=dtype, device=device)
+        self.origin_p, self.origin_q, self.axis = t(self._origin_p), t(self._origin_q), t(self._axis)
+        self.n_joints = len(self.joint_names)
+        self.device, self.dtype = device, dtype
+
+    def forward(self, q: torch.Tensor):
+        """q [B, n_joints] -> end-link position [B,3], quaternion [B,4] and the Jacobian [B, 6, n_joints] in the root frame
+        (rows 0-2: linear velocity of the end-link origin, rows 3-5: angular velocity), pytorch_kinematics convention."""
+        B = q.shape[0]
+        p = torch.zeros((B, 3), dtype=self.dtype, device=self.device)
+        r = torch.zeros((B, 4), dtype=self.dtype, device=self.device)
+        r[:, 0] = 1.0
+        joint_p, joint_axis, joint_kind = [], [], []
+        k = 0
+        for i, kind in enumerate(self._kind):
+            # joint frame = parent link frame * origin
+            p = p + U.quat_apply(r, self.origin_p[i].expand(B, 3))
+            r = U.quat_mul(r, self.origin_q[i].expand(B, 4))
+            if kind == 0:
+                continue
+            axis_w = U.quat_apply(r, self.axis[i].expand(B, 3))
+            joint_p.append(p)
+            joint_axis.append(axis_w)
+            joint_kind.append(kind)
+            if kind == 1:
+                half = 0.5 * q[:, k:k + 1]
+                dq = torch.cat([torch.cos(half), torch.sin(half) * self.axis[i]], dim=1)
+                r = U.quat_mul(r, dq)
+            else:
+                p = p + axis_w * q[:, k:k + 1]
+            k += 1
+        cols = []
+        for jp, ja, kind in zip(joint_p, joint_axis, joint_kind):
+            if kind == 1:
+                cols.append(torch.cat([torch.linalg.cross(ja, p - jp, dim=-1), ja], dim=1))
+            else:
+                cols.append(torch.cat([ja, torch.zeros_like(ja)], dim=1))
+        J = torch.stack(cols, dim=2) if cols else torch.zeros((B, 6, 0), dtype=self.dtype, device=self.device)
+        return p, r, J
+
+
+class Kinematics:
+    """kinematics.py:25-275 restricted to the GPU branch: IK of `end_link` over the controlled joints `joint_names` (the other
+    moving joints of the chain are held, kinematics.py:170-187 `qmask`)."""
+
+    def __init__(self, robot: dict, end_link: str, dof_names: Sequence[str], joint_names: Sequence[str], device):
+        self.chain = SerialChain(robot, end_link, device)
+        dof_names = list(dof_names)
+        # chain joints as indices into the articulation's qpos; which of them are controlled
+        self.chain_dof_idx = torch.tensor([dof_names.index(n) for n in self.chain.joint_names], dtype=torch.int64, device=device)
+        ctrl = [n for n in self.chain.joint_names if n in set(joint_names)]
+        if ctrl != list(joint_names):
+            raise ValueError(f"controlled joints {list(joint_names)} must be the chain joints {self.chain.joint_names} in chain order")
+        self.qmask = torch.tensor([n in set(joint_names) for n in self.chain.joint_names], dtype=torch.bool, device=device)
+        self.device = device
+
+    def fk(self, qpos: torch.Tensor):
+        p, r, _ = self.chain.forward(qpos[:, self.chain_dof_idx])
+        return p, r
+
+    def compute_ik(self, delta_pose: torch.Tensor, q0: torch.Tensor, solver_config: dict):
+        """delta_pose [B,6] = (translation, XYZ Euler rotation) of the end link in the root frame; q0 [B, dof] full qpos.
+        Returns the target positions of the controlled joints [B, n_ctrl] (kinematics.py:243-260)."""
+        qc = q0[:, self.chain_dof_idx]
+        _, _, J = self.chain.forward(qc)
+        J = J[:, :, self.qmask]
+        if solver_config.get("type", "levenberg_marquardt") == "levenberg_marquardt":
+            lambd = 0.0001  # regularisation so that J^T J is non-singular (kinematics.py:245)
+            JT = J.transpose(1, 2)
+            A = torch.bmm(JT, J) + lambd * torch.eye(J.shape[2], device=self.device, dtype=J.dtype)
+            rhs = torch.bmm(JT, delta_pose.unsqueeze(-1))
+            dq = torch.linalg.solve(A, rhs)
+        elif solver_config["type"] == "pseudo_inverse":
+            dq = torch.linalg.pinv(J) @ delta_pose.unsqueeze(-1)
+        else:
+            raise NotImplementedError(solver_config["type"])
+        return qc[:, self.qmask] + solver_config.get("alpha", 1.0) * dq.squeeze(-1)

@@ -8,7 +8,7 @@ third-party packages; only pure torch/numpy code paths of the reference execute.
 
 Covered reference functions (file:line):
   mani_skill/utils/geometry/rotation_conversions.py  quaternion_raw_multiply, quaternion_apply, quaternion_to_matrix,
-                                                     matrix_to_quaternion, euler_angles_to_matrix
+                                                     matrix_to_quaternion, euler_angles_to_matrix, matrix_to_euler_angles
   mani_skill/envs/utils/randomization/pose.py:13-34  random_quaternions
   mani_skill/utils/gym_utils.py:104-108              clip_and_scale_action
   mani_skill/utils/common.py:195-262, 300-304        flatten_state_dict, compute_angle_between
@@ -277,6 +277,13 @@ def main():
     G["pg_lforce"], G["pg_rforce"], G["pg_f1"], G["pg_f2"] = lf, rf, f1.raw_pose, f2.raw_pose
     G["pg_is_grasping"] = panda.Panda.is_grasping(fake_agent, None)
     G["pg_is_static"] = panda.Panda.is_static(fake_agent, 0.2)
+    # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
+    g2 = torch.Generator().manual_seed(99)
+    qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)
+    qe[:8, 1:] *= 0.05  # small rotations, the regime the controllers use
+    qe = torch.nn.functional.normalize(qe, dim=-1)
+    G["eul_q"] = qe
+    G["eul_xyz_from_matrix"] = rc.matrix_to_euler_angles(rc.quaternion_to_matrix(qe), "XYZ")
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

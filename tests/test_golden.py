@@ -50,6 +50,13 @@ def test_flatten_and_angle():
     close(U.compute_angle_between(T("ang_x1"), T("ang_x2")), G["ang_out"])
 
 
+def test_matrix_to_euler_xyz():
+    close(U.matrix_to_euler_xyz(U.quat_to_matrix(T("eul_q"))), G["eul_xyz_from_matrix"], 2e-6)
+    # round trip with the inverse conversion
+    e = T("eul_xyz_from_matrix")
+    close(U.quat_to_matrix(T("eul_q")), U.euler_xyz_to_matrix(e), 2e-6)
+
+
 def test_look_at():
     for name, eye, tgt in [("pick_sensor", [0.3, 0, 0.6], [-0.1, 0, 0.1]), ("pick_human", [0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), ("peg_sensor", [0, -0.3, 0.2], [0, 0, 0.1])]:
         close(U.look_at(eye, tgt), G["lookat_" + name], 1e-6)
