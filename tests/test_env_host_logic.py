@@ -96,7 +96,7 @@ def test_unsupported_modes_raise():
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, obs_mode="pointcloud", world_factory=EmuBackendWorld)
     with pytest.raises(NotImplementedError):
-        ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_delta_pose", world_factory=EmuBackendWorld)
+        ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_pose", world_factory=EmuBackendWorld)  # absolute EE targets: not built
 
 
 def test_peg_insertion_side_heterogeneous_envs():
