@@ -131,3 +131,27 @@ def test_other_tasks_match_oracle(task, steps):
     err_q, err_p, overflow = run_task_vs_oracle(task, steps, 16)
     assert err_q < 1e-4 and err_p < 1e-4, (err_q, err_p)
     assert overflow == 0
+
+
+def test_ee_target_controller_on_gpu():
+    """pd_ee_target_delta_pose through the torch path on the device (batched FK / Jacobian / damped least squares on CUDA): the tcp
+    reaches the accumulated target (CPU twin: tests/test_ee_controller.py)."""
+    import maniskill_b200 as ms
+    n = 32
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="state", control_mode="pd_ee_target_delta_pose")
+    assert env._fused is None and env.action_dim == 7
+    env.reset(seed=11)
+    p0 = env.agent.tcp.pose.p.clone()
+    a = torch.zeros((n, 7), device=env.device)
+    a[:, 0], a[:, 2], a[:, -1] = 0.5, -0.4, 1.0
+    for _ in range(3):
+        env.step(a)
+    hold = torch.zeros((n, 7), device=env.device)
+    hold[:, -1] = 1.0
+    for _ in range(12):
+        obs, rew, term, trunc, info = env.step(hold)
+    moved = env.agent.tcp.pose.p - p0
+    want = torch.tensor([0.15, 0.0, -0.12], device=env.device)
+    assert (moved - want).abs().max() < 0.01, moved
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    env.close()
