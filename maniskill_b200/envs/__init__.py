@@ -9,3 +9,6 @@ register_env("PegInsertionSide-v1", max_episode_steps=100)(PegInsertionSideEnv)
 from .open_cabinet_drawer import OpenCabinetDrawerEnv
 
 register_env("OpenCabinetDrawer-v1", max_episode_steps=100)(OpenCabinetDrawerEnv)
+from .push_cube import PushCubeEnv
+
+register_env("PushCube-v1", max_episode_steps=50)(PushCubeEnv)

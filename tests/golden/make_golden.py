@@ -18,6 +18,7 @@ Covered reference functions (file:line):
   mani_skill/agents/robots/panda/panda.py:237-269    is_grasping, is_static
   mani_skill/envs/tasks/tabletop/peg_insertion_side.py:250-360  peg_head_pose / box_hole_pose / goal_pose, has_peg_inserted,
                                                      evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358  handle_link_positions, evaluate, _get_obs_extra,
                                                      compute_dense_reward
 """
@@ -277,6 +278,29 @@ def main():
     G["pg_lforce"], G["pg_rforce"], G["pg_f1"], G["pg_f2"] = lf, rf, f1.raw_pose, f2.raw_pose
     G["pg_is_grasping"] = panda.Panda.is_grasping(fake_agent, None)
     G["pg_is_static"] = panda.Panda.is_static(fake_agent, 0.2)
+    # ---- PushCube task logic on synthetic states (appended after the older sections so that their random draws do not move)
+    g3 = torch.Generator().manual_seed(4242)
+    sys.modules["sapien"].Pose = FakeSapienPose  # isinstance checks in Pose.create need a class again
+    sys.modules["transforms3d.euler"].euler2quat = lambda *a, **k: np.array([1.0, 0, 0, 0])
+    push_mod = load("mani_skill.envs.tasks.tabletop.push_cube", "mani_skill/envs/tasks/tabletop/push_cube.py")
+    PU = push_mod.PushCubeEnv
+    m = 12
+    obj_p = torch.hstack([torch.randn(m, 2, generator=g3) * 0.1, torch.full((m, 1), 0.02)])
+    obj_p[:3, 2] += torch.tensor([0.004, 0.006, 0.02])            # lifted cubes: one inside, two outside the 5 mm band
+    goal_p = torch.hstack([obj_p[:, :2] + torch.randn(m, 2, generator=g3) * 0.12, torch.full((m, 1), 1e-3)])
+    goal_p[:4, :2] = obj_p[:4, :2] + 0.01
+    obj_raw = torch.hstack([obj_p, torch.nn.functional.normalize(torch.randn(m, 4, generator=g3), dim=-1)])
+    tcp_p = obj_p + torch.randn(m, 3, generator=g3) * 0.05
+    tcp_p[4:8] = obj_p[4:8] + torch.tensor([-0.025, 0.0, 0.0]) + torch.randn(4, 3, generator=g3) * 0.002   # at the push pose
+    tcp_raw3 = torch.hstack([tcp_p, torch.nn.functional.normalize(torch.randn(m, 4, generator=g3), dim=-1)])
+    fake_push = SimpleNamespace(obj=SimpleNamespace(pose=Pose.create(obj_raw)), goal_region=SimpleNamespace(pose=Pose.create_from_pq(goal_p)),
+                                agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(tcp_raw3))), goal_radius=0.1, cube_half_size=0.02,
+                                device=torch.device("cpu"), obs_mode_struct=SimpleNamespace(use_state=True))
+    uinfo = PU.evaluate(fake_push)
+    G["push_obj"], G["push_goal"], G["push_tcp"] = obj_raw, goal_p, tcp_raw3
+    G["push_success"] = uinfo["success"]
+    G["push_reward"] = PU.compute_dense_reward(fake_push, None, None, uinfo)
+    G["push_extra_flat"] = common.flatten_state_dict(PU._get_obs_extra(fake_push, uinfo), use_torch=True)
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

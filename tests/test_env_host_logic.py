@@ -184,3 +184,37 @@ def test_net_contact_force_on_resting_cube_is_its_weight():
     assert f[:, :2].abs().max() < 1e-2
     table = env.scene.actors["table-workspace"]
     assert torch.allclose(f, env.scene.get_pairwise_contact_forces(env.cube, table), atol=1e-6)
+
+
+def test_push_cube_reset_obs_and_a_scripted_push():
+    """PushCube-v1 (push_cube.py): reset ranges, 35-dim state observation, and a scripted push with the target end-effector
+    controller drives the cube into the goal disc."""
+    env = ms.make("PushCube-v1", num_envs=3, obs_mode="state", control_mode="pd_ee_target_delta_pos", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    # qpos, qvel, the controller's virtual target pose (base_agent.py:339-347: controller state is part of proprioception), tcp pose,
+    # goal position, cube pose
+    assert obs.shape == (3, 9 + 9 + 7 + 7 + 3 + 7) and env.action_dim == 4
+    cube, goal = env.obj.pose.p.clone(), env.goal_region.pose.p.clone()
+    assert (cube[:, :2].abs() <= 0.1 + 1e-6).all() and torch.allclose(cube[:, 2], torch.full((3,), 0.02))
+    assert torch.allclose(goal[:, :2], cube[:, :2] + torch.tensor([0.2, 0.0]), atol=1e-6) and torch.allclose(goal[:, 2], torch.full((3,), 1e-3))
+    assert not env.evaluate()["success"].any()
+
+    ctrl = env.agent.controller.controllers["arm"]
+
+    def go_to(target, steps, max_step=0.1, grip=-1.0):
+        for _ in range(steps):
+            d = (target - ctrl._target_pose.p).clamp(-max_step, max_step)  # the virtual target lives in the robot's root frame
+            a = torch.zeros(3, 4)
+            a[:, :3] = d / 0.1
+            a[:, 3] = grip
+            out = env.step(a)
+        return out
+
+    base = torch.tensor([-0.615, 0.0, 0.0])
+    behind = cube + torch.tensor([-0.06, 0.0, 0.0]) - base
+    go_to(behind + torch.tensor([0.0, 0.0, 0.08]), 12)
+    go_to(behind, 10)
+    assert (env.agent.tcp.pose.p - (behind + base)).abs().max() < 3e-3      # the controller tracks its target to millimetres
+    obs, r, te, tr, info = go_to(behind + torch.tensor([0.2, 0.0, 0.0]), 30, max_step=0.01)   # 0.2 m/s: push, do not kick
+    assert info["success"].all(), (env.obj.pose.p, env.goal_region.pose.p)
+    assert torch.allclose(r, torch.ones(3))  # normalised dense reward saturates at success

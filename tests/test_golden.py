@@ -149,3 +149,17 @@ def test_open_cabinet_drawer_evaluate_reward_obs():
     close(info["handle_link_pos"], G["cab_handle_link_pos"], 2e-6)
     close(CE.compute_dense_reward(fake, None, None, info), G["cab_reward"], 2e-6)
     close(U.flatten_state_dict(CE._get_obs_extra(fake, info)), G["cab_extra_flat"], 2e-6)
+
+
+def test_push_cube_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/push_cube.py:179-241 run by the reference's own code on the same synthetic states."""
+    from maniskill_b200.envs.push_cube import PushCubeEnv as PU
+    m = len(G["push_success"])
+    goal = Pose(torch.hstack([T("push_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(obj=SimpleNamespace(pose=Pose(T("push_obj"))), goal_region=SimpleNamespace(pose=goal),
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("push_tcp")))), goal_radius=0.1, cube_half_size=0.02, obs_mode="state")
+    info = PU.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["push_success"])
+    assert G["push_success"].any() and not G["push_success"].all()
+    close(PU.compute_dense_reward(fake, None, None, info), G["push_reward"], 2e-6)
+    close(U.flatten_state_dict(PU._get_obs_extra(fake, info)), G["push_extra_flat"], 1e-6)
