@@ -12,3 +12,6 @@ register_env("OpenCabinetDrawer-v1", max_episode_steps=100)(OpenCabinetDrawerEnv
 from .push_cube import PushCubeEnv
 
 register_env("PushCube-v1", max_episode_steps=50)(PushCubeEnv)
+from .stack_cube import StackCubeEnv
+
+register_env("StackCube-v1", max_episode_steps=50)(StackCubeEnv)

@@ -19,6 +19,8 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/peg_insertion_side.py:250-360  peg_head_pose / box_hole_pose / goal_pose, has_peg_inserted,
                                                      evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358  handle_link_positions, evaluate, _get_obs_extra,
                                                      compute_dense_reward
 """
@@ -301,6 +303,41 @@ def main():
     G["push_success"] = uinfo["success"]
     G["push_reward"] = PU.compute_dense_reward(fake_push, None, None, uinfo)
     G["push_extra_flat"] = common.flatten_state_dict(PU._get_obs_extra(fake_push, uinfo), use_torch=True)
+    # ---- UniformPlacementSampler under a fixed global seed (three sequential samples, tight bounds so that rejections happen)
+    samp = load("mani_skill.envs.utils.randomization.samplers", "mani_skill/envs/utils/randomization/samplers.py")
+    torch.manual_seed(31337)
+    sp = samp.UniformPlacementSampler(bounds=[[-0.05, -0.06], [0.05, 0.06]], batch_size=16)
+    G["sampler_pts"] = torch.stack([sp.sample(0.03, 100), sp.sample(0.03, 100, verbose=False), sp.sample(0.02, 100, verbose=False)])
+    # ---- StackCube task logic on synthetic states
+    sys.modules["mani_skill.envs.utils"].randomization = sys.modules["mani_skill.envs.utils.randomization"]
+    stack_mod = load("mani_skill.envs.tasks.tabletop.stack_cube", "mani_skill/envs/tasks/tabletop/stack_cube.py")
+    SC = stack_mod.StackCubeEnv
+    m = 12
+    B_p = torch.hstack([torch.randn(m, 2, generator=g3) * 0.1, torch.full((m, 1), 0.02)])
+    A_p = B_p + torch.randn(m, 3, generator=g3) * 0.08
+    A_p[:6] = B_p[:6] + torch.tensor([0.0, 0.0, 0.04]) + torch.randn(6, 3, generator=g3) * torch.tensor([0.012, 0.012, 0.003])  # (nearly) stacked
+    A_raw = torch.hstack([A_p, torch.nn.functional.normalize(torch.randn(m, 4, generator=g3), dim=-1)])
+    B_raw = torch.hstack([B_p, torch.nn.functional.normalize(torch.randn(m, 4, generator=g3), dim=-1)])
+    A_lin = torch.randn(m, 3, generator=g3) * 0.01
+    A_ang = torch.randn(m, 3, generator=g3) * 0.4
+    A_lin[:4] *= 0.1
+    A_ang[:4] *= 0.1
+    tcp4 = torch.hstack([A_p + torch.randn(m, 3, generator=g3) * 0.04, torch.nn.functional.normalize(torch.randn(m, 4, generator=g3), dim=-1)])
+    grasped4 = torch.tensor([False, True, False, False, True, False] * 2)
+    qpos4 = torch.rand(m, 9, generator=g3) * 0.04
+    qlim = torch.zeros(1, 9, 2)
+    qlim[0, :, 1] = 0.04
+    cubeA = SimpleNamespace(pose=Pose.create(A_raw), linear_velocity=A_lin, angular_velocity=A_ang,
+                            is_static=lambda lin_thresh=1e-2, ang_thresh=1e-1: (torch.linalg.norm(A_lin, axis=1) <= lin_thresh) & (torch.linalg.norm(A_ang, axis=1) <= ang_thresh))
+    fake_stack = SimpleNamespace(cubeA=cubeA, cubeB=SimpleNamespace(pose=Pose.create(B_raw)), cube_half_size=torch.tensor([0.02] * 3), device=torch.device("cpu"),
+                                 obs_mode="state", agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(tcp4)), is_grasping=lambda obj: grasped4,
+                                                                         robot=SimpleNamespace(get_qlimits=lambda: qlim, get_qpos=lambda: qpos4)))
+    sinfo = SC.evaluate(fake_stack)
+    G["stack_A"], G["stack_B"], G["stack_A_lin"], G["stack_A_ang"], G["stack_tcp"], G["stack_grasped"], G["stack_qpos"] = A_raw, B_raw, A_lin, A_ang, tcp4, grasped4, qpos4
+    for k_ in ("is_cubeA_on_cubeB", "is_cubeA_static", "success"):
+        G["stack_" + k_] = sinfo[k_]
+    G["stack_reward"] = SC.compute_dense_reward(fake_stack, None, None, sinfo)
+    G["stack_extra_flat"] = common.flatten_state_dict(SC._get_obs_extra(fake_stack, sinfo), use_torch=True)
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

@@ -218,3 +218,25 @@ def test_push_cube_reset_obs_and_a_scripted_push():
     obs, r, te, tr, info = go_to(behind + torch.tensor([0.2, 0.0, 0.0]), 30, max_step=0.01)   # 0.2 m/s: push, do not kick
     assert info["success"].all(), (env.obj.pose.p, env.goal_region.pose.p)
     assert torch.allclose(r, torch.ones(3))  # normalised dense reward saturates at success
+
+
+def test_stack_cube_reset_and_a_stacked_cube_counts_as_success():
+    """StackCube-v1 (stack_cube.py): the two cubes never start overlapping, 48-dim state observation, and a cube put down on the
+    other one (box on box on table) settles and is reported as stacked, static and released."""
+    env = ms.make("StackCube-v1", num_envs=4, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=5)
+    assert obs.shape == (4, 9 + 9 + 7 + 7 + 7 + 3 + 3 + 3)
+    a, b = env.cubeA.pose.p, env.cubeB.pose.p
+    assert (torch.linalg.norm(a[:, :2] - b[:, :2], dim=1) > 2 * (0.02 * 2 ** 0.5 + 0.001) - 1e-6).all()
+    assert torch.allclose(a[:, 2], torch.full((4,), 0.02)) and torch.allclose(b[:, 2], torch.full((4,), 0.02))
+    assert not env.evaluate()["success"].any()
+    from maniskill_b200.structs import Pose
+    top = env.cubeB.pose.raw_pose.clone()
+    top[:, 2] += 0.041  # 1 mm above the lower cube
+    env.cubeA.set_pose(Pose(top))
+    env.scene._gpu_apply_all()
+    for _ in range(10):
+        obs, r, te, tr, info = env.step(torch.zeros(4, 8))
+    assert info["is_cubeA_on_cubeB"].all() and info["is_cubeA_static"].all() and not info["is_cubeA_grasped"].any()
+    assert info["success"].all() and torch.allclose(r, torch.ones(4))
+    assert (env.cubeA.pose.p[:, 2] - 0.06).abs().max() < 2e-3

@@ -163,3 +163,31 @@ def test_push_cube_evaluate_reward_obs():
     assert G["push_success"].any() and not G["push_success"].all()
     close(PU.compute_dense_reward(fake, None, None, info), G["push_reward"], 2e-6)
     close(U.flatten_state_dict(PU._get_obs_extra(fake, info)), G["push_extra_flat"], 1e-6)
+
+
+def test_uniform_placement_sampler_same_stream_as_the_reference():
+    """samplers.py:13-108 under the same global torch seed: identical points (the rejection loop consumes torch.rand identically)."""
+    torch.manual_seed(31337)
+    sp = U.UniformPlacementSampler([[-0.05, -0.06], [0.05, 0.06]], 16)
+    pts = torch.stack([sp.sample(0.03, 100), sp.sample(0.03, 100), sp.sample(0.02, 100)])
+    close(pts, G["sampler_pts"], 1e-7)
+    d01 = np.linalg.norm(G["sampler_pts"][0] - G["sampler_pts"][1], axis=-1)
+    assert (d01 > 0.06).all()  # the constraint the sampler enforces (and the bounds are tight enough that rejections happened)
+
+
+def test_stack_cube_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/stack_cube.py:115-200 run by the reference's own code on the same synthetic states."""
+    from maniskill_b200.envs.stack_cube import StackCubeEnv as SC
+    grasped, qpos = T("stack_grasped"), T("stack_qpos")
+    qlim = torch.zeros(1, 9, 2)
+    qlim[0, :, 1] = 0.04
+    fake = SimpleNamespace(cubeA=SimpleNamespace(pose=Pose(T("stack_A")), linear_velocity=T("stack_A_lin"), angular_velocity=T("stack_A_ang")),
+                           cubeB=SimpleNamespace(pose=Pose(T("stack_B"))), cube_half_size=torch.tensor([0.02] * 3), obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("stack_tcp"))), is_grasping=lambda obj: grasped,
+                                                 robot=SimpleNamespace(get_qlimits=lambda: qlim, get_qpos=lambda: qpos)))
+    info = SC.evaluate(fake)
+    for k in ("is_cubeA_on_cubeB", "is_cubeA_static", "success"):
+        assert np.array_equal(info[k].numpy(), G["stack_" + k]), k
+    assert G["stack_is_cubeA_on_cubeB"].any() and not G["stack_is_cubeA_on_cubeB"].all()
+    close(SC.compute_dense_reward(fake, None, None, info), G["stack_reward"], 2e-6)
+    close(U.flatten_state_dict(SC._get_obs_extra(fake, info)), G["stack_extra_flat"], 1e-6)
