@@ -21,6 +21,8 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
+  mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
+                                                     PDJointPosMimicController.set_action; base_controller.py:125-173 action clipping
   mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358  handle_link_positions, evaluate, _get_obs_extra,
                                                      compute_dense_reward
 """
@@ -338,6 +340,48 @@ def main():
         G["stack_" + k_] = sinfo[k_]
     G["stack_reward"] = SC.compute_dense_reward(fake_stack, None, None, sinfo)
     G["stack_extra_flat"] = common.flatten_state_dict(SC._get_obs_extra(fake_stack, sinfo), use_torch=True)
+    # ---- joint-space controllers: the reference's own set_action on a stand-in controller object (row a1 of SURVEY section 8)
+    stub("gymnasium.vector")
+    stub("gymnasium.vector.utils")
+    stub("mani_skill.agents.utils")
+    sys.modules["mani_skill.utils"].gym_utils = gym_utils
+    sys.modules["mani_skill.utils.structs"].ArticulationJoint = object
+    pkg("mani_skill.agents.controllers")
+    bc = load("mani_skill.agents.controllers.base_controller", "mani_skill/agents/controllers/base_controller.py")
+    pjp = load("mani_skill.agents.controllers.pd_joint_pos", "mani_skill/agents/controllers/pd_joint_pos.py")
+    nenv = 6
+    qpos_arm = torch.randn(nenv, 7, generator=g3) * 0.5
+    acts = [torch.randn(nenv, 7, generator=g3) * 0.8 for _ in range(2)]
+    sent = []
+
+    def fake_ctrl(cls, qpos, low, high, use_delta, use_target, normalize=True, **extra):
+        c = SimpleNamespace(config=SimpleNamespace(use_delta=use_delta, use_target=use_target, interpolate=False), scene=SimpleNamespace(num_envs=nenv),
+                            action_space=SimpleNamespace(shape=(nenv, low.shape[0])), _normalize_action=normalize, action_space_low=low, action_space_high=high,
+                            qpos=qpos, _target_qpos=qpos.clone(), _start_qpos=qpos.clone(), **extra)
+        c._preprocess_action = lambda a: bc.BaseController._preprocess_action(c, a)
+        c._clip_and_scale_action = lambda a: bc.BaseController._clip_and_scale_action(c, a)
+        c.set_drive_targets = lambda t: sent.append(t.clone())
+        return c
+
+    low7, high7 = torch.full((7,), -0.1), torch.full((7,), 0.1)
+    G["ctl_qpos_arm"], G["ctl_act0"], G["ctl_act1"] = qpos_arm, acts[0], acts[1]
+    c = fake_ctrl(pjp.PDJointPosController, qpos_arm, low7, high7, True, False)
+    pjp.PDJointPosController.set_action(c, acts[0])
+    G["ctl_delta_target"] = sent[-1]
+    c = fake_ctrl(pjp.PDJointPosController, qpos_arm, low7, high7, True, True)
+    pjp.PDJointPosController.set_action(c, acts[0])
+    pjp.PDJointPosController.set_action(c, acts[1])
+    G["ctl_target_delta_target"] = sent[-1]
+    c = fake_ctrl(pjp.PDJointPosController, qpos_arm, low7, high7, False, False, normalize=False)
+    pjp.PDJointPosController.set_action(c, acts[0])
+    G["ctl_abs_target"] = sent[-1]
+    qpos_grip = torch.rand(nenv, 2, generator=g3) * 0.04
+    act_grip = torch.randn(nenv, 1, generator=g3)
+    c = fake_ctrl(pjp.PDJointPosMimicController, qpos_grip, torch.tensor([-0.01]), torch.tensor([0.04]), False, False,
+                  control_joint_indices=torch.tensor([0]), mimic_joint_indices=torch.tensor([1]), mimic_control_joint_indices=torch.tensor([0]),
+                  _multiplier=torch.ones(1), _offset=torch.zeros(1))
+    pjp.PDJointPosMimicController.set_action(c, act_grip)
+    G["ctl_qpos_grip"], G["ctl_act_grip"], G["ctl_mimic_target"] = qpos_grip, act_grip, sent[-1]
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

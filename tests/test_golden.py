@@ -191,3 +191,46 @@ def test_stack_cube_evaluate_reward_obs():
     assert G["stack_is_cubeA_on_cubeB"].any() and not G["stack_is_cubeA_on_cubeB"].all()
     close(SC.compute_dense_reward(fake, None, None, info), G["stack_reward"], 2e-6)
     close(U.flatten_state_dict(SC._get_obs_extra(fake, info)), G["stack_extra_flat"], 1e-6)
+
+
+class _FakeArticulation:
+    """Just enough of structs.Articulation for the joint controllers: qpos, limits, and a capture of the drive targets."""
+
+    def __init__(self, qpos, names):
+        self.scene = SimpleNamespace(device=torch.device("cpu"))
+        self.dof_names = names
+        self.qpos = qpos
+        self.qlimits = torch.stack([torch.full((len(names),), -3.0), torch.full((len(names),), 3.0)], 1)[None].expand(qpos.shape[0], -1, -1)
+        self.sent = None
+
+    def set_joint_drive_targets(self, targets, idx):
+        self.sent = targets.clone()
+
+
+def test_joint_controllers_match_the_reference_set_action():
+    """pd_joint_pos.py:77-101 / 207-228 with base_controller.py:125-173: drive targets written for delta, target-delta, absolute
+    and mimic control, produced by the reference's own set_action on the same inputs."""
+    from maniskill_b200.agents import PDJointPosController, PDJointPosMimicController
+    names = [f"j{i}" for i in range(7)]
+    q = T("ctl_qpos_arm")
+    art = _FakeArticulation(q, names)
+    c = PDJointPosController(art, names, -0.1, 0.1, use_delta=True)
+    c.reset()
+    c.set_action(T("ctl_act0"))
+    close(art.sent, G["ctl_delta_target"], 1e-7)
+    c = PDJointPosController(art, names, -0.1, 0.1, use_delta=True, use_target=True)
+    c.reset()
+    c.set_action(T("ctl_act0"))
+    c.set_action(T("ctl_act1"))
+    close(art.sent, G["ctl_target_delta_target"], 1e-7)
+    c = PDJointPosController(art, names, None, None, normalize_action=False)
+    c.reset()
+    c.set_action(T("ctl_act0"))
+    close(art.sent, G["ctl_abs_target"], 1e-7)
+    gq = T("ctl_qpos_grip")
+    gart = _FakeArticulation(gq, ["f1", "f2"])
+    g = PDJointPosMimicController(gart, ["f1", "f2"], -0.01, 0.04, mimic={"f2": {"joint": "f1"}})
+    g.reset()
+    g.set_action(T("ctl_act_grip"))
+    close(gart.sent, G["ctl_mimic_target"], 1e-7)
+    assert torch.equal(gart.sent[:, 0], gart.sent[:, 1])
