@@ -382,6 +382,19 @@ def main():
                   _multiplier=torch.ones(1), _offset=torch.zeros(1))
     pjp.PDJointPosMimicController.set_action(c, act_grip)
     G["ctl_qpos_grip"], G["ctl_act_grip"], G["ctl_mimic_target"] = qpos_grip, act_grip, sent[-1]
+    # ---- PDBaseForwardVelController.set_action (Fetch base, pd_base_vel.py:39-73)
+    stub("mani_skill.agents.controllers.pd_joint_vel", PDJointVelController=object, PDJointVelControllerConfig=object)
+    pbv = load("mani_skill.agents.controllers.pd_base_vel", "mani_skill/agents/controllers/pd_base_vel.py")
+    base_q = torch.hstack([torch.randn(nenv, 2, generator=g3), torch.rand(nenv, 1, generator=g3) * 6.28 - 3.14])
+    base_act = torch.randn(nenv, 2, generator=g3) * 0.9
+    vel_sent = []
+    cb = SimpleNamespace(qpos=base_q, joints=None, active_joint_indices=None, scene=SimpleNamespace(num_envs=nenv), action_space=SimpleNamespace(shape=(nenv, 2)),
+                         _normalize_action=True, action_space_low=torch.tensor([-1.0, -3.14]), action_space_high=torch.tensor([1.0, 3.14]),
+                         articulation=SimpleNamespace(set_joint_drive_velocity_targets=lambda t, j, idx: vel_sent.append(t.clone())))
+    cb._preprocess_action = lambda a: bc.BaseController._preprocess_action(cb, a)
+    cb._clip_and_scale_action = lambda a: bc.BaseController._clip_and_scale_action(cb, a)
+    pbv.PDBaseForwardVelController.set_action(cb, base_act)
+    G["ctl_base_q"], G["ctl_base_act"], G["ctl_base_vel_target"] = base_q, base_act, vel_sent[-1]
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

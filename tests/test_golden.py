@@ -234,3 +234,14 @@ def test_joint_controllers_match_the_reference_set_action():
     g.set_action(T("ctl_act_grip"))
     close(gart.sent, G["ctl_mimic_target"], 1e-7)
     assert torch.equal(gart.sent[:, 0], gart.sent[:, 1])
+
+
+def test_base_forward_velocity_controller_matches_the_reference():
+    """pd_base_vel.py:39-73 (Fetch mobile base): forward speed and yaw rate -> velocity targets of the x / y / yaw joints."""
+    from maniskill_b200.agents import PDBaseForwardVelController
+    q = T("ctl_base_q")
+    art = _FakeArticulation(q, ["x", "y", "yaw"])
+    art.set_joint_drive_velocity_targets = lambda t, idx: setattr(art, "sent", t.clone())
+    c = PDBaseForwardVelController(art, ["x", "y", "yaw"], [-1.0, -3.14], [1.0, 3.14])
+    c.set_action(T("ctl_base_act"))
+    close(art.sent, G["ctl_base_vel_target"], 1e-6)
