@@ -9,13 +9,20 @@ import torch
 
 
 class ManiSkillVectorEnv:
-    def __init__(self, env, auto_reset: bool = True, ignore_terminations: bool = False, max_episode_steps: Optional[int] = None):
+    def __init__(self, env, auto_reset: bool = True, ignore_terminations: bool = False, max_episode_steps: Optional[int] = None,
+                 record_metrics: bool = False):
         self._env = env
         self.num_envs = env.num_envs
         self.auto_reset = auto_reset
         self.ignore_terminations = ignore_terminations
         self.max_episode_steps = max_episode_steps if max_episode_steps is not None else env.max_episode_steps
         self.device = env.device
+        # gymnasium.py:79-88: running episode statistics reported as infos["episode"]
+        self.record_metrics = record_metrics
+        if record_metrics:
+            self.success_once = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            self.fail_once = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            self.returns = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
 
     @property
     def base_env(self):
@@ -26,7 +33,13 @@ class ManiSkillVectorEnv:
         return self._env
 
     def reset(self, *, seed=None, options=None):
-        return self._env.reset(seed=seed, options=dict() if options is None else options)
+        obs, info = self._env.reset(seed=seed, options=dict() if options is None else options)
+        if self.record_metrics:  # gymnasium.py:108-124: statistics restart for the sub-scenes being reset
+            idx = options["env_idx"] if options is not None and "env_idx" in options else slice(None)
+            self.success_once[idx] = False
+            self.fail_once[idx] = False
+            self.returns[idx] = 0
+        return obs, info
 
     def step(self, actions):
         obs, rew, terminations, truncations, infos = self._env.step(actions)
@@ -35,13 +48,34 @@ class ManiSkillVectorEnv:
             truncations = self._env.elapsed_steps >= self.max_episode_steps
         else:
             truncations = torch.zeros_like(terminations)
+        episode_info = None
+        if self.record_metrics:  # gymnasium.py:131-145
+            episode_info = dict()
+            self.returns += rew
+            if "success" in infos:
+                self.success_once = self.success_once | infos["success"]
+                episode_info["success_once"] = self.success_once.clone()
+            if "fail" in infos:
+                self.fail_once = self.fail_once | infos["fail"]
+                episode_info["fail_once"] = self.fail_once.clone()
+            episode_info["return"] = self.returns.clone()
+            episode_info["episode_len"] = self._env.elapsed_steps.clone()
+            episode_info["reward"] = episode_info["return"] / episode_info["episode_len"]
         if self.ignore_terminations:
             terminations = torch.zeros_like(terminations)
+            if episode_info:
+                if "success" in infos:
+                    episode_info["success_at_end"] = infos["success"].clone()
+                if "fail" in infos:
+                    episode_info["fail_at_end"] = infos["fail"].clone()
+        if self.record_metrics:
+            infos["episode"] = episode_info
         dones = torch.logical_or(terminations, truncations)
         if dones.any() and self.auto_reset:
             final_obs = obs if isinstance(obs, dict) else obs.clone()
             env_idx = torch.arange(0, self.num_envs, device=self.device)[dones]
-            final_info = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in infos.items()}
+            final_info = {k: (v.clone() if isinstance(v, torch.Tensor) else ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v))
+                          for k, v in infos.items()}
             obs, infos = self.reset(options=dict(env_idx=env_idx))
             infos["final_info"] = final_info
             infos["_final_info"] = dones

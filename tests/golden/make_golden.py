@@ -21,6 +21,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
+  mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
                                                      PDJointPosMimicController.set_action; base_controller.py:125-173 action clipping
   mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py:221-358  handle_link_positions, evaluate, _get_obs_extra,
@@ -395,6 +396,47 @@ def main():
     cb._clip_and_scale_action = lambda a: bc.BaseController._clip_and_scale_action(cb, a)
     pbv.PDBaseForwardVelController.set_action(cb, base_act)
     G["ctl_base_q"], G["ctl_base_act"], G["ctl_base_vel_target"] = base_q, base_act, vel_sent[-1]
+    # ---- ManiSkillVectorEnv.step / reset on a scripted inner env (record_metrics, partial auto-reset)
+    sys.modules["gymnasium.vector"].VectorEnv = object
+    sys.modules["gymnasium"].vector = sys.modules["gymnasium.vector"]
+    del sys.modules["mani_skill.vector.wrappers.gymnasium"]
+    vw = load("mani_skill.vector.wrappers.gymnasium", "mani_skill/vector/wrappers/gymnasium.py")
+    nv, T_ = 5, 7
+    script_rew = torch.rand(T_, nv, generator=g3)
+    script_succ = torch.rand(T_, nv, generator=g3) < 0.25
+    script_trunc = torch.zeros(T_, nv, dtype=torch.bool)
+    script_trunc[4, :] = True
+    G["vec_rew"], G["vec_succ"], G["vec_trunc"] = script_rew, script_succ, script_trunc
+
+    class ScriptedEnv:  # elapsed_steps + scripted (obs, reward, terminated, truncated, info); partial reset zeroes elapsed_steps
+        def __init__(self):
+            self.t = 0
+            self.elapsed_steps = torch.zeros(nv, dtype=torch.int32)
+            self.device = torch.device("cpu")
+            self.num_envs = nv
+        def step(self, a):
+            self.elapsed_steps = self.elapsed_steps + 1
+            t = self.t
+            self.t += 1
+            return (torch.full((nv, 2), float(t)), script_rew[t].clone(), script_succ[t].clone(), script_trunc[t].clone(),
+                    dict(success=script_succ[t].clone(), elapsed_steps=self.elapsed_steps.clone()))
+        def reset(self, seed=None, options=None):
+            idx = options["env_idx"] if options and "env_idx" in options else torch.arange(nv)
+            self.elapsed_steps[idx] = 0
+            return torch.full((nv, 2), -1.0), dict(reset=True)
+
+    inner = ScriptedEnv()
+    wrap = SimpleNamespace(_env=inner, base_env=inner, num_envs=nv, auto_reset=True, ignore_terminations=False, record_metrics=True, device=inner.device,
+                           success_once=torch.zeros(nv, dtype=torch.bool), fail_once=torch.zeros(nv, dtype=torch.bool), returns=torch.zeros(nv))
+    wrap.reset = lambda seed=None, options=None: vw.ManiSkillVectorEnv.reset(wrap, seed=seed, options=options)
+    for t in range(T_):
+        o, r, te, tr, info = vw.ManiSkillVectorEnv.step(wrap, None)
+        G[f"vec_obs_{t}"], G[f"vec_term_{t}"], G[f"vec_truncout_{t}"] = o, te, tr
+        ep = info["final_info"]["episode"] if "final_info" in info else info["episode"]
+        G[f"vec_has_final_{t}"] = torch.tensor("final_info" in info)
+        for k_ in ("success_once", "return", "episode_len", "reward"):
+            G[f"vec_{k_}_{t}"] = ep[k_]
+        G[f"vec_returns_after_{t}"] = wrap.returns.clone()
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

@@ -245,3 +245,50 @@ def test_base_forward_velocity_controller_matches_the_reference():
     c = PDBaseForwardVelController(art, ["x", "y", "yaw"], [-1.0, -3.14], [1.0, 3.14])
     c.set_action(T("ctl_base_act"))
     close(art.sent, G["ctl_base_vel_target"], 1e-6)
+
+
+def test_vector_wrapper_metrics_and_auto_reset_match_the_reference():
+    """mani_skill/vector/wrappers/gymnasium.py:96-176 (`ManiSkillVectorEnv.reset` / `.step` with record_metrics and auto reset) run
+    by the reference's own code on the same scripted inner environment: observations handed out, terminations / truncations, the
+    running episode statistics before and after partial resets."""
+    import maniskill_b200 as ms
+    rew, succ, trunc = T("vec_rew"), T("vec_succ"), T("vec_trunc")
+    n_t, nv = rew.shape
+
+    class ScriptedEnv:
+        max_episode_steps = None
+
+        def __init__(self):
+            self.t = 0
+            self.elapsed_steps = torch.zeros(nv, dtype=torch.int32)
+            self.device = torch.device("cpu")
+            self.num_envs = nv
+
+        def step(self, a):
+            self.elapsed_steps = self.elapsed_steps + 1
+            t = self.t
+            self.t += 1
+            return (torch.full((nv, 2), float(t)), rew[t].clone(), succ[t].clone(), trunc[t].clone(),
+                    dict(success=succ[t].clone(), elapsed_steps=self.elapsed_steps.clone()))
+
+        def reset(self, seed=None, options=None):
+            idx = options["env_idx"] if options and "env_idx" in options else torch.arange(nv)
+            self.elapsed_steps[idx] = 0
+            return torch.full((nv, 2), -1.0), dict(reset=True)
+
+    inner = ScriptedEnv()
+    venv = ms.ManiSkillVectorEnv(inner, auto_reset=True, record_metrics=True)
+    # the reference gets truncations from the TimeLimit wrapper inside the env; here the wrapper computes them from
+    # elapsed_steps >= max_episode_steps: script the same truncation pattern through that path
+    for t in range(n_t):
+        venv.max_episode_steps = 1 if trunc[t].all() else 10 ** 6
+        o, r, te, tr, info = venv.step(None)
+        close(o, G[f"vec_obs_{t}"])
+        assert np.array_equal(te.numpy(), G[f"vec_term_{t}"]) and np.array_equal(tr.numpy(), G[f"vec_truncout_{t}"])
+        assert ("final_info" in info) == bool(G[f"vec_has_final_{t}"])
+        ep = info["final_info"]["episode"] if "final_info" in info else info["episode"]
+        assert np.array_equal(ep["success_once"].numpy(), G[f"vec_success_once_{t}"])
+        close(ep["return"], G[f"vec_return_{t}"])
+        assert np.array_equal(ep["episode_len"].numpy(), G[f"vec_episode_len_{t}"])
+        close(ep["reward"], G[f"vec_reward_{t}"])
+        close(venv.returns, G[f"vec_returns_after_{t}"])
