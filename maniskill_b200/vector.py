@@ -41,6 +41,20 @@ class ManiSkillVectorEnv:
             self.returns[idx] = 0
         return obs, info
 
+    def _update_metrics(self, rew, infos):
+        """Running statistics of the current episodes (gymnasium.py:131-145): undiscounted return, whether success / failure has
+        been seen so far, length, mean reward."""
+        self.returns += rew
+        stats = {}
+        for flag, acc in (("success", "success_once"), ("fail", "fail_once")):
+            if flag in infos:
+                setattr(self, acc, getattr(self, acc) | infos[flag])
+                stats[acc] = getattr(self, acc).clone()
+        stats["return"] = self.returns.clone()
+        stats["episode_len"] = self._env.elapsed_steps.clone()
+        stats["reward"] = stats["return"] / stats["episode_len"]
+        return stats
+
     def step(self, actions):
         obs, rew, terminations, truncations, infos = self._env.step(actions)
         if self.max_episode_steps is not None:
@@ -48,28 +62,13 @@ class ManiSkillVectorEnv:
             truncations = self._env.elapsed_steps >= self.max_episode_steps
         else:
             truncations = torch.zeros_like(terminations)
-        episode_info = None
-        if self.record_metrics:  # gymnasium.py:131-145
-            episode_info = dict()
-            self.returns += rew
-            if "success" in infos:
-                self.success_once = self.success_once | infos["success"]
-                episode_info["success_once"] = self.success_once.clone()
-            if "fail" in infos:
-                self.fail_once = self.fail_once | infos["fail"]
-                episode_info["fail_once"] = self.fail_once.clone()
-            episode_info["return"] = self.returns.clone()
-            episode_info["episode_len"] = self._env.elapsed_steps.clone()
-            episode_info["reward"] = episode_info["return"] / episode_info["episode_len"]
+        stats = self._update_metrics(rew, infos) if self.record_metrics else None
         if self.ignore_terminations:
             terminations = torch.zeros_like(terminations)
-            if episode_info:
-                if "success" in infos:
-                    episode_info["success_at_end"] = infos["success"].clone()
-                if "fail" in infos:
-                    episode_info["fail_at_end"] = infos["fail"].clone()
-        if self.record_metrics:
-            infos["episode"] = episode_info
+            if stats is not None:  # what the episode looked like at its last step (gymnasium.py:149-156)
+                stats.update({f"{k}_at_end": infos[k].clone() for k in ("success", "fail") if k in infos})
+        if stats is not None:
+            infos["episode"] = stats
         dones = torch.logical_or(terminations, truncations)
         if dones.any() and self.auto_reset:
             final_obs = obs if isinstance(obs, dict) else obs.clone()
