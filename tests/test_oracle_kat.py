@@ -182,3 +182,59 @@ def test_cooked_cylinder_rests_on_a_facet_and_weighs_mg(support, tilt):
     assert abs(b[2] - r * np.cos(np.pi / 24)) < 1e-3, b[:3]        # lies on a facet of the prism
     assert np.abs(b[7:10]).max() < 5e-3 and np.abs(b[10:13]).max() < 5e-2
     assert w.pair_impulse(cm.actor_rows["cyl"], -1)[0, 2] == pytest.approx(m * G * DT, rel=1e-2)
+
+
+def test_stack_of_three_boxes_stays_put():
+    """Solver convergence on a contact chain: three 10 cm boxes stacked on the ground keep their heights for 400 steps and the ground
+    carries the weight of all three."""
+    s = SceneDesc(1, SimParams())
+    ground(s)
+    for i in range(3):
+        s.add_actor(ActorRec(f"box{i}", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([0.05, 0.05, 0.05]))], pose7([0.002 * i, -0.001 * i, 0.05 + 0.1 * i])))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    w.step(400)
+    b = w.get_bodies()[0]
+    for i in range(3):
+        # the soft contacts (30 Hz) sag by about a millimetre per loaded interface; no drift beyond that
+        assert abs(b[i, 2] - (0.05 + 0.1 * i)) < 1.5e-3 * (i + 1) and np.abs(b[i, :2] - [0.002 * i, -0.001 * i]).max() < 2e-3, (i, b[i, :3])
+        assert np.abs(b[i, 7:]).max() < 2e-2
+    m = 1000 * 0.1 ** 3
+    assert w.pair_impulse(cm.actor_rows["box0"], -1)[0, 2] == pytest.approx(3 * m * G * DT, rel=2e-2)
+    assert w.pair_impulse(cm.actor_rows["box1"], cm.actor_rows["box0"])[0, 2] == pytest.approx(2 * m * G * DT, rel=2e-2)
+
+
+def test_joint_limit_stops_a_falling_link():
+    """A horizontal link released under gravity swings down until its joint limit (-0.5 rad) and rests there; the limit row only
+    acts when it is reached."""
+    robot = dict(name="arm", links=[root_link(), link("l1", 0, "revolute", (0, 0, 1.0), (0, 1, 0), 1.0, com=(0.3, 0, 0), lower=-0.5, upper=0.5)],
+                 disabled_collision_pairs=[])
+    s = SceneDesc(1, SimParams())
+    s.add_articulation(ArticulationRec("arm", robot, pose7(), disable_gravity=False))
+    w = OracleWorld(s.compile(), "f64")
+    q_hist = []
+    for _ in range(300):
+        w.step(1)
+        q_hist.append(w.get_joint("qpos")[0, 0])
+    q_hist = np.array(q_hist)
+    # rotation about +y with the centre of mass along +x: gravity drives q upwards (towards +0.5); free fall first, then the stop
+    assert q_hist[5] > 0 and q_hist[5] == pytest.approx(0.5 * (G / 0.3) * (6 * DT) ** 2, rel=0.25)
+    assert q_hist.max() < 0.5 + 5e-3
+    assert abs(q_hist[-1] - 0.5) < 2e-3 and abs(w.get_joint("qvel")[0, 0]) < 1e-2
+
+
+def test_mimic_tendon_keeps_the_fingers_mirrored():
+    """The fixed-tendon coupling of the Panda gripper (`<mimic>` of finger_joint2, articulation_builder.py:161-200): with only one
+    finger driven towards closing and an obstacle-free world, both finger joints move together."""
+    from maniskill_b200.scenes import pick_cube_scene, PANDA_REST_QPOS
+    cm = pick_cube_scene(1).compile()
+    w = OracleWorld(cm, "f32")
+    q0 = PANDA_REST_QPOS.copy()[None]
+    w.set_joint("qpos", q0)
+    tq = q0.copy()
+    tq[0, 7] = 0.0   # only finger 1 is told to close; finger 2 keeps its open target
+    w.set_joint("target_qpos", tq)
+    w.step(100)
+    q = w.get_joint("qpos")[0]
+    assert abs(q[7] - q[8]) < 2e-3, q[7:]
+    assert 0.005 < q[7] < 0.035  # the two drives (one closing, one holding open) balance through the tendon
