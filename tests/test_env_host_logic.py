@@ -240,3 +240,35 @@ def test_stack_cube_reset_and_a_stacked_cube_counts_as_success():
     assert info["is_cubeA_on_cubeB"].all() and info["is_cubeA_static"].all() and not info["is_cubeA_grasped"].any()
     assert info["success"].all() and torch.allclose(r, torch.ones(4))
     assert (env.cubeA.pose.p[:, 2] - 0.06).abs().max() < 2e-3
+
+
+def test_scripted_pick_and_lift_with_the_ee_controller():
+    """End to end through the public env API on the emulated device code: approach from above, close the gripper, lift 15 cm.  The
+    cube comes along (patch friction of the finger pads, mimic tendon, soft contacts), `is_grasped` turns on and the staged reward
+    grows (pick_cube.py:161-191)."""
+    n = 2
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="state", control_mode="pd_ee_target_delta_pos", world_factory=EmuBackendWorld)
+    env.reset(seed=4)
+    ctrl = env.agent.controller.controllers["arm"]
+    base = torch.tensor([-0.615, 0.0, 0.0])
+    cube0 = env.cube.pose.p.clone()
+
+    def go_to(target, steps, grip, max_step=0.03):
+        for _ in range(steps):
+            a = torch.zeros(n, 4)
+            a[:, :3] = (target - ctrl._target_pose.p).clamp(-max_step, max_step) / 0.1
+            a[:, 3] = grip
+            out = env.step(a)
+        return out
+
+    # the cube's yaw is random: a 4 cm cube fits between the open fingers (8 cm) at any yaw
+    go_to(cube0 - base + torch.tensor([0.0, 0.0, 0.10]), 12, 1.0)
+    go_to(cube0 - base, 12, 1.0)
+    obs, r_closed, *_ = go_to(cube0 - base, 8, -1.0)
+    assert env.evaluate()["is_grasped"].all()
+    obs, r_lift, te, tr, info = go_to(cube0 - base + torch.tensor([0.0, 0.0, 0.15]), 20, -1.0, max_step=0.015)
+    lifted = env.cube.pose.p[:, 2] - cube0[:, 2]
+    assert (lifted > 0.12).all(), lifted
+    assert info["is_grasped"].all()
+    assert (torch.linalg.norm(env.cube.pose.p - env.agent.tcp.pose.p, dim=1) < 0.015).all()   # still between the fingers
+    assert (r_closed > 0.2).all()  # reaching + grasp bonus of the normalised dense reward
