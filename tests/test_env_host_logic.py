@@ -272,3 +272,50 @@ def test_scripted_pick_and_lift_with_the_ee_controller():
     assert info["is_grasped"].all()
     assert (torch.linalg.norm(env.cube.pose.p - env.agent.tcp.pose.p, dim=1) < 0.015).all()   # still between the fingers
     assert (r_closed > 0.2).all()  # reaching + grasp bonus of the normalised dense reward
+
+
+def test_modes_and_configs_the_reference_accepts():
+    """obs_mode state_dict / none, reward_mode sparse / none / dense, a different sim / control frequency, num_envs = 1 with an
+    unbatched action, explicit per-env seeds (sapien_env.py:214-245, 857-930, 1042-1071)."""
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state_dict", reward_mode="sparse", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=[3, 4])
+    assert set(obs.keys()) == {"agent", "extra"} and obs["agent"]["qpos"].shape == (2, 9) and obs["extra"]["is_grasped"].dtype == torch.bool
+    o, r, te, tr, info = env.step(torch.zeros(2, 8))
+    assert torch.equal(r, info["success"].float())          # sparse reward = success (sapien_env.py:1079-1082)
+    env_b = ms.make("PickCube-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
+    ob_b, _ = env_b.reset(seed=[3, 4])
+    assert torch.allclose(ob_b[:, :9], obs["agent"]["qpos"], atol=1e-6)   # the same seeds give the same episode whatever the obs mode
+    env_n = ms.make("PickCube-v1", num_envs=1, obs_mode="none", reward_mode="none", world_factory=EmuBackendWorld)
+    obs_n, _ = env_n.reset(seed=0)
+    o, r, te, tr, info = env_n.step(torch.zeros(8))           # unbatched action for a single sub-scene
+    assert o == {} and float(r.abs().sum()) == 0.0 and te.shape == (1,)
+    env_d = ms.make("PickCube-v1", num_envs=2, obs_mode="state", reward_mode="dense", sim_config=dict(sim_freq=200, control_freq=50), world_factory=EmuBackendWorld)
+    env_d.reset(seed=1)
+    assert env_d._sim_steps_per_control == 4
+    o, r, te, tr, info = env_d.step(torch.zeros(2, 8))
+    env_nd = ms.make("PickCube-v1", num_envs=2, obs_mode="state", sim_config=dict(sim_freq=200, control_freq=50), world_factory=EmuBackendWorld)
+    env_nd.reset(seed=1)
+    o2, r2, *_ = env_nd.step(torch.zeros(2, 8))
+    assert torch.allclose(r, 5 * r2, atol=1e-5)               # normalized_dense = dense / 5 (pick_cube.py:188-191)
+    with pytest.raises(ValueError):
+        ms.make("PickCube-v1", num_envs=1, sim_config=dict(sim_freq=100, control_freq=30), world_factory=EmuBackendWorld)
+
+
+def test_reset_to_env_states_restores_a_saved_episode():
+    """reset(options={"reset_to_env_states": ...}) (sapien_env.py:905-913): the saved state comes back, for the selected sub-scenes only."""
+    env = make(3)
+    env.reset(seed=9)
+    for _ in range(4):
+        env.step(2 * torch.rand(3, 8, generator=torch.Generator().manual_seed(1)) - 1)
+    saved = env.get_state_dict()
+    saved = {k: {n: v.clone() for n, v in d.items()} for k, d in saved.items()}
+    flat_saved = env.get_state().clone()
+    for _ in range(5):
+        env.step(2 * torch.rand(3, 8) - 1)
+    moved = env.get_state().clone()
+    assert not torch.allclose(moved, flat_saved, atol=1e-4)
+    env.reset(options=dict(env_idx=torch.tensor([0, 2]), reset_to_env_states=dict(env_states={k: {n: v[[0, 2]] for n, v in d.items()} for k, d in saved.items()})))
+    now = env.get_state()
+    assert torch.allclose(now[[0, 2]], flat_saved[[0, 2]], atol=1e-5)
+    assert torch.allclose(now[1], moved[1], atol=1e-5)
+    assert env.elapsed_steps.tolist()[0] == 0 and env.elapsed_steps.tolist()[1] == 9
