@@ -15,3 +15,6 @@ register_env("PushCube-v1", max_episode_steps=50)(PushCubeEnv)
 from .stack_cube import StackCubeEnv
 
 register_env("StackCube-v1", max_episode_steps=50)(StackCubeEnv)
+from .pull_cube import PullCubeEnv
+
+register_env("PullCube-v1", max_episode_steps=50)(PullCubeEnv)

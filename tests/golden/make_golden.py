@@ -19,6 +19,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/peg_insertion_side.py:250-360  peg_head_pose / box_hole_pose / goal_pose, has_peg_inserted,
                                                      evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/tasks/tabletop/pull_cube.py:105-152  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
@@ -437,6 +438,17 @@ def main():
         for k_ in ("success_once", "return", "episode_len", "reward"):
             G[f"vec_{k_}_{t}"] = ep[k_]
         G[f"vec_returns_after_{t}"] = wrap.returns.clone()
+    # ---- PullCube task logic (same synthetic states as PushCube, pull pose instead of push pose)
+    pull_mod = load("mani_skill.envs.tasks.tabletop.pull_cube", "mani_skill/envs/tasks/tabletop/pull_cube.py")
+    PL = pull_mod.PullCubeEnv
+    tcp_pl = tcp_raw3.clone()
+    tcp_pl[4:8, :3] = obj_p[4:8] + torch.tensor([0.03, 0.0, 0.0]) + torch.randn(4, 3, generator=g3) * 0.002   # at the pull pose
+    fake_pull = SimpleNamespace(obj=fake_push.obj, goal_region=fake_push.goal_region, agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(tcp_pl))),
+                                goal_radius=0.1, cube_half_size=0.02, device=torch.device("cpu"), obs_mode_struct=SimpleNamespace(use_state=True))
+    linfo = PL.evaluate(fake_pull)
+    G["pull_tcp"], G["pull_success"] = tcp_pl, linfo["success"]
+    G["pull_reward"] = PL.compute_dense_reward(fake_pull, None, None, linfo)
+    G["pull_extra_flat"] = common.flatten_state_dict(PL._get_obs_extra(fake_pull, linfo), use_torch=True)
     # ---- matrix_to_euler_angles (the IK step of the end-effector controllers, agents/controllers/utils/kinematics.py:233-236)
     g2 = torch.Generator().manual_seed(99)
     qe = torch.nn.functional.normalize(torch.randn(24, 4, generator=g2), dim=-1)

@@ -319,3 +319,13 @@ def test_reset_to_env_states_restores_a_saved_episode():
     assert torch.allclose(now[[0, 2]], flat_saved[[0, 2]], atol=1e-5)
     assert torch.allclose(now[1], moved[1], atol=1e-5)
     assert env.elapsed_steps.tolist()[0] == 0 and env.elapsed_steps.tolist()[1] == 9
+
+
+def test_pull_cube_reset_layout():
+    env = ms.make("PullCube-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert obs.shape == (3, 9 + 9 + 7 + 3 + 7)
+    cube, goal = env.obj.pose.p, env.goal_region.pose.p
+    assert torch.allclose(goal[:, :2], cube[:, :2] - torch.tensor([0.2, 0.0]), atol=1e-6)   # the goal lies towards the robot
+    o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert not info["success"].any() and torch.isfinite(r).all() and (r < 1).all()

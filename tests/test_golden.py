@@ -292,3 +292,16 @@ def test_vector_wrapper_metrics_and_auto_reset_match_the_reference():
         assert np.array_equal(ep["episode_len"].numpy(), G[f"vec_episode_len_{t}"])
         close(ep["reward"], G[f"vec_reward_{t}"])
         close(venv.returns, G[f"vec_returns_after_{t}"])
+
+
+def test_pull_cube_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/pull_cube.py:105-152 run by the reference's own code on the same synthetic states."""
+    from maniskill_b200.envs.pull_cube import PullCubeEnv as PL
+    m = len(G["pull_success"])
+    goal = Pose(torch.hstack([T("push_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(obj=SimpleNamespace(pose=Pose(T("push_obj"))), goal_region=SimpleNamespace(pose=goal),
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("pull_tcp")))), goal_radius=0.1, cube_half_size=0.02, obs_mode="state")
+    info = PL.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["pull_success"])
+    close(PL.compute_dense_reward(fake, None, None, info), G["pull_reward"], 2e-6)
+    close(U.flatten_state_dict(PL._get_obs_extra(fake, info)), G["pull_extra_flat"], 1e-6)
