@@ -238,3 +238,51 @@ def test_mimic_tendon_keeps_the_fingers_mirrored():
     q = w.get_joint("qpos")[0]
     assert abs(q[7] - q[8]) < 2e-3, q[7:]
     assert 0.005 < q[7] < 0.035  # the two drives (one closing, one holding open) balance through the tendon
+
+
+@pytest.mark.parametrize("support", ["plane", "box"])
+def test_sliding_ball_ends_up_rolling_at_five_sevenths_of_its_speed(support):
+    """A solid sphere thrown along the ground without spin: Coulomb friction at the contact point slows the centre and spins the
+    ball up until v = omega r, which for I = 2/5 m r^2 happens at v = 5/7 v0, and from then on nothing changes (no rolling
+    resistance, like PhysX).  Checks the friction rows' lever arm / angular coupling and the sphere paths of the narrowphase."""
+    r, v0 = 0.035, 1.0
+    s = SceneDesc(1, SimParams())
+    if support == "plane":
+        ground(s, mu=0.3)
+    else:
+        s.add_actor(ActorRec("slab", "static", [ShapeRec(SHAPE_BOX, pose7(), np.array([4.0, 1.0, 0.1]), mu=0.3)], pose7([1.5, 0, -0.1])))
+    s.add_actor(ActorRec("ball", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([r, 0, 0]), mu=0.3)], pose7([0, 0, r]), angular_damping=0.0))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    b = w.get_bodies()
+    b[0, 0, 7] = v0
+    w.set_bodies(b)
+    w.step(150)   # sliding lasts v0 * 2 / (7 mu g) = 0.1 s; 1.5 s is long after
+    b = w.get_bodies()[0, 0]
+    assert b[7] == pytest.approx(5.0 / 7.0 * v0, rel=2e-2), b[7:]
+    assert b[11] == pytest.approx(b[7] / r, rel=2e-2)            # omega_y = v / r: rolling without slipping
+    assert abs(b[2] - r) < 1e-3 and abs(b[8]) < 1e-3 and abs(b[1]) < 1e-3
+    v_before = b[7]
+    w.step(50)
+    assert w.get_bodies()[0, 0, 7] == pytest.approx(v_before, rel=5e-3)   # steady rolling
+
+
+def test_torsional_friction_of_a_spinning_box():
+    """Torsional row of a friction patch: a box spinning about the vertical on the ground is braked by the torque mu N r_eff, r_eff =
+    mean distance of the patch points from their centroid (here the four bottom corners: L / sqrt 2)."""
+    L, w0, mu = 0.1, 5.0, 0.3
+    s = SceneDesc(1, SimParams())
+    ground(s, mu=mu)
+    s.add_actor(ActorRec("box", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([L / 2] * 3), mu=mu)], pose7([0, 0, L / 2]), angular_damping=0.0))
+    cm = s.compile()
+    w = OracleWorld(cm, "f64")
+    w.step(20)  # settle
+    b = w.get_bodies()
+    b[0, 0, 12] = w0
+    w.set_bodies(b)
+    alpha = mu * G * (L / np.sqrt(2)) / (L * L / 6)   # mu m g r_eff / (m L^2 / 6)
+    w.step(2)
+    assert w.get_bodies()[0, 0, 12] == pytest.approx(w0 - alpha * 2 * DT, rel=3e-2)
+    w.step(10)
+    b = w.get_bodies()[0, 0]
+    assert abs(b[12]) < 1e-3 and np.abs(b[7:10]).max() < 1e-3   # stopped, and stays where it was
