@@ -87,3 +87,38 @@ def test_emu_edge_models_match_oracle(idx):
     if cm.scalars["n_dof"]:
         assert np.abs(e.qpos.astype(np.float64) - o.get_joint("qpos")).max() < 2e-5
     assert e.overflow() == 0
+
+
+class _EmuAsOracle:
+    """The few OracleWorld calls the known-answer tests use, on top of the emulated device code (pipelined substep)."""
+
+    def __init__(self, cm):
+        from emu import EmuWorld
+        self.cm, self.w = cm, EmuWorld(cm)
+        self.nl = cm.scalars["n_link"]
+
+    def get_bodies(self):
+        self.w.fetch()
+        return self.w.rigid_body_data[:, self.nl:].astype(np.float64).copy()
+
+    def set_bodies(self, b):
+        self.w.rigid_body_data[:, self.nl:] = b
+        self.w.apply()
+
+    def step(self, n):
+        self.w.step(n, 0)
+
+    def pair_impulse(self, a, b):
+        return self.w.pair_impulse(a, b).astype(np.float64)
+
+
+def test_device_code_reproduces_the_analytic_answers_directly(monkeypatch):
+    """Three of the known-answer tests of tests/test_oracle_kat.py run on the emulated DEVICE code instead of the oracle: the ball
+    that ends up rolling at 5/7 v0, the stack of three boxes carrying 3 m g, the cooked cylinder resting on a box."""
+    import test_oracle_kat as K
+    monkeypatch.setattr(K, "OracleWorld", lambda cm, precision="f64": _EmuAsOracle(cm))
+    K.test_sliding_ball_ends_up_rolling_at_five_sevenths_of_its_speed("box")
+    K.test_sliding_ball_ends_up_rolling_at_five_sevenths_of_its_speed("plane")
+    K.test_stack_of_three_boxes_stays_put()
+    K.test_cooked_cylinder_rests_on_a_facet_and_weighs_mg("box", True)
+    K.test_torsional_friction_of_a_spinning_box()
