@@ -418,8 +418,6 @@ B2S_HDN inline void collide_env(const DevModel& M, const DevState& St, int env, 
 template <class C>
 B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
   const size_t N = M.n_envs;
-  const int nd = M.n_dof;
-  const float dt = M.dt;
   int ovf = 0;
   int n_man = 0, n_points = 0;
   int man_sa[C::MAXMAN], man_sb[C::MAXMAN], man_np[C::MAXMAN];
