@@ -40,44 +40,51 @@ class SerialChain:
             if kind:
                 self.joint_names.append(j["name"])
         t = lambda a: torch.tensor(a, dtype=dtype, device=device)
-        self.origin_p, self.origin_q, self.axis = t(self._origin_p), t(self._origin_q), t(self._axis)
+        self.origin_p = t(self._origin_p)                       # [n_elem, 3]
+        self.origin_R = U.quat_to_matrix(t(self._origin_q))      # [n_elem, 3, 3]
+        self.axis = t(self._axis)                                # [n_elem, 3]
+        moving = [i for i, k in enumerate(self._kind) if k]
+        ax = self.axis[moving] if moving else torch.zeros((0, 3), dtype=dtype, device=device)
+        K = torch.zeros((len(moving), 3, 3), dtype=dtype, device=device)   # cross-product matrices of the joint axes
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+        self._K, self._K2 = K, K @ K
+        self._revolute = torch.tensor([self._kind[i] == 1 for i in moving], dtype=torch.bool, device=device)
+        self._eye = torch.eye(3, dtype=dtype, device=device)
         self.n_joints = len(self.joint_names)
         self.device, self.dtype = device, dtype
 
     def forward(self, q: torch.Tensor):
-        """q [B, n_joints] -> end-link position [B,3], quaternion [B,4] and the Jacobian [B, 6, n_joints] in the root frame
-        (rows 0-2: linear velocity of the end-link origin, rows 3-5: angular velocity), pytorch_kinematics convention."""
+        """q [B, n_joints] -> end-link position [B,3], rotation matrix [B,3,3] and the Jacobian [B, 6, n_joints] in the root frame
+        (rows 0-2: linear velocity of the end-link origin, rows 3-5: angular velocity), pytorch_kinematics convention.
+        Rotations of all revolute joints are built at once (Rodrigues: I + sin K + (1 - cos) K^2); the walk down the chain is then
+        a handful of small batched matrix products per joint."""
         B = q.shape[0]
+        s, c = torch.sin(q), torch.cos(q)
+        Rj = self._eye + s[..., None, None] * self._K + (1.0 - c)[..., None, None] * self._K2   # [B, n_joints, 3, 3]
         p = torch.zeros((B, 3), dtype=self.dtype, device=self.device)
-        r = torch.zeros((B, 4), dtype=self.dtype, device=self.device)
-        r[:, 0] = 1.0
-        joint_p, joint_axis, joint_kind = [], [], []
+        R = self._eye.expand(B, 3, 3)
+        joint_p, joint_axis = [], []
         k = 0
         for i, kind in enumerate(self._kind):
-            # joint frame = parent link frame * origin
-            p = p + U.quat_apply(r, self.origin_p[i].expand(B, 3))
-            r = U.quat_mul(r, self.origin_q[i].expand(B, 4))
+            p = p + R @ self.origin_p[i]          # joint frame = parent link frame * origin
+            R = R @ self.origin_R[i]
             if kind == 0:
                 continue
-            axis_w = U.quat_apply(r, self.axis[i].expand(B, 3))
+            axis_w = R @ self.axis[i]
             joint_p.append(p)
             joint_axis.append(axis_w)
-            joint_kind.append(kind)
             if kind == 1:
-                half = 0.5 * q[:, k:k + 1]
-                dq = torch.cat([torch.cos(half), torch.sin(half) * self.axis[i]], dim=1)
-                r = U.quat_mul(r, dq)
+                R = R @ Rj[:, k]
             else:
                 p = p + axis_w * q[:, k:k + 1]
             k += 1
-        cols = []
-        for jp, ja, kind in zip(joint_p, joint_axis, joint_kind):
-            if kind == 1:
-                cols.append(torch.cat([torch.linalg.cross(ja, p - jp, dim=-1), ja], dim=1))
-            else:
-                cols.append(torch.cat([ja, torch.zeros_like(ja)], dim=1))
-        J = torch.stack(cols, dim=2) if cols else torch.zeros((B, 6, 0), dtype=self.dtype, device=self.device)
-        return p, r, J
+        if not joint_p:
+            return p, R, torch.zeros((B, 6, 0), dtype=self.dtype, device=self.device)
+        JP, JA = torch.stack(joint_p, dim=2), torch.stack(joint_axis, dim=2)        # [B, 3, n]
+        lin_rev = torch.linalg.cross(JA, p.unsqueeze(2) - JP, dim=1)
+        rev = self._revolute
+        J = torch.cat([torch.where(rev, lin_rev, JA), torch.where(rev, JA, torch.zeros_like(JA))], dim=1)
+        return p, R, J
 
 
 class Kinematics:
@@ -96,8 +103,9 @@ class Kinematics:
         self.device = device
 
     def fk(self, qpos: torch.Tensor):
-        p, r, _ = self.chain.forward(qpos[:, self.chain_dof_idx])
-        return p, r
+        """End-link position and wxyz quaternion in the root frame."""
+        p, R, _ = self.chain.forward(qpos[:, self.chain_dof_idx])
+        return p, U.matrix_to_quat(R)
 
     def compute_ik(self, delta_pose: torch.Tensor, q0: torch.Tensor, solver_config: dict):
         """delta_pose [B,6] = (translation, XYZ Euler rotation) of the end link in the root frame; q0 [B, dof] full qpos.

@@ -34,16 +34,16 @@ def test_chain_fk_matches_the_simulator_and_jacobian_matches_finite_differences(
     # geometric Jacobian (linear rows, then angular) against central differences of the chain itself, in float64
     chain = SerialChain(load_robot("panda_v2"), "panda_hand_tcp", "cpu", torch.float64)
     q64 = q[:, kin.chain_dof_idx].double()
-    p0, r0, J = chain.forward(q64)
+    p0, R0, J = chain.forward(q64)
     eps = 1e-6
     for j in range(chain.n_joints):
         dq = torch.zeros_like(q64)
         dq[:, j] = eps
-        pp, rp, _ = chain.forward(q64 + dq)
-        pm, rm, _ = chain.forward(q64 - dq)
+        pp, Rp, _ = chain.forward(q64 + dq)
+        pm, Rm, _ = chain.forward(q64 - dq)
         lin = (pp - pm) / (2 * eps)
-        dr = U.quat_mul(rp, U.quat_conj(rm))          # rotation between the two perturbed frames, root frame
-        ang = 2 * dr[:, 1:] / (2 * eps)               # small-angle: vector part = half the rotation vector
+        dR = Rp @ Rm.transpose(1, 2)                  # rotation between the two perturbed frames, root frame
+        ang = torch.stack([dR[:, 2, 1] - dR[:, 1, 2], dR[:, 0, 2] - dR[:, 2, 0], dR[:, 1, 0] - dR[:, 0, 1]], 1) / 2 / (2 * eps)  # small angle
         assert torch.allclose(J[:, :3, j], lin, atol=1e-6), j
         assert torch.allclose(J[:, 3:, j], ang, atol=1e-6), j
 
