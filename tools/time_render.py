@@ -1,9 +1,11 @@
-"""Times env.step with visual observations + the raster kernel alone."""
+"""Times env.step with visual observations + the raster kernel alone: python tools/time_render.py [task] [obs_mode] [num_envs]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import maniskill_b200 as ms
-task, mode, N = sys.argv[1], sys.argv[2], int(sys.argv[3])
+task = sys.argv[1] if len(sys.argv) > 1 else "PickCube-v1"
+mode = sys.argv[2] if len(sys.argv) > 2 else "rgbd"
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 env = ms.make(task, num_envs=N, obs_mode=mode)
 venv = ms.ManiSkillVectorEnv(env)
 venv.reset(seed=0)
