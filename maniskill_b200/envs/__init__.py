@@ -18,3 +18,12 @@ register_env("StackCube-v1", max_episode_steps=50)(StackCubeEnv)
 from .pull_cube import PullCubeEnv
 
 register_env("PullCube-v1", max_episode_steps=50)(PullCubeEnv)
+from .lift_peg_upright import LiftPegUprightEnv
+
+register_env("LiftPegUpright-v1", max_episode_steps=50)(LiftPegUprightEnv)
+from .poke_cube import PokeCubeEnv
+
+register_env("PokeCube-v1", max_episode_steps=50)(PokeCubeEnv)
+from .roll_ball import RollBallEnv
+
+register_env("RollBall-v1", max_episode_steps=80)(RollBallEnv)

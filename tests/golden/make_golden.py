@@ -21,6 +21,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/push_cube.py:179-241  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/pull_cube.py:105-152  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
+  mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137, poke_cube.py:126-276, roll_ball.py:130-189  the same three functions
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -456,6 +457,80 @@ def main():
     qe = torch.nn.functional.normalize(qe, dim=-1)
     G["eul_q"] = qe
     G["eul_xyz_from_matrix"] = rc.matrix_to_euler_angles(rc.quaternion_to_matrix(qe), "XYZ")
+    # ---- LiftPegUpright / PokeCube / RollBall task logic on synthetic states (own generator: the sections above keep their draws)
+    g4 = torch.Generator().manual_seed(777)
+    rnd_q = lambda k: torch.nn.functional.normalize(torch.randn(k, 4, generator=g4), dim=-1)
+    lift_mod = load("mani_skill.envs.tasks.tabletop.lift_peg_upright", "mani_skill/envs/tasks/tabletop/lift_peg_upright.py")
+    LP = lift_mod.LiftPegUprightEnv
+    m = 12
+    # lying (the reset pose), upright (tipped about world y, a little wobble) and arbitrary pegs
+    q_lie = torch.tensor([0.5 ** 0.5, 0.5 ** 0.5, 0.0, 0.0]).expand(m, 4)
+    tip = torch.tensor([0.5 ** 0.5, 0.0, -(0.5 ** 0.5), 0.0]).expand(m, 4)
+    wob = torch.nn.functional.normalize(torch.hstack([torch.ones(m, 1), torch.randn(m, 3, generator=g4) * 0.02]), dim=-1)
+    q_up = rc.quaternion_multiply(wob, rc.quaternion_multiply(tip, q_lie))
+    peg_q = torch.vstack([q_lie[:3], q_up[3:9], rnd_q(3)])
+    peg_p = torch.hstack([torch.randn(m, 2, generator=g4) * 0.1, torch.full((m, 1), 0.025)])
+    peg_p[3:9, 2] = 0.12 + torch.tensor([0.0, 0.001, -0.002, 0.004, 0.006, 0.0])
+    peg_raw = torch.hstack([peg_p, peg_q])
+    tcp_lp = torch.hstack([peg_p + torch.randn(m, 3, generator=g4) * 0.05, rnd_q(m)])
+    grasp_lp = torch.rand(m, generator=g4) < 0.4
+    peg_ns = SimpleNamespace(pose=Pose.create(peg_raw))
+    fake_lp = SimpleNamespace(peg=peg_ns, peg_half_length=0.12, device=torch.device("cpu"), obs_mode_struct=SimpleNamespace(use_state=True),
+                              agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(tcp_lp)), is_grasping=lambda o: grasp_lp.clone()))
+    pinfo = LP.evaluate(fake_lp)
+    G["lift_peg"], G["lift_tcp"], G["lift_grasp"], G["lift_success"] = peg_raw, tcp_lp, grasp_lp, pinfo["success"]
+    G["lift_reward"] = LP.compute_dense_reward(fake_lp, None, None, pinfo)
+    G["lift_extra_flat"] = common.flatten_state_dict(LP._get_obs_extra(fake_lp, pinfo), use_torch=True)
+    # PokeCube
+    poke_mod = load("mani_skill.envs.tasks.tabletop.poke_cube", "mani_skill/envs/tasks/tabletop/poke_cube.py")
+    PK = poke_mod.PokeCubeEnv
+    yaw_q = lambda a: torch.stack([torch.cos(a / 2), torch.zeros_like(a), torch.zeros_like(a), torch.sin(a / 2)], dim=1)
+    pk_peg_yaw = torch.randn(m, generator=g4) * 0.2
+    pk_cube_yaw = pk_peg_yaw + torch.randn(m, generator=g4) * 0.06     # aligned within 0.05 rad for some, not for others
+    pk_peg_p = torch.hstack([torch.randn(m, 2, generator=g4) * 0.1, torch.full((m, 1), 0.025)])
+    pk_cube_p = pk_peg_p + torch.hstack([0.12 + torch.rand(m, 1, generator=g4) * 0.06, torch.randn(m, 1, generator=g4) * 0.01, torch.full((m, 1), -0.005)])
+    pk_goal_p = torch.hstack([pk_cube_p[:, :2] + torch.randn(m, 2, generator=g4) * 0.06, torch.full((m, 1), 1e-3)])
+    pk_peg_raw, pk_cube_raw = torch.hstack([pk_peg_p, yaw_q(pk_peg_yaw)]), torch.hstack([pk_cube_p, yaw_q(pk_cube_yaw)])
+    pk_tcp = torch.hstack([pk_peg_p + torch.randn(m, 3, generator=g4) * 0.02, rnd_q(m)])
+    pk_tcp[:6, :3] = pk_peg_p[:6] + torch.randn(6, 3, generator=g4) * 0.002    # within the 1 cm "reached" ball
+    pk_grasp = torch.rand(m, generator=g4) < 0.6
+    pk_static = torch.rand(m, generator=g4) < 0.7
+    pk_static[0] = False   # a placed cube with the arm still moving
+    pk_qvel = torch.randn(m, 9, generator=g4) * 0.1
+    fake_pk = SimpleNamespace(cube=SimpleNamespace(pose=Pose.create(pk_cube_raw)), peg=SimpleNamespace(pose=Pose.create(pk_peg_raw)),
+                              goal_region=SimpleNamespace(pose=Pose.create_from_pq(pk_goal_p)), goal_radius=0.05, cube_half_size=0.02,
+                              peg_head_offsets=Pose.create_from_pq(p=[0.12, 0, 0]), device=torch.device("cpu"), obs_mode_struct=SimpleNamespace(use_state=True),
+                              agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(pk_tcp)), is_grasping=lambda o: pk_grasp.clone(),
+                                                    is_static=lambda t: pk_static.clone(), robot=SimpleNamespace(get_qvel=lambda: pk_qvel)))
+    fake_pk.peg_head_pos = PK.peg_head_pos.fget(fake_pk)
+    fake_pk.peg_head_pose = PK.peg_head_pose.fget(fake_pk)
+    kinfo = PK.evaluate(fake_pk)
+    G["poke_peg"], G["poke_cube"], G["poke_goal"], G["poke_tcp"] = pk_peg_raw, pk_cube_raw, pk_goal_p, pk_tcp
+    G["poke_grasp"], G["poke_static"], G["poke_qvel"] = pk_grasp, pk_static, pk_qvel
+    for k_ in ("success", "is_cube_placed", "is_peg_cube_fit", "is_peg_grasped", "angle_diff", "head_to_cube_dist"):
+        G[f"poke_{k_}"] = kinfo[k_]
+    G["poke_reward"] = PK.compute_dense_reward(fake_pk, None, None, kinfo)
+    G["poke_extra_flat"] = common.flatten_state_dict(PK._get_obs_extra(fake_pk, kinfo), use_torch=True)
+    # RollBall (reached_status latches inside compute_dense_reward)
+    roll_mod = load("mani_skill.envs.tasks.tabletop.roll_ball", "mani_skill/envs/tasks/tabletop/roll_ball.py")
+    RB = roll_mod.RollBallEnv
+    rb_ball = torch.hstack([torch.randn(m, 2, generator=g4) * 0.3, torch.full((m, 1), 0.035), rnd_q(m)])
+    rb_goal = torch.hstack([rb_ball[:, :2] + torch.randn(m, 2, generator=g4) * 0.5, torch.full((m, 1), 1e-3)])
+    rb_goal[:3, :2] = rb_ball[:3, :2] + 0.03
+    unit = torch.nn.functional.normalize(rb_ball[:, :3] - rb_goal, dim=1)
+    rb_tcp = torch.hstack([rb_ball[:, :3] + torch.randn(m, 3, generator=g4) * 0.2, rnd_q(m)])
+    rb_tcp[3:7, :3] = rb_ball[3:7, :3] + unit[3:7] * 0.085 + torch.randn(4, 3, generator=g4) * 0.01    # at the hit point
+    rb_vel = torch.randn(m, 3, generator=g4)
+    rb_status0 = (torch.rand(m, generator=g4) < 0.3).float()
+    fake_rb = SimpleNamespace(ball=SimpleNamespace(pose=Pose.create(rb_ball), linear_velocity=rb_vel), goal_region=SimpleNamespace(pose=Pose.create_from_pq(rb_goal)),
+                              goal_radius=0.1, ball_radius=0.035, reached_status=rb_status0.clone(), device=torch.device("cpu"),
+                              obs_mode_struct=SimpleNamespace(use_state=True), agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(rb_tcp))))
+    binfo = RB.evaluate(fake_rb)
+    G["roll_ball"], G["roll_goal"], G["roll_tcp"], G["roll_vel"], G["roll_status0"] = rb_ball, rb_goal, rb_tcp, rb_vel, rb_status0
+    G["roll_success"] = binfo["success"]
+    G["roll_reward"] = RB.compute_dense_reward(fake_rb, None, None, binfo)
+    G["roll_status1"] = fake_rb.reached_status.clone()
+    G["roll_extra_flat"] = common.flatten_state_dict(RB._get_obs_extra(fake_rb, binfo), use_torch=True)
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

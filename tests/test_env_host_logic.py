@@ -329,3 +329,94 @@ def test_pull_cube_reset_layout():
     assert torch.allclose(goal[:, :2], cube[:, :2] - torch.tensor([0.2, 0.0]), atol=1e-6)   # the goal lies towards the robot
     o, r, te, tr, info = env.step(torch.zeros(3, 8))
     assert not info["success"].any() and torch.isfinite(r).all() and (r < 1).all()
+
+
+def test_lift_peg_upright_reset_and_an_upright_peg_counts_as_success():
+    """LiftPegUpright-v1 (lift_peg_upright.py): the peg starts lying along the world x axis rolled a quarter turn about it, 32-dim state
+    observation, and that peg tipped up about the world y axis and set down on its small face settles and is reported upright (the
+    reference reads the third XYZ Euler angle, which is +-pi/2 for every upright pose reached this way)."""
+    from maniskill_b200 import utils as U
+    from maniskill_b200.structs import Pose
+    env = ms.make("LiftPegUpright-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=1)
+    assert obs.shape == (3, 9 + 9 + 7 + 7)
+    p, q = env.peg.pose.p, env.peg.pose.q
+    assert (p[:, :2].abs() <= 0.1 + 1e-6).all() and torch.allclose(p[:, 2], torch.full((3,), 0.025))
+    assert torch.allclose(q, torch.tensor([0.5 ** 0.5, 0.5 ** 0.5, 0.0, 0.0]).expand(3, 4), atol=1e-6)
+    o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert not info["success"].any() and (r < 1).all() and torch.isfinite(r).all()
+    up = env.peg.pose.raw_pose.clone()
+    up[:, 0] += 0.2   # clear of the gripper, which hovers above the spawn area
+    up[:, 2] = 0.121
+    tip = torch.tensor([0.5 ** 0.5, 0.0, -(0.5 ** 0.5), 0.0]).expand(3, 4)  # about world y: +x (the long axis) to +z
+    up[:, 3:] = U.quat_mul(tip, q)
+    env.peg.set_pose(Pose(up))
+    env.scene._gpu_apply_all()
+    for _ in range(10):
+        o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert info["success"].all() and torch.allclose(r, torch.ones(3))
+    assert (env.peg.pose.p[:, 2] - 0.12).abs().max() < 2e-3
+
+
+def test_poke_cube_reset_layout_and_a_cube_in_the_goal():
+    """PokeCube-v1 (poke_cube.py): peg, cube and goal are laid out along +x (cube 10 cm beyond the peg head, goal 10 cm beyond the cube),
+    the cube's yaw stays within +-30 degrees, 54-dim state observation; a cube moved into the goal with the arm at rest is a success."""
+    from maniskill_b200.structs import Pose
+    env = ms.make("PokeCube-v1", num_envs=4, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=3)
+    assert obs.shape == (4, 9 + 9 + 7 + 7 + 7 + 3 * 5)
+    peg, cube, goal = env.peg.pose.p, env.cube.pose.p, env.goal_region.pose.p
+    assert torch.allclose(cube[:, 0], peg[:, 0] + 0.22, atol=1e-6) and (cube[:, 1].abs() <= 0.1 + 1e-6).all()
+    assert torch.allclose(goal[:, :2], cube[:, :2] + torch.tensor([0.1, 0.0]), atol=1e-6)
+    yaw = 2 * torch.atan2(env.cube.pose.q[:, 3], env.cube.pose.q[:, 0])
+    assert (yaw.abs() <= np.pi / 6 + 1e-5).all() and torch.allclose(env.cube.pose.q[:, 1:3], torch.zeros(4, 2), atol=1e-6)
+    assert torch.allclose(env.peg_head_pos, peg + torch.tensor([0.12, 0.0, 0.0]))
+    o, r, te, tr, info = env.step(torch.zeros(4, 8))
+    assert not info["success"].any() and not info["is_peg_grasped"].any() and (r < 0.2).all()
+    assert torch.allclose(info["head_to_cube_dist"], torch.linalg.norm((env.peg_head_pos - env.cube.pose.p)[:, :2], dim=1))
+    moved = env.cube.pose.raw_pose.clone()
+    moved[:, :2] = env.goal_region.pose.p[:, :2] + 0.01
+    env.cube.set_pose(Pose(moved))
+    env.scene._gpu_apply_all()
+    for _ in range(3):
+        o, r, te, tr, info = env.step(torch.zeros(4, 8))
+    assert info["is_cube_placed"].all() and info["success"].all() and torch.allclose(r, torch.ones(4))
+
+
+def test_roll_ball_reset_layout_stateful_reward_and_a_rolling_ball():
+    """RollBall-v1 (roll_ball.py): robot at the side of the table, ball in front of it, goal at the far end, 44-dim state observation;
+    `reached_status` latches once the TCP has been at the hit point and is cleared by a (partial) reset; a ball given a push towards
+    the goal rolls there (sphere on plane: rolling, not sliding) and is reported as success."""
+    env = ms.make("RollBall-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=2)
+    assert obs.shape == (3, 9 + 9 + 7 + 3 + 7 + 3 + 3 + 3)
+    ball, goal = env.ball.pose.p.clone(), env.goal_region.pose.p.clone()
+    assert ((ball[:, 0] + 0.1).abs() <= 0.3 + 1e-6).all() and (ball[:, 1] >= 0.5).all() and (ball[:, 1] <= 0.7).all()
+    assert ((goal[:, 0] + 0.1).abs() <= 0.3 + 1e-6).all() and (goal[:, 1] >= -0.9).all() and (goal[:, 1] <= -0.7).all()
+    assert torch.allclose(env.agent.robot.pose.p, torch.tensor([-0.1, 1.0, 0.0]).expand(3, 3))
+    tcp = env.agent.tcp.pose.p
+    assert (tcp[:, 1] < 0.6).all() and (tcp[:, 1] > 0.2).all()   # the arm reaches over the table towards -y
+    o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert (env.reached_status == 0).all() and (r < 1 / 30).all() and (r > 0).all()
+    # latch: pretend the TCP was at the hit point of env 1
+    env.reached_status[1] = 1.0
+    o, r2, te, tr, info = env.step(torch.zeros(3, 8))
+    d = torch.linalg.norm((env.ball.pose.p - env.goal_region.pose.p)[:, :2], dim=1)
+    assert torch.allclose(r2[1], (20 * (1 - torch.tanh(d[1])) + 1) / 30, atol=1e-5) and torch.allclose(r2[[0, 2]], r[[0, 2]], atol=1e-3)
+    env.reset(options=dict(env_idx=torch.tensor([1])))
+    assert (env.reached_status == 0).all()
+    # roll the balls at the goals
+    ball, goal = env.ball.pose.p, env.goal_region.pose.p
+    dirn = (goal - ball)[:, :2]
+    dist = torch.linalg.norm(dirn, dim=1, keepdim=True)
+    v = torch.zeros(3, 3)
+    v[:, :2] = dirn / dist * 1.5
+    env.ball.set_linear_velocity(v)
+    env.scene._gpu_apply_all()
+    hit = torch.zeros(3, dtype=torch.bool)
+    for _ in range(60):
+        o, r, te, tr, info = env.step(torch.zeros(3, 8))
+        hit |= info["success"]
+    assert hit.all(), (env.ball.pose.p, env.goal_region.pose.p)
+    w = env.ball.angular_velocity
+    assert (torch.linalg.norm(w, dim=1) > 1.0).any() or (torch.linalg.norm(env.ball.linear_velocity, dim=1) < 0.05).all()

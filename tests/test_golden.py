@@ -305,3 +305,58 @@ def test_pull_cube_evaluate_reward_obs():
     assert np.array_equal(info["success"].numpy(), G["pull_success"])
     close(PL.compute_dense_reward(fake, None, None, info), G["pull_reward"], 2e-6)
     close(U.flatten_state_dict(PL._get_obs_extra(fake, info)), G["pull_extra_flat"], 1e-6)
+
+
+def test_lift_peg_upright_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137 run by the reference's own code on the same synthetic states
+    (lying, upright within and outside the height band, arbitrary)."""
+    from maniskill_b200.envs.lift_peg_upright import LiftPegUprightEnv as LP
+    grasp = T("lift_grasp")
+    peg = SimpleNamespace(pose=Pose(T("lift_peg")))
+    fake = SimpleNamespace(peg=peg, peg_half_length=0.12, obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("lift_tcp"))), is_grasping=lambda o: grasp))
+    info = LP.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["lift_success"])
+    assert G["lift_success"].any() and not G["lift_success"].all()
+    close(LP.compute_dense_reward(fake, None, None, info), G["lift_reward"], 2e-6)
+    close(U.flatten_state_dict(LP._get_obs_extra(fake, info)), G["lift_extra_flat"], 1e-6)
+
+
+def test_poke_cube_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/poke_cube.py:126-276 run by the reference's own code on the same synthetic states; all reward
+    branches occur (reaching, grasped, peg fitted to the cube, cube placed with a moving arm, success)."""
+    from maniskill_b200.envs.poke_cube import PokeCubeEnv as PK
+    m = len(G["poke_success"])
+    grasp, static, qvel = T("poke_grasp"), T("poke_static"), T("poke_qvel")
+    goal = Pose(torch.hstack([T("poke_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(cube=SimpleNamespace(pose=Pose(T("poke_cube"))), peg=SimpleNamespace(pose=Pose(T("poke_peg"))), goal_region=SimpleNamespace(pose=goal),
+                           goal_radius=0.05, cube_half_size=0.02, peg_head_offsets=Pose.create_from_pq(torch.tensor([[0.12, 0.0, 0.0]])), obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("poke_tcp"))), is_grasping=lambda o: grasp, is_static=lambda t: static,
+                                                 robot=SimpleNamespace(get_qvel=lambda: qvel)))
+    fake.peg_head_pos = PK.peg_head_pos.fget(fake)
+    fake.peg_head_pose = PK.peg_head_pose.fget(fake)
+    info = PK.evaluate(fake)
+    for k in ("success", "is_cube_placed", "is_peg_cube_fit", "is_peg_grasped"):
+        assert np.array_equal(info[k].numpy(), G[f"poke_{k}"]), k
+    close(info["angle_diff"], G["poke_angle_diff"], 2e-6)
+    close(info["head_to_cube_dist"], G["poke_head_to_cube_dist"], 1e-6)
+    ref = G["poke_reward"]
+    assert (ref == 10).any() and ((ref > 7) & (ref < 10)).any() and ((ref > 4) & (ref < 7)).any() and (ref < 4).any()
+    close(PK.compute_dense_reward(fake, None, None, info), ref, 5e-6)
+    close(U.flatten_state_dict(PK._get_obs_extra(fake, info)), G["poke_extra_flat"], 1e-6)
+
+
+def test_roll_ball_evaluate_reward_obs_and_the_latched_status():
+    """mani_skill/envs/tasks/tabletop/roll_ball.py:130-189 run by the reference's own code on the same synthetic states: the reward
+    latches `reached_status` for the envs whose TCP is at the hit point and uses the latched value in the same call."""
+    from maniskill_b200.envs.roll_ball import RollBallEnv as RB
+    m = len(G["roll_success"])
+    goal = Pose(torch.hstack([T("roll_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(ball=SimpleNamespace(pose=Pose(T("roll_ball")), linear_velocity=T("roll_vel")), goal_region=SimpleNamespace(pose=goal),
+                           goal_radius=0.1, ball_radius=0.035, reached_status=T("roll_status0").clone(), obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("roll_tcp")))))
+    info = RB.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["roll_success"])
+    close(RB.compute_dense_reward(fake, None, None, info), G["roll_reward"], 2e-5)
+    assert np.array_equal(fake.reached_status.numpy(), G["roll_status1"]) and (G["roll_status1"] != G["roll_status0"]).any()
+    close(U.flatten_state_dict(RB._get_obs_extra(fake, info)), G["roll_extra_flat"], 1e-6)
