@@ -30,7 +30,7 @@ class Scene:
 
     def __init__(self, world, cm: CompiledModel, desc: SceneDesc):
         self.world = world
-        self.px = world
+        self._px = None
         self.cm = cm
         self.num_envs = world.n_envs
         self.device = world.device
@@ -54,6 +54,22 @@ class Scene:
             qlim = cm.arrays["dof_limit"].reshape(-1, 2)[d0:d1]
             self.articulations[art.name] = Articulation(self, art.name, ai, cm.link_rows[art.name], cm.dof_names[art.name], qlim)
         self._query_cache = {}
+
+    @property
+    def px(self):
+        """`scene.px` of the reference (scene.py:61-63): the `PhysxGpuSystem`-shaped view of the world, built on first use."""
+        if self._px is None:
+            from ..physx_shim import PhysxGpuSystem
+            cm = self.cm
+            names = [""] * self.world.n_rows
+            for art, rows in cm.link_rows.items():
+                for link, r in rows.items():
+                    names[r] = f"{art}_{link}"
+            for act, r in cm.actor_rows.items():
+                if r >= 0:
+                    names[r] = act
+            self._px = PhysxGpuSystem(self.world, names, [(a, len(cm.dof_names[a])) for a in cm.art_index])
+        return self._px
 
     # ---- mani_skill/envs/scene.py:379-380
     def step(self, substeps=1, fetch_mask=0):
