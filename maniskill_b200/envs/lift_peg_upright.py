@@ -1,6 +1,6 @@
 """LiftPegUpright-v1 -- mirror of mani_skill/envs/tasks/tabletop/lift_peg_upright.py:20-137 on the b200sim backend.
 
-Table scene + a 24 x 5 x 5 cm two-colour peg lying along the world y axis; success when the peg stands on one of its small faces.
+Table scene + a 24 x 5 x 5 cm two-colour peg lying along the world x axis (rolled a quarter turn about it); success when the peg stands on one of its small faces.
 State observation 9 + 9 + 7 (tcp) + 7 (peg) = 32.  Task logic on the torch path.
 """
 from __future__ import annotations
@@ -8,9 +8,10 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import building as actors
 from .. import utils as U
 from ..agents import Panda
-from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
+from ..model import SHAPE_BOX, ShapeRec, pose7
 from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
 from ..structs import Pose
 from .base_env import BaseEnv
@@ -42,9 +43,8 @@ class LiftPegUprightEnv(BaseEnv):
 
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
-        self.scene_desc.add_actor(ActorRec("peg", "dynamic", twocolor_peg_shapes(self.peg_half_length, self.peg_half_width,
-                                                                                np.array([176, 14, 14, 255]) / 255, np.array([12, 42, 160, 255]) / 255),
-                                           pose7([0, 0, 0.1])))
+        actors.build_twocolor_peg(self.scene_desc, length=self.peg_half_length, width=self.peg_half_width, color_1=np.array([176, 14, 14, 255]) / 255,
+                                  color_2=np.array([12, 42, 160, 255]) / 255, name="peg", body_type="dynamic", initial_pose=actors.Pose(p=[0, 0, 0.1]))
 
     def _after_build(self):
         self.agent = Panda(self.scene, "panda")

@@ -8,13 +8,13 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import building as actors
 from .. import utils as U
 from ..agents import Panda
 from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
 from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
 from ..structs import Pose
 from .base_env import BaseEnv
-from .lift_peg_upright import twocolor_peg_shapes
 
 
 class PokeCubeEnv(BaseEnv):
@@ -38,10 +38,10 @@ class PokeCubeEnv(BaseEnv):
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
         h = self.cube_half_size
-        self.scene_desc.add_actor(ActorRec("cube", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([h, h, h]), color=(1, 0, 0, 1))], pose7([1, 0, h])))
+        actors.build_cube(self.scene_desc, half_size=h, color=[1, 0, 0, 1], name="cube", body_type="dynamic", initial_pose=actors.Pose(p=[1, 0, h]))
         blue = np.array([12, 42, 160, 255]) / 255
-        self.scene_desc.add_actor(ActorRec("peg", "dynamic", twocolor_peg_shapes(self.peg_half_length, self.peg_half_width, blue, blue),
-                                           pose7([0, 0, self.peg_half_width])))
+        actors.build_twocolor_peg(self.scene_desc, length=self.peg_half_length, width=self.peg_half_width, color_1=blue, color_2=blue, name="peg",
+                                  body_type="dynamic", initial_pose=actors.Pose(p=[0, 0, self.peg_half_width]))
         # red/white target of the reference (thin visual cylinders, kinematic): a flat square of the same extent stands in for it
         self.scene_desc.add_actor(ActorRec("goal_region", "kinematic",
                                            [ShapeRec(SHAPE_BOX, pose7(), np.array([1e-5, self.goal_radius, self.goal_radius]), color=(0.9, 0.1, 0.1, 1), collide=False)],

@@ -11,7 +11,8 @@ import torch
 
 from .. import utils as U
 from ..agents import Panda
-from ..model import SHAPE_BOX, SHAPE_SPHERE, ActorRec, ShapeRec, pose7
+from .. import building as actors
+from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
 from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
 from ..structs import Pose
 from .base_env import BaseEnv
@@ -35,8 +36,7 @@ class RollBallEnv(BaseEnv):
 
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
-        self.scene_desc.add_actor(ActorRec("ball", "dynamic", [ShapeRec(SHAPE_SPHERE, pose7(), np.array([self.ball_radius, 0, 0]), color=(0, 0.2, 0.8, 1))],
-                                           pose7([0, 0, 0.1])))
+        actors.build_sphere(self.scene_desc, radius=self.ball_radius, color=[0, 0.2, 0.8, 1], name="ball", initial_pose=actors.Pose(p=[0, 0, 0.1]))
         self.scene_desc.add_actor(ActorRec("goal_region", "kinematic",
                                            [ShapeRec(SHAPE_BOX, pose7(), np.array([1e-5, self.goal_radius, self.goal_radius]), color=(0.9, 0.1, 0.1, 1), collide=False)],
                                            pose7([0, 0, 0.1])))
