@@ -22,6 +22,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/pull_cube.py:105-152  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137, poke_cube.py:126-276, roll_ball.py:130-189  the same three functions
+  mani_skill/utils/structs/render_camera.py:77-155     get_extrinsic_matrix / get_model_matrix (GPU branch, mounted camera)
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -531,6 +532,21 @@ def main():
     G["roll_reward"] = RB.compute_dense_reward(fake_rb, None, None, binfo)
     G["roll_status1"] = fake_rb.reached_status.clone()
     G["roll_extra_flat"] = common.flatten_state_dict(RB._get_obs_extra(fake_rb, binfo), use_torch=True)
+    # ---- camera parameters (mani_skill/utils/structs/render_camera.py:77-155, GPU branch): extrinsic_cv and the GL model matrix
+    stub("mani_skill.render", SAPIEN_RENDER_SYSTEM="3.0")
+    for mname in ("mani_skill.utils.structs.actor", "mani_skill.utils.structs.link"):
+        if mname not in sys.modules:
+            stub(mname, Actor=object, Link=object)
+    rcam = load("mani_skill.utils.structs.render_camera", "mani_skill/utils/structs/render_camera.py")
+    mount_raw = torch.hstack([torch.randn(m, 3, generator=g4), rnd_q(m)])
+    local_raw = torch.hstack([torch.randn(1, 3, generator=g4) * 0.1, rnd_q(1)])
+    cam_global = Pose.create(mount_raw) * Pose.create(local_raw)
+    fake_cam = SimpleNamespace(scene=SimpleNamespace(gpu_sim_enabled=True, device=torch.device("cpu")), mount=object(), global_pose=cam_global,
+                               _cached_extrinsic_matrix=None, _cached_model_matrix=None)
+    fake_cam.get_global_pose = lambda: fake_cam.global_pose
+    G["cam_mount"], G["cam_local"] = mount_raw, local_raw
+    G["cam_extrinsic_cv"] = rcam.RenderCamera.get_extrinsic_matrix(fake_cam)
+    G["cam_model_gl"] = rcam.RenderCamera.get_model_matrix(fake_cam)
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

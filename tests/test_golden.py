@@ -360,3 +360,24 @@ def test_roll_ball_evaluate_reward_obs_and_the_latched_status():
     close(RB.compute_dense_reward(fake, None, None, info), G["roll_reward"], 2e-5)
     assert np.array_equal(fake.reached_status.numpy(), G["roll_status1"]) and (G["roll_status1"] != G["roll_status0"]).any()
     close(U.flatten_state_dict(RB._get_obs_extra(fake, info)), G["roll_extra_flat"], 1e-6)
+
+
+def test_camera_parameters_of_a_mounted_camera():
+    """mani_skill/utils/structs/render_camera.py:77-155 (GPU branch) on the same mount / local poses: `extrinsic_cv` [N,3,4] and
+    `cam2world_gl` [N,4,4] of `CameraSensors.get_params`; intrinsics follow RenderCameraComponent.set_fovy (fy = H/2 / tan(fov/2))."""
+    from maniskill_b200.render import CameraSensors, camera_desc
+    m = len(G["cam_mount"])
+    rows = 3
+    body_view = torch.zeros(m, rows, 13)
+    body_view[:, :, 3] = 1
+    body_view[:, 1, :7] = T("cam_mount")
+    cs = CameraSensors.__new__(CameraSensors)    # the parameter path needs no device: skip the camera-group creation
+    cs.cams = [camera_desc("hand_camera", G["cam_local"][0], 128, 96, np.pi / 2, 0.01, 100, mount_row=1)]
+    p = cs.get_params(body_view)["hand_camera"]
+    close(p["extrinsic_cv"], G["cam_extrinsic_cv"], 2e-6)
+    close(p["cam2world_gl"], G["cam_model_gl"], 2e-6)
+    K = p["intrinsic_cv"]
+    assert K.shape == (m, 3, 3) and np.allclose(K[0].numpy(), [[48.0, 0, 64], [0, 48.0, 48], [0, 0, 1]], atol=1e-4)
+    # a mounted camera is recomputed every call, a fixed one is cached
+    body_view[:, 1, 0] += 1.0
+    assert not torch.allclose(cs.get_params(body_view)["hand_camera"]["extrinsic_cv"], p["extrinsic_cv"])
