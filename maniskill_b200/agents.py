@@ -147,8 +147,9 @@ class PDEEPosController(PDJointPosController):
                 self._target_pose.raw_pose[env_idx] = cur[env_idx]
 
     def compute_target_pose(self, prev: Pose, action) -> Pose:
-        """pd_ee_pose.py:85-99 with frame root_translation: keep the rotation, translate in the root frame."""
-        return Pose(torch.hstack([prev.p + action[:, :3], prev.q]))
+        """pd_ee_pose.py:85-99 with frame root_translation: keep the rotation, translate in the root frame (`delta_pose * prev`: the
+        pose product standardises the quaternion to a non-negative real part, pose.py:199)."""
+        return Pose(torch.hstack([prev.p + action[:, :3], torch.where(prev.q[..., :1] < 0, -prev.q, prev.q)]))
 
     def _delta_from_target(self, target: Pose, current: Pose):
         """utils/kinematics.py:218-241: translation difference and XYZ Euler angles of target.q * current.q^-1."""

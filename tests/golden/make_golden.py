@@ -23,6 +23,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/stack_cube.py:115-200  evaluate, _get_obs_extra, compute_dense_reward
   mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137, poke_cube.py:126-276, roll_ball.py:130-189  the same three functions
   mani_skill/utils/structs/render_camera.py:77-155     get_extrinsic_matrix / get_model_matrix (GPU branch, mounted camera)
+  mani_skill/agents/controllers/pd_ee_pose.py:85-99,229-263, utils/kinematics.py:197-260  EE controllers: action scaling, target pose, GPU IK step
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -547,6 +548,43 @@ def main():
     G["cam_mount"], G["cam_local"] = mount_raw, local_raw
     G["cam_extrinsic_cv"] = rcam.RenderCamera.get_extrinsic_matrix(fake_cam)
     G["cam_model_gl"] = rcam.RenderCamera.get_model_matrix(fake_cam)
+    # ---- end-effector controllers (pd_ee_pose.py:85-99,229-263) and the GPU IK step (utils/kinematics.py:197-260) with a scripted Jacobian
+    stub("pytorch_kinematics")
+    stub("lxml", etree=MagicMock())
+    stub("lxml.etree")
+    stub("sapien.wrapper.pinocchio_model", PinocchioModel=object)
+    for mname, attrs in (("mani_skill.utils.structs.articulation", dict(Articulation=object)), ("mani_skill.utils.structs.articulation_joint", dict(ArticulationJoint=object))):
+        if mname not in sys.modules:
+            stub(mname, **attrs)
+    kin_mod = load("mani_skill.agents.controllers.utils.kinematics", "mani_skill/agents/controllers/utils/kinematics.py")
+    if not isinstance(getattr(sys.modules["mani_skill.utils"], "sapien_utils", None), types.ModuleType):
+        sys.modules["mani_skill.utils"].sapien_utils = MagicMock()
+    ee_mod = load("mani_skill.agents.controllers.pd_ee_pose", "mani_skill/agents/controllers/pd_ee_pose.py")
+    ne = 10
+    ee_act = torch.randn(ne, 6, generator=g4) * 0.8
+    ee_act[:3, 3:] *= 3.0                                   # rotation parts with norm > 1 are clipped by norm
+    # action_space_low/high: the bounds the normalised action is scaled to (panda.py: pos_lower/upper = -+0.1, rot_lower/upper = -+0.1)
+    ee_self = SimpleNamespace(action_space_low=torch.tensor([-0.1] * 6), action_space_high=torch.tensor([0.1] * 6),
+                              config=SimpleNamespace(rot_lower=-0.1, use_delta=True, frame="root_translation:root_aligned_body_rotation"))
+    ee_scaled = ee_mod.PDEEPoseController._clip_and_scale_action(ee_self, ee_act)
+    prev_raw = torch.hstack([torch.randn(ne, 3, generator=g4) * 0.3, rnd_q(ne)])
+    G["ee_act"], G["ee_scaled"], G["ee_prev"] = ee_act, ee_scaled, prev_raw
+    G["ee_target_pose"] = ee_mod.PDEEPoseController.compute_target_pose(ee_self, Pose.create(prev_raw), ee_scaled).raw_pose
+    pos_self = SimpleNamespace(config=SimpleNamespace(use_delta=True, frame="root_translation"))
+    G["ee_target_pos_only"] = ee_mod.PDEEPosController.compute_target_pose(pos_self, Pose.create(prev_raw), ee_scaled[:, :3]).raw_pose
+    J = torch.randn(ne, 6, 7, generator=g4)
+    q0 = torch.randn(ne, 9, generator=g4)
+    cur_raw = torch.hstack([prev_raw[:, :3] + torch.randn(ne, 3, generator=g4) * 0.02, rc.quaternion_multiply(
+        torch.nn.functional.normalize(torch.hstack([torch.ones(ne, 1), torch.randn(ne, 3, generator=g4) * 0.05]), dim=-1), prev_raw[:, 3:])])
+    kin_self = SimpleNamespace(use_gpu_ik=True, active_ancestor_joint_idxs=torch.arange(7), qmask=torch.ones(7, dtype=torch.bool), device=torch.device("cpu"),
+                               pk_chain=SimpleNamespace(jacobian=lambda q: J))
+    G["ee_J"], G["ee_q0"], G["ee_cur"] = J, q0, cur_raw
+    for sname, cfg in (("lm", dict(type="levenberg_marquardt", alpha=1.0)), ("pinv", dict(type="pseudo_inverse", alpha=0.5))):
+        # virtual-target path: a target Pose + the current pose; direct path: the scaled action as a 6-vector delta
+        G[f"ee_ik_target_{sname}"] = kin_mod.Kinematics.compute_ik(kin_self, Pose.create(G["ee_target_pose"]), q0, is_delta_pose=False,
+                                                                   current_pose=Pose.create(cur_raw), solver_config=cfg)
+        G[f"ee_ik_delta_{sname}"] = kin_mod.Kinematics.compute_ik(kin_self, ee_scaled.clone(), q0, is_delta_pose=True, current_pose=Pose.create(cur_raw),
+                                                                  solver_config=cfg)
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

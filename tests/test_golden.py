@@ -381,3 +381,28 @@ def test_camera_parameters_of_a_mounted_camera():
     # a mounted camera is recomputed every call, a fixed one is cached
     body_view[:, 1, 0] += 1.0
     assert not torch.allclose(cs.get_params(body_view)["hand_camera"]["extrinsic_cv"], p["extrinsic_cv"])
+
+
+def test_end_effector_controllers_and_the_ik_step_match_the_reference():
+    """mani_skill/agents/controllers/pd_ee_pose.py:85-99,229-263 (action clipping: rotation clipped by norm and scaled by `rot_lower`;
+    target pose in the frame root_translation[:root_aligned_body_rotation]) and utils/kinematics.py:197-260 (GPU branch: delta pose
+    from a target pose, damped least squares / pseudo-inverse on a given Jacobian), run by the reference's own code on the same inputs."""
+    from maniskill_b200.agents import PDEEPosController, PDEEPoseController
+    from maniskill_b200.kinematics import Kinematics
+    act, prev = T("ee_act"), Pose(T("ee_prev"))
+    fake = SimpleNamespace(normalize_action=True, action_low=torch.full((6,), -0.1), action_high=torch.full((6,), 0.1), rot_lower=-0.1)
+    scaled = PDEEPoseController._preprocess_action(fake, act)
+    close(scaled, G["ee_scaled"], 1e-6)
+    assert (np.linalg.norm(G["ee_scaled"][:, 3:], axis=1) <= 0.1 + 1e-6).all() and (np.linalg.norm(G["ee_act"][:3, 3:], axis=1) > 1).all()
+    close(PDEEPoseController.compute_target_pose(fake, prev, scaled).raw_pose, G["ee_target_pose"], 2e-6)
+    close(PDEEPosController.compute_target_pose(fake, prev, scaled[:, :3]).raw_pose, G["ee_target_pos_only"], 1e-6)
+    J, q0 = T("ee_J"), T("ee_q0")
+    kin = Kinematics.__new__(Kinematics)
+    kin.chain = SimpleNamespace(forward=lambda q: (None, None, J))
+    kin.chain_dof_idx, kin.qmask, kin.device = torch.arange(7), torch.ones(7, dtype=torch.bool), torch.device("cpu")
+    delta_t = PDEEPosController._delta_from_target(fake, Pose(T("ee_target_pose")), Pose(T("ee_cur")))
+    for name, cfg in (("lm", dict(type="levenberg_marquardt", alpha=1.0)), ("pinv", dict(type="pseudo_inverse", alpha=0.5))):
+        close(kin.compute_ik(delta_t, q0, cfg), G[f"ee_ik_target_{name}"], 2e-4)
+        close(kin.compute_ik(scaled, q0, cfg), G[f"ee_ik_delta_{name}"], 2e-4)
+    with pytest.raises(NotImplementedError):
+        kin.compute_ik(scaled, q0, dict(type="newton"))
