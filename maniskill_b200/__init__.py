@@ -11,5 +11,6 @@ CPU path.
 from .registration import make, register_env, REGISTERED_ENVS  # noqa: F401
 from . import envs  # noqa: F401  (registers the tasks)
 from .vector import ManiSkillVectorEnv  # noqa: F401
+from .trajectory import RecordEpisode, load_trajectories, replay_trajectory  # noqa: F401
 
 __version__ = "0.1.0"

@@ -230,6 +230,15 @@ class BaseEnv:
         return self._obs_mode
 
     @property
+    def reward_mode(self):
+        return self._reward_mode
+
+    @property
+    def control_mode(self) -> str:
+        """sapien_env.py `control_mode`: the agent's active control mode."""
+        return self.agent.control_mode
+
+    @property
     def elapsed_steps(self):
         return self._elapsed_steps
 

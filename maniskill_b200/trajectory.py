@@ -1,0 +1,289 @@
+"""Trajectory recording and replay: the on-disk format either side of the step path.
+
+Mirror of `RecordEpisode` (mani_skill/utils/wrappers/record.py:113-756, trajectory part; no video) and of the replay loop of
+mani_skill/trajectory/replay_trajectory.py:111-378.  The reference writes `<name>.h5` + `<name>.json`:
+
+    traj_<k>/obs                         [T+1, ...]  (dict observations become nested groups)
+    traj_<k>/actions                     [T, A] float32
+    traj_<k>/terminated, truncated       [T] bool        traj_<k>/success, fail  [T] bool (when the task reports them)
+    traj_<k>/rewards                     [T] float32     (record_reward)
+    traj_<k>/env_states/{actors,articulations}/<name>   [T+1, 13 | 13 + 2 dof]   (record_env_state)
+    json: env_info {env_id, max_episode_steps, env_kwargs}, source_type, source_desc,
+          episodes [{episode_id, episode_seed, control_mode, elapsed_steps, reset_kwargs, success, fail}]
+
+The same keys and shapes are written here.  The container is HDF5 when `h5py` is importable; this image has no `h5py`, so the
+fallback is a NumPy `.npz` archive whose member names are the HDF5 paths ("traj_0/env_states/actors/cube") -- `load_trajectories` reads
+either into the same nested dicts.  One episode is flushed per sub-scene when it is reset (or on `close`), numbered in flush order.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+try:  # pragma: no cover - not available in this image
+    import h5py
+except ImportError:
+    h5py = None
+
+
+def _to_numpy(x):
+    if isinstance(x, dict):
+        return {k: _to_numpy(v) for k, v in x.items()}
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def _index(x, idx):
+    return {k: _index(v, idx) for k, v in x.items()} if isinstance(x, dict) else x[idx]
+
+
+def _stack(frames: List):
+    if isinstance(frames[0], dict):
+        return {k: _stack([f[k] for f in frames]) for k in frames[0]}
+    return np.stack(frames)
+
+
+def _flatten(prefix: str, x, out: Dict[str, np.ndarray]):
+    if isinstance(x, dict):
+        for k, v in x.items():
+            _flatten(f"{prefix}/{k}", v, out)
+    else:
+        out[prefix] = x
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {k: _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, np.generic):
+        return x.item()
+    return x
+
+
+class RecordEpisode:
+    """record.py:113-327.  Wraps a BaseEnv; `reset` / `step` pass through and are recorded.  As in the reference the vector wrapper
+    goes OUTSIDE (`ManiSkillVectorEnv(RecordEpisode(env, ...))`): its auto-reset then arrives here as a partial `reset(options=
+    {"env_idx": ...})`, which flushes exactly the finished episodes.
+
+    save_on_reset: flush the episodes of the sub-scenes being reset before resetting them (record.py:364-378).
+    record_env_state: store `base_env.get_state_dict()` per frame so that a replay can restore states exactly."""
+
+    def __init__(self, env, output_dir: str, save_trajectory: bool = True, trajectory_name: str = "trajectory", save_on_reset: bool = True,
+                 record_reward: bool = True, record_env_state: bool = True, source_type: Optional[str] = None, source_desc: Optional[str] = None,
+                 env_id: Optional[str] = None, env_kwargs: Optional[dict] = None):
+        self.env = env
+        self.base_env = getattr(env, "base_env", env)
+        self.num_envs = self.base_env.num_envs
+        self.output_dir = output_dir
+        self.save_trajectory, self.save_on_reset = save_trajectory, save_on_reset
+        self.record_reward, self.record_env_state = record_reward, record_env_state
+        os.makedirs(output_dir, exist_ok=True)
+        self._stem = os.path.join(output_dir, trajectory_name)
+        self._episode_id = -1
+        self._arrays: Dict[str, np.ndarray] = {}       # path -> dataset, npz fallback
+        self._h5 = h5py.File(self._stem + ".h5", "w") if (h5py is not None and save_trajectory) else None
+        from .registration import REGISTERED_ENVS
+        if env_id is None:
+            env_id = next((k for k, (cls, _) in REGISTERED_ENVS.items() if cls is type(self.base_env)), type(self.base_env).__name__)
+        kw = dict(obs_mode=self.base_env.obs_mode, reward_mode=self.base_env._reward_mode, control_mode=self.base_env.control_mode, num_envs=self.num_envs)
+        kw.update(env_kwargs or {})
+        self._json = dict(env_info=dict(env_id=env_id, max_episode_steps=self.base_env.max_episode_steps, env_kwargs=_jsonable(kw)),
+                          source_type=source_type, source_desc=source_desc, episodes=[])
+        self._frames: Optional[List[dict]] = None     # one dict of [num_envs, ...] arrays per frame since the oldest unflushed episode start
+        self._start = np.zeros(self.num_envs, dtype=np.int64)   # record.py `env_episode_ptr`
+        self._last_reset_kwargs: dict = {}
+
+    # -------------------------------------------------------------- pass-through
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def _frame(self, obs, action, reward, terminated, truncated, info):
+        f = dict(obs=_to_numpy(obs), action=_to_numpy(action), terminated=_to_numpy(terminated), truncated=_to_numpy(truncated))
+        if self.record_reward:
+            f["reward"] = _to_numpy(reward).astype(np.float32)
+        if self.record_env_state:
+            f["state"] = _to_numpy(self.base_env.get_state_dict())
+        for k in ("success", "fail"):
+            if k in info:
+                f[k] = _to_numpy(info[k])
+        return f
+
+    def reset(self, seed=None, options: Optional[dict] = None, save: bool = True):
+        idx = np.arange(self.num_envs) if not options or "env_idx" not in options else np.atleast_1d(_to_numpy(options["env_idx"])).astype(np.int64)
+        if self.save_trajectory and self.save_on_reset and self._frames is not None:
+            self.flush_trajectory(env_idxs_to_flush=idx, save=save)
+        obs, info = self.env.reset(seed=seed, options=options)
+        if self.save_trajectory:
+            N = self.num_envs
+            first = self._frame(obs, np.zeros((N, self.base_env.action_dim), dtype=np.float32), np.zeros(N, dtype=np.float32),
+                                np.ones(N, dtype=bool), np.ones(N, dtype=bool), dict(success=np.zeros(N, dtype=bool)))
+            if self._frames is None:
+                self._frames = [first]
+            else:  # the frame a flushed episode ended on becomes the first frame of the next one (record.py:427-458)
+                last = self._frames[-1]
+
+                def replace(dst, src):
+                    if isinstance(dst, dict):
+                        for k in dst:
+                            if k in src:
+                                replace(dst[k], src[k])
+                    else:
+                        dst[idx] = src[idx]
+                replace(last, first)
+                self._start[idx] = len(self._frames) - 1
+        self._last_reset_kwargs = dict(seed=_jsonable(seed)) if seed is not None else {}
+        return obs, info
+
+    def step(self, action):
+        obs, rew, terminated, truncated, info = self.env.step(action)
+        if self.base_env.max_episode_steps is not None:
+            # the env the reference's recorder wraps comes out of gym.make with the TimeLimit wrapper applied (registration.py:127-170)
+            truncated = truncated | (self.base_env.elapsed_steps >= self.base_env.max_episode_steps)
+        if self.save_trajectory:
+            self._frames.append(self._frame(obs, action, rew, terminated, truncated, info))
+        return obs, rew, terminated, truncated, info
+
+    # -------------------------------------------------------------- record.py:546-756
+    def flush_trajectory(self, env_idxs_to_flush=None, ignore_empty_transition: bool = True, save: bool = True):
+        if self._frames is None:
+            return
+        idxs = np.arange(self.num_envs) if env_idxs_to_flush is None else np.asarray(env_idxs_to_flush)
+        end = len(self._frames)
+        flushed = []
+        for e in idxs:
+            start = int(self._start[e])
+            if ignore_empty_transition and end - start <= 1:
+                continue
+            flushed.append(e)
+            if not save:
+                continue
+            self._episode_id += 1
+            fr = self._frames[start:end]
+            data = dict(obs=_stack([_index(f["obs"], e) for f in fr]), actions=np.stack([f["action"][e] for f in fr[1:]]).astype(np.float32),
+                        terminated=np.array([f["terminated"][e] for f in fr[1:]], dtype=bool), truncated=np.array([f["truncated"][e] for f in fr[1:]], dtype=bool))
+            ep = dict(episode_id=self._episode_id, episode_seed=int(self.base_env._episode_seed[e]), control_mode=self.base_env.control_mode,
+                      elapsed_steps=end - start - 1, reset_kwargs=dict(self._last_reset_kwargs) if self.num_envs == 1 else {})
+            for k in ("success", "fail"):
+                if all(k in f for f in fr[1:]):
+                    data[k] = np.array([f[k][e] for f in fr[1:]], dtype=bool)
+                    ep[k] = bool(data[k][-1])
+            if self.record_env_state:
+                data["env_states"] = _stack([_index(f["state"], e) for f in fr])
+            if self.record_reward:
+                data["rewards"] = np.array([f["reward"][e] for f in fr[1:]], dtype=np.float32)
+            self._write(f"traj_{self._episode_id}", data)
+            self._json["episodes"].append(_jsonable(ep))
+        if flushed:
+            self._start[flushed] = end - 1
+            drop = int(self._start.min())
+            if drop > 0:
+                self._frames = self._frames[drop:]
+                self._start -= drop
+            if save:
+                self._dump()
+
+    def _write(self, name: str, data: dict):
+        flat: Dict[str, np.ndarray] = {}
+        _flatten(name, data, flat)
+        if self._h5 is not None:  # pragma: no cover
+            for path, arr in flat.items():
+                big = path.rsplit("/", 1)[-1] in ("rgb", "depth", "seg")
+                self._h5.create_dataset(path, data=arr, **(dict(compression="gzip", compression_opts=5) if big else {}))
+        else:
+            self._arrays.update(flat)
+
+    def _dump(self):
+        with open(self._stem + ".json", "w") as f:
+            json.dump(self._json, f, indent=2)
+        if self._h5 is not None:  # pragma: no cover
+            self._h5.flush()
+        else:
+            np.savez_compressed(self._stem + ".npz", **self._arrays)
+
+    def close(self):
+        if self.save_trajectory:
+            self.flush_trajectory()
+            self._dump()
+            if self._h5 is not None:  # pragma: no cover
+                self._h5.close()
+        if hasattr(self.env, "close"):
+            self.env.close()
+
+
+# ------------------------------------------------------------------------------------------------ reading + replay
+def load_trajectories(path_stem: str):
+    """-> (json dict, {"traj_<k>": nested dict of arrays}) from `<stem>.json` + `<stem>.h5` | `<stem>.npz`."""
+    with open(path_stem + ".json") as f:
+        meta = json.load(f)
+    trajs: Dict[str, dict] = {}
+
+    def put(path, arr):
+        node = trajs
+        parts = path.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = arr
+
+    if os.path.exists(path_stem + ".h5"):  # pragma: no cover
+        if h5py is None:
+            raise RuntimeError("reading .h5 trajectories needs h5py")
+        with h5py.File(path_stem + ".h5", "r") as f:
+            f.visititems(lambda name, obj: put(name, obj[()]) if isinstance(obj, h5py.Dataset) else None)
+    else:
+        with np.load(path_stem + ".npz") as z:
+            for k in z.files:
+                put(k, z[k])
+    return meta, trajs
+
+
+def replay_trajectory(env, path_stem: str, use_env_states: bool = False, use_first_env_state: bool = False, count: Optional[int] = None,
+                      allow_failure: bool = True):
+    """replay_trajectory.py:111-378 for one sub-scene per episode: reset with the stored seed, optionally restore the stored first
+    state, feed the stored actions (restoring the stored state after every step with `use_env_states`), and report per episode
+    whether the replay ended in the recorded success flag and how far the final state is from the recorded one.
+
+    env: a BaseEnv with num_envs == 1 and the control mode of the recording."""
+    base = getattr(env, "base_env", env)
+    if base.num_envs != 1:
+        raise ValueError("replay one episode at a time: make the env with num_envs=1")
+    meta, trajs = load_trajectories(path_stem)
+    results = []
+    dev = base.device
+    to_t = lambda d: {k: to_t(v) for k, v in d.items()} if isinstance(d, dict) else torch.as_tensor(d, device=dev)[None]
+    for ep in meta["episodes"][:count]:
+        tr = trajs[f"traj_{ep['episode_id']}"]
+        if ep["control_mode"] != base.control_mode:
+            raise ValueError(f"episode {ep['episode_id']} was recorded with control mode {ep['control_mode']}, the env uses {base.control_mode}")
+        env.reset(seed=ep["episode_seed"])
+        states = tr.get("env_states")
+        if (use_env_states or use_first_env_state):
+            if states is None:
+                raise ValueError("the trajectory holds no env_states")
+            base.set_state_dict(to_t(_index(states, 0)))
+        info = {}
+        for t, a in enumerate(tr["actions"]):
+            _, _, _, _, info = env.step(torch.as_tensor(a, device=dev)[None])
+            if use_env_states:
+                base.set_state_dict(to_t(_index(states, t + 1)))
+        success = bool(_to_numpy(info["success"]).reshape(-1)[0]) if "success" in info else None
+        err = None
+        if states is not None:
+            flat_now, flat_rec = {}, {}
+            _flatten("", _to_numpy(base.get_state_dict()), flat_now)
+            _flatten("", _index(states, len(tr["actions"])), flat_rec)
+            err = max(float(np.abs(flat_now[k].reshape(-1) - flat_rec[k].reshape(-1)).max()) for k in flat_now)
+        res = dict(episode_id=ep["episode_id"], success=success, recorded_success=ep.get("success"), final_state_error=err)
+        if not allow_failure and ep.get("success") and not success:
+            raise RuntimeError(f"replay of episode {ep['episode_id']} did not reach the recorded success")
+        results.append(res)
+    return results
