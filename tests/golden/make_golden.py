@@ -24,6 +24,7 @@ Covered reference functions (file:line):
   mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137, poke_cube.py:126-276, roll_ball.py:130-189  the same three functions
   mani_skill/utils/structs/render_camera.py:77-155     get_extrinsic_matrix / get_model_matrix (GPU branch, mounted camera)
   mani_skill/agents/controllers/pd_ee_pose.py:85-99,229-263, utils/kinematics.py:197-260  EE controllers: action scaling, target pose, GPU IK step
+  mani_skill/utils/wrappers/record.py:356-756          RecordEpisode.reset / step / flush_trajectory (h5py replaced by a dict-backed fake)
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -585,6 +586,90 @@ def main():
                                                                    current_pose=Pose.create(cur_raw), solver_config=cfg)
         G[f"ee_ik_delta_{sname}"] = kin_mod.Kinematics.compute_ik(kin_self, ee_scaled.clone(), q0, is_delta_pose=True, current_pose=Pose.create(cur_raw),
                                                                   solver_config=cfg)
+    # ---- RecordEpisode (mani_skill/utils/wrappers/record.py:356-756) on a scripted 3-sub-scene env; h5py replaced by a dict-backed fake
+    class FakeGroup:
+        def __init__(self, store, path):
+            self.store, self.path = store, path
+        def create_group(self, name, track_order=True):
+            return FakeGroup(self.store, f"{self.path}/{name}" if self.path else name)
+        def create_dataset(self, key, data=None, dtype=None, **kw):
+            self.store[f"{self.path}/{key}"] = np.array(data, dtype=dtype)
+
+    class FakeWrapper:
+        def __init__(self, env):
+            self.env = env
+        def reset(self, *a, **k):
+            return self.env.reset(*a, **k)
+        def step(self, a):
+            return self.env.step(a)
+
+    sys.modules["gymnasium"].Wrapper = FakeWrapper
+    stub("h5py", File=object, Group=object)
+    stub("mani_skill.utils.io_utils", dump_json=lambda path, data, indent=2: None)
+    stub("mani_skill.utils.logging_utils")
+    stub("mani_skill.utils.visualization")
+    stub("mani_skill.utils.visualization.misc")
+    stub("mani_skill.utils.wrappers", CPUGymWrapper=type("CPUGymWrapper", (), {}))
+    sys.modules["mani_skill"].get_commit_info = lambda: {}
+    if not hasattr(sys.modules["mani_skill.utils"].sapien_utils, "is_state_dict_consistent") or isinstance(sys.modules["mani_skill.utils"].sapien_utils, MagicMock):
+        sys.modules["mani_skill.utils"].sapien_utils = SimpleNamespace(is_state_dict_consistent=lambda sd: True)
+    rec_mod = load("mani_skill.utils.wrappers.record", "mani_skill/utils/wrappers/record.py")
+    nr, Tr = 3, 8
+    rs_obs = torch.randn(Tr + 4, nr, 4, generator=g4)          # what the scripted env returns, frame by frame (resets consume frames too)
+    rs_rew = torch.rand(Tr, nr, generator=g4)
+    rs_succ = torch.rand(Tr, nr, generator=g4) < 0.4
+    rs_state = torch.randn(Tr + 4, nr, 5, generator=g4)
+    rs_act = torch.randn(Tr, nr, 2, generator=g4)
+    G["rec_obs"], G["rec_rew"], G["rec_succ"], G["rec_state"], G["rec_act"] = rs_obs, rs_rew, rs_succ, rs_state, rs_act
+
+    class ScriptedRecEnv:
+        def __init__(self):
+            self.k, self.t, self.num_envs, self.control_mode = 0, 0, nr, "pd_joint_delta_pos"
+            self._episode_seed = np.array([5, 6, 7])
+            self.unwrapped = self
+            self.cur = torch.zeros(nr, 5)
+        def get_wrapper_attr(self, name):
+            return SimpleNamespace(sample=lambda: np.zeros(2, dtype=np.float32))
+        def get_state_dict(self):
+            return dict(actors=dict(cube=self.cur.clone()), articulations=dict(panda=self.cur.clone() * 2))
+        def reset(self, seed=None, options=None):
+            idx = torch.arange(nr) if not options or "env_idx" not in options else torch.as_tensor(options["env_idx"])
+            self.cur[idx] = rs_state[self.k][idx]
+            obs = rs_obs[self.k].clone()
+            self.k += 1
+            return obs, dict(reconfigure=False)
+        def step(self, a):
+            self.cur = rs_state[self.k].clone()
+            obs = rs_obs[self.k].clone()
+            self.k += 1
+            t = self.t
+            self.t += 1
+            return obs, rs_rew[t].clone(), rs_succ[t].clone(), torch.zeros(nr, dtype=torch.bool), dict(success=rs_succ[t].clone())
+
+    store = {}
+    rec = rec_mod.RecordEpisode.__new__(rec_mod.RecordEpisode)
+    rec.env = ScriptedRecEnv()
+    rec.__dict__.update(_h5_file=FakeGroup(store, ""), _json_data=dict(episodes=[]), _json_path="x.json", _trajectory_buffer=None, save_on_reset=True,
+                        save_trajectory=True, record_env_state=True, record_reward=True, _episode_id=-1, _elapsed_record_steps=0, _save_video=False,
+                        save_video_trigger=None, cpu_wrapped_env=False, _already_warned_about_state_dict_inconsistency=False, last_reset_kwargs={})
+    # script: reset, 3 steps, partial reset of sub-scene 1, 2 steps, partial reset of sub-scenes 0 and 2, 2 steps, full reset, 1 step, flush
+    rec.reset(seed=5)
+    for t in range(3):
+        rec.step(rs_act[t])
+    rec.reset(options=dict(env_idx=torch.tensor([1])))
+    for t in range(3, 5):
+        rec.step(rs_act[t])
+    rec.reset(options=dict(env_idx=torch.tensor([0, 2])))
+    for t in range(5, 7):
+        rec.step(rs_act[t])
+    rec.reset()
+    rec.step(rs_act[7])
+    rec.flush_trajectory()
+    for k_, v_ in store.items():
+        G["recout/" + k_] = v_
+    G["rec_episode_steps"] = np.array([e["elapsed_steps"] for e in rec._json_data["episodes"]])
+    G["rec_episode_seed"] = np.array([e["episode_seed"] for e in rec._json_data["episodes"]])
+    G["rec_episode_success"] = np.array([e["success"] for e in rec._json_data["episodes"]])
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -406,3 +406,66 @@ def test_end_effector_controllers_and_the_ik_step_match_the_reference():
         close(kin.compute_ik(scaled, q0, cfg), G[f"ee_ik_delta_{name}"], 2e-4)
     with pytest.raises(NotImplementedError):
         kin.compute_ik(scaled, q0, dict(type="newton"))
+
+
+def test_record_episode_writes_what_the_reference_recorder_writes(tmp_path):
+    """mani_skill/utils/wrappers/record.py:356-756 run by the reference's own code (h5py replaced by a dict-backed fake) on a scripted
+    3-sub-scene env through full and partial resets: every dataset of every flushed episode -- order, keys, shapes, dtypes, values --
+    and the per-episode JSON fields."""
+    from maniskill_b200.trajectory import RecordEpisode, load_trajectories
+    obs_s, rew_s, succ_s, state_s, act_s = T("rec_obs"), T("rec_rew"), T("rec_succ"), T("rec_state"), T("rec_act")
+    nr = obs_s.shape[1]
+
+    class Scripted:
+        obs_mode, _reward_mode, control_mode, max_episode_steps, action_dim = "state", "dense", "pd_joint_delta_pos", None, 2
+
+        def __init__(self):
+            self.k, self.t, self.num_envs = 0, 0, nr
+            self._episode_seed = np.array([5, 6, 7])
+            self.cur = torch.zeros(nr, 5)
+
+        def get_state_dict(self):
+            return dict(actors=dict(cube=self.cur.clone()), articulations=dict(panda=self.cur.clone() * 2))
+
+        def reset(self, seed=None, options=None):
+            idx = torch.arange(nr) if not options or "env_idx" not in options else torch.as_tensor(options["env_idx"])
+            self.cur[idx] = state_s[self.k][idx]
+            self.k += 1
+            return obs_s[self.k - 1].clone(), dict(reconfigure=False)
+
+        def step(self, a):
+            self.cur = state_s[self.k].clone()
+            self.k += 1
+            self.t += 1
+            t = self.t - 1
+            return obs_s[self.k - 1].clone(), rew_s[t].clone(), succ_s[t].clone(), torch.zeros(nr, dtype=torch.bool), dict(success=succ_s[t].clone())
+
+    rec = RecordEpisode(Scripted(), str(tmp_path), env_id="Scripted-v0")
+    rec.reset(seed=5)
+    for t in range(3):
+        rec.step(act_s[t])
+    rec.reset(options=dict(env_idx=torch.tensor([1])))
+    for t in range(3, 5):
+        rec.step(act_s[t])
+    rec.reset(options=dict(env_idx=torch.tensor([0, 2])))
+    for t in range(5, 7):
+        rec.step(act_s[t])
+    rec.reset()
+    rec.step(act_s[7])
+    rec.flush_trajectory()
+    rec._dump()
+    meta, trajs = load_trajectories(str(tmp_path / "trajectory"))
+    flat = {}
+    from maniskill_b200.trajectory import _flatten
+    for name, tr in trajs.items():
+        _flatten(name, tr, flat)
+    ref = {k[len("recout/"):]: G[k] for k in G.files if k.startswith("recout/")}
+    assert set(flat) == set(ref) and len(ref) == 72
+    for k in ref:
+        assert flat[k].dtype == ref[k].dtype and flat[k].shape == ref[k].shape, k
+        assert np.array_equal(flat[k], ref[k]), k
+    eps = meta["episodes"]
+    assert [e["elapsed_steps"] for e in eps] == G["rec_episode_steps"].tolist()
+    assert [e["episode_seed"] for e in eps] == G["rec_episode_seed"].tolist()
+    assert [e["success"] for e in eps] == G["rec_episode_success"].tolist()
+    assert [e["episode_id"] for e in eps] == list(range(9))
