@@ -20,6 +20,7 @@ from .. import utils as U
 from ..backend import (BUF_ALL, BUF_APPLY_ALL, BUF_QF, BUF_QPOS, BUF_QVEL, BUF_RIGID, BUF_ROOT_POSE, BUF_TARGET_QPOS,
                        BUF_TARGET_QVEL)
 from ..model import CompiledModel, SceneDesc, SimParams
+from ..observations import parse_obs_mode, sensor_data_to_pointcloud
 from ..structs import Actor, Articulation, Pose
 
 
@@ -124,8 +125,8 @@ class Scene:
 class BaseEnv:
     """Mirror of mani_skill.envs.sapien_env.BaseEnv for GPU simulation (num_envs >= 1, sim_backend physx_cuda)."""
 
-    SUPPORTED_OBS_MODES = ("none", "state", "state_dict", "rgb", "depth", "segmentation", "rgbd", "rgb+depth",
-                           "rgb+depth+segmentation", "state+rgb+depth", "sensor_data")
+    # sapien_env.py:124: the named modes + "any_textures" = every '+'-combination of the textures the shader writes (and state flags)
+    SUPPORTED_OBS_MODES = ("state", "state_dict", "none", "sensor_data", "any_textures", "pointcloud")
     SUPPORTED_REWARD_MODES = ("normalized_dense", "dense", "sparse", "none")
     max_episode_steps: Optional[int] = None
 
@@ -134,8 +135,7 @@ class BaseEnv:
                  world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True):
         self.num_envs = num_envs
         self._obs_mode = "state" if obs_mode is None else obs_mode
-        if self._obs_mode not in self.SUPPORTED_OBS_MODES:
-            raise NotImplementedError(f"Unsupported obs mode: {self._obs_mode}. Must be one of {self.SUPPORTED_OBS_MODES}")
+        self.obs_mode_struct = parse_obs_mode(self._obs_mode)   # raises NotImplementedError for unknown / unsupported textures
         self._reward_mode = "normalized_dense" if reward_mode is None else reward_mode
         if self._reward_mode not in self.SUPPORTED_REWARD_MODES:
             raise NotImplementedError(f"Unsupported reward mode: {self._reward_mode}")
@@ -154,7 +154,7 @@ class BaseEnv:
         self._episode_rng = None
         self._enhanced_determinism = False
         self._sensor_overrides = sensor_configs or {}
-        self._visual = any(k in self._obs_mode for k in ("rgb", "depth", "segmentation", "sensor_data"))
+        self._visual = self.obs_mode_struct.visual
         if enable_cameras is not None:
             self._visual = self._visual or enable_cameras
         # sapien_env.py:321-327 + 899-907: the first reset seeds main/episode RNG with 2022+i BEFORE `_load_scene` runs, so
@@ -420,20 +420,22 @@ class BaseEnv:
             return self._get_obs_state_dict(info)
         # visual modes (sapien_env.py:535-625): agent + extra (+ state when requested) + sensor data / params
         obs = dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
-        if self._obs_mode.startswith("state+"):
+        if self.obs_mode_struct.state:
             obs["state"] = U.flatten_state_dict(self._get_obs_state_dict(info))
+        return self._add_sensor_obs(obs)
+
+    def _add_sensor_obs(self, obs):
+        """sapien_env.py:525-532: camera parameters + the requested textures, as a point cloud under obs mode "pointcloud"."""
         obs["sensor_param"] = self.get_sensor_params()
         obs["sensor_data"] = self._get_obs_sensor_data()
-        return obs
+        return sensor_data_to_pointcloud(obs) if self.obs_mode_struct.pointcloud else obs
 
     def _visual_obs_from_fused(self, vec, info):
         """Visual-mode observation (same structure as `get_obs`) with the agent / extra entries taken from the fused state vector."""
         obs = self._obs_from_fused(vec, info)
-        if self._obs_mode.startswith("state+"):
+        if self.obs_mode_struct.state:
             obs["state"] = vec
-        obs["sensor_param"] = self.get_sensor_params()
-        obs["sensor_data"] = self._get_obs_sensor_data()
-        return obs
+        return self._add_sensor_obs(obs)
 
     def _sensor_configs(self):
         """task hook: list of dict(uid, pose(7), width, height, fov, near, far, mount(link/actor name or None))."""
@@ -459,11 +461,8 @@ class BaseEnv:
         """sapien_env.py:578-625: hidden objects are simply absent from the sensor render-shape table (the reference
         teleports them away and back, actor.py:176-201), then update_render + take_picture on the camera group."""
         self._sensors.capture()
-        m = self._obs_mode
-        want_rgb = "rgb" in m or m == "sensor_data"
-        want_depth = "depth" in m or "rgbd" in m or m == "sensor_data"
-        want_seg = "segmentation" in m or m == "sensor_data"
-        return self._sensors.get_obs(rgb=want_rgb, depth=want_depth, segmentation=want_seg)
+        m = self.obs_mode_struct
+        return self._sensors.get_obs(rgb=m.rgb, depth=m.depth, segmentation=m.segmentation, position=m.position)
 
     def get_sensor_params(self):
         return self._sensors.get_params(self.scene.world.body_view()) if self._sensors else {}

@@ -53,3 +53,19 @@ class EmuBackendWorld:
 
     def close(self):
         pass
+
+    # ---- rendering: the CPU raster oracle stands in for b2s_camera_group_create / b2s_render (tests may use oracle/)
+    def create_camera_group(self, cameras, visuals):
+        from maniskill_b200.backend import CameraGroup
+        pix = sum(int(c["width"]) * int(c["height"]) for c in cameras)
+        g = CameraGroup(self, None, cameras, torch.zeros((self.n_envs, pix, 4), dtype=torch.uint8), torch.zeros((self.n_envs, pix, 4), dtype=torch.int16))
+        g._visuals = visuals
+        return g
+
+    def render(self, group):
+        from oracle import raster
+        out = raster.render(group._visuals, group.cameras, self.body_view().numpy())
+        for i, (color, posseg) in enumerate(out):
+            a, b = int(group._offsets[i]), int(group._offsets[i + 1])
+            group._color[:, a:b] = torch.from_numpy(np.ascontiguousarray(color)).reshape(self.n_envs, -1, 4)
+            group._posseg[:, a:b] = torch.from_numpy(np.ascontiguousarray(posseg)).reshape(self.n_envs, -1, 4)

@@ -25,6 +25,7 @@ Covered reference functions (file:line):
   mani_skill/utils/structs/render_camera.py:77-155     get_extrinsic_matrix / get_model_matrix (GPU branch, mounted camera)
   mani_skill/agents/controllers/pd_ee_pose.py:85-99,229-263, utils/kinematics.py:197-260  EE controllers: action scaling, target pose, GPU IK step
   mani_skill/utils/wrappers/record.py:356-756          RecordEpisode.reset / step / flush_trajectory (h5py replaced by a dict-backed fake)
+  mani_skill/envs/utils/observations/observations.py:16-68  sensor_data_to_pointcloud (two cameras)
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -670,6 +671,28 @@ def main():
     G["rec_episode_steps"] = np.array([e["elapsed_steps"] for e in rec._json_data["episodes"]])
     G["rec_episode_seed"] = np.array([e["episode_seed"] for e in rec._json_data["episodes"]])
     G["rec_episode_success"] = np.array([e["success"] for e in rec._json_data["episodes"]])
+    # ---- sensor_data_to_pointcloud (mani_skill/envs/utils/observations/observations.py:16-68): two cameras, synthetic targets
+    FakeCamera = type("Camera", (), {})
+    stub("mani_skill.sensors")
+    stub("mani_skill.sensors.base_sensor", BaseSensor=object, BaseSensorConfig=object)
+    stub("mani_skill.sensors.camera", Camera=FakeCamera)
+    obs_mod = load("mani_skill.envs.utils.observations.observations", "mani_skill/envs/utils/observations/observations.py")
+    npc, Hh, Ww = 2, 4, 5
+    pc_obs = dict(sensor_data={}, sensor_param={})
+    for ci, uid in enumerate(("base_camera", "hand_camera")):
+        pos = (torch.randn(npc, Hh, Ww, 3, generator=g4) * 400).to(torch.int16)
+        seg = (torch.rand(npc, Hh, Ww, 1, generator=g4) * 4).to(torch.int16)          # id 0 = background
+        rgb = (torch.rand(npc, Hh, Ww, 3, generator=g4) * 255).to(torch.uint8)
+        c2w = torch.eye(4).repeat(npc, 1, 1)
+        c2w[:, :3, :3] = rc.quaternion_to_matrix(rnd_q(npc))
+        c2w[:, :3, 3] = torch.randn(npc, 3, generator=g4)
+        pc_obs["sensor_data"][uid] = dict(rgb=rgb, position=pos, segmentation=seg)
+        pc_obs["sensor_param"][uid] = dict(cam2world_gl=c2w)
+        G[f"pcd_in_{ci}_position"], G[f"pcd_in_{ci}_segmentation"], G[f"pcd_in_{ci}_rgb"], G[f"pcd_in_{ci}_cam2world"] = pos, seg, rgb, c2w
+    pc_out = obs_mod.sensor_data_to_pointcloud(pc_obs, {"base_camera": FakeCamera(), "hand_camera": FakeCamera()})
+    assert pc_out["sensor_data"] == {}
+    for k_ in ("xyzw", "rgb", "segmentation"):
+        G[f"pcd_out_{k_}"] = pc_out["pointcloud"][k_]
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -94,7 +94,7 @@ def test_reset_places_cube_and_goal_in_range():
 
 def test_unsupported_modes_raise():
     with pytest.raises(NotImplementedError):
-        ms.make("PickCube-v1", num_envs=1, obs_mode="pointcloud", world_factory=EmuBackendWorld)
+        ms.make("PickCube-v1", num_envs=1, obs_mode="rgb+albedo", world_factory=EmuBackendWorld)   # texture the minimal shader does not write
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_pose", world_factory=EmuBackendWorld)  # absolute EE targets: not built
 

@@ -469,3 +469,20 @@ def test_record_episode_writes_what_the_reference_recorder_writes(tmp_path):
     assert [e["episode_seed"] for e in eps] == G["rec_episode_seed"].tolist()
     assert [e["success"] for e in eps] == G["rec_episode_success"].tolist()
     assert [e["episode_id"] for e in eps] == list(range(9))
+
+
+def test_sensor_data_to_pointcloud_matches_the_reference():
+    """mani_skill/envs/utils/observations/observations.py:16-68 on the same two-camera synthetic targets: world-frame homogeneous
+    points (w = 0 on background), colours and ids, cameras concatenated along the point axis, `sensor_data` emptied."""
+    from maniskill_b200.observations import sensor_data_to_pointcloud
+    obs = dict(sensor_data={}, sensor_param={})
+    for ci, uid in enumerate(("base_camera", "hand_camera")):
+        obs["sensor_data"][uid] = dict(rgb=T(f"pcd_in_{ci}_rgb"), position=T(f"pcd_in_{ci}_position"), segmentation=T(f"pcd_in_{ci}_segmentation"))
+        obs["sensor_param"][uid] = dict(cam2world_gl=T(f"pcd_in_{ci}_cam2world"))
+    pos_before = obs["sensor_data"]["base_camera"]["position"].clone()
+    out = sensor_data_to_pointcloud(obs)
+    assert out["sensor_data"] == {} and set(out["pointcloud"]) == {"xyzw", "rgb", "segmentation"}
+    close(out["pointcloud"]["xyzw"], G["pcd_out_xyzw"], 1e-6)
+    for k in ("rgb", "segmentation"):
+        assert out["pointcloud"][k].dtype == torch.from_numpy(G[f"pcd_out_{k}"]).dtype and np.array_equal(out["pointcloud"][k].numpy(), G[f"pcd_out_{k}"])
+    assert torch.equal(T("pcd_in_0_position"), pos_before)       # the render target is left in millimetres

@@ -1,0 +1,118 @@
+"""CPU: observation modes of the BaseEnv mirror with cameras, on the emulated physics + the CPU raster oracle standing in for the
+CUDA rasteriser (tests/emu_world.py).  Restates the reference's tests/test_envs.py:32-95 (obs-mode structure, shapes, dtypes) and the
+mode parsing of mani_skill/envs/utils/observations/__init__.py:37-105."""
+import numpy as np
+import pytest
+import torch
+
+import maniskill_b200 as ms
+from emu_world import EmuBackendWorld
+from maniskill_b200.observations import parse_obs_mode
+
+
+def test_parse_obs_mode():
+    m = parse_obs_mode("rgbd")
+    assert (m.rgb, m.depth, m.segmentation, m.position, m.use_state, m.visual) == (True, True, False, False, False, True)
+    m = parse_obs_mode("pointcloud")
+    assert m.pointcloud and m.rgb and m.segmentation and m.position and not m.depth
+    m = parse_obs_mode("sensor_data")
+    assert m.raw and m.rgb and m.depth and m.segmentation and m.position
+    m = parse_obs_mode("state+rgb+segmentation")
+    assert m.state and not m.state_dict and m.rgb and m.segmentation and not m.depth and m.use_state
+    m = parse_obs_mode("state_dict+depth")
+    assert m.state_dict and not m.state and m.depth
+    for name in ("state", "state_dict", "none"):
+        assert not parse_obs_mode(name).visual
+    assert parse_obs_mode("state").state and parse_obs_mode("state_dict").state_dict and not parse_obs_mode("none").use_state
+    with pytest.raises(NotImplementedError, match="Invalid texture type 'rgbx'"):
+        parse_obs_mode("rgbx+depth")
+    with pytest.raises(NotImplementedError, match="normal"):
+        parse_obs_mode("rgb+normal")
+
+
+@pytest.mark.parametrize("mode,textures", [("rgb", {"rgb"}), ("rgbd", {"rgb", "depth"}), ("depth+segmentation", {"depth", "segmentation"}),
+                                            ("rgb+position", {"rgb", "position"}), ("sensor_data", {"rgb", "depth", "segmentation", "position"})])
+def test_texture_modes_deliver_exactly_the_requested_textures(mode, textures):
+    n = 2
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode=mode, world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert set(obs) == {"agent", "extra", "sensor_param", "sensor_data"} and "obj_pose" not in obs["extra"]
+    sd = obs["sensor_data"]["base_camera"]
+    assert set(sd) == textures
+    spec = dict(rgb=(3, torch.uint8), depth=(1, torch.int16), segmentation=(1, torch.int16), position=(3, torch.int16))
+    for k in textures:
+        assert sd[k].shape == (n, 128, 128, spec[k][0]) and sd[k].dtype == spec[k][1]
+    sp = obs["sensor_param"]["base_camera"]
+    assert sp["extrinsic_cv"].shape == (n, 3, 4) and sp["intrinsic_cv"].shape == (n, 3, 3) and sp["cam2world_gl"].shape == (n, 4, 4)
+    if {"depth", "position"} <= textures:
+        assert torch.equal(sd["depth"][..., 0], -sd["position"][..., 2])       # depth = -z of the OpenGL camera frame (shaders.py:74-83)
+
+
+def test_state_plus_textures_and_the_hidden_goal():
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state+rgb+segmentation", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert obs["state"].shape == (2, 42) and "obj_pose" in obs["extra"]
+    ids = set(np.unique(obs["sensor_data"]["base_camera"]["segmentation"].numpy()).tolist())
+    cm = env.cm
+    assert cm.actor_seg_id["cube"] in ids and cm.actor_seg_id["table-workspace"] in ids and cm.actor_seg_id["goal_site"] not in ids
+    o2, *_ = env.step(torch.zeros(2, 8))
+    assert set(o2) == set(obs)
+
+
+def test_pointcloud_mode_points_lie_on_the_scene():
+    """obs mode "pointcloud" (sapien_env.py:525-527): xyzw [N, H*W, 4] in the world frame.  Points with the table's id lie in the
+    table-top plane z = 0, points with the cube's id inside the cube's box, background points have w = 0."""
+    n = 2
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="pointcloud", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=1)
+    assert obs["sensor_data"] == {} and set(obs["pointcloud"]) == {"xyzw", "rgb", "segmentation"}
+    pc = obs["pointcloud"]
+    P = 128 * 128
+    assert pc["xyzw"].shape == (n, P, 4) and pc["rgb"].shape == (n, P, 3) and pc["segmentation"].shape == (n, P, 1)
+    seg = pc["segmentation"][..., 0]
+    cm = env.cm
+    table = seg == cm.actor_seg_id["table-workspace"]
+    assert table.sum() > 1000
+    assert pc["xyzw"][..., 2][table].abs().max() < 2e-3                       # mm-quantised positions
+    assert (pc["xyzw"][..., 3][seg != 0] == 1).all() and (pc["xyzw"][..., 3][seg == 0] == 0).all()
+    cube = seg == cm.actor_seg_id["cube"]
+    for e in range(n):
+        pts = pc["xyzw"][e][cube[e]][:, :3]
+        assert len(pts) > 10
+        assert ((pts - env.cube.pose.p[e]).norm(dim=1) < 0.02 * 3 ** 0.5 + 2e-3).all()
+    # stepping keeps the structure
+    o2, *_ = env.step(torch.zeros(n, 8))
+    assert set(o2["pointcloud"]) == {"xyzw", "rgb", "segmentation"}
+
+
+def test_depth_of_the_table_top_is_analytic_on_the_raster_oracle():
+    """KAT of the raster oracle itself (the checker of the CUDA rasteriser): the centre pixel looks along the optical axis and must
+    report the analytic ray / plane distance to the table top (z = 0)."""
+    env = ms.make("PickCube-v1", num_envs=1, obs_mode="depth+segmentation", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    d = obs["sensor_data"]["base_camera"]["depth"][0, :, :, 0].numpy().astype(float)
+    seg = obs["sensor_data"]["base_camera"]["segmentation"][0, :, :, 0].numpy()
+    eye, target = np.array([0.3, 0, 0.6]), np.array([-0.1, 0, 0.1])
+    fwd = (target - eye) / np.linalg.norm(target - eye)
+    t = -eye[2] / fwd[2]
+    assert abs(d[63:65, 63:65].mean() - t * 1000) < 15
+    # rows further down the image look at nearer table points: over the table's pixels depth decreases monotonically down a column
+    on_table = seg[:, 64] == env.cm.actor_seg_id["table-workspace"]
+    assert on_table.sum() > 30 and (np.diff(d[:, 64][on_table]) <= 0).all()
+
+
+def test_wrist_camera_follows_its_mount():
+    """PegInsertionSide-v1 (panda_wristcam): the hand camera's extrinsics move with the hand link, the base camera's do not."""
+    env = ms.make("PegInsertionSide-v1", num_envs=2, obs_mode="rgbd", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert set(obs["sensor_data"]) == {"base_camera", "hand_camera"}
+    e0 = {k: obs["sensor_param"][k]["extrinsic_cv"].clone() for k in obs["sensor_param"]}
+    a = torch.zeros(2, 8)
+    a[:, 1] = 1.0
+    for _ in range(3):
+        obs, *_ = env.step(a)
+    assert torch.equal(obs["sensor_param"]["base_camera"]["extrinsic_cv"], e0["base_camera"])
+    assert (obs["sensor_param"]["hand_camera"]["extrinsic_cv"] - e0["hand_camera"]).abs().max() > 1e-3
+    # the hand camera sees the gripper fingers
+    ids = set(np.unique(obs["sensor_data"]["hand_camera"]["segmentation"].numpy()).tolist()) if "segmentation" in obs["sensor_data"]["hand_camera"] else None
+    assert ids is None      # rgbd carries no segmentation
