@@ -11,6 +11,7 @@ CPU path.
 from .registration import make, register_env, REGISTERED_ENVS  # noqa: F401
 from . import envs  # noqa: F401  (registers the tasks)
 from .vector import ManiSkillVectorEnv  # noqa: F401
+from .wrappers import FlattenObservationWrapper, FlattenRGBDObservationWrapper  # noqa: F401
 from .trajectory import RecordEpisode, load_trajectories, replay_trajectory  # noqa: F401
 
 __version__ = "0.1.0"

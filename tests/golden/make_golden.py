@@ -26,6 +26,7 @@ Covered reference functions (file:line):
   mani_skill/agents/controllers/pd_ee_pose.py:85-99,229-263, utils/kinematics.py:197-260  EE controllers: action scaling, target pose, GPU IK step
   mani_skill/utils/wrappers/record.py:356-756          RecordEpisode.reset / step / flush_trajectory (h5py replaced by a dict-backed fake)
   mani_skill/envs/utils/observations/observations.py:16-68  sensor_data_to_pointcloud (two cameras)
+  mani_skill/utils/wrappers/flatten.py:42-77            FlattenRGBDObservationWrapper.observation (two cameras, three settings)
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -693,6 +694,35 @@ def main():
     assert pc_out["sensor_data"] == {}
     for k_ in ("xyzw", "rgb", "segmentation"):
         G[f"pcd_out_{k_}"] = pc_out["pointcloud"][k_]
+    # ---- FlattenRGBDObservationWrapper.observation (mani_skill/utils/wrappers/flatten.py:42-77), two cameras
+    class FakeObsWrapper:
+        def __init__(self, env):
+            self.env = env
+    sys.modules["gymnasium"].ObservationWrapper = FakeObsWrapper
+    sys.modules["gymnasium"].ActionWrapper = FakeObsWrapper
+    stub("gymnasium.spaces")
+    stub("gymnasium.spaces.utils")
+    stub("gymnasium.vector.utils", batch_space=None)
+    flat_mod = load("mani_skill.utils.wrappers.flatten", "mani_skill/utils/wrappers/flatten.py")
+    nf = 3
+    def fl_obs():
+        gg = torch.Generator().manual_seed(31)
+        cam = lambda: dict(rgb=(torch.rand(nf, 4, 5, 3, generator=gg) * 255).to(torch.uint8), depth=(torch.rand(nf, 4, 5, 1, generator=gg) * 2000).to(torch.int16))
+        return dict(agent=dict(qpos=torch.randn(nf, 9, generator=gg), qvel=torch.randn(nf, 9, generator=gg)),
+                    extra=dict(is_grasped=torch.rand(nf, generator=gg) < 0.5, tcp_pose=torch.randn(nf, 7, generator=gg)),
+                    sensor_param=dict(base_camera=dict(), hand_camera=dict()), sensor_data=dict(base_camera=cam(), hand_camera=cam()))
+    src = fl_obs()
+    G["flat_in_state_parts"] = torch.hstack([src["agent"]["qpos"], src["agent"]["qvel"], src["extra"]["is_grasped"][:, None].float(), src["extra"]["tcp_pose"]])
+    for ci, uid in enumerate(("base_camera", "hand_camera")):
+        G[f"flat_in_rgb_{ci}"], G[f"flat_in_depth_{ci}"] = src["sensor_data"][uid]["rgb"], src["sensor_data"][uid]["depth"]
+    for tag, kw in (("sep", dict(include_rgb=True, include_depth=True, sep_depth=True, include_state=True)),
+                    ("merged", dict(include_rgb=True, include_depth=True, sep_depth=False, include_state=True)),
+                    ("rgbonly", dict(include_rgb=True, include_depth=False, sep_depth=True, include_state=False))):
+        fw = SimpleNamespace(base_env=SimpleNamespace(device=torch.device("cpu")), **kw)
+        out = flat_mod.FlattenRGBDObservationWrapper.observation(fw, fl_obs())
+        G[f"flat_keys_{tag}"] = np.array(sorted(out.keys()))
+        for k_, v_ in out.items():
+            G[f"flat_{tag}_{k_}"] = v_
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -486,3 +486,26 @@ def test_sensor_data_to_pointcloud_matches_the_reference():
     for k in ("rgb", "segmentation"):
         assert out["pointcloud"][k].dtype == torch.from_numpy(G[f"pcd_out_{k}"]).dtype and np.array_equal(out["pointcloud"][k].numpy(), G[f"pcd_out_{k}"])
     assert torch.equal(T("pcd_in_0_position"), pos_before)       # the render target is left in millimetres
+
+
+def test_flatten_rgbd_observation_wrapper_matches_the_reference():
+    """mani_skill/utils/wrappers/flatten.py:42-77 on the same two-camera observation in three settings (separate depth, merged
+    "rgbd" -- uint8 colour promoted to the int16 of depth --, colour only without state)."""
+    from maniskill_b200.wrappers import FlattenRGBDObservationWrapper as W
+
+    def obs():
+        st = T("flat_in_state_parts")
+        cams = {uid: dict(rgb=T(f"flat_in_rgb_{i}"), depth=T(f"flat_in_depth_{i}")) for i, uid in enumerate(("base_camera", "hand_camera"))}
+        return dict(agent=dict(qpos=st[:, :9], qvel=st[:, 9:18]), extra=dict(is_grasped=st[:, 18] > 0.5, tcp_pose=st[:, 19:]),
+                    sensor_param=dict(base_camera={}, hand_camera={}), sensor_data=cams)
+
+    for tag, kw in (("sep", dict(include_rgb=True, include_depth=True, sep_depth=True, include_state=True)),
+                    ("merged", dict(include_rgb=True, include_depth=True, sep_depth=False, include_state=True)),
+                    ("rgbonly", dict(include_rgb=True, include_depth=False, sep_depth=True, include_state=False))):
+        src = obs()
+        out = W.observation(SimpleNamespace(**kw), src)
+        assert sorted(out.keys()) == G[f"flat_keys_{tag}"].tolist()
+        for k, v in out.items():
+            ref = G[f"flat_{tag}_{k}"]
+            assert v.numpy().dtype == ref.dtype and np.array_equal(v.numpy(), ref), (tag, k)
+        assert "sensor_data" in src       # the caller's dict is left intact

@@ -116,3 +116,24 @@ def test_wrist_camera_follows_its_mount():
     # the hand camera sees the gripper fingers
     ids = set(np.unique(obs["sensor_data"]["hand_camera"]["segmentation"].numpy()).tolist()) if "segmentation" in obs["sensor_data"]["hand_camera"] else None
     assert ids is None      # rgbd carries no segmentation
+
+
+def test_flatten_wrappers_on_an_env():
+    """flatten.py:13-95 in place: PPO-RGB style observation from StackCube-v1 (two cameras), under the vector wrapper."""
+    from maniskill_b200.wrappers import FlattenObservationWrapper, FlattenRGBDObservationWrapper
+    env = ms.make("StackCube-v1", num_envs=2, obs_mode="rgbd", world_factory=EmuBackendWorld)
+    venv = ms.ManiSkillVectorEnv(FlattenRGBDObservationWrapper(env, rgb=True, depth=True, state=True), auto_reset=True)
+    obs, _ = venv.reset(seed=0)
+    assert set(obs) == {"state", "rgb", "depth"}
+    assert obs["rgb"].shape == (2, 128, 128, 6) and obs["rgb"].dtype == torch.uint8 and obs["depth"].shape == (2, 128, 128, 2)
+    assert obs["state"].shape == (2, 9 + 9 + 7)       # qpos, qvel, tcp pose: no privileged object poses in a visual mode
+    o2, r, te, tr, info = venv.step(torch.zeros(2, 8))
+    assert set(o2) == set(obs) and r.shape == (2,)
+    merged = FlattenRGBDObservationWrapper(ms.make("PickCube-v1", num_envs=1, obs_mode="rgb", world_factory=EmuBackendWorld), sep_depth=False)
+    o, _ = merged.reset(seed=0)
+    assert set(o) == {"state", "rgb"} and o["rgb"].shape == (1, 128, 128, 3)       # depth is not in the mode: dropped from the request
+    with pytest.raises(ValueError):
+        FlattenRGBDObservationWrapper(ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld))
+    flat = FlattenObservationWrapper(ms.make("PickCube-v1", num_envs=2, obs_mode="state_dict", world_factory=EmuBackendWorld))
+    o, _ = flat.reset(seed=0)
+    assert o.shape == (2, 42)
