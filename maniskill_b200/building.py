@@ -23,8 +23,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .model import (SHAPE_BOX, SHAPE_CAPSULE, SHAPE_CONVEX, SHAPE_PLANE, SHAPE_SPHERE, ActorRec, SceneDesc, ShapeRec, cylinder_shape, pose7, pose_inv, pose_mul,
-                    qmat)
+from .model import (SHAPE_BOX, SHAPE_CAPSULE, SHAPE_CONVEX, SHAPE_PLANE, SHAPE_SPHERE, ActorRec, ArticulationRec, SceneDesc, ShapeRec, combine_mass,
+                    cylinder_shape, pose7, pose_inv, pose_mul, qmat, qrot, sym6)
 
 
 class Pose:
@@ -373,3 +373,168 @@ def build_twocolor_peg(scene: SceneDesc, length, width, color_1, color_2, name: 
     b.add_box_visual(pose=Pose(p=[-length / 2, 0, 0]), half_size=[length / 2, width, width], material=RenderMaterial(base_color=color_1))
     b.add_box_visual(pose=Pose(p=[length / 2, 0, 0]), half_size=[length / 2, width, width], material=RenderMaterial(base_color=color_2))
     return _build_by_type(b, name, body_type, initial_pose)
+
+
+# ------------------------------------------------------------------------------------------------ articulations
+@dataclass
+class JointRecord:
+    """articulation_builder.py / sapien `LinkBuilder.joint_record`: the joint frame is given on both sides, the joint
+    moves about / along the frame's x axis."""
+    joint_type: str = "undefined"
+    limits: Sequence[float] = (-np.inf, np.inf)
+    pose_in_parent: np.ndarray = field(default_factory=pose7)
+    pose_in_child: np.ndarray = field(default_factory=pose7)
+    friction: float = 0.0
+    damping: float = 0.0
+    name: str = ""
+
+
+class LinkBuilder(ActorBuilder):
+    """`sapien.wrapper.articulation_builder.LinkBuilder(index, parent)`: an actor builder (collision / visual records of the link) + the
+    record of the joint that connects it to its parent."""
+
+    def __init__(self, index: int, parent: Optional["LinkBuilder"] = None):
+        super().__init__(None)
+        self.index, self.parent = index, parent
+        self.physx_body_type = "link"
+        self.joint_record = JointRecord()
+
+    def set_joint_name(self, name: str):
+        self.joint_record.name = name
+        return self
+
+    def set_joint_properties(self, type: str, limits, pose_in_parent=None, pose_in_child=None, friction: float = 0.0, damping: float = 0.0):
+        if type not in ("fixed", "revolute", "revolute_unwrapped", "continuous", "prismatic", "undefined"):
+            raise ValueError(f"unknown joint type {type!r}")
+        lim = np.asarray(limits, dtype=np.float64).reshape(-1) if len(np.asarray(limits).reshape(-1)) else np.array([-np.inf, np.inf])
+        j = self.joint_record
+        j.joint_type, j.limits, j.friction, j.damping = type, lim, float(friction), float(damping)
+        j.pose_in_parent, j.pose_in_child = _pose7_of(pose_in_parent), _pose7_of(pose_in_child)
+        return self
+
+    def _check(self):
+        """articulation_builder's `_check`: every non-root link needs a joint."""
+        if self.parent is not None and self.joint_record.joint_type == "undefined":
+            raise RuntimeError(f"link {self.name!r} has a parent but no joint properties")
+
+    def build(self, name=None):
+        raise RuntimeError("links are built by their ArticulationBuilder.build()")
+
+
+class ArticulationBuilder:
+    """mani_skill/utils/building/articulation_builder.py:23-215 on the scene tables: `create_link_builder(parent)` per link, then
+    `build(name, fix_root_link=True)` compiles the records into one robot description (the format tools/bake_assets.py bakes URDFs
+    into) and adds an `ArticulationRec` to the SceneDesc.  Fixed-base articulations only (the device integrates no floating roots)."""
+
+    def __init__(self, scene: Optional[SceneDesc] = None):
+        self.scene = scene
+        self.link_builders: List[LinkBuilder] = []
+        self.mimic_joint_records: List[dict] = []
+        self.name = ""
+        self.initial_pose = None
+        self.disable_gravity = False
+
+    def set_scene(self, scene: SceneDesc):
+        self.scene = scene
+        return self
+
+    def set_name(self, name: str):
+        self.name = name
+        return self
+
+    def set_initial_pose(self, pose):
+        self.initial_pose = pose
+        return self
+
+    def create_link_builder(self, parent: Optional[LinkBuilder] = None) -> LinkBuilder:
+        if parent is not None and parent not in self.link_builders:
+            raise ValueError("parent link builder belongs to another articulation")
+        if parent is None and self.link_builders:
+            raise ValueError("an articulation has one root link")
+        b = LinkBuilder(len(self.link_builders), parent)
+        self.link_builders.append(b)
+        return b
+
+    def add_mimic_joint(self, joint: str, mimic: str, multiplier: float = 1.0, offset: float = 0.0):
+        """`mimic_joint_records`: joint = multiplier * mimic + offset (a fixed tendon in the reference, articulation_builder.py:161-200)."""
+        self.mimic_joint_records.append(dict(joint=joint, mimic=mimic, multiplier=float(multiplier), offset=float(offset)))
+        return self
+
+    def _robot(self) -> dict:
+        links = []
+        for b in self.link_builders:
+            b._check()
+            if not b.name:
+                raise ValueError("every link needs a name")
+            shapes = b._shape_recs()
+            if any(s.type in (SHAPE_CAPSULE, SHAPE_PLANE) and s.collide for s in shapes):
+                raise NotImplementedError("link collision shapes: box, sphere, cylinder (articulated capsules / planes are not in the link shape table)")
+            cols = []
+            for s in shapes:
+                if not s.collide:
+                    continue   # link visuals follow the collision geometry in this renderer
+                c = dict(p=s.pose[:3].tolist(), q=s.pose[3:].tolist())
+                if s.type == SHAPE_BOX:
+                    c.update(type="box", half_size=np.asarray(s.size).tolist())
+                elif s.type == SHAPE_SPHERE:
+                    c.update(type="sphere", radius=float(s.size[0]))
+                else:
+                    c.update(type="convex", vertices=np.asarray(s.vertices).tolist(), triangles=np.asarray(s.triangles).tolist())
+                cols.append(c)
+            if b._auto_inertial:
+                m, com, I = combine_mass([s.mass_props() for s in shapes if s.collide])
+            else:
+                R = qmat(b._cmass_local_pose[3:])
+                m, com, I = b._mass, b._cmass_local_pose[:3], R @ np.diag(b._inertia) @ R.T
+            j = b.joint_record
+            link = dict(name=b.name, parent=-1 if b.parent is None else b.parent.index, mass=float(m), com=np.asarray(com).tolist(),
+                        inertia=[float(x) for x in sym6(np.asarray(I))], collisions=cols)
+            if b.parent is None or j.joint_type in ("fixed", "undefined"):
+                T0 = pose_mul(j.pose_in_parent, pose_inv(j.pose_in_child)) if b.parent is not None else pose7()
+                link["joint"] = dict(name=j.name, type="fixed", p=T0[:3].tolist(), q=T0[3:].tolist(), axis=[1, 0, 0], lower=0, upper=0, effort=0,
+                                     damping=0, friction=0)
+            else:
+                C = j.pose_in_child
+                rot_c_inv = pose7([0, 0, 0], [C[3], -C[4], -C[5], -C[6]])
+                T0 = pose_mul(j.pose_in_parent, rot_c_inv)                      # frame the joint moves: anchored at the joint, link orientation
+                axis = qrot(C[3:], [1.0, 0.0, 0.0])
+                jt = "revolute" if j.joint_type == "continuous" else j.joint_type
+                lo, hi = (float(j.limits[0]), float(j.limits[1])) if j.joint_type != "continuous" else (-1e30, 1e30)
+                lo, hi = max(lo, -1e30), min(hi, 1e30)
+                link["joint"] = dict(name=j.name, type=jt, p=T0[:3].tolist(), q=T0[3:].tolist(), axis=axis.tolist(), lower=lo, upper=hi, effort=0,
+                                     damping=j.damping, friction=j.friction)
+                if np.abs(C[:3]).max() > 0:
+                    link["frame_offset"] = pose7(-C[:3]).tolist()               # link frame inside that moving frame
+            links.append(link)
+        by_joint = {l["joint"]["name"]: l for l in links if l["joint"]["name"]}
+        for r in self.mimic_joint_records:
+            if r["joint"] not in by_joint or r["mimic"] not in by_joint:
+                raise ValueError(f"mimic record names unknown joints: {r}")
+            by_joint[r["joint"]]["joint"]["mimic"] = dict(joint=r["mimic"], multiplier=r["multiplier"], offset=r["offset"])
+        return dict(name=self.name, source="ArticulationBuilder", links=links, disabled_collision_pairs=[])
+
+    def build(self, name: Optional[str] = None, fix_root_link: Optional[bool] = True, build_mimic_joints: bool = True) -> ArticulationRec:
+        if name is not None:
+            self.name = name
+        if self.scene is None:
+            raise RuntimeError("builder has no scene")
+        if not self.name or any(a.name == self.name for a in self.scene.articulations):
+            raise RuntimeError("built articulations must have unique, non-empty names")   # articulation_builder.py:120-126
+        if not fix_root_link:
+            raise NotImplementedError("floating-base articulations are not supported: build with fix_root_link=True")
+        if not self.link_builders:
+            raise ValueError("articulation without links")
+        if not build_mimic_joints:
+            self.mimic_joint_records = []
+        rec = ArticulationRec(self.name, self._robot(), _pose7_of(self.initial_pose), disable_gravity=self.disable_gravity)
+        rec.joint_friction = {b.joint_record.name: b.joint_record.friction for b in self.link_builders if b.joint_record.name}
+        rec.link_groups = {b.name: tuple(b.collision_groups) for b in self.link_builders}
+        rec.link_mu = {b.name: float((b.collision_records[0].material or PhysxMaterial()).dynamic_friction) for b in self.link_builders if b.collision_records}
+        rec.link_patch = {b.name: float(b.collision_records[0].patch_radius) for b in self.link_builders if b.collision_records}
+        self.scene.add_articulation(rec)
+        return rec
+
+
+def scene_desc_articulation_builder(scene: SceneDesc) -> ArticulationBuilder:
+    """`scene.create_articulation_builder()` (mani_skill/envs/scene.py:192-199)."""
+    return ArticulationBuilder(scene)

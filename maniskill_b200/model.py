@@ -409,7 +409,9 @@ class SceneDesc:
                         dof_passive.append([0.0, art.joint_friction.get(J["name"], 0.0), 0.0, 0.0])
                         names.append(J["name"])
                         jname_to_dof[J["name"]] = d
-                        ab, off = d, IDENTITY.copy()
+                        # "frame_offset": the link frame inside the frame the joint moves (joints anchored off the link origin,
+                        # building.ArticulationBuilder); baked URDF robots have the two coincide
+                        ab, off = d, (np.asarray(L["frame_offset"], dtype=np.float64) if "frame_offset" in L else IDENTITY.copy())
                 link_abody[li] = (ab, off)
                 link_dof.append(ab)
                 link_offset.append(off)

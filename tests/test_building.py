@@ -125,3 +125,103 @@ def test_twocolor_peg_helper_matches_the_task_mirror():
         assert (s.type, s.collide, s.visual) == (r.type, r.collide, r.visual) and np.allclose(s.pose, r.pose) and np.allclose(s.size, r.size)
         if s.visual:
             assert np.allclose(s.color, r.color)
+
+
+def _fk_world(cm_factory, qpos):
+    """Link poses from the emulated device code after writing qpos (gpu_apply_articulation_qpos + gpu_update_articulation_kinematics)."""
+    import torch
+    from emu_world import EmuBackendWorld
+    from maniskill_b200.backend import BUF_QPOS
+    w = EmuBackendWorld(cm_factory)
+    w.qpos[:, :len(qpos)] = torch.tensor(qpos, dtype=torch.float32)
+    w.apply(BUF_QPOS)
+    w.update_kinematics()
+    return w.body_view()[0, :, :7].numpy().astype(np.float64)
+
+
+def test_articulation_builder_joint_frames_against_analytic_fk():
+    """`set_joint_properties(type, limits, pose_in_parent, pose_in_child)`: the joint frame is given on both sides and the joint moves
+    about / along its x axis (sapien convention).  Link poses from the device kinematics equal root * P1 * Rx(q1) * C1^-1 * P2 * Tx(q2) * C2^-1
+    for arbitrary frames, including a revolute joint anchored away from the link origin."""
+    rng = np.random.default_rng(3)
+    P1, C1, P2, C2 = (rand_pose(rng) for _ in range(4))
+    root = B.Pose([0.3, -0.2, 0.5], [0.9238795, 0, 0, 0.3826834])
+    scene = SceneDesc(1)
+    ab = B.scene_desc_articulation_builder(scene)
+    base = ab.create_link_builder().set_name("base")
+    base.add_box_collision(half_size=[0.05] * 3)
+    l1 = ab.create_link_builder(base).set_name("arm").set_joint_name("shoulder")
+    l1.set_joint_properties("revolute", [[-3, 3]], pose_in_parent=P1, pose_in_child=C1, friction=0.1, damping=2.0)
+    l1.add_box_collision(B.Pose(p=[0.1, 0, 0]), half_size=[0.1, 0.02, 0.02])
+    l2 = ab.create_link_builder(l1).set_name("slide").set_joint_name("rail")
+    l2.set_joint_properties("prismatic", [-0.5, 0.5], pose_in_parent=P2, pose_in_child=C2)
+    l2.add_sphere_collision(radius=0.03)
+    rec = ab.set_initial_pose(root).build(name="arm2", fix_root_link=True)
+    assert [l["joint"]["type"] for l in rec.robot["links"]] == ["fixed", "revolute", "prismatic"] and "frame_offset" in rec.robot["links"][1]
+    cm = scene.compile()
+    assert cm.dof_names["arm2"] == ["shoulder", "rail"] and np.allclose(cm.arrays["dof_limit"].reshape(-1, 2), [[-3, 3], [-0.5, 0.5]])
+    q1, q2 = 0.7, -0.15
+    got = _fk_world(cm, [q1, q2])
+    Rx = B.Pose([0, 0, 0], [np.cos(q1 / 2), np.sin(q1 / 2), 0, 0])
+    Tx = B.Pose([q2, 0, 0])
+    arm = root * P1 * Rx * C1.inv()
+    slide = arm * P2 * Tx * C2.inv()
+    rows = cm.link_rows["arm2"]
+    for name, want in (("base", root), ("arm", arm), ("slide", slide)):
+        g = got[rows[name]]
+        assert np.allclose(g[:3], want.raw()[:3], atol=2e-6), name
+        assert min(np.abs(g[3:] - want.raw()[3:]).max(), np.abs(g[3:] + want.raw()[3:]).max()) < 2e-6, name
+    # mass of the arm link from its box at density 1000
+    assert cm.arrays["dof_mass"][0] == pytest.approx(1000 * 8 * 0.1 * 0.02 * 0.02, rel=1e-6)
+
+
+def test_cabinet_standin_through_the_articulation_builder():
+    """The OpenCabinetDrawer stand-in assembled with create_link_builder / set_joint_properties compiles to the tables of the direct
+    description (joint frame x axis = the drawers' -x sliding direction)."""
+    from maniskill_b200.envs.open_cabinet_drawer import standin_cabinet
+    from maniskill_b200.model import ArticulationRec, pose7
+    robot, _ = standin_cabinet()
+    direct = SceneDesc(2)
+    d = ArticulationRec("cabinet", robot, pose7(), link_mu={L["name"]: 1.0 for L in robot["links"]}, disable_gravity=False)
+    d.link_groups = {L["name"]: (1, 1, 1 << 29, 0) for L in robot["links"]}
+    direct.add_articulation(d)
+    built = SceneDesc(2)
+    ab = B.scene_desc_articulation_builder(built)
+    mat = B.PhysxMaterial(1.0, 1.0, 0.0)
+    builders = []
+    for L in robot["links"]:
+        b = ab.create_link_builder(None if L["parent"] < 0 else builders[L["parent"]]).set_name(L["name"]).set_collision_groups([1, 1, 1 << 29, 0])
+        for c in L["collisions"]:
+            b.add_box_collision(B.Pose(c["p"], c["q"]), half_size=c["half_size"], material=mat)
+        I = L["inertia"]
+        b.set_mass_and_inertia(L["mass"], B.Pose(L["com"]), I[:3])
+        J = L["joint"]
+        if L["parent"] >= 0:
+            # the drawer slides along -x of the cabinet: joint frame = link frame turned half a turn about z
+            b.set_joint_name(J["name"]).set_joint_properties("prismatic", [J["lower"], J["upper"]], pose_in_parent=B.Pose(J["p"], [0, 0, 0, 1]),
+                                                             pose_in_child=B.Pose([0, 0, 0], [0, 0, 0, 1]))
+        builders.append(b)
+    ab.build(name="cabinet")
+    a, b_ = direct.compile(), built.compile()
+    for k in a.arrays:
+        assert np.allclose(a.arrays[k], b_.arrays[k], atol=1e-7), k
+    assert a.dof_names == b_.dof_names and a.link_rows == b_.link_rows
+
+
+def test_articulation_builder_errors():
+    scene = SceneDesc(1)
+    ab = B.scene_desc_articulation_builder(scene)
+    root = ab.create_link_builder().set_name("root")
+    with pytest.raises(ValueError):
+        ab.create_link_builder()                       # second root
+    child = ab.create_link_builder(root).set_name("child")
+    with pytest.raises(RuntimeError, match="no joint properties"):
+        ab.build(name="x")
+    child.set_joint_properties("revolute", [-1, 1])
+    with pytest.raises(NotImplementedError):
+        ab.build(name="x", fix_root_link=False)
+    ab.build(name="x")
+    with pytest.raises(RuntimeError):
+        ab.build(name="x")                             # duplicate name
+    with pytest.raises(RuntimeError):
+        child.build()
