@@ -222,6 +222,9 @@ class BaseEnv:
             if "fail" in info:
                 return info["success"].float() - info["fail"].float()
             return info["success"].float()
+        if "fail" in info:
+            # sapien_env.py:693 writes `-info["fail"]`, which torch refuses for a bool tensor; the documented intent (-1 on failure)
+            return -info["fail"].float()
         return torch.zeros(self.num_envs, device=self.device)
 
     # ------------------------------------------------------------------ properties

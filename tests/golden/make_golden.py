@@ -27,6 +27,7 @@ Covered reference functions (file:line):
   mani_skill/utils/wrappers/record.py:356-756          RecordEpisode.reset / step / flush_trajectory (h5py replaced by a dict-backed fake)
   mani_skill/envs/utils/observations/observations.py:16-68  sensor_data_to_pointcloud (two cameras)
   mani_skill/utils/wrappers/flatten.py:42-77            FlattenRGBDObservationWrapper.observation (two cameras, three settings)
+  mani_skill/envs/sapien_env.py:980-1016, envs/utils/randomization/batched_rng.py  seed derivation of reset(seed=...), per-sub-scene streams
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -723,6 +724,80 @@ def main():
         G[f"flat_keys_{tag}"] = np.array(sorted(out.keys()))
         for k_, v_ in out.items():
             G[f"flat_{tag}_{k_}"] = v_
+    # ---- BaseEnv._set_main_rng / _set_episode_rng (mani_skill/envs/sapien_env.py:980-1016) + BatchedRNG (batched_rng.py): seed derivation
+    brng = load("mani_skill.envs.utils.randomization.batched_rng", "mani_skill/envs/utils/randomization/batched_rng.py")
+    sys.modules["gymnasium"].Env = type("Env", (), {})
+    for mname in ("mani_skill.agents", "mani_skill.envs.scene", "mani_skill.envs.utils.observations", "mani_skill.envs.utils.system",
+                  "mani_skill.envs.utils.system.backend", "mani_skill.sensors.depth_camera", "mani_skill.utils.structs", "mani_skill.utils.structs.types",
+                  "mani_skill.utils.visualization.misc", "mani_skill.render.utils", "mani_skill.utils.tree", "dacite", "mani_skill.examples",
+                  "mani_skill.examples.real2sim_3d_assets", "sapien.utils", "sapien.utils.viewer", "sapien.utils.viewer.control_window", "sapien.render",
+                  "mani_skill.envs.utils", "mani_skill.envs.utils.randomization"):
+        if mname not in sys.modules or not isinstance(sys.modules[mname], (MagicMock, types.ModuleType)):
+            stub(mname)
+    import ast
+    for node in ast.walk(ast.parse(open(os.path.join(REF, "mani_skill/envs/sapien_env.py")).read())):   # every imported name must exist
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.split(".")[0] in ("mani_skill", "sapien", "gymnasium", "dacite"):
+            if node.module not in sys.modules:
+                stub(node.module)
+            for a in node.names:
+                if not hasattr(sys.modules[node.module], a.name):
+                    setattr(sys.modules[node.module], a.name, MagicMock(name=a.name))
+        elif isinstance(node, ast.Import):
+            for a in node.names:
+                if a.name.split(".")[0] in ("sapien", "gymnasium", "dacite") and a.name not in sys.modules:
+                    stub(a.name)
+    saved_base_env_stub = sys.modules.get("mani_skill.envs.sapien_env")
+    try:
+        se = load("mani_skill.envs.sapien_env_real", "mani_skill/envs/sapien_env.py")
+        RB_ = se.BaseEnv
+    finally:
+        if saved_base_env_stub is not None:
+            sys.modules["mani_skill.envs.sapien_env"] = saved_base_env_stub
+    se.BatchedRNG = brng.BatchedRNG
+    nv = 4
+    fe = SimpleNamespace(num_envs=nv, _main_seed=None, _batched_rng_backend="numpy:random_state", _enhanced_determinism=False,
+                         _episode_seed=np.zeros(nv, dtype=np.int64), _batched_episode_rng=None)
+    trace = []
+    def snap(tag):
+        trace.append(tag)
+        G[f"rng_{tag}_main_seed"] = np.asarray(fe._main_seed, dtype=np.int64)
+        G[f"rng_{tag}_episode_seed"] = np.asarray(fe._episode_seed, dtype=np.int64).copy()
+        G[f"rng_{tag}_draw"] = fe._batched_episode_rng.uniform(0, 1, size=(2,))          # advances the episode streams, like a task would
+        G[f"rng_{tag}_env0_normal"] = fe._episode_rng.normal(0, 0.02, (2, 3))
+    # reset(seed=7): one seed fans out to every sub-scene; then partial reset without seed under enhanced determinism; then a list of seeds
+    RB_._set_main_rng(fe, 7)
+    RB_._set_episode_rng(fe, 7, torch.arange(nv))
+    snap("a")
+    RB_._set_main_rng(fe, None)                           # unseeded reset: main rng untouched, episode rng keeps running
+    RB_._set_episode_rng(fe, None, torch.arange(nv))
+    snap("b")
+    fe._enhanced_determinism = True
+    RB_._set_main_rng(fe, None)
+    RB_._set_episode_rng(fe, None, torch.tensor([1, 3]))  # fresh episode seeds for the sub-scenes being reset, drawn from their main rngs
+    snap("c")
+    RB_._set_main_rng(fe, [11, 12, 13, 14])
+    RB_._set_episode_rng(fe, [11, 12, 13, 14], torch.arange(nv))
+    snap("d")
+    # ---- BaseEnv.step / get_reward / compute_sparse_reward (sapien_env.py:648-700,1042-1071) for every success / fail combination
+    ns = 6
+    st_succ, st_fail = torch.rand(ns, generator=g4) < 0.5, torch.rand(ns, generator=g4) < 0.3
+    st_dense = torch.rand(ns, generator=g4)
+    G["step_succ"], G["step_fail"], G["step_dense"] = st_succ, st_fail, st_dense
+    for tag, keys in (("sf", ("success", "fail")), ("s", ("success",)), ("f", ("fail",)), ("none", ())):
+        for mode in ("sparse", "dense", "normalized_dense", "none"):
+            if (tag, mode) == ("f", "sparse"):
+                continue        # sapien_env.py:693 negates a bool tensor, which torch refuses: the reference raises here
+            info0 = {k_: dict(success=st_succ, fail=st_fail)[k_].clone() for k_ in keys}
+            fs = SimpleNamespace(num_envs=ns, device=torch.device("cpu"), _elapsed_steps=torch.zeros(ns, dtype=torch.int32), _reward_mode=mode,
+                                 _step_action=lambda a: a, get_info=lambda: dict(info0), get_obs=lambda info, unflattened=True: dict(x=torch.ones(ns, 2)),
+                                 _flatten_raw_obs=lambda o: o["x"], compute_dense_reward=lambda obs, action, info: st_dense * 5,
+                                 compute_normalized_dense_reward=lambda obs, action, info: st_dense)
+            fs.get_reward = lambda obs, action, info: RB_.get_reward(fs, obs, action, info)
+            fs.compute_sparse_reward = lambda obs, action, info: RB_.compute_sparse_reward(fs, obs, action, info)
+            o_, r_, te_, tr_, i_ = RB_.step(fs, torch.zeros(ns, 3))
+            G[f"step_{tag}_{mode}_reward"] = torch.as_tensor(r_).float()
+            G[f"step_{tag}_{mode}_terminated"], G[f"step_{tag}_{mode}_truncated"] = te_, tr_
+            assert int(fs._elapsed_steps[0]) == 1
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -509,3 +509,60 @@ def test_flatten_rgbd_observation_wrapper_matches_the_reference():
             ref = G[f"flat_{tag}_{k}"]
             assert v.numpy().dtype == ref.dtype and np.array_equal(v.numpy(), ref), (tag, k)
         assert "sensor_data" in src       # the caller's dict is left intact
+
+
+def test_reset_seed_derivation_and_per_sub_scene_streams_match_the_reference():
+    """mani_skill/envs/sapien_env.py:980-1016 (`_set_main_rng`, `_set_episode_rng`) + envs/utils/randomization/batched_rng.py run by the
+    reference's own code: reset(seed=7) fans one seed out to every sub-scene, an unseeded reset keeps the streams running, enhanced
+    determinism re-seeds exactly the sub-scenes being reset from their main generators, a list of seeds is taken as is -- compared
+    through the seeds and through draws from the resulting generators."""
+    from maniskill_b200.envs.base_env import BaseEnv
+    nv = 4
+    fe = SimpleNamespace(num_envs=nv, _main_seed=None, _enhanced_determinism=False, _episode_seed=np.zeros(nv, dtype=np.int64), _batched_episode_rng=None,
+                         _batched_main_rng=None, _episode_rng=None)
+
+    def check(tag):
+        assert np.array_equal(np.asarray(fe._main_seed, dtype=np.int64), G[f"rng_{tag}_main_seed"]), tag
+        assert np.array_equal(np.asarray(fe._episode_seed, dtype=np.int64), G[f"rng_{tag}_episode_seed"]), tag
+        assert np.array_equal(fe._batched_episode_rng.uniform(0, 1, size=(2,)), G[f"rng_{tag}_draw"]), tag
+        assert np.array_equal(fe._episode_rng.normal(0, 0.02, (2, 3)), G[f"rng_{tag}_env0_normal"]), tag
+
+    BaseEnv._set_main_rng(fe, 7)
+    BaseEnv._set_episode_rng(fe, 7, torch.arange(nv))
+    check("a")
+    BaseEnv._set_main_rng(fe, None)
+    BaseEnv._set_episode_rng(fe, None, torch.arange(nv))
+    check("b")
+    fe._enhanced_determinism = True
+    BaseEnv._set_main_rng(fe, None)
+    BaseEnv._set_episode_rng(fe, None, torch.tensor([1, 3]))
+    check("c")
+    BaseEnv._set_main_rng(fe, [11, 12, 13, 14])
+    BaseEnv._set_episode_rng(fe, [11, 12, 13, 14], torch.arange(nv))
+    check("d")
+    assert len(set(G["rng_a_episode_seed"].tolist())) == nv and not np.array_equal(G["rng_c_episode_seed"], G["rng_b_episode_seed"])
+
+
+def test_step_termination_and_reward_dispatch_match_the_reference():
+    """mani_skill/envs/sapien_env.py:648-700,1042-1071 run by the reference's own code on scripted task hooks, for every combination of
+    success / fail being reported and every reward mode: reward, terminated (success | fail), truncated (never set by BaseEnv), and the
+    step counter.  (Fail-only + sparse is left out: the reference negates a bool tensor there and raises.)"""
+    from maniskill_b200.envs.base_env import BaseEnv
+    succ, fail, dense = T("step_succ"), T("step_fail"), T("step_dense")
+    ns = len(succ)
+    for tag, keys in (("sf", ("success", "fail")), ("s", ("success",)), ("f", ("fail",)), ("none", ())):
+        for mode in ("sparse", "dense", "normalized_dense", "none"):
+            if (tag, mode) == ("f", "sparse"):
+                continue
+            info0 = {k: dict(success=succ, fail=fail)[k].clone() for k in keys}
+            fs = SimpleNamespace(num_envs=ns, device=torch.device("cpu"), _elapsed_steps=torch.zeros(ns, dtype=torch.int32), _reward_mode=mode, _fused=None,
+                                 _state_version=0, _step_action=lambda a: a, get_info=lambda: dict(info0), get_obs=lambda info: torch.ones(ns, 2),
+                                 compute_dense_reward=lambda obs, action, info: dense * 5, compute_normalized_dense_reward=lambda obs, action, info: dense)
+            fs.get_reward = lambda obs, action, info: BaseEnv.get_reward(fs, obs, action, info)
+            fs.compute_sparse_reward = lambda obs, action, info: BaseEnv.compute_sparse_reward(fs, obs, action, info)
+            o, r, te, tr, i = BaseEnv.step(fs, torch.zeros(ns, 3))
+            close(r.float(), G[f"step_{tag}_{mode}_reward"], 1e-7)
+            assert np.array_equal(te.numpy(), G[f"step_{tag}_{mode}_terminated"]) and np.array_equal(tr.numpy(), G[f"step_{tag}_{mode}_truncated"])
+            assert int(fs._elapsed_steps[0]) == 1
+    fs = SimpleNamespace(num_envs=ns, device=torch.device("cpu"))
+    assert torch.equal(BaseEnv.compute_sparse_reward(fs, None, None, dict(fail=fail)), -fail.float())      # the documented intent of the raising line
