@@ -1,0 +1,182 @@
+"""CPU, only where the reference checkout exists (skipped elsewhere): methods of the reference's OWN `ManiSkillScene`
+(mani_skill/envs/scene.py: `_gpu_apply_all`, `_gpu_fetch_all`, `get_pairwise_contact_impulses / _forces`) executed unmodified with `self.px` =
+the `PhysxGpuSystem` facade of this repo (maniskill_b200/physx_shim.py) over the emulated backend.  The file is loaded from
+/root/reference with its imports stubbed (sapien & co. are not installed); nothing of it is copied.  What the reference code computes
+through the facade must equal what the BaseEnv mirror computes on its own path."""
+import ast
+import importlib.util
+import os
+import sys
+from types import SimpleNamespace
+from unittest.mock import MagicMock
+
+import pytest
+import torch
+
+import maniskill_b200 as ms
+from emu_world import EmuBackendWorld
+
+SCENE_PY = "/root/reference/mani_skill/envs/scene.py"
+pytestmark = pytest.mark.skipif(not os.path.exists(SCENE_PY), reason="needs the reference checkout")
+
+
+def _load_reference_module(path, as_name=None):
+    """Execute one reference source file with every `mani_skill.*` / `sapien.*` import replaced by a MagicMock module (`as_name`: also
+    register the result under that module name, so that a later file imports the real thing instead of a mock)."""
+    def ensure(name):
+        if name not in sys.modules:
+            m = MagicMock(name=name)
+            m.__name__, m.__path__, m.__all__ = name, [], []
+            sys.modules[name] = m
+
+    for node in ast.walk(ast.parse(open(path).read())):
+        names = [node.module] if isinstance(node, ast.ImportFrom) and node.module else [a.name for a in node.names] if isinstance(node, ast.Import) else []
+        for name in names:
+            if name.split(".")[0] in ("mani_skill", "sapien", "trimesh", "gymnasium", "transforms3d", "dacite", "lxml", "pytorch_kinematics"):
+                parts = name.split(".")
+                for i in range(1, len(parts) + 1):
+                    ensure(".".join(parts[:i]))
+    spec = importlib.util.spec_from_file_location(as_name or "_reference_" + os.path.basename(path)[:-3], path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod          # dataclasses look their module up while the class body runs
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def reference_module():
+    saved = dict(sys.modules)
+    try:
+        yield _load_reference_module
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+@pytest.fixture()
+def reference_scene_class(reference_module):
+    return reference_module(SCENE_PY).ManiSkillScene
+
+
+def test_reference_scene_methods_run_on_the_px_facade(reference_scene_class):
+    RS = reference_scene_class
+    n = 3
+    ours, theirs = [ms.make("PickCube-v1", num_envs=n, obs_mode="state", control_mode="pd_joint_pos", world_factory=EmuBackendWorld, fused=False) for _ in range(2)]
+    for e in (ours, theirs):
+        e.reset(seed=4)
+    px = theirs.scene.px
+    ref_scene = RS.__new__(RS)
+    ref_scene.__dict__.update(px=px, gpu_sim_enabled=True, non_static_actors=[object()], articulations={"panda": object()}, _needs_fetch=False,
+                              pairwise_contact_queries={}, _pairwise_contact_query_unique_hashes={})
+    class Obj:   # what the query code reads off an Actor / Link: `.name`, `._bodies` (one body per sub-scene), hashability
+        def __init__(self, name):
+            self.name, self._bodies = name, [[b for b in px.bodies[e] if b.name == name][0] for e in range(n)]
+    by_name = Obj
+    cube, lf, rf, table = by_name("cube"), by_name("panda_panda_leftfinger"), by_name("panda_panda_rightfinger"), by_name("table-workspace")
+    g = torch.Generator().manual_seed(2)
+    for t in range(6):
+        a = 2 * torch.rand(n, 8, generator=g) - 1
+        a[:, 7] = -1.0                                       # close the gripper
+        ours.step(a)
+        # the reference's control step (sapien_env.py:1110-1131) with the reference's own scene methods
+        theirs.agent.set_action(a)
+        theirs.scene._dirty = 0
+        RS._gpu_apply_all(ref_scene)                         # all eight px.gpu_apply_* calls
+        assert ref_scene._needs_fetch
+        for _ in range(5):
+            px.step()
+        RS._gpu_fetch_all(ref_scene)                         # all eight px.gpu_fetch_* calls
+        assert not ref_scene._needs_fetch
+        with pytest.raises(AssertionError):
+            ref_scene._needs_fetch = True
+            RS._gpu_apply_all(ref_scene)                     # the reference's guard against apply-apply without a fetch
+        ref_scene._needs_fetch = False
+        assert torch.equal(px.cuda_rigid_body_data.torch(), ours.scene.world.rigid_body_data)
+        assert torch.equal(px.cuda_articulation_qpos.torch(), ours.scene.world.qpos)
+    # contact queries through the reference's caching logic (query built once per pair of names, then re-run)
+    for a_, b_, oa, ob in ((cube, table, ours.cube, ours.table), (lf, cube, ours.agent.finger1_link, ours.cube), (rf, cube, ours.agent.finger2_link, ours.cube)):
+        imp = RS.get_pairwise_contact_impulses(ref_scene, a_, b_)
+        assert imp.shape == (n, 3) and torch.allclose(imp, ours.scene.get_pairwise_contact_impulses(oa, ob), atol=1e-7)
+        frc = RS.get_pairwise_contact_forces(ref_scene, a_, b_)
+        assert torch.allclose(frc, ours.scene.get_pairwise_contact_forces(oa, ob), atol=1e-5)
+    assert set(ref_scene.pairwise_contact_queries) == {"cubetable-workspace", "panda_panda_leftfingercube", "panda_panda_rightfingercube"}
+    assert (RS.get_pairwise_contact_impulses(ref_scene, cube, table)[:, 2] > 0).all()     # the table pushes the cube up
+
+
+def test_reference_rigid_body_struct_reads_through_the_px_facade(reference_module):
+    """mani_skill/utils/structs/base.py (`PhysxRigidBodyComponentStruct`): `_body_data_index` from `body.gpu_pose_index`, velocities sliced out
+    of `px.cuda_rigid_body_data`, the net-contact query built by `px.gpu_create_contact_body_impulse_query(self._bodies)` -- the reference's
+    own accessors, with our body handles and facade underneath."""
+    base = reference_module("/root/reference/mani_skill/utils/structs/base.py")
+    RB = base.PhysxRigidBodyComponentStruct
+    n = 3
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld, fused=False)
+    env.reset(seed=9)
+    px = env.scene.px
+    lifted = env.cube.pose.raw_pose.clone()
+    lifted[1, :3] = torch.tensor([0.3, 0.3, 0.3])             # the cube of sub-scene 1 falls (clear of the gripper), the others rest
+    from maniskill_b200.structs import Pose
+    env.cube.set_pose(Pose(lifted))
+    env.scene._gpu_apply_all()
+    for _ in range(2):
+        env.step(torch.zeros(n, 8))
+    cube = RB.__new__(RB)
+    cube.__dict__.update(scene=SimpleNamespace(px=px, gpu_sim_enabled=True, timestep=px.timestep, device=torch.device("cpu")), _body_data_name="cuda_rigid_body_data",
+                         _body_data_index_internal=None, _bodies=[[b for b in px.bodies[e] if b.name == "cube"][0] for e in range(n)])
+    assert cube._body_data_index.tolist() == [e * env.scene.world.n_rows + env.cube.row for e in range(n)]
+    assert torch.equal(cube.linear_velocity, env.cube.linear_velocity) and torch.equal(cube.angular_velocity, env.cube.angular_velocity)
+    assert float(cube.linear_velocity[1, 2]) == pytest.approx(-9.81 * 0.1, rel=2e-2) and float(cube.linear_velocity[0, 2].abs()) < 1e-3
+    imp = cube.get_net_contact_impulses()
+    assert torch.allclose(imp, env.scene.get_net_contact_impulses(env.cube), atol=1e-7)
+    assert torch.equal(imp[1], torch.zeros(3)) and (imp[[0, 2], 2] > 0).all()           # in free fall nothing touches the cube
+    assert torch.allclose(cube.get_net_contact_forces(), imp / 0.01)
+
+
+def test_reference_articulation_struct_reads_and_writes_through_the_px_facade(reference_module):
+    """mani_skill/utils/structs/articulation.py: `_data_index` from `gpu_index`, the `qpos` property (read and masked write into
+    `px.cuda_articulation_qpos`), `get_joint_target_indices` + `set_joint_drive_targets` (meshgrid write into
+    `px.cuda_articulation_target_qpos`) -- the reference's accessors on our handles; the mirror's Articulation sees the same numbers."""
+    base = reference_module("/root/reference/mani_skill/utils/structs/base.py", as_name="mani_skill.utils.structs.base")
+    sys.modules["mani_skill.utils.structs"].BaseStruct = base.BaseStruct          # the real class to inherit from, not a mock
+    art_mod = reference_module("/root/reference/mani_skill/utils/structs/articulation.py")
+    art_mod.common = SimpleNamespace(to_tensor=lambda x, device=None: torch.as_tensor(x, device=device))
+    art_mod.ArticulationJoint = type("ArticulationJoint", (), {})        # isinstance() target; joints are addressed by index here
+    RA = art_mod.Articulation
+    n = 3
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="state", control_mode="pd_joint_pos", world_factory=EmuBackendWorld, fused=False)
+    env.reset(seed=1)
+    px = env.scene.px
+    scene = SimpleNamespace(px=px, gpu_sim_enabled=True, device=torch.device("cpu"), _reset_mask=torch.tensor([True, False, True]))
+    robot = RA.__new__(RA)
+    robot.__dict__.update(scene=scene, _objs=[px.articulations[e][0] for e in range(n)], _scene_idxs=torch.arange(n), _cached_joint_target_indices={})
+    assert robot._data_index.tolist() == [0, 1, 2] and robot.max_dof == 9
+    assert torch.equal(robot.qpos, env.agent.robot.get_qpos())
+    # masked write (sub-scenes 0 and 2, as during a partial reset), then apply + kinematics + fetch through the facade
+    new_q = robot.qpos[[0, 2]].clone()
+    new_q[:, 0] += 0.25
+    before = env.agent.robot.get_qpos().clone()
+    robot.qpos = new_q
+    px.gpu_apply_articulation_qpos()
+    px.gpu_update_articulation_kinematics()
+    px.gpu_fetch_articulation_qpos()
+    after = env.agent.robot.get_qpos()
+    assert torch.allclose(after[[0, 2], 0], before[[0, 2], 0] + 0.25) and torch.equal(after[1], before[1])
+    # drive targets of the arm joints of the masked sub-scenes
+    arm = torch.arange(7, dtype=torch.int32)      # the controllers hold int32 joint indices (base_controller.py)
+    gx, gy = robot.get_joint_target_indices(arm)
+    assert gx.shape == (n, 7) and gy[0].tolist() == list(range(7))
+    q_now = robot.qpos.clone()
+    tgt = q_now[[0, 2], :7].clone()
+    tgt[:, 0] += 0.3                                          # turn the first joint, hold the others
+    robot.set_joint_drive_targets(tgt, joint_indices=arm)
+    px.gpu_apply_articulation_target_position()
+    px.gpu_fetch_articulation_target_qpos()
+    t = px.cuda_articulation_target_qpos.torch()
+    assert torch.allclose(t[[0, 2], :7], tgt) and abs(float(t[1, 0] - q_now[1, 0])) < 0.05
+    for _ in range(60):
+        px.step()
+    px.gpu_fetch_articulation_qpos()
+    q = robot.qpos
+    assert (q[[0, 2], 0] - tgt[:, 0]).abs().max() < 0.02 and abs(float(q[1, 0] - q_now[1, 0])) < 0.02      # only the driven arms turned
