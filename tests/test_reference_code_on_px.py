@@ -180,3 +180,22 @@ def test_reference_articulation_struct_reads_and_writes_through_the_px_facade(re
     px.gpu_fetch_articulation_qpos()
     q = robot.qpos
     assert (q[[0, 2], 0] - tgt[:, 0]).abs().max() < 0.02 and abs(float(q[1, 0] - q_now[1, 0])) < 0.02      # only the driven arms turned
+
+
+def test_reference_texture_transforms_on_our_render_targets(reference_module):
+    """mani_skill/render/shaders.py `PREBUILT_SHADER_CONFIGS["minimal"].texture_transforms`: the reference's own slicing of the raw `Color` /
+    `PositionSegmentation` targets, applied to the targets of our camera group, equals the `sensor_data` the mirror delivers."""
+    shaders = reference_module("/root/reference/mani_skill/render/shaders.py")
+    cfg = shaders.PREBUILT_SHADER_CONFIGS["minimal"]
+    assert cfg.texture_names == {"Color": ["rgb"], "PositionSegmentation": ["position", "depth", "segmentation"]}
+    env = ms.make("StackCube-v1", num_envs=2, obs_mode="sensor_data", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    group = env._sensors.group
+    for i, cam in enumerate(env._sensors.cams):
+        want = {}
+        for name, transform in cfg.texture_transforms.items():
+            want.update(transform(group.get_picture_cuda(name, i)))
+        got = obs["sensor_data"][cam["uid"]]
+        assert set(got) == set(want) == {"rgb", "position", "depth", "segmentation"}
+        for k in want:
+            assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), (cam["uid"], k)
