@@ -132,7 +132,8 @@ class BaseEnv:
 
     def __init__(self, num_envs: int = 1, obs_mode: Optional[str] = None, reward_mode: Optional[str] = None,
                  control_mode: Optional[str] = None, sim_config: Optional[dict] = None, device: Union[str, torch.device, None] = None,
-                 world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True):
+                 world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True,
+                 enhanced_determinism: bool = False, reconfiguration_freq: Optional[int] = None):
         self.num_envs = num_envs
         self._obs_mode = "state" if obs_mode is None else obs_mode
         self.obs_mode_struct = parse_obs_mode(self._obs_mode)   # raises NotImplementedError for unknown / unsupported textures
@@ -152,7 +153,8 @@ class BaseEnv:
         self._batched_main_rng = None
         self._batched_episode_rng = None
         self._episode_rng = None
-        self._enhanced_determinism = False
+        # sapien_env.py:115-118: with it, resets without a seed re-seed the episode RNG of the sub-scenes being reset from their main RNG
+        self._enhanced_determinism = bool(enhanced_determinism)
         self._sensor_overrides = sensor_configs or {}
         self._visual = self.obs_mode_struct.visual
         if enable_cameras is not None:
@@ -161,22 +163,39 @@ class BaseEnv:
         # tasks can draw per-env geometry from `_batched_episode_rng` while building (peg_insertion_side.py:114-120)
         self._set_main_rng([2022 + i for i in range(num_envs)])
         self._set_episode_rng([2022 + i for i in range(num_envs)], np.arange(num_envs))
-        # ---- build the scene (sapien_env.py:725-770 `_reconfigure`)
+        self._control_mode_arg, self._fused_arg = control_mode, fused
+        # sapien_env.py:91-95,215-216: rebuild the scene every `reconfiguration_freq` resets (0 = never)
+        self.reconfiguration_freq = int(reconfiguration_freq) if reconfiguration_freq is not None else 0
+        self._reconfig_counter = 0
+        self.scene = None
+        self._reconfigure(dict())
+        # sapien_env.py:321-327: main RNG seeds 2022+i, first reset
+        self._set_main_rng([2022 + i for i in range(num_envs)])
+        self._elapsed_steps[:] = 0
+        self.reset(seed=[2022 + i for i in range(num_envs)])
+
+    # ------------------------------------------------------------------ scene (re)build (sapien_env.py:725-770 `_reconfigure`)
+    def _reconfigure(self, options: dict):
+        """Build the sub-scene prototype from the task's description hooks, compile it and create the world; an existing world is
+        destroyed first.  Tasks that draw geometry while building (per-env sizes from `_batched_episode_rng`) get new draws."""
+        num_envs = self.num_envs
+        if self.scene is not None and hasattr(self.scene.world, "close"):
+            self.scene.world.close()
         self.scene_desc = SceneDesc(num_envs, self.sim_params)
         self._load_agent_desc()
         self._load_scene_desc()
         self.cm = self.scene_desc.compile()
-        if world_factory is None:
+        if self._world_factory is None:
             from ..backend import World
-            world = World(self.cm, device)
+            world = World(self.cm, self._requested_device)
         else:
-            world = world_factory(self.cm)
+            world = self._world_factory(self.cm)
         self.scene = Scene(world, self.cm, self.scene_desc)
         self.device = self.scene.device
         self._elapsed_steps = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
         self._hidden_objects = []
         self._after_build()
-        self.agent.set_control_mode(control_mode)
+        self.agent.set_control_mode(self._control_mode_arg)
         self.single_action_space_low, self.single_action_space_high = self.agent.action_bounds()
         self.action_dim = self.single_action_space_low.shape[0]
         self._sensors = self._setup_sensors() if self._visual else {}
@@ -185,12 +204,10 @@ class BaseEnv:
         # the fused control step serves the flat-state observation directly; tasks that can rebuild their observation dict from the
         # fused state vector (`_obs_from_fused`) use it under the visual modes too (B2S_FUSED_VISUAL=0 keeps the torch path there; tests/test_gpu_env.py compares the two)
         fused_visual = self._visual and hasattr(self, "_obs_from_fused") and os.environ.get("B2S_FUSED_VISUAL", "1") not in ("", "0")
-        if fused and world_factory is None and (self._obs_mode == "state" or fused_visual):
+        if self._fused_arg and self._world_factory is None and (self._obs_mode == "state" or fused_visual):
             self._fused = self._setup_fused_step()
-        # sapien_env.py:321-327: main RNG seeds 2022+i, first reset
-        self._set_main_rng([2022 + i for i in range(num_envs)])
-        self._elapsed_steps[:] = 0
-        self.reset(seed=[2022 + i for i in range(num_envs)])
+        self._state_version += 1
+        self._reconfig_counter = self.reconfiguration_freq
 
     # ------------------------------------------------------------------ task hooks (same names as the reference)
     def _load_agent_desc(self):
@@ -295,14 +312,27 @@ class BaseEnv:
             env_idx = U.to_tensor(options["env_idx"], self.device, dtype=torch.int64).long()
         else:
             env_idx = torch.arange(0, self.num_envs, device=self.device)
+        reconfigure = bool(options.get("reconfigure", False)) or (self._reconfig_counter == 0 and self.reconfiguration_freq != 0)
+        if reconfigure and len(env_idx) != self.num_envs:
+            raise RuntimeError("Cannot do a partial reset and reconfigure the environment. You must do one or the other.")   # sapien_env.py:903
         self._set_main_rng(seed)
-        self._set_episode_rng(seed, env_idx)
+        if reconfigure:  # sapien_env.py:909-916
+            self._set_episode_rng(seed if seed is not None else self._batched_main_rng.randint(2**31), env_idx)
+            with torch.random.fork_rng(devices=[self.device] if self.device.type == "cuda" else []):
+                torch.manual_seed(int(self._episode_seed[0]))
+                self._reconfigure(options)
+            env_idx = env_idx.to(self.device)
+            self._set_episode_rng(self._episode_seed, env_idx)   # again, so that what follows does not depend on the draws of the build
+        else:
+            self._set_episode_rng(seed, env_idx)
         self._state_version += 1  # invalidates per-state caches of derived poses (tasks may memoise them between fetches)
         self.scene._reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.scene._reset_mask[env_idx] = True
         self.scene._reset_all = False
         self._elapsed_steps[env_idx] = 0
         self._clear_sim_state()
+        if self.reconfiguration_freq != 0:
+            self._reconfig_counter -= 1
         self.agent.reset()
         if "reset_to_env_states" in options:
             self.set_state_dict(options["reset_to_env_states"]["env_states"], env_idx)
@@ -321,7 +351,7 @@ class BaseEnv:
         self.agent.controller_reset(env_idx)
         info = self.get_info()
         obs = self.get_obs(info)
-        info["reconfigure"] = False
+        info["reconfigure"] = reconfigure
         self._last_obs = obs
         return obs, info
 

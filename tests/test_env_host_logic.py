@@ -420,3 +420,60 @@ def test_roll_ball_reset_layout_stateful_reward_and_a_rolling_ball():
     assert hit.all(), (env.ball.pose.p, env.goal_region.pose.p)
     w = env.ball.angular_velocity
     assert (torch.linalg.norm(w, dim=1) > 1.0).any() or (torch.linalg.norm(env.ball.linear_velocity, dim=1) < 0.05).all()
+
+
+def test_seeded_sequence_reset_with_enhanced_determinism():
+    """tests/test_envs.py:166-184 of the reference: with `enhanced_determinism=True` the unseeded resets inside a rollout draw their
+    episode seeds from the main generator, so the whole sequence (17 steps through episodes of 5) repeats after `reset(seed=2000)`;
+    without it the unseeded resets continue the running streams, and the layouts after the same number of resets differ between the
+    two settings."""
+    N = 17
+    g = torch.Generator().manual_seed(0)
+    actions = [2 * torch.rand(1, 8, generator=g) - 1 for _ in range(N)]
+
+    def rollout(env):
+        obs, _ = env.reset(seed=2000)
+        for a in actions:
+            obs, _, _, _, _ = env.step(a)
+            if int(env.elapsed_steps[0]) >= 5:       # TimeLimit of the reference's gym.make(max_episode_steps=5)
+                obs, _ = env.reset()
+        return obs.clone()
+
+    env = ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
+    first, again = rollout(env), rollout(env)
+    assert torch.allclose(first, again, atol=1e-5)
+    seeds_det = env._episode_seed.copy()
+    plain = ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld)
+    p1 = rollout(plain)
+    assert plain._episode_seed[0] == 2000 and seeds_det[0] != 2000          # episode seed re-drawn only under enhanced determinism
+    assert not torch.allclose(p1, first, atol=1e-4)
+
+
+def test_reconfigure_rebuilds_the_scene():
+    """sapien_env.py:895-916 + tests/test_gpu_envs.py:145-155: `reset(options=dict(reconfigure=True))` rebuilds the scene -- tasks that draw
+    geometry while building get new draws (PegInsertionSide: per-sub-scene peg sizes), seeded reconfiguration is reproducible, a partial
+    reset cannot reconfigure, and `reconfiguration_freq=1` rebuilds on every reset."""
+    env = ms.make("PegInsertionSide-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    env.reset(seed=0)
+    sizes0 = env.peg_half_sizes.clone()
+    world0 = env.scene.world
+    obs, info = env.reset(seed=5, options=dict(reconfigure=True))
+    assert info["reconfigure"] and env.scene.world is not world0
+    sizes1 = env.peg_half_sizes.clone()
+    assert not torch.allclose(sizes0, sizes1)
+    for _ in range(3):
+        obs, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert torch.isfinite(obs).all() and int(env.elapsed_steps[0]) == 3
+    obs2, info2 = env.reset(seed=5, options=dict(reconfigure=True))
+    assert torch.allclose(env.peg_half_sizes, sizes1) and torch.allclose(obs2, env.reset(seed=5, options=dict(reconfigure=True))[0], atol=1e-5)
+    _, info3 = env.reset(seed=5)
+    assert not info3["reconfigure"] and torch.allclose(env.peg_half_sizes, sizes1)      # a plain reset keeps the geometry
+    with pytest.raises(RuntimeError, match="partial reset and reconfigure"):
+        env.reset(options=dict(reconfigure=True, env_idx=torch.tensor([0])))
+    every = ms.make("PegInsertionSide-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld, reconfiguration_freq=1)
+    a = every.peg_half_sizes.clone()
+    _, info = every.reset()
+    assert info["reconfigure"] and not torch.allclose(every.peg_half_sizes, a)
+    b = every.peg_half_sizes.clone()
+    _, info = every.reset()
+    assert info["reconfigure"] and not torch.allclose(every.peg_half_sizes, b)
