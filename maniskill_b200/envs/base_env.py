@@ -21,6 +21,7 @@ from ..backend import (BUF_ALL, BUF_APPLY_ALL, BUF_QF, BUF_QPOS, BUF_QVEL, BUF_R
                        BUF_TARGET_QVEL)
 from ..model import CompiledModel, SceneDesc, SimParams
 from ..observations import parse_obs_mode, sensor_data_to_pointcloud
+from ..visualization import camera_observations_to_images, tile_images
 from ..structs import Actor, Articulation, Pose
 
 
@@ -128,12 +129,13 @@ class BaseEnv:
     # sapien_env.py:124: the named modes + "any_textures" = every '+'-combination of the textures the shader writes (and state flags)
     SUPPORTED_OBS_MODES = ("state", "state_dict", "none", "sensor_data", "any_textures", "pointcloud")
     SUPPORTED_REWARD_MODES = ("normalized_dense", "dense", "sparse", "none")
+    SUPPORTED_RENDER_MODES = ("rgb_array", "sensors", "all")   # "human" needs the interactive viewer, which is out of scope
     max_episode_steps: Optional[int] = None
 
     def __init__(self, num_envs: int = 1, obs_mode: Optional[str] = None, reward_mode: Optional[str] = None,
                  control_mode: Optional[str] = None, sim_config: Optional[dict] = None, device: Union[str, torch.device, None] = None,
                  world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True,
-                 enhanced_determinism: bool = False, reconfiguration_freq: Optional[int] = None):
+                 enhanced_determinism: bool = False, reconfiguration_freq: Optional[int] = None, render_mode: Optional[str] = None):
         self.num_envs = num_envs
         self._obs_mode = "state" if obs_mode is None else obs_mode
         self.obs_mode_struct = parse_obs_mode(self._obs_mode)   # raises NotImplementedError for unknown / unsupported textures
@@ -164,6 +166,9 @@ class BaseEnv:
         self._set_main_rng([2022 + i for i in range(num_envs)])
         self._set_episode_rng([2022 + i for i in range(num_envs)], np.arange(num_envs))
         self._control_mode_arg, self._fused_arg = control_mode, fused
+        if render_mode not in self.SUPPORTED_RENDER_MODES + (None,):
+            raise NotImplementedError(f"Unsupported render mode {render_mode}.")
+        self.render_mode = render_mode
         # sapien_env.py:91-95,215-216: rebuild the scene every `reconfiguration_freq` resets (0 = never)
         self.reconfiguration_freq = int(reconfiguration_freq) if reconfiguration_freq is not None else 0
         self._reconfig_counter = 0
@@ -199,6 +204,7 @@ class BaseEnv:
         self.single_action_space_low, self.single_action_space_high = self.agent.action_bounds()
         self.action_dim = self.single_action_space_low.shape[0]
         self._sensors = self._setup_sensors() if self._visual else {}
+        self._human_render_cameras = None    # created on the first render_rgb_array()
         self._last_obs = None
         self._fused = None
         # the fused control step serves the flat-state observation directly; tasks that can rebuild their observation dict from the
@@ -496,6 +502,68 @@ class BaseEnv:
         self._sensors.capture()
         m = self.obs_mode_struct
         return self._sensors.get_obs(rgb=m.rgb, depth=m.depth, segmentation=m.segmentation, position=m.position)
+
+    # ------------------------------------------------------------------ render modes (sapien_env.py:1369-1439)
+    def _human_render_camera_configs(self):
+        """task hook: cameras for `render_rgb_array` (same dict layout as `_sensor_configs`)."""
+        return []
+
+    def _make_camera_group(self, configs, overrides=None, include_hidden=False):
+        from ..render import CameraSensors, camera_desc
+        cams = []
+        for c in configs:
+            c = dict(c)
+            c.update((overrides or {}).get(c["uid"], {}))
+            row = -1
+            if c.get("mount") is not None:
+                art, link = c["mount"]
+                row = self.cm.link_rows[art][link]
+            cams.append(camera_desc(c["uid"], c["pose"], c["width"], c["height"], c["fov"], c["near"], c["far"], row))
+        return CameraSensors(self.scene.world, self.cm, cams, include_hidden=include_hidden)
+
+    def render_rgb_array(self, camera_name: Optional[str] = None):
+        """[num_envs, H, W, 3] uint8 from the human render cameras (all of them tiled, or the one named); hidden objects are shown."""
+        if self._human_render_cameras is None:
+            cfgs = self._human_render_camera_configs()
+            if not cfgs:
+                return None
+            self._human_render_cameras = self._make_camera_group(cfgs, include_hidden=True)
+        self._human_render_cameras.capture()
+        data = self._human_render_cameras.get_obs(rgb=True, depth=False, segmentation=False)
+        images = [v["rgb"] for k, v in data.items() if camera_name is None or k == camera_name]
+        if not images:
+            return None
+        return images[0] if len(images) == 1 else tile_images(images)
+
+    def get_sensor_images(self):
+        """sapien_env.py:567-569: what the sensors currently see, as displayable images per sensor and texture."""
+        if not self._sensors:
+            self._sensors = self._setup_sensors()
+        self._sensors.capture()
+        data = self._sensors.get_obs(rgb=True, depth=True, segmentation=False)
+        return {uid: camera_observations_to_images(d) for uid, d in data.items()}
+
+    def render_sensors(self):
+        return tile_images([img for d in self.get_sensor_images().values() for img in d.values()])
+
+    def render_all(self):
+        images = []
+        human = self.render_rgb_array()
+        if human is not None:
+            images.append(human)
+        images += [img for d in self.get_sensor_images().values() for img in d.values()]
+        return tile_images(images)
+
+    def render(self):
+        if self.render_mode is None:
+            raise RuntimeError("render_mode is not set.")
+        if self.render_mode == "rgb_array":
+            return self.render_rgb_array()
+        if self.render_mode == "sensors":
+            return self.render_sensors()
+        if self.render_mode == "all":
+            return self.render_all()
+        raise NotImplementedError(f"Unsupported render mode {self.render_mode}.")
 
     def get_sensor_params(self):
         return self._sensors.get_params(self.scene.world.body_view()) if self._sensors else {}

@@ -55,6 +55,10 @@ class LiftPegUprightEnv(BaseEnv):
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
 
+    # ---- lift_peg_upright.py:49-52
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     # ---- table/scene_builder.py:68-103 + lift_peg_upright.py:74-86
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)

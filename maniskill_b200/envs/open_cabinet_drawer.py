@@ -153,6 +153,10 @@ class OpenCabinetDrawerEnv(BaseEnv):
         self.handle_link_goal.set_pose(Pose.create_from_pq(p=self.handle_link_positions(), device=self.device))
         self.scene._gpu_apply_all()
 
+    # ---- open_cabinet_drawer.py:102-107
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([-1.8, -1.3, 1.8], [-0.3, 0.5, 0]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     def evaluate(self):
         open_enough = self._target_joint_qpos() >= self.target_qpos
         handle_link_pos = self.handle_link_positions()

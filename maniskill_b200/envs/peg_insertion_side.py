@@ -94,6 +94,10 @@ class PegInsertionSideEnv(BaseEnv):
         return [dict(uid="base_camera", pose=U.look_at([0, -0.3, 0.2], [0, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None),
                 dict(uid="hand_camera", pose=pose7(), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=("panda_wristcam", "camera_link"))]
 
+    # ---- :101-104
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([0.5, -0.5, 0.8], [0.05, -0.1, 0.4]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     # ---- :193-249
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)

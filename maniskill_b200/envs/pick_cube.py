@@ -89,6 +89,10 @@ class PickCubeEnv(BaseEnv):
         return [dict(uid="base_camera", pose=U.look_at(self.sensor_cam_eye_pos, self.sensor_cam_target_pos), width=128, height=128,
                      fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
 
+    # ---- pick_cube.py:73-78
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     # ---- table/scene_builder.py:68-103 + pick_cube.py:106-130
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)

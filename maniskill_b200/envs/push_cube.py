@@ -53,6 +53,10 @@ class PushCubeEnv(BaseEnv):
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
 
+    # ---- push_cube.py:93-99 (PullCube-v1: pull_cube.py:49-52, the same camera)
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([0.6, 0.7, 0.6], [0.0, 0.0, 0.35]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     # ---- table/scene_builder.py:68-103 + push_cube.py:143-177
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)

@@ -52,6 +52,10 @@ class RollBallEnv(BaseEnv):
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at([-0.1, 0.9, 0.3], [0.0, 0.0, 0.0]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
 
+    # ---- roll_ball.py:60-63
+    def _human_render_camera_configs(self):
+        return [dict(uid="render_camera", pose=U.look_at([-0.6, 1.3, 0.8], [0.0, 0.13, 0.0]), width=512, height=512, fov=1, near=0.01, far=100.0, mount=None)]
+
     # ---- table/scene_builder.py:68-103 + roll_ball.py:95-128
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)

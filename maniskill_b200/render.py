@@ -64,10 +64,12 @@ def camera_desc(uid, pose7, width, height, fov, near, far, mount_row=-1):
 class CameraSensors:
     """All cameras of a task as one camera group (mani_skill/envs/scene.py:1087-1106) + the obs-facing accessors."""
 
-    def __init__(self, world, cm: CompiledModel, cams: List[dict]):
+    def __init__(self, world, cm: CompiledModel, cams: List[dict], include_hidden: bool = False):
+        """include_hidden: also draw the objects the task hides from its sensors (the human render cameras show them,
+        sapien_env.py:1373-1374)."""
         self.world = world
         self.cams = cams
-        self.visuals = build_visual_table(cm, world.n_envs)
+        self.visuals = build_visual_table(cm, world.n_envs, include_hidden=include_hidden)
         self.group = world.create_camera_group(cams, self.visuals)
 
     def capture(self):

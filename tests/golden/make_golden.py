@@ -28,6 +28,7 @@ Covered reference functions (file:line):
   mani_skill/envs/utils/observations/observations.py:16-68  sensor_data_to_pointcloud (two cameras)
   mani_skill/utils/wrappers/flatten.py:42-77            FlattenRGBDObservationWrapper.observation (two cameras, three settings)
   mani_skill/envs/sapien_env.py:980-1016, envs/utils/randomization/batched_rng.py  seed derivation of reset(seed=...), per-sub-scene streams
+  mani_skill/utils/visualization/misc.py:54-115, sensors/camera.py:256-294  tile_images, camera_observations_to_images
   mani_skill/envs/utils/randomization/samplers.py:13-108  UniformPlacementSampler (fixed global seed)
   mani_skill/vector/wrappers/gymnasium.py:96-176     ManiSkillVectorEnv.reset / step: episode metrics, auto-reset bookkeeping
   mani_skill/agents/controllers/pd_joint_pos.py:77-101,207-228  PDJointPosController.set_action (delta / target-delta / absolute),
@@ -798,6 +799,37 @@ def main():
             G[f"step_{tag}_{mode}_reward"] = torch.as_tensor(r_).float()
             G[f"step_{tag}_{mode}_terminated"], G[f"step_{tag}_{mode}_truncated"] = te_, tr_
             assert int(fs._elapsed_steps[0]) == 1
+    # ---- tile_images (mani_skill/utils/visualization/misc.py:54-115) and camera_observations_to_images (mani_skill/sensors/camera.py:256-294)
+    for mname in ("imageio", "tqdm", "PIL", "PIL.Image", "PIL.ImageDraw", "PIL.ImageFont"):
+        if mname not in sys.modules:
+            stub(mname)
+    misc = load("mani_skill.utils.visualization.misc_real", "mani_skill/utils/visualization/misc.py")
+    gi = torch.Generator().manual_seed(77)
+    rnd_img = lambda *shape: (torch.rand(*shape, generator=gi) * 255).to(torch.uint8)
+    tile_sets = dict(a=[rnd_img(2, 8, 8, 3), rnd_img(2, 4, 4, 3), rnd_img(2, 4, 4, 3)],                 # render_all of PickCube: big view + two small
+                     b=[rnd_img(2, 4, 6, 3), rnd_img(2, 4, 6, 3), rnd_img(2, 4, 6, 3)],                 # equal sizes: one per column
+                     c=[rnd_img(3, 5, 3), rnd_img(6, 4, 3), rnd_img(3, 4, 3), rnd_img(2, 5, 3)])        # unbatched, mixed
+    for tag, imgs in tile_sets.items():
+        for i_, im in enumerate(imgs):
+            G[f"tile_{tag}_in{i_}"] = im
+        G[f"tile_{tag}_out"] = misc.tile_images([im.clone() for im in imgs])
+    G["tile_b_out_2rows"] = misc.tile_images([im.clone() for im in tile_sets["b"]] + [tile_sets["b"][0].clone()], nrows=2)
+    import ast as _ast
+    cam_src = open(os.path.join(REF, "mani_skill/sensors/camera.py")).read()
+    for node in _ast.walk(_ast.parse(cam_src)):
+        if isinstance(node, _ast.ImportFrom) and node.module and node.module.split(".")[0] in ("mani_skill", "sapien"):
+            if node.module not in sys.modules:
+                stub(node.module)
+            for a in node.names:
+                if not hasattr(sys.modules[node.module], a.name):
+                    setattr(sys.modules[node.module], a.name, MagicMock(name=a.name))
+    cam_mod = load("mani_skill.sensors.camera_real", "mani_skill/sensors/camera.py")
+    co = dict(rgb=rnd_img(2, 4, 5, 3), depth=(torch.rand(2, 4, 5, 1, generator=gi) * 1500).to(torch.int16),
+              segmentation=(torch.rand(2, 4, 5, 1, generator=gi) * 20).to(torch.int16), position=(torch.randn(2, 4, 5, 3, generator=gi) * 500).to(torch.int16))
+    for k_, v_ in co.items():
+        G[f"camimg_in_{k_}"] = v_
+    for k_, v_ in cam_mod.camera_observations_to_images({k2: v2.clone() for k2, v2 in co.items()}).items():
+        G[f"camimg_out_{k_}"] = v_
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -566,3 +566,20 @@ def test_step_termination_and_reward_dispatch_match_the_reference():
             assert int(fs._elapsed_steps[0]) == 1
     fs = SimpleNamespace(num_envs=ns, device=torch.device("cpu"))
     assert torch.equal(BaseEnv.compute_sparse_reward(fs, None, None, dict(fail=fail)), -fail.float())      # the documented intent of the raising line
+
+
+def test_tile_images_and_camera_images_match_the_reference():
+    """mani_skill/utils/visualization/misc.py:54-115 (`tile_images`: batched and single images, mixed sizes, two rows) and
+    mani_skill/sensors/camera.py:256-294 (`camera_observations_to_images`: depth / position normalised to grey, hashed segmentation
+    colours) run by the reference's own code on the same inputs."""
+    from maniskill_b200.visualization import camera_observations_to_images, tile_images
+    for tag, n in (("a", 3), ("b", 3), ("c", 4)):
+        out = tile_images([T(f"tile_{tag}_in{i}") for i in range(n)])
+        assert out.numpy().dtype == G[f"tile_{tag}_out"].dtype and np.array_equal(out.numpy(), G[f"tile_{tag}_out"]), tag
+    two = tile_images([T(f"tile_b_in{i}") for i in range(3)] + [T("tile_b_in0")], nrows=2)
+    assert np.array_equal(two.numpy(), G["tile_b_out_2rows"])
+    obs = {k: T(f"camimg_in_{k}") for k in ("rgb", "depth", "segmentation", "position")}
+    out = camera_observations_to_images(obs)
+    assert set(out) == {"rgb", "depth", "segmentation", "position"}
+    for k, v in out.items():
+        assert v.numpy().dtype == G[f"camimg_out_{k}"].dtype and np.array_equal(v.numpy(), G[f"camimg_out_{k}"]), k

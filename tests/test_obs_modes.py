@@ -137,3 +137,34 @@ def test_flatten_wrappers_on_an_env():
     flat = FlattenObservationWrapper(ms.make("PickCube-v1", num_envs=2, obs_mode="state_dict", world_factory=EmuBackendWorld))
     o, _ = flat.reset(seed=0)
     assert o.shape == (2, 42)
+
+
+def test_render_modes():
+    """sapien_env.py:1369-1439: `render()` under render_mode "rgb_array" (human render camera, 512 x 512, hidden objects shown),
+    "sensors" (what the agent's cameras see: rgb + depth visualisation tiled) and "all"; no render mode -> RuntimeError."""
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld,
+                  sensor_configs=dict(base_camera=dict(width=64, height=64)))
+    env.reset(seed=0)
+    img = env.render()
+    assert img.shape == (2, 512, 512, 3) and img.dtype == torch.uint8
+    # the goal site (green sphere) is hidden from the sensors but shown to the human camera
+    green = (img[..., 1].int() - img[..., 0].int() > 80) & (img[..., 1].int() - img[..., 2].int() > 80)
+    assert green.view(2, -1).sum(1).max() > 20        # (in some layouts the arm occludes it)
+    sens = env.get_sensor_images()["base_camera"]
+    assert set(sens) == {"rgb", "depth"} and sens["depth"].shape == (2, 64, 64, 3) and sens["depth"].dtype == torch.uint8
+    sg = (sens["rgb"][..., 1].int() - sens["rgb"][..., 0].int() > 80) & (sens["rgb"][..., 1].int() - sens["rgb"][..., 2].int() > 80)
+    assert sg.sum() == 0
+    env.render_mode = "sensors"
+    assert env.render().shape == (2, 64, 128, 3)
+    env.render_mode = "all"
+    assert env.render().shape == (2, 512, 512 + 64, 3)          # the two 64 x 64 sensor images share a column next to the 512 x 512 view
+    env.render_mode = None
+    with pytest.raises(RuntimeError, match="render_mode is not set"):
+        env.render()
+    with pytest.raises(NotImplementedError):
+        ms.make("PickCube-v1", num_envs=1, render_mode="human", world_factory=EmuBackendWorld)
+    for task in ("StackCube-v1", "RollBall-v1", "OpenCabinetDrawer-v1"):
+        e = ms.make(task, num_envs=1, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld)
+        e.reset(seed=0)
+        im = e.render()
+        assert im.shape == (1, 512, 512, 3) and len(torch.unique(im.reshape(-1, 3), dim=0)) > 20, task
