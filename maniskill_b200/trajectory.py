@@ -1,6 +1,6 @@
 """Trajectory recording and replay: the on-disk format either side of the step path.
 
-Mirror of `RecordEpisode` (mani_skill/utils/wrappers/record.py:113-756, trajectory part; no video) and of the replay loop of
+Mirror of `RecordEpisode` (mani_skill/utils/wrappers/record.py:113-826: trajectories and videos; no info overlay on the frames) and of the replay loop of
 mani_skill/trajectory/replay_trajectory.py:111-378.  The reference writes `<name>.h5` + `<name>.json`:
 
     traj_<k>/obs                         [T+1, ...]  (dict observations become nested groups)
@@ -80,7 +80,8 @@ class RecordEpisode:
 
     def __init__(self, env, output_dir: str, save_trajectory: bool = True, trajectory_name: str = "trajectory", save_on_reset: bool = True,
                  record_reward: bool = True, record_env_state: bool = True, source_type: Optional[str] = None, source_desc: Optional[str] = None,
-                 env_id: Optional[str] = None, env_kwargs: Optional[dict] = None):
+                 env_id: Optional[str] = None, env_kwargs: Optional[dict] = None, save_video: bool = False, video_fps: int = 30,
+                 max_steps_per_video: Optional[int] = None):
         self.env = env
         self.base_env = getattr(env, "base_env", env)
         self.num_envs = self.base_env.num_envs
@@ -102,6 +103,35 @@ class RecordEpisode:
         self._frames: Optional[List[dict]] = None     # one dict of [num_envs, ...] arrays per frame since the oldest unflushed episode start
         self._start = np.zeros(self.num_envs, dtype=np.int64)   # record.py `env_episode_ptr`
         self._last_reset_kwargs: dict = {}
+        # videos (record.py:338-354, 758-805): `env.render()` after every step (and once before the first), all sub-scenes tiled into
+        # int(sqrt(num_envs)) rows, one `<k>.mp4` per flush (reset with save_on_reset, max_steps_per_video, close)
+        self.save_video, self.video_fps, self.max_steps_per_video = save_video, video_fps, max_steps_per_video
+        if save_video and self.base_env.render_mode is None:
+            raise RuntimeError("save_video needs an env made with a render_mode")
+        self.video_nrows = max(int(np.sqrt(self.num_envs)), 1)
+        self.render_images: List[np.ndarray] = []
+        self._video_id, self._video_steps = -1, 0
+
+    # -------------------------------------------------------------- video
+    def capture_image(self) -> np.ndarray:
+        from .visualization import tile_images
+        img = self.base_env.render()
+        if img.dim() == 3:
+            img = img[None]
+        img = img[0] if len(img) == 1 else tile_images(list(img), nrows=self.video_nrows)
+        return _to_numpy(img)
+
+    def flush_video(self, name: Optional[str] = None, suffix: str = "", ignore_empty_transition: bool = True, save: bool = True):
+        if not self.render_images or (ignore_empty_transition and len(self.render_images) == 1):
+            return None
+        path = None
+        if save:
+            self._video_id += 1
+            video_name = name if name is not None else f"{self._video_id}" + (f"_{suffix}" if suffix else "")
+            path = images_to_video(self.render_images, self.output_dir, video_name, fps=self.video_fps)
+        self._video_steps = 0
+        self.render_images = []
+        return path
 
     # -------------------------------------------------------------- pass-through
     def __getattr__(self, name):
@@ -120,6 +150,8 @@ class RecordEpisode:
 
     def reset(self, seed=None, options: Optional[dict] = None, save: bool = True):
         idx = np.arange(self.num_envs) if not options or "env_idx" not in options else np.atleast_1d(_to_numpy(options["env_idx"])).astype(np.int64)
+        if self.save_video and self.save_on_reset and self.num_envs == 1:     # record.py:364-366: with several sub-scenes videos run on
+            self.flush_video(save=save)
         if self.save_trajectory and self.save_on_reset and self._frames is not None:
             self.flush_trajectory(env_idxs_to_flush=idx, save=save)
         obs, info = self.env.reset(seed=seed, options=options)
@@ -145,12 +177,19 @@ class RecordEpisode:
         return obs, info
 
     def step(self, action):
+        if self.save_video and self._video_steps == 0:
+            self.render_images.append(self.capture_image())        # s_0, taken here so that repeated resets leave no empty videos
         obs, rew, terminated, truncated, info = self.env.step(action)
         if self.base_env.max_episode_steps is not None:
             # the env the reference's recorder wraps comes out of gym.make with the TimeLimit wrapper applied (registration.py:127-170)
             truncated = truncated | (self.base_env.elapsed_steps >= self.base_env.max_episode_steps)
         if self.save_trajectory:
             self._frames.append(self._frame(obs, action, rew, terminated, truncated, info))
+        if self.save_video:
+            self._video_steps += 1
+            self.render_images.append(self.capture_image())
+            if self.max_steps_per_video is not None and self._video_steps >= self.max_steps_per_video:
+                self.flush_video()
         return obs, rew, terminated, truncated, info
 
     # -------------------------------------------------------------- record.py:546-756
@@ -211,6 +250,8 @@ class RecordEpisode:
             np.savez_compressed(self._stem + ".npz", **self._arrays)
 
     def close(self):
+        if self.save_video and self.save_on_reset:
+            self.flush_video()
         if self.save_trajectory:
             self.flush_trajectory()
             self._dump()
@@ -218,6 +259,22 @@ class RecordEpisode:
                 self._h5.close()
         if hasattr(self.env, "close"):
             self.env.close()
+
+
+def images_to_video(images: List[np.ndarray], output_dir: str, video_name: str, fps: int = 30) -> str:
+    """mani_skill/utils/visualization/misc.py `images_to_video` (imageio + ffmpeg there; OpenCV's mp4 writer here): [H, W, 3] uint8 RGB
+    frames -> `<output_dir>/<video_name>.mp4`."""
+    import cv2
+    os.makedirs(output_dir, exist_ok=True)
+    path = os.path.join(output_dir, video_name.replace(" ", "_").replace("\n", "_") + ".mp4")
+    h, w = images[0].shape[:2]
+    writer = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
+    if not writer.isOpened():
+        raise RuntimeError(f"cannot open a video writer for {path}")
+    for im in images:
+        writer.write(cv2.cvtColor(np.ascontiguousarray(im), cv2.COLOR_RGB2BGR))
+    writer.release()
+    return path
 
 
 # ------------------------------------------------------------------------------------------------ reading + replay

@@ -81,3 +81,31 @@ def test_replay_reproduces_the_recording(tmp_path, mode):
         assert r["final_state_error"] < 1e-5 and r["success"] == r["recorded_success"]
     with pytest.raises(ValueError):
         replay_trajectory(ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos", world_factory=EmuBackendWorld), str(tmp_path / "trajectory"))
+
+
+def test_videos(tmp_path):
+    """record.py:338-354,758-805: one frame before the first step and one after every step, sub-scenes tiled into int(sqrt(n)) rows, a video
+    per flush (`max_steps_per_video`, `close`)."""
+    cv2 = pytest.importorskip("cv2")
+    env = ms.make("PickCube-v1", num_envs=4, obs_mode="state", render_mode="sensors", world_factory=EmuBackendWorld,
+                  sensor_configs=dict(base_camera=dict(width=32, height=32)))
+    rec = RecordEpisode(env, str(tmp_path), save_trajectory=False, save_video=True, video_fps=10, max_steps_per_video=3)
+    rec.reset(seed=0)
+    for _ in range(5):
+        rec.step(torch.zeros(4, 8))
+    rec.close()
+
+    def frames(path):
+        cap, out = cv2.VideoCapture(str(path)), []
+        while True:
+            ok, f = cap.read()
+            if not ok:
+                return out
+            out.append(f)
+
+    a, b = frames(tmp_path / "0.mp4"), frames(tmp_path / "1.mp4")
+    assert len(a) == 4 and len(b) == 3           # s_0 + 3 steps, then s_3 + 2 steps flushed by close()
+    assert a[0].shape == (2 * 32, 2 * 64, 3)     # 4 sub-scenes in 2 rows; each shows rgb + depth side by side
+    assert a[0].std() > 5
+    with pytest.raises(RuntimeError, match="render_mode"):
+        RecordEpisode(ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld), str(tmp_path), save_video=True)
