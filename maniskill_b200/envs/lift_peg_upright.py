@@ -10,11 +10,10 @@ import torch
 
 from .. import building as actors
 from .. import utils as U
-from ..agents import Panda
 from ..model import SHAPE_BOX, ShapeRec, pose7
-from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..scenes import add_table_scene
 from ..structs import Pose
-from .base_env import BaseEnv
+from .tabletop import PandaTabletopEnv
 
 
 def twocolor_peg_shapes(half_length, half_width, color_1, color_2):
@@ -25,35 +24,25 @@ def twocolor_peg_shapes(half_length, half_width, color_1, color_2):
             ShapeRec(SHAPE_BOX, pose7([half_length / 2, 0, 0]), half, collide=False, color=tuple(color_2))]
 
 
-class LiftPegUprightEnv(BaseEnv):
+class LiftPegUprightEnv(PandaTabletopEnv):
     max_episode_steps = 50  # @register_env("LiftPegUpright-v1", max_episode_steps=50)
     peg_half_width = 0.025
     peg_half_length = 0.12
 
-    def __init__(self, *args, robot_uids="panda", robot_init_qpos_noise=0.02, **kwargs):
-        if robot_uids != "panda":
-            raise NotImplementedError("LiftPegUpright-v1 on b200sim ships the default 'panda' robot")
-        self.robot_uids = robot_uids
-        self.robot_init_qpos_noise = robot_init_qpos_noise
-        super().__init__(*args, **kwargs)
-
     # ---- lift_peg_upright.py:54-72
-    def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda", "panda_v2", (-0.615, 0, 0)))
-
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
         actors.build_twocolor_peg(self.scene_desc, length=self.peg_half_length, width=self.peg_half_width, color_1=np.array([176, 14, 14, 255]) / 255,
                                   color_2=np.array([12, 42, 160, 255]) / 255, name="peg", body_type="dynamic", initial_pose=actors.Pose(p=[0, 0, 0.1]))
 
     def _after_build(self):
-        self.agent = Panda(self.scene, "panda")
+        self.agent = self._make_agent()
         self.table = self.scene.actors["table-workspace"]
         self.peg = self.scene.actors["peg"]
 
     # ---- lift_peg_upright.py:44-47
     def _sensor_configs(self):
-        return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
+        return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)] + self._robot_sensor_configs()
 
     # ---- lift_peg_upright.py:49-52
     def _human_render_camera_configs(self):
@@ -63,11 +52,7 @@ class LiftPegUprightEnv(BaseEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
-        qpos[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
-        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        self._initialize_table_scene(env_idx)
         xyz = torch.zeros((b, 3), device=dev)
         xyz[:, :2] = torch.rand((b, 2), device=dev) * 0.2 - 0.1
         xyz[:, 2] = self.peg_half_width

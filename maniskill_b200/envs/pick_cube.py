@@ -10,14 +10,13 @@ import numpy as np
 import torch
 
 from .. import utils as U
-from ..agents import Panda
-from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..scenes import add_table_scene
 from ..model import SHAPE_BOX, SHAPE_SPHERE, ActorRec, ShapeRec, pose7
 from ..structs import Pose
-from .base_env import BaseEnv
+from .tabletop import PandaTabletopEnv
 
 
-class PickCubeEnv(BaseEnv):
+class PickCubeEnv(PandaTabletopEnv):
     max_episode_steps = 50  # @register_env("PickCube-v1", max_episode_steps=50)
     goal_thresh = 0.025
     cube_half_size = 0.02
@@ -27,17 +26,7 @@ class PickCubeEnv(BaseEnv):
     sensor_cam_eye_pos = [0.3, 0, 0.6]
     sensor_cam_target_pos = [-0.1, 0, 0.1]
 
-    def __init__(self, *args, robot_uids="panda", robot_init_qpos_noise=0.02, **kwargs):
-        if robot_uids != "panda":
-            raise NotImplementedError("PickCube-v1 on b200sim ships the default 'panda' robot")
-        self.robot_uids = robot_uids
-        self.robot_init_qpos_noise = robot_init_qpos_noise
-        super().__init__(*args, **kwargs)
-
     # ---- pick_cube.py:79-104
-    def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda", "panda_v2", (-0.615, 0, 0)))
-
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
         self.scene_desc.add_actor(ActorRec("cube", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([self.cube_half_size] * 3), color=(1, 0, 0, 1))],
@@ -47,7 +36,7 @@ class PickCubeEnv(BaseEnv):
                                            pose7(), hidden=True))
 
     def _after_build(self):
-        self.agent = Panda(self.scene, "panda")
+        self.agent = self._make_agent()
         self.table = self.scene.actors["table-workspace"]
         self.cube = self.scene.actors["cube"]
         self.goal_site = self.scene.actors["goal_site"]
@@ -87,7 +76,7 @@ class PickCubeEnv(BaseEnv):
     # ---- pick_cube.py:66-71
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at(self.sensor_cam_eye_pos, self.sensor_cam_target_pos), width=128, height=128,
-                     fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
+                     fov=np.pi / 2, near=0.01, far=100.0, mount=None)] + self._robot_sensor_configs()
 
     # ---- pick_cube.py:73-78
     def _human_render_camera_configs(self):
@@ -97,11 +86,7 @@ class PickCubeEnv(BaseEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
-        qpos[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
-        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        self._initialize_table_scene(env_idx)
         xyz = torch.zeros((b, 3), device=dev)
         xyz[:, :2] = torch.rand((b, 2), device=dev) * self.cube_spawn_half_size * 2 - self.cube_spawn_half_size
         xyz[:, 0] += self.cube_spawn_center[0]

@@ -6,7 +6,6 @@ import numpy as np
 import torch
 
 from .. import utils as U
-from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT
 from ..model import pose7
 from ..structs import Pose
 from .push_cube import PushCubeEnv
@@ -19,11 +18,7 @@ class PullCubeEnv(PushCubeEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
-        qpos[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
-        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        self._initialize_table_scene(env_idx)
         xyz = torch.zeros((b, 3), device=dev)
         xyz[:, :2] = torch.rand((b, 2), device=dev) * 0.2 - 0.1
         xyz[:, 2] = self.cube_half_size

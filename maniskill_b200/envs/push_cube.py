@@ -10,29 +10,18 @@ import numpy as np
 import torch
 
 from .. import utils as U
-from ..agents import Panda
 from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
-from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..scenes import add_table_scene
 from ..structs import Pose
-from .base_env import BaseEnv
+from .tabletop import PandaTabletopEnv
 
 
-class PushCubeEnv(BaseEnv):
+class PushCubeEnv(PandaTabletopEnv):
     max_episode_steps = 50  # @register_env("PushCube-v1", max_episode_steps=50)
     goal_radius = 0.1
     cube_half_size = 0.02
 
-    def __init__(self, *args, robot_uids="panda", robot_init_qpos_noise=0.02, **kwargs):
-        if robot_uids != "panda":
-            raise NotImplementedError("PushCube-v1 on b200sim ships the default 'panda' robot")
-        self.robot_uids = robot_uids
-        self.robot_init_qpos_noise = robot_init_qpos_noise
-        super().__init__(*args, **kwargs)
-
     # ---- push_cube.py:105-141
-    def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda", "panda_v2", (-0.615, 0, 0)))
-
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
         h = self.cube_half_size
@@ -44,14 +33,14 @@ class PushCubeEnv(BaseEnv):
                                            pose7([0, 0, 1e-3])))
 
     def _after_build(self):
-        self.agent = Panda(self.scene, "panda")
+        self.agent = self._make_agent()
         self.table = self.scene.actors["table-workspace"]
         self.obj = self.scene.actors["cube"]
         self.goal_region = self.scene.actors["goal_region"]
 
     # ---- push_cube.py:84-92
     def _sensor_configs(self):
-        return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
+        return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)] + self._robot_sensor_configs()
 
     # ---- push_cube.py:93-99 (PullCube-v1: pull_cube.py:49-52, the same camera)
     def _human_render_camera_configs(self):
@@ -61,11 +50,7 @@ class PushCubeEnv(BaseEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
-        qpos[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
-        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        self._initialize_table_scene(env_idx)
         xyz = torch.zeros((b, 3), device=dev)
         xyz[:, :2] = torch.rand((b, 2), device=dev) * 0.2 - 0.1
         xyz[:, 2] = self.cube_half_size

@@ -10,30 +10,20 @@ import numpy as np
 import torch
 
 from .. import utils as U
-from ..agents import Panda
 from .. import building as actors
 from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
-from ..scenes import PANDA_REST_QPOS, SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..scenes import add_table_scene
 from ..structs import Pose
-from .base_env import BaseEnv
+from .tabletop import PandaTabletopEnv
 
 
-class RollBallEnv(BaseEnv):
+class RollBallEnv(PandaTabletopEnv):
     max_episode_steps = 80  # @register_env("RollBall-v1", max_episode_steps=80)
+    SUPPORTED_ROBOTS = ("panda",)  # roll_ball.py:36
     goal_radius = 0.1
     ball_radius = 0.035
 
-    def __init__(self, *args, robot_uids="panda", robot_init_qpos_noise=0.02, **kwargs):
-        if robot_uids != "panda":
-            raise NotImplementedError("RollBall-v1 ships the 'panda' robot only (as the reference: SUPPORTED_ROBOTS = ['panda'])")
-        self.robot_uids = robot_uids
-        self.robot_init_qpos_noise = robot_init_qpos_noise
-        super().__init__(*args, **kwargs)
-
     # ---- roll_ball.py:65-93
-    def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda", "panda_v2", (-0.615, 0, 0)))
-
     def _load_scene_desc(self):
         add_table_scene(self.scene_desc)
         actors.build_sphere(self.scene_desc, radius=self.ball_radius, color=[0, 0.2, 0.8, 1], name="ball", initial_pose=actors.Pose(p=[0, 0, 0.1]))
@@ -42,7 +32,7 @@ class RollBallEnv(BaseEnv):
                                            pose7([0, 0, 0.1])))
 
     def _after_build(self):
-        self.agent = Panda(self.scene, "panda")
+        self.agent = self._make_agent()
         self.table = self.scene.actors["table-workspace"]
         self.ball = self.scene.actors["ball"]
         self.goal_region = self.scene.actors["goal_region"]
@@ -50,7 +40,7 @@ class RollBallEnv(BaseEnv):
 
     # ---- roll_ball.py:55-58
     def _sensor_configs(self):
-        return [dict(uid="base_camera", pose=U.look_at([-0.1, 0.9, 0.3], [0.0, 0.0, 0.0]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)]
+        return [dict(uid="base_camera", pose=U.look_at([-0.1, 0.9, 0.3], [0.0, 0.0, 0.0]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None)] + self._robot_sensor_configs()
 
     # ---- roll_ball.py:60-63
     def _human_render_camera_configs(self):
@@ -60,10 +50,7 @@ class RollBallEnv(BaseEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + PANDA_REST_QPOS
-        qpos[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(qpos, dtype=torch.float32, device=dev))
+        self._initialize_table_scene(env_idx)
         root_q = np.array([0.7071, 0, 0, -0.7072])  # the reference's literals (roll_ball.py:101), normalised as the simulator does
         self.agent.robot.set_pose(Pose.create(pose7([-0.1, 1.0, 0], root_q / np.linalg.norm(root_q)), dev))
         xyz = torch.zeros((b, 3), device=dev)

@@ -477,3 +477,41 @@ def test_reconfigure_rebuilds_the_scene():
     b = every.peg_half_sizes.clone()
     _, info = every.reset()
     assert info["reconfigure"] and not torch.allclose(every.peg_half_sizes, b)
+
+
+def test_tabletop_tasks_accept_the_wrist_camera_panda():
+    """SUPPORTED_ROBOTS of the tabletop tasks (pick_cube.py:40 ...): `robot_uids="panda_wristcam"` loads the v3 Panda (camera link on the
+    hand), rests with the last arm joint turned the other way (table/scene_builder.py:104-108) and adds the hand camera to the sensors;
+    unknown robots are refused; RollBall-v1 keeps the reference's panda-only list."""
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state", robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert obs.shape == (2, 42) and "panda_wristcam" in env.scene.articulations and "camera_link" in env.agent.robot.links_map
+    q = env.agent.robot.get_qpos()
+    assert (q[:, 6] + np.pi / 4).abs().max() < 0.1
+    ref = ms.make("PickCube-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
+    ref.reset(seed=0)
+    assert (ref.agent.robot.get_qpos()[:, 6] - np.pi / 4).abs().max() < 0.1
+    assert torch.allclose(ref.cube.pose.p, env.cube.pose.p)                      # the same layout draws
+    for _ in range(3):
+        obs, r, te, tr, info = env.step(torch.zeros(2, 8))
+    assert torch.isfinite(obs).all()
+    vis = ms.make("PushCube-v1", num_envs=1, obs_mode="rgbd", robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
+    o, _ = vis.reset(seed=0)
+    assert set(o["sensor_data"]) == {"base_camera", "hand_camera"} and o["sensor_data"]["hand_camera"]["rgb"].shape == (1, 128, 128, 3)
+    with pytest.raises(NotImplementedError):
+        ms.make("PickCube-v1", num_envs=1, robot_uids="xarm6_robotiq", world_factory=EmuBackendWorld)
+    with pytest.raises(NotImplementedError):
+        ms.make("RollBall-v1", num_envs=1, robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
+
+
+def test_enhanced_determinism_draws_robot_noise_per_sub_scene():
+    """table/scene_builder.py:85-97: with enhanced determinism every sub-scene takes its rest-pose noise from its own generator, so a
+    sub-scene's reset does not depend on which other sub-scenes are reset with it."""
+    env = ms.make("PushCube-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
+    env.reset(seed=[5, 6, 7])
+    q_all = env.agent.robot.get_qpos().clone()
+    env.reset(seed=[5, 6, 7])
+    assert torch.allclose(env.agent.robot.get_qpos(), q_all)
+    solo = ms.make("PushCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
+    solo.reset(seed=[6])
+    assert torch.allclose(solo.agent.robot.get_qpos()[0], q_all[1], atol=1e-6)
