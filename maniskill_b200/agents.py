@@ -106,6 +106,81 @@ class PDJointPosMimicController(PDJointPosController):
         self.set_drive_targets(self._target_qpos)
 
 
+class PDJointVelController:
+    """pd_joint_vel.py:13-48: the (clipped, scaled) action is the velocity target of the joints' drives; the drives are built with
+    stiffness 0 (the gains are part of the compiled model: the task passes the control mode to the scene description)."""
+    sets_target_qpos = False
+    sets_target_qvel = True
+    use_target = False
+
+    def __init__(self, articulation: Articulation, joint_names: List[str], lower, upper, normalize_action=True):
+        self.articulation = articulation
+        self.scene = articulation.scene
+        self.device = self.scene.device
+        self.joint_names = joint_names
+        self.active_joint_indices = torch.tensor([articulation.dof_names.index(n) for n in joint_names], dtype=torch.int64, device=self.device)
+        n = len(joint_names)
+        self.normalize_action = normalize_action
+        self.action_low = torch.tensor(np.broadcast_to(np.float32(lower), n).copy(), device=self.device)
+        self.action_high = torch.tensor(np.broadcast_to(np.float32(upper), n).copy(), device=self.device)
+        self.action_dim = n
+
+    @property
+    def qpos(self):
+        return self.articulation.qpos[..., self.active_joint_indices]
+
+    def reset(self, env_idx=None):
+        """A reset sub-scene starts with zero velocity targets."""
+        rows = self.articulation._rows if env_idx is None else self.articulation._rows[env_idx]
+        self.scene.world.target_qvel[rows[:, None], self.active_joint_indices[None, :]] = 0.0
+        self.scene._dirty |= self.scene.BUF_TARGET_QVEL
+
+    def _preprocess_action(self, action):
+        return U.clip_and_scale_action(action, self.action_low, self.action_high) if self.normalize_action else action
+
+    def set_action(self, action):
+        self.articulation.set_joint_drive_velocity_targets(self._preprocess_action(action), self.active_joint_indices)
+
+    def get_state(self):
+        return {}
+
+
+class PDJointPosVelController(PDJointPosController):
+    """pd_joint_pos_vel.py:11-69: the action is [position part | velocity part]; the position half goes through the PDJointPos rules
+    (absolute / delta / target-delta), the velocity half becomes the drives' velocity targets."""
+    sets_target_qvel = True
+
+    def __init__(self, articulation: Articulation, joint_names: List[str], lower, upper, vel_lower=-1.0, vel_upper=1.0, **kw):
+        super().__init__(articulation, joint_names, lower, upper, **kw)
+        n = len(joint_names)
+        lim = np.stack([np.concatenate([self.action_low.cpu().numpy(), np.broadcast_to(np.float32(vel_lower), n)]),
+                        np.concatenate([self.action_high.cpu().numpy(), np.broadcast_to(np.float32(vel_upper), n)])], 1)
+        self._set_bounds(lim)
+        self._target_qvel = None
+
+    def reset(self, env_idx=None):
+        super().reset(env_idx)
+        if self._target_qvel is None or env_idx is None:
+            self._target_qvel = torch.zeros_like(self.qpos)
+        else:
+            self._target_qvel[env_idx] = 0.0
+        rows = self.articulation._rows if env_idx is None else self.articulation._rows[env_idx]
+        self.scene.world.target_qvel[rows[:, None], self.active_joint_indices[None, :]] = 0.0
+        self.scene._dirty |= self.scene.BUF_TARGET_QVEL
+
+    def set_action(self, action):
+        action = self._preprocess_action(action)
+        nq = action.shape[1] // 2
+        self._start_qpos = self.qpos
+        if self.use_delta:
+            self._target_qpos = (self._target_qpos if self.use_target else self._start_qpos) + action[:, :nq]
+        else:
+            self._target_qpos = torch.broadcast_to(action[:, :nq], self._start_qpos.shape).clone()
+        self.set_drive_targets(self._target_qpos)
+        self._target_qvel = action[:, nq:]
+        self.articulation.set_joint_drive_velocity_targets(self._target_qvel, self.active_joint_indices)
+
+
 class PDEEPosController(PDJointPosController):
     """pd_ee_pose.py:25-146, GPU-simulation semantics: frame "root_translation", delta actions.  Without a virtual target the
     (clipped and scaled) action IS the end-effector displacement in the root frame and goes straight into one damped least-squares
@@ -230,8 +305,15 @@ class Panda:
     arm_joint_names = [f"panda_joint{i}" for i in range(1, 8)]
     gripper_joint_names = ["panda_finger_joint1", "panda_finger_joint2"]
     ee_link_name = "panda_hand_tcp"
-    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_joint_target_delta_pos", "pd_ee_delta_pos", "pd_ee_delta_pose",
-                               "pd_ee_target_delta_pos", "pd_ee_target_delta_pose")
+    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_ee_delta_pos", "pd_ee_delta_pose", "pd_joint_target_delta_pos",
+                               "pd_ee_target_delta_pos", "pd_ee_target_delta_pose", "pd_joint_vel", "pd_joint_pos_vel", "pd_joint_delta_pos_vel")
+    arm_stiffness, arm_damping, arm_force_limit = 1e3, 1e2, 100.0          # panda.py:68-74
+
+    @classmethod
+    def drive_gains(cls, control_mode: Optional[str]):
+        """(stiffness, damping, force limit) of the arm drives under a control mode (panda.py:76-170: the velocity controller builds its
+        drives without stiffness, pd_joint_vel.py:29-36); the gains are part of the compiled scene."""
+        return (0.0, cls.arm_damping, cls.arm_force_limit) if control_mode == "pd_joint_vel" else (cls.arm_stiffness, cls.arm_damping, cls.arm_force_limit)
     robot_asset = "panda_v2"
 
     def __init__(self, scene, name="panda"):
@@ -263,6 +345,12 @@ class Panda:
             arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
         elif control_mode == "pd_joint_target_delta_pos":
             arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True, use_target=True)
+        elif control_mode == "pd_joint_vel":                   # panda.py:144-150
+            arm = PDJointVelController(self.robot, self.arm_joint_names, -1.0, 1.0)
+        elif control_mode == "pd_joint_pos_vel":               # panda.py:153-161
+            arm = PDJointPosVelController(self.robot, self.arm_joint_names, None, None, normalize_action=False)
+        elif control_mode == "pd_joint_delta_pos_vel":         # panda.py:162-170
+            arm = PDJointPosVelController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
         else:
             arm = PDJointPosController(self.robot, self.arm_joint_names, None, None, normalize_action=False)
         self.controller = CombinedController(dict(arm=arm, gripper=gripper))

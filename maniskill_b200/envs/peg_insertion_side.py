@@ -38,7 +38,10 @@ class PegInsertionSideEnv(BaseEnv):
         super().__init__(*args, **kwargs)
 
     def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda_wristcam", "panda_v3", (-0.615, 0, 0)))
+        art = panda_articulation("panda_wristcam", "panda_v3", (-0.615, 0, 0))
+        for j in Panda.arm_joint_names:      # the drive gains follow the control mode the env is made with
+            art.drive[j] = Panda.drive_gains(self._control_mode_arg)
+        self.scene_desc.add_articulation(art)
 
     # ---- peg_insertion_side.py:109-191
     def _load_scene_desc(self):

@@ -29,7 +29,10 @@ class StackCubeEnv(BaseEnv):
         super().__init__(*args, **kwargs)
 
     def _load_agent_desc(self):
-        self.scene_desc.add_articulation(panda_articulation("panda_wristcam", "panda_v3", (-0.615, 0, 0)))
+        art = panda_articulation("panda_wristcam", "panda_v3", (-0.615, 0, 0))
+        for j in Panda.arm_joint_names:      # the drive gains follow the control mode the env is made with
+            art.drive[j] = Panda.drive_gains(self._control_mode_arg)
+        self.scene_desc.add_articulation(art)
 
     # ---- stack_cube.py:57-77
     def _load_scene_desc(self):

@@ -35,7 +35,10 @@ class PandaTabletopEnv(BaseEnv):
 
     def _load_agent_desc(self):
         """`super()._load_agent(options, sapien.Pose(p=[-0.615, 0, 0]))` of the tabletop tasks."""
-        self.scene_desc.add_articulation(panda_articulation(self.robot_uids, ROBOT_ASSET[self.robot_uids], (-0.615, 0, 0)))
+        art = panda_articulation(self.robot_uids, ROBOT_ASSET[self.robot_uids], (-0.615, 0, 0))
+        for j in Panda.arm_joint_names:      # the drive gains follow the control mode the env is made with
+            art.drive[j] = Panda.drive_gains(self._control_mode_arg)
+        self.scene_desc.add_articulation(art)
 
     def _make_agent(self) -> Panda:
         return Panda(self.scene, self.robot_uids)

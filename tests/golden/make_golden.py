@@ -830,6 +830,29 @@ def main():
         G[f"camimg_in_{k_}"] = v_
     for k_, v_ in cam_mod.camera_observations_to_images({k2: v2.clone() for k2, v2 in co.items()}).items():
         G[f"camimg_out_{k_}"] = v_
+    # ---- PDJointVelController / PDJointPosVelController.set_action (pd_joint_vel.py:38-42, pd_joint_pos_vel.py:43-67)
+    sys.modules["mani_skill.agents.controllers.pd_joint_pos"] = pjp
+    pjv = load("mani_skill.agents.controllers.pd_joint_vel_real", "mani_skill/agents/controllers/pd_joint_vel.py")
+    gv = torch.Generator().manual_seed(404)
+    v_act = torch.randn(nenv, 7, generator=gv) * 0.9
+    vel_sent2, pos_sent2 = [], []
+    cv = SimpleNamespace(joints=None, active_joint_indices=None, scene=SimpleNamespace(num_envs=nenv), action_space=SimpleNamespace(shape=(nenv, 7)),
+                         _normalize_action=True, action_space_low=torch.full((7,), -1.0), action_space_high=torch.full((7,), 1.0),
+                         articulation=SimpleNamespace(set_joint_drive_velocity_targets=lambda t, j, idx: vel_sent2.append(t.clone())))
+    cv._preprocess_action = lambda a: bc.BaseController._preprocess_action(cv, a)
+    cv._clip_and_scale_action = lambda a: bc.BaseController._clip_and_scale_action(cv, a)
+    pjv.PDJointVelController.set_action(cv, v_act)
+    G["ctl_vel_act"], G["ctl_vel_target"] = v_act, vel_sent2[-1]
+    pjpv = load("mani_skill.agents.controllers.pd_joint_pos_vel_real", "mani_skill/agents/controllers/pd_joint_pos_vel.py")
+    pv_acts = [torch.randn(nenv, 14, generator=gv) * 0.8 for _ in range(2)]
+    lowpv, highpv = torch.cat([torch.full((7,), -0.1), torch.full((7,), -1.0)]), torch.cat([torch.full((7,), 0.1), torch.full((7,), 1.0)])
+    cpv = fake_ctrl(pjpv.PDJointPosVelController, qpos_arm, lowpv, highpv, True, True)
+    cpv.action_space = SimpleNamespace(shape=(nenv, 14))
+    cpv.set_drive_targets = lambda t: pos_sent2.append(t.clone())
+    cpv.set_drive_velocity_targets = lambda t: vel_sent2.append(t.clone())
+    for a_ in pv_acts:
+        pjpv.PDJointPosVelController.set_action(cpv, a_)
+    G["ctl_pv_act0"], G["ctl_pv_act1"], G["ctl_pv_pos_target"], G["ctl_pv_vel_target"] = pv_acts[0], pv_acts[1], pos_sent2[-1], vel_sent2[-1]
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

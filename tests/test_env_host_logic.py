@@ -515,3 +515,39 @@ def test_enhanced_determinism_draws_robot_noise_per_sub_scene():
     solo = ms.make("PushCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
     solo.reset(seed=[6])
     assert torch.allclose(solo.agent.robot.get_qpos()[0], q_all[1], atol=1e-6)
+
+
+def test_joint_velocity_control_modes():
+    """panda.py:143-170 / pd_joint_vel.py / pd_joint_pos_vel.py: `pd_joint_vel` drives without stiffness towards a velocity target
+    (action in [-1, 1] rad/s per arm joint); `pd_joint_delta_pos_vel` / `pd_joint_pos_vel` take [position part | velocity part]."""
+    env = ms.make("PushCube-v1", num_envs=2, obs_mode="state", control_mode="pd_joint_vel", world_factory=EmuBackendWorld)
+    env.reset(seed=0)
+    assert env.action_dim == 8
+    q0 = env.agent.robot.get_qpos().clone()
+    a = torch.zeros(2, 8)
+    a[:, 0] = 0.5                                           # +0.5 rad/s on the first joint
+    a[1, 0] = -1.5                                          # clipped to -1 rad/s
+    a[:, 7] = 1.0                                           # gripper stays open (position-controlled)
+    for _ in range(20):                                     # 1 s
+        obs, *_ = env.step(a)
+    q1, qd1 = env.agent.robot.get_qpos(), env.agent.robot.get_qvel()
+    assert abs(float(q1[0, 0] - q0[0, 0]) - 0.5) < 0.05 and abs(float(q1[1, 0] - q0[1, 0]) + 1.0) < 0.1
+    assert abs(float(qd1[0, 0]) - 0.5) < 0.02 and abs(float(qd1[1, 0]) + 1.0) < 0.05
+    # the other arm joints are velocity-held at zero: without stiffness they may creep a little under load, but do not run away
+    assert (q1[:, 2:7] - q0[:, 2:7]).abs().max() < 0.05
+    env.reset(options=dict(env_idx=torch.tensor([0])))
+    assert torch.equal(env.scene.world.target_qvel[0, :7], torch.zeros(7)) and float(env.scene.world.target_qvel[1, 0]) == -1.0
+
+    dpv = ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_delta_pos_vel", world_factory=EmuBackendWorld)
+    dpv.reset(seed=0)
+    assert dpv.action_dim == 7 + 7 + 1
+    q0 = dpv.agent.robot.get_qpos().clone()
+    a = torch.zeros(1, 15)
+    a[0, 0], a[0, 7 + 0] = 1.0, 0.3                          # +0.1 rad target step, 0.3 rad/s feed-forward on joint 0
+    dpv.step(a)
+    assert float(dpv.scene.world.target_qpos[0, 0]) == pytest.approx(float(q0[0, 0]) + 0.1, abs=1e-6)
+    assert float(dpv.scene.world.target_qvel[0, 0]) == pytest.approx(0.3, abs=1e-6)
+    pv = ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos_vel", world_factory=EmuBackendWorld)
+    pv.reset(seed=0)
+    lo, hi = pv.single_action_space_low, pv.single_action_space_high
+    assert pv.action_dim == 15 and np.allclose(lo[7:14], -1) and np.allclose(hi[7:14], 1) and lo[0] == pytest.approx(-2.8973, abs=1e-4)

@@ -583,3 +583,33 @@ def test_tile_images_and_camera_images_match_the_reference():
     assert set(out) == {"rgb", "depth", "segmentation", "position"}
     for k, v in out.items():
         assert v.numpy().dtype == G[f"camimg_out_{k}"].dtype and np.array_equal(v.numpy(), G[f"camimg_out_{k}"]), k
+
+
+def test_velocity_controllers_match_the_reference_set_action():
+    """pd_joint_vel.py:38-42 and pd_joint_pos_vel.py:43-67 with base_controller.py:125-173, produced by the reference's own set_action:
+    clipped / scaled velocity targets, and for the position + velocity controller (target-delta positions over two actions) both halves."""
+    from maniskill_b200.agents import PDJointPosVelController, PDJointVelController
+    names = [f"j{i}" for i in range(7)]
+
+    class Art(_FakeArticulation):
+        def __init__(self, qpos, names):
+            super().__init__(qpos, names)
+            self.vel_sent = None
+
+        def set_joint_drive_velocity_targets(self, targets, idx):
+            self.vel_sent = targets.clone()
+
+    art = Art(T("ctl_qpos_arm"), names)
+    v = PDJointVelController(art, names, -1.0, 1.0)
+    v.set_action(T("ctl_vel_act"))
+    close(art.vel_sent, G["ctl_vel_target"], 1e-7)
+    assert (np.abs(G["ctl_vel_target"]) <= 1 + 1e-6).all() and (np.abs(G["ctl_vel_act"]) > 1).any()
+    art.scene.world = SimpleNamespace(target_qvel=torch.zeros(len(art.qpos), 7))       # what reset() clears
+    art.scene.BUF_TARGET_QVEL, art.scene._dirty, art._rows = 64, 0, torch.arange(len(art.qpos))
+    pv = PDJointPosVelController(art, names, -0.1, 0.1, use_delta=True, use_target=True)
+    pv.reset()
+    assert pv.action_dim == 14
+    pv.set_action(T("ctl_pv_act0"))
+    pv.set_action(T("ctl_pv_act1"))
+    close(art.sent, G["ctl_pv_pos_target"], 1e-7)
+    close(art.vel_sent, G["ctl_pv_vel_target"], 1e-7)
