@@ -192,8 +192,6 @@ class PDEEPosController(PDJointPosController):
                  rot_lower=None, rot_upper=None, use_delta=True, use_target=False, normalize_action=True,
                  solver_config: Optional[dict] = None):
         from .kinematics import Kinematics
-        if not use_delta:
-            raise NotImplementedError("absolute end-effector targets (pd_ee_pose) are not available in this build")
         super().__init__(articulation, joint_names, None, None, use_delta=use_delta, use_target=use_target, normalize_action=normalize_action)
         self.kinematics = Kinematics(robot, ee_link, articulation.dof_names, joint_names, self.device)
         self.ee_link = articulation.links_map[ee_link]
@@ -238,6 +236,10 @@ class PDEEPosController(PDJointPosController):
         if self.use_target:
             self._target_pose = self.compute_target_pose(self._target_pose, action)
             delta = self._delta_from_target(self._target_pose, self.ee_pose_at_base)
+        elif not self.use_delta:
+            # absolute target in the root frame (pd_ee_pose.py:95-99,252-263 -> utils/kinematics.py:211-231: the 6-vector becomes a pose,
+            # the IK step closes the gap to the current end-effector pose)
+            delta = self._delta_from_target(self.compute_target_pose(None, action), self.ee_pose_at_base)
         else:
             delta = torch.hstack([action, torch.zeros((action.shape[0], 3), device=self.device)]) if self.pos_only else action
         self._target_qpos = self.kinematics.compute_ik(delta, self.articulation.get_qpos(), self.solver_config)
@@ -264,6 +266,8 @@ class PDEEPoseController(PDEEPosController):
 
     def compute_target_pose(self, prev: Pose, action) -> Pose:
         dq = U.matrix_to_quat(U.euler_xyz_to_matrix(action[:, 3:6]))
+        if not self.use_delta:   # pd_ee_pose.py:252-263: position and XYZ Euler angles of the target, root frame
+            return Pose(torch.hstack([action[:, :3], dq]))
         q = U.quat_mul(dq, prev.q)
         q = torch.where(q[..., :1] < 0, -q, q)
         return Pose(torch.hstack([prev.p + action[:, :3], q]))
@@ -305,7 +309,7 @@ class Panda:
     arm_joint_names = [f"panda_joint{i}" for i in range(1, 8)]
     gripper_joint_names = ["panda_finger_joint1", "panda_finger_joint2"]
     ee_link_name = "panda_hand_tcp"
-    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_ee_delta_pos", "pd_ee_delta_pose", "pd_joint_target_delta_pos",
+    SUPPORTED_CONTROL_MODES = ("pd_joint_delta_pos", "pd_joint_pos", "pd_ee_delta_pos", "pd_ee_delta_pose", "pd_ee_pose", "pd_joint_target_delta_pos",
                                "pd_ee_target_delta_pos", "pd_ee_target_delta_pose", "pd_joint_vel", "pd_joint_pos_vel", "pd_joint_delta_pos_vel")
     arm_stiffness, arm_damping, arm_force_limit = 1e3, 1e2, 100.0          # panda.py:68-74
 
@@ -339,8 +343,12 @@ class Panda:
         if control_mode.startswith("pd_ee_"):  # panda.py:103-141: pos +-0.1, rot +-0.1, ee link panda_hand_tcp
             from .model import load_robot
             cls = PDEEPoseController if control_mode.endswith("pose") else PDEEPosController
-            arm = cls(self.robot, self.arm_joint_names, -0.1, 0.1, load_robot(self.robot_asset), self.ee_link_name, rot_lower=-0.1, rot_upper=0.1,
-                      use_target="target" in control_mode)
+            if control_mode == "pd_ee_pose":      # panda.py:125-136: absolute pose target, +-2 m, rotation +-2 pi, not normalised
+                arm = cls(self.robot, self.arm_joint_names, -2.0, 2.0, load_robot(self.robot_asset), self.ee_link_name, rot_lower=-2 * np.pi,
+                          rot_upper=2 * np.pi, use_delta=False, normalize_action=False)
+            else:
+                arm = cls(self.robot, self.arm_joint_names, -0.1, 0.1, load_robot(self.robot_asset), self.ee_link_name, rot_lower=-0.1, rot_upper=0.1,
+                          use_target="target" in control_mode)
         elif control_mode == "pd_joint_delta_pos":
             arm = PDJointPosController(self.robot, self.arm_joint_names, -0.1, 0.1, use_delta=True)
         elif control_mode == "pd_joint_target_delta_pos":

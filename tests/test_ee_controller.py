@@ -119,3 +119,28 @@ def test_ee_controllers_move_the_tcp_by_the_commanded_displacement(mode):
     if "target" in mode:
         st = env.agent.controller.get_state()
         assert st["arm"]["target_pose"].shape == (n, 7)
+
+
+def test_absolute_ee_pose_mode_reaches_the_commanded_pose():
+    """pd_ee_pose (panda.py:125-136, pd_ee_pose.py:252-263): the action is the target pose itself -- position and XYZ Euler angles in the
+    robot's root frame, not normalised; held for a second the TCP arrives there, orientation included."""
+    import maniskill_b200 as ms
+    from emu_world import EmuBackendWorld
+    from maniskill_b200 import utils as U
+    env = ms.make("PushCube-v1", num_envs=2, obs_mode="state", control_mode="pd_ee_pose", world_factory=EmuBackendWorld)
+    env.reset(seed=0)
+    assert env.action_dim == 7 and np.allclose(env.single_action_space_low[:3], -2.0) and np.allclose(env.single_action_space_high[3:6], 2 * np.pi)
+    arm = env.agent.controller.controllers["arm"]
+    cur = arm.ee_pose_at_base
+    target_p = cur.p + torch.tensor([[0.05, -0.04, -0.03], [-0.03, 0.05, 0.02]])
+    yaw = torch.tensor([0.3, -0.2])
+    dq = U.matrix_to_quat(U.euler_xyz_to_matrix(torch.stack([torch.zeros(2), torch.zeros(2), yaw], 1)))
+    target_q = U.quat_mul(dq, cur.q)                                          # the current orientation turned about the root z axis
+    eul = U.matrix_to_euler_xyz(U.quat_to_matrix(target_q))
+    a = torch.hstack([target_p, eul, torch.ones(2, 1)])
+    for _ in range(25):
+        env.step(a)
+    now = arm.ee_pose_at_base
+    assert (now.p - target_p).abs().max() < 5e-3
+    err = U.quat_mul(now.q, U.quat_conj(target_q))
+    assert (2 * torch.atan2(err[:, 1:].norm(dim=1), err[:, 0].abs())).max() < 0.02

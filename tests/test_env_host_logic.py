@@ -96,7 +96,7 @@ def test_unsupported_modes_raise():
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, obs_mode="rgb+albedo", world_factory=EmuBackendWorld)   # texture the minimal shader does not write
     with pytest.raises(NotImplementedError):
-        ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_pose", world_factory=EmuBackendWorld)  # absolute EE targets: not built
+        ms.make("PickCube-v1", num_envs=1, control_mode="pd_ee_twist", world_factory=EmuBackendWorld)  # no such mode for the Panda
 
 
 def test_peg_insertion_side_heterogeneous_envs():
