@@ -390,7 +390,7 @@ def test_end_effector_controllers_and_the_ik_step_match_the_reference():
     from maniskill_b200.agents import PDEEPosController, PDEEPoseController
     from maniskill_b200.kinematics import Kinematics
     act, prev = T("ee_act"), Pose(T("ee_prev"))
-    fake = SimpleNamespace(normalize_action=True, action_low=torch.full((6,), -0.1), action_high=torch.full((6,), 0.1), rot_lower=-0.1)
+    fake = SimpleNamespace(normalize_action=True, action_low=torch.full((6,), -0.1), action_high=torch.full((6,), 0.1), rot_lower=-0.1, use_delta=True)
     scaled = PDEEPoseController._preprocess_action(fake, act)
     close(scaled, G["ee_scaled"], 1e-6)
     assert (np.linalg.norm(G["ee_scaled"][:, 3:], axis=1) <= 0.1 + 1e-6).all() and (np.linalg.norm(G["ee_act"][:3, 3:], axis=1) > 1).all()
