@@ -199,3 +199,44 @@ def test_reference_texture_transforms_on_our_render_targets(reference_module):
         assert set(got) == set(want) == {"rgb", "position", "depth", "segmentation"}
         for k in want:
             assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), (cam["uid"], k)
+
+
+def test_reference_pose_struct_over_the_sapien_shim():
+    """`install()` makes `import sapien` resolve to maniskill_b200/sapien_shim.py; the reference's REAL batched `Pose`
+    (mani_skill/utils/structs/pose.py, loaded with only its non-sapien imports stubbed) then accepts the shim's `sapien.Pose` objects:
+    `Pose.create(sapien.Pose)`, `.sp` round trip, products against our own batched Pose."""
+    saved = dict(sys.modules)
+    try:
+        from maniskill_b200 import sapien_shim
+        assert sapien_shim.install(force=True)
+        import sapien
+        import sapien.physx as physx
+        assert sapien.Pose is sapien_shim.Pose and physx.PhysxGpuSystem.__name__ == "PhysxGpuSystem" and not physx.is_gpu_enabled()
+        physx.enable_gpu()
+        assert physx.is_gpu_enabled() and sapien.Device("cuda:1").is_cuda() and sapien.Device("cuda:1").cuda_id == 1 and sapien.Device("cpu").is_cpu()
+        with pytest.raises(AttributeError):
+            sapien.Entity            # not part of the shim: fails loudly rather than pretending
+        rot = _load_reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
+        common = MagicMock()
+        common.to_tensor = lambda x, device=None: torch.as_tensor(x, device=device).float() if not isinstance(x, torch.Tensor) else x.to(device)
+        sys.modules["mani_skill.utils"] = MagicMock(common=common)
+        sys.modules["mani_skill.utils.common"] = common
+        pose_mod = _load_reference_module("/root/reference/mani_skill/utils/structs/pose.py")
+        pose_mod.common = common
+        RP = pose_mod.Pose
+        a = sapien.Pose(p=[0.1, -0.2, 0.3], q=[0.9238795, 0, 0.3826834, 0])
+        ra = RP.create(a)
+        assert ra.raw_pose.shape == (1, 7) and torch.allclose(ra.p[0], torch.tensor([0.1, -0.2, 0.3])) and torch.allclose(ra.q[0], torch.tensor(a.q))
+        b = sapien.Pose(p=[-0.3, 0.0, 0.2], q=[0.7071068, 0.7071068, 0, 0])
+        prod_ref = (ra * RP.create(b)).raw_pose[0]
+        prod_shim = a * b
+        assert torch.allclose(prod_ref[:3], torch.tensor(prod_shim.p), atol=1e-6)
+        assert min((prod_ref[3:] - torch.tensor(prod_shim.q)).abs().max(), (prod_ref[3:] + torch.tensor(prod_shim.q)).abs().max()) < 1e-6
+        from maniskill_b200.structs import Pose as OurPose
+        ours = (OurPose.create_from_pq(torch.tensor(a.p)[None], torch.tensor(a.q)[None]) * OurPose.create_from_pq(torch.tensor(b.p)[None], torch.tensor(b.q)[None])).raw_pose[0]
+        assert torch.allclose(ours, prod_ref, atol=1e-6)
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.modules.update(saved)
