@@ -27,3 +27,6 @@ register_env("PokeCube-v1", max_episode_steps=50)(PokeCubeEnv)
 from .roll_ball import RollBallEnv
 
 register_env("RollBall-v1", max_episode_steps=80)(RollBallEnv)
+from .place_sphere import PlaceSphereEnv
+
+register_env("PlaceSphere-v1", max_episode_steps=50)(PlaceSphereEnv)

@@ -153,6 +153,10 @@ class Actor(_BodyView):
         self.initial_pose = initial_pose
         self.hidden = False
 
+    def is_static(self, lin_thresh=1e-2, ang_thresh=1e-1):
+        """actor.py:220-227."""
+        return torch.logical_and(torch.linalg.norm(self.linear_velocity, axis=1) <= lin_thresh, torch.linalg.norm(self.angular_velocity, axis=1) <= ang_thresh)
+
     def set_pose(self, pose):
         pose = Pose.create(pose, self.scene.device)
         rows = _sel(self.scene, self._idx)

@@ -853,6 +853,40 @@ def main():
     for a_ in pv_acts:
         pjpv.PDJointPosVelController.set_action(cpv, a_)
     G["ctl_pv_act0"], G["ctl_pv_act1"], G["ctl_pv_pos_target"], G["ctl_pv_vel_target"] = pv_acts[0], pv_acts[1], pos_sent2[-1], vel_sent2[-1]
+    # ---- PlaceSphere task logic (place_sphere.py:186-265)
+    for mname in ("matplotlib", "matplotlib.pyplot"):
+        if mname not in sys.modules:
+            stub(mname)
+    ps_mod = load("mani_skill.envs.tasks.tabletop.place_sphere", "mani_skill/envs/tasks/tabletop/place_sphere.py")
+    PS = ps_mod.PlaceSphereEnv
+    gp = torch.Generator().manual_seed(515)
+    mps = 12
+    bin_p = torch.hstack([torch.rand(mps, 1, generator=gp) * 0.1, torch.rand(mps, 1, generator=gp) * 0.2 - 0.1, torch.full((mps, 1), 0.0025)])
+    sph_p = bin_p + torch.hstack([torch.randn(mps, 2, generator=gp) * 0.05, torch.rand(mps, 1, generator=gp) * 0.1])
+    sph_p[:6] = bin_p[:6] + torch.tensor([0.0, 0.0, 0.0225]) + torch.randn(6, 3, generator=gp) * 0.002            # in the bin
+    sph_raw = torch.hstack([sph_p, torch.nn.functional.normalize(torch.randn(mps, 4, generator=gp), dim=-1)])
+    ps_lin, ps_ang = torch.randn(mps, 3, generator=gp) * 0.008, torch.randn(mps, 3, generator=gp) * 0.3
+    ps_tcp = torch.hstack([sph_p + torch.randn(mps, 3, generator=gp) * 0.03, torch.nn.functional.normalize(torch.randn(mps, 4, generator=gp), dim=-1)])
+    ps_lin[:3] *= 0.1
+    ps_ang[:3] *= 0.1                                          # three resting spheres among the ones in the bin
+    ps_grasp = torch.rand(mps, generator=gp) < 0.4
+    ps_grasp[0], ps_grasp[1] = False, True                     # one released (success), one still held
+    ps_rstatic = torch.rand(mps, generator=gp) < 0.6
+    ps_qpos = torch.hstack([torch.randn(mps, 7, generator=gp), torch.rand(mps, 2, generator=gp) * 0.04])
+    ps_qlim = torch.tensor([[-2.9, 2.9]] * 7 + [[0.0, 0.04]] * 2)[None].repeat(mps, 1, 1)
+    obj_ns = SimpleNamespace(pose=Pose.create(sph_raw), linear_velocity=ps_lin, angular_velocity=ps_ang)
+    obj_ns.is_static = lambda lin_thresh=1e-2, ang_thresh=1e-1: torch.logical_and(torch.linalg.norm(ps_lin, axis=1) <= lin_thresh, torch.linalg.norm(ps_ang, axis=1) <= ang_thresh)
+    fake_ps = SimpleNamespace(obj=obj_ns, bin=SimpleNamespace(pose=Pose.create_from_pq(bin_p)), radius=0.02, block_half_size=PS.block_half_size, device=torch.device("cpu"),
+                              obs_mode="state", agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(ps_tcp)), is_grasping=lambda o: ps_grasp.clone(),
+                                                                      is_static=lambda t: ps_rstatic.clone(),
+                                                                      robot=SimpleNamespace(get_qlimits=lambda: ps_qlim, get_qpos=lambda: ps_qpos)))
+    sinfo = PS.evaluate(fake_ps)
+    G["place_sphere"], G["place_bin"], G["place_lin"], G["place_ang"], G["place_tcp"] = sph_raw, bin_p, ps_lin, ps_ang, ps_tcp
+    G["place_grasp"], G["place_rstatic"], G["place_qpos"] = ps_grasp, ps_rstatic, ps_qpos
+    for k_ in ("is_obj_grasped", "is_obj_on_bin", "is_obj_static", "success"):
+        G[f"place_{k_}"] = sinfo[k_]
+    G["place_reward"] = PS.compute_dense_reward(fake_ps, None, None, sinfo)
+    G["place_extra_flat"] = common.flatten_state_dict(PS._get_obs_extra(fake_ps, sinfo), use_torch=True)
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -551,3 +551,27 @@ def test_joint_velocity_control_modes():
     pv.reset(seed=0)
     lo, hi = pv.single_action_space_low, pv.single_action_space_high
     assert pv.action_dim == 15 and np.allclose(lo[7:14], -1) and np.allclose(hi[7:14], 1) and lo[0] == pytest.approx(-2.8973, abs=1e-4)
+
+
+def test_place_sphere_reset_layout_and_a_sphere_in_the_bin():
+    """PlaceSphere-v1 (place_sphere.py): sphere in the near quarter, bin in the far half, 39-dim state observation; a sphere dropped into
+    the bin comes to rest on the bottom plate between the four rims and counts as placed, static and released."""
+    from maniskill_b200.structs import Pose
+    env = ms.make("PlaceSphere-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=2)
+    assert obs.shape == (3, 9 + 9 + 1 + 7 + 3 + 7 + 3)
+    s, b = env.obj.pose.p, env.bin.pose.p
+    assert (s[:, 0] >= -0.1 - 1e-6).all() and (s[:, 0] <= -0.05 + 1e-6).all() and torch.allclose(s[:, 2], torch.full((3,), 0.02))
+    assert (b[:, 0] >= 0).all() and (b[:, 0] <= 0.1 + 1e-6).all() and torch.allclose(b[:, 2], torch.full((3,), 0.0025))
+    o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert not info["success"].any() and (r < 2 / 13 + 1e-6).all()
+    drop = env.obj.pose.raw_pose.clone()
+    drop[:, :2] = b[:, :2] + torch.tensor([0.003, -0.002])          # slightly off centre: the rims keep it in
+    drop[:, 2] = 0.0025 * 2 + 0.02 + 0.01
+    env.obj.set_pose(Pose(drop))
+    env.scene._gpu_apply_all()
+    for _ in range(12):
+        o, r, te, tr, info = env.step(torch.zeros(3, 8))
+    assert info["is_obj_on_bin"].all() and info["is_obj_static"].all() and not info["is_obj_grasped"].any()
+    assert info["success"].all() and torch.allclose(r, torch.ones(3))
+    assert (env.obj.pose.p[:, 2] - (0.005 + 0.02)).abs().max() < 1e-3

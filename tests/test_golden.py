@@ -613,3 +613,24 @@ def test_velocity_controllers_match_the_reference_set_action():
     pv.set_action(T("ctl_pv_act1"))
     close(art.sent, G["ctl_pv_pos_target"], 1e-7)
     close(art.vel_sent, G["ctl_pv_vel_target"], 1e-7)
+
+
+def test_place_sphere_evaluate_reward_obs():
+    """mani_skill/envs/tasks/tabletop/place_sphere.py:186-265 run by the reference's own code on the same synthetic states (spheres in
+    and outside the bin, resting and moving, held and released)."""
+    from maniskill_b200.envs.place_sphere import PlaceSphereEnv as PS
+    m = len(G["place_success"])
+    lin, ang, grasp, rstatic, qpos = T("place_lin"), T("place_ang"), T("place_grasp"), T("place_rstatic"), T("place_qpos")
+    qlim = torch.tensor([[-2.9, 2.9]] * 7 + [[0.0, 0.04]] * 2)[None].repeat(m, 1, 1)
+    obj = SimpleNamespace(pose=Pose(T("place_sphere")), linear_velocity=lin, angular_velocity=ang)
+    obj.is_static = lambda lin_thresh=1e-2, ang_thresh=1e-1: (lin.norm(dim=1) <= lin_thresh) & (ang.norm(dim=1) <= ang_thresh)
+    bin_pose = Pose(torch.hstack([T("place_bin"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
+    fake = SimpleNamespace(obj=obj, bin=SimpleNamespace(pose=bin_pose), radius=0.02, block_half_size=PS.block_half_size, obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("place_tcp"))), is_grasping=lambda o: grasp, is_static=lambda t: rstatic,
+                                                 robot=SimpleNamespace(get_qlimits=lambda: qlim, get_qpos=lambda: qpos)))
+    info = PS.evaluate(fake)
+    for k in ("is_obj_grasped", "is_obj_on_bin", "is_obj_static", "success"):
+        assert np.array_equal(info[k].numpy(), G[f"place_{k}"]), k
+    assert G["place_success"].any() and not G["place_success"].all()
+    close(PS.compute_dense_reward(fake, None, None, info), G["place_reward"], 5e-6)
+    close(U.flatten_state_dict(PS._get_obs_extra(fake, info)), G["place_extra_flat"], 1e-6)
