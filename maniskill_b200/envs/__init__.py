@@ -30,3 +30,6 @@ register_env("RollBall-v1", max_episode_steps=80)(RollBallEnv)
 from .place_sphere import PlaceSphereEnv
 
 register_env("PlaceSphere-v1", max_episode_steps=50)(PlaceSphereEnv)
+from .stack_pyramid import StackPyramidEnv
+
+register_env("StackPyramid-v1", max_episode_steps=250)(StackPyramidEnv)

@@ -139,7 +139,7 @@ class BaseEnv:
         self.num_envs = num_envs
         self._obs_mode = "state" if obs_mode is None else obs_mode
         self.obs_mode_struct = parse_obs_mode(self._obs_mode)   # raises NotImplementedError for unknown / unsupported textures
-        self._reward_mode = "normalized_dense" if reward_mode is None else reward_mode
+        self._reward_mode = self.SUPPORTED_REWARD_MODES[0] if reward_mode is None else reward_mode   # sapien_env.py:300-304
         if self._reward_mode not in self.SUPPORTED_REWARD_MODES:
             raise NotImplementedError(f"Unsupported reward mode: {self._reward_mode}")
         self.sim_params = SimParams(**(sim_config or {}))

@@ -887,6 +887,33 @@ def main():
         G[f"place_{k_}"] = sinfo[k_]
     G["place_reward"] = PS.compute_dense_reward(fake_ps, None, None, sinfo)
     G["place_extra_flat"] = common.flatten_state_dict(PS._get_obs_extra(fake_ps, sinfo), use_torch=True)
+    # ---- StackPyramid task logic (stack_pyramid.py:147-207)
+    sp_mod = load("mani_skill.envs.tasks.tabletop.stack_pyramid", "mani_skill/envs/tasks/tabletop/stack_pyramid.py")
+    SPy = sp_mod.StackPyramidEnv
+    gq = torch.Generator().manual_seed(616)
+    msp = 12
+    pB = torch.hstack([torch.randn(msp, 2, generator=gq) * 0.1, torch.full((msp, 1), 0.02)])
+    pA = pB + torch.hstack([torch.randn(msp, 2, generator=gq) * 0.04, torch.zeros(msp, 1)])
+    pC = (pA + pB) / 2 + torch.hstack([torch.randn(msp, 2, generator=gq) * 0.03, torch.full((msp, 1), 0.04)])
+    pA[:6] = pB[:6] + torch.tensor([0.0, 0.041, 0.0])
+    pC[:6] = (pA[:6] + pB[:6]) / 2 + torch.tensor([0.0, 0.0, 0.04]) + torch.randn(6, 3, generator=gq) * 0.002       # pyramids
+    pC[4, 2] = 0.02                                                                                                    # blue cube not on top
+    rawq = lambda p_: torch.hstack([p_, torch.nn.functional.normalize(torch.randn(msp, 4, generator=gq), dim=-1)])
+    rA, rB, rC = rawq(pA), rawq(pB), rawq(pC)
+    stat = {n_: torch.rand(msp, generator=gq) < 0.8 for n_ in "ABC"}
+    grsp = {n_: torch.rand(msp, generator=gq) < 0.15 for n_ in "ABC"}
+    sp_tcp = torch.hstack([pC + torch.randn(msp, 3, generator=gq) * 0.05, torch.nn.functional.normalize(torch.randn(msp, 4, generator=gq), dim=-1)])
+    cubes = {n_: SimpleNamespace(pose=Pose.create(r_), tag=n_) for n_, r_ in zip("ABC", (rA, rB, rC))}
+    for n_, c_ in cubes.items():
+        c_.is_static = (lambda s_: (lambda lin_thresh=1e-2, ang_thresh=0.5: s_.clone()))(stat[n_])
+    fake_sp = SimpleNamespace(cubeA=cubes["A"], cubeB=cubes["B"], cubeC=cubes["C"], cube_half_size=torch.tensor([0.02] * 3), obs_mode="state",
+                              agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose.create(sp_tcp)), is_grasping=lambda c_: grsp[c_.tag].clone()))
+    yinfo = SPy.evaluate(fake_sp)
+    G["pyr_A"], G["pyr_B"], G["pyr_C"], G["pyr_tcp"] = rA, rB, rC, sp_tcp
+    for n_ in "ABC":
+        G[f"pyr_static_{n_}"], G[f"pyr_grasp_{n_}"] = stat[n_], grsp[n_]
+    G["pyr_success"] = yinfo["success"]
+    G["pyr_extra_flat"] = common.flatten_state_dict(SPy._get_obs_extra(fake_sp, yinfo), use_torch=True)
     np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in G.items()})
     print("wrote", OUT, len(G), "arrays")
 

@@ -575,3 +575,31 @@ def test_place_sphere_reset_layout_and_a_sphere_in_the_bin():
     assert info["is_obj_on_bin"].all() and info["is_obj_static"].all() and not info["is_obj_grasped"].any()
     assert info["success"].all() and torch.allclose(r, torch.ones(3))
     assert (env.obj.pose.p[:, 2] - (0.005 + 0.02)).abs().max() < 1e-3
+
+
+def test_stack_pyramid_layout_reward_modes_and_a_built_pyramid():
+    """StackPyramid-v1 (stack_pyramid.py): three cubes that never start overlapping, 64-dim state observation, sparse reward by default
+    (the task supports "none" and "sparse" only); red next to green with blue resting on both counts as success."""
+    from maniskill_b200.structs import Pose
+    env = ms.make("StackPyramid-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
+    assert env.reward_mode == "none" and env.robot_uids == "panda_wristcam"
+    with pytest.raises(NotImplementedError):
+        ms.make("StackPyramid-v1", num_envs=1, reward_mode="dense", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=4)
+    assert obs.shape == (3, 9 + 9 + 7 + 21 + 18)
+    ps = [c.pose.p for c in (env.cubeA, env.cubeB, env.cubeC)]
+    for i in range(3):
+        for j in range(i + 1, 3):
+            assert (torch.linalg.norm((ps[i] - ps[j])[:, :2], dim=1) > 2 * 0.02 * 2 ** 0.5 - 1e-6).all()
+    assert not env.evaluate()["success"].any()
+    sp = ms.make("StackPyramid-v1", num_envs=3, obs_mode="state", reward_mode="sparse", world_factory=EmuBackendWorld)
+    sp.reset(seed=4)
+    base = torch.tensor([0.1, 0.25, 0.02])                 # away from the gripper
+    ident = torch.tensor([1.0, 0, 0, 0])
+    for cube, off in ((sp.cubeA, [0.0, 0.0, 0.0]), (sp.cubeB, [0.0, 0.0405, 0.0]), (sp.cubeC, [0.0, 0.02025, 0.041])):
+        cube.set_pose(Pose(torch.cat([base + torch.tensor(off), ident])[None].repeat(3, 1)))
+    sp.scene._gpu_apply_all()
+    for _ in range(12):
+        o, r, te, tr, info = sp.step(torch.zeros(3, 8))
+    assert info["success"].all() and torch.equal(r, torch.ones(3)) and te.all()
+    assert (sp.cubeC.pose.p[:, 2] - 0.06).abs().max() < 2e-3

@@ -634,3 +634,20 @@ def test_place_sphere_evaluate_reward_obs():
     assert G["place_success"].any() and not G["place_success"].all()
     close(PS.compute_dense_reward(fake, None, None, info), G["place_reward"], 5e-6)
     close(U.flatten_state_dict(PS._get_obs_extra(fake, info)), G["place_extra_flat"], 1e-6)
+
+
+def test_stack_pyramid_evaluate_obs():
+    """mani_skill/envs/tasks/tabletop/stack_pyramid.py:147-207 run by the reference's own code on the same synthetic states (built
+    pyramids, near misses, moving or held cubes)."""
+    from maniskill_b200.envs.stack_pyramid import StackPyramidEnv as SP
+    cubes = {}
+    for n in "ABC":
+        c = SimpleNamespace(pose=Pose(T(f"pyr_{n}")), tag=n)
+        c.is_static = (lambda s: (lambda lin_thresh=1e-2, ang_thresh=0.5: s))(T(f"pyr_static_{n}"))
+        cubes[n] = c
+    fake = SimpleNamespace(cubeA=cubes["A"], cubeB=cubes["B"], cubeC=cubes["C"], cube_half_size=torch.tensor([0.02] * 3), obs_mode="state",
+                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("pyr_tcp"))), is_grasping=lambda c: T(f"pyr_grasp_{c.tag}")))
+    fake._pair_ok = lambda offset, cube, on_top: SP._pair_ok(fake, offset, cube, on_top)
+    info = SP.evaluate(fake)
+    assert np.array_equal(info["success"].numpy(), G["pyr_success"]) and G["pyr_success"].any() and not G["pyr_success"].all()
+    close(U.flatten_state_dict(SP._get_obs_extra(fake, info)), G["pyr_extra_flat"], 1e-6)
