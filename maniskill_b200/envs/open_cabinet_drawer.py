@@ -59,6 +59,18 @@ class _PerEnvLink(Link):
         self._idx = torch.arange(scene.num_envs, device=scene.device) * scene.world.n_rows + rows
 
 
+class _JointOfPerEnvLink:
+    """`handle_link.joint` of the reference (ArticulationJoint.merge, open_cabinet_drawer.py:180-182, :308-311): the parent joint of a link
+    that differs per sub-scene; `.qpos` is that joint's position in every sub-scene."""
+
+    def __init__(self, env):
+        self._env = env
+
+    @property
+    def qpos(self):
+        return self._env._target_joint_qpos()
+
+
 class OpenCabinetDrawerEnv(BaseEnv):
     max_episode_steps = 100
     min_open_frac = 0.75
@@ -104,6 +116,7 @@ class OpenCabinetDrawerEnv(BaseEnv):
         pick = np.asarray(self._link_ids) % len(drawers)
         rows = torch.tensor([self.cabinet.links_map[drawers[i]].row for i in pick], device=dev)
         self.handle_link = _PerEnvLink(self.scene, "handle_link", rows)
+        self.handle_link.joint = _JointOfPerEnvLink(self)
         self._target_dof = torch.tensor([self.cabinet.dof_names.index(drawers[i] + "_joint") for i in pick], device=dev)
         self.handle_link_pos = torch.tensor(self._handle_local, dtype=torch.float32, device=dev)[None].expand(self.num_envs, 3)
         ar = torch.arange(self.num_envs, device=dev)

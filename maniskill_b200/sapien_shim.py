@@ -18,6 +18,7 @@ from . import building as _b
 from . import physx_shim as _px
 
 _GPU_ENABLED = False
+_ME = sys.modules[__name__]
 
 
 def _module(name: str, **attrs) -> types.ModuleType:
@@ -70,12 +71,11 @@ def install(force: bool = False) -> bool:
     `force`."""
     if not force:
         import importlib.util
-        if "sapien" in sys.modules and sys.modules["sapien"] is not sys.modules[__name__]:
+        if "sapien" in sys.modules and sys.modules["sapien"] is not _ME:
             return False
         if "sapien" not in sys.modules and importlib.util.find_spec("sapien") is not None:
             return False
-    me = sys.modules[__name__]
-    sys.modules["sapien"] = me
+    sys.modules["sapien"] = _ME
     sys.modules["sapien.physx"] = physx
     sys.modules["sapien.render"] = render
     sys.modules["sapien.wrapper"] = wrapper

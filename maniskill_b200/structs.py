@@ -68,6 +68,8 @@ class Pose:
         return Pose(self.raw_pose[i] if self.raw_pose[i].dim() == 2 else self.raw_pose[i][None])
 
     def __mul__(self, other: "Pose") -> "Pose":
+        if not isinstance(other, Pose):   # a single `sapien.Pose` (building.Pose) on the right, as pose.py:187-199 accepts
+            other = Pose.create(np.concatenate([np.asarray(other.p, dtype=np.float32), np.asarray(other.q, dtype=np.float32)]), self.raw_pose.device)
         a, b = self.raw_pose, other.raw_pose
         if b.shape[0] == 1 and a.shape[0] > 1:
             b = b.expand(a.shape[0], 7)

@@ -32,7 +32,7 @@ def _load_reference_module(path, as_name=None):
     for node in ast.walk(ast.parse(open(path).read())):
         names = [node.module] if isinstance(node, ast.ImportFrom) and node.module else [a.name for a in node.names] if isinstance(node, ast.Import) else []
         for name in names:
-            if name.split(".")[0] in ("mani_skill", "sapien", "trimesh", "gymnasium", "transforms3d", "dacite", "lxml", "pytorch_kinematics"):
+            if name.split(".")[0] in ("mani_skill", "sapien", "trimesh", "gymnasium", "transforms3d", "dacite", "lxml", "pytorch_kinematics", "matplotlib"):
                 parts = name.split(".")
                 for i in range(1, len(parts) + 1):
                     ensure(".".join(parts[:i]))
@@ -240,3 +240,59 @@ def test_reference_pose_struct_over_the_sapien_shim():
             if k not in saved:
                 del sys.modules[k]
         sys.modules.update(saved)
+
+
+TASK_FILES = {
+    "PickCube-v1": ("pick_cube.py", "PickCubeEnv"), "PushCube-v1": ("push_cube.py", "PushCubeEnv"), "PullCube-v1": ("pull_cube.py", "PullCubeEnv"),
+    "StackCube-v1": ("stack_cube.py", "StackCubeEnv"), "LiftPegUpright-v1": ("lift_peg_upright.py", "LiftPegUprightEnv"),
+    "PokeCube-v1": ("poke_cube.py", "PokeCubeEnv"), "RollBall-v1": ("roll_ball.py", "RollBallEnv"), "PlaceSphere-v1": ("place_sphere.py", "PlaceSphereEnv"),
+    "StackPyramid-v1": ("stack_pyramid.py", "StackPyramidEnv"), "PegInsertionSide-v1": ("peg_insertion_side.py", "PegInsertionSideEnv"),
+    "OpenCabinetDrawer-v1": ("../mobile_manipulation/open_cabinet_drawer.py", "OpenCabinetDrawerEnv"),
+}
+
+
+@pytest.mark.parametrize("task", sorted(TASK_FILES))
+def test_reference_task_logic_on_our_live_env(reference_module, task):
+    """The reference's own task class -- `evaluate`, `_get_obs_extra`, `compute_dense_reward` of mani_skill/envs/tasks/tabletop/<task>.py --
+    called with `self` = OUR running env (same attribute names: actors, agent, tcp, obs_mode_struct, device ...) at every step of a random
+    rollout on the emulated backend; each result must equal what the mirror's own methods return on the same state."""
+    from maniskill_b200 import sapien_shim, structs
+    fname, cls_name = TASK_FILES[task]
+    sapien_shim.install(force=True)          # `sapien.Pose(...)` inside the task code is the shim's Pose, not a mock
+    rot = reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
+    for name, attrs in (("mani_skill.envs.sapien_env", dict(BaseEnv=object)),
+                        ("mani_skill.utils.registration", dict(register_env=lambda *a, **k: (lambda cls: cls))),
+                        ("mani_skill.utils.structs.pose", dict(Pose=structs.Pose)), ("mani_skill.utils.structs", dict(Pose=structs.Pose)),
+                        ("mani_skill.utils.geometry", dict(rotation_conversions=rot))):
+        m = MagicMock(name=name, **attrs)
+        m.__name__, m.__path__, m.__all__ = name, [], []
+        sys.modules[name] = m
+    mod = reference_module(f"/root/reference/mani_skill/envs/tasks/tabletop/{fname}")
+    Ref = getattr(mod, cls_name)
+    kw = dict(reward_mode="sparse") if task == "StackPyramid-v1" else {}
+    env = ms.make(task, num_envs=3, obs_mode="state", world_factory=EmuBackendWorld, **kw)
+    env.reset(seed=3)
+    g = torch.Generator().manual_seed(0)
+    for t in range(8):
+        a = 2 * torch.rand(3, env.action_dim, generator=g) - 1
+        a[:, -1] = -1.0 if t >= 2 else 1.0                     # close the gripper after two steps: contact forces on the fingers
+        obs, rew, te, tr, info = env.step(a)
+        status0 = env.reached_status.clone() if hasattr(env, "reached_status") else None
+        ours_info = env.evaluate()
+        ref_info = Ref.evaluate(env)
+        assert set(ref_info) == set(ours_info), (set(ref_info), set(ours_info))
+        for k in ref_info:
+            assert torch.allclose(torch.as_tensor(ref_info[k]).float(), torch.as_tensor(ours_info[k]).float(), atol=1e-6), (t, k)
+        ref_extra, ours_extra = Ref._get_obs_extra(env, ref_info), env._get_obs_extra(ours_info)
+        assert list(ref_extra) == list(ours_extra)               # same keys in the same order: the flattened state vector has the same layout
+        for k in ref_extra:
+            assert torch.allclose(ref_extra[k].float(), ours_extra[k].float(), atol=1e-6), (t, k)
+        if hasattr(Ref, "compute_dense_reward") and "compute_dense_reward" in Ref.__dict__:
+            ours_r = env.compute_dense_reward(obs, a, ours_info)
+            status1 = env.reached_status.clone() if status0 is not None else None
+            if status0 is not None:
+                env.reached_status = status0.clone()
+            ref_r = Ref.compute_dense_reward(env, obs, a, {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in ref_info.items()})
+            assert torch.allclose(ref_r, ours_r, atol=2e-5), (t, ref_r, ours_r)
+            if status0 is not None:
+                assert torch.equal(env.reached_status, status1)
