@@ -40,6 +40,8 @@ class Pose:
     def create(cls, pose, device=None):
         if isinstance(pose, Pose):
             return pose
+        if hasattr(pose, "p") and hasattr(pose, "q") and not isinstance(pose, torch.Tensor):   # a single `sapien.Pose` (pose.py:128-135)
+            pose = np.concatenate([np.asarray(pose.p, dtype=np.float32), np.asarray(pose.q, dtype=np.float32)])
         t = U.to_tensor(pose, device)
         if t.dim() == 1:
             t = t[None]

@@ -296,3 +296,55 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
             assert torch.allclose(ref_r, ours_r, atol=2e-5), (t, ref_r, ours_r)
             if status0 is not None:
                 assert torch.equal(env.reached_status, status1)
+
+
+INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1"]
+
+
+@pytest.mark.parametrize("task", INIT_TASKS)
+def test_reference_episode_initialisation_on_our_env(reference_module, task):
+    """`reset(seed)` with the episode initialisation done by the REFERENCE's code: the task's own `_initialize_episode` and the real
+    `TableSceneBuilder.initialize` (mani_skill/utils/scene_builder/table/scene_builder.py:68-127), `random_quaternions` and
+    `UniformPlacementSampler` run against our env object (actors' `set_pose`, `agent.reset`, the episode RNG, `sapien.Pose` from the shim).
+    The resulting simulation state must equal the state after the mirror's own reset with the same seed: same random streams, same
+    layout, same robot configuration."""
+    from maniskill_b200 import sapien_shim, structs, utils as U
+    fname, cls_name = TASK_FILES[task]
+    sapien_shim.install(force=True)
+    rot = reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
+    stubs = dict([("mani_skill.envs.sapien_env", dict(BaseEnv=object)), ("mani_skill.utils.registration", dict(register_env=lambda *a, **k: (lambda cls: cls))),
+                  ("mani_skill.utils.structs.pose", dict(Pose=structs.Pose)), ("mani_skill.utils.structs", dict(Pose=structs.Pose)),
+                  ("mani_skill.utils.geometry", dict(rotation_conversions=rot)), ("transforms3d", dict()), ("transforms3d.euler", dict(euler2quat=U.euler2quat)),
+                  ("mani_skill.utils.scene_builder", dict(SceneBuilder=object)),
+                  ("mani_skill.utils.common", dict(to_tensor=lambda x, device=None: torch.as_tensor(x, device=device)))])
+    for name, attrs in stubs.items():
+        m = MagicMock(name=name, **attrs)
+        m.__name__, m.__path__, m.__all__ = name, [], []
+        sys.modules[name] = m
+    sys.modules["mani_skill.utils"] = MagicMock(common=sys.modules["mani_skill.utils.common"])
+    rpose = reference_module("/root/reference/mani_skill/envs/utils/randomization/pose.py")
+    rsamp = reference_module("/root/reference/mani_skill/envs/utils/randomization/samplers.py")
+    rsamp.common = sys.modules["mani_skill.utils.common"]
+    rcommon = reference_module("/root/reference/mani_skill/envs/utils/randomization/common.py")
+    rcommon.common = sys.modules["mani_skill.utils.common"]
+    rnd = MagicMock(random_quaternions=rpose.random_quaternions, UniformPlacementSampler=rsamp.UniformPlacementSampler, uniform=rcommon.uniform)
+    rnd.__name__, rnd.__path__, rnd.__all__ = "mani_skill.envs.utils.randomization", [], []
+    sys.modules["mani_skill.envs.utils.randomization"] = rnd
+    sys.modules["mani_skill.envs.utils"] = MagicMock(randomization=rnd)
+    table_mod = reference_module("/root/reference/mani_skill/utils/scene_builder/table/scene_builder.py")
+    mod = reference_module(f"/root/reference/mani_skill/envs/tasks/tabletop/{fname}")
+    mod.randomization = rnd
+    Ref = getattr(mod, cls_name)
+    kw = dict(reward_mode="sparse") if task == "StackPyramid-v1" else {}
+    ours, theirs = [ms.make(task, num_envs=4, obs_mode="state", world_factory=EmuBackendWorld, **kw) for _ in range(2)]
+    builder = table_mod.TableSceneBuilder.__new__(table_mod.TableSceneBuilder)
+    builder.env, builder.table, builder.robot_init_qpos_noise = theirs, theirs.table, getattr(theirs, "robot_init_qpos_noise", 0.02)
+    theirs.table_scene = builder
+    theirs._initialize_episode = lambda env_idx, options: Ref._initialize_episode(theirs, env_idx, options)
+    for seed, idx in ((11, None), (12, torch.tensor([1, 3]))):
+        opts = dict() if idx is None else dict(env_idx=idx)
+        o1, _ = ours.reset(seed=seed, options=dict(opts))
+        o2, _ = theirs.reset(seed=seed, options=dict(opts))
+        s1, s2 = ours.get_state(), theirs.get_state()
+        assert torch.allclose(s1, s2, atol=1e-6), (task, seed, float((s1 - s2).abs().max()))
+        assert torch.allclose(o1, o2, atol=1e-5)
