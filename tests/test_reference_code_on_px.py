@@ -348,3 +348,48 @@ def test_reference_episode_initialisation_on_our_env(reference_module, task):
         s1, s2 = ours.get_state(), theirs.get_state()
         assert torch.allclose(s1, s2, atol=1e-6), (task, seed, float((s1 - s2).abs().max()))
         assert torch.allclose(o1, o2, atol=1e-5)
+
+
+def test_reference_panda_grasp_checks_on_our_agent_during_a_scripted_grasp(reference_module):
+    """mani_skill/agents/robots/panda/panda.py `is_grasping` / `is_static` (with the real `common.compute_angle_between`) called with `self` =
+    our agent while a scripted pick closes the gripper on the cube and lifts it: the reference's verdict follows ours through approach,
+    grasp and lift (contact forces come from the px-level queries of the emulated device code)."""
+    from maniskill_b200 import sapien_shim
+    sapien_shim.install(force=True)
+    for name, attrs in (("mani_skill.agents.base_agent", dict(BaseAgent=object, Keyframe=lambda **k: None)),
+                        ("mani_skill.agents.registration", dict(register_agent=lambda *a, **k: (lambda cls: cls)))):
+        m = MagicMock(name=name, **attrs)
+        m.__name__, m.__path__, m.__all__ = name, [], []
+        sys.modules[name] = m
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    sys.modules["mani_skill.utils"] = MagicMock(common=common)
+    panda_mod = reference_module("/root/reference/mani_skill/agents/robots/panda/panda.py")
+    panda_mod.common = common
+    RefPanda = panda_mod.Panda
+    n = 2
+    env = ms.make("PickCube-v1", num_envs=n, obs_mode="state", control_mode="pd_ee_target_delta_pos", world_factory=EmuBackendWorld)
+    env.reset(seed=4)
+    ctrl = env.agent.controller.controllers["arm"]
+    base = torch.tensor([-0.615, 0.0, 0.0])
+    cube0 = env.cube.pose.p.clone()
+    seen = []
+
+    def go_to(target, steps, grip, max_step=0.03):
+        for _ in range(steps):
+            a = torch.zeros(n, 4)
+            a[:, :3] = (target - ctrl._target_pose.p).clamp(-max_step, max_step) / 0.1
+            a[:, 3] = grip
+            env.step(a)
+            ours_g, ref_g = env.agent.is_grasping(env.cube), RefPanda.is_grasping(env.agent, env.cube)
+            assert torch.equal(ours_g, ref_g)
+            assert torch.equal(env.agent.is_static(0.2), RefPanda.is_static(env.agent, 0.2))
+            for angle in (20, 85):
+                assert torch.equal(env.agent.is_grasping(env.cube, max_angle=angle), RefPanda.is_grasping(env.agent, env.cube, max_angle=angle))
+            seen.append(bool(ref_g.all()))
+
+    go_to(cube0 - base + torch.tensor([0.0, 0.0, 0.10]), 12, 1.0)
+    go_to(cube0 - base, 12, 1.0)
+    assert not any(seen)
+    go_to(cube0 - base, 8, -1.0)
+    go_to(cube0 - base + torch.tensor([0.0, 0.0, 0.10]), 14, -1.0, max_step=0.015)
+    assert seen[-1] and (env.cube.pose.p[:, 2] - cube0[:, 2] > 0.08).all()       # grasped and lifted, by the reference's own check
