@@ -58,6 +58,17 @@ class Scene:
         self._query_cache = {}
 
     @property
+    def _reset_mask(self):
+        """Which sub-scenes the setters act on (mani_skill/envs/scene.py `_reset_mask`).  Assigning a new mask drops the python-side
+        "all sub-scenes" shortcut; code that knows the mask is all-true sets `_reset_all = True` afterwards."""
+        return self.__dict__["_reset_mask_tensor"]
+
+    @_reset_mask.setter
+    def _reset_mask(self, mask):
+        self.__dict__["_reset_mask_tensor"] = mask
+        self._reset_all = False
+
+    @property
     def px(self):
         """`scene.px` of the reference (scene.py:61-63): the `PhysxGpuSystem`-shaped view of the world, built on first use."""
         if self._px is None:

@@ -10,6 +10,7 @@ import sys
 from types import SimpleNamespace
 from unittest.mock import MagicMock
 
+import numpy as np
 import pytest
 import torch
 
@@ -393,3 +394,36 @@ def test_reference_panda_grasp_checks_on_our_agent_during_a_scripted_grasp(refer
     go_to(cube0 - base, 8, -1.0)
     go_to(cube0 - base + torch.tensor([0.0, 0.0, 0.10]), 14, -1.0, max_step=0.015)
     assert seen[-1] and (env.cube.pose.p[:, 2] - cube0[:, 2] > 0.08).all()       # grasped and lifted, by the reference's own check
+
+
+def test_reference_base_env_reset_drives_our_env(reference_module):
+    """`BaseEnv.reset` of mani_skill/envs/sapien_env.py:857-978 itself -- seeding, reset mask, velocity clearing, episode initialisation
+    under the forked torch RNG, `scene._gpu_apply_all()`, `scene.px.gpu_update_articulation_kinematics()`, `scene._gpu_fetch_all()`,
+    controller reset, first observation -- executed with `self` = our env.  After the same sequence of seeded, partial and unseeded resets
+    (with steps in between) it must leave the state and return the observation of the mirror's own `reset`."""
+    gym = MagicMock(Env=type("Env", (), {}))
+    gym.__name__, gym.__path__, gym.__all__ = "gymnasium", [], []
+    sys.modules["gymnasium"] = gym
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    brng = reference_module("/root/reference/mani_skill/envs/utils/randomization/batched_rng.py")
+    brng.common = common
+    se = reference_module("/root/reference/mani_skill/envs/sapien_env.py")
+    se.common, se.BatchedRNG = common, brng.BatchedRNG
+    RefBaseEnv = se.BaseEnv
+    for task in ("PickCube-v1", "PushCube-v1"):
+        ours, theirs = [ms.make(task, num_envs=4, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
+        theirs._batched_rng_backend = "numpy:random_state"
+        g = torch.Generator().manual_seed(1)
+        script = [dict(seed=21), dict(options=dict(env_idx=torch.tensor([0, 2]))), dict(seed=[5, 6, 7, 8]), dict(), dict(seed=3, options=dict(env_idx=torch.tensor([1])))]
+        for kw in script:
+            a = 2 * torch.rand(4, ours.action_dim, generator=g) - 1
+            for e in (ours, theirs):
+                e.step(a)
+            torch.manual_seed(99)            # unseeded resets draw from the global torch stream: give both the same one
+            o1, i1 = ours.reset(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+            torch.manual_seed(99)
+            o2, i2 = RefBaseEnv.reset(theirs, **{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+            assert torch.allclose(o1, o2, atol=1e-5), (task, kw, (o1 - o2).abs().max(dim=1).values, (o1 - o2).abs().max(dim=0).values.nonzero().flatten())
+            assert torch.allclose(ours.get_state(), theirs.get_state(), atol=1e-6), (task, kw)
+            assert torch.equal(ours.elapsed_steps, theirs.elapsed_steps) and i2["reconfigure"] is False
+            assert np.array_equal(np.asarray(ours._episode_seed), np.asarray(theirs._episode_seed))
