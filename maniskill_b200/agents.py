@@ -285,6 +285,17 @@ class CombinedController:
             d += c.action_dim
         self.action_dim = d
 
+    @property
+    def sets_target_qpos(self) -> bool:
+        return any(c.sets_target_qpos for c in self.controllers.values())
+
+    @property
+    def sets_target_qvel(self) -> bool:
+        return any(c.sets_target_qvel for c in self.controllers.values())
+
+    def before_simulation_step(self):
+        """Interpolated targets are not part of this build: nothing changes between the simulation steps of a control step."""
+
     def reset(self, env_idx=None):
         for c in self.controllers.values():
             c.reset(env_idx)
@@ -392,6 +403,10 @@ class Panda:
 
     def set_action(self, action):
         self.controller.set_action(action)
+
+    def before_simulation_step(self):
+        """base_agent.py:332-334."""
+        self.controller.before_simulation_step()
 
     def get_proprioception(self):
         obs = dict(qpos=self.robot.get_qpos(), qvel=self.robot.get_qvel())
@@ -503,6 +518,7 @@ class Fetch:
     action_bounds = Panda.action_bounds
     reset = Panda.reset
     set_action = Panda.set_action
+    before_simulation_step = Panda.before_simulation_step
     get_proprioception = Panda.get_proprioception
 
     def controller_reset(self, env_idx=None):

@@ -11,6 +11,7 @@ interface through ``world_factory`` (tests/ only).
 from __future__ import annotations
 
 import os
+from types import SimpleNamespace
 from typing import Dict, Optional, Sequence, Union
 
 import numpy as np
@@ -21,6 +22,7 @@ from ..backend import (BUF_ALL, BUF_APPLY_ALL, BUF_QF, BUF_QPOS, BUF_QVEL, BUF_R
                        BUF_TARGET_QVEL)
 from ..model import CompiledModel, SceneDesc, SimParams
 from ..observations import parse_obs_mode, sensor_data_to_pointcloud
+from ..sapien_shim import Device
 from ..visualization import camera_observations_to_images, tile_images
 from ..structs import Actor, Articulation, Pose
 
@@ -214,6 +216,9 @@ class BaseEnv:
         self.agent.set_control_mode(self._control_mode_arg)
         self.single_action_space_low, self.single_action_space_high = self.agent.action_bounds()
         self.action_dim = self.single_action_space_low.shape[0]
+        self._orig_single_action_space = SimpleNamespace(shape=(self.action_dim,), low=self.single_action_space_low, high=self.single_action_space_high)
+        # `sapien.Device` of the simulation (sapien_env.py:1111 asks `.is_cuda()`): this backend is the GPU simulation by construction
+        self._sim_device = Device(f"cuda:{self.device.index or 0}")
         self._sensors = self._setup_sensors() if self._visual else {}
         self._human_render_cameras = None    # created on the first render_rgb_array()
         self._last_obs = None
@@ -436,10 +441,24 @@ class BaseEnv:
             self.agent.set_action(action)
             self.scene._gpu_apply_all()  # px.gpu_apply_articulation_target_position (sapien_env.py:1118-1121)
         self._before_control_step()
-        # `for _ in range(self._sim_steps_per_control): scene.step()` + `_gpu_fetch_all()` as one fused launch
-        self.scene.step(self._sim_steps_per_control, BUF_ALL)
+        cls = type(self)
+        if cls._before_simulation_step is BaseEnv._before_simulation_step and cls._after_simulation_step is BaseEnv._after_simulation_step:
+            # `for _ in range(self._sim_steps_per_control): scene.step()` + `_gpu_fetch_all()` as one fused launch
+            self.scene.step(self._sim_steps_per_control, BUF_ALL)
+        else:  # a task hooks into the individual simulation steps (sapien_env.py:1123-1128): one launch per step, then the fetch
+            for _ in range(self._sim_steps_per_control):
+                self._before_simulation_step()
+                self.scene.step(1, 0)
+                self._after_simulation_step()
+            self.scene._gpu_fetch_all()
         self._after_control_step()
         return action
+
+    def _before_simulation_step(self):
+        """task hook, called before every simulation step of a control step (sapien_env.py:1473-1476)."""
+
+    def _after_simulation_step(self):
+        """task hook, called after every simulation step of a control step."""
 
     def _before_control_step(self):
         pass
@@ -459,20 +478,26 @@ class BaseEnv:
     def _get_obs_state_dict(self, info):
         return dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
 
-    def get_obs(self, info=None):
+    def get_obs(self, info=None, unflattened: bool = False):
+        """sapien_env.py:501-533.  `unflattened` returns the raw nested dict (what the reward functions are handed in `step`)."""
         if info is None:
             info = self.get_info()
         if self._obs_mode == "none":
             return dict()
+        if self._obs_mode in ("state", "state_dict"):
+            obs = self._get_obs_state_dict(info)
+        else:  # visual modes (sapien_env.py:535-625): agent + extra + sensor data / params
+            obs = self._add_sensor_obs(dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info)))
+        return obs if unflattened else self._flatten_raw_obs(obs)
+
+    def _flatten_raw_obs(self, obs):
+        """sapien_env.py:535-544: "state" flattens everything; a visual mode with the `state` flag replaces `agent` and `extra` by one
+        flat `state` vector next to the sensor entries."""
         if self._obs_mode == "state":
-            return U.flatten_state_dict(self._get_obs_state_dict(info))
-        if self._obs_mode == "state_dict":
-            return self._get_obs_state_dict(info)
-        # visual modes (sapien_env.py:535-625): agent + extra (+ state when requested) + sensor data / params
-        obs = dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
-        if self.obs_mode_struct.state:
-            obs["state"] = U.flatten_state_dict(self._get_obs_state_dict(info))
-        return self._add_sensor_obs(obs)
+            return U.flatten_state_dict(obs)
+        if self.obs_mode_struct.state and isinstance(obs, dict) and "agent" in obs:
+            obs["state"] = U.flatten_state_dict(dict(agent=obs.pop("agent"), extra=obs.pop("extra")))
+        return obs
 
     def _add_sensor_obs(self, obs):
         """sapien_env.py:525-532: camera parameters + the requested textures, as a point cloud under obs mode "pointcloud"."""
@@ -481,11 +506,13 @@ class BaseEnv:
         return sensor_data_to_pointcloud(obs) if self.obs_mode_struct.pointcloud else obs
 
     def _visual_obs_from_fused(self, vec, info):
-        """Visual-mode observation (same structure as `get_obs`) with the agent / extra entries taken from the fused state vector."""
-        obs = self._obs_from_fused(vec, info)
+        """Visual-mode observation (same structure as `get_obs`) with the agent / extra entries -- or, under the `state` flag, the flat
+        state vector that replaces them -- taken from the fused state vector."""
         if self.obs_mode_struct.state:
+            obs = self._add_sensor_obs(dict())
             obs["state"] = vec
-        return self._add_sensor_obs(obs)
+            return obs
+        return self._add_sensor_obs(self._obs_from_fused(vec, info))
 
     def _sensor_configs(self):
         """task hook: list of dict(uid, pose(7), width, height, fov, near, far, mount(link/actor name or None))."""

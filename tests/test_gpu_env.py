@@ -93,7 +93,7 @@ def test_fused_step_matches_python_path():
 
 def test_fused_step_serves_visual_obs_modes(monkeypatch):
     """The fused control step also runs under the visual observation modes (default; B2S_FUSED_VISUAL=0 turns it off): same
-    observation dict (agent, extra, state, sensor data) as the torch path."""
+    observation dict (state, sensor parameters, sensor data) as the torch path."""
     import maniskill_b200 as ms
     n = 16
     monkeypatch.setenv("B2S_FUSED_VISUAL", "1")
@@ -107,12 +107,9 @@ def test_fused_step_serves_visual_obs_modes(monkeypatch):
         a = 2 * torch.rand((n, 8), device=e1.device, generator=g) - 1
         o1, r1, t1, _, i1 = e1.step(a)
         o2, r2, t2, _, i2 = e2.step(a)
-        assert set(o1.keys()) == set(o2.keys()) == {"agent", "extra", "state", "sensor_param", "sensor_data"}
-        assert torch.allclose(o1["state"], o2["state"], atol=2e-5)
-        for grp in ("agent", "extra"):
-            assert set(o1[grp].keys()) == set(o2[grp].keys())
-            for k in o1[grp]:
-                assert o1[grp][k].dtype == o2[grp][k].dtype and torch.allclose(o1[grp][k].float(), o2[grp][k].float(), atol=2e-5), (grp, k)
+        # a visual mode with the `state` flag carries one flat state vector in place of agent / extra (sapien_env.py:540-544)
+        assert set(o1.keys()) == set(o2.keys()) == {"state", "sensor_param", "sensor_data"}
+        assert o1["state"].shape == (n, 42) and torch.allclose(o1["state"], o2["state"], atol=2e-5)
         for k in ("rgb", "depth"):
             d = (o1["sensor_data"]["base_camera"][k].int() - o2["sensor_data"]["base_camera"][k].int()).abs()
             assert (d > 1).float().mean() < 1e-3, k  # the two envs' physics agree to ~1e-5: a handful of edge pixels may flip

@@ -51,7 +51,7 @@ def test_texture_modes_deliver_exactly_the_requested_textures(mode, textures):
 def test_state_plus_textures_and_the_hidden_goal():
     env = ms.make("PickCube-v1", num_envs=2, obs_mode="state+rgb+segmentation", world_factory=EmuBackendWorld)
     obs, _ = env.reset(seed=0)
-    assert obs["state"].shape == (2, 42) and "obj_pose" in obs["extra"]
+    assert set(obs) == {"state", "sensor_param", "sensor_data"} and obs["state"].shape == (2, 42)      # agent / extra folded into `state`
     ids = set(np.unique(obs["sensor_data"]["base_camera"]["segmentation"].numpy()).tolist())
     cm = env.cm
     assert cm.actor_seg_id["cube"] in ids and cm.actor_seg_id["table-workspace"] in ids and cm.actor_seg_id["goal_site"] not in ids

@@ -427,3 +427,47 @@ def test_reference_base_env_reset_drives_our_env(reference_module):
             assert torch.allclose(ours.get_state(), theirs.get_state(), atol=1e-6), (task, kw)
             assert torch.equal(ours.elapsed_steps, theirs.elapsed_steps) and i2["reconfigure"] is False
             assert np.array_equal(np.asarray(ours._episode_seed), np.asarray(theirs._episode_seed))
+
+
+def test_reference_base_env_step_drives_our_env(reference_module):
+    """`BaseEnv.step` and `_step_action` of mani_skill/envs/sapien_env.py:1042-1132 themselves, with `self` = our env: the action goes
+    through our agent, `self.scene.px.gpu_apply_articulation_target_position()`, five `self.scene.step()`, `self.scene._gpu_fetch_all()`, then
+    `get_info` / `get_obs(info, unflattened=True)` / `get_reward` / `_flatten_raw_obs` and the termination logic of the reference.  Every
+    return value equals the mirror's own `step` (one fused launch instead of five) over a rollout, in state and in state+rgb mode."""
+    gym = MagicMock(Env=type("Env", (), {}))
+    gym.__name__, gym.__path__, gym.__all__ = "gymnasium", [], []
+    sys.modules["gymnasium"] = gym
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    se = reference_module("/root/reference/mani_skill/envs/sapien_env.py")
+    se.common = common
+    se.MultiAgent = type("MultiAgent", (), {})
+    RefBaseEnv = se.BaseEnv
+    calls = []
+    for task, mode, cm in (("PickCube-v1", "state", "pd_joint_delta_pos"), ("PushCube-v1", "state_dict", "pd_joint_vel"), ("PickCube-v1", "state+rgb", "pd_joint_pos")):
+        ours, theirs = [ms.make(task, num_envs=3, obs_mode=mode, control_mode=cm, world_factory=EmuBackendWorld, fused=False,
+                                sensor_configs=dict(base_camera=dict(width=16, height=16))) for _ in range(2)]
+        for e in (ours, theirs):
+            e.reset(seed=8)
+        theirs._step_action = (lambda e: (lambda action: RefBaseEnv._step_action(e, action)))(theirs)      # the reference's, not the mirror's
+        px = theirs.scene.px
+        for name in ("gpu_apply_articulation_target_position", "gpu_apply_articulation_target_velocity"):
+            orig = getattr(px, name)
+            setattr(px, name, (lambda o, n_: (lambda: (calls.append(n_), o())[1]))(orig, name))
+        g = torch.Generator().manual_seed(5)
+        for t in range(6):
+            a = 2 * torch.rand(3, ours.action_dim, generator=g) - 1
+            o1, r1, te1, tr1, i1 = ours.step(a)
+            o2, r2, te2, tr2, i2 = RefBaseEnv.step(theirs, a)
+
+            def same(x, y, path=""):
+                if isinstance(x, dict):
+                    assert set(x) == set(y), path
+                    for k in x:
+                        same(x[k], y[k], path + "/" + k)
+                else:
+                    assert x.dtype == y.dtype and torch.allclose(x.float(), y.float(), atol=1e-6), (task, mode, t, path)
+            same(o1, o2, "obs")
+            same(i1, i2, "info")
+            assert torch.allclose(r1, r2, atol=1e-6) and torch.equal(te1, te2) and torch.equal(tr1, tr2)
+            assert torch.equal(ours.scene.world.rigid_body_data, theirs.scene.world.rigid_body_data)
+    assert "gpu_apply_articulation_target_position" in calls and "gpu_apply_articulation_target_velocity" in calls
