@@ -471,3 +471,64 @@ def test_reference_base_env_step_drives_our_env(reference_module):
             assert torch.allclose(r1, r2, atol=1e-6) and torch.equal(te1, te2) and torch.equal(tr1, tr2)
             assert torch.equal(ours.scene.world.rigid_body_data, theirs.scene.world.rigid_body_data)
     assert "gpu_apply_articulation_target_position" in calls and "gpu_apply_articulation_target_velocity" in calls
+
+
+def test_reference_vector_wrapper_and_timelimit_around_our_env(reference_module):
+    """The reference's `TimeLimitWrapper.step` (mani_skill/utils/registration.py:127-170) and `ManiSkillVectorEnv.step / reset`
+    (mani_skill/vector/wrappers/gymnasium.py:96-176) wrapped around OUR env, against the mirror's own vector wrapper around a twin env:
+    observations, rewards, terminations, truncations, `final_info` / `final_observation`, the auto-reset of finished sub-scenes and the
+    episode metrics agree over a rollout that crosses the time limit."""
+    class Wrapper:                                   # gymnasium.Wrapper: forwards to `.env`
+        def __init__(self, env):
+            self.env = env
+        def reset(self, *a, **k):
+            return self.env.reset(*a, **k)
+        def step(self, a):
+            return self.env.step(a)
+    gym = MagicMock(Wrapper=Wrapper, Env=type("Env", (), {}))
+    gym.__name__, gym.__path__, gym.__all__ = "gymnasium", [], []
+    sys.modules["gymnasium"] = gym
+    vec = MagicMock(VectorEnv=object)
+    vec.__name__, vec.__path__, vec.__all__ = "gymnasium.vector", [], []
+    sys.modules["gymnasium.vector"] = vec
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    sys.modules["mani_skill.utils"] = MagicMock(common=common)
+    reg = reference_module("/root/reference/mani_skill/utils/registration.py")
+    vw = reference_module("/root/reference/mani_skill/vector/wrappers/gymnasium.py")
+    vw.common = common
+    n, limit = 3, 7
+    ours_env, their_env = [ms.make("PushCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
+    their_env.unwrapped = their_env
+    tl = reg.TimeLimitWrapper.__new__(reg.TimeLimitWrapper)
+    tl.env, tl._max_episode_steps = their_env, limit
+    tl.unwrapped = their_env
+    ref = vw.ManiSkillVectorEnv.__new__(vw.ManiSkillVectorEnv)
+    ref.__dict__.update(_env=tl, num_envs=n, auto_reset=True, ignore_terminations=False, record_metrics=True,
+                        success_once=torch.zeros(n, dtype=torch.bool), fail_once=torch.zeros(n, dtype=torch.bool), returns=torch.zeros(n))
+    ours = ms.ManiSkillVectorEnv(ours_env, auto_reset=True, record_metrics=True, max_episode_steps=limit)
+    torch.manual_seed(0)
+    o1, _ = ours.reset(seed=3)
+    torch.manual_seed(0)
+    o2, _ = ref.reset(seed=3)
+    assert torch.allclose(o1, o2, atol=1e-6)
+    g = torch.Generator().manual_seed(2)
+    finals = 0
+    for t in range(16):
+        a = 2 * torch.rand(n, 8, generator=g) - 1
+        torch.manual_seed(100 + t)                  # the unseeded auto-resets draw from the global stream
+        r1 = ours.step(a)
+        torch.manual_seed(100 + t)
+        r2 = ref.step(a)
+        for x, y in zip(r1[:4], r2[:4]):
+            assert x.dtype == y.dtype and torch.allclose(x.float(), y.float(), atol=1e-6), t
+        i1, i2 = r1[4], r2[4]
+        assert ("final_info" in i1) == ("final_info" in i2)
+        ep1 = i1["final_info"]["episode"] if "final_info" in i1 else i1["episode"]
+        ep2 = i2["final_info"]["episode"] if "final_info" in i2 else i2["episode"]
+        assert set(ep1) == set(ep2)
+        for k in ep1:
+            assert torch.allclose(ep1[k].float(), ep2[k].float(), atol=1e-6), (t, k)
+        if "final_info" in i1:
+            finals += 1
+            assert torch.allclose(i1["final_observation"], i2["final_observation"], atol=1e-6) and torch.equal(i1["_final_info"], i2["_final_info"])
+    assert finals == 2 and r1[3].sum() == 0 and int(ours_env.elapsed_steps[0]) == 2
