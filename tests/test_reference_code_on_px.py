@@ -33,7 +33,7 @@ def _load_reference_module(path, as_name=None):
     for node in ast.walk(ast.parse(open(path).read())):
         names = [node.module] if isinstance(node, ast.ImportFrom) and node.module else [a.name for a in node.names] if isinstance(node, ast.Import) else []
         for name in names:
-            if name.split(".")[0] in ("mani_skill", "sapien", "trimesh", "gymnasium", "transforms3d", "dacite", "lxml", "pytorch_kinematics", "matplotlib"):
+            if name.split(".")[0] in ("mani_skill", "sapien", "trimesh", "gymnasium", "transforms3d", "dacite", "lxml", "pytorch_kinematics", "matplotlib", "h5py", "imageio", "tqdm", "PIL"):
                 parts = name.split(".")
                 for i in range(1, len(parts) + 1):
                     ensure(".".join(parts[:i]))
@@ -532,3 +532,72 @@ def test_reference_vector_wrapper_and_timelimit_around_our_env(reference_module)
             finals += 1
             assert torch.allclose(i1["final_observation"], i2["final_observation"], atol=1e-6) and torch.equal(i1["_final_info"], i2["_final_info"])
     assert finals == 2 and r1[3].sum() == 0 and int(ours_env.elapsed_steps[0]) == 2
+
+
+def test_reference_record_episode_around_our_env(reference_module, tmp_path):
+    """The reference's `RecordEpisode.reset / step / flush_trajectory` (mani_skill/utils/wrappers/record.py:356-756, h5py replaced by a
+    dict-backed stand-in) recording OUR env -- observations, actions, rewards, flags and `get_state_dict()` of a real rollout with a partial
+    reset -- writes exactly the datasets the mirror's recorder writes for a twin env."""
+    from maniskill_b200.trajectory import RecordEpisode, _flatten, load_trajectories
+
+    class Group:
+        def __init__(self, store, path):
+            self.store, self.path = store, path
+        def create_group(self, name, track_order=True):
+            return Group(self.store, f"{self.path}/{name}" if self.path else name)
+        def create_dataset(self, key, data=None, dtype=None, **kw):
+            self.store[f"{self.path}/{key}"] = np.array(data, dtype=dtype)
+
+    class Wrapper:
+        def __init__(self, env):
+            self.env = env
+        def reset(self, *a, **k):
+            return self.env.reset(*a, **k)
+        def step(self, a):
+            return self.env.step(a)
+    gym = MagicMock(Wrapper=Wrapper, Env=type("Env", (), {}))
+    gym.__name__, gym.__path__, gym.__all__ = "gymnasium", [], []
+    sys.modules["gymnasium"] = gym
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    sys.modules["mani_skill.utils"] = MagicMock(common=common, sapien_utils=SimpleNamespace(is_state_dict_consistent=lambda sd: True))
+    sys.modules["mani_skill.utils.io_utils"] = MagicMock(dump_json=lambda *a, **k: None)
+    rec_mod = reference_module("/root/reference/mani_skill/utils/wrappers/record.py")
+    rec_mod.common, rec_mod.dump_json = common, (lambda *a, **k: None)
+    rec_mod.sapien_utils = SimpleNamespace(is_state_dict_consistent=lambda sd: True)
+    n = 3
+    ours_env, their_env = [ms.make("PushCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
+    for e in (ours_env, their_env):
+        e.max_episode_steps = None                   # the reference's recorder sees no TimeLimit here: compare the raw flags
+    their_env.unwrapped = their_env
+    their_env.get_wrapper_attr = lambda name: SimpleNamespace(sample=lambda: np.zeros(8, dtype=np.float32))
+    store = {}
+    ref = rec_mod.RecordEpisode.__new__(rec_mod.RecordEpisode)
+    ref.env = their_env
+    ref.__dict__.update(_h5_file=Group(store, ""), _json_data=dict(episodes=[]), _json_path="x.json", _trajectory_buffer=None, save_on_reset=True,
+                        save_trajectory=True, record_env_state=True, record_reward=True, _episode_id=-1, _elapsed_record_steps=0, _save_video=False,
+                        save_video_trigger=None, cpu_wrapped_env=False, _already_warned_about_state_dict_inconsistency=False, last_reset_kwargs={})
+    ours = RecordEpisode(ours_env, str(tmp_path))
+    g = torch.Generator().manual_seed(9)
+    for r in (ours, ref):
+        r.reset(seed=4)
+    for t in range(7):
+        a = 2 * torch.rand(n, 8, generator=g) - 1
+        for r in (ours, ref):
+            r.step(a)
+        if t == 3:
+            torch.manual_seed(1)
+            ours.reset(options=dict(env_idx=torch.tensor([2])))
+            torch.manual_seed(1)
+            ref.reset(options=dict(env_idx=torch.tensor([2])))
+    ours.flush_trajectory()
+    ours._dump()
+    ref.flush_trajectory()
+    meta, trajs = load_trajectories(str(tmp_path / "trajectory"))
+    flat = {}
+    for name, tr in trajs.items():
+        _flatten(name, tr, flat)
+    assert set(flat) == set(store) and len(store) == 4 * 10       # four episodes x (obs, actions, 3 flags, rewards, 4 state arrays)
+    for k in store:
+        assert flat[k].dtype == store[k].dtype and flat[k].shape == store[k].shape and np.allclose(flat[k], store[k], atol=1e-6), k
+    assert [e["elapsed_steps"] for e in meta["episodes"]] == [e["elapsed_steps"] for e in ref._json_data["episodes"]] == [4, 7, 7, 3]
+    assert [e["episode_seed"] for e in meta["episodes"]] == [int(e["episode_seed"]) for e in ref._json_data["episodes"]]
