@@ -601,3 +601,33 @@ def test_reference_record_episode_around_our_env(reference_module, tmp_path):
         assert flat[k].dtype == store[k].dtype and flat[k].shape == store[k].shape and np.allclose(flat[k], store[k], atol=1e-6), k
     assert [e["elapsed_steps"] for e in meta["episodes"]] == [e["elapsed_steps"] for e in ref._json_data["episodes"]] == [4, 7, 7, 3]
     assert [e["episode_seed"] for e in meta["episodes"]] == [int(e["episode_seed"]) for e in ref._json_data["episodes"]]
+
+
+def test_reference_flatten_wrappers_on_our_live_observations(reference_module):
+    """mani_skill/utils/wrappers/flatten.py: the reference's `FlattenRGBDObservationWrapper.observation` and `FlattenObservationWrapper.observation`
+    applied to observations produced by OUR env (two cameras, visual and state_dict modes) equal the mirror's wrappers."""
+    from maniskill_b200.wrappers import FlattenObservationWrapper, FlattenRGBDObservationWrapper
+
+    class ObsWrapper:
+        def __init__(self, env):
+            self.env = env
+    gym = MagicMock(ObservationWrapper=ObsWrapper, ActionWrapper=ObsWrapper, Env=type("Env", (), {}))
+    gym.__name__, gym.__path__, gym.__all__ = "gymnasium", [], []
+    sys.modules["gymnasium"] = gym
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    sys.modules["mani_skill.utils"] = MagicMock(common=common)
+    fl = reference_module("/root/reference/mani_skill/utils/wrappers/flatten.py")
+    fl.common = common
+    for mode in ("rgbd", "state+rgb+depth"):
+        env = ms.make("StackCube-v1", num_envs=2, obs_mode=mode, world_factory=EmuBackendWorld, sensor_configs=dict(base_camera=dict(width=16, height=16), hand_camera=dict(width=16, height=16)))
+        obs, _ = env.reset(seed=0)
+        for sep in (True, False):
+            ref_self = SimpleNamespace(base_env=SimpleNamespace(device=torch.device("cpu")), include_rgb=True, include_depth=True, sep_depth=sep, include_state=True)
+            want = fl.FlattenRGBDObservationWrapper.observation(ref_self, {k: (dict(v) if isinstance(v, dict) else v) for k, v in obs.items()})
+            got = FlattenRGBDObservationWrapper(env, sep_depth=sep).observation(obs)
+            assert set(got) == set(want)
+            for k in want:
+                assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), (mode, sep, k)
+    sd = ms.make("PickCube-v1", num_envs=2, obs_mode="state_dict", world_factory=EmuBackendWorld)
+    o, _ = sd.reset(seed=0)
+    assert torch.equal(FlattenObservationWrapper(sd).observation(o), fl.FlattenObservationWrapper.observation(SimpleNamespace(), o))
