@@ -125,6 +125,9 @@ class RenderMaterial:
     specular: float = 0.5
     metallic: float = 0.0
 
+    def set_base_color(self, color: Sequence[float]):
+        self.base_color = tuple(float(c) for c in color)
+
 
 @dataclass
 class CollisionRecord:

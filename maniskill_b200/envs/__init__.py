@@ -33,3 +33,6 @@ register_env("PlaceSphere-v1", max_episode_steps=50)(PlaceSphereEnv)
 from .stack_pyramid import StackPyramidEnv
 
 register_env("StackPyramid-v1", max_episode_steps=250)(StackPyramidEnv)
+from .pull_cube_tool import PullCubeToolEnv
+
+register_env("PullCubeTool-v1", max_episode_steps=100)(PullCubeToolEnv)

@@ -603,3 +603,33 @@ def test_stack_pyramid_layout_reward_modes_and_a_built_pyramid():
         o, r, te, tr, info = sp.step(torch.zeros(3, 8))
     assert info["success"].all() and torch.equal(r, torch.ones(3)) and te.all()
     assert (sp.cubeC.pose.p[:, 2] - 0.06).abs().max() < 2e-3
+
+
+def test_pull_cube_tool_layout_and_dragging_the_cube_with_the_tool():
+    """PullCubeTool-v1 (pull_cube_tool.py): tool within reach (x, y in [-0.3, -0.1]), cube beyond it, 39-dim state observation; the hook of
+    the L-shaped tool (two boxes in one body, handle at half density) drags the cube along when the tool is pulled towards the robot."""
+    from maniskill_b200.structs import Pose
+    env = ms.make("PullCubeTool-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=1)
+    assert obs.shape == (2, 9 + 9 + 7 + 7 + 7)
+    tool, cube = env.l_shape_tool.pose.p, env.cube.pose.p
+    assert (tool[:, :2] <= -0.1 + 1e-6).all() and (tool[:, :2] >= -0.3 - 1e-6).all() and torch.allclose(tool[:, 2], torch.full((2,), 0.025))
+    assert (cube[:, 0] >= 0.05 - 1e-6).all() and (cube[:, 0] <= 0.25 + 1e-6).all()
+    o, r, te, tr, info = env.step(torch.zeros(2, 8))
+    assert info["success"].shape == (2,) and info["cube_progress"].dim() == 0 and torch.isfinite(r).all()
+    # hook the cube: tool placed so that its hook (at x = 0.15..0.2, y = 0..0.1 in the tool frame) sits just beyond the cube, then drag it back
+    start = env.cube.pose.p.clone()
+    tp = torch.zeros(2, 7)
+    tp[:, 3] = 1.0
+    tp[:, 0] = start[:, 0] - 0.15 + 0.03
+    tp[:, 1] = start[:, 1] - 0.05
+    tp[:, 2] = 0.025
+    env.l_shape_tool.set_pose(Pose(tp))
+    env.scene._gpu_apply_all()
+    for _ in range(30):
+        tp[:, 0] -= 0.004
+        env.l_shape_tool.set_pose(Pose(tp.clone()))
+        env.l_shape_tool.set_linear_velocity(torch.tensor([-0.08, 0.0, 0.0]))
+        env.scene._gpu_apply_all()
+        env.step(torch.zeros(2, 8))
+    assert (env.cube.pose.p[:, 0] < start[:, 0] - 0.05).all()       # the cube came along

@@ -249,6 +249,7 @@ TASK_FILES = {
     "PokeCube-v1": ("poke_cube.py", "PokeCubeEnv"), "RollBall-v1": ("roll_ball.py", "RollBallEnv"), "PlaceSphere-v1": ("place_sphere.py", "PlaceSphereEnv"),
     "StackPyramid-v1": ("stack_pyramid.py", "StackPyramidEnv"), "PegInsertionSide-v1": ("peg_insertion_side.py", "PegInsertionSideEnv"),
     "OpenCabinetDrawer-v1": ("../mobile_manipulation/open_cabinet_drawer.py", "OpenCabinetDrawerEnv"),
+    "PullCubeTool-v1": ("pull_cube_tool.py", "PullCubeToolEnv"),
 }
 
 
@@ -299,7 +300,7 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
                 assert torch.equal(env.reached_status, status1)
 
 
-INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1"]
+INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1", "PullCubeTool-v1"]
 
 
 @pytest.mark.parametrize("task", INIT_TASKS)
@@ -340,7 +341,7 @@ def test_reference_episode_initialisation_on_our_env(reference_module, task):
     ours, theirs = [ms.make(task, num_envs=4, obs_mode="state", world_factory=EmuBackendWorld, **kw) for _ in range(2)]
     builder = table_mod.TableSceneBuilder.__new__(table_mod.TableSceneBuilder)
     builder.env, builder.table, builder.robot_init_qpos_noise = theirs, theirs.table, getattr(theirs, "robot_init_qpos_noise", 0.02)
-    theirs.table_scene = builder
+    theirs.table_scene = theirs.scene_builder = builder      # (PullCubeTool-v1 calls it scene_builder)
     theirs._initialize_episode = lambda env_idx, options: Ref._initialize_episode(theirs, env_idx, options)
     for seed, idx in ((11, None), (12, torch.tensor([1, 3]))):
         opts = dict() if idx is None else dict(env_idx=idx)
