@@ -334,6 +334,7 @@ class Panda:
     def __init__(self, scene, name="panda"):
         self.scene = scene
         self.device = scene.device
+        self.uid = name                       # "panda" | "panda_wristcam" (panda_wristcam.py:12-16 only changes uid, urdf and the camera)
         self.robot: Articulation = scene.articulations[name]
         lm = self.robot.links_map
         self.finger1_link = lm["panda_leftfinger"]

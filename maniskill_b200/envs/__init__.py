@@ -36,3 +36,6 @@ register_env("StackPyramid-v1", max_episode_steps=250)(StackPyramidEnv)
 from .pull_cube_tool import PullCubeToolEnv
 
 register_env("PullCubeTool-v1", max_episode_steps=100)(PullCubeToolEnv)
+from .plug_charger import PlugChargerEnv
+
+register_env("PlugCharger-v1", max_episode_steps=200)(PlugChargerEnv)

@@ -554,8 +554,8 @@ class BaseEnv:
             c.update((overrides or {}).get(c["uid"], {}))
             row = -1
             if c.get("mount") is not None:
-                art, link = c["mount"]
-                row = self.cm.link_rows[art][link]
+                owner, name = c["mount"]          # (articulation, link) or ("actor", actor name)
+                row = self.cm.actor_rows[name] if owner == "actor" else self.cm.link_rows[owner][name]
             cams.append(camera_desc(c["uid"], c["pose"], c["width"], c["height"], c["fov"], c["near"], c["far"], row))
         return CameraSensors(self.scene.world, self.cm, cams, include_hidden=include_hidden)
 

@@ -633,3 +633,23 @@ def test_pull_cube_tool_layout_and_dragging_the_cube_with_the_tool():
         env.scene._gpu_apply_all()
         env.step(torch.zeros(2, 8))
     assert (env.cube.pose.p[:, 0] < start[:, 0] - 0.05).all()       # the cube came along
+
+
+def test_plug_charger_layout_and_a_plugged_in_charger():
+    """PlugCharger-v1 (plug_charger.py): 46-dim state observation, receptacle facing the robot 10 cm above the table, sparse reward modes only;
+    a charger set into the receptacle (pins in the 0.5 mm-clearance slots) stays put under gravity and counts as success."""
+    env = ms.make("PlugCharger-v1", num_envs=2, obs_mode="state", reward_mode="sparse", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=2)
+    assert obs.shape == (2, 9 + 9 + 7 + 21) and env.agent.uid == "panda_wristcam"
+    assert torch.allclose(env.receptacle.pose.p[:, 2], torch.full((2,), 0.1)) and (env.charger.pose.p[:, 0] < 0).all()
+    o, r, te, tr, info = env.step(torch.zeros(2, 8))
+    assert not info["success"].any() and (info["obj_to_goal_dist"] > 0.05).all() and torch.equal(r, torch.zeros(2))
+    env.charger.set_pose(env.goal_pose)
+    env.scene._gpu_apply_all()
+    for _ in range(10):
+        o, r, te, tr, info = env.step(torch.zeros(2, 8))
+    assert info["success"].all() and torch.equal(r, torch.ones(2)), (info["obj_to_goal_dist"], info["obj_to_goal_angle"])
+    assert (info["obj_to_goal_dist"] < 4e-3).all()        # held by the slots: the cantilevered base sags within the clearance
+    img = ms.make("PlugCharger-v1", num_envs=1, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld)
+    img.reset(seed=0)
+    assert img.render().shape == (1, 512, 512, 3)         # the human camera is mounted on the receptacle actor

@@ -249,7 +249,7 @@ TASK_FILES = {
     "PokeCube-v1": ("poke_cube.py", "PokeCubeEnv"), "RollBall-v1": ("roll_ball.py", "RollBallEnv"), "PlaceSphere-v1": ("place_sphere.py", "PlaceSphereEnv"),
     "StackPyramid-v1": ("stack_pyramid.py", "StackPyramidEnv"), "PegInsertionSide-v1": ("peg_insertion_side.py", "PegInsertionSideEnv"),
     "OpenCabinetDrawer-v1": ("../mobile_manipulation/open_cabinet_drawer.py", "OpenCabinetDrawerEnv"),
-    "PullCubeTool-v1": ("pull_cube_tool.py", "PullCubeToolEnv"),
+    "PullCubeTool-v1": ("pull_cube_tool.py", "PullCubeToolEnv"), "PlugCharger-v1": ("plug_charger.py", "PlugChargerEnv"),
 }
 
 
@@ -271,7 +271,7 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
         sys.modules[name] = m
     mod = reference_module(f"/root/reference/mani_skill/envs/tasks/tabletop/{fname}")
     Ref = getattr(mod, cls_name)
-    kw = dict(reward_mode="sparse") if task == "StackPyramid-v1" else {}
+    kw = dict(reward_mode="sparse") if task in ("StackPyramid-v1", "PlugCharger-v1") else {}
     env = ms.make(task, num_envs=3, obs_mode="state", world_factory=EmuBackendWorld, **kw)
     env.reset(seed=3)
     g = torch.Generator().manual_seed(0)
@@ -300,7 +300,7 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
                 assert torch.equal(env.reached_status, status1)
 
 
-INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1", "PullCubeTool-v1"]
+INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1", "PullCubeTool-v1", "PlugCharger-v1"]
 
 
 @pytest.mark.parametrize("task", INIT_TASKS)
@@ -337,7 +337,7 @@ def test_reference_episode_initialisation_on_our_env(reference_module, task):
     mod = reference_module(f"/root/reference/mani_skill/envs/tasks/tabletop/{fname}")
     mod.randomization = rnd
     Ref = getattr(mod, cls_name)
-    kw = dict(reward_mode="sparse") if task == "StackPyramid-v1" else {}
+    kw = dict(reward_mode="sparse") if task in ("StackPyramid-v1", "PlugCharger-v1") else {}
     ours, theirs = [ms.make(task, num_envs=4, obs_mode="state", world_factory=EmuBackendWorld, **kw) for _ in range(2)]
     builder = table_mod.TableSceneBuilder.__new__(table_mod.TableSceneBuilder)
     builder.env, builder.table, builder.robot_init_qpos_noise = theirs, theirs.table, getattr(theirs, "robot_init_qpos_noise", 0.02)
@@ -348,7 +348,7 @@ def test_reference_episode_initialisation_on_our_env(reference_module, task):
         o1, _ = ours.reset(seed=seed, options=dict(opts))
         o2, _ = theirs.reset(seed=seed, options=dict(opts))
         s1, s2 = ours.get_state(), theirs.get_state()
-        assert torch.allclose(s1, s2, atol=1e-6), (task, seed, float((s1 - s2).abs().max()))
+        assert torch.allclose(s1, s2, atol=1e-6), (task, seed, float((s1 - s2).abs().max()), (s1 - s2).abs().max(dim=0).values.nonzero().flatten().tolist())
         assert torch.allclose(o1, o2, atol=1e-5)
 
 

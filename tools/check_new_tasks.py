@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0, "/root/repo")
 import torch, maniskill_b200 as ms
 for task, cm in [("PushCube-v1", "pd_ee_target_delta_pos"), ("StackCube-v1", None), ("PullCube-v1", None),
-                 ("LiftPegUpright-v1", None), ("PokeCube-v1", None), ("RollBall-v1", None), ("PlaceSphere-v1", None), ("StackPyramid-v1", None), ("PullCubeTool-v1", None)]:
+                 ("LiftPegUpright-v1", None), ("PokeCube-v1", None), ("RollBall-v1", None), ("PlaceSphere-v1", None), ("StackPyramid-v1", None), ("PullCubeTool-v1", None), ("PlugCharger-v1", None)]:
     env = ms.ManiSkillVectorEnv(ms.make(task, num_envs=1024, obs_mode="state", control_mode=cm), auto_reset=True)
     obs, _ = env.reset(seed=0)
     A = env.base_env.action_dim
