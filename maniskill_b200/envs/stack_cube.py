@@ -10,29 +10,20 @@ import numpy as np
 import torch
 
 from .. import utils as U
-from ..agents import Panda
 from ..model import SHAPE_BOX, ActorRec, ShapeRec, pose7
-from ..scenes import SQRT_HALF, TABLE_HEIGHT, add_table_scene, panda_articulation
+from ..scenes import add_table_scene
 from ..structs import Pose
-from .base_env import BaseEnv
+from .tabletop import PandaTabletopEnv
 
 
-class StackCubeEnv(BaseEnv):
+class StackCubeEnv(PandaTabletopEnv):
     max_episode_steps = 50  # @register_env("StackCube-v1", max_episode_steps=50)
 
-    def __init__(self, *args, robot_uids="panda_wristcam", robot_init_qpos_noise=0.02, **kwargs):
-        if robot_uids != "panda_wristcam":
-            raise NotImplementedError("StackCube-v1 on b200sim ships the default 'panda_wristcam' robot")
-        self.robot_uids = robot_uids
-        self.robot_init_qpos_noise = robot_init_qpos_noise
+    default_robot_uids = "panda_wristcam"   # stack_cube.py:36-41; "panda" is accepted too (SUPPORTED_ROBOTS)
+
+    def __init__(self, *args, **kwargs):
         kwargs.setdefault("fused", False)
         super().__init__(*args, **kwargs)
-
-    def _load_agent_desc(self):
-        art = panda_articulation("panda_wristcam", "panda_v3", (-0.615, 0, 0))
-        for j in Panda.arm_joint_names:      # the drive gains follow the control mode the env is made with
-            art.drive[j] = Panda.drive_gains(self._control_mode_arg)
-        self.scene_desc.add_articulation(art)
 
     # ---- stack_cube.py:57-77
     def _load_scene_desc(self):
@@ -42,7 +33,7 @@ class StackCubeEnv(BaseEnv):
         self.scene_desc.add_actor(ActorRec("cubeB", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), h, color=(0, 1, 0, 1))], pose7([1, 0, 0.1])))
 
     def _after_build(self):
-        self.agent = Panda(self.scene, "panda_wristcam")
+        self.agent = self._make_agent()
         self.table = self.scene.actors["table-workspace"]
         self.cubeA = self.scene.actors["cubeA"]
         self.cubeB = self.scene.actors["cubeB"]
@@ -51,7 +42,7 @@ class StackCubeEnv(BaseEnv):
     # ---- stack_cube.py:45-48 and agents/robots/panda/panda_wristcam.py:19-32
     def _sensor_configs(self):
         return [dict(uid="base_camera", pose=U.look_at([0.3, 0, 0.6], [-0.1, 0, 0.1]), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=None),
-                dict(uid="hand_camera", pose=pose7(), width=128, height=128, fov=np.pi / 2, near=0.01, far=100.0, mount=("panda_wristcam", "camera_link"))]
+                ] + self._robot_sensor_configs()
 
     # ---- stack_cube.py:49-52
     def _human_render_camera_configs(self):
@@ -61,12 +52,7 @@ class StackCubeEnv(BaseEnv):
     def _initialize_episode(self, env_idx: torch.Tensor, options: dict):
         b = len(env_idx)
         dev = self.device
-        self.table.set_pose(Pose.create(pose7([-0.12, 0, -TABLE_HEIGHT], [SQRT_HALF, 0, 0, SQRT_HALF]), dev))
-        qpos = np.array([0.0, np.pi / 8, 0, -np.pi * 5 / 8, 0, np.pi * 3 / 4, -np.pi / 4, 0.04, 0.04])
-        q = self._episode_rng.normal(0, self.robot_init_qpos_noise, (b, 9)) + qpos
-        q[:, -2:] = 0.04
-        self.agent.reset(torch.tensor(q, dtype=torch.float32, device=dev))
-        self.agent.robot.set_pose(Pose.create(pose7([-0.615, 0, 0]), dev))
+        self._initialize_table_scene(env_idx)
         xyz = torch.zeros((b, 3), device=dev)
         xyz[:, 2] = 0.02
         xy = torch.rand((b, 2), device=dev) * 0.2 - 0.1

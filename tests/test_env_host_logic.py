@@ -653,3 +653,11 @@ def test_plug_charger_layout_and_a_plugged_in_charger():
     img = ms.make("PlugCharger-v1", num_envs=1, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld)
     img.reset(seed=0)
     assert img.render().shape == (1, 512, 512, 3)         # the human camera is mounted on the receptacle actor
+
+
+def test_stack_cube_accepts_the_plain_panda():
+    """stack_cube.py:36: SUPPORTED_ROBOTS = ["panda_wristcam", "panda", "fetch"] -- the plain Panda loads without the hand camera."""
+    env = ms.make("StackCube-v1", num_envs=2, obs_mode="rgbd", robot_uids="panda", world_factory=EmuBackendWorld)
+    obs, _ = env.reset(seed=0)
+    assert set(obs["sensor_data"]) == {"base_camera"} and env.agent.uid == "panda" and "camera_link" not in env.agent.robot.links_map
+    assert (env.agent.robot.get_qpos()[:, 6] - np.pi / 4).abs().max() < 0.1
