@@ -632,3 +632,32 @@ def test_reference_flatten_wrappers_on_our_live_observations(reference_module):
     sd = ms.make("PickCube-v1", num_envs=2, obs_mode="state_dict", world_factory=EmuBackendWorld)
     o, _ = sd.reset(seed=0)
     assert torch.equal(FlattenObservationWrapper(sd).observation(o), fl.FlattenObservationWrapper.observation(SimpleNamespace(), o))
+
+
+def test_reference_fetch_checks_on_our_agent(reference_module):
+    """mani_skill/agents/robots/fetch/fetch.py `is_static` / `is_grasping` with `self` = our Fetch while it drives around and moves its arm
+    (OpenCabinetDrawer-v1): same verdicts as the mirror, including the base-velocity threshold."""
+    from maniskill_b200 import sapien_shim
+    sapien_shim.install(force=True)
+    for name, attrs in (("mani_skill.agents.base_agent", dict(BaseAgent=object, Keyframe=lambda **k: None, DictControllerConfig=dict)),
+                        ("mani_skill.agents.registration", dict(register_agent=lambda *a, **k: (lambda cls: cls)))):
+        m = MagicMock(name=name, **attrs)
+        m.__name__, m.__path__, m.__all__ = name, [], []
+        sys.modules[name] = m
+    common = reference_module("/root/reference/mani_skill/utils/common.py", as_name="mani_skill.utils.common")
+    sys.modules["mani_skill.utils"] = MagicMock(common=common)
+    fetch_mod = reference_module("/root/reference/mani_skill/agents/robots/fetch/fetch.py")
+    fetch_mod.common = common
+    RefFetch = fetch_mod.Fetch
+    env = ms.make("OpenCabinetDrawer-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
+    env.reset(seed=0)
+    g = torch.Generator().manual_seed(0)
+    verdicts = []
+    for t in range(10):
+        a = torch.zeros(2, env.action_dim) if t < 3 else 2 * torch.rand(2, env.action_dim, generator=g) - 1
+        env.step(a)
+        ours_s, ref_s = env.agent.is_static(0.2), RefFetch.is_static(env.agent, 0.2)
+        assert torch.equal(ours_s, ref_s), t
+        assert torch.equal(env.agent.is_grasping(env.handle_link), RefFetch.is_grasping(env.agent, env.handle_link))
+        verdicts.append(bool(ref_s.all()))
+    assert verdicts[1] and not all(verdicts)           # at rest first, moving later
