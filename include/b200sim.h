@@ -107,7 +107,7 @@ typedef struct B2SModel {
   const float* dof_inertia;    /* [n_dof*6] xx yy zz xy xz yz about com, abody axes */
   const float* dof_gravity;    /* [n_dof] 1 = gravity acts, 0 = disabled (agents/base_agent.py:278-282) */
   const float* dof_limit;      /* [n_dof*2] lower, upper (+-1e30 = none) */
-  const float* dof_drive;      /* [n_dof*4] stiffness, damping, force_limit, reserved */
+  const float* dof_drive;      /* [n_dof*4] stiffness, damping, force_limit, max joint velocity (0 = unlimited; PhysX default 100) */
   const float* dof_passive;    /* [n_dof*4] joint damping, joint friction, armature, reserved */
   const uint32_t* dof_anc_mask;/* [n_dof] bit j set iff abody j is an ancestor-or-self */
   /* ---- links, [n_link] ---- */
@@ -168,8 +168,16 @@ typedef struct B2SBufferTable {
   int32_t n_rows;          /* rigid rows per env = n_link + n_fb */
   int32_t max_dof;
   int32_t* contact_count;  /* [n_envs] contacts generated in the last substep */
-  int32_t* overflow_flag;  /* [1] set if any env exceeded max_contacts */
+  int32_t* overflow_flag;  /* [1] sticky OR of B2S_OVF_* reasons: a fixed capacity dropped a contact or constraint row in some sub-scene */
 } B2SBufferTable;
+
+/* bits of *overflow_flag (PhysX reports exceeded GPUMemoryConfig capacities, mani_skill/utils/structs/types.py:16-32) */
+#define B2S_OVF_MANIFOLDS 1  /* more contact patches than max_manifolds (<= 24) in a sub-scene */
+#define B2S_OVF_CONTACTS 2   /* more contact points than max_contacts (<= 64) */
+#define B2S_OVF_ROWS 4       /* more constraint rows than the compiled row capacity */
+#define B2S_OVF_ART_ROWS 8   /* (unused since rows touching an articulation share the row capacity) */
+#define B2S_OVF_LIMITS 16    /* more simultaneously active joint limits than 24 */
+#define B2S_OVF_EQ 32        /* more tendon couplings than 2 */
 
 /* apply / fetch selection bits */
 #define B2S_BUF_RIGID (1u << 0)      /* free-body rows of rigid_body_data (pose + velocity) */

@@ -67,6 +67,20 @@ std::mutex g_mu;
 std::unordered_map<uint64_t, World*> g_worlds;
 uint64_t g_next = 1;
 
+// Every entry point runs on the world's own device whatever the caller's current device is (the reference's
+// `physx_cuda:n` backend, mani_skill/envs/utils/system/backend.py:46-68), and leaves the caller's device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 World* get(uint64_t h) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_worlds.find(h);
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
 // once, so the launch lasts as long as the slowest one: what counts is the dependent chain of a row visit.  Measured on B200
 // (PickCube-v1, ms per control step, 4096 / 16384 envs): 4 lanes 0.93 / 1.78, 8 lanes 0.93 / 1.82, 16 lanes 1.00 / 2.21; one lane
 // per sub-scene with instruction-level parallelism instead of shuffles 1.4 / 2.2.
-#define B2S_SOLVE_EPB 32  // sub-scenes per block
+#define B2S_SOLVE_EPB 16  // sub-scenes per block (2 warps of 8 groups with 4 lanes; the impulse table of a block is EPB x MAXROW x 8 B of shared memory)
 template <int NUQ, int L>
 __global__ void __launch_bounds__(B2S_SOLVE_EPB * L) solve_kernel(b2s::DevModel M, b2s::DevState S) {
   constexpr int MR = b2s::CapsS::MAXROW;
@@ -302,7 +316,7 @@ int32_t b2s_world_create(const B2SModel* model, int32_t device, uint64_t* world)
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(B2S_ERR_NO_DEVICE, "no CUDA device: b200sim has no CPU path");
   if (device < 0 || device >= count) return fail(B2S_ERR_INVALID, "bad device index");
-  CK(cudaSetDevice(device));
+  DeviceGuard guard_(device);
   World* w = new World();
   w->device = device;
   const char* err = w->build(*model);
@@ -338,7 +352,7 @@ int32_t b2s_world_destroy(uint64_t world) {
     w = it->second;
     g_worlds.erase(it);
   }
-  cudaSetDevice(w->device);
+  DeviceGuard guard_(w->device);
   cudaDeviceSynchronize();
   for (auto& kv : w->graphs) cudaGraphExecDestroy(kv.second);
   if (w->cap) cudaStreamDestroy(w->cap);
@@ -355,6 +369,7 @@ int32_t b2s_world_destroy(uint64_t world) {
 int32_t b2s_world_buffers(uint64_t world, B2SBufferTable* out) {
   World* w = get(world);
   if (!w || !out) return fail(B2S_ERR_INVALID, "unknown world");
+  DeviceGuard guard_(w->device);
   out->rigid_body_data = w->S.body_data;
   out->qpos = w->S.xq; out->qvel = w->S.xqd; out->qacc = w->S.xqacc; out->qf = w->S.xqf;
   out->target_qpos = w->S.xtq; out->target_qvel = w->S.xtqd;
@@ -439,6 +454,7 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
 int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* stream) {
   World* w = get(world);
   if (!w) return fail(B2S_ERR_INVALID, "unknown world");
+  DeviceGuard guard_(w->device);
   if (substeps < 1) return fail(B2S_ERR_INVALID, "substeps < 1");
   cudaStream_t st = (cudaStream_t)stream;
   static int graph_on = getenv("B2S_GRAPH") ? atoi(getenv("B2S_GRAPH")) : 1;
@@ -466,6 +482,7 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
 int32_t b2s_apply(uint64_t world, uint32_t mask, void* stream) {
   World* w = get(world);
   if (!w) return fail(B2S_ERR_INVALID, "unknown world");
+  DeviceGuard guard_(w->device);
   int N = w->M.n_envs;
   apply_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->M, w->S, mask);
   CK(cudaGetLastError());
@@ -475,6 +492,7 @@ int32_t b2s_apply(uint64_t world, uint32_t mask, void* stream) {
 int32_t b2s_fetch(uint64_t world, uint32_t mask, void* stream) {
   World* w = get(world);
   if (!w) return fail(B2S_ERR_INVALID, "unknown world");
+  DeviceGuard guard_(w->device);
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
   if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, mask);
@@ -491,6 +509,7 @@ int32_t b2s_update_kinematics(uint64_t world, void* stream) {
 int32_t b2s_contact_query_create(uint64_t world, const int32_t* rows, int32_t n_query, uint64_t* query) {
   World* w = get(world);
   if (!w || !rows || !query || n_query < 1) return fail(B2S_ERR_INVALID, "bad contact query");
+  DeviceGuard guard_(w->device);
   Query q;
   q.n = n_query;
   CK(cudaMalloc(&q.rows_dev, sizeof(int) * 2 * n_query));
@@ -503,6 +522,7 @@ int32_t b2s_contact_query_create(uint64_t world, const int32_t* rows, int32_t n_
 int32_t b2s_contact_query_run(uint64_t world, uint64_t query, float* out_dev, void* stream) {
   World* w = get(world);
   if (!w || query < 1 || query > w->queries.size() || !out_dev) return fail(B2S_ERR_INVALID, "bad contact query");
+  DeviceGuard guard_(w->device);
   const Query& q = w->queries[query - 1];
   int N = w->M.n_envs;
   query_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w->M, w->S, q.rows_dev, q.n, out_dev);
@@ -514,6 +534,7 @@ int32_t b2s_camera_group_create(uint64_t world, const B2SCameraDesc* cams, int32
                                 uint64_t* group, B2SRenderTargets* out) {
   World* w = get(world);
   if (!w || !cams || !vis || !group || !out || n_cam < 1) return fail(B2S_ERR_INVALID, "bad camera group");
+  DeviceGuard guard_(w->device);
   b2s::RasterGroup* g = nullptr;
   const char* err = b2s::raster_create(w->M, w->S, w->host, cams, n_cam, vis, &g, out);
   if (err) return fail(B2S_ERR_INVALID, "%s", err);
@@ -525,6 +546,7 @@ int32_t b2s_camera_group_create(uint64_t world, const B2SCameraDesc* cams, int32
 int32_t b2s_render(uint64_t world, uint64_t group, void* stream) {
   World* w = get(world);
   if (!w || group < 1 || group > w->groups.size()) return fail(B2S_ERR_INVALID, "bad camera group");
+  DeviceGuard guard_(w->device);
   const char* err = b2s::raster_run(w->M, w->S, w->groups[group - 1], (cudaStream_t)stream);
   if (err) return fail(B2S_ERR_CUDA, "%s", err);
   return B2S_OK;
@@ -533,6 +555,7 @@ int32_t b2s_render(uint64_t world, uint64_t group, void* stream) {
 int32_t b2s_pick_task_create(uint64_t world, const B2SJointController* c, const B2SPickTask* task, uint64_t* handle) {
   World* w = get(world);
   if (!w || !c || !task || !handle) return fail(B2S_ERR_INVALID, "bad pick task");
+  DeviceGuard guard_(w->device);
   int nd = w->M.n_dof, nr = w->M.n_rows;
   const int rows[5] = {task->tcp_row, task->obj_row, task->goal_row, task->lfinger_row, task->rfinger_row};
   for (int r : rows)
@@ -555,6 +578,7 @@ int32_t b2s_pick_task_step(uint64_t world, uint64_t handle, const float* actions
   World* w = get(world);
   if (!w || handle < 1 || handle > w->pick_tasks.size() || !out || !out->obs || !out->reward || !out->flags || !out->elapsed)
     return fail(B2S_ERR_INVALID, "bad pick task step");
+  DeviceGuard guard_(w->device);
   const PickTaskDev& T = w->pick_tasks[handle - 1];
   cudaStream_t st = (cudaStream_t)stream;
   int N = w->M.n_envs;

@@ -52,7 +52,7 @@ B2S_HD void emit_joint_rows(const DevModel& M, const DevState& St, int env, cons
   const v3 zero3 = mk3(0, 0, 0);
   int n_row = 0, ovf = 0;
   for (int e = 0; e < M.n_eq && e < C::MAXEQ; e++) {
-    if (n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; break; }
+    if (n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf |= OVF_EQ; break; }
     const int ri = n_row++;
     const int a = M.eq_dof[2 * e], b = M.eq_dof[2 * e + 1];
     const float mult = M.eq_param[4 * e], off = M.eq_param[4 * e + 1], kk = M.eq_param[4 * e + 2];
@@ -68,14 +68,14 @@ B2S_HD void emit_joint_rows(const DevModel& M, const DevState& St, int env, cons
     for (int side = 0; side < 2; side++) {
       const bool act = side == 0 ? (lo > -1e29f && qi - lo < limit_margin) : (hi < 1e29f && hi - qi < limit_margin);
       if (!act) continue;
-      if (n_lim >= C::MAXLIM || n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf = 1; continue; }
+      if (n_lim >= C::MAXLIM || n_row >= C::MAXAR || n_row >= C::MAXROW) { ovf |= n_lim >= C::MAXLIM ? OVF_LIMITS : OVF_ROWS; continue; }
       n_lim++;
       const int ri = n_row++;
       emit_desc(RD, ri, ROW_LIMIT, 0, 0, -1, 0, 0, zero3, zero3, side == 0 ? qi - lo : hi - qi, 0.f, 0.f, i, side == 0 ? 1.f : -1.f, -1, 0.f);
     }
   }
   St.sol_nrow[env] = n_row;  // manifest continues from here
-  if (ovf) *St.overflow = 1;
+  if (ovf) raise_overflow(St.overflow, ovf);
   (void)N;
 }
 
@@ -475,7 +475,7 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
       man_patch[merge] = fmaxf(man_patch[merge], fmaxf(M.shape_patch[a], M.shape_patch[b]));
       continue;
     }
-    if (n_man >= max_man || n_points + n > max_cp) { ovf = 1; continue; }
+    if (n_man >= max_man || n_points + n > max_cp) { ovf |= n_man >= max_man ? OVF_MANIFOLDS : OVF_CONTACTS; continue; }
     man_sa[n_man] = a; man_sb[n_man] = b; man_np[n_man] = n; man_n[n_man] = nrm;
     for (int i = 0; i < n; i++) { man_p[n_man][i] = op[i]; man_s[n_man][i] = os[i]; }
     man_mu[n_man] = 0.5f * (M.shape_mu[a] + M.shape_mu[b]);
@@ -511,7 +511,7 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
       else if (kind == OWNER_BODY) sides |= (ow + 1) << (16 * sde + 8);
     }
     int nrows_needed = np + 2 + (rad > 0.f ? 1 : 0);
-    if (n_row + nrows_needed > C::MAXROW || (any_art && n_ar + nrows_needed > C::MAXAR)) { ovf = 1; continue; }
+    if (n_row + nrows_needed > C::MAXROW || (any_art && n_ar + nrows_needed > C::MAXAR)) { ovf |= n_row + nrows_needed > C::MAXROW ? OVF_ROWS : OVF_ART_ROWS; continue; }
     const int mo = n_out++;
     B2S_NO_UNROLL
     for (int k = 0; k < nrows_needed; k++) {
@@ -535,7 +535,7 @@ B2S_HDN void manifest_env(const DevModel& M, const DevState& St, int env) {
   }
   St.sol_nrow[env] = n_row;
   St.man_count[env] = n_out;
-  if (ovf) *St.overflow = 1;
+  if (ovf) raise_overflow(St.overflow, ovf);
 }
 
 // ------------------------------------------------------------------------------------------------ rowfill

@@ -90,15 +90,17 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
   const float inv_h = 1.f / h, max_depen = M.max_depen_vel;
   const int n_row = valid ? St.sol_nrow[env] : 0;
   const float* rows = St.sol_rows + (size_t)(valid ? env : 0) * MAXROW * RF;
-  float u[SL], du[SL], uf[SL], ac[SL], af[SL], dm[SL];
+  float u[SL], du[SL], uf[SL], ac[SL], af[SL], dm[SL], umax[SL];
 #pragma unroll
   for (int k = 0; k < SL; k++) {
     const int s = k * L + lane;
-    u[k] = 0.f; du[k] = 0.f; ac[k] = 0.f; af[k] = 0.f; dm[k] = 1.f; uf[k] = 0.f;
+    u[k] = 0.f; du[k] = 0.f; ac[k] = 0.f; af[k] = 0.f; dm[k] = 1.f; uf[k] = 0.f; umax[k] = 3.0e38f;
     if (!valid) continue;
     if (s < nd) {
       u[k] = St.qd[s * N + env];
       af[k] = h * St.sol_qdd[s * N + env];
+      const float vmax = M.dof_drive[4 * s + 3];  // PhysX maxJointVelocity (0 = no clamp)
+      if (vmax > 0.f) umax[k] = vmax;
     } else if (s < M.n_u) {
       // slot -> (dynamic body, component)
       int b = 0;
@@ -202,6 +204,8 @@ B2S_HDN void solve_env(const DevModel& M, const DevState& St, int env, int lane,
     }
 #undef B2S_FETCH_ROW
 #undef B2S_VISIT_ROW
+#pragma unroll
+    for (int k = 0; k < SL; k++) u[k] = fmaxf(-umax[k], fminf(umax[k], u[k]));  // joint velocity clamp after every sweep
     if (!relax) {
 #pragma unroll
       for (int k = 0; k < SL; k++) {

@@ -76,6 +76,17 @@ struct DevState {
 };
 
 enum { OWNER_STATIC = 0, OWNER_LINK = 1, OWNER_BODY = 2 };
+// Reasons recorded in the sticky overflow word (include/b200sim.h B2S_OVF_*): which fixed capacity dropped a contact / row.  The
+// reference's PhysX reports its buffer-capacity overflows the same way: loudly, with the knob to raise
+// (mani_skill/utils/structs/types.py:16-32, GPUMemoryConfig).
+enum { OVF_MANIFOLDS = 1, OVF_CONTACTS = 2, OVF_ROWS = 4, OVF_ART_ROWS = 8, OVF_LIMITS = 16, OVF_EQ = 32 };
+B2S_HD void raise_overflow(int* word, int code) {
+#if defined(__CUDA_ARCH__)
+  if ((*(volatile int*)word & code) != code) atomicOr(word, code);
+#else
+  *word |= code;
+#endif
+}
 enum { ROW_CONTACT_N = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_EQ = 3, ROW_PATCH_START = 0x10 /* flag: first normal row of a patch */ };
 enum {
   BUF_RIGID = 1u << 0, BUF_ROOT_POSE = 1u << 1, BUF_QPOS = 1u << 2, BUF_QVEL = 1u << 3, BUF_QF = 1u << 4,
@@ -85,9 +96,9 @@ enum {
 template <int MAXD_, int MAXFB_, int MAXSH_, int MAXART_>
 struct Caps {
   static constexpr int MAXD = MAXD_, MAXFB = MAXFB_, MAXSH = MAXSH_, MAXART = MAXART_;
-  static constexpr int MAXMAN = 12, MAXCP = 32, MAXLIM = 8, MAXEQ = 2;
+  static constexpr int MAXMAN = 24, MAXCP = 64, MAXLIM = 24, MAXEQ = 2;  // MAXLIM: one active limit per joint
   static constexpr int MAXROW = MAXEQ + MAXLIM + MAXCP + 3 * MAXMAN;
-  static constexpr int MAXAR = 48;  // rows that touch an articulation
+  static constexpr int MAXAR = MAXROW;  // rows that touch an articulation (no separate limit)
 };
 
 template <class C>
@@ -358,7 +369,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       man_patch[merge] = fmaxf(man_patch[merge], fmaxf(M.shape_patch[a], M.shape_patch[b]));
       continue;
     }
-    if (n_man >= max_man || n_points + n > max_cp) { *overflow = 1; continue; }
+    if (n_man >= max_man || n_points + n > max_cp) { *overflow |= n_man >= max_man ? OVF_MANIFOLDS : OVF_CONTACTS; continue; }
     man_sa[n_man] = a; man_sb[n_man] = b; man_np[n_man] = n; man_n[n_man] = out[0].n;
     for (int i = 0; i < n; i++) { man_p[n_man][i] = out[i].p; man_s[n_man][i] = out[i].sep - M.rest_offset; }
     man_mu[n_man] = 0.5f * (M.shape_mu[a] + M.shape_mu[b]);
@@ -526,7 +537,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
   }
 
   for (int e = 0; e < M.n_eq && e < C::MAXEQ; e++) {
-    if (n_ar >= C::MAXAR || n_row >= C::MAXROW) { *overflow = 1; break; }
+    if (n_ar >= C::MAXAR || n_row >= C::MAXROW) { *overflow |= OVF_EQ; break; }
     int ri = n_row++;
     B2S_BLANK_ROW(ri, ROW_EQ);
     int a = M.eq_dof[2 * e], b = M.eq_dof[2 * e + 1];
@@ -549,7 +560,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     for (int side = 0; side < 2; side++) {
       bool act = side == 0 ? (lo > -1e29f && L.q[i] - lo < limit_margin) : (hi < 1e29f && hi - L.q[i] < limit_margin);
       if (!act) continue;
-      if (n_lim >= C::MAXLIM || n_ar >= C::MAXAR || n_row >= C::MAXROW) { *overflow = 1; continue; }
+      if (n_lim >= C::MAXLIM || n_ar >= C::MAXAR || n_row >= C::MAXROW) { *overflow |= n_lim >= C::MAXLIM ? OVF_LIMITS : OVF_ROWS; continue; }
       n_lim++;
       int ri = n_row++;
       B2S_BLANK_ROW(ri, ROW_LIMIT);
@@ -581,7 +592,7 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
     for (int sde = 0; sde < 2; sde++)
       if (M.shape_owner_kind[sh[sde]] == OWNER_LINK && M.shape_owner[sh[sde]] >= 0) any_art = true;
     int nrows_needed = np + 2 + (rad > 0.f ? 1 : 0);
-    if (n_row + nrows_needed > C::MAXROW || (any_art && n_ar + nrows_needed > C::MAXAR)) { *overflow = 1; continue; }
+    if (n_row + nrows_needed > C::MAXROW || (any_art && n_ar + nrows_needed > C::MAXAR)) { *overflow |= n_row + nrows_needed > C::MAXROW ? OVF_ROWS : OVF_ART_ROWS; continue; }
     B2S_NO_UNROLL
     for (int k = 0; k < nrows_needed; k++) {
       int ri = n_row++;
@@ -749,6 +760,11 @@ B2S_HDN void substep(const DevModel& M, Lane<C>& L, int env, int* overflow) {
       r_lambda[ri] = nl;
       if (dl != 0.f) B2S_ROW_APPLY(ri, dl);
     }
+    // joint velocity clamp (PhysX maxJointVelocity, dof_drive[4 j + 3]; 0 = none) after every sweep
+    for (int j = 0; j < nd; j++) {
+      const float vmax = M.dof_drive[4 * j + 3];
+      if (vmax > 0.f) v[j] = fmaxf(-vmax, fminf(vmax, v[j]));
+    }
     for (int ri = 0; ri < n_row; ri++) r_total[ri] += r_lambda[ri];
     if (!relax) {
       for (int j = 0; j < nd; j++) ac[j] = v[j] - vfree[j];
@@ -913,7 +929,7 @@ B2S_HDN void step_env(const DevModel& M, const DevState& St, int env, int subste
   load_lane<C>(M, St, env, L);
   int ovf = 0;
   for (int s = 0; s < substeps; s++) substep<C, ND>(M, L, env, &ovf);
-  if (ovf) *St.overflow = 1;
+  if (ovf) raise_overflow(St.overflow, ovf);
   store_lane<C>(M, St, env, L);
   if (fetch_mask) {
     fk<C>(M, L);

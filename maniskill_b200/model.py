@@ -291,12 +291,13 @@ class SimParams:
     solver_position_iterations: int = 15
     solver_velocity_iterations: int = 1
     static_friction: float = 0.3
-    max_contacts: int = 32
-    max_manifolds: int = 12
+    max_contacts: int = 64
+    max_manifolds: int = 24
     max_depenetration_velocity: float = 3.0
     contact_hertz: float = 30.0
     contact_zeta: float = 10.0
     margin_min: float = 0.005
+    max_joint_velocity: float = 100.0   # PxArticulationJointReducedCoordinate maxJointVelocity default (rad/s | m/s); 0 = unlimited
 
 
 class CompiledModel:
@@ -405,7 +406,7 @@ class SceneDesc:
                             lo, hi = -1e30, 1e30
                         dof_limit.append([lo, hi])
                         kp, kd, fl = art.drive.get(J["name"], (0.0, 0.0, 1e10))
-                        dof_drive.append([kp, kd, fl, 0.0])
+                        dof_drive.append([kp, kd, fl, float(self.sim.max_joint_velocity)])
                         dof_passive.append([0.0, art.joint_friction.get(J["name"], 0.0), 0.0, 0.0])
                         names.append(J["name"])
                         jname_to_dof[J["name"]] = d

@@ -624,6 +624,14 @@ static void step_env(Oracle& O, Env& E) {
       if (dl != 0) apply(r, dl);
     }
   };
+  // PhysX clamps articulation joint velocities to PxArticulationJointReducedCoordinate::maxJointVelocity (default 100 rad/s | m/s,
+  // which sapien leaves untouched); here: after every sweep, dof_drive[4 j + 3] (0 = no clamp)
+  auto clamp_joint_velocity = [&]() {
+    for (int j = 0; j < nd; j++) {
+      const R vmax = O.dof_drive[4 * j + 3];
+      if (vmax > 0) v[j] = std::fmax(-vmax, std::fmin(vmax, v[j]));
+    }
+  };
   for (int it = 0; it < npos; it++) {
     for (int j = 0; j < nd; j++) v[j] += h * qdd[j];
     for (int b = 0; b < nfb; b++) {
@@ -638,6 +646,7 @@ static void step_env(Oracle& O, Env& E) {
       for (int b = 0; b < nfb; b++) { fv[b] = fv[b] + acv[b]; fw[b] = fw[b] + acw[b]; }
     }
     sweep(false);
+    clamp_joint_velocity();
     for (int j = 0; j < nd; j++) ac[j] = v[j] - vfree[j];
     for (int b = 0; b < nfb; b++) { acv[b] = fv[b] - fvfree[b]; acw[b] = fw[b] - fwfree[b]; }
     for (size_t ri = 0; ri < rows.size(); ri++) rows[ri].total += rows[ri].lambda;
@@ -650,6 +659,7 @@ static void step_env(Oracle& O, Env& E) {
   for (int it = 0; it < m.n_vel_iters; it++) {
     for (size_t ri = 0; ri < rows.size(); ri++) rows[ri].total -= rows[ri].lambda;
     sweep(true);
+    clamp_joint_velocity();
     for (size_t ri = 0; ri < rows.size(); ri++) rows[ri].total += rows[ri].lambda;
   }
   // ------------------------------------------------------------ 6. integrate + export

@@ -59,7 +59,7 @@ class EmuWorld:
 
         self.rigid_body_data = view(0, (N, self.n_rows, 13))
         self.qpos, self.qvel, self.qacc, self.qf, self.target_qpos, self.target_qvel = [view(i, (N * na, md)) for i in range(1, 7)]
-        self.man = view(7, (12 * 8, N))
+        self.man = view(7, (24 * 8, N))
         self.man_count = np.ctypeslib.as_array(lib().emu_man_count(self.h), shape=(N,))
         lib().emu_fetch(self.h, BUF_ALL)
 
