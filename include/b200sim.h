@@ -24,6 +24,8 @@
  *   b2s_render                camera_group.take_picture() (+ set_cuda_poses / update_render)    utils/structs/render_camera.py:269-273, envs/scene.py:404-427
  *   b2s_pick_task_create/step BaseEnv.step() for the PickCube-v1 family (controller + 5 substeps + evaluate + obs +
  *                             reward) as one launch sequence                                   envs/sapien_env.py:1042-1132
+ *   b2s_pick_task_step_autoreset  the same + ManiSkillVectorEnv's auto-reset of finished sub-scenes on the device
+ *                                                                                               vector/wrappers/gymnasium.py:160-176
  *
  * Memory: all device buffers are owned by the world (cudaMalloc at create); b2s_world_buffers() hands out
  * borrowed device pointers that alias the live state, exactly like `px.cuda_rigid_body_data.torch()` does.
@@ -222,7 +224,7 @@ typedef struct B2SCameraDesc {
 
 typedef struct B2SVisualTable {
   int32_t n_visual;        /* <= 64 render shapes per sub-scene */
-  const int32_t* type;     /* B2S_SHAPE_* (box / sphere / plane are ray-cast, convex is rasterised) */
+  const int32_t* type;     /* B2S_SHAPE_* (convex hulls and boxes are rasterised, spheres / planes / near-plane crossing boxes ray-cast) */
   const int32_t* row;      /* exposed body row the shape follows, or -1 static */
   const float* pose;       /* [n*7] local pose in the body frame */
   const float* size;       /* [n*3] */
@@ -232,9 +234,14 @@ typedef struct B2SVisualTable {
   int32_t n_ov;
   const float* ov_size;    /* [n_envs*n_ov*3] env-major */
   const float* ov_pose;    /* [n_envs*n_ov*7] env-major */
-  int32_t n_tri;           /* triangle soup of all convex visuals */
-  const int32_t* tri_vis;  /* [n_tri] owning visual */
-  const float* tri_verts;  /* [n_tri*9] vertices in the visual's local frame */
+  /* indexed triangle geometry of the visuals that are rasterised: convex hulls (vertices in the visual's frame) and boxes
+   * (the 8 corners of the unit cube (+-1), scaled by the -- possibly per-env -- half extents when they are projected) */
+  int32_t n_vert;
+  const float* vert_local;  /* [n_vert*3] */
+  const int32_t* vert_vis;  /* [n_vert] owning visual */
+  int32_t n_tri;
+  const int32_t* tri_idx;   /* [n_tri*3] vertex indices, wound so that the normal points out of the solid */
+  const int32_t* tri_vis;   /* [n_tri] owning visual */
 } B2SVisualTable;
 
 typedef struct B2SRenderTargets {
@@ -288,6 +295,48 @@ int32_t b2s_pick_task_create(uint64_t world, const B2SJointController* ctrl, con
 /* actions: device [n_envs, n_action] float32, or NULL to step without a new action */
 int32_t b2s_pick_task_step(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
                            void* stream);
+
+/*
+ * Auto-reset on the device -- `ManiSkillVectorEnv.step` (vector/wrappers/gymnasium.py:127-184: final_info / final_observation
+ * bookkeeping, partial `reset(options={"env_idx": ...})`) + `BaseEnv.reset` for the sub-scenes that finished
+ * (envs/sapien_env.py:857-978 -> PickCube `_initialize_episode`, tasks/tabletop/pick_cube.py:106-130, and
+ * `TableSceneBuilder.initialize`, utils/scene_builder/table/scene_builder.py:68-103) without the `dones.any()` host sync:
+ * after the control step the kernels (1) mark done = terminated | truncated (elapsed >= max_episode_steps), copy the observation of
+ * done sub-scenes to `final_obs`, (2) re-initialise their state from the caller's random numbers (cube xy / yaw, goal xyz uniform,
+ * robot rest pose + Gaussian noise, zero velocities, drive targets = reset pose, elapsed = 0), (3) refresh the exposed buffers and
+ * (4) rewrite their observation row.  Which random stream feeds an un-seeded reset is unspecified in the reference (the global torch
+ * RNG); here it is the `rand` tensor the caller fills each step.
+ */
+typedef struct B2SPickReset {
+  float cube_spawn_half_size;  /* pick_cube.py:38 */
+  float cube_spawn_center[2];
+  float cube_half_size;
+  float max_goal_height;
+  float robot_qpos_noise;      /* table/scene_builder.py:73 robot_init_qpos_noise */
+  int32_t n_rest;              /* dofs of articulation 0 */
+  float rest_qpos[16];         /* rest configuration; the last two (fingers) are set without noise */
+  int32_t obj_fb, goal_fb;     /* free-body indices of the object and the goal site */
+} B2SPickReset;
+
+typedef struct B2SPickAutoReset {
+  const float* rand;           /* [n_envs, 24] uniform [0,1): 0-1 cube xy, 2 cube yaw, 3-4 goal xy, 5 goal z, 6-23 pairs for 9 Box-Muller normals */
+  float* final_obs;            /* [n_envs, obs_dim] observation of the finished episode (rows of sub-scenes with done = 0 are untouched) */
+  uint8_t* done;               /* [n_envs] out: 1 where the sub-scene was reset */
+  int32_t ignore_terminations; /* 1: only truncation ends an episode (ManiSkillVectorEnv(ignore_terminations=True)) */
+  int32_t max_episode_steps;   /* TimeLimit (utils/registration.py:160-168): truncated = elapsed >= max_episode_steps, written to flags[:, 5] */
+} B2SPickAutoReset;
+
+int32_t b2s_pick_task_set_reset(uint64_t world, uint64_t handle, const B2SPickReset* reset);
+/* the auto-reset alone, after a b2s_pick_task_step (lets the caller render the finished state in between) */
+int32_t b2s_pick_task_autoreset(uint64_t world, uint64_t handle, const B2SPickOutputs* out, const B2SPickAutoReset* ar, void* stream);
+/* dst[env] = src[env] (row_bytes per sub-scene, a multiple of 16) where mask[env] != 0 -- `final_observation` images of the sub-scenes
+ * that are about to be reset (vector/wrappers/gymnasium.py:165 clones the whole observation; here only finished rows move) */
+int32_t b2s_masked_copy(uint64_t world, void* dst_dev, const void* src_dev, uint64_t row_bytes, const uint8_t* mask_dev, void* stream);
+/* b2s_render for the sub-scenes with env_mask[env] != 0 only (NULL = all): re-render after a partial reset */
+int32_t b2s_render_masked(uint64_t world, uint64_t group, const uint8_t* env_mask_dev, void* stream);
+/* b2s_pick_task_step followed by the device-side auto-reset; out->flags / reward describe the finished step (what final_info holds) */
+int32_t b2s_pick_task_step_autoreset(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
+                                     const B2SPickAutoReset* ar, void* stream);
 
 #ifdef __cplusplus
 }

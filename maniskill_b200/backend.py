@@ -39,7 +39,8 @@ class B2SCameraDesc(C.Structure):
 class B2SVisualTable(C.Structure):
     _fields_ = [("n_visual", C.c_int32), ("type", C.c_void_p), ("row", C.c_void_p), ("pose", C.c_void_p), ("size", C.c_void_p),
                 ("color", C.c_void_p), ("seg_id", C.c_void_p), ("ov_slot", C.c_void_p), ("n_ov", C.c_int32), ("ov_size", C.c_void_p),
-                ("ov_pose", C.c_void_p), ("n_tri", C.c_int32), ("tri_vis", C.c_void_p), ("tri_verts", C.c_void_p)]
+                ("ov_pose", C.c_void_p), ("n_vert", C.c_int32), ("vert_local", C.c_void_p), ("vert_vis", C.c_void_p), ("n_tri", C.c_int32),
+                ("tri_idx", C.c_void_p), ("tri_vis", C.c_void_p)]
 
 
 class B2SRenderTargets(C.Structure):
@@ -59,6 +60,17 @@ class B2SPickTask(C.Structure):
 
 class B2SPickOutputs(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p), ("elapsed", C.c_void_p)]
+
+
+class B2SPickReset(C.Structure):
+    _fields_ = [("cube_spawn_half_size", C.c_float), ("cube_spawn_center", C.c_float * 2), ("cube_half_size", C.c_float),
+                ("max_goal_height", C.c_float), ("robot_qpos_noise", C.c_float), ("n_rest", C.c_int32), ("rest_qpos", C.c_float * 16),
+                ("obj_fb", C.c_int32), ("goal_fb", C.c_int32)]
+
+
+class B2SPickAutoReset(C.Structure):
+    _fields_ = [("rand", C.c_void_p), ("final_obs", C.c_void_p), ("done", C.c_void_p), ("ignore_terminations", C.c_int32),
+                ("max_episode_steps", C.c_int32)]
 
 
 _lib = None
@@ -85,15 +97,21 @@ def load_library():
     lib.b2s_contact_query_run.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.b2s_camera_group_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(B2SRenderTargets)]
     lib.b2s_render.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.b2s_render_masked.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.b2s_masked_copy.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.b2s_pick_task_autoreset.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b2s_pick_task_create.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.b2s_pick_task_step.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.b2s_pick_task_set_reset.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.b2s_pick_task_step_autoreset.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["b2s_last_error", "b2s_version", "b2s_world_create", "b2s_world_destroy", "b2s_world_buffers", "b2s_step",
                     "b2s_apply", "b2s_fetch", "b2s_update_kinematics", "b2s_contact_query_create", "b2s_contact_query_run",
-                    "b2s_camera_group_create", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step"]
+                    "b2s_camera_group_create", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step", "b2s_pick_task_set_reset",
+                    "b2s_pick_task_step_autoreset", "b2s_pick_task_autoreset", "b2s_masked_copy", "b2s_render_masked"]
 
 
 class _DevArray:
@@ -125,12 +143,32 @@ class CameraGroup:
     def take_picture(self):
         self.world.render(self)
 
-    def get_picture_cuda(self, name: str, cam: int = 0):
-        """[N, H, W, 4] view of one camera's render target ('Color' uint8 | 'PositionSegmentation' int16)."""
+    def get_picture_cuda(self, name: str, cam: int = 0, final: bool = False):
+        """[N, H, W, 4] view of one camera's render target ('Color' uint8 | 'PositionSegmentation' int16); final=True: the copy kept for
+        sub-scenes that an auto-reset re-rendered (maniskill_b200/render.py `keep_final`)."""
         c = self.cameras[cam]
         a, b = int(self._offsets[cam]), int(self._offsets[cam + 1])
-        buf = self._color if name == "Color" else self._posseg
+        if final:
+            buf = self._final_color if name == "Color" else self._final_posseg
+        else:
+            buf = self._color if name == "Color" else self._posseg
         return buf[:, a:b].view(self.world.n_envs, int(c["height"]), int(c["width"]), 4)
+
+
+# bits of the sticky overflow word (include/b200sim.h B2S_OVF_*) -> the capacity that was exceeded and how to raise it
+OVERFLOW_REASONS = {
+    1: "contact patches per sub-scene > max_manifolds (sim_config max_manifolds, compiled cap 24)",
+    2: "contact points per sub-scene > max_contacts (sim_config max_contacts, compiled cap 64)",
+    4: "constraint rows per sub-scene > the compiled row capacity (csrc/b2s_step.cuh Caps::MAXROW)",
+    8: "constraint rows on an articulation > capacity",
+    16: "active joint limits per sub-scene > 24",
+    32: "tendon couplings per sub-scene > 2",
+}
+
+
+class CapacityWarning(RuntimeWarning):
+    """A fixed per-sub-scene capacity dropped a contact or a constraint row (the reference's PhysX reports exceeded
+    GPUMemoryConfig capacities in the same spirit, mani_skill/utils/structs/types.py:16-32)."""
 
 
 ANY_BODY = -2  # include/b200sim.h B2S_ANY_BODY: second row of a contact query = every body (net impulse on the first)
@@ -242,6 +280,35 @@ class World:
         _check(self.lib, self.lib.b2s_pick_task_step(self.h, handle, a, int(substeps), C.byref(out), self._stream()))
         self.kernel_launches += (2 if actions is not None else 1) + self._step_launches(substeps, BUF_ALL)
 
+    def set_pick_reset(self, handle, cube_spawn_half_size, cube_spawn_center, cube_half_size, max_goal_height, robot_qpos_noise, rest_qpos,
+                       obj_fb, goal_fb):
+        """Episode initialisation of the pick task for the device-side auto-reset (include/b200sim.h B2SPickReset)."""
+        r = B2SPickReset()
+        r.cube_spawn_half_size, r.cube_half_size, r.max_goal_height = float(cube_spawn_half_size), float(cube_half_size), float(max_goal_height)
+        r.cube_spawn_center = (C.c_float * 2)(float(cube_spawn_center[0]), float(cube_spawn_center[1]))
+        r.robot_qpos_noise = float(robot_qpos_noise)
+        rest = [float(x) for x in rest_qpos]
+        r.n_rest = len(rest)
+        r.rest_qpos = (C.c_float * 16)(*(rest + [0.0] * (16 - len(rest))))
+        r.obj_fb, r.goal_fb = int(obj_fb), int(goal_fb)
+        _check(self.lib, self.lib.b2s_pick_task_set_reset(self.h, handle, C.byref(r)))
+
+    def pick_task_autoreset(self, handle, obs, reward, flags, elapsed, rand, final_obs, done, ignore_terminations=False, max_episode_steps=0):
+        """The auto-reset alone, after `pick_task_step` (the caller may render the finished state in between)."""
+        out = B2SPickOutputs(obs.data_ptr(), reward.data_ptr(), flags.data_ptr(), elapsed.data_ptr())
+        ar = B2SPickAutoReset(rand.data_ptr(), final_obs.data_ptr(), done.data_ptr(), 1 if ignore_terminations else 0, int(max_episode_steps or 0))
+        _check(self.lib, self.lib.b2s_pick_task_autoreset(self.h, handle, C.byref(out), C.byref(ar), self._stream()))
+        self.kernel_launches += 3
+
+    def pick_task_step_autoreset(self, handle, actions, substeps, obs, reward, flags, elapsed, rand, final_obs, done, ignore_terminations=False,
+                                 max_episode_steps=0):
+        """b2s_pick_task_step + the auto-reset of finished sub-scenes, all on the device (no host sync)."""
+        out = B2SPickOutputs(obs.data_ptr(), reward.data_ptr(), flags.data_ptr(), elapsed.data_ptr())
+        ar = B2SPickAutoReset(rand.data_ptr(), final_obs.data_ptr(), done.data_ptr(), 1 if ignore_terminations else 0, int(max_episode_steps or 0))
+        a = C.c_void_p(actions.data_ptr()) if actions is not None else None
+        _check(self.lib, self.lib.b2s_pick_task_step_autoreset(self.h, handle, a, int(substeps), C.byref(out), C.byref(ar), self._stream()))
+        self.kernel_launches += (2 if actions is not None else 1) + self._step_launches(substeps, BUF_ALL) + 3
+
     # ------------------------------------------------------------------ rendering
     def create_camera_group(self, cameras, visuals):
         """cameras: list of dict(width, height, fx, fy, cx, cy, near, far, mount_row, local_pose7);
@@ -260,8 +327,8 @@ class World:
             if keep[k].size == 0:
                 keep[k] = np.zeros(1, dtype=keep[k].dtype)
         vt = B2SVisualTable()
-        vt.n_visual, vt.n_ov, vt.n_tri = int(visuals["n_visual"]), int(visuals["n_ov"]), int(visuals["n_tri"])
-        for name in ("type", "row", "pose", "size", "color", "seg_id", "ov_slot", "ov_size", "ov_pose", "tri_vis", "tri_verts"):
+        vt.n_visual, vt.n_ov, vt.n_vert, vt.n_tri = int(visuals["n_visual"]), int(visuals["n_ov"]), int(visuals["n_vert"]), int(visuals["n_tri"])
+        for name in ("type", "row", "pose", "size", "color", "seg_id", "ov_slot", "ov_size", "ov_pose", "vert_local", "vert_vis", "tri_idx", "tri_vis"):
             setattr(vt, name, keep[name].ctypes.data_as(C.c_void_p))
         g = C.c_uint64(0)
         rt = B2SRenderTargets()
@@ -272,13 +339,46 @@ class World:
         posseg = _as_tensor(rt.position_seg, (self.n_envs, pix, 4), "<i2", self, self.device)
         return CameraGroup(self, g, cameras, color, posseg)
 
-    def render(self, group):
-        _check(self.lib, self.lib.b2s_render(self.h, group.handle, self._stream()))
+    def render(self, group, env_mask=None):
+        """take_picture(); `env_mask` ([n_envs] uint8 / bool device tensor): only those sub-scenes are re-rendered."""
+        if env_mask is None:
+            _check(self.lib, self.lib.b2s_render(self.h, group.handle, self._stream()))
+        else:
+            _check(self.lib, self.lib.b2s_render_masked(self.h, group.handle, C.c_void_p(env_mask.data_ptr()), self._stream()))
         self.kernel_launches += 1
+
+    def masked_copy(self, dst, src, env_mask):
+        """dst[env] = src[env] where env_mask[env] (both [n_envs, ...] contiguous device tensors of the same layout)."""
+        row_bytes = src[0].numel() * src.element_size()
+        _check(self.lib, self.lib.b2s_masked_copy(self.h, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()), row_bytes,
+                                                  C.c_void_p(env_mask.data_ptr()), self._stream()))
+        self.kernel_launches += 1
+
+    # ------------------------------------------------------------------ capacity overflow (sticky, device side)
+    def overflow_reasons(self):
+        """Reads the sticky overflow word (one device sync) -> list of messages, empty when nothing was ever dropped."""
+        code = int(self.overflow_flag.item())
+        return [msg for bit, msg in OVERFLOW_REASONS.items() if code & bit]
+
+    def check_overflow(self, strict: bool = False):
+        """Warn (CapacityWarning) or raise (strict) when a sub-scene exceeded a capacity since the world was created.  Called by the
+        env on full resets and on close, i.e. off the per-step path: the check costs a device sync."""
+        reasons = self.overflow_reasons()
+        if reasons:
+            msg = "b200sim dropped contacts / constraint rows: " + "; ".join(reasons)
+            if strict:
+                raise RuntimeError(msg)
+            import warnings
+            warnings.warn(msg, CapacityWarning, stacklevel=2)
+        return reasons
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
             torch.cuda.synchronize(self.device)
+            try:
+                self.check_overflow()
+            except Exception:
+                pass
             self.lib.b2s_world_destroy(self.h)
             self.h = C.c_uint64(0)
 

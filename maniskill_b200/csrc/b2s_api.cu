@@ -6,6 +6,7 @@
 // B2S_FUSED=1 selects the single-kernel form (one lane per sub-scene, everything in per-lane scratch) kept for comparison.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -48,6 +49,8 @@ struct PickTaskDev {
   int *dof_action, *dof_use_delta, *dof_normalize;
   float *dof_low, *dof_high;
   B2SPickTask task;
+  B2SPickReset reset;
+  int has_reset;
 };
 
 struct World : b2s::WorldT<DevMem> {
@@ -226,11 +229,14 @@ __global__ void controller_kernel(b2s::DevModel M, b2s::DevState S, PickTaskDev 
 
 // ---- fused control step, launch 3: evaluate + reward + observation of the pick task (pick_cube.py:132-191,
 // panda.py:237-269, base_agent.py:339-347).  Reads the freshly fetched exposed buffers, so the python path sees the same data.
+// `only` (nullable): second use after a device-side auto-reset -- only the sub-scenes with only[env] != 0 are visited and only their
+// observation row is rewritten (reward, flags and elapsed keep describing the finished step / were set by the reset).
 __global__ void pick_epilogue_kernel(b2s::DevModel M, b2s::DevState S, PickTaskDev T, float* __restrict__ obs, float* __restrict__ reward,
-                                     uint8_t* __restrict__ flags, int* __restrict__ elapsed) {
+                                     uint8_t* __restrict__ flags, int* __restrict__ elapsed, const uint8_t* __restrict__ only) {
   using namespace b2s;
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
+  if (only && !only[env]) return;
   const size_t N = M.n_envs;
   const B2SPickTask& K = T.task;
   const int nr = M.n_rows, nd = M.n_dof, md = M.max_dof_per_art;
@@ -283,12 +289,14 @@ __global__ void pick_epilogue_kernel(b2s::DevModel M, b2s::DevState S, PickTaskD
   r += (1.f - tanhf(5.f * sqrtf(vsq))) * (is_obj_placed ? 1.f : 0.f);
   if (success) r = 5.f;
   if (K.normalized_reward) r = r / 5.f;
-  reward[env] = r;
-  int el = elapsed[env] + 1;
-  elapsed[env] = el;
-  uint8_t* f = flags + (size_t)env * 6;
-  f[0] = success; f[1] = is_obj_placed; f[2] = is_static; f[3] = is_grasped; f[4] = success;
-  f[5] = (K.max_episode_steps > 0 && el >= K.max_episode_steps) ? 1 : 0;
+  if (!only) {
+    reward[env] = r;
+    int el = elapsed[env] + 1;
+    elapsed[env] = el;
+    uint8_t* f = flags + (size_t)env * 6;
+    f[0] = success; f[1] = is_obj_placed; f[2] = is_static; f[3] = is_grasped; f[4] = success;
+    f[5] = (K.max_episode_steps > 0 && el >= K.max_episode_steps) ? 1 : 0;
+  }
   // observation: qpos, qvel, is_grasped, tcp_pose, goal_pos, obj_pose, tcp_to_obj_pos, obj_to_goal_pos
   int d0 = M.art_dof_start[0], d1 = M.art_dof_start[1], nq = d1 - d0;
   float* o = obs + (size_t)env * (2 * nq + 24);
@@ -302,6 +310,51 @@ __global__ void pick_epilogue_kernel(b2s::DevModel M, b2s::DevState S, PickTaskD
   o[18] = t2o.x; o[19] = t2o.y; o[20] = t2o.z;
   o[21] = o2g.x; o[22] = o2g.y; o[23] = o2g.z;
   (void)nd;
+}
+
+// ---- device-side auto-reset of the pick task (include/b200sim.h B2SPickAutoReset): one lane per sub-scene; lanes whose episode
+// goes on return at once.  Writes the INTERNAL state (env-major SoA); the fetch that follows refreshes the exposed buffers.
+__global__ void pick_reset_kernel(b2s::DevModel M, b2s::DevState S, PickTaskDev T, const float* __restrict__ obs, uint8_t* __restrict__ flags,
+                                  int* __restrict__ elapsed, const float* __restrict__ rnd, float* __restrict__ final_obs,
+                                  uint8_t* __restrict__ done, int ignore_terminations, int max_episode_steps) {
+  using namespace b2s;
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= M.n_envs) return;
+  const size_t N = M.n_envs;
+  uint8_t* f = flags + (size_t)env * 6;
+  if (max_episode_steps > 0) f[5] = elapsed[env] >= max_episode_steps ? 1 : 0;  // TimeLimit truncation
+  const bool d = (f[4] && !ignore_terminations) || f[5];
+  done[env] = d ? 1 : 0;
+  if (!d) return;
+  const B2SPickReset& R = T.reset;
+  const int d0 = M.art_dof_start[0], d1 = M.art_dof_start[1], nq = d1 - d0;
+  const int od = 2 * nq + 24;
+  for (int k = 0; k < od; k++) final_obs[(size_t)env * od + k] = obs[(size_t)env * od + k];
+  const float* u = rnd + (size_t)env * 24;
+  // robot: rest configuration + Gaussian noise (Box-Muller on the caller's uniforms), fingers exact, zero velocity / force,
+  // drive targets hold the reset configuration until the first action
+  for (int i = 0; i < nq; i++) {
+    float q = R.rest_qpos[i];
+    if (i < nq - 2) {
+      const float u1 = fmaxf(u[6 + 2 * i], 1.0e-7f), u2 = u[7 + 2 * i];
+      q += R.robot_qpos_noise * sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);
+    }
+    const size_t o = (size_t)(d0 + i) * N + env;
+    S.q[o] = q; S.qd[o] = 0.f; S.qf[o] = 0.f; S.tq[o] = q; S.tqd[o] = 0.f; S.qacc[o] = 0.f;
+  }
+  // object: xy uniform in the spawn square, resting on the table, random yaw (random_quaternions(lock_x, lock_y)); zero velocity
+  const float hs = R.cube_spawn_half_size;
+  const float cx = R.cube_spawn_center[0] + (2.f * u[0] - 1.f) * hs, cy = R.cube_spawn_center[1] + (2.f * u[1] - 1.f) * hs, cz = R.cube_half_size;
+  const float yaw = 6.283185307179586f * u[2];
+  float* ob = S.fb + (size_t)(R.obj_fb * 13) * N + env;
+  const float po[13] = {cx, cy, cz, cosf(0.5f * yaw), 0.f, 0.f, sinf(0.5f * yaw), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < 13; k++) ob[(size_t)k * N] = po[k];
+  // goal: xy uniform in the same square, height uniform in [0, max_goal_height] above the object's centre
+  float* gb = S.fb + (size_t)(R.goal_fb * 13) * N + env;
+  const float pg[13] = {R.cube_spawn_center[0] + (2.f * u[3] - 1.f) * hs, R.cube_spawn_center[1] + (2.f * u[4] - 1.f) * hs,
+                        u[5] * R.max_goal_height + cz, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < 13; k++) gb[(size_t)k * N] = pg[k];
+  elapsed[env] = 0;
 }
 
 }  // namespace
@@ -547,7 +600,16 @@ int32_t b2s_render(uint64_t world, uint64_t group, void* stream) {
   World* w = get(world);
   if (!w || group < 1 || group > w->groups.size()) return fail(B2S_ERR_INVALID, "bad camera group");
   DeviceGuard guard_(w->device);
-  const char* err = b2s::raster_run(w->M, w->S, w->groups[group - 1], (cudaStream_t)stream);
+  const char* err = b2s::raster_run(w->M, w->S, w->groups[group - 1], nullptr, (cudaStream_t)stream);
+  if (err) return fail(B2S_ERR_CUDA, "%s", err);
+  return B2S_OK;
+}
+
+int32_t b2s_render_masked(uint64_t world, uint64_t group, const uint8_t* env_mask_dev, void* stream) {
+  World* w = get(world);
+  if (!w || group < 1 || group > w->groups.size()) return fail(B2S_ERR_INVALID, "bad camera group");
+  DeviceGuard guard_(w->device);
+  const char* err = b2s::raster_run(w->M, w->S, w->groups[group - 1], env_mask_dev, (cudaStream_t)stream);
   if (err) return fail(B2S_ERR_CUDA, "%s", err);
   return B2S_OK;
 }
@@ -564,6 +626,8 @@ int32_t b2s_pick_task_create(uint64_t world, const B2SJointController* c, const 
   PickTaskDev T;
   T.n_action = c->n_action;
   T.task = *task;
+  T.has_reset = 0;
+  memset(&T.reset, 0, sizeof(T.reset));
   T.dof_action = (int*)w->up(c->dof_action, nd); T.dof_use_delta = (int*)w->up(c->dof_use_delta, nd);
   T.dof_normalize = (int*)w->up(c->dof_normalize, nd);
   T.dof_low = (float*)w->up(c->dof_low, nd); T.dof_high = (float*)w->up(c->dof_high, nd);
@@ -585,7 +649,68 @@ int32_t b2s_pick_task_step(uint64_t world, uint64_t handle, const float* actions
   if (actions_dev) controller_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, actions_dev);
   int32_t rc = b2s_step(world, substeps, 0xFFFFFFFFu, stream);
   if (rc != B2S_OK) return rc;
-  pick_epilogue_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->reward, out->flags, out->elapsed);
+  pick_epilogue_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->reward, out->flags, out->elapsed, nullptr);
+  CK(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t b2s_pick_task_set_reset(uint64_t world, uint64_t handle, const B2SPickReset* reset) {
+  World* w = get(world);
+  if (!w || handle < 1 || handle > w->pick_tasks.size() || !reset) return fail(B2S_ERR_INVALID, "bad pick task reset");
+  const int nq = w->M.n_art > 0 ? w->host.max_dof_per_art : 0;
+  if (reset->n_rest < 2 || reset->n_rest > 16 || reset->n_rest > nq) return fail(B2S_ERR_INVALID, "pick task reset: bad rest configuration length");
+  if (reset->obj_fb < 0 || reset->obj_fb >= w->M.n_fb || reset->goal_fb < 0 || reset->goal_fb >= w->M.n_fb)
+    return fail(B2S_ERR_INVALID, "pick task reset: free-body index out of range");
+  PickTaskDev& T = w->pick_tasks[handle - 1];
+  T.reset = *reset;
+  T.has_reset = 1;
+  return B2S_OK;
+}
+
+int32_t b2s_pick_task_autoreset(uint64_t world, uint64_t handle, const B2SPickOutputs* out, const B2SPickAutoReset* ar, void* stream) {
+  World* w = get(world);
+  if (!w || handle < 1 || handle > w->pick_tasks.size() || !out || !out->obs || !out->reward || !out->flags || !out->elapsed || !ar || !ar->rand ||
+      !ar->final_obs || !ar->done)
+    return fail(B2S_ERR_INVALID, "bad pick task auto-reset");
+  if (!w->pick_tasks[handle - 1].has_reset) return fail(B2S_ERR_INVALID, "b2s_pick_task_set_reset has not been called");
+  int32_t rc = B2S_OK;
+  DeviceGuard guard_(w->device);
+  const PickTaskDev& T = w->pick_tasks[handle - 1];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = w->M.n_envs;
+  pick_reset_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->flags, out->elapsed, ar->rand, ar->final_obs, ar->done,
+                                                     ar->ignore_terminations, ar->max_episode_steps);
+  // exposed buffers of every sub-scene from the internal state (unchanged where no reset happened), then the observation rows of
+  // the reset sub-scenes
+  rc = b2s_fetch(world, 0xFFFFFFFFu, stream);
+  if (rc != B2S_OK) return rc;
+  pick_epilogue_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->reward, out->flags, out->elapsed, ar->done);
+  CK(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t b2s_pick_task_step_autoreset(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
+                                     const B2SPickAutoReset* ar, void* stream) {
+  int32_t rc = b2s_pick_task_step(world, handle, actions_dev, substeps, out, stream);
+  if (rc != B2S_OK) return rc;
+  return b2s_pick_task_autoreset(world, handle, out, ar, stream);
+}
+
+// dst[env] = src[env] (row_bytes each, 16-byte multiples) for the sub-scenes with mask[env] != 0: blocks of other sub-scenes exit at once
+__global__ void masked_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t row_vec, const uint8_t* __restrict__ mask) {
+  const int env = blockIdx.y;
+  if (!mask[env]) return;
+  const size_t base = (size_t)env * row_vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_vec; i += (size_t)gridDim.x * blockDim.x) dst[base + i] = src[base + i];
+}
+
+int32_t b2s_masked_copy(uint64_t world, void* dst_dev, const void* src_dev, uint64_t row_bytes, const uint8_t* mask_dev, void* stream) {
+  World* w = get(world);
+  if (!w || !dst_dev || !src_dev || !mask_dev || row_bytes == 0 || row_bytes % 16 != 0) return fail(B2S_ERR_INVALID, "bad masked copy");
+  DeviceGuard guard_(w->device);
+  const size_t row_vec = row_bytes / 16;
+  const int bx = (int)((row_vec + 255) / 256 < 64 ? (row_vec + 255) / 256 : 64);
+  masked_copy_kernel<<<dim3(bx, w->M.n_envs), 256, 0, (cudaStream_t)stream>>>((uint4*)dst_dev, (const uint4*)src_dev, row_vec, mask_dev);
   CK(cudaGetLastError());
   return B2S_OK;
 }

@@ -28,10 +28,9 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   RasterModel& R = g->R;
   memset(&R, 0, sizeof(R));
   const size_t N = M.n_envs;
-  R.n_envs = M.n_envs; R.n_cam = n_cam; R.n_vis = vis->n_visual; R.n_tri_total = vis->n_tri; R.n_rows = M.n_rows; R.n_ov = vis->n_ov;
+  R.n_envs = M.n_envs; R.n_cam = n_cam; R.n_vis = vis->n_visual; R.n_vert = vis->n_vert; R.n_tri = vis->n_tri; R.n_rows = M.n_rows; R.n_ov = vis->n_ov;
   R.vis_type = dev_copy(g, vis->type, vis->n_visual); R.vis_row = dev_copy(g, vis->row, vis->n_visual);
   R.vis_pose = dev_copy(g, vis->pose, (size_t)vis->n_visual * 7); R.vis_size = dev_copy(g, vis->size, (size_t)vis->n_visual * 3);
-  R.vis_hull = nullptr;
   R.vis_color = dev_copy(g, vis->color, (size_t)vis->n_visual * 4); R.vis_seg = dev_copy(g, vis->seg_id, vis->n_visual);
   R.vis_ov = dev_copy(g, vis->ov_slot, vis->n_visual);
   {
@@ -43,8 +42,12 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
     R.ov_size = dev_copy(g, sz.data(), sz.size());
     R.ov_pose = dev_copy(g, ps.data(), ps.size());
   }
+  for (int t = 0; t < vis->n_tri * 3; t++)
+    if (vis->tri_idx[t] < 0 || vis->tri_idx[t] >= vis->n_vert) { raster_destroy(g); return "triangle vertex index out of range"; }
+  R.vert_local = dev_copy(g, vis->vert_local, (size_t)vis->n_vert * 3);
+  R.vert_vis = dev_copy(g, vis->vert_vis, vis->n_vert);
+  R.tri_idx = dev_copy(g, vis->tri_idx, (size_t)vis->n_tri * 3);
   R.tri_vis = dev_copy(g, vis->tri_vis, vis->n_tri);
-  R.tri_verts = dev_copy(g, vis->tri_verts, (size_t)vis->n_tri * 9);
   std::vector<int> w(n_cam), h(n_cam), mount(n_cam);
   std::vector<float> intr(n_cam * 6), cp(n_cam * 7);
   std::vector<size_t> off(n_cam);
@@ -59,7 +62,7 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
     pix += (size_t)w[c] * h[c];
     if (w[c] * h[c] > g->max_pixels) g->max_pixels = w[c] * h[c];
   }
-  if ((size_t)g->max_pixels * 4 > 200 * 1024) { raster_destroy(g); return "camera image does not fit the shared-memory depth buffer (max ~224x224)"; }
+  if ((size_t)g->max_pixels * 4 > 190 * 1024) { raster_destroy(g); return "camera image does not fit the shared-memory depth buffer (max ~220x220)"; }
   R.cam_w = dev_copy(g, w.data(), n_cam); R.cam_h = dev_copy(g, h.data(), n_cam); R.cam_mount = dev_copy(g, mount.data(), n_cam);
   R.cam_intr = dev_copy(g, intr.data(), intr.size()); R.cam_pose = dev_copy(g, cp.data(), cp.size());
   R.cam_offset = dev_copy(g, off.data(), n_cam);
@@ -79,11 +82,10 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   return nullptr;
 }
 
-const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, cudaStream_t st) {
+const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st) {
   int grid = M.n_envs * g->R.n_cam;
-  // 512 threads = 16 warps per image: two images per SM (shared-memory bound) then keep 32 warps in flight
-  static int threads = getenv("B2S_RASTER_THREADS") ? atoi(getenv("B2S_RASTER_THREADS")) : 512;
-  raster_kernel<<<grid, threads, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg);
+  // 512 threads = 16 warps per image: two images per SM (shared-memory bound) keep 32 warps in flight
+  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg, env_mask);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -1,4 +1,4 @@
-// b200sim batched tiled rasteriser -- replaces `camera_group.take_picture()` of the reference
+// b200sim batched rasteriser -- replaces `camera_group.take_picture()` of the reference
 // (mani_skill/utils/structs/render_camera.py:269-273; camera group creation mani_skill/envs/scene.py:1087-1106; pose
 // sync physics->renderer mani_skill/envs/scene.py:404-427) for the "minimal" shader pack
 // (mani_skill/render/shaders.py:68-84): per camera and sub-scene it produces
@@ -6,15 +6,22 @@
 //     PositionSegmentation  [H, W, 4] int16  x, y, z in millimetres (OpenGL camera frame: x right, y up, z backward,
 //                                            so depth = -z) and the segmentation id (= per_scene_id, 0 = background)
 //
-// One CTA renders one (sub-scene, camera) image.  The whole depth/id buffer of the image lives in shared memory
-// (H*W 32-bit keys: 24-bit reversed-z depth | 8-bit visual id; 64 KB for 128x128):
-//   pass 1  all threads stride over the triangles of the convex-hull visuals: body pose (read once from
-//           rigid_body_data) x local pose -> camera frame, project, top-left fill rule, shared-memory atomicMin
-//   pass 2  each thread owns pixels: analytic ray tests against boxes / spheres / the ground half-space, merge with the
-//           rasterised key, shade (ambient 0.3 + two directional lights, mani_skill/envs/sapien_env.py:845-853), write
-//           the two render targets straight to HBM with 4-byte (rgba8) and 8-byte (4 x int16) stores, coalesced by row.
-// HBM traffic per image: the body rows once in, 12 B per pixel out.  The per-pixel arithmetic is restated in
-// oracle/b2s_oracle_raster.cpp; this translation unit is compiled with -fmad=false so both produce identical masks.
+// One CTA renders one (sub-scene, camera) image; the 32-bit depth/id buffer of the whole image lives in shared memory (24-bit
+// reversed-z key of 1/depth | 8-bit visual id; 64 KB for 128 x 128).  Everything that can hide something goes through that key:
+//   stage 0  per visual: camera-from-visual transform (body pose read once from rigid_body_data); boxes whose corners are all in
+//            front of the near plane are RASTERISED like the convex hulls (12 triangles), the others stay analytic
+//   stage 1  the vertices of all rasterised visuals are transformed and projected ONCE into a shared-memory cache
+//            (screen x, y, 1/depth: one division per vertex instead of three per triangle)
+//   stage 2  indexed triangles: back-face cull by the sign of the screen area, top-left-free ">= 0" edge rule on counter-clockwise
+//            triangles, 1/depth interpolated in screen space, shared-memory atomicMin on the key; small triangles by one thread,
+//            larger ones queued and rasterised by a warp, huge ones (close-ups) by the CTA
+//   stage 3  per pixel: the analytic visuals (half-spaces: no division -- 1/depth is linear in the ray; spheres and near-plane
+//            crossing boxes: ray tests inside their screen rectangle) produce keys of the same form, the smallest key wins,
+//            depth = 1 / (dequantised 1/depth): ONE division per covered pixel; flat normals from the geometry (box face from
+//            the hit point, plane, sphere) or from the depth neighbourhood (hulls); Lambert shading (ambient 0.3 + the two
+//            directional lights of mani_skill/envs/sapien_env.py:845-853); 4-byte and 8-byte stores, coalesced by row.
+// HBM traffic per image: the body rows in, 12 B per pixel out.  The arithmetic is restated operation by operation in
+// oracle/b2s_oracle_raster.cpp; this translation unit is compiled with -fmad=false so that both produce identical integers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,20 +34,21 @@
 namespace b2s {
 
 struct RasterModel {
-  int n_envs, n_cam, n_vis, n_tri_total, n_rows, n_ov;
+  int n_envs, n_cam, n_vis, n_vert, n_tri, n_rows, n_ov;
   const int* vis_type;
   const int* vis_row;
   const float* vis_pose;   // [n_vis*7]
   const float* vis_size;   // [n_vis*3]
-  const int* vis_hull;
   const float* vis_color;  // [n_vis*4]
   const int* vis_seg;
   const int* vis_ov;       // per-env override slot or -1
   const float* ov_size;    // SoA [n_ov*3][N]
   const float* ov_pose;    // SoA [n_ov*7][N]
-  // triangle soup of the hull visuals
-  const int* tri_vis;      // [n_tri_total] owning visual
-  const float* tri_verts;  // [n_tri_total*9] local (hull frame) vertices
+  // indexed geometry of the rasterised visuals (convex hulls: local vertices; boxes: the corners of the unit cube, scaled by the size)
+  const float* vert_local; // [n_vert*3]
+  const int* vert_vis;     // [n_vert]
+  const int* tri_idx;      // [n_tri*3] vertex indices, wound outwards
+  const int* tri_vis;      // [n_tri]
   // cameras
   const int* cam_w;
   const int* cam_h;
@@ -61,9 +69,9 @@ struct RasterGroup {
 
 #define B2S_DEPTH_BITS 24
 #define B2S_DEPTH_MAX 16777215.0f
+#define B2S_NO_HIT 0xFFFFFFFFu
 
-// Reversed-z quantisation shared by the raster and the analytic pass, on 1/depth.  The constants of a camera are computed once
-// (DepthMap), a sample costs no division: the key comes from the interpolated 1/depth directly, the near/far test is done on it.
+// Reversed-z quantisation on 1/depth.  The constants of a camera are computed once (DepthMap).
 struct DepthMap {
   float invn, invf, range, scale, inv_max;  // 1/near, 1/far, invn - invf, 1 / range, 1 / B2S_DEPTH_MAX
 };
@@ -90,10 +98,8 @@ B2S_HD float key_depth(unsigned k, const DepthMap& m) {
 }
 
 // ray (origin o, direction dvec, both in the box frame) against an axis-aligned box of half extents h: entry distance
-B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit, v3& n_local) {
+B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit) {
   float tmin = -1e30f, tmax = 1e30f;
-  int axis = 0;
-  float sgn = 1.0f;
   float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
   for (int k = 0; k < 3; k++) {
     if (fabsf(dd[k]) < 1e-12f) {
@@ -101,38 +107,45 @@ B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit, v3& n_local) {
     } else {
       float inv = 1.0f / dd[k];
       float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
-      float s = -1.0f;
-      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; s = 1.0f; }
-      if (t0 > tmin) { tmin = t0; axis = k; sgn = s; }
+      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
+      if (t0 > tmin) tmin = t0;
       if (t1 < tmax) tmax = t1;
     }
   }
   if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
   t_hit = tmin;
-  n_local = mk3(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f);
   return true;
 }
-B2S_HD bool ray_sphere(v3 o, v3 dv, float r, float& t_hit, v3& n_local) {
+B2S_HD bool ray_sphere(v3 o, v3 dv, float r, float& t_hit) {
   float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
   float disc = b * b - a * c;
   if (disc < 0.0f) return false;
   float t = (-b - sqrtf(disc)) / a;
   if (t <= 0.0f) return false;
   t_hit = t;
-  n_local = (o + dv * t) * (1.0f / r);
   return true;
+}
+// outward face normal of a box (half extents h) at a surface point pl of its frame: the face whose plane is nearest
+B2S_HD v3 box_face_normal(v3 pl, v3 h) {
+  float d0 = fabsf(pl.x) - h.x, d1 = fabsf(pl.y) - h.y, d2 = fabsf(pl.z) - h.z;
+  int axis = 0;
+  float best = d0;
+  if (d1 > best) { best = d1; axis = 1; }
+  if (d2 > best) { best = d2; axis = 2; }
+  float c = axis == 0 ? pl.x : (axis == 1 ? pl.y : pl.z);
+  float s = c >= 0.0f ? 1.0f : -1.0f;
+  return mk3(axis == 0 ? s : 0.0f, axis == 1 ? s : 0.0f, axis == 2 ? s : 0.0f);
 }
 
 B2S_HD uint8_t to_u8(float x) {
   float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
   return (uint8_t)c;
 }
-B2S_HD v3 shade(v3 base, v3 n_world) {
+B2S_HD float shade_weight(v3 n_world) {
   // ambient 0.3 + directional [1,1,-1] + directional [0,0,-1] (white), Lambert
   const float k = 0.57735026f;
   v3 l1 = mk3(-k, -k, k), l2 = mk3(0.0f, 0.0f, 1.0f);
-  float w = 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
-  return base * w;
+  return 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
 }
 B2S_HD int16_t to_mm(float x) {
   float v = x * 1000.0f;
@@ -151,162 +164,200 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
   return P;
 }
 
-#define B2S_MAX_BIG_TRIS 512
+#define B2S_RASTER_THREADS 512
+#define B2S_MAX_VIS 64
+#define B2S_VERT_CACHE 1536       // projected vertices kept in shared memory (18 KB); vertices beyond are projected on use
+#define B2S_MAX_BIG_TRIS 1024
 #define B2S_BIG_TRI_PIXELS 24     // bounding boxes above this many pixels leave the one-thread path
 #define B2S_HUGE_TRI_PIXELS 2048  // ... and above this many are shared by the whole CTA instead of one warp
 
+enum { VM_RASTER = 0, VM_ANALYTIC = 1 };
+
+struct RasterShared {
+  float vis_R[B2S_MAX_VIS][9];   // camera-from-visual rotation (row major)
+  float vis_t[B2S_MAX_VIS][3];   // camera-from-visual translation
+  float vis_Rw[B2S_MAX_VIS][9];  // world-from-visual rotation (lighting)
+  float vis_sz[B2S_MAX_VIS][3];
+  float vis_o[B2S_MAX_VIS][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
+  float vis_c[B2S_MAX_VIS];      // half-spaces: -1 / o.x, so that 1/depth of the ray hit = c * (ray direction).x
+  int vis_rect[B2S_MAX_VIS][4];  // conservative screen rectangle (x0, x1, y0, y1) of the analytic primitives
+  int vis_kind[B2S_MAX_VIS];
+  int vis_mode[B2S_MAX_VIS];
+  float vert[B2S_VERT_CACHE][3];  // screen x, screen y, 1/depth (0 = at or behind the near plane)
+  unsigned short big[B2S_MAX_BIG_TRIS];
+  int n_big;
+};
+
+// local vertex i of the rasterised geometry -> screen x, y, 1/depth (out[2] = 0 when it is not in front of the near plane)
+__device__ __forceinline__ void project_vertex(const RasterModel& R, const RasterShared& sh, int i, float fx, float fy, float cx, float cy, float nearp,
+                                               float* out) {
+  const int v = R.vert_vis[i];
+  float lx = R.vert_local[3 * i], ly = R.vert_local[3 * i + 1], lz = R.vert_local[3 * i + 2];
+  if (sh.vis_kind[v] == SH_BOX) { lx = lx * sh.vis_sz[v][0]; ly = ly * sh.vis_sz[v][1]; lz = lz * sh.vis_sz[v][2]; }
+  const float xc = sh.vis_R[v][0] * lx + sh.vis_R[v][1] * ly + sh.vis_R[v][2] * lz + sh.vis_t[v][0];
+  const float yc = sh.vis_R[v][3] * lx + sh.vis_R[v][4] * ly + sh.vis_R[v][5] * lz + sh.vis_t[v][1];
+  const float zc = sh.vis_R[v][6] * lx + sh.vis_R[v][7] * ly + sh.vis_R[v][8] * lz + sh.vis_t[v][2];
+  if (xc <= nearp) { out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; return; }
+  const float inv = 1.0f / xc;
+  out[0] = cx - fx * yc * inv;
+  out[1] = cy - fy * zc * inv;
+  out[2] = inv;
+}
+
+// screen-space setup of triangle t: false when it is culled (behind the near plane, back facing, off screen)
+struct TriSetup {
+  float px[3], py[3], pd[3], inv_area;
+  int x0, y0, x1, y1, v;
+};
+__device__ __forceinline__ bool setup_triangle(const RasterModel& R, const RasterShared& sh, int t, int W, int H, float fx, float fy, float cx, float cy,
+                                               float nearp, TriSetup& T) {
+  const int v = R.tri_vis[t];
+  if (v >= B2S_MAX_VIS || sh.vis_mode[v] != VM_RASTER) return false;
+  T.v = v;
+  for (int k = 0; k < 3; k++) {
+    const int i = R.tri_idx[3 * t + k];
+    float p[3];
+    if (i < B2S_VERT_CACHE) { p[0] = sh.vert[i][0]; p[1] = sh.vert[i][1]; p[2] = sh.vert[i][2]; }
+    else project_vertex(R, sh, i, fx, fy, cx, cy, nearp, p);
+    if (p[2] == 0.0f) return false;  // triangles touching the near plane are dropped (robot links never get that close)
+    T.px[k] = p[0]; T.py[k] = p[1]; T.pd[k] = p[2];
+  }
+  float area = (T.px[1] - T.px[0]) * (T.py[2] - T.py[0]) - (T.px[2] - T.px[0]) * (T.py[1] - T.py[0]);
+  // triangles are wound outwards: with screen x to the right and y down a front face has negative area; back faces are culled
+  // (the solids are closed: they are hidden by the front faces), front faces are made counter-clockwise
+  if (!(area < 0.0f)) return false;
+  float s;
+  s = T.px[1]; T.px[1] = T.px[2]; T.px[2] = s;
+  s = T.py[1]; T.py[1] = T.py[2]; T.py[2] = s;
+  s = T.pd[1]; T.pd[1] = T.pd[2]; T.pd[2] = s;
+  area = -area;
+  const float minx = fminf(T.px[0], fminf(T.px[1], T.px[2])), maxx = fmaxf(T.px[0], fmaxf(T.px[1], T.px[2]));
+  const float miny = fminf(T.py[0], fminf(T.py[1], T.py[2])), maxy = fmaxf(T.py[0], fmaxf(T.py[1], T.py[2]));
+  T.x0 = max(0, (int)floorf(minx - 0.5f)); T.x1 = min(W - 1, (int)ceilf(maxx - 0.5f));
+  T.y0 = max(0, (int)floorf(miny - 0.5f)); T.y1 = min(H - 1, (int)ceilf(maxy - 0.5f));
+  if (T.x0 > T.x1 || T.y0 > T.y1) return false;
+  T.inv_area = 1.0f / area;
+  return true;
+}
+
 // one coverage + depth sample: edge functions at the pixel centre, 1/depth interpolated in screen space, atomicMin on the key
-__device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int y, const float* px, const float* py, const float* pd, float inv_area,
-                                              int v, const DepthMap& dm) {
-  float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
-  float w0 = (px[2] - px[1]) * (sy - py[1]) - (py[2] - py[1]) * (sx - px[1]);
-  float w1 = (px[0] - px[2]) * (sy - py[2]) - (py[0] - py[2]) * (sx - px[2]);
-  float w2 = (px[1] - px[0]) * (sy - py[0]) - (py[1] - py[0]) * (sx - px[0]);
+__device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int y, const TriSetup& T, const DepthMap& dm) {
+  const float sx = (float)x + 0.5f, sy = (float)y + 0.5f;
+  const float w0 = (T.px[2] - T.px[1]) * (sy - T.py[1]) - (T.py[2] - T.py[1]) * (sx - T.px[1]);
+  const float w1 = (T.px[0] - T.px[2]) * (sy - T.py[2]) - (T.py[0] - T.py[2]) * (sx - T.px[2]);
+  const float w2 = (T.px[1] - T.px[0]) * (sy - T.py[0]) - (T.py[1] - T.py[0]) * (sx - T.px[0]);
   if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) return;
-  float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
+  const float inv = (w0 * T.pd[0] + w1 * T.pd[1] + w2 * T.pd[2]) * T.inv_area;
   if (!inv_depth_in_range(inv, dm)) return;
-  unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+  const unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)T.v;
   atomicMin(&zkey[y * W + x], key);
 }
 
-__global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
-                                                     int16_t* __restrict__ posseg) {
+// env_mask (nullable): only sub-scenes with env_mask[env] != 0 are rendered (re-render after a partial reset); the others keep
+// their previous picture.
+__global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
+                                                                    int16_t* __restrict__ posseg, const uint8_t* __restrict__ env_mask) {
   extern __shared__ unsigned zkey[];
-  __shared__ float vis_R[64][9];   // camera-from-visual rotation (row major)
-  __shared__ float vis_t[64][3];   // camera-from-visual translation
-  __shared__ float vis_Rw[64][9];  // world-from-visual rotation (lighting)
-  __shared__ float vis_sz[64][3];
-  __shared__ int vis_rect[64][4];  // conservative screen rectangle (x0, x1, y0, y1) of the ray-cast primitives
-  __shared__ int vis_kind[64];
-  __shared__ float vis_o[64][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
-  __shared__ float big_tri[B2S_MAX_BIG_TRIS][10];
-  __shared__ int big_box[B2S_MAX_BIG_TRIS][7];  // x0 y0 width count visual, walk step (x, y) of the unit that rasterises it
-  __shared__ int n_big;
-  if (threadIdx.x == 0) n_big = 0;
+  __shared__ RasterShared sh;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
+  if (env_mask && !env_mask[env]) return;
+  if (threadIdx.x == 0) sh.n_big = 0;
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
   const float nearp = R.cam_intr[6 * cam + 4], farp = R.cam_intr[6 * cam + 5];
   const DepthMap dm = depth_map(nearp, farp);
   const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
   const int npix = W * H;
-  for (int i = threadIdx.x; i < npix; i += blockDim.x) zkey[i] = 0xFFFFFFFFu;
-  // camera pose in the sub-scene frame
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) zkey[i] = B2S_NO_HIT;
+  // ---------------- stage 0: camera pose in the sub-scene frame, camera-from-visual transforms
   pose Xc = pmul(raster_body_pose(body_data, R.n_rows, env, R.cam_mount[cam]), pose7(R.cam_pose + 7 * cam));
   Xc.q = qnormalized(Xc.q);
-  m3 Rc = qmat(Xc.q);
-  const int nv = R.n_vis < 64 ? R.n_vis : 64;
+  const m3 Rc = qmat(Xc.q);
+  const int nv = R.n_vis < B2S_MAX_VIS ? R.n_vis : B2S_MAX_VIS;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) {
     float lp[7];
-    int ov = R.vis_ov[v];
+    const int ov = R.vis_ov[v];
     if (ov >= 0) {
       for (int k = 0; k < 7; k++) lp[k] = R.ov_pose[(size_t)(ov * 7 + k) * R.n_envs + env];
-      for (int k = 0; k < 3; k++) vis_sz[v][k] = R.ov_size[(size_t)(ov * 3 + k) * R.n_envs + env];
+      for (int k = 0; k < 3; k++) sh.vis_sz[v][k] = R.ov_size[(size_t)(ov * 3 + k) * R.n_envs + env];
     } else {
       for (int k = 0; k < 7; k++) lp[k] = R.vis_pose[7 * v + k];
-      for (int k = 0; k < 3; k++) vis_sz[v][k] = R.vis_size[3 * v + k];
+      for (int k = 0; k < 3; k++) sh.vis_sz[v][k] = R.vis_size[3 * v + k];
     }
     pose Xv = pmul(raster_body_pose(body_data, R.n_rows, env, R.vis_row[v]), pose7(lp));
     Xv.q = qnormalized(Xv.q);
-    m3 Rv = qmat(Xv.q);
-    m3 Rcv = mul(transpose(Rc), Rv);
-    v3 tcv = tmul(Rc, Xv.p - Xc.p);
-    for (int k = 0; k < 9; k++) { vis_R[v][k] = Rcv.m[k]; vis_Rw[v][k] = Rv.m[k]; }
-    vis_t[v][0] = tcv.x; vis_t[v][1] = tcv.y; vis_t[v][2] = tcv.z;
-    vis_o[v][0] = -(Rcv.m[0] * tcv.x + Rcv.m[3] * tcv.y + Rcv.m[6] * tcv.z);
-    vis_o[v][1] = -(Rcv.m[1] * tcv.x + Rcv.m[4] * tcv.y + Rcv.m[7] * tcv.z);
-    vis_o[v][2] = -(Rcv.m[2] * tcv.x + Rcv.m[5] * tcv.y + Rcv.m[8] * tcv.z);
+    const m3 Rv = qmat(Xv.q);
+    const m3 Rcv = mul(transpose(Rc), Rv);
+    const v3 tcv = tmul(Rc, Xv.p - Xc.p);
+    for (int k = 0; k < 9; k++) { sh.vis_R[v][k] = Rcv.m[k]; sh.vis_Rw[v][k] = Rv.m[k]; }
+    sh.vis_t[v][0] = tcv.x; sh.vis_t[v][1] = tcv.y; sh.vis_t[v][2] = tcv.z;
+    const float ox = -(Rcv.m[0] * tcv.x + Rcv.m[3] * tcv.y + Rcv.m[6] * tcv.z);
+    sh.vis_o[v][0] = ox;
+    sh.vis_o[v][1] = -(Rcv.m[1] * tcv.x + Rcv.m[4] * tcv.y + Rcv.m[7] * tcv.z);
+    sh.vis_o[v][2] = -(Rcv.m[2] * tcv.x + Rcv.m[5] * tcv.y + Rcv.m[8] * tcv.z);
+    const int ty = R.vis_type[v];
+    sh.vis_kind[v] = ty;
+    sh.vis_c[v] = (ty == SH_PLANE && ox > 0.0f) ? -1.0f / ox : 0.0f;
     // screen rectangle that surely contains the primitive (whole image when it reaches behind the near plane)
     int rx0 = 0, rx1 = W - 1, ry0 = 0, ry1 = H - 1;
-    int ty = R.vis_type[v];
-    vis_kind[v] = ty;
+    int mode = ty == SH_CONVEX ? VM_RASTER : VM_ANALYTIC;
     if (ty == SH_BOX || ty == SH_SPHERE) {
-      float hx = vis_sz[v][0], hy = ty == SH_BOX ? vis_sz[v][1] : vis_sz[v][0], hz = ty == SH_BOX ? vis_sz[v][2] : vis_sz[v][0];
+      const float hx = sh.vis_sz[v][0], hy = ty == SH_BOX ? sh.vis_sz[v][1] : sh.vis_sz[v][0], hz = ty == SH_BOX ? sh.vis_sz[v][2] : sh.vis_sz[v][0];
       float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
       bool behind = false;
       for (int c = 0; c < 8; c++) {
-        v3 l = mk3((c & 1) ? hx : -hx, (c & 2) ? hy : -hy, (c & 4) ? hz : -hz);
-        v3 pc = mul(Rcv, l) + tcv;
+        const v3 l = mk3((c & 1) ? hx : -hx, (c & 2) ? hy : -hy, (c & 4) ? hz : -hz);
+        const v3 pc = mul(Rcv, l) + tcv;
         if (pc.x <= nearp) { behind = true; break; }
-        float u = cx - fx * pc.y / pc.x, w = cy - fy * pc.z / pc.x;
+        const float u = cx - fx * pc.y / pc.x, w = cy - fy * pc.z / pc.x;
         mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w);
       }
       if (!behind) {
         rx0 = max(0, (int)floorf(mnx) - 1); rx1 = min(W - 1, (int)ceilf(mxx) + 1);
         ry0 = max(0, (int)floorf(mny) - 1); ry1 = min(H - 1, (int)ceilf(mxy) + 1);
+        if (ty == SH_BOX) mode = VM_RASTER;  // all eight corners in front of the near plane: its twelve triangles are rasterised
       }
     }
-    vis_rect[v][0] = rx0; vis_rect[v][1] = rx1; vis_rect[v][2] = ry0; vis_rect[v][3] = ry1;
+    sh.vis_mode[v] = mode;
+    sh.vis_rect[v][0] = rx0; sh.vis_rect[v][1] = rx1; sh.vis_rect[v][2] = ry0; sh.vis_rect[v][3] = ry1;
   }
   __syncthreads();
-  // ---------------- pass 1: rasterise hull triangles (camera frame: x forward, y left, z up)
-  for (int t = threadIdx.x; t < R.n_tri_total; t += blockDim.x) {
-    int v = R.tri_vis[t];
-    if (v >= nv) continue;
-    const float* tv = R.tri_verts + 9 * (size_t)t;
-    float px[3], py[3], pd[3];
-    bool ok = true;
-    for (int k = 0; k < 3; k++) {
-      v3 l = mk3(tv[3 * k], tv[3 * k + 1], tv[3 * k + 2]);
-      float xc = vis_R[v][0] * l.x + vis_R[v][1] * l.y + vis_R[v][2] * l.z + vis_t[v][0];
-      float yc = vis_R[v][3] * l.x + vis_R[v][4] * l.y + vis_R[v][5] * l.z + vis_t[v][1];
-      float zc = vis_R[v][6] * l.x + vis_R[v][7] * l.y + vis_R[v][8] * l.z + vis_t[v][2];
-      if (xc <= nearp) ok = false;
-      float inv = 1.0f / xc;
-      px[k] = cx - fx * yc * inv;
-      py[k] = cy - fy * zc * inv;
-      pd[k] = inv;
+  // ---------------- stage 1: project the vertices once
+  {
+    const int nc = R.n_vert < B2S_VERT_CACHE ? R.n_vert : B2S_VERT_CACHE;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) project_vertex(R, sh, i, fx, fy, cx, cy, nearp, sh.vert[i]);
+  }
+  __syncthreads();
+  // ---------------- stage 2: triangles (camera frame: x forward, y left, z up)
+  for (int t = threadIdx.x; t < R.n_tri; t += blockDim.x) {
+    TriSetup T;
+    if (!setup_triangle(R, sh, t, W, H, fx, fy, cx, cy, nearp, T)) continue;
+    const int cnt = (T.x1 - T.x0 + 1) * (T.y1 - T.y0 + 1);
+    if (cnt > B2S_BIG_TRI_PIXELS && t < 65536) {
+      // larger on-screen triangle: queued and rasterised by a whole warp (by the whole CTA when huge) so that the one-thread path
+      // stays short and balanced
+      const int slot = atomicAdd(&sh.n_big, 1);
+      if (slot < B2S_MAX_BIG_TRIS) { sh.big[slot] = (unsigned short)t; continue; }
     }
-    if (!ok) continue;  // triangles touching the near plane are dropped (robot links never get that close)
-    float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
-    // hull triangles are wound outwards (render.py build_visual_table): with screen x to the right and y down a front face has
-    // negative area; back faces are culled (hulls are closed: they are hidden by the front faces), front faces made counter-clockwise
-    if (!(area < 0.0f)) continue;
-    float tx = px[1]; px[1] = px[2]; px[2] = tx;
-    float ty = py[1]; py[1] = py[2]; py[2] = ty;
-    float td = pd[1]; pd[1] = pd[2]; pd[2] = td;
-    area = -area;
-    float minx = fminf(px[0], fminf(px[1], px[2])), maxx = fmaxf(px[0], fmaxf(px[1], px[2]));
-    float miny = fminf(py[0], fminf(py[1], py[2])), maxy = fmaxf(py[0], fmaxf(py[1], py[2]));
-    int x0 = max(0, (int)floorf(minx - 0.5f)), x1 = min(W - 1, (int)ceilf(maxx - 0.5f));
-    int y0 = max(0, (int)floorf(miny - 0.5f)), y1 = min(H - 1, (int)ceilf(maxy - 0.5f));
-    if (x0 > x1 || y0 > y1) continue;
-    float inv_area = 1.0f / area;
-    const int bw = x1 - x0 + 1, cnt = bw * (y1 - y0 + 1);
-    if (cnt > B2S_BIG_TRI_PIXELS) {
-      // larger on-screen triangle: queued and rasterised by a whole warp (by the whole CTA when huge: close-ups of the wrist camera)
-      // so that the one-thread path stays short and balanced
-      int slot = atomicAdd(&n_big, 1);
-      if (slot < B2S_MAX_BIG_TRIS) {
-        float* o = big_tri[slot];
-        o[0] = px[0]; o[1] = px[1]; o[2] = px[2]; o[3] = py[0]; o[4] = py[1]; o[5] = py[2];
-        o[6] = pd[0]; o[7] = pd[1]; o[8] = pd[2]; o[9] = inv_area;
-        const int stride = cnt > B2S_HUGE_TRI_PIXELS ? (int)blockDim.x : 32;  // pixels between two samples of one lane
-        const int sy_ = stride / bw;
-        big_box[slot][0] = x0; big_box[slot][1] = y0; big_box[slot][2] = bw; big_box[slot][3] = cnt; big_box[slot][4] = v;
-        big_box[slot][5] = stride - sy_ * bw; big_box[slot][6] = sy_;
-        continue;
-      }
-    }
-    for (int y = y0; y <= y1; y++)
-      for (int x = x0; x <= x1; x++) raster_sample(zkey, W, x, y, px, py, pd, inv_area, v, dm);
+    for (int y = T.y0; y <= T.y1; y++)
+      for (int x = T.x0; x <= T.x1; x++) raster_sample(zkey, W, x, y, T, dm);
   }
   __syncthreads();
   {
-    // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride`
-    // pixels, (xx, yy) follow incrementally with the precomputed (stride % width, stride / width)
-    const int nb = n_big < B2S_MAX_BIG_TRIS ? n_big : B2S_MAX_BIG_TRIS;
+    // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride` pixels
+    const int nb = sh.n_big < B2S_MAX_BIG_TRIS ? sh.n_big : B2S_MAX_BIG_TRIS;
     const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5, lane = threadIdx.x & 31;
     for (int pass = 0; pass < 2; pass++) {  // 0: warp-sized triangles, one warp each; 1: huge ones, all threads
       for (int b = pass == 0 ? warp : 0; b < nb; b += pass == 0 ? n_warp : 1) {
-        const int cnt = big_box[b][3];
+        TriSetup T;
+        if (!setup_triangle(R, sh, (int)sh.big[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+        const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
         if ((cnt > B2S_HUGE_TRI_PIXELS) != (pass == 1)) continue;
-        const float* o = big_tri[b];
-        const int x0 = big_box[b][0], y0 = big_box[b][1], bw = big_box[b][2], v = big_box[b][4], sx_ = big_box[b][5], sy_ = big_box[b][6];
         const int first = pass == 0 ? lane : (int)threadIdx.x, stride = pass == 0 ? 32 : (int)blockDim.x;
+        const int sy_ = stride / bw, sx_ = stride - sy_ * bw;
         int yy = first / bw, xx = first - yy * bw;
         for (int p = first; p < cnt; p += stride) {
-          raster_sample(zkey, W, x0 + xx, y0 + yy, o, o + 3, o + 6, o[9], v, dm);
+          raster_sample(zkey, W, T.x0 + xx, T.y0 + yy, T, dm);
           xx += sx_; yy += sy_;
           if (xx >= bw) { xx -= bw; yy++; }
         }
@@ -314,12 +365,11 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
     }
   }
   __syncthreads();
-  // ---------------- pass 2: per pixel analytic primitives + merge + shade + store
+  // ---------------- stage 3: per pixel analytic primitives + merge + shade + store
   uint8_t* cbase = color + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
   int16_t* pbase = posseg + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
-  // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel).  With W dividing blockDim the
-  // column of a thread is fixed, so the set of ray-cast primitives whose screen rectangle covers that column is one
-  // 64-bit mask computed once per column.
+  // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel).  With W dividing blockDim the column of a
+  // thread is fixed, so the set of analytic primitives whose screen rectangle covers that column is one 64-bit mask per column.
   int x = threadIdx.x % W, y = threadIdx.x / W;
   const int step_x = blockDim.x % W, step_y = blockDim.x / W;
   int mask_x = -1;
@@ -329,72 +379,83 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
     if (x != mask_x) {
       xmask = 0ull;
       for (int v = 0; v < nv; v++)
-        if (vis_kind[v] != SH_CONVEX && x >= vis_rect[v][0] && x <= vis_rect[v][1]) xmask |= 1ull << v;
+        if (sh.vis_mode[v] == VM_ANALYTIC && x >= sh.vis_rect[v][0] && x <= sh.vis_rect[v][1]) xmask |= 1ull << v;
       mask_x = x;
     }
-    float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
-    v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
-    float best = 1e30f;
-    int best_v = -1;
-    v3 best_n = mk3(0, 0, 0);  // world normal
-    unsigned k = zkey[i];
-    if (k != 0xFFFFFFFFu) {
-      best = key_depth(k >> 8, dm);
-      best_v = (int)(k & 255u);
-    }
-    bool raster_hit = best_v >= 0;
+    const float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
+    const v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
+    unsigned best = zkey[i];
     for (unsigned long long m = xmask; m != 0ull; m &= m - 1ull) {
       const int v = __ffsll((long long)m) - 1;
-      if (y < vis_rect[v][2] || y > vis_rect[v][3]) continue;
-      const int ty = vis_kind[v];
-      // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
-      v3 o = mk3(vis_o[v][0], vis_o[v][1], vis_o[v][2]);
-      v3 dl = mk3(vis_R[v][0] * rdir.x + vis_R[v][3] * rdir.y + vis_R[v][6] * rdir.z, vis_R[v][1] * rdir.x + vis_R[v][4] * rdir.y + vis_R[v][7] * rdir.z,
-                  vis_R[v][2] * rdir.x + vis_R[v][5] * rdir.y + vis_R[v][8] * rdir.z);
-      float th;
-      v3 nl;
-      bool hit = false;
-      if (ty == SH_BOX) hit = ray_box(o, dl, mk3(vis_sz[v][0], vis_sz[v][1], vis_sz[v][2]), th, nl);
-      else if (ty == SH_SPHERE) hit = ray_sphere(o, dl, vis_sz[v][0], th, nl);
-      else if (ty == SH_PLANE) {  // half-space, normal = +x of the visual frame
-        if (dl.x < -1e-9f && o.x > 0.0f) { th = -o.x / dl.x; nl = mk3(1, 0, 0); hit = true; }
+      if (y < sh.vis_rect[v][2] || y > sh.vis_rect[v][3]) continue;
+      const int ty = sh.vis_kind[v];
+      float inv = 0.0f;
+      if (ty == SH_PLANE) {  // half-space, normal = +x of the visual frame: 1/depth is linear in the ray direction
+        const float dlx = sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z;
+        if (dlx < -1e-9f) inv = dlx * sh.vis_c[v];
+      } else {
+        // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
+        const v3 o = mk3(sh.vis_o[v][0], sh.vis_o[v][1], sh.vis_o[v][2]);
+        const v3 dl = mk3(sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z,
+                          sh.vis_R[v][1] * rdir.x + sh.vis_R[v][4] * rdir.y + sh.vis_R[v][7] * rdir.z,
+                          sh.vis_R[v][2] * rdir.x + sh.vis_R[v][5] * rdir.y + sh.vis_R[v][8] * rdir.z);
+        float th = 0.0f;
+        bool hit = false;
+        if (ty == SH_BOX) hit = ray_box(o, dl, mk3(sh.vis_sz[v][0], sh.vis_sz[v][1], sh.vis_sz[v][2]), th);
+        else if (ty == SH_SPHERE) hit = ray_sphere(o, dl, sh.vis_sz[v][0], th);
+        if (hit) inv = 1.0f / th;
       }
-      if (hit && th > nearp && th < farp && th < best) {
-        best = th;
-        best_v = v;
-        raster_hit = false;
-        best_n = mk3(vis_Rw[v][0] * nl.x + vis_Rw[v][1] * nl.y + vis_Rw[v][2] * nl.z, vis_Rw[v][3] * nl.x + vis_Rw[v][4] * nl.y + vis_Rw[v][5] * nl.z,
-                     vis_Rw[v][6] * nl.x + vis_Rw[v][7] * nl.y + vis_Rw[v][8] * nl.z);
+      if (inv_depth_in_range(inv, dm)) {
+        const unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+        best = key < best ? key : best;
       }
     }
     uchar4 c4 = make_uchar4(0, 0, 0, 255);
     short4 p4 = make_short4(0, 0, 0, 0);
-    if (best_v >= 0) {
-      v3 pc = rdir * best;  // camera-frame hit point
-      if (raster_hit) {
+    if (best != B2S_NO_HIT) {
+      const int bv = (int)(best & 255u);
+      const float depth = key_depth(best >> 8, dm);
+      const v3 pc = rdir * depth;  // camera-frame hit point
+      const int ty = sh.vis_kind[bv];
+      v3 n_world;
+      if (ty == SH_CONVEX) {
         // screen-space normal from neighbouring depths of the same visual (flat-ish shading of hull faces)
-        int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
-        unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
+        const int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
+        const unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
         v3 n_cam = mk3(-1, 0, 0);
-        if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
-          float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
-          v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
-          v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
+        if (kx != B2S_NO_HIT && ky != B2S_NO_HIT && (int)(kx & 255u) == bv && (int)(ky & 255u) == bv) {
+          const float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
+          const v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
+          const v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
           v3 e1 = pxn - pc, e2 = pyn - pc;
           if (xn < x) e1 = -e1;
           if (yn < y) e2 = -e2;
-          v3 nn = cross(e2, e1);  // screen x runs to -y_cam, screen y to -z_cam: e2 x e1 faces the camera
-          float l = norm(nn);
+          const v3 nn = cross(e2, e1);  // screen x runs to -y_cam, screen y to -z_cam: e2 x e1 faces the camera
+          const float l = norm(nn);
           if (l > 1e-20f) n_cam = nn * (1.0f / l);
           if (n_cam.x > 0.0f) n_cam = -n_cam;
         }
-        best_n = mul(Rc, n_cam);
+        n_world = mul(Rc, n_cam);
+      } else {
+        v3 nl = mk3(1, 0, 0);  // half-space
+        if (ty != SH_PLANE) {
+          // hit point in the visual's frame: Rcv^T (pc - tcv)
+          const v3 dpc = mk3(pc.x - sh.vis_t[bv][0], pc.y - sh.vis_t[bv][1], pc.z - sh.vis_t[bv][2]);
+          const v3 pl = mk3(sh.vis_R[bv][0] * dpc.x + sh.vis_R[bv][3] * dpc.y + sh.vis_R[bv][6] * dpc.z,
+                            sh.vis_R[bv][1] * dpc.x + sh.vis_R[bv][4] * dpc.y + sh.vis_R[bv][7] * dpc.z,
+                            sh.vis_R[bv][2] * dpc.x + sh.vis_R[bv][5] * dpc.y + sh.vis_R[bv][8] * dpc.z);
+          if (ty == SH_BOX) nl = box_face_normal(pl, mk3(sh.vis_sz[bv][0], sh.vis_sz[bv][1], sh.vis_sz[bv][2]));
+          else nl = pl * (1.0f / sh.vis_sz[bv][0]);
+        }
+        n_world = mk3(sh.vis_Rw[bv][0] * nl.x + sh.vis_Rw[bv][1] * nl.y + sh.vis_Rw[bv][2] * nl.z,
+                      sh.vis_Rw[bv][3] * nl.x + sh.vis_Rw[bv][4] * nl.y + sh.vis_Rw[bv][5] * nl.z,
+                      sh.vis_Rw[bv][6] * nl.x + sh.vis_Rw[bv][7] * nl.y + sh.vis_Rw[bv][8] * nl.z);
       }
-      const float* col = R.vis_color + 4 * best_v;
-      v3 rgb = shade(mk3(col[0], col[1], col[2]), best_n);
-      c4 = make_uchar4(to_u8(rgb.x), to_u8(rgb.y), to_u8(rgb.z), 255);
+      const float* col = R.vis_color + 4 * bv;
+      const float w = shade_weight(n_world);
+      c4 = make_uchar4(to_u8(col[0] * w), to_u8(col[1] * w), to_u8(col[2] * w), 255);
       // OpenGL camera frame: x right = -y_cam, y up = z_cam, z backward = -x_cam
-      p4 = make_short4(to_mm(-pc.y), to_mm(pc.z), to_mm(-pc.x), (short)R.vis_seg[best_v]);
+      p4 = make_short4(to_mm(-pc.y), to_mm(pc.z), to_mm(-pc.x), (short)R.vis_seg[bv]);
     }
     *reinterpret_cast<uchar4*>(cbase + (size_t)i * 4) = c4;
     *reinterpret_cast<short4*>(pbase + (size_t)i * 4) = p4;
@@ -405,7 +466,7 @@ __global__ void __launch_bounds__(512) raster_kernel(RasterModel R, const float*
 
 const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& host, const B2SCameraDesc* cams, int n_cam,
                           const B2SVisualTable* vis, RasterGroup** out, B2SRenderTargets* targets);
-const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, cudaStream_t st);
+const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st);
 void raster_destroy(RasterGroup* g);
 
 }  // namespace b2s

@@ -155,7 +155,7 @@ class BaseEnv:
         self._reward_mode = self.SUPPORTED_REWARD_MODES[0] if reward_mode is None else reward_mode   # sapien_env.py:300-304
         if self._reward_mode not in self.SUPPORTED_REWARD_MODES:
             raise NotImplementedError(f"Unsupported reward mode: {self._reward_mode}")
-        self.sim_params = SimParams(**(sim_config or {}))
+        self.sim_params = SimParams.from_config(sim_config)
         self._sim_freq, self._control_freq = self.sim_params.sim_freq, self.sim_params.control_freq
         if self._sim_freq % self._control_freq != 0:
             raise ValueError("sim_freq must be divisible by control_freq")  # sapien_env.py:279-283 warns; we are strict
@@ -348,6 +348,8 @@ class BaseEnv:
         else:
             self._set_episode_rng(seed, env_idx)
         self._state_version += 1  # invalidates per-state caches of derived poses (tasks may memoise them between fetches)
+        if len(env_idx) == self.num_envs and hasattr(self.scene.world, "check_overflow"):
+            self.scene.world.check_overflow()   # full resets are off the per-step path: report dropped contacts / rows loudly here
         self.scene._reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.scene._reset_mask[env_idx] = True
         self.scene._reset_all = False
@@ -418,15 +420,84 @@ class BaseEnv:
                 raise TypeError(type(action))
             action = action.to(device=self.device, dtype=torch.float32)
             if action.shape == (self.action_dim,):
-                action = action[None]
+                action = action[None].expand(self.num_envs, self.action_dim)   # the torch path broadcasts one action over the sub-scenes
+            if tuple(action.shape) != (self.num_envs, self.action_dim):
+                # the controller kernel reads actions[env * n_action + col] for every sub-scene: a wrong shape would read out of bounds
+                raise ValueError(f"action must have shape {(self.num_envs, self.action_dim)} (or {(self.action_dim,)}), got {tuple(action.shape)}")
             action = action.contiguous()
+        self.scene._gpu_apply_all()   # pending setter writes (set_qpos, set_pose, ...) reach the simulation state before the step
         f = self._fused
         self.scene.world.pick_task_step(f["handle"], action, self._sim_steps_per_control, f["obs"], f["reward"], f["flags"], self._elapsed_steps)
-        fl = f["flags"]
+        self._state_version += 1
+        # Like the torch path and the reference, every step hands out FRESH tensors: one clone of the packed outputs; the views below
+        # share that clone, not the persistent kernel output buffers (which the next step overwrites).
+        fl = f["flags"].clone()
+        vec = f["obs"].clone()
         info = dict(elapsed_steps=self._elapsed_steps.clone(), success=fl[:, 0], is_obj_placed=fl[:, 1], is_robot_static=fl[:, 2], is_grasped=fl[:, 3])
-        obs = f["obs"] if self._obs_mode == "state" else self._visual_obs_from_fused(f["obs"], info)
+        obs = vec if self._obs_mode == "state" else self._visual_obs_from_fused(vec, info)
         self._last_obs = obs
-        return obs, f["reward"], fl[:, 4].clone(), torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+        return obs, f["reward"].clone(), fl[:, 4], torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+
+    def supports_device_autoreset(self) -> bool:
+        """True when `step_autoreset` is available: the fused control step is active and the task registered its episode
+        initialisation with the backend."""
+        return self._fused is not None and bool(self._fused.get("autoreset"))
+
+    def enable_time_limit(self, max_episode_steps: int) -> bool:
+        """The TimeLimit the vector wrapper enforces (registration.py:160-168), handed to the device-side auto-reset."""
+        if not self.supports_device_autoreset():
+            return False
+        self._fused["max_episode_steps"] = int(max_episode_steps)
+        return True
+
+    def step_autoreset(self, action, ignore_terminations: bool = False):
+        """`ManiSkillVectorEnv.step` for the fused task family with the auto-reset done on the device (include/b200sim.h
+        b2s_pick_task_autoreset): no `dones.any()` host sync, no python-side partial reset.  Returns
+        (obs, reward, terminated, truncated, info) where info always carries `final_info`, `final_observation` and the masks
+        `_final_info` / `_final_observation` / `_elapsed_steps` (= done; all-false on steps where nothing finished -- the reference adds
+        the keys only on such steps, which needs the host to look at `dones`).  Un-seeded resets draw from the torch CUDA generator."""
+        if action is not None:
+            if isinstance(action, np.ndarray):
+                action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+            elif not isinstance(action, torch.Tensor):
+                raise TypeError(type(action))
+            action = action.to(device=self.device, dtype=torch.float32)
+            if action.shape == (self.action_dim,):
+                action = action[None].expand(self.num_envs, self.action_dim)
+            if tuple(action.shape) != (self.num_envs, self.action_dim):
+                raise ValueError(f"action must have shape {(self.num_envs, self.action_dim)} (or {(self.action_dim,)}), got {tuple(action.shape)}")
+            action = action.contiguous()
+        f = self._fused
+        w = self.scene.world
+        self.scene._gpu_apply_all()
+        w.pick_task_step(f["handle"], action, self._sim_steps_per_control, f["obs"], f["reward"], f["flags"], self._elapsed_steps)
+        self._state_version += 1
+        visual = self._obs_mode != "state"
+        if visual:
+            self._sensors.capture()                      # the finished state, for final_observation
+        rew = f["reward"].clone()
+        elapsed = self._elapsed_steps.clone()
+        rand = torch.rand((self.num_envs, 24), dtype=torch.float32, device=self.device)
+        w.pick_task_autoreset(f["handle"], f["obs"], f["reward"], f["flags"], self._elapsed_steps, rand, f["final_obs"], f["done"], ignore_terminations,
+                              f.get("max_episode_steps", 0))
+        fl = f["flags"].clone()      # the finished step's flags, with the time-limit truncation the reset kernel decided
+        done = f["done"].clone()
+        if visual:
+            self._sensors.keep_final(f["done"])          # pictures of the finished sub-scenes -> final buffers (masked copy)
+            self._sensors.capture(env_mask=f["done"])    # re-render only what was reset
+        vec = f["obs"].clone()
+        final_vec = f["final_obs"].clone()
+        info = dict(elapsed_steps=self._elapsed_steps.clone(), success=fl[:, 0], is_obj_placed=fl[:, 1], is_robot_static=fl[:, 2], is_grasped=fl[:, 3])
+        final_info = dict(elapsed_steps=elapsed, success=fl[:, 0], is_obj_placed=fl[:, 1], is_robot_static=fl[:, 2], is_grasped=fl[:, 3])
+        if visual:
+            obs = self._visual_obs_from_fused(vec, info, render=False)
+            final_obs = self._visual_obs_from_fused(final_vec, final_info, render=False, final=True)
+        else:
+            obs, final_obs = vec, final_vec
+        info.update(final_info=final_info, final_observation=final_obs, _final_info=done, _final_observation=done, _elapsed_steps=done)
+        self._last_obs = obs
+        terminated = torch.zeros_like(fl[:, 4]) if ignore_terminations else fl[:, 4]
+        return obs, rew, terminated, fl[:, 5], info
 
     def _step_action(self, action):
         if action is not None:
@@ -499,20 +570,21 @@ class BaseEnv:
             obs["state"] = U.flatten_state_dict(dict(agent=obs.pop("agent"), extra=obs.pop("extra")))
         return obs
 
-    def _add_sensor_obs(self, obs):
+    def _add_sensor_obs(self, obs, render: bool = True, final: bool = False):
         """sapien_env.py:525-532: camera parameters + the requested textures, as a point cloud under obs mode "pointcloud"."""
         obs["sensor_param"] = self.get_sensor_params()
-        obs["sensor_data"] = self._get_obs_sensor_data()
+        obs["sensor_data"] = self._get_obs_sensor_data(render=render, final=final)
         return sensor_data_to_pointcloud(obs) if self.obs_mode_struct.pointcloud else obs
 
-    def _visual_obs_from_fused(self, vec, info):
+    def _visual_obs_from_fused(self, vec, info, render: bool = True, final: bool = False):
         """Visual-mode observation (same structure as `get_obs`) with the agent / extra entries -- or, under the `state` flag, the flat
-        state vector that replaces them -- taken from the fused state vector."""
+        state vector that replaces them -- taken from the fused state vector.  render=False: the pictures are already taken;
+        final=True: the pictures kept for the finished sub-scenes (`CameraSensors.keep_final`)."""
         if self.obs_mode_struct.state:
-            obs = self._add_sensor_obs(dict())
+            obs = self._add_sensor_obs(dict(), render=render, final=final)
             obs["state"] = vec
             return obs
-        return self._add_sensor_obs(self._obs_from_fused(vec, info))
+        return self._add_sensor_obs(self._obs_from_fused(vec, info), render=render, final=final)
 
     def _sensor_configs(self):
         """task hook: list of dict(uid, pose(7), width, height, fov, near, far, mount(link/actor name or None))."""
@@ -534,12 +606,13 @@ class BaseEnv:
             raise NotImplementedError("this task defines no sensor cameras")
         return CameraSensors(self.scene.world, self.cm, cams)
 
-    def _get_obs_sensor_data(self):
+    def _get_obs_sensor_data(self, render: bool = True, final: bool = False):
         """sapien_env.py:578-625: hidden objects are simply absent from the sensor render-shape table (the reference
         teleports them away and back, actor.py:176-201), then update_render + take_picture on the camera group."""
-        self._sensors.capture()
+        if render:
+            self._sensors.capture()
         m = self.obs_mode_struct
-        return self._sensors.get_obs(rgb=m.rgb, depth=m.depth, segmentation=m.segmentation, position=m.position)
+        return self._sensors.get_obs(rgb=m.rgb, depth=m.depth, segmentation=m.segmentation, position=m.position, final=final)
 
     # ------------------------------------------------------------------ render modes (sapien_env.py:1369-1439)
     def _human_render_camera_configs(self):

@@ -70,8 +70,17 @@ class PickCubeEnv(PandaTabletopEnv):
         if self._reward_mode not in ("normalized_dense", "dense"):
             return None
         N = self.num_envs
-        return dict(handle=handle, obs=torch.zeros((N, 2 * nd + 24), dtype=torch.float32, device=self.device),
-                    reward=torch.zeros(N, dtype=torch.float32, device=self.device), flags=torch.zeros((N, 6), dtype=torch.bool, device=self.device))
+        fused = dict(handle=handle, obs=torch.zeros((N, 2 * nd + 24), dtype=torch.float32, device=self.device),
+                     reward=torch.zeros(N, dtype=torch.float32, device=self.device), flags=torch.zeros((N, 6), dtype=torch.bool, device=self.device))
+        # episode initialisation for the device-side auto-reset (b2s_pick_task_autoreset): what `_initialize_episode` below draws, as
+        # parameters; only when this class's own initialisation is in effect (subclasses that override it keep the python reset)
+        if type(self)._initialize_episode is PickCubeEnv._initialize_episode and not self._enhanced_determinism:
+            from .tabletop import REST_QPOS
+            w.set_pick_reset(handle, self.cube_spawn_half_size, self.cube_spawn_center, self.cube_half_size, self.max_goal_height,
+                             self.robot_init_qpos_noise, REST_QPOS[self.robot_uids], self.cube.fb_index, self.goal_site.fb_index)
+            fused.update(autoreset=True, final_obs=torch.zeros((N, 2 * nd + 24), dtype=torch.float32, device=self.device),
+                         done=torch.zeros(N, dtype=torch.bool, device=self.device))
+        return fused
 
     # ---- pick_cube.py:66-71
     def _sensor_configs(self):

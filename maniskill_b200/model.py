@@ -299,6 +299,34 @@ class SimParams:
     margin_min: float = 0.005
     max_joint_velocity: float = 100.0   # PxArticulationJointReducedCoordinate maxJointVelocity default (rad/s | m/s); 0 = unlimited
 
+    @classmethod
+    def from_config(cls, cfg=None) -> "SimParams":
+        """Accepts what the reference's tasks pass as `sim_config` / `_default_sim_config` (mani_skill/utils/structs/types.py:78-97): a
+        flat dict of this class's fields, or the nested `SimConfig` layout -- `scene_config` (SceneConfig: gravity, contact_offset,
+        rest_offset, solver_position_iterations, solver_velocity_iterations, ...), `default_materials_config` (static_friction) and
+        `gpu_memory_config` (PhysX buffer capacities, which have no counterpart here: the per-sub-scene capacities are `max_contacts` /
+        `max_manifolds`) -- as dicts or dataclass instances.  Unknown keys are ignored like dacite's non-strict mode would; a key that is
+        known but not honoured by this backend (enable_ccd, enable_tgs=False, ...) is kept out silently as well."""
+        import dataclasses
+        if cfg is None:
+            return cls()
+        if isinstance(cfg, cls):
+            return cfg
+        if dataclasses.is_dataclass(cfg):
+            cfg = dataclasses.asdict(cfg)
+        flat = {}
+        names = {f.name for f in dataclasses.fields(cls)}
+        for k, v in dict(cfg).items():
+            if dataclasses.is_dataclass(v):
+                v = dataclasses.asdict(v)
+            if k in ("scene_config", "default_materials_config", "gpu_memory_config") and isinstance(v, dict):
+                for kk, vv in v.items():
+                    if kk in names:
+                        flat[kk] = vv
+            elif k in names:
+                flat[k] = v
+        return cls(**flat)
+
 
 class CompiledModel:
     """Flat tables + name maps. ``struct()`` gives a ctypes B2SModel whose pointers alias arrays kept alive here."""

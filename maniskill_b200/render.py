@@ -12,7 +12,13 @@ from typing import Dict, List
 import numpy as np
 import torch
 
-from .model import SHAPE_CONVEX, CompiledModel
+from .model import SHAPE_BOX, SHAPE_CONVEX, CompiledModel
+
+
+# corners of the unit cube (x fastest) and its twelve triangles
+_UNIT_CUBE_VERTS = np.array([[(1 if c & 1 else -1), (1 if c & 2 else -1), (1 if c & 4 else -1)] for c in range(8)], dtype=np.float64)
+_UNIT_CUBE_TRIS = np.array([[0, 1, 3], [0, 3, 2], [4, 5, 7], [4, 7, 6], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
+                            [1, 3, 7], [1, 7, 5]], dtype=np.int64)
 
 
 def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = False) -> Dict[str, np.ndarray]:
@@ -21,7 +27,7 @@ def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = Fa
     hull_verts = cm.arrays["hull_verts"].reshape(-1, 3)
     types, rows, poses, sizes, colors, segs, ov_slot = [], [], [], [], [], [], []
     ov_size, ov_pose = [], []
-    tri_vis, tri_verts = [], []
+    vert_local, vert_vis, tri_idx, tri_vis = [], [], [], []
     for i, v in enumerate(vis):
         types.append(v["type"]); rows.append(v["row"]); poses.append(v["pose"]); sizes.append(v["size"])
         colors.append(v["color"]); segs.append(v["seg"])
@@ -31,25 +37,37 @@ def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = Fa
             ov_pose.append(np.asarray(v["per_env_pose"] if v["per_env_pose"] is not None else np.tile(v["pose"], (n_envs, 1)), dtype=np.float32))
         else:
             ov_slot.append(-1)
+        # indexed triangle geometry of the visuals the rasteriser draws as meshes: hulls (their vertices) and boxes (the corners of the
+        # unit cube; the kernel scales them by the -- possibly per-env -- half extents)
         if v["type"] == SHAPE_CONVEX:
             h = v["hull"]
-            verts = hull_verts[hull_off[h]:hull_off[h + 1]]
-            tris = cm.hull_tris[h]
-            tv = verts[tris].astype(np.float64)  # [n_tri, 3, 3]
-            # outward winding (normal away from the hull centre): the rasteriser culls back faces by the sign of the screen area
-            nrm = np.cross(tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0])
-            inward = np.einsum("ij,ij->i", nrm, tv.mean(1) - verts.mean(0)) < 0
-            tv[inward] = tv[inward][:, [0, 2, 1]]
-            tri_verts.append(tv.astype(np.float32).reshape(-1, 9))
-            tri_vis.extend([i] * len(tris))
+            verts = hull_verts[hull_off[h]:hull_off[h + 1]].astype(np.float64)
+            tris = np.asarray(cm.hull_tris[h], dtype=np.int64)
+        elif v["type"] == SHAPE_BOX:
+            verts, tris = _UNIT_CUBE_VERTS, _UNIT_CUBE_TRIS
+        else:
+            continue
+        tv = verts[tris]  # [n_tri, 3, 3]
+        # outward winding (normal away from the solid's centre): the rasteriser culls back faces by the sign of the screen area
+        nrm = np.cross(tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0])
+        inward = np.einsum("ij,ij->i", nrm, tv.mean(1) - verts.mean(0)) < 0
+        tris = tris.copy()
+        tris[inward] = tris[inward][:, [0, 2, 1]]
+        base = len(vert_vis)
+        vert_local.append(verts.astype(np.float32))
+        vert_vis.extend([i] * len(verts))
+        tri_idx.append((tris + base).astype(np.int32))
+        tri_vis.extend([i] * len(tris))
     f32 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(shape))
     n = len(vis)
     return dict(
-        n_visual=n, n_ov=len(ov_size), n_tri=len(tri_vis),
+        n_visual=n, n_ov=len(ov_size), n_vert=len(vert_vis), n_tri=len(tri_vis),
         type=np.asarray(types, dtype=np.int32), row=np.asarray(rows, dtype=np.int32), pose=f32(poses, (-1,)), size=f32(sizes, (-1,)),
         color=f32(colors, (-1,)), seg_id=np.asarray(segs, dtype=np.int32), ov_slot=np.asarray(ov_slot, dtype=np.int32),
         ov_size=f32(np.stack(ov_size, 1) if ov_size else np.zeros(0), (-1,)), ov_pose=f32(np.stack(ov_pose, 1) if ov_pose else np.zeros(0), (-1,)),
-        tri_vis=np.asarray(tri_vis, dtype=np.int32), tri_verts=f32(np.concatenate(tri_verts) if tri_verts else np.zeros(0), (-1,)),
+        vert_local=f32(np.concatenate(vert_local) if vert_local else np.zeros(0), (-1,)), vert_vis=np.asarray(vert_vis, dtype=np.int32),
+        tri_idx=np.ascontiguousarray(np.concatenate(tri_idx).reshape(-1) if tri_idx else np.zeros(0, dtype=np.int32), dtype=np.int32),
+        tri_vis=np.asarray(tri_vis, dtype=np.int32),
     )
 
 
@@ -72,18 +90,31 @@ class CameraSensors:
         self.visuals = build_visual_table(cm, world.n_envs, include_hidden=include_hidden)
         self.group = world.create_camera_group(cams, self.visuals)
 
-    def capture(self):
-        self.group.take_picture()
+    def capture(self, env_mask=None):
+        """take_picture(); env_mask ([N] bool / uint8 on the device): only those sub-scenes are rendered again."""
+        if env_mask is None:
+            self.group.take_picture()
+        else:
+            self.world.render(self.group, env_mask)
 
-    def get_obs(self, rgb=True, depth=True, segmentation=True, position=False):
+    def keep_final(self, env_mask):
+        """Copies the current pictures of the masked sub-scenes into the `final` render targets (what `final_observation` shows after an
+        auto-reset re-rendered them); rows of other sub-scenes keep whatever they held."""
+        g = self.group
+        if getattr(g, "_final_color", None) is None:
+            g._final_color, g._final_posseg = torch.zeros_like(g._color), torch.zeros_like(g._posseg)
+        self.world.masked_copy(g._final_color, g._color, env_mask)
+        self.world.masked_copy(g._final_posseg, g._posseg, env_mask)
+
+    def get_obs(self, rgb=True, depth=True, segmentation=True, position=False, final=False):
         """sensor_data[uid] = {rgb [N,H,W,3] uint8, depth [N,H,W,1] int16 (mm), segmentation [N,H,W,1] int16}
-        (texture_transforms of the minimal shader pack, mani_skill/render/shaders.py:74-83)."""
+        (texture_transforms of the minimal shader pack, mani_skill/render/shaders.py:74-83).  final=True reads the targets `keep_final` filled."""
         out = {}
         for i, c in enumerate(self.cams):
             d = {}
             if rgb:
-                d["rgb"] = self.group.get_picture_cuda("Color", i)[..., :3]
-            ps = self.group.get_picture_cuda("PositionSegmentation", i)
+                d["rgb"] = self.group.get_picture_cuda("Color", i, final=final)[..., :3]
+            ps = self.group.get_picture_cuda("PositionSegmentation", i, final=final)
             if depth:
                 d["depth"] = -ps[..., 2:3]  # strided elementwise negation; a slice, not a gather
             if position:

@@ -34,8 +34,9 @@ def _to_numpy(x):
     if isinstance(x, dict):
         return {k: _to_numpy(v) for k, v in x.items()}
     if isinstance(x, torch.Tensor):
-        return x.detach().cpu().numpy()
-    return np.asarray(x)
+        x = x.detach()
+        return x.cpu().numpy() if x.is_cuda else x.numpy().copy()   # never alias a caller-owned CPU buffer
+    return np.array(x, copy=True)
 
 
 def _index(x, idx):
@@ -91,7 +92,7 @@ class RecordEpisode:
         os.makedirs(output_dir, exist_ok=True)
         self._stem = os.path.join(output_dir, trajectory_name)
         self._episode_id = -1
-        self._arrays: Dict[str, np.ndarray] = {}       # path -> dataset, npz fallback
+        self._npz_started = False                      # npz fallback: datasets are appended to the zip at each flush
         self._h5 = h5py.File(self._stem + ".h5", "w") if (h5py is not None and save_trajectory) else None
         from .registration import REGISTERED_ENVS
         if env_id is None:
@@ -239,15 +240,23 @@ class RecordEpisode:
                 big = path.rsplit("/", 1)[-1] in ("rgb", "depth", "seg")
                 self._h5.create_dataset(path, data=arr, **(dict(compression="gzip", compression_opts=5) if big else {}))
         else:
-            self._arrays.update(flat)
+            # `.npz` container (h5py missing): one zip member per dataset, appended at each flush and dropped from memory -- O(1) work and
+            # host RAM per flushed episode, readable with np.load like a file written by np.savez_compressed
+            import zipfile
+            with zipfile.ZipFile(self._stem + ".npz", "a" if self._npz_started else "w", zipfile.ZIP_DEFLATED, allowZip64=True) as zf:
+                for path, arr in flat.items():
+                    with zf.open(path + ".npy", "w", force_zip64=True) as member:
+                        np.lib.format.write_array(member, np.asanyarray(arr), allow_pickle=False)
+            self._npz_started = True
 
     def _dump(self):
         with open(self._stem + ".json", "w") as f:
             json.dump(self._json, f, indent=2)
         if self._h5 is not None:  # pragma: no cover
             self._h5.flush()
-        else:
-            np.savez_compressed(self._stem + ".npz", **self._arrays)
+        elif not self._npz_started:   # nothing flushed yet: still leave a (valid, empty) container next to the json
+            np.savez_compressed(self._stem + ".npz")
+            self._npz_started = True
 
     def close(self):
         if self.save_video and self.save_on_reset:

@@ -8,9 +8,16 @@ from typing import Optional
 import torch
 
 
+def _clone_tree(x):
+    """Deep clone of a tensor / nested dict of tensors (mani_skill/utils/common.py `torch_clone_dict`)."""
+    if isinstance(x, dict):
+        return {k: _clone_tree(v) for k, v in x.items()}
+    return x.clone() if isinstance(x, torch.Tensor) else x
+
+
 class ManiSkillVectorEnv:
     def __init__(self, env, auto_reset: bool = True, ignore_terminations: bool = False, max_episode_steps: Optional[int] = None,
-                 record_metrics: bool = False):
+                 record_metrics: bool = False, device_autoreset: Optional[bool] = None):
         self._env = env
         self.num_envs = env.num_envs
         self.auto_reset = auto_reset
@@ -23,6 +30,11 @@ class ManiSkillVectorEnv:
             self.success_once = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
             self.fail_once = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
             self.returns = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        # Device-side auto-reset (b2s_pick_task_autoreset) when the env offers it for this configuration; `device_autoreset=False` keeps
+        # the reference's python flow (gymnasium.py:160-176), which is also what every other task uses.
+        self._device_autoreset = bool(device_autoreset if device_autoreset is not None else True) and auto_reset and not record_metrics \
+            and hasattr(env, "supports_device_autoreset") and env.supports_device_autoreset() \
+            and self.max_episode_steps is not None and env.enable_time_limit(self.max_episode_steps)
 
     @property
     def base_env(self):
@@ -56,6 +68,9 @@ class ManiSkillVectorEnv:
         return stats
 
     def step(self, actions):
+        if self._device_autoreset:
+            # the whole of what follows (time limit, dones, final_info / final_observation, partial reset) on the device, no host sync
+            return self._env.step_autoreset(actions, ignore_terminations=self.ignore_terminations)
         obs, rew, terminations, truncations, infos = self._env.step(actions)
         if self.max_episode_steps is not None:
             # TimeLimitWrapper.step (registration.py:160-168)
@@ -71,10 +86,9 @@ class ManiSkillVectorEnv:
             infos["episode"] = stats
         dones = torch.logical_or(terminations, truncations)
         if dones.any() and self.auto_reset:
-            final_obs = obs if isinstance(obs, dict) else obs.clone()
+            final_obs = _clone_tree(obs)   # gymnasium.py:165 `torch_clone_dict(obs)`: image entries alias the render targets the reset re-renders
             env_idx = torch.arange(0, self.num_envs, device=self.device)[dones]
-            final_info = {k: (v.clone() if isinstance(v, torch.Tensor) else ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v))
-                          for k, v in infos.items()}
+            final_info = _clone_tree(infos)
             obs, infos = self.reset(options=dict(env_idx=env_idx))
             infos["final_info"] = final_info
             infos["_final_info"] = dones

@@ -6,10 +6,13 @@
 // SAPIEN's renderer is not in /root/reference and cannot run here, and the reference ships no reference images or
 // masks: PARITY UNPINNED for absolute pixel values.  What this oracle pins is the CUDA rasteriser's own definition:
 //   * pinhole camera, sapien camera frame (x forward, y left, z up), pixel centres at (u + 0.5, v + 0.5), v = 0 at the top
-//   * convex-hull visuals: triangles projected to the screen, sample inside iff the three edge functions are >= 0 after
-//     orienting the triangle counter-clockwise, 1/depth interpolated linearly in screen space, depth quantised to a
-//     24-bit reversed-z key; nearest key wins, ties broken by the lower visual index
-//   * boxes / spheres / half-spaces: analytic ray tests per pixel, a primitive wins only if strictly nearer
+//   * convex hulls, and boxes whose eight corners are in front of the near plane, are triangle meshes: vertices projected to the
+//     screen, sample inside iff the three edge functions are >= 0 after orienting the triangle counter-clockwise, 1/depth
+//     interpolated linearly in screen space, quantised to a 24-bit reversed-z key; back faces culled
+//   * half-spaces, spheres and the remaining boxes are analytic: per pixel they produce a key of the same form (half-space: 1/depth
+//     linear in the ray direction, no division; sphere / box: 1 / ray parameter)
+//   * the smallest (key << 8 | visual index) wins, depth = 1 / dequantised(1/depth); normals: box face nearest to the hit point,
+//     half-space normal, sphere radius, hulls from the depth neighbourhood
 //   * segmentation = per_scene_id of the winning visual, 0 = background; position = hit point in mm (round to nearest even)
 // Plain loops, float32, compiled with -ffp-contract=off; the CUDA translation unit is compiled with -fmad=false, so the
 // integer outputs (segmentation, position) are expected to agree bit for bit.
@@ -107,10 +110,8 @@ inline float key_depth(unsigned k, const DepthMap& m) {
   float inv = m.invf + t * m.range;
   return 1.0f / inv;
 }
-inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, F3& n_local) {
+inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit) {
   float tmin = -1e30f, tmax = 1e30f;
-  int axis = 0;
-  float sgn = 1.0f;
   float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
   for (int k = 0; k < 3; k++) {
     if (fabsf(dd[k]) < 1e-12f) {
@@ -118,26 +119,33 @@ inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, F3& n_local) {
     } else {
       float inv = 1.0f / dd[k];
       float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
-      float s = -1.0f;
-      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; s = 1.0f; }
-      if (t0 > tmin) { tmin = t0; axis = k; sgn = s; }
+      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
+      if (t0 > tmin) tmin = t0;
       if (t1 < tmax) tmax = t1;
     }
   }
   if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
   t_hit = tmin;
-  n_local = f3(axis == 0 ? sgn : 0.0f, axis == 1 ? sgn : 0.0f, axis == 2 ? sgn : 0.0f);
   return true;
 }
-inline bool ray_sphere(F3 o, F3 dv, float r, float& t_hit, F3& n_local) {
+inline bool ray_sphere(F3 o, F3 dv, float r, float& t_hit) {
   float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
   float disc = b * b - a * c;
   if (disc < 0.0f) return false;
   float t = (-b - sqrtf(disc)) / a;
   if (t <= 0.0f) return false;
   t_hit = t;
-  n_local = (o + dv * t) * (1.0f / r);
   return true;
+}
+inline F3 box_face_normal(F3 pl, F3 h) {
+  float d0 = fabsf(pl.x) - h.x, d1 = fabsf(pl.y) - h.y, d2 = fabsf(pl.z) - h.z;
+  int axis = 0;
+  float best = d0;
+  if (d1 > best) { best = d1; axis = 1; }
+  if (d2 > best) { best = d2; axis = 2; }
+  float c = axis == 0 ? pl.x : (axis == 1 ? pl.y : pl.z);
+  float s = c >= 0.0f ? 1.0f : -1.0f;
+  return f3(axis == 0 ? s : 0.0f, axis == 1 ? s : 0.0f, axis == 2 ? s : 0.0f);
 }
 inline uint8_t to_u8(float x) {
   float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
@@ -157,17 +165,19 @@ extern "C" {
 
 // Renders one camera of one sub-scene.
 //   vis_*: render-shape table (same arrays the C-ABI B2SVisualTable carries); per-env size/pose already resolved by the caller
+//   vert_* / tri_*: indexed triangle geometry of the hull and box visuals (box vertices = corners of the unit cube)
 //   body:  [n_rows*13] float32 rows of this sub-scene
 //   cam:   w h fx fy cx cy near far mount_row local_pose(7)  as 16 floats
 //   out:   color [h*w*4] uint8, posseg [h*w*4] int16
 void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const float* vis_pose, const float* vis_size,
-                    const float* vis_color, const int* vis_seg, int n_tri, const int* tri_vis, const float* tri_verts,
-                    int n_rows, const float* body, const float* cam, uint8_t* color, int16_t* posseg) {
+                    const float* vis_color, const int* vis_seg, int n_vert, const float* vert_local, const int* vert_vis, int n_tri,
+                    const int* tri_idx, const int* tri_vis, int n_rows, const float* body, const float* cam, uint8_t* color, int16_t* posseg) {
   const int W = (int)cam[0], H = (int)cam[1];
   const float fx = cam[2], fy = cam[3], cx = cam[4], cy = cam[5], nearp = cam[6], farp = cam[7];
   const DepthMap dm = depth_map(nearp, farp);
   const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
   const int mount = (int)cam[8];
+  const unsigned NO_HIT = 0xFFFFFFFFu;
   auto body_pose = [&](int row) {
     if (row < 0) return ident();
     return p7(body + (size_t)row * 13);
@@ -176,42 +186,68 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
   Xc.q = qnorm(Xc.q);
   float Rc[9];
   qmat(Xc.q, Rc);
-  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vRw(n_vis * 9);
+  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vRw(n_vis * 9), vo(n_vis * 3), vc(n_vis, 0.0f);
+  std::vector<int> vmode(n_vis, 1);  // 0 rasterised, 1 analytic
   for (int v = 0; v < n_vis; v++) {
     P7 Xv = pmul(body_pose(vis_row[v]), p7(vis_pose + 7 * v));
     Xv.q = qnorm(Xv.q);
     float Rv[9];
     qmat(Xv.q, Rv);
+    float* Rm = &vR[v * 9];
     // Rcv = Rc^T Rv
     for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) vR[v * 9 + 3 * i + j] = Rc[i] * Rv[j] + Rc[3 + i] * Rv[3 + j] + Rc[6 + i] * Rv[6 + j];
+      for (int j = 0; j < 3; j++) Rm[3 * i + j] = Rc[i] * Rv[j] + Rc[3 + i] * Rv[3 + j] + Rc[6 + i] * Rv[6 + j];
     F3 t = tmulm(Rc, Xv.p - Xc.p);
     vt[v * 3] = t.x; vt[v * 3 + 1] = t.y; vt[v * 3 + 2] = t.z;
     for (int k = 0; k < 9; k++) vRw[v * 9 + k] = Rv[k];
+    vo[v * 3] = -(Rm[0] * t.x + Rm[3] * t.y + Rm[6] * t.z);
+    vo[v * 3 + 1] = -(Rm[1] * t.x + Rm[4] * t.y + Rm[7] * t.z);
+    vo[v * 3 + 2] = -(Rm[2] * t.x + Rm[5] * t.y + Rm[8] * t.z);
+    const int ty = vis_type[v];
+    if (ty == 0 && vo[v * 3] > 0.0f) vc[v] = -1.0f / vo[v * 3];
+    if (ty == 4) vmode[v] = 0;
+    if (ty == 1) {
+      bool behind = false;
+      for (int c = 0; c < 8 && !behind; c++) {
+        F3 l = f3((c & 1) ? vis_size[3 * v] : -vis_size[3 * v], (c & 2) ? vis_size[3 * v + 1] : -vis_size[3 * v + 1],
+                  (c & 4) ? vis_size[3 * v + 2] : -vis_size[3 * v + 2]);
+        F3 pc = mulm(Rm, l) + t;
+        if (pc.x <= nearp) behind = true;
+      }
+      if (!behind) vmode[v] = 0;
+    }
+  }
+  // vertices: screen x, y, 1/depth (0 = not in front of the near plane)
+  std::vector<float> vert((size_t)n_vert * 3 + 3);
+  for (int i = 0; i < n_vert; i++) {
+    const int v = vert_vis[i];
+    float lx = vert_local[3 * i], ly = vert_local[3 * i + 1], lz = vert_local[3 * i + 2];
+    if (vis_type[v] == 1) { lx = lx * vis_size[3 * v]; ly = ly * vis_size[3 * v + 1]; lz = lz * vis_size[3 * v + 2]; }
+    const float* Rm = &vR[v * 9];
+    float xc = Rm[0] * lx + Rm[1] * ly + Rm[2] * lz + vt[v * 3];
+    float yc = Rm[3] * lx + Rm[4] * ly + Rm[5] * lz + vt[v * 3 + 1];
+    float zc = Rm[6] * lx + Rm[7] * ly + Rm[8] * lz + vt[v * 3 + 2];
+    float* o = &vert[(size_t)3 * i];
+    if (xc <= nearp) { o[0] = o[1] = o[2] = 0.0f; continue; }
+    float inv = 1.0f / xc;
+    o[0] = cx - fx * yc * inv;
+    o[1] = cy - fy * zc * inv;
+    o[2] = inv;
   }
   const int npix = W * H;
-  std::vector<unsigned> zkey(npix, 0xFFFFFFFFu);
+  std::vector<unsigned> zkey(npix, NO_HIT);
   for (int t = 0; t < n_tri; t++) {
     int v = tri_vis[t];
-    const float* tv = tri_verts + 9 * (size_t)t;
-    const float* Rm = &vR[v * 9];
+    if (vmode[v] != 0) continue;
     float px[3], py[3], pd[3];
     bool ok = true;
     for (int k = 0; k < 3; k++) {
-      F3 l = f3(tv[3 * k], tv[3 * k + 1], tv[3 * k + 2]);
-      float xc = Rm[0] * l.x + Rm[1] * l.y + Rm[2] * l.z + vt[v * 3];
-      float yc = Rm[3] * l.x + Rm[4] * l.y + Rm[5] * l.z + vt[v * 3 + 1];
-      float zc = Rm[6] * l.x + Rm[7] * l.y + Rm[8] * l.z + vt[v * 3 + 2];
-      if (xc <= nearp) ok = false;
-      float inv = 1.0f / xc;
-      px[k] = cx - fx * yc * inv;
-      py[k] = cy - fy * zc * inv;
-      pd[k] = inv;
+      const float* p = &vert[(size_t)3 * tri_idx[3 * t + k]];
+      if (p[2] == 0.0f) ok = false;
+      px[k] = p[0]; py[k] = p[1]; pd[k] = p[2];
     }
     if (!ok) continue;
     float area = (px[1] - px[0]) * (py[2] - py[0]) - (px[2] - px[0]) * (py[1] - py[0]);
-    // hull triangles are wound outwards (render.py build_visual_table): with screen x to the right and y down a front face has
-    // negative area; back faces are culled (hulls are closed: they are hidden by the front faces), front faces made counter-clockwise
     if (!(area < 0.0f)) continue;
     float tx = px[1]; px[1] = px[2]; px[2] = tx;
     float ty = py[1]; py[1] = py[2]; py[2] = ty;
@@ -243,49 +279,45 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
     int x = i % W, y = i / W;
     float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
     F3 rdir = f3(1.0f, ry, rz);
-    float best = 1e30f;
-    int best_v = -1;
-    F3 best_n = f3(0, 0, 0);
-    unsigned k = zkey[i];
-    if (k != 0xFFFFFFFFu) {
-      best = key_depth(k >> 8, dm);
-      best_v = (int)(k & 255u);
-    }
-    bool raster_hit = best_v >= 0;
+    unsigned best = zkey[i];
     for (int v = 0; v < n_vis; v++) {
+      if (vmode[v] != 1) continue;
       int ty = vis_type[v];
-      if (ty == 4) continue;
       const float* Rm = &vR[v * 9];
-      F3 tt = f3(vt[v * 3], vt[v * 3 + 1], vt[v * 3 + 2]);
-      F3 o = f3(-(Rm[0] * tt.x + Rm[3] * tt.y + Rm[6] * tt.z), -(Rm[1] * tt.x + Rm[4] * tt.y + Rm[7] * tt.z), -(Rm[2] * tt.x + Rm[5] * tt.y + Rm[8] * tt.z));
-      F3 dl = f3(Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z, Rm[1] * rdir.x + Rm[4] * rdir.y + Rm[7] * rdir.z,
-                 Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
-      float th = 0;
-      F3 nl = f3(0, 0, 0);
-      bool hit = false;
-      if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th, nl);
-      else if (ty == 2) hit = ray_sphere(o, dl, vis_size[3 * v], th, nl);
-      else if (ty == 0) {
-        if (dl.x < -1e-9f && o.x > 0.0f) { th = -o.x / dl.x; nl = f3(1, 0, 0); hit = true; }
+      float inv = 0.0f;
+      if (ty == 0) {
+        float dlx = Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z;
+        if (dlx < -1e-9f) inv = dlx * vc[v];
+      } else {
+        F3 o = f3(vo[v * 3], vo[v * 3 + 1], vo[v * 3 + 2]);
+        F3 dl = f3(Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z, Rm[1] * rdir.x + Rm[4] * rdir.y + Rm[7] * rdir.z,
+                   Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
+        float th = 0.0f;
+        bool hit = false;
+        if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th);
+        else if (ty == 2) hit = ray_sphere(o, dl, vis_size[3 * v], th);
+        if (hit) inv = 1.0f / th;
       }
-      if (hit && th > nearp && th < farp && th < best) {
-        best = th;
-        best_v = v;
-        raster_hit = false;
-        best_n = mulm(&vRw[v * 9], nl);
+      if (inv_depth_in_range(inv, dm)) {
+        unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+        if (key < best) best = key;
       }
     }
     uint8_t* c4 = color + (size_t)i * 4;
     int16_t* p4 = posseg + (size_t)i * 4;
     c4[0] = c4[1] = c4[2] = 0; c4[3] = 255;
     p4[0] = p4[1] = p4[2] = p4[3] = 0;
-    if (best_v >= 0) {
-      F3 pc = rdir * best;
-      if (raster_hit) {
+    if (best != NO_HIT) {
+      const int bv = (int)(best & 255u);
+      const float depth = key_depth(best >> 8, dm);
+      F3 pc = rdir * depth;
+      const int ty = vis_type[bv];
+      F3 n_world;
+      if (ty == 4) {
         int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
         unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
         F3 n_cam = f3(-1, 0, 0);
-        if (kx != 0xFFFFFFFFu && ky != 0xFFFFFFFFu && (int)(kx & 255u) == best_v && (int)(ky & 255u) == best_v) {
+        if (kx != NO_HIT && ky != NO_HIT && (int)(kx & 255u) == bv && (int)(ky & 255u) == bv) {
           float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
           F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
           F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
@@ -297,14 +329,25 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
           if (l > 1e-20f) n_cam = nn * (1.0f / l);
           if (n_cam.x > 0.0f) n_cam = -n_cam;
         }
-        best_n = mulm(Rc, n_cam);
+        n_world = mulm(Rc, n_cam);
+      } else {
+        F3 nl = f3(1, 0, 0);
+        if (ty != 0) {
+          const float* Rm = &vR[bv * 9];
+          F3 dpc = f3(pc.x - vt[bv * 3], pc.y - vt[bv * 3 + 1], pc.z - vt[bv * 3 + 2]);
+          F3 pl = f3(Rm[0] * dpc.x + Rm[3] * dpc.y + Rm[6] * dpc.z, Rm[1] * dpc.x + Rm[4] * dpc.y + Rm[7] * dpc.z,
+                     Rm[2] * dpc.x + Rm[5] * dpc.y + Rm[8] * dpc.z);
+          if (ty == 1) nl = box_face_normal(pl, f3(vis_size[3 * bv], vis_size[3 * bv + 1], vis_size[3 * bv + 2]));
+          else nl = pl * (1.0f / vis_size[3 * bv]);
+        }
+        n_world = mulm(&vRw[bv * 9], nl);
       }
-      const float* col = vis_color + 4 * best_v;
+      const float* col = vis_color + 4 * bv;
       const float kk = 0.57735026f;
       F3 l1 = f3(-kk, -kk, kk), l2 = f3(0.0f, 0.0f, 1.0f);
-      float w = 0.3f + 0.5f * fmaxf(dot(best_n, l1), 0.0f) + 0.5f * fmaxf(dot(best_n, l2), 0.0f);
+      float w = 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
       c4[0] = to_u8(col[0] * w); c4[1] = to_u8(col[1] * w); c4[2] = to_u8(col[2] * w);
-      p4[0] = to_mm(-pc.y); p4[1] = to_mm(pc.z); p4[2] = to_mm(-pc.x); p4[3] = (int16_t)vis_seg[best_v];
+      p4[0] = to_mm(-pc.y); p4[1] = to_mm(pc.z); p4[2] = to_mm(-pc.x); p4[3] = (int16_t)vis_seg[bv];
     }
   }
 }

@@ -14,7 +14,7 @@ def lib():
     if _lib is None:
         subprocess.check_call(["make", "-C", _DIR, "-s"])
         _lib = C.CDLL(os.path.join(_DIR, "libb2s_oracle_raster.so"))
-        _lib.b2o_render_one.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.b2o_render_one.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
     return _lib
 
 
@@ -46,7 +46,8 @@ def render(visuals: dict, cameras: list, body: np.ndarray):
             pose = np.ascontiguousarray(pose, dtype=np.float32)
             size = np.ascontiguousarray(size, dtype=np.float32)
             L.b2o_render_one(nv, p(visuals["type"]), p(visuals["row"]), p(pose), p(size), p(visuals["color"]), p(visuals["seg_id"]),
-                             int(visuals["n_tri"]), p(visuals["tri_vis"]), p(visuals["tri_verts"]), n_rows, p(body[e]), p(camv),
+                             int(visuals["n_vert"]), p(visuals["vert_local"]), p(visuals["vert_vis"]), int(visuals["n_tri"]), p(visuals["tri_idx"]),
+                             p(visuals["tri_vis"]), n_rows, p(body[e]), p(camv),
                              p(color[e]), p(posseg[e]))
         out.append((color, posseg))
     return out
