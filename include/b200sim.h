@@ -244,13 +244,30 @@ typedef struct B2SVisualTable {
   const int32_t* tri_vis;   /* [n_tri] owning visual */
 } B2SVisualTable;
 
+/* what a camera group writes per pixel: the shader pack's raw render targets (render/shaders.py:68-84, what
+ * `get_picture_cuda(name)` hands out) and / or the textures the observation modes deliver (render/shaders.py:74-83 texture_transforms:
+ * rgb = Color[..., :3], depth = -PositionSegmentation[..., 2], segmentation = PositionSegmentation[..., 3]) as contiguous tensors */
+#define B2S_OUT_COLOR 1u
+#define B2S_OUT_POSSEG 2u
+#define B2S_OUT_RGB 4u
+#define B2S_OUT_DEPTH 8u
+#define B2S_OUT_SEG 16u
+#define B2S_OUT_RAW (B2S_OUT_COLOR | B2S_OUT_POSSEG)
+
 typedef struct B2SRenderTargets {
-  uint8_t* color;        /* [n_envs, n_cam, h, w, 4] rgba8  (render/shaders.py:68-84 "Color") */
-  int16_t* position_seg; /* [n_envs, n_cam, h, w, 4] int16: x,y,z (mm, OpenGL camera frame), segmentation id */
+  uint8_t* color;        /* [n_envs, n_cam, h, w, 4] rgba8  (render/shaders.py:68-84 "Color"); NULL unless B2S_OUT_COLOR */
+  int16_t* position_seg; /* [n_envs, n_cam, h, w, 4] int16: x,y,z (mm, OpenGL camera frame), segmentation id; NULL unless B2S_OUT_POSSEG */
+  uint8_t* rgb;          /* [n_envs, n_cam, h, w, 3] uint8; NULL unless B2S_OUT_RGB */
+  int16_t* depth;        /* [n_envs, n_cam, h, w] int16 mm; NULL unless B2S_OUT_DEPTH */
+  int16_t* segmentation; /* [n_envs, n_cam, h, w] int16; NULL unless B2S_OUT_SEG */
 } B2SRenderTargets;
 
+/* raw render targets (B2S_OUT_RAW) */
 int32_t b2s_camera_group_create(uint64_t world, const B2SCameraDesc* cams, int32_t n_cam, const B2SVisualTable* vis,
                                 uint64_t* group, B2SRenderTargets* out);
+/* the same with a choice of outputs (a mask of B2S_OUT_*) */
+int32_t b2s_camera_group_create_outputs(uint64_t world, const B2SCameraDesc* cams, int32_t n_cam, const B2SVisualTable* vis,
+                                        uint32_t outputs, uint64_t* group, B2SRenderTargets* out);
 int32_t b2s_render(uint64_t world, uint64_t group, void* stream);
 
 /*

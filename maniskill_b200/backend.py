@@ -44,7 +44,12 @@ class B2SVisualTable(C.Structure):
 
 
 class B2SRenderTargets(C.Structure):
-    _fields_ = [("color", C.c_void_p), ("position_seg", C.c_void_p)]
+    _fields_ = [("color", C.c_void_p), ("position_seg", C.c_void_p), ("rgb", C.c_void_p), ("depth", C.c_void_p), ("segmentation", C.c_void_p)]
+
+
+# include/b200sim.h B2S_OUT_*: what a camera group writes per pixel
+OUT_COLOR, OUT_POSSEG, OUT_RGB, OUT_DEPTH, OUT_SEG = 1, 2, 4, 8, 16
+OUT_RAW = OUT_COLOR | OUT_POSSEG
 
 
 class B2SJointController(C.Structure):
@@ -96,6 +101,8 @@ def load_library():
     lib.b2s_contact_query_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
     lib.b2s_contact_query_run.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.b2s_camera_group_create.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(B2SRenderTargets)]
+    lib.b2s_camera_group_create_outputs.argtypes = [C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64),
+                                                    C.POINTER(B2SRenderTargets)]
     lib.b2s_render.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
     lib.b2s_render_masked.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.b2s_masked_copy.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -110,7 +117,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["b2s_last_error", "b2s_version", "b2s_world_create", "b2s_world_destroy", "b2s_world_buffers", "b2s_step",
                     "b2s_apply", "b2s_fetch", "b2s_update_kinematics", "b2s_contact_query_create", "b2s_contact_query_run",
-                    "b2s_camera_group_create", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step", "b2s_pick_task_set_reset",
+                    "b2s_camera_group_create", "b2s_camera_group_create_outputs", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step", "b2s_pick_task_set_reset",
                     "b2s_pick_task_step_autoreset", "b2s_pick_task_autoreset", "b2s_masked_copy", "b2s_render_masked"]
 
 
@@ -135,10 +142,30 @@ class CameraGroup:
     """What ``render_system_group.create_camera_group(...)`` returns in the reference (mani_skill/envs/scene.py:1087-1106):
     ``take_picture()`` renders every camera of every sub-scene, ``get_picture_cuda(name)`` hands out zero-copy tensors."""
 
-    def __init__(self, world, handle, cameras, color, posseg):
+    def __init__(self, world, handle, cameras, color, posseg, rgb=None, depth=None, seg=None):
         self.world, self.handle, self.cameras = world, handle, cameras
+        # raw render targets [N, P, 4] (None when the group only writes compact textures) and the compact textures
+        # rgb [N, P, 3] uint8, depth [N, P] int16, segmentation [N, P] int16 (None unless requested)
         self._color, self._posseg = color, posseg
+        self._rgb, self._depth, self._seg = rgb, depth, seg
+        self._final = None   # same-named copies kept for finished sub-scenes (render.CameraSensors.keep_final)
         self._offsets = np.cumsum([0] + [int(c["width"]) * int(c["height"]) for c in cameras])
+
+    def buffers(self):
+        """name -> tensor of every output this group writes."""
+        return {k: v for k, v in (("color", self._color), ("posseg", self._posseg), ("rgb", self._rgb), ("depth", self._depth), ("seg", self._seg))
+                if v is not None}
+
+    def texture(self, name: str, cam: int = 0, final: bool = False):
+        """Compact texture of one camera: 'rgb' [N,H,W,3] uint8 | 'depth' [N,H,W,1] int16 | 'seg' [N,H,W,1] int16, or None when the group
+        does not write it."""
+        src = self._final if final else self.buffers()
+        buf = src.get(name)
+        if buf is None:
+            return None
+        c = self.cameras[cam]
+        a, b = int(self._offsets[cam]), int(self._offsets[cam + 1])
+        return buf[:, a:b].view(self.world.n_envs, int(c["height"]), int(c["width"]), 3 if name == "rgb" else 1)
 
     def take_picture(self):
         self.world.render(self)
@@ -148,10 +175,10 @@ class CameraGroup:
         sub-scenes that an auto-reset re-rendered (maniskill_b200/render.py `keep_final`)."""
         c = self.cameras[cam]
         a, b = int(self._offsets[cam]), int(self._offsets[cam + 1])
-        if final:
-            buf = self._final_color if name == "Color" else self._final_posseg
-        else:
-            buf = self._color if name == "Color" else self._posseg
+        key = "color" if name == "Color" else "posseg"
+        buf = (self._final if final else self.buffers()).get(key)
+        if buf is None:
+            raise RuntimeError(f"this camera group does not write the raw render target '{name}' (created with compact outputs only)")
         return buf[:, a:b].view(self.world.n_envs, int(c["height"]), int(c["width"]), 4)
 
 
@@ -310,7 +337,7 @@ class World:
         self.kernel_launches += (2 if actions is not None else 1) + self._step_launches(substeps, BUF_ALL) + 3
 
     # ------------------------------------------------------------------ rendering
-    def create_camera_group(self, cameras, visuals):
+    def create_camera_group(self, cameras, visuals, outputs: int = OUT_RAW):
         """cameras: list of dict(width, height, fx, fy, cx, cy, near, far, mount_row, local_pose7);
         visuals: dict of numpy arrays (see maniskill_b200/render.py).  Returns a CameraGroup with aliasing tensors
         ``color`` [N, P, 4] uint8 and ``position_seg`` [N, P, 4] int16 (P = pixels of all cameras of one sub-scene)."""
@@ -333,11 +360,12 @@ class World:
         g = C.c_uint64(0)
         rt = B2SRenderTargets()
         with torch.cuda.device(self.device):
-            _check(self.lib, self.lib.b2s_camera_group_create(self.h, C.cast(arr, C.c_void_p), n_cam, C.byref(vt), C.byref(g), C.byref(rt)))
+            _check(self.lib, self.lib.b2s_camera_group_create_outputs(self.h, C.cast(arr, C.c_void_p), n_cam, C.byref(vt), int(outputs), C.byref(g),
+                                                                      C.byref(rt)))
         pix = sum(int(c["width"]) * int(c["height"]) for c in cameras)
-        color = _as_tensor(rt.color, (self.n_envs, pix, 4), "|u1", self, self.device)
-        posseg = _as_tensor(rt.position_seg, (self.n_envs, pix, 4), "<i2", self, self.device)
-        return CameraGroup(self, g, cameras, color, posseg)
+        t = lambda ptr, shape, ty: _as_tensor(ptr, shape, ty, self, self.device) if ptr else None
+        return CameraGroup(self, g, cameras, t(rt.color, (self.n_envs, pix, 4), "|u1"), t(rt.position_seg, (self.n_envs, pix, 4), "<i2"),
+                           t(rt.rgb, (self.n_envs, pix, 3), "|u1"), t(rt.depth, (self.n_envs, pix), "<i2"), t(rt.segmentation, (self.n_envs, pix), "<i2"))
 
     def render(self, group, env_mask=None):
         """take_picture(); `env_mask` ([n_envs] uint8 / bool device tensor): only those sub-scenes are re-rendered."""

@@ -585,11 +585,16 @@ int32_t b2s_contact_query_run(uint64_t world, uint64_t query, float* out_dev, vo
 
 int32_t b2s_camera_group_create(uint64_t world, const B2SCameraDesc* cams, int32_t n_cam, const B2SVisualTable* vis,
                                 uint64_t* group, B2SRenderTargets* out) {
+  return b2s_camera_group_create_outputs(world, cams, n_cam, vis, B2S_OUT_RAW, group, out);
+}
+
+int32_t b2s_camera_group_create_outputs(uint64_t world, const B2SCameraDesc* cams, int32_t n_cam, const B2SVisualTable* vis,
+                                        uint32_t outputs, uint64_t* group, B2SRenderTargets* out) {
   World* w = get(world);
   if (!w || !cams || !vis || !group || !out || n_cam < 1) return fail(B2S_ERR_INVALID, "bad camera group");
   DeviceGuard guard_(w->device);
   b2s::RasterGroup* g = nullptr;
-  const char* err = b2s::raster_create(w->M, w->S, w->host, cams, n_cam, vis, &g, out);
+  const char* err = b2s::raster_create(w->M, w->S, w->host, cams, n_cam, vis, outputs, &g, out);
   if (err) return fail(B2S_ERR_INVALID, "%s", err);
   w->groups.push_back(g);
   *group = w->groups.size();

@@ -22,7 +22,8 @@ T* dev_copy(RasterGroup* g, const T* src, size_t n) {
 }  // namespace
 
 const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& host, const B2SCameraDesc* cams, int n_cam,
-                          const B2SVisualTable* vis, RasterGroup** out, B2SRenderTargets* targets) {
+                          const B2SVisualTable* vis, unsigned outputs, RasterGroup** out, B2SRenderTargets* targets) {
+  if (outputs == 0 || (outputs & ~(unsigned)(B2S_OUT_COLOR | B2S_OUT_POSSEG | B2S_OUT_RGB | B2S_OUT_DEPTH | B2S_OUT_SEG))) return "bad render output mask";
   if (vis->n_visual > 64) return "more than 64 render shapes per sub-scene";
   RasterGroup* g = new RasterGroup();
   RasterModel& R = g->R;
@@ -67,16 +68,24 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   R.cam_intr = dev_copy(g, intr.data(), intr.size()); R.cam_pose = dev_copy(g, cp.data(), cp.size());
   R.cam_offset = dev_copy(g, off.data(), n_cam);
   R.pixels_per_env = pix;
-  g->color = dev_copy<uint8_t>(g, nullptr, N * pix * 4);
-  g->posseg = dev_copy<int16_t>(g, nullptr, N * pix * 4);
+  memset(&g->T, 0, sizeof(g->T));
+  g->T.mask = outputs;
+  if (outputs & B2S_OUT_COLOR) g->T.color = dev_copy<uint8_t>(g, nullptr, N * pix * 4);
+  if (outputs & B2S_OUT_POSSEG) g->T.posseg = dev_copy<int16_t>(g, nullptr, N * pix * 4);
+  if (outputs & B2S_OUT_RGB) g->T.rgb = dev_copy<uint8_t>(g, nullptr, N * pix * 3 + 4);
+  if (outputs & B2S_OUT_DEPTH) g->T.depth = dev_copy<int16_t>(g, nullptr, N * pix + 2);
+  if (outputs & B2S_OUT_SEG) g->T.seg = dev_copy<int16_t>(g, nullptr, N * pix + 2);
   for (void* p : g->allocs)
     if (!p) { raster_destroy(g); return "rasteriser allocation failed"; }
   if (cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess) {
     raster_destroy(g);
     return "cannot reserve shared memory for the depth buffer";
   }
-  targets->color = g->color;
-  targets->position_seg = g->posseg;
+  targets->color = g->T.color;
+  targets->position_seg = g->T.posseg;
+  targets->rgb = g->T.rgb;
+  targets->depth = g->T.depth;
+  targets->segmentation = g->T.seg;
   (void)S; (void)host;
   *out = g;
   return nullptr;
@@ -85,7 +94,7 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
 const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st) {
   int grid = M.n_envs * g->R.n_cam;
   // 512 threads = 16 warps per image: two images per SM (shared-memory bound) keep 32 warps in flight
-  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->color, g->posseg, env_mask);
+  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

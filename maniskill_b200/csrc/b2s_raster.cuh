@@ -20,7 +20,8 @@
 //            depth = 1 / (dequantised 1/depth): ONE division per covered pixel; flat normals from the geometry (box face from
 //            the hit point, plane, sphere) or from the depth neighbourhood (hulls); Lambert shading (ambient 0.3 + the two
 //            directional lights of mani_skill/envs/sapien_env.py:845-853); 4-byte and 8-byte stores, coalesced by row.
-// HBM traffic per image: the body rows in, 12 B per pixel out.  The arithmetic is restated operation by operation in
+// HBM traffic per image: the body rows in; out 12 B per pixel for the raw render targets, or only the textures the observation mode
+// delivers (rgb 3 B + depth 2 B [+ segmentation 2 B] per pixel, written as whole 32-bit words assembled per warp).  The arithmetic is restated operation by operation in
 // oracle/b2s_oracle_raster.cpp; this translation unit is compiled with -fmad=false so that both produce identical integers.
 #pragma once
 #include <cuda_runtime.h>
@@ -59,11 +60,22 @@ struct RasterModel {
   size_t pixels_per_env;
 };
 
+// what a camera group writes per pixel (include/b200sim.h B2S_OUT_*): the shader pack's raw render targets and / or the compact
+// textures the observation modes deliver (render/shaders.py:74-83: rgb = Color[..., :3], depth = -PositionSegmentation[..., 2],
+// segmentation = PositionSegmentation[..., 3])
+struct RasterTargets {
+  unsigned mask;
+  uint8_t* color;   // [N, pixels, 4] u8
+  int16_t* posseg;  // [N, pixels, 4] i16
+  uint8_t* rgb;     // [N, pixels, 3] u8
+  int16_t* depth;   // [N, pixels]    i16 (mm)
+  int16_t* seg;     // [N, pixels]    i16
+};
+
 struct RasterGroup {
   RasterModel R;
   std::vector<void*> allocs;
-  uint8_t* color;
-  int16_t* posseg;
+  RasterTargets T;
   int max_pixels;  // largest camera image (pixels) -> shared memory size
 };
 
@@ -185,6 +197,7 @@ struct RasterShared {
   int vis_mode[B2S_MAX_VIS];
   float vert[B2S_VERT_CACHE][3];  // screen x, screen y, 1/depth (0 = at or behind the near plane)
   unsigned short big[B2S_MAX_BIG_TRIS];
+  unsigned rgb_stage[B2S_RASTER_THREADS / 32][24];  // 32 pixels x 3 bytes of a warp, regrouped into 24 words
   int n_big;
 };
 
@@ -255,8 +268,8 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
 
 // env_mask (nullable): only sub-scenes with env_mask[env] != 0 are rendered (re-render after a partial reset); the others keep
 // their previous picture.
-__global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, uint8_t* __restrict__ color,
-                                                                    int16_t* __restrict__ posseg, const uint8_t* __restrict__ env_mask) {
+__global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
+                                                                    const uint8_t* __restrict__ env_mask) {
   extern __shared__ unsigned zkey[];
   __shared__ RasterShared sh;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
@@ -366,8 +379,13 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   }
   __syncthreads();
   // ---------------- stage 3: per pixel analytic primitives + merge + shade + store
-  uint8_t* cbase = color + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
-  int16_t* pbase = posseg + ((size_t)env * R.pixels_per_env + R.cam_offset[cam]) * 4;
+  const size_t pix0 = (size_t)env * R.pixels_per_env + R.cam_offset[cam];  // first pixel of this image in the targets
+  uint8_t* cbase = O.color + pix0 * 4;
+  int16_t* pbase = O.posseg + pix0 * 4;
+  // the compact textures are written as 32-bit words assembled per warp (32 consecutive pixels = 96 B of rgb, 64 B of depth): needs
+  // whole warps on consecutive pixels, i.e. a pixel count that is a multiple of the CTA size; otherwise element-wise stores
+  const bool packed = (npix % (int)blockDim.x) == 0 && (pix0 % 32) == 0;
+  const int warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
   // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel).  With W dividing blockDim the column of a
   // thread is fixed, so the set of analytic primitives whose screen rectangle covers that column is one 64-bit mask per column.
   int x = threadIdx.x % W, y = threadIdx.x / W;
@@ -457,15 +475,39 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
       // OpenGL camera frame: x right = -y_cam, y up = z_cam, z backward = -x_cam
       p4 = make_short4(to_mm(-pc.y), to_mm(pc.z), to_mm(-pc.x), (short)R.vis_seg[bv]);
     }
-    *reinterpret_cast<uchar4*>(cbase + (size_t)i * 4) = c4;
-    *reinterpret_cast<short4*>(pbase + (size_t)i * 4) = p4;
+    if (O.mask & B2S_OUT_COLOR) *reinterpret_cast<uchar4*>(cbase + (size_t)i * 4) = c4;
+    if (O.mask & B2S_OUT_POSSEG) *reinterpret_cast<short4*>(pbase + (size_t)i * 4) = p4;
+    if (O.mask & (B2S_OUT_RGB | B2S_OUT_DEPTH | B2S_OUT_SEG)) {
+      const short dmm = (short)(-(int)p4.z);  // depth = -z of the OpenGL frame, with int16 negation semantics
+      if (packed) {
+        if (O.mask & B2S_OUT_RGB) {
+          uint8_t* wb = reinterpret_cast<uint8_t*>(sh.rgb_stage[warp_id]);
+          wb[3 * lane_id] = c4.x; wb[3 * lane_id + 1] = c4.y; wb[3 * lane_id + 2] = c4.z;
+          __syncwarp();
+          if (lane_id < 24) reinterpret_cast<unsigned*>(O.rgb + (pix0 + (size_t)(i - lane_id)) * 3)[lane_id] = sh.rgb_stage[warp_id][lane_id];
+          __syncwarp();
+        }
+        if (O.mask & B2S_OUT_DEPTH) {
+          const unsigned lo = (unsigned)(unsigned short)dmm, hi = __shfl_down_sync(0xffffffffu, lo, 1);
+          if (!(lane_id & 1)) *reinterpret_cast<unsigned*>(O.depth + pix0 + i) = lo | (hi << 16);
+        }
+        if (O.mask & B2S_OUT_SEG) {
+          const unsigned lo = (unsigned)(unsigned short)p4.w, hi = __shfl_down_sync(0xffffffffu, lo, 1);
+          if (!(lane_id & 1)) *reinterpret_cast<unsigned*>(O.seg + pix0 + i) = lo | (hi << 16);
+        }
+      } else {
+        if (O.mask & B2S_OUT_RGB) { uint8_t* o3 = O.rgb + (pix0 + i) * 3; o3[0] = c4.x; o3[1] = c4.y; o3[2] = c4.z; }
+        if (O.mask & B2S_OUT_DEPTH) O.depth[pix0 + i] = dmm;
+        if (O.mask & B2S_OUT_SEG) O.seg[pix0 + i] = p4.w;
+      }
+    }
   }
 }
 
 #endif  // __CUDACC__ && B2S_RASTER_IMPL
 
 const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& host, const B2SCameraDesc* cams, int n_cam,
-                          const B2SVisualTable* vis, RasterGroup** out, B2SRenderTargets* targets);
+                          const B2SVisualTable* vis, unsigned outputs, RasterGroup** out, B2SRenderTargets* targets);
 const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st);
 void raster_destroy(RasterGroup* g);
 

@@ -148,8 +148,12 @@ class BaseEnv:
     def __init__(self, num_envs: int = 1, obs_mode: Optional[str] = None, reward_mode: Optional[str] = None,
                  control_mode: Optional[str] = None, sim_config: Optional[dict] = None, device: Union[str, torch.device, None] = None,
                  world_factory=None, sensor_configs: Optional[dict] = None, enable_cameras: Optional[bool] = None, fused: bool = True,
-                 enhanced_determinism: bool = False, reconfiguration_freq: Optional[int] = None, render_mode: Optional[str] = None):
+                 enhanced_determinism: bool = False, reconfiguration_freq: Optional[int] = None, render_mode: Optional[str] = None,
+                 sensor_outputs: str = "auto"):
         self.num_envs = num_envs
+        if sensor_outputs not in ("auto", "raw", "compact"):
+            raise ValueError("sensor_outputs must be 'auto', 'raw' or 'compact'")
+        self._sensor_outputs = sensor_outputs
         self._obs_mode = "state" if obs_mode is None else obs_mode
         self.obs_mode_struct = parse_obs_mode(self._obs_mode)   # raises NotImplementedError for unknown / unsupported textures
         self._reward_mode = self.SUPPORTED_REWARD_MODES[0] if reward_mode is None else reward_mode   # sapien_env.py:300-304
@@ -604,7 +608,13 @@ class BaseEnv:
             cams.append(camera_desc(c["uid"], c["pose"], c["width"], c["height"], c["fov"], c["near"], c["far"], row))
         if not cams:
             raise NotImplementedError("this task defines no sensor cameras")
-        return CameraSensors(self.scene.world, self.cm, cams)
+        # the sensors of the observation write only the textures the mode delivers (rgb 3 B + depth 2 B + segmentation 2 B per pixel) unless a
+        # texture needs the raw targets (position) or the caller asks for them (`sensor_outputs="raw"`: get_picture_cuda stays available)
+        m = self.obs_mode_struct
+        outputs = 3
+        if self._sensor_outputs == "compact" or (self._sensor_outputs == "auto" and m.visual and not m.position and not m.pointcloud):
+            outputs = (4 if m.rgb else 0) | (8 if m.depth else 0) | (16 if m.segmentation else 0)
+        return CameraSensors(self.scene.world, self.cm, cams, outputs=outputs or 3)
 
     def _get_obs_sensor_data(self, render: bool = True, final: bool = False):
         """sapien_env.py:578-625: hidden objects are simply absent from the sensor render-shape table (the reference

@@ -82,13 +82,14 @@ def camera_desc(uid, pose7, width, height, fov, near, far, mount_row=-1):
 class CameraSensors:
     """All cameras of a task as one camera group (mani_skill/envs/scene.py:1087-1106) + the obs-facing accessors."""
 
-    def __init__(self, world, cm: CompiledModel, cams: List[dict], include_hidden: bool = False):
+    def __init__(self, world, cm: CompiledModel, cams: List[dict], include_hidden: bool = False, outputs: int = 3):
         """include_hidden: also draw the objects the task hides from its sensors (the human render cameras show them,
-        sapien_env.py:1373-1374)."""
+        sapien_env.py:1373-1374).  outputs: mask of backend.OUT_* -- the raw render targets (3, what `get_picture_cuda` hands out) and / or
+        the compact textures an observation mode delivers (rgb 4, depth 8, segmentation 16): the kernel then writes only those."""
         self.world = world
         self.cams = cams
         self.visuals = build_visual_table(cm, world.n_envs, include_hidden=include_hidden)
-        self.group = world.create_camera_group(cams, self.visuals)
+        self.group = world.create_camera_group(cams, self.visuals, outputs) if outputs != 3 else world.create_camera_group(cams, self.visuals)
 
     def capture(self, env_mask=None):
         """take_picture(); env_mask ([N] bool / uint8 on the device): only those sub-scenes are rendered again."""
@@ -101,10 +102,10 @@ class CameraSensors:
         """Copies the current pictures of the masked sub-scenes into the `final` render targets (what `final_observation` shows after an
         auto-reset re-rendered them); rows of other sub-scenes keep whatever they held."""
         g = self.group
-        if getattr(g, "_final_color", None) is None:
-            g._final_color, g._final_posseg = torch.zeros_like(g._color), torch.zeros_like(g._posseg)
-        self.world.masked_copy(g._final_color, g._color, env_mask)
-        self.world.masked_copy(g._final_posseg, g._posseg, env_mask)
+        if g._final is None:
+            g._final = {k: torch.zeros_like(v) for k, v in g.buffers().items()}
+        for k, v in g.buffers().items():
+            self.world.masked_copy(g._final[k], v, env_mask)
 
     def get_obs(self, rgb=True, depth=True, segmentation=True, position=False, final=False):
         """sensor_data[uid] = {rgb [N,H,W,3] uint8, depth [N,H,W,1] int16 (mm), segmentation [N,H,W,1] int16}
@@ -112,15 +113,19 @@ class CameraSensors:
         out = {}
         for i, c in enumerate(self.cams):
             d = {}
+            g = self.group
+            tex = lambda name: g.texture(name, i, final=final)   # the compact texture when the group writes it
+            ps = None
+            if position or (depth and tex("depth") is None) or (segmentation and tex("seg") is None):
+                ps = g.get_picture_cuda("PositionSegmentation", i, final=final)
             if rgb:
-                d["rgb"] = self.group.get_picture_cuda("Color", i, final=final)[..., :3]
-            ps = self.group.get_picture_cuda("PositionSegmentation", i, final=final)
+                d["rgb"] = tex("rgb") if tex("rgb") is not None else g.get_picture_cuda("Color", i, final=final)[..., :3]
             if depth:
-                d["depth"] = -ps[..., 2:3]  # strided elementwise negation; a slice, not a gather
+                d["depth"] = tex("depth") if tex("depth") is not None else -ps[..., 2:3]  # strided elementwise negation; a slice, not a gather
             if position:
                 d["position"] = ps[..., :3]
             if segmentation:
-                d["segmentation"] = ps[..., 3:4]  # a view of the render target
+                d["segmentation"] = tex("seg") if tex("seg") is not None else ps[..., 3:4]  # a view of the render target
             out[c["uid"]] = d
         return out
 

@@ -55,17 +55,27 @@ class EmuBackendWorld:
         pass
 
     # ---- rendering: the CPU raster oracle stands in for b2s_camera_group_create / b2s_render (tests may use oracle/)
-    def create_camera_group(self, cameras, visuals):
+    def create_camera_group(self, cameras, visuals, outputs=3):
         from maniskill_b200.backend import CameraGroup
         pix = sum(int(c["width"]) * int(c["height"]) for c in cameras)
-        g = CameraGroup(self, None, cameras, torch.zeros((self.n_envs, pix, 4), dtype=torch.uint8), torch.zeros((self.n_envs, pix, 4), dtype=torch.int16))
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt)
+        g = CameraGroup(self, None, cameras, z((self.n_envs, pix, 4), torch.uint8), z((self.n_envs, pix, 4), torch.int16),
+                        z((self.n_envs, pix, 3), torch.uint8) if outputs & 4 else None, z((self.n_envs, pix), torch.int16) if outputs & 8 else None,
+                        z((self.n_envs, pix), torch.int16) if outputs & 16 else None)
         g._visuals = visuals
         return g
 
-    def render(self, group):
+    def render(self, group, env_mask=None):
         from oracle import raster
         out = raster.render(group._visuals, group.cameras, self.body_view().numpy())
         for i, (color, posseg) in enumerate(out):
             a, b = int(group._offsets[i]), int(group._offsets[i + 1])
             group._color[:, a:b] = torch.from_numpy(np.ascontiguousarray(color)).reshape(self.n_envs, -1, 4)
             group._posseg[:, a:b] = torch.from_numpy(np.ascontiguousarray(posseg)).reshape(self.n_envs, -1, 4)
+        # the compact textures follow from the raw targets (render/shaders.py:74-83 texture_transforms)
+        if group._rgb is not None:
+            group._rgb[:] = group._color[..., :3]
+        if group._depth is not None:
+            group._depth[:] = -group._posseg[..., 2]
+        if group._seg is not None:
+            group._seg[:] = group._posseg[..., 3]

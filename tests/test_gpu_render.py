@@ -62,7 +62,7 @@ def test_peg_insertion_rgbd_two_cameras_heterogeneous_envs():
     import maniskill_b200 as ms
     from oracle import raster
     n = 5
-    env = ms.make("PegInsertionSide-v1", num_envs=n, obs_mode="rgbd")
+    env = ms.make("PegInsertionSide-v1", num_envs=n, obs_mode="rgbd", sensor_outputs="raw")   # raw render targets: get_picture_cuda below
     obs, _ = env.reset(seed=1)
     g = torch.Generator(device=env.device).manual_seed(0)
     for _ in range(3):
