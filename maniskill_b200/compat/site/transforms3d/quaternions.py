@@ -1,0 +1,87 @@
+"""transforms3d.quaternions (wxyz): quat2mat, mat2quat, qmult, qinverse, qconjugate, axangle2quat, quat2axangle, rotate_vector, nearly_equivalent."""
+import math
+
+import numpy as np
+
+_FLOAT_EPS = np.finfo(np.float64).eps
+
+
+def quat2mat(q):
+    w, x, y, z = q
+    Nq = w * w + x * x + y * y + z * z
+    if Nq < _FLOAT_EPS:
+        return np.eye(3)
+    s = 2.0 / Nq
+    X, Y, Z = x * s, y * s, z * s
+    wX, wY, wZ = w * X, w * Y, w * Z
+    xX, xY, xZ = x * X, x * Y, x * Z
+    yY, yZ, zZ = y * Y, y * Z, z * Z
+    return np.array([[1.0 - (yY + zZ), xY - wZ, xZ + wY], [xY + wZ, 1.0 - (xX + zZ), yZ - wX], [xZ - wY, yZ + wX, 1.0 - (xX + yY)]])
+
+
+def mat2quat(M):
+    Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz = np.asarray(M, dtype=np.float64).flat
+    K = np.array([[Qxx - Qyy - Qzz, 0, 0, 0], [Qyx + Qxy, Qyy - Qxx - Qzz, 0, 0], [Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, 0],
+                  [Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz]]) / 3.0
+    vals, vecs = np.linalg.eigh(K)
+    q = vecs[[3, 0, 1, 2], np.argmax(vals)]
+    if q[0] < 0:
+        q = -q
+    return q
+
+
+def qmult(q1, q2):
+    w1, x1, y1, z1 = q1
+    w2, x2, y2, z2 = q2
+    return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                     w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2, w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2])
+
+
+def qconjugate(q):
+    return np.array(q) * np.array([1.0, -1, -1, -1])
+
+
+def qnorm(q):
+    return np.sqrt(np.dot(q, q))
+
+
+def qinverse(q):
+    return qconjugate(q) / np.dot(q, q)
+
+
+def axangle2quat(vector, theta, is_normalized=False):
+    vector = np.array(vector, dtype=np.float64)
+    if not is_normalized:
+        vector = vector / math.sqrt(np.dot(vector, vector))
+    t2 = theta / 2.0
+    return np.concatenate(([math.cos(t2)], vector * math.sin(t2)))
+
+
+def quat2axangle(quat, identity_thresh=None):
+    w, x, y, z = quat
+    Nq = w * w + x * x + y * y + z * z
+    if not np.isfinite(Nq):
+        return np.array([1.0, 0, 0]), float("nan")
+    if identity_thresh is None:
+        identity_thresh = np.finfo(np.float64).eps * 3
+    if Nq < _FLOAT_EPS**2:
+        return np.array([1.0, 0, 0]), 0.0
+    if Nq != 1:
+        s = math.sqrt(Nq)
+        w, x, y, z = w / s, x / s, y / s, z / s
+    len2 = x * x + y * y + z * z
+    if len2 < identity_thresh**2:
+        return np.array([1.0, 0, 0]), 0.0
+    theta = 2 * math.acos(max(min(w, 1), -1))
+    return np.array([x, y, z]) / math.sqrt(len2), theta
+
+
+def rotate_vector(v, q, is_normalized=True):
+    varr = np.zeros((4,))
+    varr[1:] = v
+    return qmult(q, qmult(varr, qconjugate(q) if is_normalized else qinverse(q)))[1:]
+
+
+def nearly_equivalent(q1, q2, rtol=1e-5, atol=1e-8):
+    q1, q2 = np.array(q1), np.array(q2)
+    return bool(np.allclose(q1, q2, rtol, atol) or np.allclose(q1 * -1, q2, rtol, atol))

@@ -180,6 +180,7 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
 #define B2S_MAX_VIS 64
 #define B2S_VERT_CACHE 1536       // projected vertices kept in shared memory (18 KB); vertices beyond are projected on use
 #define B2S_MAX_BIG_TRIS 1024
+#define B2S_MAX_HUGE_TRIS 128
 #define B2S_BIG_TRI_PIXELS 24     // bounding boxes above this many pixels leave the one-thread path
 #define B2S_HUGE_TRI_PIXELS 2048  // ... and above this many are shared by the whole CTA instead of one warp
 
@@ -196,9 +197,10 @@ struct RasterShared {
   int vis_kind[B2S_MAX_VIS];
   int vis_mode[B2S_MAX_VIS];
   float vert[B2S_VERT_CACHE][3];  // screen x, screen y, 1/depth (0 = at or behind the near plane)
-  unsigned short big[B2S_MAX_BIG_TRIS];
+  unsigned short big[B2S_MAX_BIG_TRIS];    // triangles rasterised by one warp each
+  unsigned short huge[B2S_MAX_HUGE_TRIS];  // triangles rasterised by the whole CTA
   unsigned rgb_stage[B2S_RASTER_THREADS / 32][24];  // 32 pixels x 3 bytes of a warp, regrouped into 24 words
-  int n_big;
+  int n_big, n_huge;
 };
 
 // local vertex i of the rasterised geometry -> screen x, y, 1/depth (out[2] = 0 when it is not in front of the near plane)
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   __shared__ RasterShared sh;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
   if (env_mask && !env_mask[env]) return;
-  if (threadIdx.x == 0) sh.n_big = 0;
+  if (threadIdx.x == 0) { sh.n_big = 0; sh.n_huge = 0; }
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
   const float nearp = R.cam_intr[6 * cam + 4], farp = R.cam_intr[6 * cam + 5];
@@ -349,6 +351,10 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     if (cnt > B2S_BIG_TRI_PIXELS && t < 65536) {
       // larger on-screen triangle: queued and rasterised by a whole warp (by the whole CTA when huge) so that the one-thread path
       // stays short and balanced
+      if (cnt > B2S_HUGE_TRI_PIXELS) {
+        const int slot = atomicAdd(&sh.n_huge, 1);
+        if (slot < B2S_MAX_HUGE_TRIS) { sh.huge[slot] = (unsigned short)t; continue; }
+      }
       const int slot = atomicAdd(&sh.n_big, 1);
       if (slot < B2S_MAX_BIG_TRIS) { sh.big[slot] = (unsigned short)t; continue; }
     }
@@ -358,22 +364,53 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   __syncthreads();
   {
     // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride` pixels
-    const int nb = sh.n_big < B2S_MAX_BIG_TRIS ? sh.n_big : B2S_MAX_BIG_TRIS;
     const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5, lane = threadIdx.x & 31;
-    for (int pass = 0; pass < 2; pass++) {  // 0: warp-sized triangles, one warp each; 1: huge ones, all threads
-      for (int b = pass == 0 ? warp : 0; b < nb; b += pass == 0 ? n_warp : 1) {
+    // warp-sized triangles: a warp takes 32 queued triangles at a time -- every lane sets up ONE of them (the setup is not repeated by the
+    // 32 lanes), then the triangles are rasterised one after the other by the whole warp, the setup of triangle j broadcast from lane j
+    const int nb = sh.n_big < B2S_MAX_BIG_TRIS ? sh.n_big : B2S_MAX_BIG_TRIS;
+    for (int base = warp * 32; base < nb; base += n_warp * 32) {
+      TriSetup mine;
+      const bool ok = base + lane < nb && setup_triangle(R, sh, (int)sh.big[base + lane], W, H, fx, fy, cx, cy, nearp, mine);
+      if (!ok) { mine.x0 = 0; mine.x1 = -1; mine.y0 = 0; mine.y1 = -1; mine.v = 0; mine.inv_area = 0.0f;
+                 for (int k = 0; k < 3; k++) { mine.px[k] = 0.0f; mine.py[k] = 0.0f; mine.pd[k] = 0.0f; } }
+      unsigned todo = __ballot_sync(0xffffffffu, ok);
+      while (todo) {
+        const int j = __ffs((int)todo) - 1;
+        todo &= todo - 1;
         TriSetup T;
-        if (!setup_triangle(R, sh, (int)sh.big[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          T.px[k] = __shfl_sync(0xffffffffu, mine.px[k], j);
+          T.py[k] = __shfl_sync(0xffffffffu, mine.py[k], j);
+          T.pd[k] = __shfl_sync(0xffffffffu, mine.pd[k], j);
+        }
+        T.inv_area = __shfl_sync(0xffffffffu, mine.inv_area, j);
+        T.x0 = __shfl_sync(0xffffffffu, mine.x0, j); T.x1 = __shfl_sync(0xffffffffu, mine.x1, j);
+        T.y0 = __shfl_sync(0xffffffffu, mine.y0, j); T.y1 = __shfl_sync(0xffffffffu, mine.y1, j);
+        T.v = __shfl_sync(0xffffffffu, mine.v, j);
         const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
-        if ((cnt > B2S_HUGE_TRI_PIXELS) != (pass == 1)) continue;
-        const int first = pass == 0 ? lane : (int)threadIdx.x, stride = pass == 0 ? 32 : (int)blockDim.x;
-        const int sy_ = stride / bw, sx_ = stride - sy_ * bw;
-        int yy = first / bw, xx = first - yy * bw;
-        for (int p = first; p < cnt; p += stride) {
+        const int sy_ = 32 / bw, sx_ = 32 - sy_ * bw;
+        int yy = lane / bw, xx = lane - yy * bw;
+        for (int p = lane; p < cnt; p += 32) {
           raster_sample(zkey, W, T.x0 + xx, T.y0 + yy, T, dm);
           xx += sx_; yy += sy_;
           if (xx >= bw) { xx -= bw; yy++; }
         }
+      }
+    }
+    // huge triangles (close-ups, table faces): the whole CTA walks the bounding box of each
+    const int nh = sh.n_huge < B2S_MAX_HUGE_TRIS ? sh.n_huge : B2S_MAX_HUGE_TRIS;
+    for (int b = 0; b < nh; b++) {
+      TriSetup T;
+      if (!setup_triangle(R, sh, (int)sh.huge[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+      const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
+      const int first = (int)threadIdx.x, stride = (int)blockDim.x;
+      const int sy_ = stride / bw, sx_ = stride - sy_ * bw;
+      int yy = first / bw, xx = first - yy * bw;
+      for (int p = first; p < cnt; p += stride) {
+        raster_sample(zkey, W, T.x0 + xx, T.y0 + yy, T, dm);
+        xx += sx_; yy += sy_;
+        if (xx >= bw) { xx -= bw; yy++; }
       }
     }
   }

@@ -456,6 +456,13 @@ class SceneDesc:
                     dof_mass_parts[ab].append((L["mass"], off[:3] + R @ np.asarray(L["com"]), rotate_inertia(Il, R)))
                 groups = art.link_groups.get(L["name"], (1, 1, 0, 0))
                 for s in L["collisions"]:
+                    if "rec" in s:   # a ready ShapeRec in the link frame (maniskill_b200/compat/compile.py): collision and / or visual
+                        rec = ShapeRec(**{**s["rec"].__dict__})
+                        rec.pose = pose_mul(off, s["rec"].pose)
+                        if rec.per_env_pose is not None:
+                            rec.per_env_pose = np.stack([pose_mul(off, p) for p in rec.per_env_pose])
+                        shapes.append(dict(rec=rec, owner_kind=OWNER_LINK, owner=ab, row=row, art=ai, link=li, seg=seg_next, hidden=False))
+                        continue
                     lp = pose_mul(off, pose7(s["p"], s["q"]))
                     mu = art.link_mu.get(L["name"], sim.static_friction)
                     if s["type"] == "box":
