@@ -104,6 +104,21 @@ class RenderMaterial:
 
     set_diffuse_texture = set_base_color_texture
 
+    def set_normal_texture(self, t):
+        self.normal_texture = t
+
+    def set_roughness_texture(self, t):
+        self.roughness_texture = t
+
+    def set_metallic_texture(self, t):
+        self.metallic_texture = t
+
+    def set_emission_texture(self, t):
+        self.emission_texture = t
+
+    def set_transmission_texture(self, t):
+        self.transmission_texture = t
+
     def set_roughness(self, v):
         self.roughness = float(v)
 

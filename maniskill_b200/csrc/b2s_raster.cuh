@@ -365,37 +365,19 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   {
     // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride` pixels
     const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5, lane = threadIdx.x & 31;
-    // warp-sized triangles: a warp takes 32 queued triangles at a time -- every lane sets up ONE of them (the setup is not repeated by the
-    // 32 lanes), then the triangles are rasterised one after the other by the whole warp, the setup of triangle j broadcast from lane j
+    // warp-sized triangles, one warp each (the 32 lanes repeat the cheap setup from the vertex cache; setting it up on one lane and
+    // broadcasting it with shuffles measured slower: 2.4 ms vs 1.8 ms per 4096 images)
     const int nb = sh.n_big < B2S_MAX_BIG_TRIS ? sh.n_big : B2S_MAX_BIG_TRIS;
-    for (int base = warp * 32; base < nb; base += n_warp * 32) {
-      TriSetup mine;
-      const bool ok = base + lane < nb && setup_triangle(R, sh, (int)sh.big[base + lane], W, H, fx, fy, cx, cy, nearp, mine);
-      if (!ok) { mine.x0 = 0; mine.x1 = -1; mine.y0 = 0; mine.y1 = -1; mine.v = 0; mine.inv_area = 0.0f;
-                 for (int k = 0; k < 3; k++) { mine.px[k] = 0.0f; mine.py[k] = 0.0f; mine.pd[k] = 0.0f; } }
-      unsigned todo = __ballot_sync(0xffffffffu, ok);
-      while (todo) {
-        const int j = __ffs((int)todo) - 1;
-        todo &= todo - 1;
-        TriSetup T;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          T.px[k] = __shfl_sync(0xffffffffu, mine.px[k], j);
-          T.py[k] = __shfl_sync(0xffffffffu, mine.py[k], j);
-          T.pd[k] = __shfl_sync(0xffffffffu, mine.pd[k], j);
-        }
-        T.inv_area = __shfl_sync(0xffffffffu, mine.inv_area, j);
-        T.x0 = __shfl_sync(0xffffffffu, mine.x0, j); T.x1 = __shfl_sync(0xffffffffu, mine.x1, j);
-        T.y0 = __shfl_sync(0xffffffffu, mine.y0, j); T.y1 = __shfl_sync(0xffffffffu, mine.y1, j);
-        T.v = __shfl_sync(0xffffffffu, mine.v, j);
-        const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
-        const int sy_ = 32 / bw, sx_ = 32 - sy_ * bw;
-        int yy = lane / bw, xx = lane - yy * bw;
-        for (int p = lane; p < cnt; p += 32) {
-          raster_sample(zkey, W, T.x0 + xx, T.y0 + yy, T, dm);
-          xx += sx_; yy += sy_;
-          if (xx >= bw) { xx -= bw; yy++; }
-        }
+    for (int b = warp; b < nb; b += n_warp) {
+      TriSetup T;
+      if (!setup_triangle(R, sh, (int)sh.big[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+      const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
+      const int sy_ = 32 / bw, sx_ = 32 - sy_ * bw;
+      int yy = lane / bw, xx = lane - yy * bw;
+      for (int p = lane; p < cnt; p += 32) {
+        raster_sample(zkey, W, T.x0 + xx, T.y0 + yy, T, dm);
+        xx += sx_; yy += sy_;
+        if (xx >= bw) { xx -= bw; yy++; }
       }
     }
     // huge triangles (close-ups, table faces): the whole CTA walks the bounding box of each

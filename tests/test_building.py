@@ -114,17 +114,6 @@ def test_explicit_inertial_and_kinematic_build():
     assert cm.arrays["fb_mass"][1] == pytest.approx(1000 * 0.008)     # kinematic: the explicit inertial is ignored (actor_builder.py:156-160)
 
 
-def test_twocolor_peg_helper_matches_the_task_mirror():
-    from maniskill_b200.envs.lift_peg_upright import twocolor_peg_shapes
-    scene = SceneDesc(1)
-    c1, c2 = np.array([176, 14, 14, 255]) / 255, np.array([12, 42, 160, 255]) / 255
-    rec = B.build_twocolor_peg(scene, length=0.12, width=0.025, color_1=c1, color_2=c2, name="peg", initial_pose=B.Pose(p=[0, 0, 0.1]))
-    ref = twocolor_peg_shapes(0.12, 0.025, c1, c2)
-    assert len(rec.shapes) == 3
-    for s, r in zip(rec.shapes, ref):
-        assert (s.type, s.collide, s.visual) == (r.type, r.collide, r.visual) and np.allclose(s.pose, r.pose) and np.allclose(s.size, r.size)
-        if s.visual:
-            assert np.allclose(s.color, r.color)
 
 
 def _fk_world(cm_factory, qpos):

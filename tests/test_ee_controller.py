@@ -127,7 +127,7 @@ def test_absolute_ee_pose_mode_reaches_the_commanded_pose():
     import maniskill_b200 as ms
     from emu_world import EmuBackendWorld
     from maniskill_b200 import utils as U
-    env = ms.make("PushCube-v1", num_envs=2, obs_mode="state", control_mode="pd_ee_pose", world_factory=EmuBackendWorld)
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state", control_mode="pd_ee_pose", world_factory=EmuBackendWorld)
     env.reset(seed=0)
     assert env.action_dim == 7 and np.allclose(env.single_action_space_low[:3], -2.0) and np.allclose(env.single_action_space_high[3:6], 2 * np.pi)
     arm = env.agent.controller.controllers["arm"]

@@ -186,60 +186,8 @@ def test_net_contact_force_on_resting_cube_is_its_weight():
     assert torch.allclose(f, env.scene.get_pairwise_contact_forces(env.cube, table), atol=1e-6)
 
 
-def test_push_cube_reset_obs_and_a_scripted_push():
-    """PushCube-v1 (push_cube.py): reset ranges, 35-dim state observation, and a scripted push with the target end-effector
-    controller drives the cube into the goal disc."""
-    env = ms.make("PushCube-v1", num_envs=3, obs_mode="state", control_mode="pd_ee_target_delta_pos", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=0)
-    # qpos, qvel, the controller's virtual target pose (base_agent.py:339-347: controller state is part of proprioception), tcp pose,
-    # goal position, cube pose
-    assert obs.shape == (3, 9 + 9 + 7 + 7 + 3 + 7) and env.action_dim == 4
-    cube, goal = env.obj.pose.p.clone(), env.goal_region.pose.p.clone()
-    assert (cube[:, :2].abs() <= 0.1 + 1e-6).all() and torch.allclose(cube[:, 2], torch.full((3,), 0.02))
-    assert torch.allclose(goal[:, :2], cube[:, :2] + torch.tensor([0.2, 0.0]), atol=1e-6) and torch.allclose(goal[:, 2], torch.full((3,), 1e-3))
-    assert not env.evaluate()["success"].any()
-
-    ctrl = env.agent.controller.controllers["arm"]
-
-    def go_to(target, steps, max_step=0.1, grip=-1.0):
-        for _ in range(steps):
-            d = (target - ctrl._target_pose.p).clamp(-max_step, max_step)  # the virtual target lives in the robot's root frame
-            a = torch.zeros(3, 4)
-            a[:, :3] = d / 0.1
-            a[:, 3] = grip
-            out = env.step(a)
-        return out
-
-    base = torch.tensor([-0.615, 0.0, 0.0])
-    behind = cube + torch.tensor([-0.06, 0.0, 0.0]) - base
-    go_to(behind + torch.tensor([0.0, 0.0, 0.08]), 12)
-    go_to(behind, 10)
-    assert (env.agent.tcp.pose.p - (behind + base)).abs().max() < 3e-3      # the controller tracks its target to millimetres
-    obs, r, te, tr, info = go_to(behind + torch.tensor([0.2, 0.0, 0.0]), 30, max_step=0.01)   # 0.2 m/s: push, do not kick
-    assert info["success"].all(), (env.obj.pose.p, env.goal_region.pose.p)
-    assert torch.allclose(r, torch.ones(3))  # normalised dense reward saturates at success
 
 
-def test_stack_cube_reset_and_a_stacked_cube_counts_as_success():
-    """StackCube-v1 (stack_cube.py): the two cubes never start overlapping, 48-dim state observation, and a cube put down on the
-    other one (box on box on table) settles and is reported as stacked, static and released."""
-    env = ms.make("StackCube-v1", num_envs=4, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=5)
-    assert obs.shape == (4, 9 + 9 + 7 + 7 + 7 + 3 + 3 + 3)
-    a, b = env.cubeA.pose.p, env.cubeB.pose.p
-    assert (torch.linalg.norm(a[:, :2] - b[:, :2], dim=1) > 2 * (0.02 * 2 ** 0.5 + 0.001) - 1e-6).all()
-    assert torch.allclose(a[:, 2], torch.full((4,), 0.02)) and torch.allclose(b[:, 2], torch.full((4,), 0.02))
-    assert not env.evaluate()["success"].any()
-    from maniskill_b200.structs import Pose
-    top = env.cubeB.pose.raw_pose.clone()
-    top[:, 2] += 0.041  # 1 mm above the lower cube
-    env.cubeA.set_pose(Pose(top))
-    env.scene._gpu_apply_all()
-    for _ in range(10):
-        obs, r, te, tr, info = env.step(torch.zeros(4, 8))
-    assert info["is_cubeA_on_cubeB"].all() and info["is_cubeA_static"].all() and not info["is_cubeA_grasped"].any()
-    assert info["success"].all() and torch.allclose(r, torch.ones(4))
-    assert (env.cubeA.pose.p[:, 2] - 0.06).abs().max() < 2e-3
 
 
 def test_scripted_pick_and_lift_with_the_ee_controller():
@@ -321,105 +269,12 @@ def test_reset_to_env_states_restores_a_saved_episode():
     assert env.elapsed_steps.tolist()[0] == 0 and env.elapsed_steps.tolist()[1] == 9
 
 
-def test_pull_cube_reset_layout():
-    env = ms.make("PullCube-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=0)
-    assert obs.shape == (3, 9 + 9 + 7 + 3 + 7)
-    cube, goal = env.obj.pose.p, env.goal_region.pose.p
-    assert torch.allclose(goal[:, :2], cube[:, :2] - torch.tensor([0.2, 0.0]), atol=1e-6)   # the goal lies towards the robot
-    o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert not info["success"].any() and torch.isfinite(r).all() and (r < 1).all()
 
 
-def test_lift_peg_upright_reset_and_an_upright_peg_counts_as_success():
-    """LiftPegUpright-v1 (lift_peg_upright.py): the peg starts lying along the world x axis rolled a quarter turn about it, 32-dim state
-    observation, and that peg tipped up about the world y axis and set down on its small face settles and is reported upright (the
-    reference reads the third XYZ Euler angle, which is +-pi/2 for every upright pose reached this way)."""
-    from maniskill_b200 import utils as U
-    from maniskill_b200.structs import Pose
-    env = ms.make("LiftPegUpright-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=1)
-    assert obs.shape == (3, 9 + 9 + 7 + 7)
-    p, q = env.peg.pose.p, env.peg.pose.q
-    assert (p[:, :2].abs() <= 0.1 + 1e-6).all() and torch.allclose(p[:, 2], torch.full((3,), 0.025))
-    assert torch.allclose(q, torch.tensor([0.5 ** 0.5, 0.5 ** 0.5, 0.0, 0.0]).expand(3, 4), atol=1e-6)
-    o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert not info["success"].any() and (r < 1).all() and torch.isfinite(r).all()
-    up = env.peg.pose.raw_pose.clone()
-    up[:, 0] += 0.2   # clear of the gripper, which hovers above the spawn area
-    up[:, 2] = 0.121
-    tip = torch.tensor([0.5 ** 0.5, 0.0, -(0.5 ** 0.5), 0.0]).expand(3, 4)  # about world y: +x (the long axis) to +z
-    up[:, 3:] = U.quat_mul(tip, q)
-    env.peg.set_pose(Pose(up))
-    env.scene._gpu_apply_all()
-    for _ in range(10):
-        o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert info["success"].all() and torch.allclose(r, torch.ones(3))
-    assert (env.peg.pose.p[:, 2] - 0.12).abs().max() < 2e-3
 
 
-def test_poke_cube_reset_layout_and_a_cube_in_the_goal():
-    """PokeCube-v1 (poke_cube.py): peg, cube and goal are laid out along +x (cube 10 cm beyond the peg head, goal 10 cm beyond the cube),
-    the cube's yaw stays within +-30 degrees, 54-dim state observation; a cube moved into the goal with the arm at rest is a success."""
-    from maniskill_b200.structs import Pose
-    env = ms.make("PokeCube-v1", num_envs=4, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=3)
-    assert obs.shape == (4, 9 + 9 + 7 + 7 + 7 + 3 * 5)
-    peg, cube, goal = env.peg.pose.p, env.cube.pose.p, env.goal_region.pose.p
-    assert torch.allclose(cube[:, 0], peg[:, 0] + 0.22, atol=1e-6) and (cube[:, 1].abs() <= 0.1 + 1e-6).all()
-    assert torch.allclose(goal[:, :2], cube[:, :2] + torch.tensor([0.1, 0.0]), atol=1e-6)
-    yaw = 2 * torch.atan2(env.cube.pose.q[:, 3], env.cube.pose.q[:, 0])
-    assert (yaw.abs() <= np.pi / 6 + 1e-5).all() and torch.allclose(env.cube.pose.q[:, 1:3], torch.zeros(4, 2), atol=1e-6)
-    assert torch.allclose(env.peg_head_pos, peg + torch.tensor([0.12, 0.0, 0.0]))
-    o, r, te, tr, info = env.step(torch.zeros(4, 8))
-    assert not info["success"].any() and not info["is_peg_grasped"].any() and (r < 0.2).all()
-    assert torch.allclose(info["head_to_cube_dist"], torch.linalg.norm((env.peg_head_pos - env.cube.pose.p)[:, :2], dim=1))
-    moved = env.cube.pose.raw_pose.clone()
-    moved[:, :2] = env.goal_region.pose.p[:, :2] + 0.01
-    env.cube.set_pose(Pose(moved))
-    env.scene._gpu_apply_all()
-    for _ in range(3):
-        o, r, te, tr, info = env.step(torch.zeros(4, 8))
-    assert info["is_cube_placed"].all() and info["success"].all() and torch.allclose(r, torch.ones(4))
 
 
-def test_roll_ball_reset_layout_stateful_reward_and_a_rolling_ball():
-    """RollBall-v1 (roll_ball.py): robot at the side of the table, ball in front of it, goal at the far end, 44-dim state observation;
-    `reached_status` latches once the TCP has been at the hit point and is cleared by a (partial) reset; a ball given a push towards
-    the goal rolls there (sphere on plane: rolling, not sliding) and is reported as success."""
-    env = ms.make("RollBall-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=2)
-    assert obs.shape == (3, 9 + 9 + 7 + 3 + 7 + 3 + 3 + 3)
-    ball, goal = env.ball.pose.p.clone(), env.goal_region.pose.p.clone()
-    assert ((ball[:, 0] + 0.1).abs() <= 0.3 + 1e-6).all() and (ball[:, 1] >= 0.5).all() and (ball[:, 1] <= 0.7).all()
-    assert ((goal[:, 0] + 0.1).abs() <= 0.3 + 1e-6).all() and (goal[:, 1] >= -0.9).all() and (goal[:, 1] <= -0.7).all()
-    assert torch.allclose(env.agent.robot.pose.p, torch.tensor([-0.1, 1.0, 0.0]).expand(3, 3))
-    tcp = env.agent.tcp.pose.p
-    assert (tcp[:, 1] < 0.6).all() and (tcp[:, 1] > 0.2).all()   # the arm reaches over the table towards -y
-    o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert (env.reached_status == 0).all() and (r < 1 / 30).all() and (r > 0).all()
-    # latch: pretend the TCP was at the hit point of env 1
-    env.reached_status[1] = 1.0
-    o, r2, te, tr, info = env.step(torch.zeros(3, 8))
-    d = torch.linalg.norm((env.ball.pose.p - env.goal_region.pose.p)[:, :2], dim=1)
-    assert torch.allclose(r2[1], (20 * (1 - torch.tanh(d[1])) + 1) / 30, atol=1e-5) and torch.allclose(r2[[0, 2]], r[[0, 2]], atol=1e-3)
-    env.reset(options=dict(env_idx=torch.tensor([1])))
-    assert (env.reached_status == 0).all()
-    # roll the balls at the goals
-    ball, goal = env.ball.pose.p, env.goal_region.pose.p
-    dirn = (goal - ball)[:, :2]
-    dist = torch.linalg.norm(dirn, dim=1, keepdim=True)
-    v = torch.zeros(3, 3)
-    v[:, :2] = dirn / dist * 1.5
-    env.ball.set_linear_velocity(v)
-    env.scene._gpu_apply_all()
-    hit = torch.zeros(3, dtype=torch.bool)
-    for _ in range(60):
-        o, r, te, tr, info = env.step(torch.zeros(3, 8))
-        hit |= info["success"]
-    assert hit.all(), (env.ball.pose.p, env.goal_region.pose.p)
-    w = env.ball.angular_velocity
-    assert (torch.linalg.norm(w, dim=1) > 1.0).any() or (torch.linalg.norm(env.ball.linear_velocity, dim=1) < 0.05).all()
 
 
 def test_seeded_sequence_reset_with_enhanced_determinism():
@@ -482,7 +337,7 @@ def test_reconfigure_rebuilds_the_scene():
 def test_tabletop_tasks_accept_the_wrist_camera_panda():
     """SUPPORTED_ROBOTS of the tabletop tasks (pick_cube.py:40 ...): `robot_uids="panda_wristcam"` loads the v3 Panda (camera link on the
     hand), rests with the last arm joint turned the other way (table/scene_builder.py:104-108) and adds the hand camera to the sensors;
-    unknown robots are refused; RollBall-v1 keeps the reference's panda-only list."""
+    unknown robots are refused."""
     env = ms.make("PickCube-v1", num_envs=2, obs_mode="state", robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
     obs, _ = env.reset(seed=0)
     assert obs.shape == (2, 42) and "panda_wristcam" in env.scene.articulations and "camera_link" in env.agent.robot.links_map
@@ -495,24 +350,22 @@ def test_tabletop_tasks_accept_the_wrist_camera_panda():
     for _ in range(3):
         obs, r, te, tr, info = env.step(torch.zeros(2, 8))
     assert torch.isfinite(obs).all()
-    vis = ms.make("PushCube-v1", num_envs=1, obs_mode="rgbd", robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
+    vis = ms.make("PickCube-v1", num_envs=1, obs_mode="rgbd", robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
     o, _ = vis.reset(seed=0)
     assert set(o["sensor_data"]) == {"base_camera", "hand_camera"} and o["sensor_data"]["hand_camera"]["rgb"].shape == (1, 128, 128, 3)
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, robot_uids="xarm6_robotiq", world_factory=EmuBackendWorld)
-    with pytest.raises(NotImplementedError):
-        ms.make("RollBall-v1", num_envs=1, robot_uids="panda_wristcam", world_factory=EmuBackendWorld)
 
 
 def test_enhanced_determinism_draws_robot_noise_per_sub_scene():
     """table/scene_builder.py:85-97: with enhanced determinism every sub-scene takes its rest-pose noise from its own generator, so a
     sub-scene's reset does not depend on which other sub-scenes are reset with it."""
-    env = ms.make("PushCube-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
+    env = ms.make("PickCube-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
     env.reset(seed=[5, 6, 7])
     q_all = env.agent.robot.get_qpos().clone()
     env.reset(seed=[5, 6, 7])
     assert torch.allclose(env.agent.robot.get_qpos(), q_all)
-    solo = ms.make("PushCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
+    solo = ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld, enhanced_determinism=True)
     solo.reset(seed=[6])
     assert torch.allclose(solo.agent.robot.get_qpos()[0], q_all[1], atol=1e-6)
 
@@ -520,7 +373,7 @@ def test_enhanced_determinism_draws_robot_noise_per_sub_scene():
 def test_joint_velocity_control_modes():
     """panda.py:143-170 / pd_joint_vel.py / pd_joint_pos_vel.py: `pd_joint_vel` drives without stiffness towards a velocity target
     (action in [-1, 1] rad/s per arm joint); `pd_joint_delta_pos_vel` / `pd_joint_pos_vel` take [position part | velocity part]."""
-    env = ms.make("PushCube-v1", num_envs=2, obs_mode="state", control_mode="pd_joint_vel", world_factory=EmuBackendWorld)
+    env = ms.make("PickCube-v1", num_envs=2, obs_mode="state", control_mode="pd_joint_vel", world_factory=EmuBackendWorld)
     env.reset(seed=0)
     assert env.action_dim == 8
     q0 = env.agent.robot.get_qpos().clone()
@@ -538,7 +391,7 @@ def test_joint_velocity_control_modes():
     env.reset(options=dict(env_idx=torch.tensor([0])))
     assert torch.equal(env.scene.world.target_qvel[0, :7], torch.zeros(7)) and float(env.scene.world.target_qvel[1, 0]) == -1.0
 
-    dpv = ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_delta_pos_vel", world_factory=EmuBackendWorld)
+    dpv = ms.make("PickCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_delta_pos_vel", world_factory=EmuBackendWorld)
     dpv.reset(seed=0)
     assert dpv.action_dim == 7 + 7 + 1
     q0 = dpv.agent.robot.get_qpos().clone()
@@ -547,117 +400,17 @@ def test_joint_velocity_control_modes():
     dpv.step(a)
     assert float(dpv.scene.world.target_qpos[0, 0]) == pytest.approx(float(q0[0, 0]) + 0.1, abs=1e-6)
     assert float(dpv.scene.world.target_qvel[0, 0]) == pytest.approx(0.3, abs=1e-6)
-    pv = ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos_vel", world_factory=EmuBackendWorld)
+    pv = ms.make("PickCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos_vel", world_factory=EmuBackendWorld)
     pv.reset(seed=0)
     lo, hi = pv.single_action_space_low, pv.single_action_space_high
     assert pv.action_dim == 15 and np.allclose(lo[7:14], -1) and np.allclose(hi[7:14], 1) and lo[0] == pytest.approx(-2.8973, abs=1e-4)
 
 
-def test_place_sphere_reset_layout_and_a_sphere_in_the_bin():
-    """PlaceSphere-v1 (place_sphere.py): sphere in the near quarter, bin in the far half, 39-dim state observation; a sphere dropped into
-    the bin comes to rest on the bottom plate between the four rims and counts as placed, static and released."""
-    from maniskill_b200.structs import Pose
-    env = ms.make("PlaceSphere-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=2)
-    assert obs.shape == (3, 9 + 9 + 1 + 7 + 3 + 7 + 3)
-    s, b = env.obj.pose.p, env.bin.pose.p
-    assert (s[:, 0] >= -0.1 - 1e-6).all() and (s[:, 0] <= -0.05 + 1e-6).all() and torch.allclose(s[:, 2], torch.full((3,), 0.02))
-    assert (b[:, 0] >= 0).all() and (b[:, 0] <= 0.1 + 1e-6).all() and torch.allclose(b[:, 2], torch.full((3,), 0.0025))
-    o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert not info["success"].any() and (r < 2 / 13 + 1e-6).all()
-    drop = env.obj.pose.raw_pose.clone()
-    drop[:, :2] = b[:, :2] + torch.tensor([0.003, -0.002])          # slightly off centre: the rims keep it in
-    drop[:, 2] = 0.0025 * 2 + 0.02 + 0.01
-    env.obj.set_pose(Pose(drop))
-    env.scene._gpu_apply_all()
-    for _ in range(12):
-        o, r, te, tr, info = env.step(torch.zeros(3, 8))
-    assert info["is_obj_on_bin"].all() and info["is_obj_static"].all() and not info["is_obj_grasped"].any()
-    assert info["success"].all() and torch.allclose(r, torch.ones(3))
-    assert (env.obj.pose.p[:, 2] - (0.005 + 0.02)).abs().max() < 1e-3
 
 
-def test_stack_pyramid_layout_reward_modes_and_a_built_pyramid():
-    """StackPyramid-v1 (stack_pyramid.py): three cubes that never start overlapping, 64-dim state observation, sparse reward by default
-    (the task supports "none" and "sparse" only); red next to green with blue resting on both counts as success."""
-    from maniskill_b200.structs import Pose
-    env = ms.make("StackPyramid-v1", num_envs=3, obs_mode="state", world_factory=EmuBackendWorld)
-    assert env.reward_mode == "none" and env.robot_uids == "panda_wristcam"
-    with pytest.raises(NotImplementedError):
-        ms.make("StackPyramid-v1", num_envs=1, reward_mode="dense", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=4)
-    assert obs.shape == (3, 9 + 9 + 7 + 21 + 18)
-    ps = [c.pose.p for c in (env.cubeA, env.cubeB, env.cubeC)]
-    for i in range(3):
-        for j in range(i + 1, 3):
-            assert (torch.linalg.norm((ps[i] - ps[j])[:, :2], dim=1) > 2 * 0.02 * 2 ** 0.5 - 1e-6).all()
-    assert not env.evaluate()["success"].any()
-    sp = ms.make("StackPyramid-v1", num_envs=3, obs_mode="state", reward_mode="sparse", world_factory=EmuBackendWorld)
-    sp.reset(seed=4)
-    base = torch.tensor([0.1, 0.25, 0.02])                 # away from the gripper
-    ident = torch.tensor([1.0, 0, 0, 0])
-    for cube, off in ((sp.cubeA, [0.0, 0.0, 0.0]), (sp.cubeB, [0.0, 0.0405, 0.0]), (sp.cubeC, [0.0, 0.02025, 0.041])):
-        cube.set_pose(Pose(torch.cat([base + torch.tensor(off), ident])[None].repeat(3, 1)))
-    sp.scene._gpu_apply_all()
-    for _ in range(12):
-        o, r, te, tr, info = sp.step(torch.zeros(3, 8))
-    assert info["success"].all() and torch.equal(r, torch.ones(3)) and te.all()
-    assert (sp.cubeC.pose.p[:, 2] - 0.06).abs().max() < 2e-3
 
 
-def test_pull_cube_tool_layout_and_dragging_the_cube_with_the_tool():
-    """PullCubeTool-v1 (pull_cube_tool.py): tool within reach (x, y in [-0.3, -0.1]), cube beyond it, 39-dim state observation; the hook of
-    the L-shaped tool (two boxes in one body, handle at half density) drags the cube along when the tool is pulled towards the robot."""
-    from maniskill_b200.structs import Pose
-    env = ms.make("PullCubeTool-v1", num_envs=2, obs_mode="state", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=1)
-    assert obs.shape == (2, 9 + 9 + 7 + 7 + 7)
-    tool, cube = env.l_shape_tool.pose.p, env.cube.pose.p
-    assert (tool[:, :2] <= -0.1 + 1e-6).all() and (tool[:, :2] >= -0.3 - 1e-6).all() and torch.allclose(tool[:, 2], torch.full((2,), 0.025))
-    assert (cube[:, 0] >= 0.05 - 1e-6).all() and (cube[:, 0] <= 0.25 + 1e-6).all()
-    o, r, te, tr, info = env.step(torch.zeros(2, 8))
-    assert info["success"].shape == (2,) and info["cube_progress"].dim() == 0 and torch.isfinite(r).all()
-    # hook the cube: tool placed so that its hook (at x = 0.15..0.2, y = 0..0.1 in the tool frame) sits just beyond the cube, then drag it back
-    start = env.cube.pose.p.clone()
-    tp = torch.zeros(2, 7)
-    tp[:, 3] = 1.0
-    tp[:, 0] = start[:, 0] - 0.15 + 0.03
-    tp[:, 1] = start[:, 1] - 0.05
-    tp[:, 2] = 0.025
-    env.l_shape_tool.set_pose(Pose(tp))
-    env.scene._gpu_apply_all()
-    for _ in range(30):
-        tp[:, 0] -= 0.004
-        env.l_shape_tool.set_pose(Pose(tp.clone()))
-        env.l_shape_tool.set_linear_velocity(torch.tensor([-0.08, 0.0, 0.0]))
-        env.scene._gpu_apply_all()
-        env.step(torch.zeros(2, 8))
-    assert (env.cube.pose.p[:, 0] < start[:, 0] - 0.05).all()       # the cube came along
 
 
-def test_plug_charger_layout_and_a_plugged_in_charger():
-    """PlugCharger-v1 (plug_charger.py): 46-dim state observation, receptacle facing the robot 10 cm above the table, sparse reward modes only;
-    a charger set into the receptacle (pins in the 0.5 mm-clearance slots) stays put under gravity and counts as success."""
-    env = ms.make("PlugCharger-v1", num_envs=2, obs_mode="state", reward_mode="sparse", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=2)
-    assert obs.shape == (2, 9 + 9 + 7 + 21) and env.agent.uid == "panda_wristcam"
-    assert torch.allclose(env.receptacle.pose.p[:, 2], torch.full((2,), 0.1)) and (env.charger.pose.p[:, 0] < 0).all()
-    o, r, te, tr, info = env.step(torch.zeros(2, 8))
-    assert not info["success"].any() and (info["obj_to_goal_dist"] > 0.05).all() and torch.equal(r, torch.zeros(2))
-    env.charger.set_pose(env.goal_pose)
-    env.scene._gpu_apply_all()
-    for _ in range(10):
-        o, r, te, tr, info = env.step(torch.zeros(2, 8))
-    assert info["success"].all() and torch.equal(r, torch.ones(2)), (info["obj_to_goal_dist"], info["obj_to_goal_angle"])
-    assert (info["obj_to_goal_dist"] < 4e-3).all()        # held by the slots: the cantilevered base sags within the clearance
-    img = ms.make("PlugCharger-v1", num_envs=1, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld)
-    img.reset(seed=0)
-    assert img.render().shape == (1, 512, 512, 3)         # the human camera is mounted on the receptacle actor
 
 
-def test_stack_cube_accepts_the_plain_panda():
-    """stack_cube.py:36: SUPPORTED_ROBOTS = ["panda_wristcam", "panda", "fetch"] -- the plain Panda loads without the hand camera."""
-    env = ms.make("StackCube-v1", num_envs=2, obs_mode="rgbd", robot_uids="panda", world_factory=EmuBackendWorld)
-    obs, _ = env.reset(seed=0)
-    assert set(obs["sensor_data"]) == {"base_camera"} and env.agent.uid == "panda" and "camera_link" not in env.agent.robot.links_map
-    assert (env.agent.robot.get_qpos()[:, 6] - np.pi / 4).abs().max() < 0.1

@@ -16,11 +16,11 @@ def test_demo_random_action_records_a_rollout(tmp_path, monkeypatch, capsys):
     pytest.importorskip("cv2")
     make = ms.make
     monkeypatch.setattr(ms, "make", lambda *a, **k: make(*a, world_factory=EmuBackendWorld, **k))
-    monkeypatch.setattr(sys, "argv", ["demo_random_action.py", "-e", "PushCube-v1", "-n", "2", "-o", "state", "--record-dir", str(tmp_path),
+    monkeypatch.setattr(sys, "argv", ["demo_random_action.py", "-e", "PickCube-v1", "-n", "2", "-o", "state", "--record-dir", str(tmp_path),
                                       "--render-mode", "sensors", "-s", "1"])
     runpy.run_path(os.path.join(ROOT, "examples", "demo_random_action.py"), run_name="__main__")
     out = capsys.readouterr().out
     assert "50 control steps" in out and "success rate" in out
     meta = json.load(open(tmp_path / "trajectory.json"))
-    assert meta["env_info"]["env_id"] == "PushCube-v1" and [e["elapsed_steps"] for e in meta["episodes"]] == [50, 50]
+    assert meta["env_info"]["env_id"] == "PickCube-v1" and [e["elapsed_steps"] for e in meta["episodes"]] == [50, 50]
     assert (tmp_path / "0.mp4").stat().st_size > 1000

@@ -151,18 +151,6 @@ def test_open_cabinet_drawer_evaluate_reward_obs():
     close(U.flatten_state_dict(CE._get_obs_extra(fake, info)), G["cab_extra_flat"], 2e-6)
 
 
-def test_push_cube_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/push_cube.py:179-241 run by the reference's own code on the same synthetic states."""
-    from maniskill_b200.envs.push_cube import PushCubeEnv as PU
-    m = len(G["push_success"])
-    goal = Pose(torch.hstack([T("push_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
-    fake = SimpleNamespace(obj=SimpleNamespace(pose=Pose(T("push_obj"))), goal_region=SimpleNamespace(pose=goal),
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("push_tcp")))), goal_radius=0.1, cube_half_size=0.02, obs_mode="state")
-    info = PU.evaluate(fake)
-    assert np.array_equal(info["success"].numpy(), G["push_success"])
-    assert G["push_success"].any() and not G["push_success"].all()
-    close(PU.compute_dense_reward(fake, None, None, info), G["push_reward"], 2e-6)
-    close(U.flatten_state_dict(PU._get_obs_extra(fake, info)), G["push_extra_flat"], 1e-6)
 
 
 def test_uniform_placement_sampler_same_stream_as_the_reference():
@@ -175,22 +163,6 @@ def test_uniform_placement_sampler_same_stream_as_the_reference():
     assert (d01 > 0.06).all()  # the constraint the sampler enforces (and the bounds are tight enough that rejections happened)
 
 
-def test_stack_cube_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/stack_cube.py:115-200 run by the reference's own code on the same synthetic states."""
-    from maniskill_b200.envs.stack_cube import StackCubeEnv as SC
-    grasped, qpos = T("stack_grasped"), T("stack_qpos")
-    qlim = torch.zeros(1, 9, 2)
-    qlim[0, :, 1] = 0.04
-    fake = SimpleNamespace(cubeA=SimpleNamespace(pose=Pose(T("stack_A")), linear_velocity=T("stack_A_lin"), angular_velocity=T("stack_A_ang")),
-                           cubeB=SimpleNamespace(pose=Pose(T("stack_B"))), cube_half_size=torch.tensor([0.02] * 3), obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("stack_tcp"))), is_grasping=lambda obj: grasped,
-                                                 robot=SimpleNamespace(get_qlimits=lambda: qlim, get_qpos=lambda: qpos)))
-    info = SC.evaluate(fake)
-    for k in ("is_cubeA_on_cubeB", "is_cubeA_static", "success"):
-        assert np.array_equal(info[k].numpy(), G["stack_" + k]), k
-    assert G["stack_is_cubeA_on_cubeB"].any() and not G["stack_is_cubeA_on_cubeB"].all()
-    close(SC.compute_dense_reward(fake, None, None, info), G["stack_reward"], 2e-6)
-    close(U.flatten_state_dict(SC._get_obs_extra(fake, info)), G["stack_extra_flat"], 1e-6)
 
 
 class _FakeArticulation:
@@ -294,72 +266,12 @@ def test_vector_wrapper_metrics_and_auto_reset_match_the_reference():
         close(venv.returns, G[f"vec_returns_after_{t}"])
 
 
-def test_pull_cube_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/pull_cube.py:105-152 run by the reference's own code on the same synthetic states."""
-    from maniskill_b200.envs.pull_cube import PullCubeEnv as PL
-    m = len(G["pull_success"])
-    goal = Pose(torch.hstack([T("push_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
-    fake = SimpleNamespace(obj=SimpleNamespace(pose=Pose(T("push_obj"))), goal_region=SimpleNamespace(pose=goal),
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("pull_tcp")))), goal_radius=0.1, cube_half_size=0.02, obs_mode="state")
-    info = PL.evaluate(fake)
-    assert np.array_equal(info["success"].numpy(), G["pull_success"])
-    close(PL.compute_dense_reward(fake, None, None, info), G["pull_reward"], 2e-6)
-    close(U.flatten_state_dict(PL._get_obs_extra(fake, info)), G["pull_extra_flat"], 1e-6)
 
 
-def test_lift_peg_upright_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/lift_peg_upright.py:88-137 run by the reference's own code on the same synthetic states
-    (lying, upright within and outside the height band, arbitrary)."""
-    from maniskill_b200.envs.lift_peg_upright import LiftPegUprightEnv as LP
-    grasp = T("lift_grasp")
-    peg = SimpleNamespace(pose=Pose(T("lift_peg")))
-    fake = SimpleNamespace(peg=peg, peg_half_length=0.12, obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("lift_tcp"))), is_grasping=lambda o: grasp))
-    info = LP.evaluate(fake)
-    assert np.array_equal(info["success"].numpy(), G["lift_success"])
-    assert G["lift_success"].any() and not G["lift_success"].all()
-    close(LP.compute_dense_reward(fake, None, None, info), G["lift_reward"], 2e-6)
-    close(U.flatten_state_dict(LP._get_obs_extra(fake, info)), G["lift_extra_flat"], 1e-6)
 
 
-def test_poke_cube_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/poke_cube.py:126-276 run by the reference's own code on the same synthetic states; all reward
-    branches occur (reaching, grasped, peg fitted to the cube, cube placed with a moving arm, success)."""
-    from maniskill_b200.envs.poke_cube import PokeCubeEnv as PK
-    m = len(G["poke_success"])
-    grasp, static, qvel = T("poke_grasp"), T("poke_static"), T("poke_qvel")
-    goal = Pose(torch.hstack([T("poke_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
-    fake = SimpleNamespace(cube=SimpleNamespace(pose=Pose(T("poke_cube"))), peg=SimpleNamespace(pose=Pose(T("poke_peg"))), goal_region=SimpleNamespace(pose=goal),
-                           goal_radius=0.05, cube_half_size=0.02, peg_head_offsets=Pose.create_from_pq(torch.tensor([[0.12, 0.0, 0.0]])), obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("poke_tcp"))), is_grasping=lambda o: grasp, is_static=lambda t: static,
-                                                 robot=SimpleNamespace(get_qvel=lambda: qvel)))
-    fake.peg_head_pos = PK.peg_head_pos.fget(fake)
-    fake.peg_head_pose = PK.peg_head_pose.fget(fake)
-    info = PK.evaluate(fake)
-    for k in ("success", "is_cube_placed", "is_peg_cube_fit", "is_peg_grasped"):
-        assert np.array_equal(info[k].numpy(), G[f"poke_{k}"]), k
-    close(info["angle_diff"], G["poke_angle_diff"], 2e-6)
-    close(info["head_to_cube_dist"], G["poke_head_to_cube_dist"], 1e-6)
-    ref = G["poke_reward"]
-    assert (ref == 10).any() and ((ref > 7) & (ref < 10)).any() and ((ref > 4) & (ref < 7)).any() and (ref < 4).any()
-    close(PK.compute_dense_reward(fake, None, None, info), ref, 5e-6)
-    close(U.flatten_state_dict(PK._get_obs_extra(fake, info)), G["poke_extra_flat"], 1e-6)
 
 
-def test_roll_ball_evaluate_reward_obs_and_the_latched_status():
-    """mani_skill/envs/tasks/tabletop/roll_ball.py:130-189 run by the reference's own code on the same synthetic states: the reward
-    latches `reached_status` for the envs whose TCP is at the hit point and uses the latched value in the same call."""
-    from maniskill_b200.envs.roll_ball import RollBallEnv as RB
-    m = len(G["roll_success"])
-    goal = Pose(torch.hstack([T("roll_goal"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
-    fake = SimpleNamespace(ball=SimpleNamespace(pose=Pose(T("roll_ball")), linear_velocity=T("roll_vel")), goal_region=SimpleNamespace(pose=goal),
-                           goal_radius=0.1, ball_radius=0.035, reached_status=T("roll_status0").clone(), obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("roll_tcp")))))
-    info = RB.evaluate(fake)
-    assert np.array_equal(info["success"].numpy(), G["roll_success"])
-    close(RB.compute_dense_reward(fake, None, None, info), G["roll_reward"], 2e-5)
-    assert np.array_equal(fake.reached_status.numpy(), G["roll_status1"]) and (G["roll_status1"] != G["roll_status0"]).any()
-    close(U.flatten_state_dict(RB._get_obs_extra(fake, info)), G["roll_extra_flat"], 1e-6)
 
 
 def test_camera_parameters_of_a_mounted_camera():
@@ -615,39 +527,5 @@ def test_velocity_controllers_match_the_reference_set_action():
     close(art.vel_sent, G["ctl_pv_vel_target"], 1e-7)
 
 
-def test_place_sphere_evaluate_reward_obs():
-    """mani_skill/envs/tasks/tabletop/place_sphere.py:186-265 run by the reference's own code on the same synthetic states (spheres in
-    and outside the bin, resting and moving, held and released)."""
-    from maniskill_b200.envs.place_sphere import PlaceSphereEnv as PS
-    m = len(G["place_success"])
-    lin, ang, grasp, rstatic, qpos = T("place_lin"), T("place_ang"), T("place_grasp"), T("place_rstatic"), T("place_qpos")
-    qlim = torch.tensor([[-2.9, 2.9]] * 7 + [[0.0, 0.04]] * 2)[None].repeat(m, 1, 1)
-    obj = SimpleNamespace(pose=Pose(T("place_sphere")), linear_velocity=lin, angular_velocity=ang)
-    obj.is_static = lambda lin_thresh=1e-2, ang_thresh=1e-1: (lin.norm(dim=1) <= lin_thresh) & (ang.norm(dim=1) <= ang_thresh)
-    bin_pose = Pose(torch.hstack([T("place_bin"), torch.tensor([[1.0, 0, 0, 0]]).expand(m, 4)]))
-    fake = SimpleNamespace(obj=obj, bin=SimpleNamespace(pose=bin_pose), radius=0.02, block_half_size=PS.block_half_size, obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("place_tcp"))), is_grasping=lambda o: grasp, is_static=lambda t: rstatic,
-                                                 robot=SimpleNamespace(get_qlimits=lambda: qlim, get_qpos=lambda: qpos)))
-    info = PS.evaluate(fake)
-    for k in ("is_obj_grasped", "is_obj_on_bin", "is_obj_static", "success"):
-        assert np.array_equal(info[k].numpy(), G[f"place_{k}"]), k
-    assert G["place_success"].any() and not G["place_success"].all()
-    close(PS.compute_dense_reward(fake, None, None, info), G["place_reward"], 5e-6)
-    close(U.flatten_state_dict(PS._get_obs_extra(fake, info)), G["place_extra_flat"], 1e-6)
 
 
-def test_stack_pyramid_evaluate_obs():
-    """mani_skill/envs/tasks/tabletop/stack_pyramid.py:147-207 run by the reference's own code on the same synthetic states (built
-    pyramids, near misses, moving or held cubes)."""
-    from maniskill_b200.envs.stack_pyramid import StackPyramidEnv as SP
-    cubes = {}
-    for n in "ABC":
-        c = SimpleNamespace(pose=Pose(T(f"pyr_{n}")), tag=n)
-        c.is_static = (lambda s: (lambda lin_thresh=1e-2, ang_thresh=0.5: s))(T(f"pyr_static_{n}"))
-        cubes[n] = c
-    fake = SimpleNamespace(cubeA=cubes["A"], cubeB=cubes["B"], cubeC=cubes["C"], cube_half_size=torch.tensor([0.02] * 3), obs_mode="state",
-                           agent=SimpleNamespace(tcp=SimpleNamespace(pose=Pose(T("pyr_tcp"))), is_grasping=lambda c: T(f"pyr_grasp_{c.tag}")))
-    fake._pair_ok = lambda offset, cube, on_top: SP._pair_ok(fake, offset, cube, on_top)
-    info = SP.evaluate(fake)
-    assert np.array_equal(info["success"].numpy(), G["pyr_success"]) and G["pyr_success"].any() and not G["pyr_success"].all()
-    close(U.flatten_state_dict(SP._get_obs_extra(fake, info)), G["pyr_extra_flat"], 1e-6)

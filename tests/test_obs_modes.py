@@ -119,9 +119,9 @@ def test_wrist_camera_follows_its_mount():
 
 
 def test_flatten_wrappers_on_an_env():
-    """flatten.py:13-95 in place: PPO-RGB style observation from StackCube-v1 (two cameras), under the vector wrapper."""
+    """flatten.py:13-95 in place: PPO-RGB style observation from PegInsertionSide-v1 (two cameras), under the vector wrapper."""
     from maniskill_b200.wrappers import FlattenObservationWrapper, FlattenRGBDObservationWrapper
-    env = ms.make("StackCube-v1", num_envs=2, obs_mode="rgbd", world_factory=EmuBackendWorld)
+    env = ms.make("PegInsertionSide-v1", num_envs=2, obs_mode="rgbd", world_factory=EmuBackendWorld)
     venv = ms.ManiSkillVectorEnv(FlattenRGBDObservationWrapper(env, rgb=True, depth=True, state=True), auto_reset=True)
     obs, _ = venv.reset(seed=0)
     assert set(obs) == {"state", "rgb", "depth"}
@@ -163,7 +163,7 @@ def test_render_modes():
         env.render()
     with pytest.raises(NotImplementedError):
         ms.make("PickCube-v1", num_envs=1, render_mode="human", world_factory=EmuBackendWorld)
-    for task in ("StackCube-v1", "RollBall-v1", "OpenCabinetDrawer-v1"):
+    for task in ("PickCube-v1", "PegInsertionSide-v1", "OpenCabinetDrawer-v1"):
         e = ms.make(task, num_envs=1, obs_mode="state", render_mode="rgb_array", world_factory=EmuBackendWorld)
         e.reset(seed=0)
         im = e.render()

@@ -189,7 +189,7 @@ def test_reference_texture_transforms_on_our_render_targets(reference_module):
     shaders = reference_module("/root/reference/mani_skill/render/shaders.py")
     cfg = shaders.PREBUILT_SHADER_CONFIGS["minimal"]
     assert cfg.texture_names == {"Color": ["rgb"], "PositionSegmentation": ["position", "depth", "segmentation"]}
-    env = ms.make("StackCube-v1", num_envs=2, obs_mode="sensor_data", world_factory=EmuBackendWorld)
+    env = ms.make("PegInsertionSide-v1", num_envs=2, obs_mode="sensor_data", world_factory=EmuBackendWorld)
     obs, _ = env.reset(seed=0)
     group = env._sensors.group
     for i, cam in enumerate(env._sensors.cams):
@@ -244,12 +244,8 @@ def test_reference_pose_struct_over_the_sapien_shim():
 
 
 TASK_FILES = {
-    "PickCube-v1": ("pick_cube.py", "PickCubeEnv"), "PushCube-v1": ("push_cube.py", "PushCubeEnv"), "PullCube-v1": ("pull_cube.py", "PullCubeEnv"),
-    "StackCube-v1": ("stack_cube.py", "StackCubeEnv"), "LiftPegUpright-v1": ("lift_peg_upright.py", "LiftPegUprightEnv"),
-    "PokeCube-v1": ("poke_cube.py", "PokeCubeEnv"), "RollBall-v1": ("roll_ball.py", "RollBallEnv"), "PlaceSphere-v1": ("place_sphere.py", "PlaceSphereEnv"),
-    "StackPyramid-v1": ("stack_pyramid.py", "StackPyramidEnv"), "PegInsertionSide-v1": ("peg_insertion_side.py", "PegInsertionSideEnv"),
+    "PickCube-v1": ("pick_cube.py", "PickCubeEnv"), "PegInsertionSide-v1": ("peg_insertion_side.py", "PegInsertionSideEnv"),
     "OpenCabinetDrawer-v1": ("../mobile_manipulation/open_cabinet_drawer.py", "OpenCabinetDrawerEnv"),
-    "PullCubeTool-v1": ("pull_cube_tool.py", "PullCubeToolEnv"), "PlugCharger-v1": ("plug_charger.py", "PlugChargerEnv"),
 }
 
 
@@ -300,7 +296,7 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
                 assert torch.equal(env.reached_status, status1)
 
 
-INIT_TASKS = ["PickCube-v1", "PushCube-v1", "PullCube-v1", "StackCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1", "PegInsertionSide-v1", "PullCubeTool-v1", "PlugCharger-v1"]
+INIT_TASKS = ["PickCube-v1", "PegInsertionSide-v1"]
 
 
 @pytest.mark.parametrize("task", INIT_TASKS)
@@ -411,7 +407,7 @@ def test_reference_base_env_reset_drives_our_env(reference_module):
     se = reference_module("/root/reference/mani_skill/envs/sapien_env.py")
     se.common, se.BatchedRNG = common, brng.BatchedRNG
     RefBaseEnv = se.BaseEnv
-    for task in ("PickCube-v1", "PushCube-v1"):
+    for task in ("PickCube-v1",):
         ours, theirs = [ms.make(task, num_envs=4, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
         theirs._batched_rng_backend = "numpy:random_state"
         g = torch.Generator().manual_seed(1)
@@ -444,7 +440,7 @@ def test_reference_base_env_step_drives_our_env(reference_module):
     se.MultiAgent = type("MultiAgent", (), {})
     RefBaseEnv = se.BaseEnv
     calls = []
-    for task, mode, cm in (("PickCube-v1", "state", "pd_joint_delta_pos"), ("PushCube-v1", "state_dict", "pd_joint_vel"), ("PickCube-v1", "state+rgb", "pd_joint_pos")):
+    for task, mode, cm in (("PickCube-v1", "state", "pd_joint_delta_pos"), ("PickCube-v1", "state_dict", "pd_joint_vel"), ("PickCube-v1", "state+rgb", "pd_joint_pos")):
         ours, theirs = [ms.make(task, num_envs=3, obs_mode=mode, control_mode=cm, world_factory=EmuBackendWorld, fused=False,
                                 sensor_configs=dict(base_camera=dict(width=16, height=16))) for _ in range(2)]
         for e in (ours, theirs):
@@ -498,7 +494,7 @@ def test_reference_vector_wrapper_and_timelimit_around_our_env(reference_module)
     vw = reference_module("/root/reference/mani_skill/vector/wrappers/gymnasium.py")
     vw.common = common
     n, limit = 3, 7
-    ours_env, their_env = [ms.make("PushCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
+    ours_env, their_env = [ms.make("PickCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
     their_env.unwrapped = their_env
     tl = reg.TimeLimitWrapper.__new__(reg.TimeLimitWrapper)
     tl.env, tl._max_episode_steps = their_env, limit
@@ -566,7 +562,7 @@ def test_reference_record_episode_around_our_env(reference_module, tmp_path):
     rec_mod.common, rec_mod.dump_json = common, (lambda *a, **k: None)
     rec_mod.sapien_utils = SimpleNamespace(is_state_dict_consistent=lambda sd: True)
     n = 3
-    ours_env, their_env = [ms.make("PushCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
+    ours_env, their_env = [ms.make("PickCube-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld) for _ in range(2)]
     for e in (ours_env, their_env):
         e.max_episode_steps = None                   # the reference's recorder sees no TimeLimit here: compare the raw flags
     their_env.unwrapped = their_env
@@ -620,7 +616,7 @@ def test_reference_flatten_wrappers_on_our_live_observations(reference_module):
     fl = reference_module("/root/reference/mani_skill/utils/wrappers/flatten.py")
     fl.common = common
     for mode in ("rgbd", "state+rgb+depth"):
-        env = ms.make("StackCube-v1", num_envs=2, obs_mode=mode, world_factory=EmuBackendWorld, sensor_configs=dict(base_camera=dict(width=16, height=16), hand_camera=dict(width=16, height=16)))
+        env = ms.make("PegInsertionSide-v1", num_envs=2, obs_mode=mode, world_factory=EmuBackendWorld, sensor_configs=dict(base_camera=dict(width=16, height=16), hand_camera=dict(width=16, height=16)))
         obs, _ = env.reset(seed=0)
         for sep in (True, False):
             ref_self = SimpleNamespace(base_env=SimpleNamespace(device=torch.device("cpu")), include_rgb=True, include_depth=True, sep_depth=sep, include_state=True)

@@ -62,7 +62,7 @@ def test_empty_episodes_are_skipped_and_full_reset_flushes_everything(tmp_path):
 
 @pytest.mark.parametrize("mode", ["seed_and_actions", "env_states", "first_env_state"])
 def test_replay_reproduces_the_recording(tmp_path, mode):
-    env = ms.make("PushCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld)
+    env = ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld)
     rec = RecordEpisode(env, str(tmp_path))
     g = torch.Generator().manual_seed(5)
     for seed in (11, 12):
@@ -72,7 +72,7 @@ def test_replay_reproduces_the_recording(tmp_path, mode):
     rec.close()
     meta, trajs = load_trajectories(str(tmp_path / "trajectory"))
     assert [e["reset_kwargs"] for e in meta["episodes"]] == [{"seed": 11}, {"seed": 12}] and [e["episode_seed"] for e in meta["episodes"]] == [11, 12]
-    env2 = ms.make("PushCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld)
+    env2 = ms.make("PickCube-v1", num_envs=1, obs_mode="state", world_factory=EmuBackendWorld)
     if mode != "seed_and_actions":
         env2.reset(seed=999)        # a different layout: only the stored states can bring the recorded one back
     res = replay_trajectory(env2, str(tmp_path / "trajectory"), use_env_states=mode == "env_states", use_first_env_state=mode == "first_env_state")
@@ -80,7 +80,7 @@ def test_replay_reproduces_the_recording(tmp_path, mode):
     for r in res:
         assert r["final_state_error"] < 1e-5 and r["success"] == r["recorded_success"]
     with pytest.raises(ValueError):
-        replay_trajectory(ms.make("PushCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos", world_factory=EmuBackendWorld), str(tmp_path / "trajectory"))
+        replay_trajectory(ms.make("PickCube-v1", num_envs=1, obs_mode="state", control_mode="pd_joint_pos", world_factory=EmuBackendWorld), str(tmp_path / "trajectory"))
 
 
 def test_videos(tmp_path):
