@@ -2,7 +2,7 @@
 """Random-action rollout on the b200sim backend -- the counterpart of mani_skill/examples/demo_random_action.py (same short flags).
 
     python examples/demo_random_action.py -e PickCube-v1 -n 1024 -o state
-    python examples/demo_random_action.py -e StackCube-v1 -n 4 -o rgbd --record-dir out/     # trajectory .npz/.json + .mp4 per episode batch
+    python examples/demo_random_action.py -e PegInsertionSide-v1 -n 4 -o rgbd --record-dir out/     # trajectory .npz/.json + .mp4 per episode batch
 
 Runs until every sub-scene has finished one episode (success or the task's time limit) and prints the return / success statistics the
 vector wrapper keeps (mani_skill/vector/wrappers/gymnasium.py:131-156)."""
@@ -18,7 +18,7 @@ import maniskill_b200 as ms  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("-e", "--env-id", default="PushCube-v1", choices=sorted(ms.REGISTERED_ENVS))
+    ap.add_argument("-e", "--env-id", default="PickCube-v1", choices=sorted(ms.REGISTERED_ENVS))
     ap.add_argument("-o", "--obs-mode", default="state")
     ap.add_argument("-n", "--num-envs", type=int, default=1)
     ap.add_argument("-c", "--control-mode", default=None)

@@ -146,8 +146,7 @@ def load_glb_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, Tuple[float,
 
 
 def load_mesh_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, tuple]]:
-    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb`.  glTF's y-up axes are kept as stored: sapien loads
-    meshes through assimp, which leaves the vertex coordinates of the file untouched as well."""
+    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb` (vertex coordinates as stored, node transforms applied)."""
     ext = os.path.splitext(path)[1].lower()
     if not os.path.exists(path):
         raise RuntimeError(f"mesh file {path} does not exist")
