@@ -168,12 +168,33 @@ __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevS
   b2s::rowfill_env<C, ND, NUQ, L>(M, S, env, r);
 }
 
+// gpu_fetch_*: internal env-major SoA state -> the exposed AoS buffers.  One lane computes one sub-scene (FK + link velocities); its
+// [n_rows][13] block of rigid_body_data (936 B for PickCube-v1) is written to a shared-memory tile, and the tile of the CTA's 32
+// sub-scenes -- contiguous in HBM, 32 x n_rows x 52 B, a multiple of 16 -- leaves with ONE bulk asynchronous copy
+// (cp.async.bulk.global.shared::cta, the TMA engine) instead of 32 lanes storing single floats 936 B apart.  The staged path needs
+// the whole rows to be rewritten (mask has BUF_LINK and BUF_RIGID) and a full CTA; otherwise the lanes store directly.
+#define B2S_FETCH_EPB 32
 template <class C>
-__global__ void fetch_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask) {
-  int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= M.n_envs) return;
-  b2s::fetch_env<C>(M, S, env, mask);
+__global__ void __launch_bounds__(B2S_FETCH_EPB) fetch_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask) {
+  extern __shared__ __align__(128) float fetch_tile[];
+  const int env0 = blockIdx.x * B2S_FETCH_EPB, env = env0 + threadIdx.x;
+  const int per_env = M.n_rows * 13;
+  const unsigned tile_bytes = (unsigned)(B2S_FETCH_EPB * per_env * sizeof(float));
+  const bool staged = (mask & b2s::BUF_LINK) && (mask & b2s::BUF_RIGID) && env0 + B2S_FETCH_EPB <= M.n_envs && (tile_bytes % 16u) == 0;
+  if (env < M.n_envs) b2s::fetch_env<C>(M, S, env, mask, staged ? fetch_tile + (size_t)threadIdx.x * per_env : nullptr);
+  if (!staged) return;
+  // generic-proxy writes to shared memory must be visible to the async proxy before the bulk copy reads them
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* dst = S.body_data + (size_t)env0 * per_env;
+    const unsigned src = (unsigned)__cvta_generic_to_shared(fetch_tile);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(tile_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must stay alive until the engine has read it
+  }
 }
+static size_t fetch_smem(const b2s::DevModel& M) { return (size_t)B2S_FETCH_EPB * M.n_rows * 13 * sizeof(float); }
 
 __global__ void apply_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,8 +411,12 @@ int32_t b2s_world_create(const B2SModel* model, int32_t device, uint64_t* world)
   *world = h;
   // initial fetch so the exposed buffers are valid right after create (px.gpu_init semantics)
   int N = w->M.n_envs;
-  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + 63) / 64, 64>>>(w->M, w->S, 0xFFFFFFFFu);
-  else fetch_kernel<b2s::CapsL><<<(N + 63) / 64, 64>>>(w->M, w->S, 0xFFFFFFFFu);
+  if (fetch_smem(w->M) > 48 * 1024) {
+    cudaFuncSetAttribute(fetch_kernel<b2s::CapsS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fetch_smem(w->M));
+    cudaFuncSetAttribute(fetch_kernel<b2s::CapsL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fetch_smem(w->M));
+  }
+  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu);
+  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu);
   CK(cudaDeviceSynchronize());
   return B2S_OK;
 }
@@ -485,8 +510,8 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
       launch_solve(w->M, w->S, st);
     }
     if (fetch_mask) {
-      if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, fetch_mask);
-      else fetch_kernel<b2s::CapsL><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, fetch_mask);
+      if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, fetch_mask);
+      else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, fetch_mask);
     }
     CK(cudaGetLastError());
     return B2S_OK;
@@ -548,8 +573,8 @@ int32_t b2s_fetch(uint64_t world, uint32_t mask, void* stream) {
   DeviceGuard guard_(w->device);
   int N = w->M.n_envs;
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, mask);
-  else fetch_kernel<b2s::CapsL><<<(N + 63) / 64, 64, 0, st>>>(w->M, w->S, mask);
+  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask);
+  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask);
   CK(cudaGetLastError());
   return B2S_OK;
 }

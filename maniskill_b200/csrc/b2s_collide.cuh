@@ -608,6 +608,116 @@ B2S_HDN inline int hull_box_patch(const WShape& H, const WShape& Bx, v3 n_out, b
   return k;
 }
 
+// ---- convex mesh against convex mesh: a multi-point patch where PhysX's persistent manifold would have accumulated one over frames
+// (`enable_pcm`, mani_skill/utils/structs/types.py:50).  Around the GJK / EPA normal each hull has a SUPPORT FACE: its vertices within
+// `tol` of its supporting plane.  A support-face vertex of one hull whose foot point lies inside the other hull's support-face polygon
+// (both directions are tried) is a contact candidate, the separation measured along the normal; reduce4 keeps the deepest one and the
+// spread.  Faces with fewer than three vertices (edge / vertex contacts) and crossing edges fall back to the single GJK / EPA point.
+#define B2S_FACE_MAX 24
+struct FacePoly {
+  int n;
+  v3 c, t1, t2;        // centroid, in-plane basis
+  float x[B2S_FACE_MAX], y[B2S_FACE_MAX];  // vertices in the basis, counter-clockwise
+};
+// vertices of H within tol of its extreme along dir -> world points (at most B2S_FACE_MAX), returns the extreme value
+B2S_HDN inline float support_face(const WShape& H, v3 dir, float tol, v3* pts, int& n) {
+  float smax = -3.0e38f;
+  for (int i = 0; i < H.nverts; i++) {
+    v3 vw = H.X.p + mul(H.R, mk3(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2]));
+    smax = fmaxf(smax, dot(vw, dir));
+  }
+  n = 0;
+  for (int i = 0; i < H.nverts && n < B2S_FACE_MAX; i++) {
+    v3 vw = H.X.p + mul(H.R, mk3(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2]));
+    if (smax - dot(vw, dir) < tol) pts[n++] = vw;
+  }
+  return smax;
+}
+B2S_HDN inline bool face_polygon(const v3* pts, int n, v3 dir, FacePoly& P) {
+  P.n = 0;
+  if (n < 3) return false;
+  v3 c = mk3(0, 0, 0);
+  for (int i = 0; i < n; i++) c = c + pts[i];
+  c = c * (1.f / n);
+  v3 t1 = fabsf(dir.x) < 0.57735f ? normalized(cross(dir, mk3(1, 0, 0))) : normalized(cross(dir, mk3(0, 1, 0)));
+  v3 t2 = cross(dir, t1);
+  P.c = c; P.t1 = t1; P.t2 = t2; P.n = n;
+  for (int i = 0; i < n; i++) { v3 d = pts[i] - c; P.x[i] = dot(d, t1); P.y[i] = dot(d, t2); }
+  // insertion sort by angle around the centroid: lower half-plane after the upper one, inside a half-plane by the sign of the cross product
+  for (int i = 1; i < n; i++) {
+    float xi = P.x[i], yi = P.y[i];
+    int hi_ = (yi < 0.f || (yi == 0.f && xi < 0.f)) ? 1 : 0;
+    int j = i - 1;
+    while (j >= 0) {
+      int hj = (P.y[j] < 0.f || (P.y[j] == 0.f && P.x[j] < 0.f)) ? 1 : 0;
+      bool after = hj > hi_ || (hj == hi_ && P.x[j] * yi - P.y[j] * xi < 0.f);  // j comes after i
+      if (!after) break;
+      P.x[j + 1] = P.x[j]; P.y[j + 1] = P.y[j];
+      j--;
+    }
+    P.x[j + 1] = xi; P.y[j + 1] = yi;
+  }
+  return true;
+}
+B2S_HDN inline bool face_contains(const FacePoly& P, v3 q, float tol) {
+  v3 d = q - P.c;
+  float qx = dot(d, P.t1), qy = dot(d, P.t2);
+  for (int i = 0; i < P.n; i++) {
+    int k = i + 1 < P.n ? i + 1 : 0;
+    float ex = P.x[k] - P.x[i], ey = P.y[k] - P.y[i];
+    float len = sqrtf(ex * ex + ey * ey);
+    if (len < 1e-9f) continue;
+    if ((ex * (qy - P.y[i]) - ey * (qx - P.x[i])) < -tol * len) return false;
+  }
+  return true;
+}
+B2S_HDN inline int hull_hull_patch(const WShape& A, const WShape& B, v3 n_out, const CPoint& c0, float margin, CPoint* out) {
+  // n_out points from B towards A: A's support face is its extreme along -n_out, B's along +n_out
+  const float tol = 1e-3f;
+  v3 fa[B2S_FACE_MAX], fb[B2S_FACE_MAX];
+  int na = 0, nb = 0;
+  const float sa = support_face(A, -n_out, tol, fa, na);   // max of dot(v, -n) over A  -> A's lowest extent along n is -sa
+  const float sb = support_face(B, n_out, tol, fb, nb);    // B's highest extent along n
+  FacePoly PA, PB;
+  const bool okA = face_polygon(fa, na, n_out, PA), okB = face_polygon(fb, nb, n_out, PB);
+  if (!okA && !okB) return 1;
+  v3 cand[2 * B2S_FACE_MAX + 1];
+  float dist[2 * B2S_FACE_MAX + 1];
+  int m = 0;
+  cand[m] = c0.p; dist[m] = c0.sep; m++;
+  const float gap = -sa - sb;  // separation of the two supporting planes along n (negative when they overlap)
+  if (!(gap < margin)) return 1;
+  if (okB) {  // vertices of A's face over B's face polygon
+    for (int i = 0; i < na; i++) {
+      const float sp = dot(fa[i], n_out) - sb;
+      if (!(sp < margin)) continue;
+      const v3 q = fa[i] - n_out * sp;
+      if (!face_contains(PB, q, tol)) continue;
+      const v3 cp = fa[i] - n_out * (sp * 0.5f);
+      const v3 dc = cp - c0.p;
+      if (dot(dc, dc) < 1e-6f) { cand[0] = cp; dist[0] = sp; continue; }
+      cand[m] = cp; dist[m] = sp; m++;
+    }
+  }
+  if (okA) {  // vertices of B's face under A's face polygon
+    for (int i = 0; i < nb; i++) {
+      const float sp = -sa - dot(fb[i], n_out);
+      if (!(sp < margin)) continue;
+      const v3 q = fb[i] + n_out * sp;
+      if (!face_contains(PA, q, tol)) continue;
+      const v3 cp = fb[i] + n_out * (sp * 0.5f);
+      const v3 dc = cp - c0.p;
+      if (dot(dc, dc) < 1e-6f) { cand[0] = cp; dist[0] = sp; continue; }
+      cand[m] = cp; dist[m] = sp; m++;
+    }
+  }
+  if (m == 1) return 1;
+  int keep[4];
+  const int k = reduce4(m, cand, dist, keep);
+  for (int i = 0; i < k; i++) { out[i].p = cand[keep[i]]; out[i].n = n_out; out[i].sep = dist[keep[i]]; }
+  return k;
+}
+
 B2S_HDN inline int collide_pair(const WShape& a, const WShape& b, float margin, CPoint* out) {
   if (a.type == SH_PLANE && b.type == SH_PLANE) return 0;
   if (b.type == SH_PLANE) return collide_plane_any(a, b, margin, out);
@@ -625,6 +735,10 @@ B2S_HDN inline int collide_pair(const WShape& a, const WShape& b, float margin, 
   if (k == 1 && a.type == SH_BOX && b.type == SH_CONVEX) {
     CPoint c0 = out[0];
     return hull_box_patch(b, a, c0.n, false, c0, margin, out);
+  }
+  if (k == 1 && a.type == SH_CONVEX && b.type == SH_CONVEX) {
+    CPoint c0 = out[0];
+    return hull_hull_patch(a, b, c0.n, c0, margin, out);
   }
   return k;
 }

@@ -848,9 +848,12 @@ B2S_HDN void store_lane(const DevModel& M, const DevState& St, int env, const La
 }
 
 // exposed env-major AoS buffers <- lane (the fused gpu_fetch_*).  Needs a valid FK cache for BUF_LINK.
+// body_out: where the [n_rows][13] block of this sub-scene goes -- its place in St.body_data, or a shared-memory staging tile that the
+// kernel then moves to HBM with one bulk copy (fetch_kernel in b2s_api.cu)
 template <class C>
-B2S_HDN void fetch_lane(const DevModel& M, const DevState& St, int env, const Lane<C>& L, unsigned mask) {
+B2S_HDN void fetch_lane(const DevModel& M, const DevState& St, int env, const Lane<C>& L, unsigned mask, float* body_out = nullptr) {
   const int nr = M.n_rows;
+  if (!body_out) body_out = St.body_data + (size_t)env * nr * 13;
   if (mask & BUF_LINK) {
     for (int l = 0; l < M.n_link; l++) {
       int d = M.link_dof[l];
@@ -863,14 +866,14 @@ B2S_HDN void fetch_lane(const DevModel& M, const DevState& St, int env, const La
         av = L.V[d].a;
         lv = L.V[d].l + cross(av, P.p - L.root[a].p);
       }
-      float* o = St.body_data + ((size_t)env * nr + l) * 13;
+      float* o = body_out + (size_t)l * 13;
       o[0] = P.p.x; o[1] = P.p.y; o[2] = P.p.z; o[3] = P.q.w; o[4] = P.q.x; o[5] = P.q.y; o[6] = P.q.z;
       o[7] = lv.x; o[8] = lv.y; o[9] = lv.z; o[10] = av.x; o[11] = av.y; o[12] = av.z;
     }
   }
   if (mask & BUF_RIGID) {
     for (int b = 0; b < M.n_fb; b++) {
-      float* o = St.body_data + ((size_t)env * nr + M.n_link + b) * 13;
+      float* o = body_out + (size_t)(M.n_link + b) * 13;
       o[0] = L.fbX[b].p.x; o[1] = L.fbX[b].p.y; o[2] = L.fbX[b].p.z;
       o[3] = L.fbX[b].q.w; o[4] = L.fbX[b].q.x; o[5] = L.fbX[b].q.y; o[6] = L.fbX[b].q.z;
       o[7] = L.fbv[b].x; o[8] = L.fbv[b].y; o[9] = L.fbv[b].z; o[10] = L.fbw[b].x; o[11] = L.fbw[b].y; o[12] = L.fbw[b].z;
@@ -938,11 +941,11 @@ B2S_HDN void step_env(const DevModel& M, const DevState& St, int env, int subste
 }
 
 template <class C>
-B2S_HDN void fetch_env(const DevModel& M, const DevState& St, int env, unsigned mask) {
+B2S_HDN void fetch_env(const DevModel& M, const DevState& St, int env, unsigned mask, float* body_out = nullptr) {
   Lane<C> L;
   load_lane<C>(M, St, env, L);
   fk<C>(M, L);
-  fetch_lane<C>(M, St, env, L, mask);
+  fetch_lane<C>(M, St, env, L, mask, body_out);
 }
 
 }  // namespace b2s

@@ -7,6 +7,8 @@
 // Configuration follows the reference: contact generated when distance < contact_offset_A + contact_offset_B
 // (mani_skill/utils/structs/types.py:44-45), at most 4 points per pair.
 #pragma once
+#include <utility>
+#include <vector>
 #include "b2s_oracle_math.h"
 
 #define SHAPE_PLANE 0
@@ -647,6 +649,102 @@ static inline int hull_box_patch(const WShape& H, const WShape& Bx, V3 n_out, bo
   return k;
 }
 
+// ---- convex mesh against convex mesh: multi-point patch from the two support faces around the GJK / EPA normal (what PhysX's
+// persistent contact manifold accumulates over frames).  support face = the hull's vertices within tol of its supporting plane;
+// candidates = support-face vertices of one hull whose foot point lies inside the other hull's support-face polygon.
+struct FacePolygon {
+  std::vector<std::pair<R, R>> pts;  // counter-clockwise in the basis (t1, t2) around c
+  V3 c, t1, t2;
+};
+static inline R support_face_points(const WShape& H, V3 dir, R tol, std::vector<V3>& pts) {
+  R smax = R(-3.0e38);
+  std::vector<V3> world(H.nverts);
+  for (int i = 0; i < H.nverts; i++) {
+    world[i] = H.X.p + H.Rm * V3(H.verts[3 * i], H.verts[3 * i + 1], H.verts[3 * i + 2]);
+    smax = std::fmax(smax, dot(world[i], dir));
+  }
+  pts.clear();
+  for (int i = 0; i < H.nverts && (int)pts.size() < 24; i++)
+    if (smax - dot(world[i], dir) < tol) pts.push_back(world[i]);
+  return smax;
+}
+static inline bool build_face_polygon(const std::vector<V3>& pts, V3 dir, FacePolygon& P) {
+  P.pts.clear();
+  const int n = (int)pts.size();
+  if (n < 3) return false;
+  V3 c(0, 0, 0);
+  for (const V3& p : pts) c = c + p;
+  c = c * (R(1) / n);
+  V3 t1 = std::fabs(dir.x) < R(0.57735) ? normalized(cross(dir, V3(1, 0, 0))) : normalized(cross(dir, V3(0, 1, 0)));
+  V3 t2 = cross(dir, t1);
+  P.c = c; P.t1 = t1; P.t2 = t2;
+  for (const V3& p : pts) P.pts.push_back({dot(p - c, t1), dot(p - c, t2)});
+  auto half = [](const std::pair<R, R>& a) { return (a.second < 0 || (a.second == 0 && a.first < 0)) ? 1 : 0; };
+  // the same insertion order as the device code (ties resolve identically)
+  for (int i = 1; i < n; i++) {
+    std::pair<R, R> cur = P.pts[i];
+    int j = i - 1;
+    while (j >= 0) {
+      bool after = half(P.pts[j]) > half(cur) || (half(P.pts[j]) == half(cur) && P.pts[j].first * cur.second - P.pts[j].second * cur.first < 0);
+      if (!after) break;
+      P.pts[j + 1] = P.pts[j];
+      j--;
+    }
+    P.pts[j + 1] = cur;
+  }
+  return true;
+}
+static inline bool polygon_contains(const FacePolygon& P, V3 q, R tol) {
+  R qx = dot(q - P.c, P.t1), qy = dot(q - P.c, P.t2);
+  const int n = (int)P.pts.size();
+  for (int i = 0; i < n; i++) {
+    const auto& a = P.pts[i];
+    const auto& b = P.pts[(i + 1) % n];
+    R ex = b.first - a.first, ey = b.second - a.second;
+    R len = std::sqrt(ex * ex + ey * ey);
+    if (len < R(1e-9)) continue;
+    if (ex * (qy - a.second) - ey * (qx - a.first) < -tol * len) return false;
+  }
+  return true;
+}
+static inline int hull_hull_patch(const WShape& A, const WShape& B, V3 n_out, const Contact& c0, R margin, Contact* out) {
+  const R tol = R(1e-3);
+  std::vector<V3> fa, fb;
+  const R sa = support_face_points(A, -n_out, tol, fa);
+  const R sb = support_face_points(B, n_out, tol, fb);
+  FacePolygon PA, PB;
+  const bool okA = build_face_polygon(fa, n_out, PA), okB = build_face_polygon(fb, n_out, PB);
+  if (!okA && !okB) return 1;
+  if (!(-sa - sb < margin)) return 1;
+  V3 cand[49];
+  R dist[49];
+  int m = 0;
+  cand[m] = c0.p; dist[m] = c0.sep; m++;
+  if (okB)
+    for (const V3& v : fa) {
+      R sp = dot(v, n_out) - sb;
+      if (!(sp < margin)) continue;
+      if (!polygon_contains(PB, v - n_out * sp, tol)) continue;
+      V3 cp = v - n_out * (sp * R(0.5));
+      if (dot(cp - c0.p, cp - c0.p) < R(1e-6)) { cand[0] = cp; dist[0] = sp; continue; }
+      cand[m] = cp; dist[m] = sp; m++;
+    }
+  if (okA)
+    for (const V3& v : fb) {
+      R sp = -sa - dot(v, n_out);
+      if (!(sp < margin)) continue;
+      if (!polygon_contains(PA, v + n_out * sp, tol)) continue;
+      V3 cp = v + n_out * (sp * R(0.5));
+      if (dot(cp - c0.p, cp - c0.p) < R(1e-6)) { cand[0] = cp; dist[0] = sp; continue; }
+      cand[m] = cp; dist[m] = sp; m++;
+    }
+  if (m == 1) return 1;
+  int keep[4];
+  int k = reduce4(m, cand, dist, keep);
+  for (int i = 0; i < k; i++) { out[i].p = cand[keep[i]]; out[i].n = n_out; out[i].sep = dist[keep[i]]; }
+  return k;
+}
+
 // dispatch; out normals point from shape b towards shape a
 static inline int collide_pair(const WShape& a, const WShape& b, R margin, Contact* out) {
   if (a.type == SHAPE_PLANE && b.type == SHAPE_PLANE) return 0;
@@ -665,6 +763,10 @@ static inline int collide_pair(const WShape& a, const WShape& b, R margin, Conta
   if (k == 1 && a.type == SHAPE_BOX && b.type == SHAPE_CONVEX) {
     Contact c0 = out[0];
     return hull_box_patch(b, a, c0.n, false, c0, margin, out);
+  }
+  if (k == 1 && a.type == SHAPE_CONVEX && b.type == SHAPE_CONVEX) {
+    Contact c0 = out[0];
+    return hull_hull_patch(a, b, c0.n, c0, margin, out);
   }
   return k;
 }

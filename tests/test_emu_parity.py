@@ -57,10 +57,16 @@ def _edge_scenes():
     # differently, so 1e-7 differences between the two code paths flip rows -- and tells nothing about parity
     s4.add_actor(ActorRec("cyl", "dynamic", [cylinder_shape(0.03, 0.05)], pose7([0, 0, 0.0325], [0.9990482, 0, 0, 0.0436194])))
     s4.add_actor(ActorRec("hullbox", "dynamic", [ShapeRec(SHAPE_BOX, pose7(), np.array([0.03, 0.03, 0.03]))], pose7([0.3, 0.01, 0.05])))
-    return [("bodies-only", s1, 120), ("articulation-only", s2, 120), ("two-bodies-no-static", s3, 80), ("hull-on-box", s4, 150)]
+    # convex mesh resting on a convex mesh (support-face patch of both hulls): a small prism standing on a larger one
+    s5 = SceneDesc(n, SimParams())
+    ground(s5)
+    up = [0.7071068, 0, -0.7071068, 0]   # cylinder axis (local x) -> world z
+    s5.add_actor(ActorRec("base", "dynamic", [cylinder_shape(0.12, 0.05)], pose7([0, 0, 0.0501], up)))
+    s5.add_actor(ActorRec("top", "dynamic", [cylinder_shape(0.05, 0.04)], pose7([0.01, 0.005, 0.1405], up)))
+    return [("bodies-only", s1, 120), ("articulation-only", s2, 120), ("two-bodies-no-static", s3, 80), ("hull-on-box", s4, 150), ("hull-on-hull", s5, 150)]
 
 
-@pytest.mark.parametrize("idx", [0, 1, 2, 3], ids=["bodies-only", "articulation-only", "two-bodies-no-static", "hull-on-box"])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4], ids=["bodies-only", "articulation-only", "two-bodies-no-static", "hull-on-box", "hull-on-hull"])
 def test_emu_edge_models_match_oracle(idx):
     from emu import EmuWorld
     from oracle.oracle import OracleWorld

@@ -64,7 +64,7 @@ def test_contact_query_matches_oracle(cm):
     assert np.median(np.abs(ref_imp[:, 2, 2])) == pytest.approx(0.064 * 9.81 * 0.01, rel=0.05)
 
 
-@pytest.mark.parametrize("idx", [0, 1, 2, 3], ids=["bodies-only", "articulation-only", "two-bodies-no-static", "hull-on-box"])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4], ids=["bodies-only", "articulation-only", "two-bodies-no-static", "hull-on-box", "hull-on-hull"])
 def test_edge_models_vs_oracle(idx):
     """Degenerate model shapes through the C-ABI: 0 dofs, 0 candidate pairs / 0 bodies, bodies without static geometry
     (the scenes of tests/test_emu_parity.py::test_emu_edge_models_match_oracle)."""

@@ -286,3 +286,28 @@ def test_torsional_friction_of_a_spinning_box():
     w.step(10)
     b = w.get_bodies()[0, 0]
     assert abs(b[12]) < 1e-3 and np.abs(b[7:10]).max() < 1e-3   # stopped, and stays where it was
+
+
+def test_convex_mesh_rests_on_a_convex_mesh():
+    """Multi-point convex-vs-convex manifold (the support faces of both hulls): a 48-vertex prism standing on a larger one stays put for
+    600 substeps and the stack loads the ground with the weight of both (a single GJK/EPA point per pair let the upper prism spin up
+    and fall off within 300 substeps)."""
+    from maniskill_b200.model import ActorRec, SceneDesc, SimParams, cylinder_shape, pose7
+    s = SceneDesc(2, SimParams())
+    ground(s)
+    up = [0.7071068, 0, -0.7071068, 0]
+    s.add_actor(ActorRec("base", "dynamic", [cylinder_shape(0.12, 0.05)], pose7([0, 0, 0.0501], up)))
+    s.add_actor(ActorRec("top", "dynamic", [cylinder_shape(0.05, 0.04)], pose7([0.01, 0.005, 0.1405], up)))
+    cm = s.compile()
+    o = OracleWorld(cm, "f64")
+    o.step(600)
+    b = o.rigid_body_data()
+    top, base = cm.actor_rows["top"], cm.actor_rows["base"]
+    assert np.abs(b[:, top, 7:]).max() < 5e-3 and np.abs(b[:, base, 7:]).max() < 5e-3
+    assert abs(b[0, top, 2] - 0.14) < 2e-3 and abs(b[0, top, 0] - 0.01) < 1e-3 and abs(b[0, top, 1] - 0.005) < 1e-3
+    m_top = cm.arrays["fb_mass"][cm.actor_fb["top"]]
+    m_base = cm.arrays["fb_mass"][cm.actor_fb["base"]]
+    imp_top = o.pair_impulse(top, base)[0]
+    assert imp_top[2] == pytest.approx(m_top * 9.81 * 0.01, rel=0.03)
+    imp_ground = o.pair_impulse(base, -2)[0]     # net impulse on the base: ground pushes up with both weights, the top pushes down with its own
+    assert imp_ground[2] == pytest.approx(m_base * 9.81 * 0.01, rel=0.05)
