@@ -94,7 +94,10 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
 const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st) {
   int grid = M.n_envs * g->R.n_cam;
   // 512 threads = 16 warps per image: two images per SM (shared-memory bound) keep 32 warps in flight
-  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask);
+  // bounding boxes above this many pixels leave the one-thread path for the warp path; neighbouring triangles of the list belong to the
+  // same hull and have similar sizes, so the lanes of a warp stay balanced well beyond one warp's worth of pixels (measured)
+  static int big = getenv("B2S_RASTER_BIG") ? atoi(getenv("B2S_RASTER_BIG")) : B2S_BIG_TRI_PIXELS;
+  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -271,7 +271,7 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
 // env_mask (nullable): only sub-scenes with env_mask[env] != 0 are rendered (re-render after a partial reset); the others keep
 // their previous picture.
 __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
-                                                                    const uint8_t* __restrict__ env_mask) {
+                                                                    const uint8_t* __restrict__ env_mask, int big_tri_pixels) {
   extern __shared__ unsigned zkey[];
   __shared__ RasterShared sh;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     TriSetup T;
     if (!setup_triangle(R, sh, t, W, H, fx, fy, cx, cy, nearp, T)) continue;
     const int cnt = (T.x1 - T.x0 + 1) * (T.y1 - T.y0 + 1);
-    if (cnt > B2S_BIG_TRI_PIXELS && t < 65536) {
+    if (cnt > big_tri_pixels && t < 65536) {
       // larger on-screen triangle: queued and rasterised by a whole warp (by the whole CTA when huge) so that the one-thread path
       // stays short and balanced
       if (cnt > B2S_HUGE_TRI_PIXELS) {

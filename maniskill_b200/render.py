@@ -24,7 +24,8 @@ _UNIT_CUBE_TRIS = np.array([[0, 1, 3], [0, 3, 2], [4, 5, 7], [4, 7, 6], [0, 1, 5
 def build_visual_table(cm: CompiledModel, n_envs: int, include_hidden: bool = False) -> Dict[str, np.ndarray]:
     vis = [v for v in cm.visuals if include_hidden or not v["hidden"]]
     hull_off = cm.arrays["hull_offset"]
-    hull_verts = cm.arrays["hull_verts"].reshape(-1, 3)
+    hv = cm.arrays["hull_verts"]
+    hull_verts = hv.reshape(-1, 3) if hv.size % 3 == 0 and cm.scalars["n_hull"] > 0 else np.zeros((0, 3), dtype=np.float32)  # (a model without hulls keeps a 1-element placeholder)
     types, rows, poses, sizes, colors, segs, ov_slot = [], [], [], [], [], [], []
     ov_size, ov_pose = [], []
     vert_local, vert_vis, tri_idx, tri_vis = [], [], [], []

@@ -20,7 +20,11 @@ for r in rows[hdr_i + 1:]:
     if len(r) <= iv:
         continue
     key = r[iid]
-    d = launch.setdefault(key, dict(name=r[ik].split("(")[0].split("<")[0].split("::")[-1], full=r[ik]))
+    full = r[ik]
+    short = full[5:] if full.startswith("void ") else full
+    short = short.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    short = short.split("<")[0].split("(")[0].split("::")[-1].strip()
+    d = launch.setdefault(key, dict(name=short, full=full))
     try:
         d[r[im]] = float(r[iv].replace(",", "")) * scale.get(r[iu], 1)
     except ValueError:
