@@ -48,7 +48,25 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   R.vert_local = dev_copy(g, vis->vert_local, (size_t)vis->n_vert * 3);
   R.vert_vis = dev_copy(g, vis->vert_vis, vis->n_vert);
   R.tri_idx = dev_copy(g, vis->tri_idx, (size_t)vis->n_tri * 3);
-  R.tri_vis = dev_copy(g, vis->tri_vis, vis->n_tri);
+  {
+    // owning visual | face << 8: a triangle of a box lies in the face whose coordinate its three unit-cube corners share
+    // (face = 2 * axis + (that coordinate > 0)); hull triangles carry face 0
+    std::vector<int> packed(vis->n_tri + 1);
+    for (int t = 0; t < vis->n_tri; t++) {
+      const int v = vis->tri_vis[t];
+      if (v < 0 || v >= vis->n_visual) { raster_destroy(g); return "triangle visual index out of range"; }
+      int face = 0;
+      if (vis->type[v] == SH_BOX) {
+        const float* a = vis->vert_local + 3 * (size_t)vis->tri_idx[3 * t];
+        const float* b = vis->vert_local + 3 * (size_t)vis->tri_idx[3 * t + 1];
+        const float* c = vis->vert_local + 3 * (size_t)vis->tri_idx[3 * t + 2];
+        for (int k = 0; k < 3; k++)
+          if (a[k] == b[k] && b[k] == c[k]) face = 2 * k + (a[k] > 0.0f ? 1 : 0);
+      }
+      packed[t] = v | (face << 8);
+    }
+    R.tri_vis = dev_copy(g, packed.data(), vis->n_tri);
+  }
   std::vector<int> w(n_cam), h(n_cam), mount(n_cam);
   std::vector<float> intr(n_cam * 6), cp(n_cam * 7);
   std::vector<size_t> off(n_cam);
@@ -77,7 +95,8 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   if (outputs & B2S_OUT_SEG) g->T.seg = dev_copy<int16_t>(g, nullptr, N * pix + 2);
   for (void* p : g->allocs)
     if (!p) { raster_destroy(g); return "rasteriser allocation failed"; }
-  if (cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess) {
+  if (cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess ||
+      cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess) {
     raster_destroy(g);
     return "cannot reserve shared memory for the depth buffer";
   }
@@ -97,7 +116,8 @@ const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, con
   // bounding boxes above this many pixels leave the one-thread path for the warp path; neighbouring triangles of the list belong to the
   // same hull and have similar sizes, so the lanes of a warp stay balanced well beyond one warp's worth of pixels (measured)
   static int big = getenv("B2S_RASTER_BIG") ? atoi(getenv("B2S_RASTER_BIG")) : B2S_BIG_TRI_PIXELS;
-  raster_kernel<<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
+  if (g->T.mask & (B2S_OUT_COLOR | B2S_OUT_POSSEG)) raster_kernel<true><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
+  else raster_kernel<false><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

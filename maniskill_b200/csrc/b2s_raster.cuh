@@ -79,9 +79,14 @@ struct RasterGroup {
   int max_pixels;  // largest camera image (pixels) -> shared memory size
 };
 
-#define B2S_DEPTH_BITS 24
-#define B2S_DEPTH_MAX 16777215.0f
+// depth-buffer key: 23-bit reversed-z depth | 3-bit face of a box (2 * axis + (outward normal positive)) | 6-bit visual index
+#define B2S_DEPTH_BITS 23
+#define B2S_DEPTH_MAX 8388607.0f
+#define B2S_KEY_SHIFT 9
 #define B2S_NO_HIT 0xFFFFFFFFu
+B2S_HD unsigned raster_key(unsigned depth_key, int face, int v) { return (depth_key << B2S_KEY_SHIFT) | ((unsigned)face << 6) | (unsigned)v; }
+B2S_HD int key_visual(unsigned key) { return (int)(key & 63u); }
+B2S_HD int key_face(unsigned key) { return (int)((key >> 6) & 7u); }
 
 // Reversed-z quantisation on 1/depth.  The constants of a camera are computed once (DepthMap).
 struct DepthMap {
@@ -110,8 +115,9 @@ B2S_HD float key_depth(unsigned k, const DepthMap& m) {
 }
 
 // ray (origin o, direction dvec, both in the box frame) against an axis-aligned box of half extents h: entry distance
-B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit) {
+B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit, int& face) {
   float tmin = -1e30f, tmax = 1e30f;
+  face = 0;
   float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
   for (int k = 0; k < 3; k++) {
     if (fabsf(dd[k]) < 1e-12f) {
@@ -120,7 +126,7 @@ B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit) {
       float inv = 1.0f / dd[k];
       float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
       if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
-      if (t0 > tmin) tmin = t0;
+      if (t0 > tmin) { tmin = t0; face = 2 * k + (inv < 0.0f ? 1 : 0); }  // entered through the -h face when the ray runs towards +k
       if (t1 < tmax) tmax = t1;
     }
   }
@@ -137,18 +143,6 @@ B2S_HD bool ray_sphere(v3 o, v3 dv, float r, float& t_hit) {
   t_hit = t;
   return true;
 }
-// outward face normal of a box (half extents h) at a surface point pl of its frame: the face whose plane is nearest
-B2S_HD v3 box_face_normal(v3 pl, v3 h) {
-  float d0 = fabsf(pl.x) - h.x, d1 = fabsf(pl.y) - h.y, d2 = fabsf(pl.z) - h.z;
-  int axis = 0;
-  float best = d0;
-  if (d1 > best) { best = d1; axis = 1; }
-  if (d2 > best) { best = d2; axis = 2; }
-  float c = axis == 0 ? pl.x : (axis == 1 ? pl.y : pl.z);
-  float s = c >= 0.0f ? 1.0f : -1.0f;
-  return mk3(axis == 0 ? s : 0.0f, axis == 1 ? s : 0.0f, axis == 2 ? s : 0.0f);
-}
-
 B2S_HD uint8_t to_u8(float x) {
   float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
   return (uint8_t)c;
@@ -158,6 +152,11 @@ B2S_HD float shade_weight(v3 n_world) {
   const float k = 0.57735026f;
   v3 l1 = mk3(-k, -k, k), l2 = mk3(0.0f, 0.0f, 1.0f);
   return 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
+}
+// flat colour of a surface with world normal n: rgb bytes packed r | g << 8 | b << 16
+B2S_HD unsigned shade_rgb(v3 n_world, const float* col) {
+  const float w = shade_weight(n_world);
+  return (unsigned)to_u8(col[0] * w) | ((unsigned)to_u8(col[1] * w) << 8) | ((unsigned)to_u8(col[2] * w) << 16);
 }
 B2S_HD int16_t to_mm(float x) {
   float v = x * 1000.0f;
@@ -181,15 +180,25 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
 #define B2S_VERT_CACHE 1536       // projected vertices kept in shared memory (18 KB); vertices beyond are projected on use
 #define B2S_MAX_BIG_TRIS 1024
 #define B2S_MAX_HUGE_TRIS 128
+#define B2S_BIG_CACHE 160         // screen-space setups of the first queued warp-sized triangles are kept (60 B each) ...
+#define B2S_HUGE_CACHE 32         // ... and of the first CTA-sized ones; triangles queued beyond are set up again from the vertex cache
 #define B2S_BIG_TRI_PIXELS 24     // bounding boxes above this many pixels leave the one-thread path
 #define B2S_HUGE_TRI_PIXELS 2048  // ... and above this many are shared by the whole CTA instead of one warp
 
 enum { VM_RASTER = 0, VM_ANALYTIC = 1 };
 
+// screen-space setup of a triangle
+struct TriSetup {
+  float px[3], py[3], pd[3], inv_area;
+  int x0, y0, x1, y1, vf;  // vf = the low 9 key bits: face << 6 | visual
+};
+
 struct RasterShared {
   float vis_R[B2S_MAX_VIS][9];   // camera-from-visual rotation (row major)
   float vis_t[B2S_MAX_VIS][3];   // camera-from-visual translation
-  float vis_Rw[B2S_MAX_VIS][9];  // world-from-visual rotation (lighting)
+  float vis_col[B2S_MAX_VIS][3]; // base colour (per-pixel shading of spheres and hulls)
+  unsigned face_rgb[B2S_MAX_VIS][6];  // shaded colour of the six faces of a box / of a half-space (face 1 = +x), packed r | g << 8 | b << 16
+  short vis_seg[B2S_MAX_VIS];
   float vis_sz[B2S_MAX_VIS][3];
   float vis_o[B2S_MAX_VIS][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
   float vis_c[B2S_MAX_VIS];      // half-spaces: -1 / o.x, so that 1/depth of the ray hit = c * (ray direction).x
@@ -199,6 +208,8 @@ struct RasterShared {
   float vert[B2S_VERT_CACHE][3];  // screen x, screen y, 1/depth (0 = at or behind the near plane)
   unsigned short big[B2S_MAX_BIG_TRIS];    // triangles rasterised by one warp each
   unsigned short huge[B2S_MAX_HUGE_TRIS];  // triangles rasterised by the whole CTA
+  TriSetup big_setup[B2S_BIG_CACHE];
+  TriSetup huge_setup[B2S_HUGE_CACHE];
   unsigned rgb_stage[B2S_RASTER_THREADS / 32][24];  // 32 pixels x 3 bytes of a warp, regrouped into 24 words
   int n_big, n_huge;
 };
@@ -220,15 +231,12 @@ __device__ __forceinline__ void project_vertex(const RasterModel& R, const Raste
 }
 
 // screen-space setup of triangle t: false when it is culled (behind the near plane, back facing, off screen)
-struct TriSetup {
-  float px[3], py[3], pd[3], inv_area;
-  int x0, y0, x1, y1, v;
-};
 __device__ __forceinline__ bool setup_triangle(const RasterModel& R, const RasterShared& sh, int t, int W, int H, float fx, float fy, float cx, float cy,
                                                float nearp, TriSetup& T) {
-  const int v = R.tri_vis[t];
+  const int vf = R.tri_vis[t];  // visual | box face << 8 (packed by raster_create)
+  const int v = vf & 255;
   if (v >= B2S_MAX_VIS || sh.vis_mode[v] != VM_RASTER) return false;
-  T.v = v;
+  T.vf = ((vf >> 8) << 6) | v;
   for (int k = 0; k < 3; k++) {
     const int i = R.tri_idx[3 * t + k];
     float p[3];
@@ -264,12 +272,14 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
   if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) return;
   const float inv = (w0 * T.pd[0] + w1 * T.pd[1] + w2 * T.pd[2]) * T.inv_area;
   if (!inv_depth_in_range(inv, dm)) return;
-  const unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)T.v;
+  const unsigned key = (depth_key_inv(inv, dm) << B2S_KEY_SHIFT) | (unsigned)T.vf;
   atomicMin(&zkey[y * W + x], key);
 }
 
 // env_mask (nullable): only sub-scenes with env_mask[env] != 0 are rendered (re-render after a partial reset); the others keep
 // their previous picture.
+// RAW: the shader pack's Color / PositionSegmentation targets are written (the hit position is needed); otherwise only the compact textures
+template <bool RAW>
 __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
                                                                     const uint8_t* __restrict__ env_mask, int big_tri_pixels) {
   extern __shared__ unsigned zkey[];
@@ -304,7 +314,18 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     const m3 Rv = qmat(Xv.q);
     const m3 Rcv = mul(transpose(Rc), Rv);
     const v3 tcv = tmul(Rc, Xv.p - Xc.p);
-    for (int k = 0; k < 9; k++) { sh.vis_R[v][k] = Rcv.m[k]; sh.vis_Rw[v][k] = Rv.m[k]; }
+    for (int k = 0; k < 9; k++) sh.vis_R[v][k] = Rcv.m[k];
+    {
+      // Lambert shading is constant on a flat face: the six face colours of a box (a half-space: face 1, its +x) are computed once
+      const float* col = R.vis_color + 4 * v;
+      for (int k = 0; k < 3; k++) sh.vis_col[v][k] = col[k];
+      sh.vis_seg[v] = (short)R.vis_seg[v];
+      for (int f = 0; f < 6; f++) {
+        const int a = f >> 1;
+        const float sgn = (f & 1) ? 1.0f : -1.0f;
+        sh.face_rgb[v][f] = shade_rgb(mk3(Rv.m[a] * sgn, Rv.m[3 + a] * sgn, Rv.m[6 + a] * sgn), col);
+      }
+    }
     sh.vis_t[v][0] = tcv.x; sh.vis_t[v][1] = tcv.y; sh.vis_t[v][2] = tcv.z;
     const float ox = -(Rcv.m[0] * tcv.x + Rcv.m[3] * tcv.y + Rcv.m[6] * tcv.z);
     sh.vis_o[v][0] = ox;
@@ -353,10 +374,18 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
       // stays short and balanced
       if (cnt > B2S_HUGE_TRI_PIXELS) {
         const int slot = atomicAdd(&sh.n_huge, 1);
-        if (slot < B2S_MAX_HUGE_TRIS) { sh.huge[slot] = (unsigned short)t; continue; }
+        if (slot < B2S_MAX_HUGE_TRIS) {
+          sh.huge[slot] = (unsigned short)t;
+          if (slot < B2S_HUGE_CACHE) sh.huge_setup[slot] = T;
+          continue;
+        }
       }
       const int slot = atomicAdd(&sh.n_big, 1);
-      if (slot < B2S_MAX_BIG_TRIS) { sh.big[slot] = (unsigned short)t; continue; }
+      if (slot < B2S_MAX_BIG_TRIS) {
+        sh.big[slot] = (unsigned short)t;
+        if (slot < B2S_BIG_CACHE) sh.big_setup[slot] = T;
+        continue;
+      }
     }
     for (int y = T.y0; y <= T.y1; y++)
       for (int x = T.x0; x <= T.x1; x++) raster_sample(zkey, W, x, y, T, dm);
@@ -365,12 +394,12 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   {
     // pixel walk over a bounding box without a division per sample: a lane starts at pixel `first` and advances by `stride` pixels
     const int warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5, lane = threadIdx.x & 31;
-    // warp-sized triangles, one warp each (the 32 lanes repeat the cheap setup from the vertex cache; setting it up on one lane and
-    // broadcasting it with shuffles measured slower: 2.4 ms vs 1.8 ms per 4096 images)
+    // warp-sized triangles, one warp each; the setup of the first pass is read back from shared memory (broadcast loads)
     const int nb = sh.n_big < B2S_MAX_BIG_TRIS ? sh.n_big : B2S_MAX_BIG_TRIS;
     for (int b = warp; b < nb; b += n_warp) {
       TriSetup T;
-      if (!setup_triangle(R, sh, (int)sh.big[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+      if (b < B2S_BIG_CACHE) T = sh.big_setup[b];
+      else if (!setup_triangle(R, sh, (int)sh.big[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
       const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
       const int sy_ = 32 / bw, sx_ = 32 - sy_ * bw;
       int yy = lane / bw, xx = lane - yy * bw;
@@ -384,7 +413,8 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     const int nh = sh.n_huge < B2S_MAX_HUGE_TRIS ? sh.n_huge : B2S_MAX_HUGE_TRIS;
     for (int b = 0; b < nh; b++) {
       TriSetup T;
-      if (!setup_triangle(R, sh, (int)sh.huge[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
+      if (b < B2S_HUGE_CACHE) T = sh.huge_setup[b];
+      else if (!setup_triangle(R, sh, (int)sh.huge[b], W, H, fx, fy, cx, cy, nearp, T)) continue;
       const int bw = T.x1 - T.x0 + 1, cnt = bw * (T.y1 - T.y0 + 1);
       const int first = (int)threadIdx.x, stride = (int)blockDim.x;
       const int sy_ = stride / bw, sx_ = stride - sy_ * bw;
@@ -427,6 +457,7 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
       if (y < sh.vis_rect[v][2] || y > sh.vis_rect[v][3]) continue;
       const int ty = sh.vis_kind[v];
       float inv = 0.0f;
+      int face = 1;
       if (ty == SH_PLANE) {  // half-space, normal = +x of the visual frame: 1/depth is linear in the ray direction
         const float dlx = sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z;
         if (dlx < -1e-9f) inv = dlx * sh.vis_c[v];
@@ -438,61 +469,55 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
                           sh.vis_R[v][2] * rdir.x + sh.vis_R[v][5] * rdir.y + sh.vis_R[v][8] * rdir.z);
         float th = 0.0f;
         bool hit = false;
-        if (ty == SH_BOX) hit = ray_box(o, dl, mk3(sh.vis_sz[v][0], sh.vis_sz[v][1], sh.vis_sz[v][2]), th);
+        face = 0;
+        if (ty == SH_BOX) hit = ray_box(o, dl, mk3(sh.vis_sz[v][0], sh.vis_sz[v][1], sh.vis_sz[v][2]), th, face);
         else if (ty == SH_SPHERE) hit = ray_sphere(o, dl, sh.vis_sz[v][0], th);
         if (hit) inv = 1.0f / th;
       }
       if (inv_depth_in_range(inv, dm)) {
-        const unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+        const unsigned key = raster_key(depth_key_inv(inv, dm), face, v);
         best = key < best ? key : best;
       }
     }
     uchar4 c4 = make_uchar4(0, 0, 0, 255);
     short4 p4 = make_short4(0, 0, 0, 0);
     if (best != B2S_NO_HIT) {
-      const int bv = (int)(best & 255u);
-      const float depth = key_depth(best >> 8, dm);
-      const v3 pc = rdir * depth;  // camera-frame hit point
+      const int bv = key_visual(best);
+      const float depth = key_depth(best >> B2S_KEY_SHIFT, dm);
       const int ty = sh.vis_kind[bv];
-      v3 n_world;
-      if (ty == SH_CONVEX) {
-        // screen-space normal from neighbouring depths of the same visual (flat-ish shading of hull faces)
-        const int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
-        const unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
-        v3 n_cam = mk3(-1, 0, 0);
-        if (kx != B2S_NO_HIT && ky != B2S_NO_HIT && (int)(kx & 255u) == bv && (int)(ky & 255u) == bv) {
-          const float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
-          const v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
-          const v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
-          v3 e1 = pxn - pc, e2 = pyn - pc;
-          if (xn < x) e1 = -e1;
-          if (yn < y) e2 = -e2;
-          const v3 nn = cross(e2, e1);  // screen x runs to -y_cam, screen y to -z_cam: e2 x e1 faces the camera
-          const float l = norm(nn);
-          if (l > 1e-20f) n_cam = nn * (1.0f / l);
-          if (n_cam.x > 0.0f) n_cam = -n_cam;
-        }
-        n_world = mul(Rc, n_cam);
+      unsigned rgbw;
+      if (ty == SH_BOX || ty == SH_PLANE) {
+        rgbw = sh.face_rgb[bv][key_face(best)];  // flat face: shaded once per image in stage 0
       } else {
-        v3 nl = mk3(1, 0, 0);  // half-space
-        if (ty != SH_PLANE) {
-          // hit point in the visual's frame: Rcv^T (pc - tcv)
-          const v3 dpc = mk3(pc.x - sh.vis_t[bv][0], pc.y - sh.vis_t[bv][1], pc.z - sh.vis_t[bv][2]);
-          const v3 pl = mk3(sh.vis_R[bv][0] * dpc.x + sh.vis_R[bv][3] * dpc.y + sh.vis_R[bv][6] * dpc.z,
-                            sh.vis_R[bv][1] * dpc.x + sh.vis_R[bv][4] * dpc.y + sh.vis_R[bv][7] * dpc.z,
-                            sh.vis_R[bv][2] * dpc.x + sh.vis_R[bv][5] * dpc.y + sh.vis_R[bv][8] * dpc.z);
-          if (ty == SH_BOX) nl = box_face_normal(pl, mk3(sh.vis_sz[bv][0], sh.vis_sz[bv][1], sh.vis_sz[bv][2]));
-          else nl = pl * (1.0f / sh.vis_sz[bv][0]);
+        const v3 pc = rdir * depth;  // camera-frame hit point
+        v3 n_cam = mk3(-1, 0, 0);
+        if (ty == SH_CONVEX) {
+          // screen-space normal from neighbouring depths of the same visual (flat-ish shading of hull faces)
+          const int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
+          const unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
+          if (kx != B2S_NO_HIT && ky != B2S_NO_HIT && key_visual(kx) == bv && key_visual(ky) == bv) {
+            const float dx_ = key_depth(kx >> B2S_KEY_SHIFT, dm), dy_ = key_depth(ky >> B2S_KEY_SHIFT, dm);
+            const v3 pxn = mk3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
+            const v3 pyn = mk3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
+            v3 e1 = pxn - pc, e2 = pyn - pc;
+            if (xn < x) e1 = -e1;
+            if (yn < y) e2 = -e2;
+            const v3 nn = cross(e2, e1);  // screen x runs to -y_cam, screen y to -z_cam: e2 x e1 faces the camera
+            const float l = norm(nn);
+            if (l > 1e-20f) n_cam = nn * (1.0f / l);
+            if (n_cam.x > 0.0f) n_cam = -n_cam;
+          }
+        } else {
+          // sphere: (hit point - centre) / radius, in the camera frame
+          n_cam = mk3(pc.x - sh.vis_t[bv][0], pc.y - sh.vis_t[bv][1], pc.z - sh.vis_t[bv][2]) * (1.0f / sh.vis_sz[bv][0]);
         }
-        n_world = mk3(sh.vis_Rw[bv][0] * nl.x + sh.vis_Rw[bv][1] * nl.y + sh.vis_Rw[bv][2] * nl.z,
-                      sh.vis_Rw[bv][3] * nl.x + sh.vis_Rw[bv][4] * nl.y + sh.vis_Rw[bv][5] * nl.z,
-                      sh.vis_Rw[bv][6] * nl.x + sh.vis_Rw[bv][7] * nl.y + sh.vis_Rw[bv][8] * nl.z);
+        rgbw = shade_rgb(mul(Rc, n_cam), sh.vis_col[bv]);
       }
-      const float* col = R.vis_color + 4 * bv;
-      const float w = shade_weight(n_world);
-      c4 = make_uchar4(to_u8(col[0] * w), to_u8(col[1] * w), to_u8(col[2] * w), 255);
-      // OpenGL camera frame: x right = -y_cam, y up = z_cam, z backward = -x_cam
-      p4 = make_short4(to_mm(-pc.y), to_mm(pc.z), to_mm(-pc.x), (short)R.vis_seg[bv]);
+      c4 = make_uchar4((uint8_t)(rgbw & 255u), (uint8_t)((rgbw >> 8) & 255u), (uint8_t)((rgbw >> 16) & 255u), 255);
+      // OpenGL camera frame: x right = -y_cam, y up = z_cam, z backward = -x_cam (the hit point is ray * depth, the ray's x is 1)
+      p4.z = to_mm(-depth);
+      p4.w = sh.vis_seg[bv];
+      if (RAW) { p4.x = to_mm(-(ry * depth)); p4.y = to_mm(rz * depth); }
     }
     if (O.mask & B2S_OUT_COLOR) *reinterpret_cast<uchar4*>(cbase + (size_t)i * 4) = c4;
     if (O.mask & B2S_OUT_POSSEG) *reinterpret_cast<short4*>(pbase + (size_t)i * 4) = p4;

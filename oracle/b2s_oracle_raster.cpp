@@ -8,11 +8,12 @@
 //   * pinhole camera, sapien camera frame (x forward, y left, z up), pixel centres at (u + 0.5, v + 0.5), v = 0 at the top
 //   * convex hulls, and boxes whose eight corners are in front of the near plane, are triangle meshes: vertices projected to the
 //     screen, sample inside iff the three edge functions are >= 0 after orienting the triangle counter-clockwise, 1/depth
-//     interpolated linearly in screen space, quantised to a 24-bit reversed-z key; back faces culled
+//     interpolated linearly in screen space, quantised to a 23-bit reversed-z key; back faces culled
 //   * half-spaces, spheres and the remaining boxes are analytic: per pixel they produce a key of the same form (half-space: 1/depth
 //     linear in the ray direction, no division; sphere / box: 1 / ray parameter)
-//   * the smallest (key << 8 | visual index) wins, depth = 1 / dequantised(1/depth); normals: box face nearest to the hit point,
-//     half-space normal, sphere radius, hulls from the depth neighbourhood
+//   * the smallest (key << 9 | box face << 6 | visual index) wins, depth = 1 / dequantised(1/depth); flat faces (boxes: the face of the
+//     winning triangle / the face the ray enters through; half-spaces) have one shaded colour per image; spheres: normal = (hit - centre) / r;
+//     hulls: normal from the depth neighbourhood
 //   * segmentation = per_scene_id of the winning visual, 0 = background; position = hit point in mm (round to nearest even)
 // Plain loops, float32, compiled with -ffp-contract=off; the CUDA translation unit is compiled with -fmad=false, so the
 // integer outputs (segmentation, position) are expected to agree bit for bit.
@@ -84,7 +85,9 @@ inline P7 ident() {
   return p;
 }
 
-const float DEPTH_MAX = 16777215.0f;
+const float DEPTH_MAX = 8388607.0f;
+const int KEY_SHIFT = 9;
+inline unsigned make_key(unsigned dk, int face, int v) { return (dk << KEY_SHIFT) | ((unsigned)face << 6) | (unsigned)v; }
 // reversed-z quantisation on 1/depth; per-camera constants computed once (maniskill_b200/csrc/b2s_raster.cuh DepthMap)
 struct DepthMap {
   float invn, invf, range, scale, inv_max;
@@ -110,8 +113,9 @@ inline float key_depth(unsigned k, const DepthMap& m) {
   float inv = m.invf + t * m.range;
   return 1.0f / inv;
 }
-inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit) {
+inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, int& face) {
   float tmin = -1e30f, tmax = 1e30f;
+  face = 0;
   float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
   for (int k = 0; k < 3; k++) {
     if (fabsf(dd[k]) < 1e-12f) {
@@ -120,7 +124,7 @@ inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit) {
       float inv = 1.0f / dd[k];
       float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
       if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
-      if (t0 > tmin) tmin = t0;
+      if (t0 > tmin) { tmin = t0; face = 2 * k + (inv < 0.0f ? 1 : 0); }
       if (t1 < tmax) tmax = t1;
     }
   }
@@ -137,16 +141,6 @@ inline bool ray_sphere(F3 o, F3 dv, float r, float& t_hit) {
   t_hit = t;
   return true;
 }
-inline F3 box_face_normal(F3 pl, F3 h) {
-  float d0 = fabsf(pl.x) - h.x, d1 = fabsf(pl.y) - h.y, d2 = fabsf(pl.z) - h.z;
-  int axis = 0;
-  float best = d0;
-  if (d1 > best) { best = d1; axis = 1; }
-  if (d2 > best) { best = d2; axis = 2; }
-  float c = axis == 0 ? pl.x : (axis == 1 ? pl.y : pl.z);
-  float s = c >= 0.0f ? 1.0f : -1.0f;
-  return f3(axis == 0 ? s : 0.0f, axis == 1 ? s : 0.0f, axis == 2 ? s : 0.0f);
-}
 inline uint8_t to_u8(float x) {
   float c = fminf(fmaxf(x, 0.0f), 1.0f) * 255.0f + 0.5f;
   return (uint8_t)c;
@@ -155,6 +149,12 @@ inline int16_t to_mm(float x) {
   float v = x * 1000.0f;
   v = fminf(fmaxf(v, -32768.0f), 32767.0f);
   return (int16_t)rintf(v);
+}
+inline unsigned shade_rgb(F3 n_world, const float* col) {
+  const float kk = 0.57735026f;
+  F3 l1 = f3(-kk, -kk, kk), l2 = f3(0.0f, 0.0f, 1.0f);
+  float w = 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
+  return (unsigned)to_u8(col[0] * w) | ((unsigned)to_u8(col[1] * w) << 8) | ((unsigned)to_u8(col[2] * w) << 16);
 }
 inline F3 mulm(const float* m, F3 v) { return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
 inline F3 tmulm(const float* m, F3 v) { return f3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z); }
@@ -186,7 +186,8 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
   Xc.q = qnorm(Xc.q);
   float Rc[9];
   qmat(Xc.q, Rc);
-  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vRw(n_vis * 9), vo(n_vis * 3), vc(n_vis, 0.0f);
+  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vo(n_vis * 3), vc(n_vis, 0.0f);
+  std::vector<unsigned> face_rgb(n_vis * 6);
   std::vector<int> vmode(n_vis, 1);  // 0 rasterised, 1 analytic
   for (int v = 0; v < n_vis; v++) {
     P7 Xv = pmul(body_pose(vis_row[v]), p7(vis_pose + 7 * v));
@@ -199,7 +200,11 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
       for (int j = 0; j < 3; j++) Rm[3 * i + j] = Rc[i] * Rv[j] + Rc[3 + i] * Rv[3 + j] + Rc[6 + i] * Rv[6 + j];
     F3 t = tmulm(Rc, Xv.p - Xc.p);
     vt[v * 3] = t.x; vt[v * 3 + 1] = t.y; vt[v * 3 + 2] = t.z;
-    for (int k = 0; k < 9; k++) vRw[v * 9 + k] = Rv[k];
+    for (int f = 0; f < 6; f++) {
+      const int a = f >> 1;
+      const float sgn = (f & 1) ? 1.0f : -1.0f;
+      face_rgb[v * 6 + f] = shade_rgb(f3(Rv[a] * sgn, Rv[3 + a] * sgn, Rv[6 + a] * sgn), vis_color + 4 * v);
+    }
     vo[v * 3] = -(Rm[0] * t.x + Rm[3] * t.y + Rm[6] * t.z);
     vo[v * 3 + 1] = -(Rm[1] * t.x + Rm[4] * t.y + Rm[7] * t.z);
     vo[v * 3 + 2] = -(Rm[2] * t.x + Rm[5] * t.y + Rm[8] * t.z);
@@ -239,6 +244,14 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
   for (int t = 0; t < n_tri; t++) {
     int v = tri_vis[t];
     if (vmode[v] != 0) continue;
+    int face = 0;
+    if (vis_type[v] == 1) {  // the face of the unit cube this triangle lies in
+      const float* a = vert_local + 3 * (size_t)tri_idx[3 * t];
+      const float* b = vert_local + 3 * (size_t)tri_idx[3 * t + 1];
+      const float* c = vert_local + 3 * (size_t)tri_idx[3 * t + 2];
+      for (int k = 0; k < 3; k++)
+        if (a[k] == b[k] && b[k] == c[k]) face = 2 * k + (a[k] > 0.0f ? 1 : 0);
+    }
     float px[3], py[3], pd[3];
     bool ok = true;
     for (int k = 0; k < 3; k++) {
@@ -271,7 +284,7 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
         if (w0 < 0.0f || w1 < 0.0f || w2 < 0.0f) continue;
         float inv = (w0 * pd[0] + w1 * pd[1] + w2 * pd[2]) * inv_area;
         if (!inv_depth_in_range(inv, dm)) continue;
-        unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+        unsigned key = make_key(depth_key_inv(inv, dm), face, v);
         if (key < zkey[y * W + x]) zkey[y * W + x] = key;
       }
   }
@@ -285,6 +298,7 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
       int ty = vis_type[v];
       const float* Rm = &vR[v * 9];
       float inv = 0.0f;
+      int face = 1;
       if (ty == 0) {
         float dlx = Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z;
         if (dlx < -1e-9f) inv = dlx * vc[v];
@@ -294,12 +308,13 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
                    Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
         float th = 0.0f;
         bool hit = false;
-        if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th);
+        face = 0;
+        if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th, face);
         else if (ty == 2) hit = ray_sphere(o, dl, vis_size[3 * v], th);
         if (hit) inv = 1.0f / th;
       }
       if (inv_depth_in_range(inv, dm)) {
-        unsigned key = (depth_key_inv(inv, dm) << 8) | (unsigned)v;
+        unsigned key = make_key(depth_key_inv(inv, dm), face, v);
         if (key < best) best = key;
       }
     }
@@ -308,45 +323,36 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
     c4[0] = c4[1] = c4[2] = 0; c4[3] = 255;
     p4[0] = p4[1] = p4[2] = p4[3] = 0;
     if (best != NO_HIT) {
-      const int bv = (int)(best & 255u);
-      const float depth = key_depth(best >> 8, dm);
+      const int bv = (int)(best & 63u);
+      const float depth = key_depth(best >> KEY_SHIFT, dm);
       F3 pc = rdir * depth;
       const int ty = vis_type[bv];
-      F3 n_world;
-      if (ty == 4) {
-        int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
-        unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
-        F3 n_cam = f3(-1, 0, 0);
-        if (kx != NO_HIT && ky != NO_HIT && (int)(kx & 255u) == bv && (int)(ky & 255u) == bv) {
-          float dx_ = key_depth(kx >> 8, dm), dy_ = key_depth(ky >> 8, dm);
-          F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
-          F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
-          F3 e1 = pxn - pc, e2 = pyn - pc;
-          if (xn < x) e1 = -e1;
-          if (yn < y) e2 = -e2;
-          F3 nn = cross(e2, e1);
-          float l = norm(nn);
-          if (l > 1e-20f) n_cam = nn * (1.0f / l);
-          if (n_cam.x > 0.0f) n_cam = -n_cam;
-        }
-        n_world = mulm(Rc, n_cam);
+      unsigned rgbw;
+      if (ty == 1 || ty == 0) {
+        rgbw = face_rgb[bv * 6 + (int)((best >> 6) & 7u)];
       } else {
-        F3 nl = f3(1, 0, 0);
-        if (ty != 0) {
-          const float* Rm = &vR[bv * 9];
-          F3 dpc = f3(pc.x - vt[bv * 3], pc.y - vt[bv * 3 + 1], pc.z - vt[bv * 3 + 2]);
-          F3 pl = f3(Rm[0] * dpc.x + Rm[3] * dpc.y + Rm[6] * dpc.z, Rm[1] * dpc.x + Rm[4] * dpc.y + Rm[7] * dpc.z,
-                     Rm[2] * dpc.x + Rm[5] * dpc.y + Rm[8] * dpc.z);
-          if (ty == 1) nl = box_face_normal(pl, f3(vis_size[3 * bv], vis_size[3 * bv + 1], vis_size[3 * bv + 2]));
-          else nl = pl * (1.0f / vis_size[3 * bv]);
+        F3 n_cam = f3(-1, 0, 0);
+        if (ty == 4) {
+          int xn = x + 1 < W ? x + 1 : x - 1, yn = y + 1 < H ? y + 1 : y - 1;
+          unsigned kx = zkey[y * W + xn], ky = zkey[yn * W + x];
+          if (kx != NO_HIT && ky != NO_HIT && (int)(kx & 63u) == bv && (int)(ky & 63u) == bv) {
+            float dx_ = key_depth(kx >> KEY_SHIFT, dm), dy_ = key_depth(ky >> KEY_SHIFT, dm);
+            F3 pxn = f3(1.0f, -((float)xn + 0.5f - cx) * inv_fx, rz) * dx_;
+            F3 pyn = f3(1.0f, ry, -((float)yn + 0.5f - cy) * inv_fy) * dy_;
+            F3 e1 = pxn - pc, e2 = pyn - pc;
+            if (xn < x) e1 = -e1;
+            if (yn < y) e2 = -e2;
+            F3 nn = cross(e2, e1);
+            float l = norm(nn);
+            if (l > 1e-20f) n_cam = nn * (1.0f / l);
+            if (n_cam.x > 0.0f) n_cam = -n_cam;
+          }
+        } else {
+          n_cam = f3(pc.x - vt[bv * 3], pc.y - vt[bv * 3 + 1], pc.z - vt[bv * 3 + 2]) * (1.0f / vis_size[3 * bv]);
         }
-        n_world = mulm(&vRw[bv * 9], nl);
+        rgbw = shade_rgb(mulm(Rc, n_cam), vis_color + 4 * bv);
       }
-      const float* col = vis_color + 4 * bv;
-      const float kk = 0.57735026f;
-      F3 l1 = f3(-kk, -kk, kk), l2 = f3(0.0f, 0.0f, 1.0f);
-      float w = 0.3f + 0.5f * fmaxf(dot(n_world, l1), 0.0f) + 0.5f * fmaxf(dot(n_world, l2), 0.0f);
-      c4[0] = to_u8(col[0] * w); c4[1] = to_u8(col[1] * w); c4[2] = to_u8(col[2] * w);
+      c4[0] = (uint8_t)(rgbw & 255u); c4[1] = (uint8_t)((rgbw >> 8) & 255u); c4[2] = (uint8_t)((rgbw >> 16) & 255u);
       p4[0] = to_mm(-pc.y); p4[1] = to_mm(pc.z); p4[2] = to_mm(-pc.x); p4[3] = (int16_t)vis_seg[bv];
     }
   }
