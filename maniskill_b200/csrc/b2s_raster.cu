@@ -116,8 +116,11 @@ const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, con
   // bounding boxes above this many pixels leave the one-thread path for the warp path; neighbouring triangles of the list belong to the
   // same hull and have similar sizes, so the lanes of a warp stay balanced well beyond one warp's worth of pixels (measured)
   static int big = getenv("B2S_RASTER_BIG") ? atoi(getenv("B2S_RASTER_BIG")) : B2S_BIG_TRI_PIXELS;
-  if (g->T.mask & (B2S_OUT_COLOR | B2S_OUT_POSSEG)) raster_kernel<true><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
-  else raster_kernel<false><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big);
+  // faces of a box whose screen rectangle is larger than this are tested per pixel; part of the rasteriser's definition (the CPU
+  // restatement uses the same constant; the override exists for tuning runs only)
+  static int patch = getenv("B2S_RASTER_PATCH") ? atoi(getenv("B2S_RASTER_PATCH")) : B2S_PATCH_PIXELS;
+  if (g->T.mask & (B2S_OUT_COLOR | B2S_OUT_POSSEG)) raster_kernel<true><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch);
+  else raster_kernel<false><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -114,26 +114,6 @@ B2S_HD float key_depth(unsigned k, const DepthMap& m) {
   return 1.0f / inv;
 }
 
-// ray (origin o, direction dvec, both in the box frame) against an axis-aligned box of half extents h: entry distance
-B2S_HD bool ray_box(v3 o, v3 dv, v3 h, float& t_hit, int& face) {
-  float tmin = -1e30f, tmax = 1e30f;
-  face = 0;
-  float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
-  for (int k = 0; k < 3; k++) {
-    if (fabsf(dd[k]) < 1e-12f) {
-      if (fabsf(oo[k]) > hh[k]) return false;
-    } else {
-      float inv = 1.0f / dd[k];
-      float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
-      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
-      if (t0 > tmin) { tmin = t0; face = 2 * k + (inv < 0.0f ? 1 : 0); }  // entered through the -h face when the ray runs towards +k
-      if (t1 < tmax) tmax = t1;
-    }
-  }
-  if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
-  t_hit = tmin;
-  return true;
-}
 B2S_HD bool ray_sphere(v3 o, v3 dv, float r, float& t_hit) {
   float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
   float disc = b * b - a * c;
@@ -184,6 +164,9 @@ __device__ __forceinline__ pose raster_body_pose(const float* body_data, int n_r
 #define B2S_HUGE_CACHE 32         // ... and of the first CTA-sized ones; triangles queued beyond are set up again from the vertex cache
 #define B2S_BIG_TRI_PIXELS 24     // bounding boxes above this many pixels leave the one-thread path
 #define B2S_HUGE_TRI_PIXELS 2048  // ... and above this many are shared by the whole CTA instead of one warp
+#define B2S_PATCH_PIXELS 1024     // faces of a projected box with a larger screen rectangle are tested per pixel instead of rasterised
+#define B2S_MAX_PATCH 192         // flat faces tested per pixel (at most three faces of a box face the camera)
+#define B2S_MAX_SPHERES 16
 
 enum { VM_RASTER = 0, VM_ANALYTIC = 1 };
 
@@ -191,6 +174,15 @@ enum { VM_RASTER = 0, VM_ANALYTIC = 1 };
 struct TriSetup {
   float px[3], py[3], pd[3], inv_area;
   int x0, y0, x1, y1, vf;  // vf = the low 9 key bits: face << 6 | visual
+};
+
+// a flat face tested per pixel instead of being rasterised: the plane (local axis a = face >> 1) = s h_a of visual v, bounded by the
+// other two half extents (boxes) or unbounded (half-spaces); 1/depth of the ray hit = (ray direction)_a * cc
+struct FacePatch {
+  short x0, x1, y0, y1;  // screen rectangle that contains it
+  float cc;              // 1 / (s h_a - (camera origin)_a)
+  short v, face;
+  int bounded;
 };
 
 struct RasterShared {
@@ -201,7 +193,6 @@ struct RasterShared {
   short vis_seg[B2S_MAX_VIS];
   float vis_sz[B2S_MAX_VIS][3];
   float vis_o[B2S_MAX_VIS][3];   // camera origin in the visual's frame (ray origin of the analytic tests)
-  float vis_c[B2S_MAX_VIS];      // half-spaces: -1 / o.x, so that 1/depth of the ray hit = c * (ray direction).x
   int vis_rect[B2S_MAX_VIS][4];  // conservative screen rectangle (x0, x1, y0, y1) of the analytic primitives
   int vis_kind[B2S_MAX_VIS];
   int vis_mode[B2S_MAX_VIS];
@@ -210,6 +201,10 @@ struct RasterShared {
   unsigned short huge[B2S_MAX_HUGE_TRIS];  // triangles rasterised by the whole CTA
   TriSetup big_setup[B2S_BIG_CACHE];
   TriSetup huge_setup[B2S_HUGE_CACHE];
+  FacePatch patch[B2S_MAX_PATCH];
+  unsigned face_patch[B2S_MAX_VIS];  // bit f: face f of this box is a patch (its two triangles are skipped)
+  unsigned char sphere[B2S_MAX_SPHERES];
+  int n_patch, n_sphere;
   unsigned rgb_stage[B2S_RASTER_THREADS / 32][24];  // 32 pixels x 3 bytes of a warp, regrouped into 24 words
   int n_big, n_huge;
 };
@@ -236,6 +231,7 @@ __device__ __forceinline__ bool setup_triangle(const RasterModel& R, const Raste
   const int vf = R.tri_vis[t];  // visual | box face << 8 (packed by raster_create)
   const int v = vf & 255;
   if (v >= B2S_MAX_VIS || sh.vis_mode[v] != VM_RASTER) return false;
+  if ((sh.face_patch[v] >> (vf >> 8)) & 1u) return false;  // this face is tested per pixel (stage 3)
   T.vf = ((vf >> 8) << 6) | v;
   for (int k = 0; k < 3; k++) {
     const int i = R.tri_idx[3 * t + k];
@@ -281,12 +277,12 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
 // RAW: the shader pack's Color / PositionSegmentation targets are written (the hit position is needed); otherwise only the compact textures
 template <bool RAW>
 __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
-                                                                    const uint8_t* __restrict__ env_mask, int big_tri_pixels) {
+                                                                    const uint8_t* __restrict__ env_mask, int big_tri_pixels, int patch_pixels) {
   extern __shared__ unsigned zkey[];
   __shared__ RasterShared sh;
   const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
   if (env_mask && !env_mask[env]) return;
-  if (threadIdx.x == 0) { sh.n_big = 0; sh.n_huge = 0; }
+  if (threadIdx.x == 0) { sh.n_big = 0; sh.n_huge = 0; sh.n_patch = 0; sh.n_sphere = 0; }
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
   const float nearp = R.cam_intr[6 * cam + 4], farp = R.cam_intr[6 * cam + 5];
@@ -333,7 +329,7 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     sh.vis_o[v][2] = -(Rcv.m[2] * tcv.x + Rcv.m[5] * tcv.y + Rcv.m[8] * tcv.z);
     const int ty = R.vis_type[v];
     sh.vis_kind[v] = ty;
-    sh.vis_c[v] = (ty == SH_PLANE && ox > 0.0f) ? -1.0f / ox : 0.0f;
+    sh.face_patch[v] = 0u;
     // screen rectangle that surely contains the primitive (whole image when it reaches behind the near plane)
     int rx0 = 0, rx1 = W - 1, ry0 = 0, ry1 = H - 1;
     int mode = ty == SH_CONVEX ? VM_RASTER : VM_ANALYTIC;
@@ -356,12 +352,55 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
     }
     sh.vis_mode[v] = mode;
     sh.vis_rect[v][0] = rx0; sh.vis_rect[v][1] = rx1; sh.vis_rect[v][2] = ry0; sh.vis_rect[v][3] = ry1;
+    if (ty == SH_SPHERE) {
+      const int slot = atomicAdd(&sh.n_sphere, 1);
+      if (slot < B2S_MAX_SPHERES) sh.sphere[slot] = (unsigned char)v;
+    }
   }
   __syncthreads();
-  // ---------------- stage 1: project the vertices once
+  // ---------------- stage 1: project the vertices once; pick the flat faces that are tested per pixel
   {
     const int nc = R.n_vert < B2S_VERT_CACHE ? R.n_vert : B2S_VERT_CACHE;
     for (int i = threadIdx.x; i < nc; i += blockDim.x) project_vertex(R, sh, i, fx, fy, cx, cy, nearp, sh.vert[i]);
+    // flat faces: half-spaces; the camera-facing faces of a box that reaches behind the near plane (it cannot be projected); the
+    // camera-facing faces of the other boxes whose screen rectangle is large (two bounding-box walks of two huge triangles cost
+    // more than one plane test per pixel, and the per-pixel pass is perfectly balanced)
+    for (int vf = threadIdx.x; vf < nv * 6; vf += blockDim.x) {
+      const int v = vf / 6, f = vf - 6 * v, a = f >> 1, ty = sh.vis_kind[v];
+      const float sgn = (f & 1) ? 1.0f : -1.0f;
+      float ha;
+      if (ty == SH_PLANE) { if (f != 1) continue; ha = 0.0f; }
+      else if (ty == SH_BOX) ha = sh.vis_sz[v][a];
+      else continue;
+      const float oa = sh.vis_o[v][a];
+      if (!(oa * sgn > ha)) continue;  // the camera is behind this face
+      int rx0 = 0, rx1 = W - 1, ry0 = 0, ry1 = H - 1;
+      if (ty == SH_BOX && sh.vis_mode[v] == VM_RASTER) {
+        const int b = a == 2 ? 0 : a + 1, c = b == 2 ? 0 : b + 1;
+        float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+        for (int k = 0; k < 4; k++) {
+          float l[3];
+          l[a] = sgn * ha; l[b] = (k & 1) ? sh.vis_sz[v][b] : -sh.vis_sz[v][b]; l[c] = (k & 2) ? sh.vis_sz[v][c] : -sh.vis_sz[v][c];
+          const float* Rm = sh.vis_R[v];
+          const float px_ = Rm[0] * l[0] + Rm[1] * l[1] + Rm[2] * l[2] + sh.vis_t[v][0];
+          const float py_ = Rm[3] * l[0] + Rm[4] * l[1] + Rm[5] * l[2] + sh.vis_t[v][1];
+          const float pz_ = Rm[6] * l[0] + Rm[7] * l[1] + Rm[8] * l[2] + sh.vis_t[v][2];
+          const float u = cx - fx * py_ / px_, w = cy - fy * pz_ / px_;
+          mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w);
+        }
+        rx0 = max(0, (int)floorf(mnx) - 1); rx1 = min(W - 1, (int)ceilf(mxx) + 1);
+        ry0 = max(0, (int)floorf(mny) - 1); ry1 = min(H - 1, (int)ceilf(mxy) + 1);
+        if (rx0 > rx1 || ry0 > ry1 || (rx1 - rx0 + 1) * (ry1 - ry0 + 1) <= patch_pixels) continue;  // stays a pair of triangles
+      }
+      const int slot = atomicAdd(&sh.n_patch, 1);
+      if (slot >= B2S_MAX_PATCH) continue;
+      if (ty == SH_BOX) atomicOr(&sh.face_patch[v], 1u << f);
+      FacePatch P;
+      P.x0 = (short)rx0; P.x1 = (short)rx1; P.y0 = (short)ry0; P.y1 = (short)ry1;
+      P.cc = 1.0f / (sgn * ha - oa);
+      P.v = (short)v; P.face = (short)f; P.bounded = ty == SH_BOX;
+      sh.patch[slot] = P;
+    }
   }
   __syncthreads();
   // ---------------- stage 2: triangles (camera frame: x forward, y left, z up)
@@ -435,47 +474,52 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
   // whole warps on consecutive pixels, i.e. a pixel count that is a multiple of the CTA size; otherwise element-wise stores
   const bool packed = (npix % (int)blockDim.x) == 0 && (pix0 % 32) == 0;
   const int warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
-  // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel).  With W dividing blockDim the column of a
-  // thread is fixed, so the set of analytic primitives whose screen rectangle covers that column is one 64-bit mask per column.
+  // pixel walk: i = tid + k * blockDim; x, y advance incrementally (no division per pixel)
   int x = threadIdx.x % W, y = threadIdx.x / W;
   const int step_x = blockDim.x % W, step_y = blockDim.x / W;
-  int mask_x = -1;
-  unsigned long long xmask = 0ull;
-  for (int i = threadIdx.x; i < npix; i += blockDim.x, x += step_x, y += step_y) {
+  const int n_patch = sh.n_patch < B2S_MAX_PATCH ? sh.n_patch : B2S_MAX_PATCH, n_sphere = sh.n_sphere < B2S_MAX_SPHERES ? sh.n_sphere : B2S_MAX_SPHERES;
+  // running output pointers of the packed stores: per iteration a warp advances by blockDim pixels
+  unsigned* rgb_w = reinterpret_cast<unsigned*>(O.rgb + pix0 * 3) + (size_t)warp_id * 24 + lane_id;
+  unsigned* depth_w = reinterpret_cast<unsigned*>(O.depth + pix0) + (threadIdx.x >> 1);
+  unsigned* seg_w = reinterpret_cast<unsigned*>(O.seg + pix0) + (threadIdx.x >> 1);
+  const int rgb_step = (int)(blockDim.x >> 5) * 24, half_step = (int)(blockDim.x >> 1);
+  for (int i = threadIdx.x; i < npix; i += blockDim.x, x += step_x, y += step_y, rgb_w += rgb_step, depth_w += half_step, seg_w += half_step) {
     if (x >= W) { x -= W; y++; }
-    if (x != mask_x) {
-      xmask = 0ull;
-      for (int v = 0; v < nv; v++)
-        if (sh.vis_mode[v] == VM_ANALYTIC && x >= sh.vis_rect[v][0] && x <= sh.vis_rect[v][1]) xmask |= 1ull << v;
-      mask_x = x;
-    }
     const float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
     const v3 rdir = mk3(1.0f, ry, rz);  // camera frame, depth = distance along x
     unsigned best = zkey[i];
-    for (unsigned long long m = xmask; m != 0ull; m &= m - 1ull) {
-      const int v = __ffsll((long long)m) - 1;
-      if (y < sh.vis_rect[v][2] || y > sh.vis_rect[v][3]) continue;
-      const int ty = sh.vis_kind[v];
-      float inv = 0.0f;
-      int face = 1;
-      if (ty == SH_PLANE) {  // half-space, normal = +x of the visual frame: 1/depth is linear in the ray direction
-        const float dlx = sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z;
-        if (dlx < -1e-9f) inv = dlx * sh.vis_c[v];
-      } else {
-        // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
-        const v3 o = mk3(sh.vis_o[v][0], sh.vis_o[v][1], sh.vis_o[v][2]);
-        const v3 dl = mk3(sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z,
-                          sh.vis_R[v][1] * rdir.x + sh.vis_R[v][4] * rdir.y + sh.vis_R[v][7] * rdir.z,
-                          sh.vis_R[v][2] * rdir.x + sh.vis_R[v][5] * rdir.y + sh.vis_R[v][8] * rdir.z);
-        float th = 0.0f;
-        bool hit = false;
-        face = 0;
-        if (ty == SH_BOX) hit = ray_box(o, dl, mk3(sh.vis_sz[v][0], sh.vis_sz[v][1], sh.vis_sz[v][2]), th, face);
-        else if (ty == SH_SPHERE) hit = ray_sphere(o, dl, sh.vis_sz[v][0], th);
-        if (hit) inv = 1.0f / th;
+    for (int k = 0; k < n_patch; k++) {
+      const FacePatch P = sh.patch[k];
+      if (x < P.x0 || x > P.x1 || y < P.y0 || y > P.y1) continue;
+      const float* Rm = sh.vis_R[P.v];
+      const int a = P.face >> 1;
+      // ray direction in the visual's frame is Rcv^T rdir; 1/depth of the hit with the face plane is linear in it: no division
+      const float inv = (Rm[a] * rdir.x + Rm[3 + a] * ry + Rm[6 + a] * rz) * P.cc;
+      if (!inv_depth_in_range(inv, dm)) continue;
+      if (P.bounded) {
+        // hit point (o + dl / inv) inside the face: |o_b inv + dl_b| <= h_b inv for the other two axes (inv > 0)
+        const int b = a == 2 ? 0 : a + 1, c = b == 2 ? 0 : b + 1;
+        const float lb = sh.vis_o[P.v][b] * inv + (Rm[b] * rdir.x + Rm[3 + b] * ry + Rm[6 + b] * rz);
+        if (fabsf(lb) > sh.vis_sz[P.v][b] * inv * 1.00001f) continue;
+        const float lc = sh.vis_o[P.v][c] * inv + (Rm[c] * rdir.x + Rm[3 + c] * ry + Rm[6 + c] * rz);
+        if (fabsf(lc) > sh.vis_sz[P.v][c] * inv * 1.00001f) continue;
       }
+      const unsigned key = raster_key(depth_key_inv(inv, dm), P.face, P.v);
+      best = key < best ? key : best;
+    }
+    for (int k = 0; k < n_sphere; k++) {
+      const int v = sh.sphere[k];
+      if (x < sh.vis_rect[v][0] || x > sh.vis_rect[v][1] || y < sh.vis_rect[v][2] || y > sh.vis_rect[v][3]) continue;
+      // ray in the visual's frame: o = Rcv^T (0 - t), d = Rcv^T rdir
+      const v3 o = mk3(sh.vis_o[v][0], sh.vis_o[v][1], sh.vis_o[v][2]);
+      const v3 dl = mk3(sh.vis_R[v][0] * rdir.x + sh.vis_R[v][3] * rdir.y + sh.vis_R[v][6] * rdir.z,
+                        sh.vis_R[v][1] * rdir.x + sh.vis_R[v][4] * rdir.y + sh.vis_R[v][7] * rdir.z,
+                        sh.vis_R[v][2] * rdir.x + sh.vis_R[v][5] * rdir.y + sh.vis_R[v][8] * rdir.z);
+      float th = 0.0f;
+      if (!ray_sphere(o, dl, sh.vis_sz[v][0], th)) continue;
+      const float inv = 1.0f / th;
       if (inv_depth_in_range(inv, dm)) {
-        const unsigned key = raster_key(depth_key_inv(inv, dm), face, v);
+        const unsigned key = raster_key(depth_key_inv(inv, dm), 0, v);
         best = key < best ? key : best;
       }
     }
@@ -528,16 +572,16 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
           uint8_t* wb = reinterpret_cast<uint8_t*>(sh.rgb_stage[warp_id]);
           wb[3 * lane_id] = c4.x; wb[3 * lane_id + 1] = c4.y; wb[3 * lane_id + 2] = c4.z;
           __syncwarp();
-          if (lane_id < 24) reinterpret_cast<unsigned*>(O.rgb + (pix0 + (size_t)(i - lane_id)) * 3)[lane_id] = sh.rgb_stage[warp_id][lane_id];
+          if (lane_id < 24) *rgb_w = sh.rgb_stage[warp_id][lane_id];
           __syncwarp();
         }
         if (O.mask & B2S_OUT_DEPTH) {
           const unsigned lo = (unsigned)(unsigned short)dmm, hi = __shfl_down_sync(0xffffffffu, lo, 1);
-          if (!(lane_id & 1)) *reinterpret_cast<unsigned*>(O.depth + pix0 + i) = lo | (hi << 16);
+          if (!(lane_id & 1)) *depth_w = lo | (hi << 16);
         }
         if (O.mask & B2S_OUT_SEG) {
           const unsigned lo = (unsigned)(unsigned short)p4.w, hi = __shfl_down_sync(0xffffffffu, lo, 1);
-          if (!(lane_id & 1)) *reinterpret_cast<unsigned*>(O.seg + pix0 + i) = lo | (hi << 16);
+          if (!(lane_id & 1)) *seg_w = lo | (hi << 16);
         }
       } else {
         if (O.mask & B2S_OUT_RGB) { uint8_t* o3 = O.rgb + (pix0 + i) * 3; o3[0] = c4.x; o3[1] = c4.y; o3[2] = c4.z; }

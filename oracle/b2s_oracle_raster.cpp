@@ -9,14 +9,17 @@
 //   * convex hulls, and boxes whose eight corners are in front of the near plane, are triangle meshes: vertices projected to the
 //     screen, sample inside iff the three edge functions are >= 0 after orienting the triangle counter-clockwise, 1/depth
 //     interpolated linearly in screen space, quantised to a 23-bit reversed-z key; back faces culled
-//   * half-spaces, spheres and the remaining boxes are analytic: per pixel they produce a key of the same form (half-space: 1/depth
-//     linear in the ray direction, no division; sphere / box: 1 / ray parameter)
+//   * flat faces tested per pixel (half-spaces; the camera-facing faces of a box that reaches behind the near plane; camera-facing box
+//     faces whose screen rectangle exceeds PATCH_PIXELS, which are then not rasterised): 1/depth of the plane hit is linear in the ray
+//     direction (no division), the hit is inside the face iff |o_b inv + d_b| <= h_b inv (1 + 1e-5) for the two in-plane axes;
+//     spheres: 1 / ray parameter
 //   * the smallest (key << 9 | box face << 6 | visual index) wins, depth = 1 / dequantised(1/depth); flat faces (boxes: the face of the
 //     winning triangle / the face the ray enters through; half-spaces) have one shaded colour per image; spheres: normal = (hit - centre) / r;
 //     hulls: normal from the depth neighbourhood
 //   * segmentation = per_scene_id of the winning visual, 0 = background; position = hit point in mm (round to nearest even)
 // Plain loops, float32, compiled with -ffp-contract=off; the CUDA translation unit is compiled with -fmad=false, so the
 // integer outputs (segmentation, position) are expected to agree bit for bit.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -87,6 +90,7 @@ inline P7 ident() {
 
 const float DEPTH_MAX = 8388607.0f;
 const int KEY_SHIFT = 9;
+const int PATCH_PIXELS = 1024;  // maniskill_b200/csrc/b2s_raster.cuh B2S_PATCH_PIXELS
 inline unsigned make_key(unsigned dk, int face, int v) { return (dk << KEY_SHIFT) | ((unsigned)face << 6) | (unsigned)v; }
 // reversed-z quantisation on 1/depth; per-camera constants computed once (maniskill_b200/csrc/b2s_raster.cuh DepthMap)
 struct DepthMap {
@@ -112,25 +116,6 @@ inline float key_depth(unsigned k, const DepthMap& m) {
   float t = (DEPTH_MAX - (float)k) * m.inv_max;
   float inv = m.invf + t * m.range;
   return 1.0f / inv;
-}
-inline bool ray_box(F3 o, F3 dv, F3 h, float& t_hit, int& face) {
-  float tmin = -1e30f, tmax = 1e30f;
-  face = 0;
-  float oo[3] = {o.x, o.y, o.z}, dd[3] = {dv.x, dv.y, dv.z}, hh[3] = {h.x, h.y, h.z};
-  for (int k = 0; k < 3; k++) {
-    if (fabsf(dd[k]) < 1e-12f) {
-      if (fabsf(oo[k]) > hh[k]) return false;
-    } else {
-      float inv = 1.0f / dd[k];
-      float t0 = (-hh[k] - oo[k]) * inv, t1 = (hh[k] - oo[k]) * inv;
-      if (t0 > t1) { float tt = t0; t0 = t1; t1 = tt; }
-      if (t0 > tmin) { tmin = t0; face = 2 * k + (inv < 0.0f ? 1 : 0); }
-      if (t1 < tmax) tmax = t1;
-    }
-  }
-  if (tmin > tmax || tmax <= 0.0f || tmin <= 0.0f) return false;
-  t_hit = tmin;
-  return true;
 }
 inline bool ray_sphere(F3 o, F3 dv, float r, float& t_hit) {
   float a = dot(dv, dv), b = dot(o, dv), c = dot(o, o) - r * r;
@@ -186,7 +171,10 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
   Xc.q = qnorm(Xc.q);
   float Rc[9];
   qmat(Xc.q, Rc);
-  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vo(n_vis * 3), vc(n_vis, 0.0f);
+  std::vector<float> vR(n_vis * 9), vt(n_vis * 3), vo(n_vis * 3);
+  struct Patch { int x0, x1, y0, y1; float cc; int v, face, bounded; };
+  std::vector<Patch> patches;
+  std::vector<unsigned> face_patch(n_vis, 0u);
   std::vector<unsigned> face_rgb(n_vis * 6);
   std::vector<int> vmode(n_vis, 1);  // 0 rasterised, 1 analytic
   for (int v = 0; v < n_vis; v++) {
@@ -209,7 +197,6 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
     vo[v * 3 + 1] = -(Rm[1] * t.x + Rm[4] * t.y + Rm[7] * t.z);
     vo[v * 3 + 2] = -(Rm[2] * t.x + Rm[5] * t.y + Rm[8] * t.z);
     const int ty = vis_type[v];
-    if (ty == 0 && vo[v * 3] > 0.0f) vc[v] = -1.0f / vo[v * 3];
     if (ty == 4) vmode[v] = 0;
     if (ty == 1) {
       bool behind = false;
@@ -222,6 +209,38 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
       if (!behind) vmode[v] = 0;
     }
   }
+  for (int v = 0; v < n_vis; v++)
+    for (int f = 0; f < 6; f++) {
+      const int a = f >> 1, ty = vis_type[v];
+      const float sgn = (f & 1) ? 1.0f : -1.0f;
+      float ha;
+      if (ty == 0) { if (f != 1) continue; ha = 0.0f; }
+      else if (ty == 1) ha = vis_size[3 * v + a];
+      else continue;
+      const float oa = vo[v * 3 + a];
+      if (!(oa * sgn > ha)) continue;
+      int rx0 = 0, rx1 = W - 1, ry0 = 0, ry1 = H - 1;
+      if (ty == 1 && vmode[v] == 0) {
+        const int b = a == 2 ? 0 : a + 1, c = b == 2 ? 0 : b + 1;
+        float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+        const float* Rm = &vR[v * 9];
+        for (int k = 0; k < 4; k++) {
+          float l[3];
+          l[a] = sgn * ha; l[b] = (k & 1) ? vis_size[3 * v + b] : -vis_size[3 * v + b]; l[c] = (k & 2) ? vis_size[3 * v + c] : -vis_size[3 * v + c];
+          const float px_ = Rm[0] * l[0] + Rm[1] * l[1] + Rm[2] * l[2] + vt[v * 3];
+          const float py_ = Rm[3] * l[0] + Rm[4] * l[1] + Rm[5] * l[2] + vt[v * 3 + 1];
+          const float pz_ = Rm[6] * l[0] + Rm[7] * l[1] + Rm[8] * l[2] + vt[v * 3 + 2];
+          const float u = cx - fx * py_ / px_, w = cy - fy * pz_ / px_;
+          mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w);
+        }
+        rx0 = std::max(0, (int)floorf(mnx) - 1); rx1 = std::min(W - 1, (int)ceilf(mxx) + 1);
+        ry0 = std::max(0, (int)floorf(mny) - 1); ry1 = std::min(H - 1, (int)ceilf(mxy) + 1);
+        if (rx0 > rx1 || ry0 > ry1 || (rx1 - rx0 + 1) * (ry1 - ry0 + 1) <= PATCH_PIXELS) continue;
+      }
+      if (ty == 1) face_patch[v] |= 1u << f;
+      Patch P = {rx0, rx1, ry0, ry1, 1.0f / (sgn * ha - oa), v, f, ty == 1};
+      patches.push_back(P);
+    }
   // vertices: screen x, y, 1/depth (0 = not in front of the near plane)
   std::vector<float> vert((size_t)n_vert * 3 + 3);
   for (int i = 0; i < n_vert; i++) {
@@ -251,6 +270,7 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
       const float* c = vert_local + 3 * (size_t)tri_idx[3 * t + 2];
       for (int k = 0; k < 3; k++)
         if (a[k] == b[k] && b[k] == c[k]) face = 2 * k + (a[k] > 0.0f ? 1 : 0);
+      if ((face_patch[v] >> face) & 1u) continue;  // tested per pixel below
     }
     float px[3], py[3], pd[3];
     bool ok = true;
@@ -293,28 +313,33 @@ void b2o_render_one(int n_vis, const int* vis_type, const int* vis_row, const fl
     float ry = -((float)x + 0.5f - cx) * inv_fx, rz = -((float)y + 0.5f - cy) * inv_fy;
     F3 rdir = f3(1.0f, ry, rz);
     unsigned best = zkey[i];
-    for (int v = 0; v < n_vis; v++) {
-      if (vmode[v] != 1) continue;
-      int ty = vis_type[v];
-      const float* Rm = &vR[v * 9];
-      float inv = 0.0f;
-      int face = 1;
-      if (ty == 0) {
-        float dlx = Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z;
-        if (dlx < -1e-9f) inv = dlx * vc[v];
-      } else {
-        F3 o = f3(vo[v * 3], vo[v * 3 + 1], vo[v * 3 + 2]);
-        F3 dl = f3(Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z, Rm[1] * rdir.x + Rm[4] * rdir.y + Rm[7] * rdir.z,
-                   Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
-        float th = 0.0f;
-        bool hit = false;
-        face = 0;
-        if (ty == 1) hit = ray_box(o, dl, f3(vis_size[3 * v], vis_size[3 * v + 1], vis_size[3 * v + 2]), th, face);
-        else if (ty == 2) hit = ray_sphere(o, dl, vis_size[3 * v], th);
-        if (hit) inv = 1.0f / th;
+    for (const Patch& P : patches) {
+      if (x < P.x0 || x > P.x1 || y < P.y0 || y > P.y1) continue;
+      const float* Rm = &vR[P.v * 9];
+      const int a = P.face >> 1;
+      const float inv = (Rm[a] * rdir.x + Rm[3 + a] * ry + Rm[6 + a] * rz) * P.cc;
+      if (!inv_depth_in_range(inv, dm)) continue;
+      if (P.bounded) {
+        const int b = a == 2 ? 0 : a + 1, c = b == 2 ? 0 : b + 1;
+        const float lb = vo[P.v * 3 + b] * inv + (Rm[b] * rdir.x + Rm[3 + b] * ry + Rm[6 + b] * rz);
+        if (fabsf(lb) > vis_size[3 * P.v + b] * inv * 1.00001f) continue;
+        const float lc = vo[P.v * 3 + c] * inv + (Rm[c] * rdir.x + Rm[3 + c] * ry + Rm[6 + c] * rz);
+        if (fabsf(lc) > vis_size[3 * P.v + c] * inv * 1.00001f) continue;
       }
+      unsigned key = make_key(depth_key_inv(inv, dm), P.face, P.v);
+      if (key < best) best = key;
+    }
+    for (int v = 0; v < n_vis; v++) {
+      if (vis_type[v] != 2) continue;
+      const float* Rm = &vR[v * 9];
+      F3 o = f3(vo[v * 3], vo[v * 3 + 1], vo[v * 3 + 2]);
+      F3 dl = f3(Rm[0] * rdir.x + Rm[3] * rdir.y + Rm[6] * rdir.z, Rm[1] * rdir.x + Rm[4] * rdir.y + Rm[7] * rdir.z,
+                 Rm[2] * rdir.x + Rm[5] * rdir.y + Rm[8] * rdir.z);
+      float th = 0.0f;
+      if (!ray_sphere(o, dl, vis_size[3 * v], th)) continue;
+      float inv = 1.0f / th;
       if (inv_depth_in_range(inv, dm)) {
-        unsigned key = make_key(depth_key_inv(inv, dm), face, v);
+        unsigned key = make_key(depth_key_inv(inv, dm), 0, v);
         if (key < best) best = key;
       }
     }
