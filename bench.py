@@ -235,10 +235,17 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def make(obs_mode, n):
-        env = ms.make("PickCube-v1", num_envs=n, obs_mode=obs_mode, device=dev)
+    phases = {}
+
+    def make(obs_mode, n, task="PickCube-v1"):
+        t0 = time.time()
+        env = ms.make(task, num_envs=n, obs_mode=obs_mode, device=dev)
+        t1 = time.time()
         venv = ms.ManiSkillVectorEnv(env, auto_reset=not args.no_auto_reset)
         venv.reset(seed=shard_seeds(2022, n * world_size, rank, world_size))  # seeds keep the global env id
+        torch.cuda.synchronize()
+        phases.setdefault("make_s", []).append(round(t1 - t0, 2))
+        phases.setdefault("reset_s", []).append(round(time.time() - t1, 2))
         return env, venv
 
     def flat_state(o):
@@ -442,6 +449,21 @@ def run_gpu(args):
                 env_n.close()
                 del env_n, venv_n
         side["num_envs_scan"] = scan
+    if not args.no_other_configs:
+        # BASELINE.json configs[2] and configs[3], device-timed like `value` (L2 flushed, auto-reset on); their task epilogues (evaluate /
+        # reward / observation) are eager torch over the C-ABI buffers, not the fused kernel PickCube has
+        other = {}
+        cab_n = max(1, 2048 // world_size)
+        for key, task, m, n in (("configs[2]", "PegInsertionSide-v1", "rgbd", 4096), ("configs[3]", "OpenCabinetDrawer-v1", "state", cab_n)):
+            env_o, venv_o = make(m, n, task)
+            to, _, lo, _, _ = timed_value(env_o, venv_o, n, 10, 0)
+            check_overflow(env_o, f"the {task} run")
+            to_m, = reduce_max([to])
+            other[key] = {"workload": f"{task} num_envs={n}/GPU obs_mode={m}", "env_steps_per_s": n * world_size * 10 / (to_m * 1e-3),
+                          "ms_per_step": to_m / 10, "steps": 10, "gpu_launches": int(lo)}
+            env_o.close()
+            del env_o, venv_o
+        side["other_configs"] = other
     line["side"] = side
     if rank == 0:
         if not args.no_cpu_baseline and world_size == 1:
@@ -457,6 +479,7 @@ def run_gpu(args):
         else:
             line["cpu_baseline"] = None
         line["config"]["total_s"] = time.time() - t_build0
+        line["config"]["build_phases_rank0"] = phases
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()
@@ -483,6 +506,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-state-only", action="store_true", help="skip the state-only side measurement")
     ap.add_argument("--no-scan", action="store_true", help="skip the num_envs = 1024 / 16384 side measurements")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the PegInsertionSide-v1 rgbd / OpenCabinetDrawer-v1 side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
