@@ -136,6 +136,41 @@ class Scene:
             self.articulations[k].set_state(s, env_idx)
 
 
+class _GraphedEpilogue:
+    """`BaseEnv._epilogue` captured into a CUDA graph after a few eager runs (which also create the contact queries and cached
+    constants the task code allocates lazily).  The captured tensors live in the graph's memory pool; every replay overwrites them, so
+    callers get clones (the eager path returns fresh tensors too)."""
+    WARMUP = 2
+
+    def __init__(self, env):
+        self.env, self.graph, self.out, self.action, self.runs = env, None, None, None, 0
+
+    def run(self, action):
+        env = self.env
+        if self.graph is None:
+            if self.runs < self.WARMUP or action is None:
+                self.runs += 1
+                return env._epilogue(action)
+            self.action = action.clone()
+            torch.cuda.synchronize(env.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.out = env._epilogue(self.action)
+            self.graph = graph
+        if action is not None:
+            self.action.copy_(action)
+        self.graph.replay()
+        return _clone_tree(self.out)
+
+
+def _clone_tree(x):
+    if isinstance(x, dict):
+        return {k: _clone_tree(v) for k, v in x.items()}
+    if isinstance(x, (tuple, list)):
+        return type(x)(_clone_tree(v) for v in x)
+    return x.clone() if isinstance(x, torch.Tensor) else x
+
+
 class BaseEnv:
     """Mirror of mani_skill.envs.sapien_env.BaseEnv for GPU simulation (num_envs >= 1, sim_backend physx_cuda)."""
 
@@ -166,6 +201,7 @@ class BaseEnv:
         self._sim_steps_per_control = self._sim_freq // self._control_freq
         self._world_factory = world_factory
         self._state_version = 0
+        self._epilogue_runner = None
         self._requested_device = device
         self._main_seed = None
         self._episode_seed = np.zeros(num_envs, dtype=np.int64)
@@ -232,6 +268,9 @@ class BaseEnv:
         fused_visual = self._visual and hasattr(self, "_obs_from_fused") and os.environ.get("B2S_FUSED_VISUAL", "1") not in ("", "0")
         if self._fused_arg and self._world_factory is None and (self._obs_mode == "state" or fused_visual):
             self._fused = self._setup_fused_step()
+        self._epilogue_runner = None
+        if self._fused is None and self.graph_epilogue and self._world_factory is None and os.environ.get("B2S_GRAPH_EPILOGUE", "1") not in ("", "0"):
+            self._epilogue_runner = _GraphedEpilogue(self)
         self._state_version += 1
         self._reconfig_counter = self.reconfiguration_freq
 
@@ -400,15 +439,47 @@ class BaseEnv:
         action = self._step_action(action)
         self._elapsed_steps += 1
         self._state_version += 1
+        if self._epilogue_runner is not None:
+            info, core, reward, terminated = self._epilogue_runner.run(action)
+        else:
+            info, core, reward, terminated = self._epilogue(action)
+        obs = self._obs_from_core(core)
+        self._last_obs = obs
+        return obs, reward, terminated, torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+
+    # the part of `step` after the simulation (sapien_env.py:1056-1071): evaluate -> observation (without the pictures) -> reward ->
+    # termination.  Pure tensor code over the persistent C-ABI buffers, no host synchronisation: tasks that set `graph_epilogue` have it
+    # captured once into a CUDA graph and replayed (one launch instead of a few hundred small ones).
+    graph_epilogue = False
+
+    def _epilogue(self, action):
         info = self.get_info()
-        obs = self.get_obs(info)
-        reward = self.get_reward(obs=obs, action=action, info=info)
+        if self._obs_mode == "none":
+            core = dict()
+        else:
+            core = dict(agent=self._get_obs_agent(), extra=self._get_obs_extra(info))
+            if self._obs_mode == "state" or self.obs_mode_struct.state:
+                core = dict(state=U.flatten_state_dict(core))
+        reward = self.get_reward(obs=core, action=action, info=info)
         if "success" in info:
             terminated = torch.logical_or(info["success"], info["fail"]) if "fail" in info else info["success"].clone()
         else:
             terminated = info["fail"].clone() if "fail" in info else torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        self._last_obs = obs
-        return obs, reward, terminated, torch.zeros(self.num_envs, dtype=torch.bool, device=self.device), info
+        return info, core, reward, terminated
+
+    def _obs_from_core(self, core):
+        """`get_obs` from the pictureless part computed by `_epilogue` (the cameras are rendered here, outside the captured part)."""
+        if self._obs_mode == "none":
+            return dict()
+        if self._obs_mode == "state":
+            return core["state"]
+        if self._obs_mode == "state_dict":
+            return core
+        if "state" in core:  # the flat state vector goes after the sensor entries (sapien_env.py:535-544 pops agent / extra, then adds it)
+            obs = self._add_sensor_obs(dict())
+            obs["state"] = core["state"]
+            return obs
+        return self._add_sensor_obs(dict(core))
 
     def _setup_fused_step(self):
         """task hook: return a fused-step handle (backend.create_pick_task) or None to use the torch path."""

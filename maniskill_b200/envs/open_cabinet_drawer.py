@@ -72,6 +72,7 @@ class _JointOfPerEnvLink:
 
 
 class OpenCabinetDrawerEnv(BaseEnv):
+    graph_epilogue = True   # evaluate / observation / reward: pure tensor code, captured into a CUDA graph (base_env._GraphedEpilogue)
     max_episode_steps = 100
     min_open_frac = 0.75
 

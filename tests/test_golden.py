@@ -468,10 +468,12 @@ def test_step_termination_and_reward_dispatch_match_the_reference():
                 continue
             info0 = {k: dict(success=succ, fail=fail)[k].clone() for k in keys}
             fs = SimpleNamespace(num_envs=ns, device=torch.device("cpu"), _elapsed_steps=torch.zeros(ns, dtype=torch.int32), _reward_mode=mode, _fused=None,
-                                 _state_version=0, _step_action=lambda a: a, get_info=lambda: dict(info0), get_obs=lambda info: torch.ones(ns, 2),
+                                 _state_version=0, _step_action=lambda a: a, get_info=lambda: dict(info0), _obs_mode="none", _epilogue_runner=None,
                                  compute_dense_reward=lambda obs, action, info: dense * 5, compute_normalized_dense_reward=lambda obs, action, info: dense)
             fs.get_reward = lambda obs, action, info: BaseEnv.get_reward(fs, obs, action, info)
             fs.compute_sparse_reward = lambda obs, action, info: BaseEnv.compute_sparse_reward(fs, obs, action, info)
+            fs._epilogue = lambda action: BaseEnv._epilogue(fs, action)
+            fs._obs_from_core = lambda core: BaseEnv._obs_from_core(fs, core)
             o, r, te, tr, i = BaseEnv.step(fs, torch.zeros(ns, 3))
             close(r.float(), G[f"step_{tag}_{mode}_reward"], 1e-7)
             assert np.array_equal(te.numpy(), G[f"step_{tag}_{mode}_terminated"]) and np.array_equal(tr.numpy(), G[f"step_{tag}_{mode}_truncated"])
