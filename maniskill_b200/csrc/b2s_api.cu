@@ -60,6 +60,7 @@ struct World : b2s::WorldT<DevMem> {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // captured control steps, keyed by (substeps, fetch_mask); `cap` is the stream they are captured on
   cudaStream_t cap = nullptr;
+  bool pdl_refused = false;  // capture / instantiation with programmatic dependencies failed once: plain edges from then on
   std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::vector<Query> queries;
   std::vector<b2s::RasterGroup*> groups;
@@ -90,6 +91,33 @@ World* get(uint64_t h) {
   return it == g_worlds.end() ? nullptr : it->second;
 }
 
+// ---- programmatic dependent launch (sm_90+): the kernels of a control step form a chain; launched with the
+// programmatic-stream-serialization attribute, the next kernel of the chain is scheduled while its predecessor still runs and parks at
+// griddepcontrol.wait until the predecessor has completed and flushed its writes -- the launch latency and block scheduling of 31 graph
+// nodes no longer sit between the kernels.  Every chained kernel starts with pdl_enter(): wait first, then allow ITS dependents to be
+// scheduled (one kernel of look-ahead, not the whole graph).  Without the attribute both instructions are no-ops.
+__device__ int g_pdl_early_trigger = 0;
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (g_pdl_early_trigger) asm volatile("griddepcontrol.launch_dependents;");
+}
+static int pdl_enabled() {
+  static int on = getenv("B2S_PDL") ? atoi(getenv("B2S_PDL")) : 0;
+  return on;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_chain(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <class C, int ND>
 __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState S, int substeps, unsigned fetch_mask) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,6 +132,7 @@ __global__ void __launch_bounds__(32) step_kernel(b2s::DevModel M, b2s::DevState
 #define B2S_SOLVE_EPB 16  // sub-scenes per block (2 warps of 8 groups with 4 lanes; the impulse table of a block is EPB x MAXROW x 8 B of shared memory)
 template <int NUQ, int L>
 __global__ void __launch_bounds__(B2S_SOLVE_EPB * L) solve_kernel(b2s::DevModel M, b2s::DevState S) {
+  pdl_enter();
   constexpr int MR = b2s::CapsS::MAXROW;
   constexpr int EPB = B2S_SOLVE_EPB;
   __shared__ b2s::LamTot s_lt[EPB][MR];
@@ -123,23 +152,23 @@ static int solve_lanes() {
   static int forced = getenv("B2S_SOLVE_L") ? atoi(getenv("B2S_SOLVE_L")) : 0;
   return forced == 2 ? 2 : 4;
 }
-static void launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st) {
+static cudaError_t launch_solve(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st, bool pdl) {
   const int N = M.n_envs;
   const int L = solve_lanes();
-  const int grid = (N + B2S_SOLVE_EPB - 1) / B2S_SOLVE_EPB;
+  const dim3 grid((N + B2S_SOLVE_EPB - 1) / B2S_SOLVE_EPB), block(B2S_SOLVE_EPB * L);
   if (L == 2) {
-    if (M.n_u > 16) solve_kernel<32, 2><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
-    else solve_kernel<16, 2><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
-  } else {
-    if (M.n_u > 16) solve_kernel<32, 4><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
-    else solve_kernel<16, 4><<<grid, B2S_SOLVE_EPB * L, 0, st>>>(M, S);
+    if (M.n_u > 16) return launch_chain(pdl, solve_kernel<32, 2>, grid, block, 0, st, M, S);
+    return launch_chain(pdl, solve_kernel<16, 2>, grid, block, 0, st, M, S);
   }
+  if (M.n_u > 16) return launch_chain(pdl, solve_kernel<32, 4>, grid, block, 0, st, M, S);
+  return launch_chain(pdl, solve_kernel<16, 4>, grid, block, 0, st, M, S);
 }
 
 // ---- pipelined phase A (b2s_pipe.cuh): kin (lane per sub-scene) -> collide (lane per candidate pair x sub-scene) ->
 // manifest (lane per sub-scene) -> rowfill (lane per row x sub-scene); phase B is the solve_kernel above
 template <class C, int ND, int PART>
 __global__ void __launch_bounds__(32) kin_kernel(b2s::DevModel M, b2s::DevState S) {
+  pdl_enter();
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   b2s::kin_env<C, ND, PART>(M, S, env);
@@ -147,6 +176,7 @@ __global__ void __launch_bounds__(32) kin_kernel(b2s::DevModel M, b2s::DevState 
 
 #define B2S_COLLIDE_THREADS 64
 __global__ void __launch_bounds__(B2S_COLLIDE_THREADS) collide_kernel(b2s::DevModel M, b2s::DevState S) {
+  pdl_enter();
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   b2s::collide_env(M, S, env, blockIdx.y);
@@ -154,6 +184,7 @@ __global__ void __launch_bounds__(B2S_COLLIDE_THREADS) collide_kernel(b2s::DevMo
 
 template <class C>
 __global__ void __launch_bounds__(64) manifest_kernel(b2s::DevModel M, b2s::DevState S) {
+  pdl_enter();
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   b2s::manifest_env<C>(M, S, env);
@@ -161,6 +192,7 @@ __global__ void __launch_bounds__(64) manifest_kernel(b2s::DevModel M, b2s::DevS
 
 template <class C, int ND, int NUQ, int L>
 __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevState S) {
+  pdl_enter();
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   const int r = blockIdx.y;
@@ -176,6 +208,7 @@ __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevS
 #define B2S_FETCH_EPB 32
 template <class C>
 __global__ void __launch_bounds__(B2S_FETCH_EPB) fetch_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask) {
+  pdl_enter();
   extern __shared__ __align__(128) float fetch_tile[];
   const int env0 = blockIdx.x * B2S_FETCH_EPB, env = env0 + threadIdx.x;
   const int per_env = M.n_rows * 13;
@@ -460,7 +493,7 @@ int32_t b2s_world_buffers(uint64_t world, B2SBufferTable* out) {
 
 // Enqueues the kernels of `substeps` physics substeps (+ the fetch) on `st`.  The dynamics half of kin runs on the world's side
 // stream between a fork and a join event; under stream capture the same calls become the dependency edges of the graph.
-static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_t st) {
+static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_t st, bool pdl = false) {
   const int N = w->M.n_envs;
   static int fused = getenv("B2S_FUSED") ? atoi(getenv("B2S_FUSED")) : 0;
   if (!fused && w->M.n_u <= 32) {
@@ -472,46 +505,51 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
       CK(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     }
     const bool overlap = overlap_on != 0;
+    const b2s::DevModel& M = w->M;
+    const b2s::DevState& S = w->S;
     for (int sidx = 0; sidx < substeps; sidx++) {
-      const int pg = (N + 31) / 32;
-#define B2S_KIN(PART_, STREAM_)                                                                                  \
-  {                                                                                                              \
-    if (w->caps == 0 && w->M.n_dof == 9) kin_kernel<b2s::CapsS, 9, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);   \
-    else if (w->caps == 0) kin_kernel<b2s::CapsS, 0, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);                 \
-    else kin_kernel<b2s::CapsL, 0, PART_><<<pg, 32, 0, STREAM_>>>(w->M, w->S);                                   \
+      const dim3 pg((N + 31) / 32), b32(32);
+      // the chain on `st` is launched with programmatic dependencies (pdl); the dynamics half of kin runs on the side stream behind a
+      // full event dependency
+#define B2S_KIN(PART_, STREAM_, PDL_)                                                                                        \
+  {                                                                                                                          \
+    if (w->caps == 0 && M.n_dof == 9) { CK(launch_chain(PDL_, kin_kernel<b2s::CapsS, 9, PART_>, pg, b32, 0, STREAM_, M, S)); } \
+    else if (w->caps == 0) { CK(launch_chain(PDL_, kin_kernel<b2s::CapsS, 0, PART_>, pg, b32, 0, STREAM_, M, S)); } \
+    else { CK(launch_chain(PDL_, kin_kernel<b2s::CapsL, 0, PART_>, pg, b32, 0, STREAM_, M, S)); } \
   }
       if (overlap) {
-        B2S_KIN(1, st)
+        B2S_KIN(1, st, pdl)
         CK(cudaEventRecord(w->ev_fork, st));
         CK(cudaStreamWaitEvent(w->side, w->ev_fork, 0));
-        B2S_KIN(2, w->side)
+        B2S_KIN(2, w->side, false)
         CK(cudaEventRecord(w->ev_join, w->side));
       } else {
-        B2S_KIN(0, st)
+        B2S_KIN(0, st, pdl)
       }
 #undef B2S_KIN
-      if (w->M.n_pair > 0)
-        collide_kernel<<<dim3((N + B2S_COLLIDE_THREADS - 1) / B2S_COLLIDE_THREADS, w->M.n_pair), B2S_COLLIDE_THREADS, 0, st>>>(w->M, w->S);
-      if (w->caps == 0) manifest_kernel<b2s::CapsS><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
-      else manifest_kernel<b2s::CapsL><<<(N + 31) / 32, 32, 0, st>>>(w->M, w->S);
+      if (M.n_pair > 0)
+        CK(launch_chain(pdl, collide_kernel, dim3((N + B2S_COLLIDE_THREADS - 1) / B2S_COLLIDE_THREADS, M.n_pair), dim3(B2S_COLLIDE_THREADS), 0, st, M, S));
+      if (w->caps == 0) { CK(launch_chain(pdl, manifest_kernel<b2s::CapsS>, pg, b32, 0, st, M, S)); }
+      else { CK(launch_chain(pdl, manifest_kernel<b2s::CapsL>, pg, b32, 0, st, M, S)); }
       if (overlap) CK(cudaStreamWaitEvent(st, w->ev_join, 0));
-      const dim3 rg((N + 127) / 128, MR);
-#define B2S_ROWFILL(C_, ND_, NUQ_)                                                                  \
-  {                                                                                                \
-    if (solve_lanes() == 2) rowfill_kernel<C_, ND_, NUQ_, 2><<<rg, 128, 0, st>>>(w->M, w->S);      \
-    else rowfill_kernel<C_, ND_, NUQ_, 4><<<rg, 128, 0, st>>>(w->M, w->S);                         \
+      const dim3 rg((N + 127) / 128, MR), b128(128);
+#define B2S_ROWFILL(C_, ND_, NUQ_)                                                                                   \
+  {                                                                                                                 \
+    if (solve_lanes() == 2) { CK(launch_chain(pdl, rowfill_kernel<C_, ND_, NUQ_, 2>, rg, b128, 0, st, M, S)); } \
+    else { CK(launch_chain(pdl, rowfill_kernel<C_, ND_, NUQ_, 4>, rg, b128, 0, st, M, S)); } \
   }
-      if (w->caps == 0 && w->M.n_dof == 9 && w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 9, 16)
-      else if (w->caps == 0 && w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 0, 16)
+      if (w->caps == 0 && M.n_dof == 9 && M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 9, 16)
+      else if (w->caps == 0 && M.n_u <= 16) B2S_ROWFILL(b2s::CapsS, 0, 16)
       else if (w->caps == 0) B2S_ROWFILL(b2s::CapsS, 0, 32)
-      else if (w->M.n_u <= 16) B2S_ROWFILL(b2s::CapsL, 0, 16)
+      else if (M.n_u <= 16) B2S_ROWFILL(b2s::CapsL, 0, 16)
       else B2S_ROWFILL(b2s::CapsL, 0, 32)
 #undef B2S_ROWFILL
-      launch_solve(w->M, w->S, st);
+      CK(launch_solve(M, S, st, pdl));
     }
     if (fetch_mask) {
-      if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, fetch_mask);
-      else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, fetch_mask);
+      const dim3 fg((N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB), fb(B2S_FETCH_EPB);
+      if (w->caps == 0) { CK(launch_chain(pdl, fetch_kernel<b2s::CapsS>, fg, fb, fetch_smem(M), st, M, S, fetch_mask)); }
+      else { CK(launch_chain(pdl, fetch_kernel<b2s::CapsL>, fg, fb, fetch_smem(M), st, M, S, fetch_mask)); }
     }
     CK(cudaGetLastError());
     return B2S_OK;
@@ -541,16 +579,28 @@ int32_t b2s_step(uint64_t world, int32_t substeps, uint32_t fetch_mask, void* st
   auto it = w->graphs.find(key);
   if (it == w->graphs.end()) {
     if (!w->cap) CK(cudaStreamCreateWithFlags(&w->cap, cudaStreamNonBlocking));
-    CK(cudaStreamBeginCapture(w->cap, cudaStreamCaptureModeRelaxed));
-    int rc = enqueue_step(w, substeps, fetch_mask, w->cap);
-    cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(w->cap, &g);
-    if (rc != B2S_OK) { if (g) cudaGraphDestroy(g); return rc; }
-    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
     cudaGraphExec_t ex = nullptr;
-    e = cudaGraphInstantiate(&ex, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) return fail(B2S_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+    // first with programmatic dependencies between the kernels of the chain; a driver that refuses them in a capture gets plain edges
+    if (pdl_enabled()) {
+      int early = pdl_enabled() >= 2;  // B2S_PDL=1: dependents are released when a kernel's blocks exit; 2: right after its own wait
+      CK(cudaMemcpyToSymbol(g_pdl_early_trigger, &early, sizeof(int)));
+    }
+    for (int attempt = (pdl_enabled() && !w->pdl_refused) ? 0 : 1; attempt < 2 && !ex; attempt++) {
+      const bool pdl = attempt == 0;
+      CK(cudaStreamBeginCapture(w->cap, cudaStreamCaptureModeRelaxed));
+      int rc = enqueue_step(w, substeps, fetch_mask, w->cap, pdl);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(w->cap, &g);
+      if (rc == B2S_OK && e == cudaSuccess) e = cudaGraphInstantiate(&ex, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (rc != B2S_OK || e != cudaSuccess) {
+        ex = nullptr;
+        cudaGetLastError();
+        if (pdl) { w->pdl_refused = true; continue; }
+        if (rc != B2S_OK) return rc;
+        return fail(B2S_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+      }
+    }
     it = w->graphs.emplace(key, ex).first;
   }
   CK(cudaGraphLaunch(it->second, st));
