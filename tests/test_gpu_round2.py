@@ -294,3 +294,44 @@ def test_graphed_epilogue_equals_the_eager_one(task, obs_mode, monkeypatch):
             if x[k] is None:
                 continue
             assert torch.equal(x[k], y[k]), (task, obs_mode, i, k)
+
+
+def test_record_and_replay_on_the_device(tmp_path):
+    """RecordEpisode / replay_trajectory (mani_skill/utils/wrappers/record.py, mani_skill/trajectory/replay_trajectory.py) over the CUDA
+    world: 8 sub-scenes recorded through the fused control step with device tensors, partial flush after a partial reset, then replayed
+    from seed + actions and from the stored environment states on a fresh world."""
+    import torch
+    import maniskill_b200 as ms
+    from maniskill_b200.trajectory import RecordEpisode, load_trajectories, replay_trajectory
+    env = ms.make("PickCube-v1", num_envs=1, obs_mode="state", device="cuda:0")
+    rec = RecordEpisode(env, str(tmp_path))
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    for seed in (11, 12):
+        rec.reset(seed=seed)
+        for _ in range(6):
+            rec.step(2 * torch.rand(1, 8, generator=g, device="cuda:0") - 1)
+    rec.close()
+    meta, trajs = load_trajectories(str(tmp_path / "trajectory"))
+    assert [e["episode_seed"] for e in meta["episodes"]] == [11, 12] and trajs["traj_0"]["actions"].shape == (6, 8)
+    for mode in ("seed_and_actions", "env_states"):
+        env2 = ms.make("PickCube-v1", num_envs=1, obs_mode="state", device="cuda:0")
+        if mode != "seed_and_actions":
+            env2.reset(seed=999)
+        res = replay_trajectory(env2, str(tmp_path / "trajectory"), use_env_states=mode == "env_states")
+        assert len(res) == 2
+        for r in res:
+            assert r["final_state_error"] < 1e-5 and r["success"] == r["recorded_success"], (mode, r)
+        env2.close()
+    # many sub-scenes, partial reset -> partial flush
+    envn = ms.make("PickCube-v1", num_envs=8, obs_mode="state", device="cuda:0")
+    recn = RecordEpisode(envn, str(tmp_path / "many"))
+    recn.reset(seed=3)
+    for _ in range(4):
+        recn.step(2 * torch.rand(8, 8, generator=g, device="cuda:0") - 1)
+    recn.reset(options=dict(env_idx=torch.tensor([2, 5], device="cuda:0")))
+    for _ in range(2):
+        recn.step(2 * torch.rand(8, 8, generator=g, device="cuda:0") - 1)
+    recn.close()
+    meta, trajs = load_trajectories(str(tmp_path / "many" / "trajectory"))
+    lens = sorted(t["actions"].shape[0] for t in trajs.values())
+    assert lens == [2, 2, 4, 4, 6, 6, 6, 6, 6, 6], lens
