@@ -193,17 +193,46 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def pin_rank_to_cores(local_rank, world_size):
-    """Each rank gets its own contiguous slice of the usable cores (on the usual two-socket boxes contiguous core ids and GPU ids share a
-    NUMA node); keeps eight python processes from migrating over each other."""
+    """Each rank gets its own slice of the host cores that are local to ITS GPU (NVML's CPU affinity of the device = the NUMA node its PCIe
+    root hangs off), shared evenly with the other ranks whose GPUs sit on the same node: the pinned host buffers of the end-to-end loop are
+    then first-touched on the node the GPU copies into.  Falls back to contiguous slices of the usable cores.  Returns (cores, how)."""
     try:
         cores = sorted(os.sched_getaffinity(0))
-        per = len(cores) // max(world_size, 1)
-        if world_size > 1 and per >= 2:
-            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
-            return per
+    except Exception:
+        return None, "unpinned"
+    if world_size <= 1:
+        return None, "unpinned"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        words = max(cores) // 64 + 1
+        masks = []
+        for g in range(world_size):
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(g).uuid))
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(g)
+            aff = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            masks.append(frozenset(64 * w + b for w, word in enumerate(aff) for b in range(64) if (int(word) >> b) & 1) & frozenset(cores))
+        mine = masks[local_rank]
+        peers = [g for g in range(world_size) if masks[g] == mine]
+        per = len(mine) // len(peers)
+        if per >= 2:
+            lst = sorted(mine)
+            k = peers.index(local_rank)
+            os.sched_setaffinity(0, lst[k * per:(k + 1) * per])
+            return per, "nvml-numa"
     except Exception:
         pass
-    return None
+    try:
+        per = len(cores) // world_size
+        if per >= 2:
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+            return per, "contiguous"
+    except Exception:
+        pass
+    return None, "unpinned"
 
 
 def run_gpu(args):
@@ -215,7 +244,7 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    pinned_cores = pin_rank_to_cores(local_rank, world_size)
+    pinned_cores, pinned_how = pin_rank_to_cores(local_rank, world_size)
     torch.set_num_threads(max(1, min(4, pinned_cores or 4)))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -407,7 +436,7 @@ def run_gpu(args):
                    "wall_s": t_wall_max, "step_ms_median_rank0": step_ms[len(step_ms) // 2], "step_ms_max_rank0": step_ms[-1],
                    "host_loop_s_max_over_ranks": t_loop_max, "host_loop_s_min_over_ranks": -neg[0],
                    "e2e_loop_s_max_over_ranks": t_e2e_loop_max, "e2e_loop_s_min_over_ranks": -neg[1],
-                   "build_s": build_s, "cores_per_rank": pinned_cores},
+                   "build_s": build_s, "cores_per_rank": pinned_cores, "core_pinning": pinned_how},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "pinned host actions in; state + rgb + depth + reward + done out to pinned host memory every step, device->host copies of "
                        "step i overlapped with step i+1 (copy stream), host waits for step i-1 before issuing step i+1"},
