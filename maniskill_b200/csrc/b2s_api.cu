@@ -60,7 +60,10 @@ struct World : b2s::WorldT<DevMem> {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // captured control steps, keyed by (substeps, fetch_mask); `cap` is the stream they are captured on
   cudaStream_t cap = nullptr;
-  bool pdl_refused = false;  // capture / instantiation with programmatic dependencies failed once: plain edges from then on
+  bool pdl_refused = false;
+  // dynamics half of kin: 0 = one lane per sub-scene (kin_kernel<.., 2>, default), 1 = eight lanes per sub-scene (kin_dyn_kernel).  The group
+  // kernel alone is 1.5x (9 joints) to 2.6x (24 joints) faster, but next to collide + manifest it slows the control step
+  int kin_group = 0;  // capture / instantiation with programmatic dependencies failed once: plain edges from then on
   std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::vector<Query> queries;
   std::vector<b2s::RasterGroup*> groups;
@@ -172,6 +175,34 @@ __global__ void __launch_bounds__(32) kin_kernel(b2s::DevModel M, b2s::DevState 
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= M.n_envs) return;
   b2s::kin_env<C, ND, PART>(M, S, env);
+}
+
+// the dynamics half of kin with 8 lanes per sub-scene (b2s_pipe.cuh kin_dyn_group): the articulated inertias in shared memory, lane r
+// owns row r of the 6x6 sweeps, reductions by shuffles inside the 8-lane group, one M~^-1 column per lane
+// Sub-scenes per CTA: the scratch is 7.5 KB (12 joints) / 15 KB (24 joints) per sub-scene; 30 KB per CTA keeps 7 CTAs per SM so that the 1024 CTAs of
+// 4096 (2048 large) sub-scenes are resident in one wave -- with 8 sub-scenes per CTA the launch ran in two waves and was slower than the one-lane kernel
+#define B2S_KIN_G 8
+template <class C, int EPB>
+__global__ void __launch_bounds__(B2S_KIN_G * EPB) kin_dyn_kernel(b2s::DevModel M, b2s::DevState S) {
+  constexpr int B2S_KIN_EPB = EPB;
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char kin_dyn_smem[];
+  b2s::KinDynScratch<C, B2S_KIN_G>* W = reinterpret_cast<b2s::KinDynScratch<C, B2S_KIN_G>*>(kin_dyn_smem);
+  const int g = threadIdx.x / B2S_KIN_G, lane = threadIdx.x % B2S_KIN_G;
+  const int env = blockIdx.x * B2S_KIN_EPB + g;
+  if (env >= M.n_envs) return;
+  b2s::kin_dyn_group<C, B2S_KIN_G>(M, S, env, lane, b2s::group_mask<B2S_KIN_G>(threadIdx.x & 31), W[g]);
+}
+template <class C, int EPB>
+static cudaError_t launch_kin_dyn(const b2s::DevModel& M, const b2s::DevState& S, cudaStream_t st) {
+  const size_t smem = sizeof(b2s::KinDynScratch<C, B2S_KIN_G>) * EPB;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kin_dyn_kernel<C, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_chain(false, kin_dyn_kernel<C, EPB>, dim3((M.n_envs + EPB - 1) / EPB), dim3(B2S_KIN_G * EPB), smem, st, M, S);
 }
 
 #define B2S_COLLIDE_THREADS 64
@@ -426,6 +457,7 @@ int32_t b2s_world_create(const B2SModel* model, int32_t device, uint64_t* world)
   DeviceGuard guard_(device);
   World* w = new World();
   w->device = device;
+  w->kin_group = getenv("B2S_KIN_GROUP") ? atoi(getenv("B2S_KIN_GROUP")) : 0;  // read per world (tests compare both forms in one process)
   const char* err = w->build(*model);
   if (err) {
     w->release();
@@ -521,7 +553,12 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
         B2S_KIN(1, st, pdl)
         CK(cudaEventRecord(w->ev_fork, st));
         CK(cudaStreamWaitEvent(w->side, w->ev_fork, 0));
-        B2S_KIN(2, w->side, false)
+        if (w->kin_group) {
+          if (w->caps == 0) { CK((launch_kin_dyn<b2s::CapsS, 4>(M, S, w->side))); }
+          else { CK((launch_kin_dyn<b2s::CapsL, 2>(M, S, w->side))); }
+        } else {
+          B2S_KIN(2, w->side, false)
+        }
         CK(cudaEventRecord(w->ev_join, w->side));
       } else {
         B2S_KIN(0, st, pdl)

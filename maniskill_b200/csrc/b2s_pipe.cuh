@@ -79,6 +79,39 @@ B2S_HD void emit_joint_rows(const DevModel& M, const DevState& St, int env, cons
   (void)N;
 }
 
+// free body b: world centre of mass, inverse mass, world inverse inertia (zero for kinematic bodies) -> kin_fb
+B2S_HDN void kin_free_body(const DevModel& M, const DevState& St, int env, int b) {
+  const size_t N = M.n_envs;
+  int ov = M.fb_ov[b];
+  float mass, in6[6];
+  v3 com;
+  if (ov >= 0) {
+    mass = M.ov_fb_mass[(size_t)(ov * 10) * N + env];
+    com = mk3(M.ov_fb_mass[(size_t)(ov * 10 + 1) * N + env], M.ov_fb_mass[(size_t)(ov * 10 + 2) * N + env],
+              M.ov_fb_mass[(size_t)(ov * 10 + 3) * N + env]);
+    for (int k = 0; k < 6; k++) in6[k] = M.ov_fb_mass[(size_t)(ov * 10 + 4 + k) * N + env];
+  } else {
+    mass = M.fb_mass[b];
+    com = mk3(M.fb_com[3 * b], M.fb_com[3 * b + 1], M.fb_com[3 * b + 2]);
+    for (int k = 0; k < 6; k++) in6[k] = M.fb_inertia[6 * b + k];
+  }
+  float f[7];
+  for (int k = 0; k < 7; k++) f[k] = St.fb[(size_t)(b * 13 + k) * N + env];
+  pose Xb = pose7(f);
+  m3 Rm = qmat(Xb.q);
+  v3 fcom = Xb.p + mul(Rm, com);
+  float finvm = 0.f;
+  m3 fI;
+  for (int k = 0; k < 9; k++) fI.m[k] = 0.f;
+  if (M.fb_type[b] == 0) {
+    finvm = 1.f / mass;
+    fI = mul(mul(Rm, inverse3(sym6(in6[0], in6[1], in6[2], in6[3], in6[4], in6[5]))), transpose(Rm));
+  }
+  float* o = St.kin_fb + (size_t)(b * B2S_KF) * N + env;
+  o[0] = fcom.x; o[N] = fcom.y; o[2 * N] = fcom.z; o[3 * N] = finvm;
+  for (int k = 0; k < 9; k++) o[(4 + k) * N] = fI.m[k];
+}
+
 // ------------------------------------------------------------------------------------------------ kin
 // PART 0: everything.  The library runs it as two kernels so that the dynamics overlap the collision pass: PART 1 = forward
 // kinematics only (joint frames, velocities, motion axes -> kin_link; clears the hit bitmap), PART 2 = the rest (reloads kin_link).
@@ -235,37 +268,187 @@ B2S_HDN void kin_env(const DevModel& M, const DevState& St, int env) {
       St.kin_minv[(size_t)(i * nd + j) * N + env] = qd2;
     }
   }
-  // free bodies: world centre of mass, inverse mass, world inverse inertia (zero for kinematic bodies)
-  for (int b = 0; b < M.n_fb; b++) {
-    int ov = M.fb_ov[b];
-    float mass, in6[6];
-    v3 com;
-    if (ov >= 0) {
-      mass = M.ov_fb_mass[(size_t)(ov * 10) * N + env];
-      com = mk3(M.ov_fb_mass[(size_t)(ov * 10 + 1) * N + env], M.ov_fb_mass[(size_t)(ov * 10 + 2) * N + env],
-                M.ov_fb_mass[(size_t)(ov * 10 + 3) * N + env]);
-      for (int k = 0; k < 6; k++) in6[k] = M.ov_fb_mass[(size_t)(ov * 10 + 4 + k) * N + env];
-    } else {
-      mass = M.fb_mass[b];
-      com = mk3(M.fb_com[3 * b], M.fb_com[3 * b + 1], M.fb_com[3 * b + 2]);
-      for (int k = 0; k < 6; k++) in6[k] = M.fb_inertia[6 * b + k];
-    }
-    float f[7];
-    for (int k = 0; k < 7; k++) f[k] = St.fb[(size_t)(b * 13 + k) * N + env];
-    pose Xb = pose7(f);
-    m3 Rm = qmat(Xb.q);
-    v3 fcom = Xb.p + mul(Rm, com);
-    float finvm = 0.f;
-    m3 fI;
-    for (int k = 0; k < 9; k++) fI.m[k] = 0.f;
-    if (M.fb_type[b] == 0) {
-      finvm = 1.f / mass;
-      fI = mul(mul(Rm, inverse3(sym6(in6[0], in6[1], in6[2], in6[3], in6[4], in6[5]))), transpose(Rm));
-    }
-    float* o = St.kin_fb + (size_t)(b * B2S_KF) * N + env;
-    o[0] = fcom.x; o[N] = fcom.y; o[2 * N] = fcom.z; o[3 * N] = finvm;
-    for (int k = 0; k < 9; k++) o[(4 + k) * N] = fI.m[k];
+  for (int b = 0; b < M.n_fb; b++) kin_free_body(M, St, env, b);
+}
+
+// ------------------------------------------------------------------------------------------------ kin, dynamics half, G lanes per sub-scene
+// The same arithmetic as kin_env<C, ND, 2> shared by a group of G lanes (device: G = 8, four sub-scenes per warp; host emulation:
+// G = 1).  What is parallel: the per-joint preparation (lanes stride over the joints), the 6x6 articulated-inertia sweeps (lane r owns
+// ROW r of every 6x6 matrix and component r of every spatial vector: U = IA S, the rank-one downdate and the shift to the parent are
+// row-local, the scalars D = S.U and u = tau - S.pA are reductions over the group by shuffles), the forward acceleration sweep (one
+// reduction per joint), the unit-torque solves for the columns of M~^-1 (one column per lane) and the free bodies (one per lane).
+// The matrices live in the group's scratch (shared memory on the device) instead of 324+ floats of local memory per lane.
+template <int G>
+B2S_HD unsigned group_mask(int lane_in_warp) {
+  return G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane_in_warp & ~(G - 1)));
+}
+template <int G>
+B2S_HD float group_sum_m(float x, unsigned mask) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) x += __shfl_xor_sync(mask, x, o);
+#endif
+  (void)mask;
+  return x;
+}
+B2S_HD void group_sync_m(unsigned mask) {
+#if defined(__CUDA_ARCH__)
+  __syncwarp(mask);
+#endif
+  (void)mask;
+}
+
+template <class C, int G>
+struct KinDynScratch {
+  float S[C::MAXD][6], V[C::MAXD][6], cvp[C::MAXD][6], pA[C::MAXD][6], U[C::MAXD][6], acc[C::MAXD][6], fext[C::MAXD][6];
+  float IA[C::MAXD][36];
+  float Iw[C::MAXD][9], cW[C::MAXD][3];
+  float Dinv[C::MAXD], u[C::MAXD], tau[C::MAXD], arm[C::MAXD], qdd[C::MAXD], q[C::MAXD], qd[C::MAXD], tq[C::MAXD], tqd[C::MAXD], qf[C::MAXD];
+  float col_uu[G][C::MAXD], col_aa[G][C::MAXD][6];
+  int sat;
+};
+
+B2S_HD v6 load6(const float* p) { return mk6(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5])); }
+B2S_HD void store6(float* p, v6 x) { p[0] = x.a.x; p[1] = x.a.y; p[2] = x.a.z; p[3] = x.l.x; p[4] = x.l.y; p[5] = x.l.z; }
+
+// lane: 0 .. G-1 within the group; mask: the group's lanes of the warp (group_mask)
+template <class C, int G>
+B2S_HDN void kin_dyn_group(const DevModel& M, const DevState& St, int env, int lane, unsigned mask, KinDynScratch<C, G>& W) {
+  const size_t N = M.n_envs;
+  const int nd = M.n_dof;
+  const float dt = M.dt;
+  const v3 grav = mk3(M.gx, M.gy, M.gz);
+  // ---- per joint: state, FK results of part 1, bias forces, world inertia, drive torque and implicit diagonal
+  for (int i = lane; i < nd; i += G) {
+    const float q = St.q[i * N + env], qd = St.qd[i * N + env], tq = St.tq[i * N + env], tqd = St.tqd[i * N + env], qf = St.qf[i * N + env];
+    W.q[i] = q; W.qd[i] = qd; W.tq[i] = tq; W.tqd[i] = tqd; W.qf[i] = qf;
+    const float* o = St.kin_link + (size_t)(i * B2S_KL) * N + env;
+    float w[B2S_KL];
+    for (int k = 0; k < B2S_KL; k++) w[k] = o[k * N];
+    const pose X = pose7(w);
+    const v6 V = mk6(mk3(w[7], w[8], w[9]), mk3(w[10], w[11], w[12]));
+    const v6 S = mk6(mk3(w[13], w[14], w[15]), mk3(w[16], w[17], w[18]));
+    const int a = M.dof_art[i];
+    const v3 Oa = mk3(St.root[(size_t)(a * 7) * N + env], St.root[(size_t)(a * 7 + 1) * N + env], St.root[(size_t)(a * 7 + 2) * N + env]);
+    store6(W.S[i], S); store6(W.V[i], V);
+    store6(W.cvp[i], crm(V, S * qd));
+    const m3 Rm = qmat(X.q);
+    const v3 com = mk3(M.dof_com[3 * i], M.dof_com[3 * i + 1], M.dof_com[3 * i + 2]);
+    const v3 c = X.p + mul(Rm, com) - Oa;
+    const float* in6 = M.dof_inertia + 6 * i;
+    const m3 Iw = mul(mul(Rm, sym6(in6[0], in6[1], in6[2], in6[3], in6[4], in6[5])), transpose(Rm));
+    const float mass = M.dof_mass[i];
+    W.cW[i][0] = c.x; W.cW[i][1] = c.y; W.cW[i][2] = c.z;
+    for (int k = 0; k < 9; k++) W.Iw[i][k] = Iw.m[k];
+    const v3 fg = grav * (mass * M.dof_gravity[i]);
+    store6(W.fext[i], mk6(cross(c, fg), fg));
+    const float kp = M.dof_drive[4 * i], kd = M.dof_drive[4 * i + 1];
+    const float damp = M.dof_passive[4 * i], armature = M.dof_passive[4 * i + 2];
+    W.tau[i] = kp * (tq - q - dt * qd) + kd * (tqd - qd) + qf - damp * qd;
+    W.arm[i] = armature + dt * kd + dt * dt * kp + dt * damp;
   }
+  group_sync_m(mask);
+  // ---- ABA with the implicit drive in the joint diagonal; second pass for force-limited drives
+  for (int pass = 0; pass < 2; pass++) {
+    for (int i = lane; i < nd; i += G) {
+      float I[36];
+      m3 Iw;
+      for (int k = 0; k < 9; k++) Iw.m[k] = W.Iw[i][k];
+      spatial_inertia(I, M.dof_mass[i], mk3(W.cW[i][0], W.cW[i][1], W.cW[i][2]), Iw);
+      for (int k = 0; k < 36; k++) W.IA[i][k] = I[k];
+      const v6 V = load6(W.V[i]);
+      store6(W.pA[i], crf(V, m6mul(I, V)) - load6(W.fext[i]));
+    }
+    if (lane == 0) W.sat = 0;
+    group_sync_m(mask);
+    B2S_NO_UNROLL
+    for (int i = nd - 1; i >= 0; i--) {
+      const int p = M.dof_parent[i];
+      float d = 0.f, e = 0.f;
+      for (int r = lane; r < 6; r += G) {
+        float ur = 0.f;
+        for (int c = 0; c < 6; c++) ur += W.IA[i][6 * r + c] * W.S[i][c];
+        W.U[i][r] = ur;
+        d += W.S[i][r] * ur;
+        e += W.S[i][r] * W.pA[i][r];
+      }
+      d = group_sum_m<G>(d, mask);
+      e = group_sum_m<G>(e, mask);
+      const float Dinv = 1.f / (d + W.arm[i]);
+      const float ui = W.tau[i] - e;
+      if (lane == 0) { W.Dinv[i] = Dinv; W.u[i] = ui; }
+      group_sync_m(mask);  // U of this joint is complete
+      if (p >= 0) {
+        for (int r = lane; r < 6; r += G) {
+          const float ur = W.U[i][r];
+          float par = W.pA[i][r] + ur * (ui * Dinv);
+          for (int c = 0; c < 6; c++) {
+            const float ia = W.IA[i][6 * r + c] - ur * W.U[i][c] * Dinv;
+            par += ia * W.cvp[i][c];
+            W.IA[p][6 * r + c] += ia;
+          }
+          W.pA[p][r] += par;  // rows are owned by lanes: the parent's row r is only ever touched by this lane
+        }
+      }
+    }
+    B2S_NO_UNROLL
+    for (int i = 0; i < nd; i++) {
+      const int p = M.dof_parent[i];
+      float t = 0.f, apr[6];
+      for (int r = lane; r < 6; r += G) {
+        apr[r] = (p >= 0 ? W.acc[p][r] : 0.f) + W.cvp[i][r];
+        t += W.U[i][r] * apr[r];
+      }
+      t = group_sum_m<G>(t, mask);
+      const float qdd = (W.u[i] - t) * W.Dinv[i];
+      for (int r = lane; r < 6; r += G) W.acc[i][r] = apr[r] + W.S[i][r] * qdd;
+      if (lane == 0) W.qdd[i] = qdd;
+    }
+    group_sync_m(mask);
+    if (pass == 1) break;
+    for (int i = lane; i < nd; i += G) {
+      const float kp = M.dof_drive[4 * i], kd = M.dof_drive[4 * i + 1], fl = M.dof_drive[4 * i + 2];
+      const float damp = M.dof_passive[4 * i], armature = M.dof_passive[4 * i + 2];
+      const float qd1 = W.qd[i] + dt * W.qdd[i];
+      const float f = kp * (W.tq[i] - W.q[i] - dt * qd1) + kd * (W.tqd[i] - qd1);
+      if (fabsf(f) > fl) {
+        W.sat = 1;
+        W.tau[i] = (f > 0.f ? fl : -fl) + W.qf[i] - damp * W.qd[i];
+        W.arm[i] = armature + dt * damp;
+      }
+    }
+    group_sync_m(mask);
+    const int any_sat = W.sat;
+    group_sync_m(mask);  // everybody has read the flag before the next pass clears it
+    if (!any_sat) break;
+  }
+  for (int j = lane; j < nd; j += G) St.sol_qdd[j * N + env] = W.qdd[j];
+  // ---- M~^-1 columns from unit-torque solves on the cached factorisation: one column per lane
+  for (int j = lane; j < nd; j += G) {
+    float* uu = W.col_uu[lane];
+    for (int i = 0; i < nd; i++) uu[i] = 0.f;
+    uu[j] = 1.f;
+    v6 carry = load6(W.U[j]) * W.Dinv[j];
+    int p = M.dof_parent[j];
+    while (p >= 0) {
+      uu[p] = -dot6(load6(W.S[p]), carry);
+      carry = carry + load6(W.U[p]) * (uu[p] * W.Dinv[p]);
+      p = M.dof_parent[p];
+    }
+    B2S_NO_UNROLL
+    for (int i = 0; i < nd; i++) {
+      float qd2 = 0.f;
+      if (M.dof_art[i] == M.dof_art[j]) {
+        const int pi = M.dof_parent[i];
+        const v6 ap = pi >= 0 ? load6(W.col_aa[lane][pi]) : zero6();
+        qd2 = (uu[i] - dot6(load6(W.U[i]), ap)) * W.Dinv[i];
+        store6(W.col_aa[lane][i], ap + load6(W.S[i]) * qd2);
+      }
+      St.kin_minv[(size_t)(i * nd + j) * N + env] = qd2;
+    }
+  }
+  // ---- free bodies: world centre of mass, inverse mass, world inverse inertia (zero for kinematic bodies)
+  for (int b = lane; b < M.n_fb; b += G) kin_free_body(M, St, env, b);
 }
 
 // ------------------------------------------------------------------------------------------------ collide

@@ -23,7 +23,12 @@ static void pipe_substep(World* w) {
   b2s::LamTot lamtot[MR];
   float stage[2 * 32];
   for (int e = 0; e < w->M.n_envs; e++) {
-    b2s::kin_env<C, ND>(w->M, w->S, e);
+    // forward kinematics + joint rows, then the dynamics in the group form the CUDA library runs (here a group of one lane)
+    b2s::kin_env<C, ND, 1>(w->M, w->S, e);
+    {
+      static b2s::KinDynScratch<C, 1> scratch;
+      b2s::kin_dyn_group<C, 1>(w->M, w->S, e, 0, 1u, scratch);
+    }
     for (int k = 0; k < w->M.n_pair; k++) b2s::collide_env(w->M, w->S, e, k);
     b2s::manifest_env<C>(w->M, w->S, e);
     for (int r = 0; r < w->S.sol_nrow[e]; r++) b2s::rowfill_env<C, ND, NUQ, 1>(w->M, w->S, e, r);

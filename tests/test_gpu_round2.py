@@ -335,3 +335,34 @@ def test_record_and_replay_on_the_device(tmp_path):
     meta, trajs = load_trajectories(str(tmp_path / "many" / "trajectory"))
     lens = sorted(t["actions"].shape[0] for t in trajs.values())
     assert lens == [2, 2, 4, 4, 6, 6, 6, 6, 6, 6], lens
+
+
+@pytest.mark.parametrize("task", ["PickCube-v1", "OpenCabinetDrawer-v1"])
+def test_group_dynamics_kernel_equals_the_lane_kernel(task, monkeypatch):
+    """The dynamics half of kin with eight lanes per sub-scene (kin_dyn_kernel: articulated inertias in shared memory, lane r owns row r of
+    the 6x6 sweeps, shuffle reductions inside the group, one M~^-1 column per lane; B2S_KIN_GROUP=1) against the one-lane kernel: same
+    arithmetic, different summation order in three reductions per joint."""
+    import torch
+    import maniskill_b200 as ms
+
+    def rollout(group):
+        monkeypatch.setenv("B2S_KIN_GROUP", "1" if group else "0")
+        torch.manual_seed(0)
+        env = ms.make(task, num_envs=64, obs_mode="state", device="cuda:0")
+        env.reset(seed=9)
+        gen = torch.Generator(device="cuda:0")
+        gen.manual_seed(2)
+        for _ in range(6):
+            env.step(2 * torch.rand((64, env.action_dim), device="cuda:0", generator=gen) - 1)
+        w = env.scene.world
+        torch.cuda.synchronize()
+        out = (w.qpos.clone(), w.qvel.clone(), w.body_view().clone(), int(w.overflow_flag.item()))
+        env.close()
+        return out
+
+    a, b = rollout(False), rollout(True)
+    assert a[3] == 0 and b[3] == 0
+    assert torch.isfinite(b[2]).all()
+    # 30 substeps of a contact-rich system amplify the last-bit differences of the reductions; the bar of the oracle parity tests is 1e-4
+    assert (a[0] - b[0]).abs().max() < 1e-4 and (a[2][..., :7] - b[2][..., :7]).abs().max() < 1e-4
+    assert (a[1] - b[1]).abs().max() < 2e-2 * max(1.0, float(a[1].abs().max()))
