@@ -234,16 +234,18 @@ class PhysxCollisionShapeConvexMesh(PhysxCollisionShape):
         return [PhysxCollisionShapeConvexMesh(filename=filename, scale=scale, material=material, vertices=part) for part in meshio.load_parts(filename)]
 
 
-class PhysxCollisionShapeTriangleMesh(PhysxCollisionShape):
-    """Non-convex triangle meshes (static scenery) collide through their convex hull here."""
-    kind = "convex_mesh"
+class PhysxCollisionShapeTriangleMesh(PhysxCollisionShapeConvexMesh):
+    """Non-convex triangle meshes (static scenery) collide through their convex hull here: fine for slabs and blocks, wrong for anything an
+    object is meant to sit INSIDE of (arenas, bowls) -- a warning says so once per file."""
+    _warned = set()
 
     def __init__(self, filename: str = None, scale=(1, 1, 1), material=None, vertices=None, triangles=None):
-        PhysxCollisionShapeConvexMesh.__init__(self, filename=filename, scale=scale, material=material, vertices=vertices)
-
-    get_vertices = PhysxCollisionShapeConvexMesh.get_vertices
-    get_triangles = PhysxCollisionShapeConvexMesh.get_triangles
-    get_scale = PhysxCollisionShapeConvexMesh.get_scale
+        super().__init__(filename=filename, scale=scale, material=material, vertices=vertices)
+        key = filename or "<vertices>"
+        if key not in PhysxCollisionShapeTriangleMesh._warned:
+            PhysxCollisionShapeTriangleMesh._warned.add(key)
+            import warnings
+            warnings.warn(f"non-convex collision mesh {key}: this backend collides its convex hull ({len(self.vertices)} vertices)")
 
 
 # ------------------------------------------------------------------------------------------------ components
