@@ -43,11 +43,17 @@ def reference():
         return info
 
     SE.parse_sim_and_render_backend = parse
+    # the emulated world IS the GPU simulation: the reference's controllers must take their GPU kinematics path (batched torch FK / Jacobian,
+    # mani_skill/agents/controllers/utils/kinematics.py:88-93 picks it from device.type == "cuda"), not pinocchio
+    import mani_skill.agents.controllers.utils.kinematics as K
+    setup_cpu = K.Kinematics._setup_cpu
+    K.Kinematics._setup_cpu = K.Kinematics._setup_gpu
     sync = torch.cuda.synchronize
     if not torch.cuda.is_available():   # sapien_env.py:624 synchronises the device after rendering; there is none on this box
         torch.cuda.synchronize = lambda *a, **k: None
     yield gym
     torch.cuda.synchronize = sync
+    K.Kinematics._setup_cpu = setup_cpu
     SE.parse_sim_and_render_backend = orig
     compat.WORLD_FACTORY = None
 
@@ -62,6 +68,40 @@ def test_the_shim_is_what_got_imported(reference):
         assert m.__file__.startswith(site), m.__file__
     import mani_skill
     assert mani_skill.__file__.startswith(REF)
+
+
+def _run_reference_test(module_file, fn_name, *args):
+    """Executes one test function of /root/reference/tests/<module_file> as it is (the module does `from tests.utils import ...`)."""
+    spec = importlib.util.spec_from_file_location("ref_" + module_file[:-3], os.path.join(REF, "tests", module_file))
+    ref_tests = importlib.util.spec_from_file_location("tests", os.path.join(REF, "tests", "__init__.py"), submodule_search_locations=[os.path.join(REF, "tests")])
+    saved = {k: v for k, v in sys.modules.items() if k == "tests" or k.startswith("tests.")}
+    try:
+        pkg = importlib.util.module_from_spec(ref_tests)
+        sys.modules["tests"] = pkg
+        ref_tests.loader.exec_module(pkg)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        getattr(mod, fn_name)(*args)
+    finally:
+        for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+@pytest.mark.parametrize("fn,args", [
+    ("test_env_control_modes", ("PickCube-v1", "pd_joint_delta_pos")), ("test_env_control_modes", ("PickCube-v1", "pd_joint_pos")),
+    ("test_env_control_modes", ("PickCube-v1", "pd_ee_delta_pose")), ("test_env_control_modes", ("PickCube-v1", "pd_ee_delta_pos")),
+    ("test_env_control_modes", ("StackCube-v1", "pd_ee_delta_pose")),
+    ("test_robots", ("PickCube-v1", "panda")), ("test_multi_agent", ("TwoRobotPickCube-v1",)), ("test_timelimits", ()), ("test_hidden_objs", ("PickCube-v1",)),
+    ("test_wrappers.py:test_multi_agent_flatten_action_space_gpu", ("TwoRobotStackCube-v1",)),
+], ids=lambda v: "-".join(v) if isinstance(v, tuple) else str(v))
+def test_reference_own_gpu_env_tests(reference, fn, args):
+    """/root/reference/tests/test_gpu_envs.py: control modes (the end-effector ones through the reference's GPU kinematics over the
+    pytorch_kinematics stand-in), robots, multi-agent, time limits, hidden objects; tests/test_wrappers.py: the flattened multi-agent action
+    space -- 16 sub-scenes each, executed as they are.
+    (`test_envs_obs_modes` asserts `device == cuda:0` and can only run where a GPU and the reference are on the same machine.)"""
+    module_file, _, fn = fn.rpartition(":")
+    _run_reference_test(module_file or "test_gpu_envs.py", fn, *args)
 
 
 def test_reference_own_test_partial_resets(reference):
