@@ -81,6 +81,8 @@ def _run_reference_test(module_file, fn_name, *args):
         ref_tests.loader.exec_module(pkg)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        torch.manual_seed(0)   # the tests reset without a seed: episode layouts then come from torch's global generator (test_timelimits needs
+        np.random.seed(0)      # "no sub-scene succeeds by chance within 50 idle steps", which one layout in a dozen violates)
         getattr(mod, fn_name)(*args)
     finally:
         for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
