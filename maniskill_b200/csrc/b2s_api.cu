@@ -813,12 +813,15 @@ int32_t b2s_pick_task_step_autoreset(uint64_t world, uint64_t handle, const floa
   return b2s_pick_task_autoreset(world, handle, out, ar, stream);
 }
 
-// dst[env] = src[env] (row_bytes each, 16-byte multiples) for the sub-scenes with mask[env] != 0: blocks of other sub-scenes exit at once
-__global__ void masked_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t row_vec, const uint8_t* __restrict__ mask) {
-  const int env = blockIdx.y;
-  if (!mask[env]) return;
-  const size_t base = (size_t)env * row_vec;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_vec; i += (size_t)gridDim.x * blockDim.x) dst[base + i] = src[base + i];
+// dst[env] = src[env] (row_bytes each, 16-byte multiples) for the sub-scenes with mask[env] != 0.  A fixed grid of CTAs strides over the
+// sub-scenes, so a step on which nothing finished costs one small launch instead of tens of thousands of blocks that exit at once.
+__global__ void __launch_bounds__(256) masked_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t row_vec, const uint8_t* __restrict__ mask,
+                                                          int n_envs) {
+  for (int env = blockIdx.x; env < n_envs; env += gridDim.x) {
+    if (!mask[env]) continue;
+    const size_t base = (size_t)env * row_vec;
+    for (size_t i = threadIdx.x; i < row_vec; i += blockDim.x) dst[base + i] = src[base + i];
+  }
 }
 
 int32_t b2s_masked_copy(uint64_t world, void* dst_dev, const void* src_dev, uint64_t row_bytes, const uint8_t* mask_dev, void* stream) {
@@ -826,8 +829,8 @@ int32_t b2s_masked_copy(uint64_t world, void* dst_dev, const void* src_dev, uint
   if (!w || !dst_dev || !src_dev || !mask_dev || row_bytes == 0 || row_bytes % 16 != 0) return fail(B2S_ERR_INVALID, "bad masked copy");
   DeviceGuard guard_(w->device);
   const size_t row_vec = row_bytes / 16;
-  const int bx = (int)((row_vec + 255) / 256 < 64 ? (row_vec + 255) / 256 : 64);
-  masked_copy_kernel<<<dim3(bx, w->M.n_envs), 256, 0, (cudaStream_t)stream>>>((uint4*)dst_dev, (const uint4*)src_dev, row_vec, mask_dev);
+  const int grid = w->M.n_envs < 148 * 8 ? w->M.n_envs : 148 * 8;
+  masked_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint4*)dst_dev, (const uint4*)src_dev, row_vec, mask_dev, w->M.n_envs);
   CK(cudaGetLastError());
   return B2S_OK;
 }

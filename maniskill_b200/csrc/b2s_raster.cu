@@ -93,6 +93,14 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
   if (outputs & B2S_OUT_RGB) g->T.rgb = dev_copy<uint8_t>(g, nullptr, N * pix * 3 + 4);
   if (outputs & B2S_OUT_DEPTH) g->T.depth = dev_copy<int16_t>(g, nullptr, N * pix + 2);
   if (outputs & B2S_OUT_SEG) g->T.seg = dev_copy<int16_t>(g, nullptr, N * pix + 2);
+  g->work = dev_copy<int>(g, nullptr, 2);
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long n_img = (long)N * n_cam;
+    g->n_ctas = (int)(n_img < 2L * sms ? n_img : 2L * sms);
+  }
   for (void* p : g->allocs)
     if (!p) { raster_destroy(g); return "rasteriser allocation failed"; }
   if (cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_pixels * 4) != cudaSuccess ||
@@ -111,7 +119,7 @@ const char* raster_create(const DevModel& M, const DevState& S, const B2SModel& 
 }
 
 const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, const uint8_t* env_mask, cudaStream_t st) {
-  int grid = M.n_envs * g->R.n_cam;
+  const int grid = g->n_ctas;
   // 512 threads = 16 warps per image: two images per SM (shared-memory bound) keep 32 warps in flight
   // bounding boxes above this many pixels leave the one-thread path for the warp path; neighbouring triangles of the list belong to the
   // same hull and have similar sizes, so the lanes of a warp stay balanced well beyond one warp's worth of pixels (measured)
@@ -119,8 +127,8 @@ const char* raster_run(const DevModel& M, const DevState& S, RasterGroup* g, con
   // faces of a box whose screen rectangle is larger than this are tested per pixel; part of the rasteriser's definition (the CPU
   // restatement uses the same constant; the override exists for tuning runs only)
   static int patch = getenv("B2S_RASTER_PATCH") ? atoi(getenv("B2S_RASTER_PATCH")) : B2S_PATCH_PIXELS;
-  if (g->T.mask & (B2S_OUT_COLOR | B2S_OUT_POSSEG)) raster_kernel<true><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch);
-  else raster_kernel<false><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch);
+  if (g->T.mask & (B2S_OUT_COLOR | B2S_OUT_POSSEG)) raster_kernel<true><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch, g->work);
+  else raster_kernel<false><<<grid, B2S_RASTER_THREADS, (size_t)g->max_pixels * 4, st>>>(g->R, S.body_data, g->T, env_mask, big, patch, g->work);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -73,6 +73,8 @@ struct RasterTargets {
 };
 
 struct RasterGroup {
+  int* work;      // [2] image ticket counter + finished-CTA counter (device)
+  int n_ctas;     // CTAs of a launch: two per SM (shared-memory bound), at most one per image
   RasterModel R;
   std::vector<void*> allocs;
   RasterTargets T;
@@ -276,12 +278,8 @@ __device__ __forceinline__ void raster_sample(unsigned* zkey, int W, int x, int 
 // their previous picture.
 // RAW: the shader pack's Color / PositionSegmentation targets are written (the hit position is needed); otherwise only the compact textures
 template <bool RAW>
-__global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
-                                                                    const uint8_t* __restrict__ env_mask, int big_tri_pixels, int patch_pixels) {
-  extern __shared__ unsigned zkey[];
-  __shared__ RasterShared sh;
-  const int env = blockIdx.x / R.n_cam, cam = blockIdx.x % R.n_cam;
-  if (env_mask && !env_mask[env]) return;
+__device__ __forceinline__ void raster_image(const RasterModel& R, const float* __restrict__ body_data, const RasterTargets& O, int env, int cam,
+                                             int big_tri_pixels, int patch_pixels, unsigned* zkey, RasterShared& sh) {
   if (threadIdx.x == 0) { sh.n_big = 0; sh.n_huge = 0; sh.n_patch = 0; sh.n_sphere = 0; }
   const int W = R.cam_w[cam], H = R.cam_h[cam];
   const float fx = R.cam_intr[6 * cam], fy = R.cam_intr[6 * cam + 1], cx = R.cam_intr[6 * cam + 2], cy = R.cam_intr[6 * cam + 3];
@@ -590,6 +588,33 @@ __global__ void __launch_bounds__(B2S_RASTER_THREADS) raster_kernel(RasterModel 
       }
     }
   }
+}
+
+
+// The images of a launch are handed out through a counter in global memory: `work[0]` = next image, `work[1]` = CTAs that have finished
+// (the last one rewinds both for the next launch).  A CTA keeps taking images until none is left; images of sub-scenes that are masked out
+// are skipped by the one thread that takes the ticket, so a masked re-render after a step on which nothing finished costs a handful of
+// atomics instead of thousands of CTA launches with 110 KB of shared memory each.
+template <bool RAW>
+__global__ void __launch_bounds__(B2S_RASTER_THREADS, 2) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
+                                                                    const uint8_t* __restrict__ env_mask, int big_tri_pixels, int patch_pixels, int* work) {
+  extern __shared__ unsigned zkey[];
+  __shared__ RasterShared sh;
+  __shared__ int s_img;
+  const int n_img = R.n_envs * R.n_cam;
+  for (;;) {
+    __syncthreads();  // the previous image's shared state is no longer read
+    if (threadIdx.x == 0) {
+      int img;
+      do { img = atomicAdd(&work[0], 1); } while (img < n_img && env_mask && !env_mask[img / R.n_cam]);
+      s_img = img;
+    }
+    __syncthreads();
+    const int img = s_img;
+    if (img >= n_img) break;
+    raster_image<RAW>(R, body_data, O, img / R.n_cam, img % R.n_cam, big_tri_pixels, patch_pixels, zkey, sh);
+  }
+  if (threadIdx.x == 0 && atomicAdd(&work[1], 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
 }
 
 #endif  // __CUDACC__ && B2S_RASTER_IMPL
