@@ -238,10 +238,12 @@ __global__ void __launch_bounds__(128) rowfill_kernel(b2s::DevModel M, b2s::DevS
 // the whole rows to be rewritten (mask has BUF_LINK and BUF_RIGID) and a full CTA; otherwise the lanes store directly.
 #define B2S_FETCH_EPB 32
 template <class C>
-__global__ void __launch_bounds__(B2S_FETCH_EPB) fetch_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask) {
+__global__ void __launch_bounds__(B2S_FETCH_EPB) fetch_kernel(b2s::DevModel M, b2s::DevState S, unsigned mask, const uint8_t* __restrict__ only) {
   pdl_enter();
   extern __shared__ __align__(128) float fetch_tile[];
   const int env0 = blockIdx.x * B2S_FETCH_EPB, env = env0 + threadIdx.x;
+  // `only` (nullable): CTAs none of whose sub-scenes is flagged leave their rows as they are (refresh after a partial reset)
+  if (only && !__syncthreads_or(env < M.n_envs && only[env])) return;
   const int per_env = M.n_rows * 13;
   const unsigned tile_bytes = (unsigned)(B2S_FETCH_EPB * per_env * sizeof(float));
   const bool staged = (mask & b2s::BUF_LINK) && (mask & b2s::BUF_RIGID) && env0 + B2S_FETCH_EPB <= M.n_envs && (tile_bytes % 16u) == 0;
@@ -480,8 +482,8 @@ int32_t b2s_world_create(const B2SModel* model, int32_t device, uint64_t* world)
     cudaFuncSetAttribute(fetch_kernel<b2s::CapsS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fetch_smem(w->M));
     cudaFuncSetAttribute(fetch_kernel<b2s::CapsL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fetch_smem(w->M));
   }
-  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu);
-  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu);
+  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu, nullptr);
+  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M)>>>(w->M, w->S, 0xFFFFFFFFu, nullptr);
   CK(cudaDeviceSynchronize());
   return B2S_OK;
 }
@@ -585,8 +587,8 @@ static int enqueue_step(World* w, int substeps, unsigned fetch_mask, cudaStream_
     }
     if (fetch_mask) {
       const dim3 fg((N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB), fb(B2S_FETCH_EPB);
-      if (w->caps == 0) { CK(launch_chain(pdl, fetch_kernel<b2s::CapsS>, fg, fb, fetch_smem(M), st, M, S, fetch_mask)); }
-      else { CK(launch_chain(pdl, fetch_kernel<b2s::CapsL>, fg, fb, fetch_smem(M), st, M, S, fetch_mask)); }
+      if (w->caps == 0) { CK(launch_chain(pdl, fetch_kernel<b2s::CapsS>, fg, fb, fetch_smem(M), st, M, S, fetch_mask, (const uint8_t*)nullptr)); }
+      else { CK(launch_chain(pdl, fetch_kernel<b2s::CapsL>, fg, fb, fetch_smem(M), st, M, S, fetch_mask, (const uint8_t*)nullptr)); }
     }
     CK(cudaGetLastError());
     return B2S_OK;
@@ -654,16 +656,19 @@ int32_t b2s_apply(uint64_t world, uint32_t mask, void* stream) {
   return B2S_OK;
 }
 
+static int32_t fetch_rows(World* w, uint32_t mask, const uint8_t* only, cudaStream_t st) {
+  const int N = w->M.n_envs;
+  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask, only);
+  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask, only);
+  CK(cudaGetLastError());
+  return B2S_OK;
+}
+
 int32_t b2s_fetch(uint64_t world, uint32_t mask, void* stream) {
   World* w = get(world);
   if (!w) return fail(B2S_ERR_INVALID, "unknown world");
   DeviceGuard guard_(w->device);
-  int N = w->M.n_envs;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (w->caps == 0) fetch_kernel<b2s::CapsS><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask);
-  else fetch_kernel<b2s::CapsL><<<(N + B2S_FETCH_EPB - 1) / B2S_FETCH_EPB, B2S_FETCH_EPB, fetch_smem(w->M), st>>>(w->M, w->S, mask);
-  CK(cudaGetLastError());
-  return B2S_OK;
+  return fetch_rows(w, mask, nullptr, (cudaStream_t)stream);
 }
 
 int32_t b2s_update_kinematics(uint64_t world, void* stream) {
@@ -797,9 +802,9 @@ int32_t b2s_pick_task_autoreset(uint64_t world, uint64_t handle, const B2SPickOu
   const int N = w->M.n_envs;
   pick_reset_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->flags, out->elapsed, ar->rand, ar->final_obs, ar->done,
                                                      ar->ignore_terminations, ar->max_episode_steps);
-  // exposed buffers of every sub-scene from the internal state (unchanged where no reset happened), then the observation rows of
-  // the reset sub-scenes
-  rc = b2s_fetch(world, 0xFFFFFFFFu, stream);
+  // exposed buffers of the reset sub-scenes from their new internal state (CTAs of 32 sub-scenes none of which was reset exit at once),
+  // then their observation rows
+  rc = fetch_rows(w, 0xFFFFFFFFu, ar->done, st);
   if (rc != B2S_OK) return rc;
   pick_epilogue_kernel<<<(N + 127) / 128, 128, 0, st>>>(w->M, w->S, T, out->obs, out->reward, out->flags, out->elapsed, ar->done);
   CK(cudaGetLastError());
