@@ -591,22 +591,33 @@ __device__ __forceinline__ void raster_image(const RasterModel& R, const float* 
 }
 
 
-// The images of a launch are handed out through a counter in global memory: `work[0]` = next image, `work[1]` = CTAs that have finished
-// (the last one rewinds both for the next launch).  A CTA keeps taking images until none is left; images of sub-scenes that are masked out
-// are skipped by the one thread that takes the ticket, so a masked re-render after a step on which nothing finished costs a handful of
-// atomics instead of thousands of CTA launches with 110 KB of shared memory each.
+// The images of a launch are handed out through a counter in global memory: `work[0]` = next ticket, `work[1]` = CTAs that have finished
+// (the last one rewinds both for the next launch).  A CTA keeps taking tickets until none is left; images of sub-scenes that are masked out
+// are skipped by the one thread that takes the ticket, so a masked re-render after a step on which nothing finished costs 128 atomics
+// instead of thousands of CTA launches with 110 KB of shared memory each.
 template <bool RAW>
 __global__ void __launch_bounds__(B2S_RASTER_THREADS, 2) raster_kernel(RasterModel R, const float* __restrict__ body_data, RasterTargets O,
                                                                     const uint8_t* __restrict__ env_mask, int big_tri_pixels, int patch_pixels, int* work) {
   extern __shared__ unsigned zkey[];
   __shared__ RasterShared sh;
-  __shared__ int s_img;
+  __shared__ int s_img, s_cur, s_end;
   const int n_img = R.n_envs * R.n_cam;
+  // a ticket is one image of a full render (best balance) and 32 consecutive images of a masked one (the taker scans their flags)
+  const int chunk = env_mask ? 32 : 1;
+  if (threadIdx.x == 0) { s_cur = 0; s_end = 0; }
   for (;;) {
     __syncthreads();  // the previous image's shared state is no longer read
     if (threadIdx.x == 0) {
-      int img;
-      do { img = atomicAdd(&work[0], 1); } while (img < n_img && env_mask && !env_mask[img / R.n_cam]);
+      int img = n_img;
+      for (;;) {
+        if (s_cur >= s_end) {
+          s_cur = atomicAdd(&work[0], chunk);
+          s_end = s_cur + chunk < n_img ? s_cur + chunk : n_img;
+          if (s_cur >= n_img) break;
+        }
+        const int c = s_cur++;
+        if (!env_mask || env_mask[c / R.n_cam]) { img = c; break; }
+      }
       s_img = img;
     }
     __syncthreads();
