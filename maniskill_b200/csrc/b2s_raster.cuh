@@ -6,20 +6,21 @@
 //     PositionSegmentation  [H, W, 4] int16  x, y, z in millimetres (OpenGL camera frame: x right, y up, z backward,
 //                                            so depth = -z) and the segmentation id (= per_scene_id, 0 = background)
 //
-// One CTA renders one (sub-scene, camera) image; the 32-bit depth/id buffer of the whole image lives in shared memory (24-bit
-// reversed-z key of 1/depth | 8-bit visual id; 64 KB for 128 x 128).  Everything that can hide something goes through that key:
-//   stage 0  per visual: camera-from-visual transform (body pose read once from rigid_body_data); boxes whose corners are all in
-//            front of the near plane are RASTERISED like the convex hulls (12 triangles), the others stay analytic
-//   stage 1  the vertices of all rasterised visuals are transformed and projected ONCE into a shared-memory cache
-//            (screen x, y, 1/depth: one division per vertex instead of three per triangle)
-//   stage 2  indexed triangles: back-face cull by the sign of the screen area, top-left-free ">= 0" edge rule on counter-clockwise
-//            triangles, 1/depth interpolated in screen space, shared-memory atomicMin on the key; small triangles by one thread,
-//            larger ones queued and rasterised by a warp, huge ones (close-ups) by the CTA
-//   stage 3  per pixel: the analytic visuals (half-spaces: no division -- 1/depth is linear in the ray; spheres and near-plane
-//            crossing boxes: ray tests inside their screen rectangle) produce keys of the same form, the smallest key wins,
-//            depth = 1 / (dequantised 1/depth): ONE division per covered pixel; flat normals from the geometry (box face from
-//            the hit point, plane, sphere) or from the depth neighbourhood (hulls); Lambert shading (ambient 0.3 + the two
-//            directional lights of mani_skill/envs/sapien_env.py:845-853); 4-byte and 8-byte stores, coalesced by row.
+// A CTA renders one (sub-scene, camera) image at a time (two CTAs per SM take images from a ticket counter); the 32-bit depth/id
+// buffer of the whole image lives in shared memory (23-bit reversed-z key of 1/depth | 3-bit box face | 6-bit visual index; 64 KB for
+// 128 x 128).  Everything that can hide something goes through that key:
+//   stage 0  per visual: camera-from-visual transform (body pose read once from rigid_body_data); the Lambert-shaded colour of the six
+//            faces of a box / of a half-space (ambient 0.3 + the two directional lights of mani_skill/envs/sapien_env.py:845-853)
+//   stage 1  the vertices of all rasterised visuals (hulls, boxes as 12 triangles) are projected ONCE into a shared-memory cache (screen
+//            x, y, 1/depth: one division per vertex instead of three per triangle); flat faces that are tested per pixel are picked:
+//            half-spaces, camera-facing faces of boxes that reach behind the near plane, camera-facing box faces with a large rectangle
+//   stage 2  indexed triangles: back-face cull by the sign of the screen area, ">= 0" edge rule on counter-clockwise triangles, 1/depth
+//            interpolated in screen space, shared-memory atomicMin on the key; small triangles by the thread that set them up,
+//            larger ones queued (their setups kept in shared memory) and rasterised by a warp, huge ones by the CTA
+//   stage 3  per pixel: the flat-face patches (1/depth of a ray-plane hit is linear in the ray: no division; inside test on the two
+//            in-plane axes) and spheres produce keys of the same form, the smallest key wins, depth = 1 / (dequantised 1/depth): ONE
+//            division per covered pixel; box / half-space pixels look their colour up by (visual, face), sphere pixels shade with
+//            (hit - centre) / r, hull pixels with a normal from the depth neighbourhood; 32-bit stores assembled per warp.
 // HBM traffic per image: the body rows in; out 12 B per pixel for the raw render targets, or only the textures the observation mode
 // delivers (rgb 3 B + depth 2 B [+ segmentation 2 B] per pixel, written as whole 32-bit words assembled per warp).  The arithmetic is restated operation by operation in
 // oracle/b2s_oracle_raster.cpp; this translation unit is compiled with -fmad=false so that both produce identical integers.
