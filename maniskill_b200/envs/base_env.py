@@ -147,8 +147,10 @@ class _GraphedEpilogue:
 
     def run(self, action):
         env = self.env
+        if action is None:   # `step(None)` (no new action): nothing to feed the captured action buffer with -- eager
+            return env._epilogue(None)
         if self.graph is None:
-            if self.runs < self.WARMUP or action is None:
+            if self.runs < self.WARMUP:
                 self.runs += 1
                 return env._epilogue(action)
             self.action = action.clone()
@@ -157,8 +159,7 @@ class _GraphedEpilogue:
             with torch.cuda.graph(graph):
                 self.out = env._epilogue(self.action)
             self.graph = graph
-        if action is not None:
-            self.action.copy_(action)
+        self.action.copy_(action)
         self.graph.replay()
         return _clone_tree(self.out)
 
