@@ -355,6 +355,30 @@ int32_t b2s_render_masked(uint64_t world, uint64_t group, const uint8_t* env_mas
 int32_t b2s_pick_task_step_autoreset(uint64_t world, uint64_t handle, const float* actions_dev, int32_t substeps, const B2SPickOutputs* out,
                                      const B2SPickAutoReset* ar, void* stream);
 
+/* ---- end-effector controllers: one damped least-squares IK step per sub-scene.
+ * Replaces the GPU branch of `Kinematics.compute_ik` (mani_skill/agents/controllers/utils/kinematics.py:197-260: pytorch_kinematics
+ * serial-chain Jacobian, then (J^T J + 1e-4 I) dq = J^T delta_pose) for the pd_ee_* control modes (agents/controllers/pd_ee_pose.py:101-133).
+ * The chain is the root link -> end link path of the robot: per element the joint origin in the parent link frame, the joint axis in
+ * the joint frame and its kind. */
+typedef struct B2SChainDesc {
+  int32_t n_elem;              /* joints along the chain, fixed ones included, root first */
+  const float* origin;         /* [n_elem*7] joint frame in the parent link frame: position xyz + quaternion wxyz */
+  const float* axis;           /* [n_elem*3] joint axis in the joint frame */
+  const int32_t* kind;         /* [n_elem] 0 fixed, 1 revolute, 2 prismatic */
+  const int32_t* qpos_column;  /* [n_elem] column of the joint in the qpos buffer (moving joints; ignored for fixed ones) */
+  const uint8_t* controlled;   /* [n_elem] 1 = the joint is solved for (the other moving joints are held; kinematics.py:170-187 qmask) */
+  float lambda;                /* damping: 1e-4 in the reference (kinematics.py:245) */
+  float alpha;                 /* step scale (solver_config["alpha"]) */
+} B2SChainDesc;
+
+int32_t b2s_ik_create(uint64_t world, const B2SChainDesc* chain, uint64_t* ik);
+/* delta_pose_dev [n_envs, 6]: translation + XYZ Euler rotation of the end link in the root frame; qpos_dev [n_envs, qpos_stride] the current
+ * joint positions; target_dev [n_envs, n_controlled] out: q + alpha dq of the controlled joints, chain order.
+ * dq = J^T (J J^T + lambda I)^-1 delta_pose -- the same vector as (J^T J + lambda I)^-1 J^T delta_pose, through the better conditioned
+ * 6 x 6 system (Cholesky). */
+int32_t b2s_ik_step(uint64_t world, uint64_t ik, const float* delta_pose_dev, const float* qpos_dev, int32_t qpos_stride, float* target_dev,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

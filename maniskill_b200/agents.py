@@ -193,7 +193,7 @@ class PDEEPosController(PDJointPosController):
                  solver_config: Optional[dict] = None):
         from .kinematics import Kinematics
         super().__init__(articulation, joint_names, None, None, use_delta=use_delta, use_target=use_target, normalize_action=normalize_action)
-        self.kinematics = Kinematics(robot, ee_link, articulation.dof_names, joint_names, self.device)
+        self.kinematics = Kinematics(robot, ee_link, articulation.dof_names, joint_names, self.device, articulation=articulation)
         self.ee_link = articulation.links_map[ee_link]
         self.root_link = articulation.root
         self.solver_config = dict(type="levenberg_marquardt", alpha=1.0) if solver_config is None else solver_config

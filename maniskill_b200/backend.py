@@ -73,6 +73,11 @@ class B2SPickReset(C.Structure):
                 ("obj_fb", C.c_int32), ("goal_fb", C.c_int32)]
 
 
+class B2SChainDesc(C.Structure):
+    _fields_ = [("n_elem", C.c_int32), ("origin", C.c_void_p), ("axis", C.c_void_p), ("kind", C.c_void_p), ("qpos_column", C.c_void_p),
+                ("controlled", C.c_void_p), ("lambda_", C.c_float), ("alpha", C.c_float)]
+
+
 class B2SPickAutoReset(C.Structure):
     _fields_ = [("rand", C.c_void_p), ("final_obs", C.c_void_p), ("done", C.c_void_p), ("ignore_terminations", C.c_int32),
                 ("max_episode_steps", C.c_int32)]
@@ -111,6 +116,8 @@ def load_library():
     lib.b2s_pick_task_step.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.b2s_pick_task_set_reset.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
     lib.b2s_pick_task_step_autoreset.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.b2s_ik_create.argtypes = [C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.b2s_ik_step.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -118,7 +125,7 @@ def load_library():
 EXPORTED_SYMBOLS = ["b2s_last_error", "b2s_version", "b2s_world_create", "b2s_world_destroy", "b2s_world_buffers", "b2s_step",
                     "b2s_apply", "b2s_fetch", "b2s_update_kinematics", "b2s_contact_query_create", "b2s_contact_query_run",
                     "b2s_camera_group_create", "b2s_camera_group_create_outputs", "b2s_render", "b2s_pick_task_create", "b2s_pick_task_step", "b2s_pick_task_set_reset",
-                    "b2s_pick_task_step_autoreset", "b2s_pick_task_autoreset", "b2s_masked_copy", "b2s_render_masked"]
+                    "b2s_pick_task_step_autoreset", "b2s_pick_task_autoreset", "b2s_masked_copy", "b2s_render_masked", "b2s_ik_create", "b2s_ik_step"]
 
 
 class _DevArray:
@@ -335,6 +342,25 @@ class World:
         a = C.c_void_p(actions.data_ptr()) if actions is not None else None
         _check(self.lib, self.lib.b2s_pick_task_step_autoreset(self.h, handle, a, int(substeps), C.byref(out), C.byref(ar), self._stream()))
         self.kernel_launches += (2 if actions is not None else 1) + self._step_launches(substeps, BUF_ALL) + 3
+
+    # ------------------------------------------------------------------ end-effector controllers
+    def create_ik(self, origin7, axis3, kind, qpos_column, controlled, lambd=1e-4, alpha=1.0):
+        """Serial chain root -> end link (include/b200sim.h B2SChainDesc) -> handle for `ik_step`."""
+        o = np.ascontiguousarray(origin7, dtype=np.float32).reshape(-1, 7)
+        a = np.ascontiguousarray(axis3, dtype=np.float32).reshape(-1, 3)
+        k = np.ascontiguousarray(kind, dtype=np.int32)
+        c = np.ascontiguousarray(qpos_column, dtype=np.int32)
+        m = np.ascontiguousarray(controlled, dtype=np.uint8)
+        d = B2SChainDesc(len(k), o.ctypes.data, a.ctypes.data, k.ctypes.data, c.ctypes.data, m.ctypes.data, float(lambd), float(alpha))
+        h = C.c_uint64(0)
+        _check(self.lib, self.lib.b2s_ik_create(self.h, C.byref(d), C.byref(h)))
+        return h.value
+
+    def ik_step(self, handle, delta_pose, qpos, qpos_stride, target):
+        """One damped least-squares step: target[env] = q + alpha J^T (J J^T + lambda I)^-1 delta_pose[env] for the controlled joints."""
+        _check(self.lib, self.lib.b2s_ik_step(self.h, C.c_uint64(handle), C.c_void_p(delta_pose.data_ptr()), C.c_void_p(qpos.data_ptr()), int(qpos_stride),
+                                              C.c_void_p(target.data_ptr()), self._stream()))
+        self.kernel_launches += 1
 
     # ------------------------------------------------------------------ rendering
     def create_camera_group(self, cameras, visuals, outputs: int = OUT_RAW):

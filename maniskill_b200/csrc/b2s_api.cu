@@ -44,6 +44,16 @@ struct Query {
   int* rows_dev;
 };
 
+#define B2S_IK_MAX_ELEM 32
+#define B2S_IK_MAX_CTRL 12
+struct IKChainDev {
+  int n_elem, n_ctrl;
+  float lambda, alpha;
+  float *origin, *axis;   // device
+  int *kind, *column;
+  unsigned char* controlled;
+};
+
 struct PickTaskDev {
   int n_action;
   int *dof_action, *dof_use_delta, *dof_normalize;
@@ -60,6 +70,7 @@ struct World : b2s::WorldT<DevMem> {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // captured control steps, keyed by (substeps, fetch_mask); `cap` is the stream they are captured on
   cudaStream_t cap = nullptr;
+  std::vector<IKChainDev> iks;
   bool pdl_refused = false;
   // dynamics half of kin: 0 = one lane per sub-scene (kin_kernel<.., 2>, default), 1 = eight lanes per sub-scene (kin_dyn_kernel).  The group
   // kernel alone is 1.5x (9 joints) to 2.6x (24 joints) faster, but next to collide + manifest it slows the control step
@@ -505,6 +516,7 @@ int32_t b2s_world_destroy(uint64_t world) {
   if (w->ev_fork) cudaEventDestroy(w->ev_fork);
   if (w->ev_join) cudaEventDestroy(w->ev_join);
   for (auto& q : w->queries) cudaFree(q.rows_dev);
+  for (auto& k : w->iks) { cudaFree(k.origin); cudaFree(k.axis); cudaFree(k.kind); cudaFree(k.column); cudaFree(k.controlled); }
   for (auto* g : w->groups) b2s::raster_destroy(g);
   w->release();
   delete w;
@@ -836,6 +848,119 @@ int32_t b2s_masked_copy(uint64_t world, void* dst_dev, const void* src_dev, uint
   const size_t row_vec = row_bytes / 16;
   const int grid = w->M.n_envs < 148 * 8 ? w->M.n_envs : 148 * 8;
   masked_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint4*)dst_dev, (const uint4*)src_dev, row_vec, mask_dev, w->M.n_envs);
+  CK(cudaGetLastError());
+  return B2S_OK;
+}
+
+
+}  // extern "C"
+
+// One damped least-squares IK step of a serial chain, one lane per sub-scene: forward kinematics down the chain (joint frames, axes and
+// anchor points in the root frame), geometric Jacobian columns of the controlled joints, M = J J^T + lambda I (6 x 6, SPD) by Cholesky,
+// dq = J^T M^-1 delta.
+__global__ void __launch_bounds__(128) ik_dls_kernel(int n_envs, IKChainDev K, const float* __restrict__ delta, const float* __restrict__ qpos, int stride,
+                                                     float* __restrict__ target) {
+  using namespace b2s;
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_envs) return;
+  v3 p = mk3(0, 0, 0);
+  m3 R;
+  for (int k = 0; k < 9; k++) R.m[k] = (k % 4 == 0) ? 1.f : 0.f;
+  v3 jp[B2S_IK_MAX_CTRL], ja[B2S_IK_MAX_CTRL];
+  float qc[B2S_IK_MAX_CTRL];
+  bool rev[B2S_IK_MAX_CTRL];
+  int nc = 0;
+  for (int e = 0; e < K.n_elem; e++) {
+    const float* o = K.origin + 7 * e;
+    p = p + mul(R, mk3(o[0], o[1], o[2]));
+    R = mul(R, qmat(mkq(o[3], o[4], o[5], o[6])));
+    const int kind = K.kind[e];
+    if (kind == 0) continue;
+    const v3 ax = mk3(K.axis[3 * e], K.axis[3 * e + 1], K.axis[3 * e + 2]);
+    const v3 aw = mul(R, ax);
+    const float q = qpos[(size_t)env * stride + K.column[e]];
+    if (K.controlled[e] && nc < B2S_IK_MAX_CTRL) { jp[nc] = p; ja[nc] = aw; qc[nc] = q; rev[nc] = kind == 1; nc++; }
+    if (kind == 1) R = mul(R, qmat(qaxis_angle(ax, q)));
+    else p = p + aw * q;
+  }
+  // Jacobian columns (linear rows first, then angular: the pytorch_kinematics convention)
+  float J[6][B2S_IK_MAX_CTRL];
+  for (int c = 0; c < nc; c++) {
+    const v3 lin = rev[c] ? cross(ja[c], p - jp[c]) : ja[c];
+    const v3 ang = rev[c] ? ja[c] : mk3(0, 0, 0);
+    J[0][c] = lin.x; J[1][c] = lin.y; J[2][c] = lin.z; J[3][c] = ang.x; J[4][c] = ang.y; J[5][c] = ang.z;
+  }
+  float M[6][6], y[6];
+  for (int i = 0; i < 6; i++) {
+    y[i] = delta[(size_t)env * 6 + i];
+    for (int j = 0; j <= i; j++) {
+      float s = i == j ? K.lambda : 0.f;
+      for (int c = 0; c < nc; c++) s += J[i][c] * J[j][c];
+      M[i][j] = s;
+    }
+  }
+  // Cholesky M = L L^T in place (lower triangle), then L z = delta, L^T y = z
+  for (int i = 0; i < 6; i++) {
+    for (int j = 0; j <= i; j++) {
+      float s = M[i][j];
+      for (int k = 0; k < j; k++) s -= M[i][k] * M[j][k];
+      M[i][j] = i == j ? sqrtf(fmaxf(s, 1e-20f)) : s / M[j][j];
+    }
+  }
+  for (int i = 0; i < 6; i++) {
+    float s = y[i];
+    for (int k = 0; k < i; k++) s -= M[i][k] * y[k];
+    y[i] = s / M[i][i];
+  }
+  for (int i = 5; i >= 0; i--) {
+    float s = y[i];
+    for (int k = i + 1; k < 6; k++) s -= M[k][i] * y[k];
+    y[i] = s / M[i][i];
+  }
+  for (int c = 0; c < nc; c++) {
+    float dq = 0.f;
+    for (int i = 0; i < 6; i++) dq += J[i][c] * y[i];
+    target[(size_t)env * K.n_ctrl + c] = qc[c] + K.alpha * dq;
+  }
+}
+
+extern "C" {
+
+int32_t b2s_ik_create(uint64_t world, const B2SChainDesc* chain, uint64_t* ik) {
+  World* w = get(world);
+  if (!w || !chain || !ik || chain->n_elem < 1 || chain->n_elem > B2S_IK_MAX_ELEM || !chain->origin || !chain->axis || !chain->kind || !chain->qpos_column ||
+      !chain->controlled)
+    return fail(B2S_ERR_INVALID, "bad IK chain (1..32 elements, all tables given)");
+  DeviceGuard guard_(w->device);
+  IKChainDev K;
+  K.n_elem = chain->n_elem;
+  K.n_ctrl = 0;
+  for (int e = 0; e < chain->n_elem; e++) {
+    if (chain->kind[e] < 0 || chain->kind[e] > 2) return fail(B2S_ERR_INVALID, "IK chain: joint kind must be 0, 1 or 2");
+    if (chain->kind[e] != 0 && chain->controlled[e]) K.n_ctrl++;
+  }
+  if (K.n_ctrl < 1 || K.n_ctrl > B2S_IK_MAX_CTRL) return fail(B2S_ERR_INVALID, "IK chain: 1..12 controlled joints");
+  K.lambda = chain->lambda;
+  K.alpha = chain->alpha;
+  const size_t n = chain->n_elem;
+  CK(cudaMalloc(&K.origin, n * 7 * sizeof(float))); CK(cudaMalloc(&K.axis, n * 3 * sizeof(float)));
+  CK(cudaMalloc(&K.kind, n * sizeof(int))); CK(cudaMalloc(&K.column, n * sizeof(int))); CK(cudaMalloc(&K.controlled, n));
+  CK(cudaMemcpy(K.origin, chain->origin, n * 7 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(K.axis, chain->axis, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(K.kind, chain->kind, n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(K.column, chain->qpos_column, n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(K.controlled, chain->controlled, n, cudaMemcpyHostToDevice));
+  w->iks.push_back(K);
+  *ik = w->iks.size();
+  return B2S_OK;
+}
+
+int32_t b2s_ik_step(uint64_t world, uint64_t ik, const float* delta_pose_dev, const float* qpos_dev, int32_t qpos_stride, float* target_dev, void* stream) {
+  World* w = get(world);
+  if (!w || ik < 1 || ik > w->iks.size() || !delta_pose_dev || !qpos_dev || !target_dev || qpos_stride < 1) return fail(B2S_ERR_INVALID, "bad IK step");
+  DeviceGuard guard_(w->device);
+  const int N = w->M.n_envs;
+  ik_dls_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, w->iks[ik - 1], delta_pose_dev, qpos_dev, qpos_stride, target_dev);
   CK(cudaGetLastError());
   return B2S_OK;
 }

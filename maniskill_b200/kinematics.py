@@ -7,6 +7,7 @@ Here the chain comes from the baked robot description (tools/bake_assets.py) and
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import torch
@@ -91,7 +92,7 @@ class Kinematics:
     """kinematics.py:25-275 restricted to the GPU branch: IK of `end_link` over the controlled joints `joint_names` (the other
     moving joints of the chain are held, kinematics.py:170-187 `qmask`)."""
 
-    def __init__(self, robot: dict, end_link: str, dof_names: Sequence[str], joint_names: Sequence[str], device):
+    def __init__(self, robot: dict, end_link: str, dof_names: Sequence[str], joint_names: Sequence[str], device, articulation=None):
         self.chain = SerialChain(robot, end_link, device)
         dof_names = list(dof_names)
         # chain joints as indices into the articulation's qpos; which of them are controlled
@@ -101,6 +102,23 @@ class Kinematics:
             raise ValueError(f"controlled joints {list(joint_names)} must be the chain joints {self.chain.joint_names} in chain order")
         self.qmask = torch.tensor([n in set(joint_names) for n in self.chain.joint_names], dtype=torch.bool, device=device)
         self.device = device
+        # on the CUDA world the Levenberg-Marquardt step is one kernel (include/b200sim.h b2s_ik_step); the torch code below stays the
+        # reference it is tested against (tests/test_gpu_round2.py) and serves worlds without the entry point (host emulation)
+        self._ik = None
+        world = getattr(getattr(articulation, "scene", None), "world", None)
+        if world is not None and hasattr(world, "create_ik") and os.environ.get("B2S_IK_KERNEL", "1") not in ("", "0"):
+            c = self.chain
+            moving = [k != 0 for k in c._kind]
+            names = iter(c.joint_names)
+            columns, controlled = [], []
+            for mv in moving:
+                n = next(names) if mv else None
+                columns.append(dof_names.index(n) if mv else 0)
+                controlled.append(1 if mv and n in set(joint_names) else 0)
+            origin7 = [list(p) + list(q) for p, q in zip(c._origin_p, c._origin_q)]
+            self._ik_world, self._ik_art = world, articulation
+            self._ik_args = (origin7, c._axis, c._kind, columns, controlled)
+            self._ik_handles = {}
 
     def fk(self, qpos: torch.Tensor):
         """End-link position and wxyz quaternion in the root frame."""
@@ -110,6 +128,9 @@ class Kinematics:
     def compute_ik(self, delta_pose: torch.Tensor, q0: torch.Tensor, solver_config: dict):
         """delta_pose [B,6] = (translation, XYZ Euler rotation) of the end link in the root frame; q0 [B, dof] full qpos.
         Returns the target positions of the controlled joints [B, n_ctrl] (kinematics.py:243-260)."""
+        kind = solver_config.get("type", "levenberg_marquardt")
+        if getattr(self, "_ik_args", None) is not None and kind == "levenberg_marquardt":
+            return self._compute_ik_kernel(delta_pose, float(solver_config.get("alpha", 1.0)))
         qc = q0[:, self.chain_dof_idx]
         _, _, J = self.chain.forward(qc)
         J = J[:, :, self.qmask]
@@ -124,3 +145,16 @@ class Kinematics:
         else:
             raise NotImplementedError(solver_config["type"])
         return qc[:, self.qmask] + solver_config.get("alpha", 1.0) * dq.squeeze(-1)
+
+    def _compute_ik_kernel(self, delta_pose: torch.Tensor, alpha: float):
+        """The same step through the C-ABI: reads the articulation's row of the world's qpos buffer in place."""
+        w, art = self._ik_world, self._ik_art
+        h = self._ik_handles.get(alpha)
+        if h is None:
+            h = self._ik_handles[alpha] = w.create_ik(*self._ik_args, lambd=1e-4, alpha=alpha)
+        n_ctrl = int(self.qmask.sum())
+        out = torch.empty((delta_pose.shape[0], n_ctrl), dtype=torch.float32, device=self.device)
+        n_art = max(w.n_art, 1)
+        qpos = w.qpos[art.art_index:]            # row env * n_art + art_index, as a pointer offset + a stride of n_art rows
+        w.ik_step(h, delta_pose.to(torch.float32).contiguous(), qpos, n_art * w.max_dof, out)
+        return out

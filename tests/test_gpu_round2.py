@@ -366,3 +366,42 @@ def test_group_dynamics_kernel_equals_the_lane_kernel(task, monkeypatch):
     # 30 substeps of a contact-rich system amplify the last-bit differences of the reductions; the bar of the oracle parity tests is 1e-4
     assert (a[0] - b[0]).abs().max() < 1e-4 and (a[2][..., :7] - b[2][..., :7]).abs().max() < 1e-4
     assert (a[1] - b[1]).abs().max() < 2e-2 * max(1.0, float(a[1].abs().max()))
+
+
+@pytest.mark.parametrize("task,mode", [("PickCube-v1", "pd_ee_delta_pose"), ("PickCube-v1", "pd_ee_delta_pos"), ("PegInsertionSide-v1", "pd_ee_delta_pose")])
+def test_ik_kernel_matches_the_torch_step(task, mode):
+    """b2s_ik_step (one damped least-squares step per sub-scene in one kernel: chain FK, Jacobian, 6 x 6 Cholesky) against the batched
+    torch restatement of the reference's GPU branch (mani_skill/agents/controllers/utils/kinematics.py:243-260: (J^T J + 1e-4 I) dq = J^T d).
+    fp32, damping 1e-4: tolerance 2e-4 rad on the joint targets for end-effector displacements of a few centimetres."""
+    import torch
+    import maniskill_b200 as ms
+    n = 96
+    env = ms.make(task, num_envs=n, obs_mode="state", control_mode=mode, device="cuda:0")
+    env.reset(seed=4)
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(8)
+    for _ in range(3):   # move away from the rest pose
+        env.step(2 * torch.rand((n, env.action_dim), device="cuda:0", generator=gen) - 1)
+    ctrl = env.agent.controller.controllers["arm"]
+    kin = ctrl.kinematics
+    assert kin._ik_args is not None, "the CUDA world must provide the IK entry point"
+    delta = (2 * torch.rand((n, 6), device="cuda:0", generator=gen) - 1) * torch.tensor([0.05, 0.05, 0.05, 0.2, 0.2, 0.2], device="cuda:0")
+    q0 = env.agent.robot.get_qpos()
+    cfg = dict(type="levenberg_marquardt", alpha=1.0)
+    got = kin.compute_ik(delta, q0, cfg)
+    args, kin._ik_args = kin._ik_args, None
+    try:
+        ref = kin.compute_ik(delta, q0, cfg)
+    finally:
+        kin._ik_args = args
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 2e-4, float((got - ref).abs().max())
+    # the step moves the end effector by the requested translation (first order): FK of the new targets
+    q1 = q0.clone()
+    cols = kin.chain_dof_idx[kin.qmask]
+    q1[:, cols] = got
+    p0, _ = kin.fk(q0)
+    p1, _ = kin.fk(q1)
+    assert ((p1 - p0) - delta[:, :3]).abs().max() < 0.02
+    env.close()
