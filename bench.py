@@ -244,9 +244,9 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)   # before anything queries device properties: a rank never initialises another rank's GPU
     pinned_cores, pinned_how = pin_rank_to_cores(local_rank, world_size)
     torch.set_num_threads(max(1, min(4, pinned_cores or 4)))
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
