@@ -311,3 +311,80 @@ def test_convex_mesh_rests_on_a_convex_mesh():
     assert imp_top[2] == pytest.approx(m_top * 9.81 * 0.01, rel=0.03)
     imp_ground = o.pair_impulse(base, -2)[0]     # net impulse on the base: ground pushes up with both weights, the top pushes down with its own
     assert imp_ground[2] == pytest.approx(m_base * 9.81 * 0.01, rel=0.05)
+
+
+def _rand_quat(rng):
+    q = rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def _qmat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def test_narrowphase_against_independent_geometry():
+    """The oracle's narrowphase against computations that share nothing with it (numpy / scipy): (1) a rotated box over the ground plane --
+    separations and points are the box corners below the margin; (2) a sphere near a rotated box -- closest point on the box in closed
+    form; (3) two separated convex hulls (GJK) -- the distance between the two point sets' hulls from a quadratic programme over convex
+    combinations (scipy SLSQP)."""
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(11)
+    plane = dict(type=SHAPE_PLANE, pose=[0, 0, 0, 0.7071068, 0, -0.7071068, 0])   # normal +z
+    for _ in range(20):
+        h = rng.uniform(0.02, 0.08, 3)
+        q = _rand_quat(rng)
+        R = _qmat(q)
+        corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * h
+        zmin = (corners @ R.T)[:, 2].min()
+        t = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), -zmin + rng.uniform(-0.004, 0.01)])
+        world = corners @ R.T + t
+        c = collide(dict(type=SHAPE_BOX, pose=list(t) + list(q), size=list(h)), plane, margin=0.02)
+        below = np.sort(world[world[:, 2] < 0.02][:, 2])
+        assert len(c) == min(len(below), 4) and len(c) >= 1
+        assert np.allclose(np.sort(c[:, 6])[0], below[0], atol=1e-9) and np.allclose(c[:, 3:6], [0, 0, 1], atol=1e-9)
+        for p, sep in zip(c[:, :3], c[:, 6]):     # every reported point sits midway between a corner and the plane, separation = the corner's height
+            d = np.linalg.norm(world - (p + np.array([0, 0, 0.5 * sep])), axis=1)
+            assert d.min() < 1e-9 and abs(world[d.argmin(), 2] - sep) < 1e-9
+    for _ in range(20):
+        h = rng.uniform(0.02, 0.08, 3)
+        q = _rand_quat(rng)
+        R = _qmat(q)
+        r = rng.uniform(0.01, 0.04)
+        local = rng.uniform(-1, 1, 3) * (h + r + 0.05)
+        if np.all(np.abs(local) <= h):
+            local[0] = h[0] + r + 0.005
+        closest = np.clip(local, -h, h)
+        dist = np.linalg.norm(local - closest)
+        centre = R @ local + np.array([0.3, -0.2, 0.5])
+        c = collide(dict(type=SHAPE_SPHERE, pose=list(centre) + [1, 0, 0, 0], size=[r, 0, 0]),
+                    dict(type=SHAPE_BOX, pose=[0.3, -0.2, 0.5] + list(q), size=list(h)), margin=0.02)
+        if dist - r < 0.02:
+            assert len(c) == 1 and c[0, 6] == pytest.approx(dist - r, abs=1e-9)
+            assert np.allclose(c[0, 3:6], R @ ((local - closest) / dist), atol=1e-7)     # normal from the box towards the sphere
+        else:
+            assert len(c) == 0
+    for _ in range(12):
+        A = rng.normal(size=(14, 3)) * 0.04
+        B = rng.normal(size=(11, 3)) * 0.04
+        ta = np.array([0.0, 0.0, 0.0])
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        # place B along d so that the hulls are separated by a gap inside the margin
+        gap = rng.uniform(0.002, 0.015)
+        tb = d * ((A @ d).max() - (B @ d).min() + gap)
+
+        def f(x):
+            la, mu = x[:len(A)], x[len(A):]
+            v = la @ A - (mu @ B + tb)
+            return v @ v
+        cons = [dict(type="eq", fun=lambda x: x[:len(A)].sum() - 1), dict(type="eq", fun=lambda x: x[len(A):].sum() - 1)]
+        x0 = np.concatenate([np.full(len(A), 1 / len(A)), np.full(len(B), 1 / len(B))])
+        res = minimize(f, x0, bounds=[(0, 1)] * len(x0), constraints=cons, method="SLSQP", options=dict(maxiter=500, ftol=1e-16))
+        dist = np.sqrt(res.fun)
+        assert dist >= gap - 1e-7     # the gap between the support planes along d is a lower bound
+        c = collide(dict(type=4, pose=list(ta) + [1, 0, 0, 0], size=[0, 0, 0], verts=A.astype(np.float32)),
+                    dict(type=4, pose=list(tb) + [1, 0, 0, 0], size=[0, 0, 0], verts=B.astype(np.float32)), margin=0.04)
+        if dist < 0.035:
+            assert len(c) >= 1 and c[:, 6].min() == pytest.approx(dist, abs=2e-5), (c[:, 6], dist)
