@@ -390,6 +390,44 @@ __device__ __forceinline__ void raster_image(const RasterModel& R, const float* 
         rx0 = max(0, (int)floorf(mnx) - 1); rx1 = min(W - 1, (int)ceilf(mxx) + 1);
         ry0 = max(0, (int)floorf(mny) - 1); ry1 = min(H - 1, (int)ceilf(mxy) + 1);
         if (rx0 > rx1 || ry0 > ry1 || (rx1 - rx0 + 1) * (ry1 - ry0 + 1) <= patch_pixels) continue;  // stays a pair of triangles
+      } else if (ty == SH_BOX) {
+        // the box reaches behind the near plane: its face is clipped against that plane first (a quadrilateral against one plane: at most
+        // five corners) and the screen rectangle of what is left prunes the per-pixel test.  Pruning only: the rectangle is widened by two
+        // pixels and the hit test decides, so the CPU restatement may (and does) test every pixel for these faces.
+        const int b = a == 2 ? 0 : a + 1, c = b == 2 ? 0 : b + 1;
+        const float* Rm = sh.vis_R[v];
+        float qx[4], qy[4], qz[4];
+        for (int k = 0; k < 4; k++) {
+          float l[3];
+          const int kb = (k == 1 || k == 2), kc = (k >= 2);  // corners in order around the face
+          l[a] = sgn * ha; l[b] = kb ? sh.vis_sz[v][b] : -sh.vis_sz[v][b]; l[c] = kc ? sh.vis_sz[v][c] : -sh.vis_sz[v][c];
+          qx[k] = Rm[0] * l[0] + Rm[1] * l[1] + Rm[2] * l[2] + sh.vis_t[v][0];
+          qy[k] = Rm[3] * l[0] + Rm[4] * l[1] + Rm[5] * l[2] + sh.vis_t[v][1];
+          qz[k] = Rm[6] * l[0] + Rm[7] * l[1] + Rm[8] * l[2] + sh.vis_t[v][2];
+        }
+        float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+        int kept = 0;
+        for (int k = 0; k < 4; k++) {
+          const int k1 = (k + 1) & 3;
+          const bool in0 = qx[k] > nearp, in1 = qx[k1] > nearp;
+          if (in0) {
+            const float u = cx - fx * qy[k] / qx[k], w = cy - fy * qz[k] / qx[k];
+            mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w); kept++;
+          }
+          if (in0 != in1) {  // the edge crosses the near plane
+            const float tt = (nearp - qx[k]) / (qx[k1] - qx[k]);
+            const float ey = qy[k] + tt * (qy[k1] - qy[k]), ez = qz[k] + tt * (qz[k1] - qz[k]);
+            const float u = cx - fx * ey / nearp, w = cy - fy * ez / nearp;
+            mnx = fminf(mnx, u); mxx = fmaxf(mxx, u); mny = fminf(mny, w); mxy = fmaxf(mxy, w); kept++;
+          }
+        }
+        if (kept == 0) continue;  // the whole face is behind the near plane
+        // points on the near plane project far outside the image: clamp before the float -> int conversion
+        mnx = fminf(fmaxf(mnx, -4.0f), (float)W + 4.0f); mxx = fminf(fmaxf(mxx, -4.0f), (float)W + 4.0f);
+        mny = fminf(fmaxf(mny, -4.0f), (float)H + 4.0f); mxy = fminf(fmaxf(mxy, -4.0f), (float)H + 4.0f);
+        rx0 = max(0, (int)floorf(mnx) - 2); rx1 = min(W - 1, (int)ceilf(mxx) + 2);
+        ry0 = max(0, (int)floorf(mny) - 2); ry1 = min(H - 1, (int)ceilf(mxy) + 2);
+        if (rx0 > rx1 || ry0 > ry1) continue;
       }
       const int slot = atomicAdd(&sh.n_patch, 1);
       if (slot >= B2S_MAX_PATCH) continue;
