@@ -145,8 +145,136 @@ def load_glb_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, Tuple[float,
     return out
 
 
+def load_dae_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, Tuple[float, float, float, float]]]:
+    """COLLADA 1.4 (`.dae`; the Fetch robot's visual meshes): `<triangles>` / `<polylist>` / `<polygons>` of every `<geometry>` instantiated by the
+    visual scene, node transforms (`<matrix>`, `<translate>`, `<rotate>`, `<scale>`) applied, `<unit meter>` and `<up_axis>` honoured (result is z-up,
+    metres); colour = the bound material's phong / lambert diffuse colour where it is a plain colour (textures: grey)."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    ns = root.tag[:root.tag.index("}") + 1] if root.tag.startswith("{") else ""
+    q = lambda tag: ns + tag
+    unit = root.find(f"{q('asset')}/{q('unit')}")
+    meter = float(unit.get("meter", 1.0)) if unit is not None else 1.0
+    up = (root.findtext(f"{q('asset')}/{q('up_axis')}") or "Y_UP").strip()
+    floats = lambda text: np.array(text.split(), dtype=np.float64)
+
+    effects = {}
+    for e in root.iter(q("effect")):
+        col = next((c for d in e.iter(q("diffuse")) for c in d.findall(q("color"))), None)
+        if col is not None:
+            effects[e.get("id")] = tuple(floats(col.text)[:4])
+    materials = {m.get("id"): effects.get(m.find(q("instance_effect")).get("url", "#")[1:]) for m in root.iter(q("material")) if m.find(q("instance_effect")) is not None}
+
+    geoms = {}
+    for g in root.iter(q("geometry")):
+        mesh = g.find(q("mesh"))
+        if mesh is None:
+            continue
+        sources = {}
+        for src in mesh.findall(q("source")):
+            fa = src.find(q("float_array"))
+            acc = src.find(f"{q('technique_common')}/{q('accessor')}")
+            if fa is not None and fa.text:
+                stride = int(acc.get("stride", 3)) if acc is not None else 3
+                sources[src.get("id")] = floats(fa.text).reshape(-1, stride)
+        vert_src = {}
+        for vs in mesh.findall(q("vertices")):
+            for inp in vs.findall(q("input")):
+                if inp.get("semantic") == "POSITION":
+                    vert_src[vs.get("id")] = inp.get("source")[1:]
+        prims = []
+        for kind in ("triangles", "polylist", "polygons"):
+            for prim in mesh.findall(q(kind)):
+                inputs = prim.findall(q("input"))
+                n_off = max(int(i.get("offset", 0)) for i in inputs) + 1
+                vin = next((i for i in inputs if i.get("semantic") == "VERTEX"), None)
+                if vin is None:
+                    continue
+                pos = sources.get(vert_src.get(vin.get("source")[1:], ""))
+                if pos is None:
+                    continue
+                off = int(vin.get("offset", 0))
+                tris = []
+                if kind == "polygons":
+                    polys = [np.array(pe.text.split(), dtype=np.int64).reshape(-1, n_off)[:, off] for pe in prim.findall(q("p")) if pe.text]
+                else:
+                    pe = prim.find(q("p"))
+                    if pe is None or not pe.text:
+                        continue
+                    idx = np.array(pe.text.split(), dtype=np.int64).reshape(-1, n_off)[:, off]
+                    if kind == "triangles":
+                        polys = list(idx.reshape(-1, 3))
+                    else:
+                        vc = np.array(prim.find(q("vcount")).text.split(), dtype=np.int64)
+                        ends = np.cumsum(vc)
+                        polys = [idx[e - c:e] for c, e in zip(vc, ends)]
+                for poly in polys:
+                    for k in range(1, len(poly) - 1):   # fan
+                        tris.append((poly[0], poly[k], poly[k + 1]))
+                if tris:
+                    prims.append((pos[:, :3], np.array(tris, dtype=np.int64), prim.get("material")))
+        geoms[g.get("id")] = prims
+
+    out = []
+
+    def emit(gid, M, bind):
+        for pos, tris, mat in geoms.get(gid, []):
+            used, inv = np.unique(tris.reshape(-1), return_inverse=True)
+            v = pos[used] @ M[:3, :3].T + M[:3, 3]
+            v = v * meter
+            if up == "Y_UP":
+                v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], axis=1)
+            elif up == "X_UP":
+                v = np.stack([-v[:, 1], v[:, 0], v[:, 2]], axis=1)
+            col = materials.get(bind.get(mat, mat)) or (0.8, 0.8, 0.8, 1.0)
+            col = tuple(float(c) for c in (list(col) + [1.0])[:4])
+            out.append((v.astype(np.float32), inv.reshape(-1, 3).astype(np.int32), col))
+
+    def node_matrix(n):
+        M = np.eye(4)
+        for ch in n:
+            tag = ch.tag[len(ns):]
+            if tag == "matrix":
+                M = M @ floats(ch.text).reshape(4, 4)
+            elif tag == "translate":
+                T = np.eye(4)
+                T[:3, 3] = floats(ch.text)[:3]
+                M = M @ T
+            elif tag == "scale":
+                M = M @ np.diag(list(floats(ch.text)[:3]) + [1.0])
+            elif tag == "rotate":
+                x, y, z, deg = floats(ch.text)[:4]
+                a = np.array([x, y, z])
+                nrm = np.linalg.norm(a)
+                if nrm > 0:
+                    a = a / nrm
+                    t = np.deg2rad(deg)
+                    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+                    R = np.eye(4)
+                    R[:3, :3] = np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * (K @ K)
+                    M = M @ R
+        return M
+
+    def visit(n, parent):
+        M = parent @ node_matrix(n)
+        for ig in n.findall(q("instance_geometry")):
+            bind = {im.get("symbol"): im.get("target", "#")[1:] for im in ig.iter(q("instance_material"))}
+            emit(ig.get("url", "#")[1:], M, bind)
+        for c in n.findall(q("node")):
+            visit(c, M)
+
+    scenes = list(root.iter(q("visual_scene")))
+    for vs in scenes:
+        for n in vs.findall(q("node")):
+            visit(n, np.eye(4))
+    if not out:   # no scene graph: every geometry as stored
+        for gid in geoms:
+            emit(gid, np.eye(4), {})
+    return out
+
+
 def load_mesh_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, tuple]]:
-    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb` (vertex coordinates as stored, node transforms applied)."""
+    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb`, `.dae` (vertex coordinates as stored, node transforms applied)."""
     ext = os.path.splitext(path)[1].lower()
     if not os.path.exists(path):
         raise RuntimeError(f"mesh file {path} does not exist")
@@ -157,7 +285,9 @@ def load_mesh_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, tuple]]:
         return [(v, f, (0.8, 0.8, 0.8, 1.0)) for v, f in load_obj_parts(path)]
     if ext in (".glb",):
         return load_glb_parts(path)
-    raise RuntimeError(f"unsupported mesh format '{ext}' ({path}): stl, obj and glb are read")
+    if ext == ".dae":
+        return load_dae_parts(path)
+    raise RuntimeError(f"unsupported mesh format '{ext}' ({path}): stl, obj, glb and dae are read")
 
 
 def load_points(path: str) -> np.ndarray:

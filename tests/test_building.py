@@ -214,3 +214,36 @@ def test_articulation_builder_errors():
         ab.build(name="x")                             # duplicate name
     with pytest.raises(RuntimeError):
         child.build()
+
+
+def test_collada_reader(tmp_path):
+    """meshio.load_dae_parts (the Fetch robot's visual meshes are COLLADA): <triangles> and <polylist> primitives, node transforms, <unit>, Y_UP -> z-up,
+    the bound material's diffuse colour."""
+    from maniskill_b200.meshio import load_mesh_parts
+    dae = """<?xml version="1.0"?>
+<COLLADA xmlns="http://www.collada.org/2005/11/COLLADASchema" version="1.4.1">
+ <asset><unit name="centimeter" meter="0.01"/><up_axis>Y_UP</up_axis></asset>
+ <library_effects><effect id="fx"><profile_COMMON><technique sid="c"><phong><diffuse><color>0.2 0.4 0.6 1</color></diffuse></phong></technique></profile_COMMON></effect></library_effects>
+ <library_materials><material id="mat"><instance_effect url="#fx"/></material></library_materials>
+ <library_geometries><geometry id="g"><mesh>
+  <source id="pos"><float_array id="pa" count="12">0 0 0  100 0 0  100 100 0  0 100 0</float_array>
+   <technique_common><accessor source="#pa" count="4" stride="3"/></technique_common></source>
+  <source id="nrm"><float_array id="na" count="3">0 0 1</float_array><technique_common><accessor source="#na" count="1" stride="3"/></technique_common></source>
+  <vertices id="v"><input semantic="POSITION" source="#pos"/></vertices>
+  <polylist material="m0" count="1"><input semantic="VERTEX" source="#v" offset="0"/><input semantic="NORMAL" source="#nrm" offset="1"/>
+   <vcount>4</vcount><p>0 0 1 0 2 0 3 0</p></polylist>
+  <triangles material="m0" count="1"><input semantic="VERTEX" source="#v" offset="0"/><p>0 1 2</p></triangles>
+ </mesh></geometry></library_geometries>
+ <library_visual_scenes><visual_scene id="s"><node id="n"><translate>0 0 50</translate>
+  <instance_geometry url="#g"><bind_material><technique_common><instance_material symbol="m0" target="#mat"/></technique_common></bind_material></instance_geometry>
+ </node></visual_scene></library_visual_scenes>
+</COLLADA>"""
+    path = tmp_path / "quad.dae"
+    path.write_text(dae)
+    parts = load_mesh_parts(str(path))
+    assert len(parts) == 2
+    (v2, f2, _), (v, f, col) = sorted(parts, key=lambda p: len(p[1]))
+    assert f.shape == (2, 3) and f2.shape == (1, 3) and v.shape == (4, 3) and v2.shape == (3, 3)
+    np.testing.assert_allclose(col, (0.2, 0.4, 0.6, 1.0))
+    # centimetres, translated by 50 along the file's z, then (x, y, z)_yup -> (x, -z, y)_zup
+    np.testing.assert_allclose(sorted(map(tuple, v.tolist())), sorted([(0, -0.5, 0), (1, -0.5, 0), (1, -0.5, 1), (0, -0.5, 1)]), atol=1e-6)
