@@ -26,6 +26,28 @@ class Trimesh:
         box.vertices = box.vertices + (b[0] + b[1]) / 2
         return box
 
+    @property
+    def centroid(self):
+        return self.vertices.mean(0) if len(self.vertices) else np.zeros(3)
+
+    @property
+    def volume(self):
+        if not len(self.faces):
+            return 0.0
+        a, b, c = (self.vertices[self.faces[:, k]] for k in range(3))
+        return float(np.einsum("ij,ij->i", a, np.cross(b, c)).sum() / 6.0)
+
+    @property
+    def center_mass(self):
+        """Volume centroid of a closed mesh (signed tetrahedra against the origin); the centre of the bounds for an open / empty one."""
+        if len(self.faces):
+            a, b, c = (self.vertices[self.faces[:, k]] for k in range(3))
+            vol = np.einsum("ij,ij->i", a, np.cross(b, c)) / 6.0
+            if abs(vol.sum()) > 1e-12:
+                return ((a + b + c) / 4.0 * vol[:, None]).sum(0) / vol.sum()
+        b = self.bounds
+        return np.zeros(3) if b is None else (b[0] + b[1]) / 2
+
     def apply_transform(self, T):
         T = np.asarray(T, dtype=np.float64)
         self.vertices = self.vertices @ T[:3, :3].T + T[:3, 3]

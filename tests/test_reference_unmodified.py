@@ -31,6 +31,15 @@ def reference():
     compat.WORLD_FACTORY = lambda cm, dev: EmuBackendWorld(cm)
     if REF not in sys.path:
         sys.path.insert(0, REF)
+    if "MS_ASSET_DIR" not in os.environ:
+        # OpenCabinetDrawer-v1 reads PartNet-Mobility cabinets from $MS_ASSET_DIR/data (a download that is not available): stand-in URDFs of the same kind
+        # (tools/make_standin_partnet.py); the variable is read when mani_skill is imported
+        import tempfile
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+        import make_standin_partnet
+        assets = tempfile.mkdtemp(prefix="b200sim_ms_assets_")
+        make_standin_partnet.main(os.path.join(REF, "mani_skill", "assets", "partnet_mobility", "meta"), assets)
+        os.environ["MS_ASSET_DIR"] = assets
     import gymnasium as gym
     import mani_skill.envs  # noqa: F401  (registers every task: all task modules, scene builders and robots import)
     import mani_skill.envs.sapien_env as SE
@@ -107,7 +116,7 @@ def test_reference_own_gpu_env_tests(reference, fn, args):
 
 
 @pytest.mark.parametrize("fn,args", [
-    ("test_sim_state.py:test_raw_heterogeneous_actor_sim_states", ()),
+    ("test_sim_state.py:test_raw_heterogeneous_actor_sim_states", ()), ("test_sim_state.py:test_raw_heterogeneous_articulations_sim_states", ()),
     ("test_gpu_envs.py:test_env_control_modes", ("PegInsertionSide-v1", "pd_joint_pos")), ("test_gpu_envs.py:test_robots", ("StackCube-v1", "panda")),
     ("structs/test_actor.py:test_actor_pose_gpu", ()), ("structs/test_link.py:test_link_pose_gpu", ()),
     ("structs/test_pose.py:test_pose_creation", ()), ("structs/test_pose.py:test_pose_create_with_p", ()), ("structs/test_pose.py:test_pose_create_with_q", ()),
@@ -116,7 +125,8 @@ def test_reference_own_gpu_env_tests(reference, fn, args):
 ], ids=lambda v: "-".join(v) if isinstance(v, tuple) else str(v))
 def test_reference_own_tests_second_batch(reference, fn, args):
     """More of /root/reference/tests executed as they are: the state get / set round trip of PegInsertionSide-v1 (sub-scenes with different peg and
-    hole geometry, state width 13 * 3 + 13 + 9 * 2; tests/test_sim_state.py:40-71), further task x control-mode / robot cases of
+    hole geometry, state width 13 * 3 + 13 + 9 * 2; tests/test_sim_state.py:40-71) and of OpenCabinetDrawer-v1 (Fetch + one cabinet per sub-scene merged into one
+    view, state width 13 + 13 + 2 * max_dof + 13 + 15 * 2; :73-103; stand-in cabinet assets, see the fixture), further task x control-mode / robot cases of
     tests/test_gpu_envs.py, and tests/structs/ (Actor / Link pose setters on the GPU buffers, the Pose struct over sapien.Pose)."""
     module_file, _, fn = fn.rpartition(":")
     _run_reference_test(module_file, fn, *args)
@@ -291,7 +301,7 @@ def test_reference_obs_modes(reference, obs_mode):
 REFERENCE_TASKS = ["PushCube-v1", "StackCube-v1", "PullCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1",
                    "PullCubeTool-v1", "PlugCharger-v1", "PegInsertionSide-v1", "PushT-v1", "TwoRobotPickCube-v1", "Empty-v1", "RotateValveLevel0-v1",
                    "RotateSingleObjectInHandLevel0-v1", "PickCubeSO100-v1", "SO100GraspCube-v1", "MS-CartpoleBalance-v1", "MS-CartpoleSwingUp-v1",
-                   "MS-HopperHop-v1", "TwoRobotStackCube-v1"]
+                   "MS-HopperHop-v1", "TwoRobotStackCube-v1", "OpenCabinetDrawer-v1"]
 
 
 @pytest.mark.parametrize("task", REFERENCE_TASKS)
@@ -307,4 +317,34 @@ def test_reference_task_builds_and_steps(reference, task):
         obs, r, te, tr, info = env.step(a)
     assert isinstance(obs, torch.Tensor) and obs.shape[0] == 2 and torch.isfinite(obs).all() and torch.isfinite(r).all()
     assert int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
+    env.close()
+
+
+def test_reference_open_cabinet_drawer(reference):
+    """BASELINE.json configs[3]'s task through the reference's own module (mani_skill/envs/tasks/mobile_manipulation/open_cabinet_drawer.py), unchanged: the Fetch
+    URDF (COLLADA visuals) through the reference's loader subclass, one PartNet-style cabinet per sub-scene (`set_scene_idxs([i])`, different model ids) merged
+    with `Articulation.merge` / `Link.merge`, the handle position from the visual named `handle_*` (`Link.generate_mesh` + trimesh `center_mass`), the per-step
+    `gpu_update_articulation_kinematics` / goal-site update.  The cabinets are stand-ins of the absent dataset (tools/make_standin_partnet.py).  Checked: shapes,
+    closed drawers after reset, the goal site sits on the target handle, `open_enough` flips when the target drawer is pulled out."""
+    gym = reference
+    n = 4
+    env = gym.make("OpenCabinetDrawer-v1", num_envs=n, obs_mode="state", sim_backend="physx_cuda")
+    obs, _ = env.reset(seed=0)
+    e = env.unwrapped
+    assert obs.shape == (n, 44) and e.agent.robot.max_dof == 15 and e.cabinet.max_dof == 2 and len({c.name for c in e._cabinets}) == n
+    assert e.get_state().shape == (n, 13 + 13 + 2 * 2 + 13 + 15 * 2)
+    ql = e.cabinet.get_qlimits()
+    assert torch.allclose(e.cabinet.qpos, ql[..., 0], atol=2e-3)
+    assert float((e.handle_link_goal.pose.p - e.handle_link_positions()).abs().max()) < 1e-5
+    assert float((e.handle_link_positions()[:, 0] - (-0.28)).abs().max()) < 5e-3          # the handle bar in front of the closed drawer (-D/2 - 0.03)
+    for _ in range(2):
+        obs, r, te, tr, info = env.step(torch.as_tensor(env.action_space.sample()))
+    assert torch.isfinite(obs).all() and torch.isfinite(r).all() and not info["open_enough"].any()
+    e.cabinet.set_qpos(ql[..., 1])
+    e.scene._gpu_apply_all()
+    e.scene.px.gpu_update_articulation_kinematics()
+    e.scene._gpu_fetch_all()
+    ev = e.evaluate()
+    assert ev["open_enough"].all() and float((ev["handle_link_pos"][:, 0] - (-0.28 - 0.35)).abs().max()) < 5e-3
+    assert int(e.scene.px._world.overflow_flag.item()) == 0
     env.close()
