@@ -233,6 +233,7 @@ class RenderShapeTriangleMeshPart:
 class RenderShapeTriangleMesh(RenderShape):
     """A triangle mesh from a file (every primitive becomes a part with its own base colour) or from arrays."""
     kind = "mesh"
+    _scaled: dict = {}
 
     def __init__(self, filename: str = None, scale=(1, 1, 1), material=None, vertices=None, triangles=None, normals=None, uvs=None):
         super().__init__(material)
@@ -240,9 +241,19 @@ class RenderShapeTriangleMesh(RenderShape):
         self.scale = np.asarray(scale, dtype=np.float32).reshape(3)
         if filename is not None:
             from maniskill_b200 import meshio
-            for v, f, color in meshio.load_mesh_parts(filename):
+            # every sub-scene attaches the same files: the scaled vertex arrays are shared (read-only) instead of copied N times
+            key = (filename, tuple(float(x) for x in self.scale))
+            scaled = RenderShapeTriangleMesh._scaled.get(key)
+            if scaled is None:
+                scaled = []
+                for v, f, color in meshio.load_mesh_parts(filename):
+                    sv = np.asarray(v, dtype=np.float64) * self.scale.astype(np.float64)
+                    sv.setflags(write=False)
+                    scaled.append((sv, f, color))
+                RenderShapeTriangleMesh._scaled[key] = scaled
+            for sv, f, color in scaled:
                 mat = material if material is not None else RenderMaterial(base_color=color)
-                self.parts.append(RenderShapeTriangleMeshPart(np.asarray(v, dtype=np.float64) * self.scale.astype(np.float64), f, mat))
+                self.parts.append(RenderShapeTriangleMeshPart(sv, f, mat))
         else:
             self.parts.append(RenderShapeTriangleMeshPart(np.asarray(vertices, dtype=np.float64) * self.scale.astype(np.float64), np.asarray(triangles), self.material))
 

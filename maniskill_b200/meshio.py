@@ -273,11 +273,27 @@ def load_dae_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, Tuple[float,
     return out
 
 
+_MESH_CACHE: dict = {}
+_HULL_CACHE: dict = {}
+
+
 def load_mesh_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, tuple]]:
-    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb`, `.dae` (vertex coordinates as stored, node transforms applied)."""
-    ext = os.path.splitext(path)[1].lower()
+    """-> [(vertices [n,3], triangles [m,3], base colour)] for `.stl`, `.obj`, `.glb`, `.dae` (vertex coordinates as stored, node transforms applied).
+    Cached per (file, mtime): the reference builds every sub-scene from the same files (N x the Panda's 20 meshes); the arrays are read-only."""
     if not os.path.exists(path):
         raise RuntimeError(f"mesh file {path} does not exist")
+    key = (os.path.abspath(path), os.path.getmtime(path))
+    if key not in _MESH_CACHE:
+        parts = _load_mesh_parts(path)
+        for v, f, _ in parts:
+            v.setflags(write=False)
+            f.setflags(write=False)
+        _MESH_CACHE[key] = parts
+    return list(_MESH_CACHE[key])
+
+
+def _load_mesh_parts(path: str) -> List[Tuple[np.ndarray, np.ndarray, tuple]]:
+    ext = os.path.splitext(path)[1].lower()
     if ext == ".stl":
         v, f = load_stl(path)
         return [(v, f, (0.8, 0.8, 0.8, 1.0))]
@@ -306,6 +322,19 @@ def load_parts(path: str) -> List[np.ndarray]:
 def cook_hull(points, max_verts: int = MAX_HULL_VERTS):
     """Convex hull with at most `max_verts` vertices (support points of a Fibonacci direction set, the most extreme ones kept) ->
     (vertices [n,3] float64, triangles [[i,j,k]] wound outwards)."""
+    import hashlib
+    from scipy.spatial import ConvexHull
+    raw = np.ascontiguousarray(points, dtype=np.float64)
+    key = (raw.shape, hashlib.blake2b(raw.tobytes(), digest_size=16).digest(), int(max_verts))
+    hit = _HULL_CACHE.get(key)     # the same mesh is cooked once per sub-scene by the reference's builders (4096 x 9 Panda hulls)
+    if hit is not None:
+        return hit[0].copy(), [list(t) for t in hit[1]]
+    v, tris = _cook_hull(raw, max_verts)
+    _HULL_CACHE[key] = (v, tris)
+    return v.copy(), [list(t) for t in tris]
+
+
+def _cook_hull(points, max_verts):
     from scipy.spatial import ConvexHull
     pts = np.unique(np.round(np.asarray(points, dtype=np.float64), 7), axis=0)
     hull = ConvexHull(pts)

@@ -1,0 +1,233 @@
+"""B200: the UNMODIFIED reference package (`mani_skill`, pip-installed into baseline/_ref by tools/install_reference.py -- /root/reference does not exist on the
+GPU box) on the `sapien` shim with the CUDA world behind it: VERDICT r1 item 4 "and the same on B200 by shipping only the shim".  Nothing of the reference is
+patched here: `gym.make(..., num_envs=N)` picks `physx_cuda`, its tensors live on cuda:0, every `px.gpu_*` call and `cuda_*` buffer is the C-ABI library's.
+
+The CPU box runs the same file against the emulated world with `B2S_REFPKG_EMU=1` (dry run of the test code itself; not part of the default CPU suite)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "baseline", "_ref")
+EMU = os.environ.get("B2S_REFPKG_EMU") == "1"
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(os.path.join(PKG, "mani_skill", "__init__.py")),
+                                                  reason="baseline/_ref is not installed (python tools/install_reference.py where /root/reference exists)")]
+DEV = torch.device("cpu") if EMU else torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gym():
+    import maniskill_b200.compat as compat
+    compat.install()
+    if "MS_ASSET_DIR" not in os.environ:
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_standin_partnet
+        assets = tempfile.mkdtemp(prefix="b200sim_ms_assets_")
+        make_standin_partnet.main(os.path.join(PKG, "mani_skill", "assets", "partnet_mobility", "meta"), assets)
+        os.environ["MS_ASSET_DIR"] = assets
+    if "mani_skill" not in sys.modules and PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    undo = []
+    if EMU:
+        from emu_world import EmuBackendWorld
+        compat.WORLD_FACTORY = lambda cm, dev: EmuBackendWorld(cm)
+        import mani_skill.envs.sapien_env as SE
+        import mani_skill.envs.utils.system.backend as B
+        orig = B.parse_sim_and_render_backend
+
+        def parse(sim_backend, render_backend):
+            info = orig(sim_backend, render_backend)
+            info.device = torch.device("cpu")
+            return info
+        SE.parse_sim_and_render_backend = parse
+        sync = torch.cuda.synchronize
+        torch.cuda.synchronize = lambda *a, **k: None
+        undo = [lambda: setattr(SE, "parse_sim_and_render_backend", orig), lambda: setattr(torch.cuda, "synchronize", sync), lambda: setattr(compat, "WORLD_FACTORY", None)]
+    import gymnasium
+    import mani_skill
+    import mani_skill.envs  # noqa: F401
+    import sapien
+    site = os.path.join(ROOT, "maniskill_b200", "compat", "site")
+    assert sapien.__file__.startswith(site) and gymnasium.__file__.startswith(site)
+    assert "reference" in mani_skill.__file__ or mani_skill.__file__.startswith(PKG), mani_skill.__file__
+    yield gymnasium
+    for u in undo:
+        u()
+
+
+def _tree(x, fn):
+    if isinstance(x, dict):
+        for v in x.values():
+            _tree(v, fn)
+    else:
+        fn(x)
+
+
+def _on_device(x):
+    assert isinstance(x, torch.Tensor) and x.device == DEV, (type(x), getattr(x, "device", None))
+
+
+@pytest.mark.parametrize("obs_mode", ["state", "state_dict", "rgb+depth+segmentation", "pointcloud", "depth+state"])
+def test_pick_cube_observation_modes(gym, obs_mode):
+    """what the reference's tests/test_gpu_envs.py::test_envs_obs_modes asks of an environment: tensors on cuda:0, texture shapes and dtypes, sensor parameters"""
+    from mani_skill.vector.wrappers.gymnasium import ManiSkillVectorEnv
+    n = 16
+    env = ManiSkillVectorEnv(gym.make("PickCube-v1", num_envs=n, obs_mode=obs_mode), auto_reset=True, ignore_terminations=False)
+    base = env.base_env
+    if not EMU:
+        from maniskill_b200.backend import World
+        assert isinstance(base.scene.px._world, World) and base.gpu_sim_enabled and base.device == DEV
+    obs, _ = env.reset(seed=0)
+    _tree(obs, _on_device)
+    for _ in range(3):
+        obs, rew, term, trunc, info = env.step(env.action_space.sample())
+        for t in (rew, term, trunc):
+            _on_device(t)
+        _tree(obs, _on_device)
+        _tree(info, _on_device)
+    if obs_mode == "state":
+        assert obs.shape == (n, 42) and torch.isfinite(obs).all()
+    elif obs_mode == "state_dict":
+        assert obs["agent"]["qpos"].shape == (n, 9) and obs["extra"]["tcp_pose"].shape == (n, 7)
+    elif obs_mode == "pointcloud":
+        pc = obs["pointcloud"]
+        assert pc["xyzw"].shape == (n, 128 * 128, 4) and pc["rgb"].shape == (n, 128 * 128, 3) and pc["segmentation"].dtype == torch.int16
+    else:
+        sd, sp = obs["sensor_data"]["base_camera"], obs["sensor_param"]["base_camera"]
+        assert sd["depth"].shape == (n, 128, 128, 1) and sd["depth"].dtype == torch.int16 and int(sd["depth"].max()) > 0
+        assert sp["extrinsic_cv"].shape == (n, 3, 4) and sp["intrinsic_cv"].shape == (n, 3, 3) and sp["cam2world_gl"].shape == (n, 4, 4)
+        if "rgb" in obs_mode:
+            assert sd["rgb"].shape == (n, 128, 128, 3) and sd["rgb"].dtype == torch.uint8
+            seg = sd["segmentation"]
+            assert seg.shape == (n, 128, 128, 1) and seg.dtype == torch.int16
+            names = {base.segmentation_id_map[i].name for i in torch.unique(seg).tolist() if i in base.segmentation_id_map}
+            assert "cube" in names and "table-workspace" in names and any(k.startswith("panda_link") for k in names), names
+        else:
+            assert obs["state"].shape[0] == n
+    assert int(base.scene.px._world.overflow_flag.item()) == 0
+    env.close()
+
+
+def test_rollout_equals_the_mirror_task(gym):
+    """25 control steps of the reference's PickCube-v1 and of this repo's mirror of it (the path bench.py times), same seed and actions, both on the same world type"""
+    import maniskill_b200 as ms
+    n = 8
+    ref = gym.make("PickCube-v1", num_envs=n, obs_mode="state")
+    kw = dict(world_factory=__import__("emu_world").EmuBackendWorld) if EMU else dict(device="cuda:0")
+    mir = ms.make("PickCube-v1", num_envs=n, obs_mode="state", **kw)
+    ref.reset(seed=5)
+    mir.reset(seed=5)
+    sd = ref.unwrapped.get_state_dict()     # same start: the reference's state dictionary into the mirror (also true of the seeds where both draw on one device)
+    mir.set_state_dict({k: {kk: vv.clone() for kk, vv in v.items()} for k, v in sd.items()})
+    o1, o2 = ref.unwrapped.get_obs(), mir.get_obs()
+    assert o1.shape == (n, 42) and float((o1 - o2).abs().max()) < 1e-5
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for i in range(25):
+        a = 2 * torch.rand((n, 8), device=DEV, generator=g) - 1
+        o1, r1, _, _, i1 = ref.step(a)
+        o2, r2, _, _, i2 = mir.step(a)
+        assert float((o1 - o2).abs().max()) < 1e-4 and float((r1 - r2).abs().max()) < 1e-4, i
+        assert torch.equal(i1["is_grasped"], i2["is_grasped"])
+    ref.close()
+    mir.close()
+
+
+def test_reference_env_against_the_cpu_oracle(gym):
+    """the reference's env on the CUDA world against the CPU oracle started from the same buffers and fed the drive targets the reference's controller wrote:
+    q and body positions within 1e-4 after 20 control steps = 100 substeps (north_star's tolerance), through the reference's own step()"""
+    from oracle.oracle import OracleWorld
+    n = 16
+    env = gym.make("PickCube-v1", num_envs=n, obs_mode="state")
+    env.reset(seed=7)
+    px = env.unwrapped.scene.px
+    w, cm = px._world, px._compiled.cm
+    o = OracleWorld(cm, "f32")
+    o.set_joint("qpos", w.qpos.double().cpu().numpy())
+    o.set_joint("qvel", w.qvel.double().cpu().numpy())
+    o.set_joint("target_qpos", w.target_qpos.double().cpu().numpy())
+    o.set_bodies(w.body_view().double().cpu().numpy()[:, cm.scalars["n_link"]:])
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for _ in range(20):
+        env.step(2 * torch.rand((n, 8), device=DEV, generator=g) - 1)
+        o.set_joint("target_qpos", w.target_qpos.double().cpu().numpy())
+        o.step(5)
+    err_q = np.abs(w.qpos.double().cpu().numpy() - o.get_joint("qpos")).max()
+    err_p = np.abs(w.body_view().double().cpu().numpy()[..., :3] - o.rigid_body_data()[..., :3]).max()
+    assert err_q < 1e-4 and err_p < 1e-4, (err_q, err_p)
+    env.close()
+
+
+def test_partial_reset_and_state_round_trip(gym):
+    n = 16
+    env = gym.make("PickCube-v1", num_envs=n, obs_mode="state")
+    e = env.unwrapped
+    env.reset(seed=1)
+    for _ in range(3):
+        env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
+    before = e.get_state().clone()
+    assert before.shape == (n, 70)
+    idx = torch.tensor([0, 3, 15], device=DEV)
+    env.reset(options=dict(env_idx=idx))
+    after = e.get_state()
+    keep = torch.ones(n, dtype=torch.bool, device=DEV)
+    keep[idx] = False
+    assert torch.allclose(after[keep], before[keep], atol=1e-6) and not torch.allclose(after[~keep], before[~keep], atol=1e-3)
+    assert (e.elapsed_steps[idx] == 0).all() and (e.elapsed_steps[keep] == 3).all()
+    obs0 = e.get_obs()
+    for _ in range(3):
+        env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
+    e.set_state(after)
+    assert float((e.get_obs() - obs0).abs().max()) < 1e-4
+    env.close()
+
+
+def test_peg_insertion_side_rgbd_and_open_cabinet_drawer(gym):
+    """the other two tasks BASELINE.json names, through the reference's own modules: per-sub-scene peg / hole geometry with two cameras; Fetch + one (stand-in)
+    PartNet cabinet per sub-scene merged into one articulation view"""
+    n = 8
+    env = gym.make("PegInsertionSide-v1", num_envs=n, obs_mode="rgbd")
+    obs, _ = env.reset(seed=0)
+    for _ in range(2):
+        obs, r, _, _, info = env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
+    for cam in ("base_camera", "hand_camera"):
+        sd = obs["sensor_data"][cam]
+        assert sd["rgb"].shape == (n, 128, 128, 3) and sd["depth"].shape == (n, 128, 128, 1) and sd["rgb"].device == DEV and int(sd["depth"].max()) > 0
+    assert torch.isfinite(r).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
+    env.close()
+    env = gym.make("OpenCabinetDrawer-v1", num_envs=n, obs_mode="state")
+    obs, _ = env.reset(seed=0)
+    e = env.unwrapped
+    assert obs.shape == (n, 44) and e.cabinet.max_dof == 2 and e.get_state().shape == (n, 13 + 13 + 2 * 2 + 13 + 15 * 2)
+    for _ in range(2):
+        obs, r, _, _, info = env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
+    assert torch.isfinite(obs).all() and torch.isfinite(r).all() and not info["open_enough"].any()
+    assert float((e.handle_link_goal.pose.p - e.handle_link_positions()).abs().max()) < 1e-4
+    assert int(e.scene.px._world.overflow_flag.item()) == 0
+    env.close()
+
+
+def test_reference_benchmark_protocol_throughput(gym):
+    """mani_skill/examples/benchmarking/gpu_sim.py:91-108 on the reference's own env object: reset(seed=2022), a warm-up step, reset, then random actions in
+    [-1, 1] with a device synchronisation either side; prints env-steps/s of the UNMODIFIED reference python on this backend (python-bound: ~100 torch launches
+    per step come from the reference's own obs / reward code -- bench.py times the fused mirror path).  No threshold beyond 'it runs and stays finite'."""
+    import time
+    n, steps = (64, 5) if EMU else (4096, 100)
+    env = gym.make("PickCube-v1", num_envs=n, obs_mode="state")
+    env.reset(seed=2022)
+    env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
+    env.reset(seed=2022)
+    if not EMU:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        obs, rew, term, trunc, info = env.step(2 * torch.rand(env.action_space.shape, device=DEV) - 1)
+    if not EMU:
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
+    print(f"\nREFERENCE_PYTHON_ON_SHIM PickCube-v1 state num_envs={n}: {n * steps / dt:.0f} env-steps/s ({1e3 * dt / steps:.2f} ms/step)")
+    env.close()
