@@ -6,7 +6,7 @@ tests/test_zzz_gpu_reference_package.py and bench.py's `reference_python_on_shim
 
 (`/root/reference` is read-only and the build writes an egg-info next to setup.py: installed from a copy under /tmp; `--no-deps` because sapien, gymnasium, ... are
 not installable here -- the shim provides them.)  After the install the asset directories of robots / environment maps no test uses are deleted to keep the
-snapshot small (about 110 MB instead of 228 MB); every python file is byte-identical to the reference's.
+snapshot small (about 70 MB instead of 228 MB); every python file is byte-identical to the reference's.
 """
 import os
 import shutil
@@ -39,6 +39,17 @@ def install(reference="/root/reference", force=False) -> str:
         p = os.path.join(robots, d)
         if os.path.isdir(p) and d not in KEEP_ROBOTS and sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(p) for f in fs) > 2 << 20:
             shutil.rmtree(p)
+    # single large data files nothing in the tests reads (python files are never touched)
+    keep = ("robots/panda/franka_description", "robots/panda/realsense2_description/meshes/d415.stl", "robots/fetch", "utils/scene_builder/table",
+            "robots/so100", "partnet_mobility")
+    pkg = os.path.join(TARGET, "mani_skill")
+    for sub in ("assets", os.path.join("utils", "scene_builder")):
+        for r, _, fs in os.walk(os.path.join(pkg, sub)):
+            for f in fs:
+                path = os.path.join(r, f)
+                rel = os.path.relpath(path, pkg).replace(os.sep, "/")
+                if not f.endswith(".py") and os.path.getsize(path) > (1 << 20) and not any(k in rel for k in keep):
+                    os.remove(path)
     return TARGET
 
 
