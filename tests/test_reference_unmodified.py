@@ -117,7 +117,9 @@ def test_reference_own_gpu_env_tests(reference, fn, args):
 
 @pytest.mark.parametrize("fn,args", [
     ("test_sim_state.py:test_raw_heterogeneous_actor_sim_states", ()), ("test_sim_state.py:test_raw_heterogeneous_articulations_sim_states", ()),
-    ("test_gpu_envs.py:test_env_control_modes", ("PegInsertionSide-v1", "pd_joint_pos")), ("test_gpu_envs.py:test_robots", ("StackCube-v1", "panda")),
+    ("test_gpu_envs.py:test_env_control_modes", ("PegInsertionSide-v1", "pd_joint_pos")), ("test_gpu_envs.py:test_env_control_modes", ("PegInsertionSide-v1", "pd_ee_delta_pose")),
+    ("test_gpu_envs.py:test_env_control_modes", ("StackCube-v1", "pd_joint_delta_pos")), ("test_gpu_envs.py:test_env_control_modes", ("StackCube-v1", "pd_ee_delta_pos")),
+    ("test_gpu_envs.py:test_robots", ("StackCube-v1", "panda")), ("test_gpu_envs.py:test_multi_agent", ("TwoRobotStackCube-v1",)),
     ("structs/test_actor.py:test_actor_pose_gpu", ()), ("structs/test_link.py:test_link_pose_gpu", ()),
     ("structs/test_pose.py:test_pose_creation", ()), ("structs/test_pose.py:test_pose_create_with_p", ()), ("structs/test_pose.py:test_pose_create_with_q", ()),
     ("structs/test_pose.py:test_pose_to_sapien_pose", ()), ("structs/test_pose.py:test_pose_mult", ()), ("structs/test_pose.py:test_pose_inv", ()),
@@ -126,14 +128,15 @@ def test_reference_own_gpu_env_tests(reference, fn, args):
 def test_reference_own_tests_second_batch(reference, fn, args):
     """More of /root/reference/tests executed as they are: the state get / set round trip of PegInsertionSide-v1 (sub-scenes with different peg and
     hole geometry, state width 13 * 3 + 13 + 9 * 2; tests/test_sim_state.py:40-71) and of OpenCabinetDrawer-v1 (Fetch + one cabinet per sub-scene merged into one
-    view, state width 13 + 13 + 2 * max_dof + 13 + 15 * 2; :73-103; stand-in cabinet assets, see the fixture), further task x control-mode / robot cases of
+    view, state width 13 + 13 + 2 * max_dof + 13 + 15 * 2; :73-103; stand-in cabinet assets, see the fixture), further task x control-mode / robot / multi-agent cases of
     tests/test_gpu_envs.py, and tests/structs/ (Actor / Link pose setters on the GPU buffers, the Pose struct over sapien.Pose)."""
     module_file, _, fn = fn.rpartition(":")
     _run_reference_test(module_file, fn, *args)
 
 
 @pytest.mark.parametrize("env_id,obs_mode", [("PickCube-v1", m) for m in ("state_dict", "state", "rgb", "rgb+depth+segmentation", "pointcloud", "depth+state", "state+rgb+segmentation")]
-                         + [("PegInsertionSide-v1", "rgb+depth+segmentation")])
+                         + [("StackCube-v1", m) for m in ("state_dict", "rgb+depth+segmentation", "pointcloud")]
+                         + [("PegInsertionSide-v1", m) for m in ("state", "rgb", "rgb+depth+segmentation", "pointcloud", "depth+state", "state+rgb+segmentation")])
 def test_reference_own_test_envs_obs_modes(reference, env_id, obs_mode):
     """/root/reference/tests/test_gpu_envs.py:44-121 (`test_envs_obs_modes`: tensor types, camera texture shapes / dtypes, sensor parameters and point clouds
     of every observation mode).  Its helper asserts `x.device == torch.device("cuda:0")`; this box has no GPU, so the ONE literal "cuda:0" of the function's
