@@ -220,7 +220,12 @@ class URDFLoader:
             ab = self.scene.create_articulation_builder()
             mimics = []
 
+            seen = set()
+
             def visit(lname, joint_el, parent_builder):
+                if lname in seen or lname not in links:
+                    raise RuntimeError(f"URDF {urdf_file}: link '{lname}' " + ("is its own ancestor (joint cycle)" if lname in seen else "is referenced by a joint but not defined"))
+                seen.add(lname)
                 lb = ab.create_link_builder(parent_builder)
                 self._fill_link(lb, links[lname], urdf_dir)
                 if joint_el is None:

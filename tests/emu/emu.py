@@ -48,7 +48,8 @@ class EmuWorld:
         self.cm = cm
         self._struct = cm.struct()
         self.h = lib().emu_create(C.addressof(self._struct))
-        assert self.h
+        if not self.h:   # the CUDA library reports the same condition through b2s_last_error(); without a handle nothing may be destroyed
+            raise RuntimeError("emu_create failed: the model exceeds the capacities the emulation is compiled for (see stderr)")
         s = cm.scalars
         N, na, md = s["n_envs"], s["n_art"], max(s["max_dof_per_art"], 1)
         self.n_envs, self.n_rows, self.n_link = N, cm.n_rows, s["n_link"]
@@ -94,6 +95,7 @@ class EmuWorld:
 
     def __del__(self):
         try:
-            lib().emu_destroy(self.h)
+            if getattr(self, "h", None):
+                lib().emu_destroy(self.h)
         except Exception:
             pass

@@ -299,12 +299,14 @@ def test_reference_obs_modes(reference, obs_mode):
 # every task of the reference whose assets ship inside the repository and whose scene this backend can express (fixed-base articulations,
 # primitive / convex shapes): tabletop family, two-robot tasks, the dexterous-hand and valve tasks, other arms (SO100), an MJCF-built
 # control task.  Not in the list: tasks that download assets (YCB, PartNet-Mobility, ReplicaCAD, Anymal / Unitree robots), free-floating
-# articulation roots, the drawing tasks (hundreds of kinematic dots per sub-scene exceed the compiled capacities), non-convex arenas
-# (TriFinger: its bowl would collide as its hull).
+# articulation roots, the drawing tasks (hundreds of kinematic dots per sub-scene exceed the compiled capacities).  A scan of all 74 registered ids
+# (num_envs=2, reset + one step) loads 36: the ones below, the further levels of RotateValve / TriFingerRotateCube (TriFinger's arena collides as its convex
+# hull, with a warning) -- 24 need downloads, 6 have free-floating roots, 5 exceed capacities, 3 need packages that are not installed.
 REFERENCE_TASKS = ["PushCube-v1", "StackCube-v1", "PullCube-v1", "LiftPegUpright-v1", "PokeCube-v1", "RollBall-v1", "PlaceSphere-v1", "StackPyramid-v1",
                    "PullCubeTool-v1", "PlugCharger-v1", "PegInsertionSide-v1", "PushT-v1", "TwoRobotPickCube-v1", "Empty-v1", "RotateValveLevel0-v1",
                    "RotateSingleObjectInHandLevel0-v1", "PickCubeSO100-v1", "SO100GraspCube-v1", "MS-CartpoleBalance-v1", "MS-CartpoleSwingUp-v1",
-                   "MS-HopperHop-v1", "TwoRobotStackCube-v1", "OpenCabinetDrawer-v1"]
+                   "MS-HopperHop-v1", "TwoRobotStackCube-v1", "OpenCabinetDrawer-v1", "OpenCabinetDoor-v1", "MS-HopperStand-v1", "RotateValveLevel1-v1",
+                   "RotateSingleObjectInHandLevel1-v1", "TriFingerRotateCubeLevel0-v1", "TriFingerRotateCubeLevel4-v1"]
 
 
 @pytest.mark.parametrize("task", REFERENCE_TASKS)
@@ -334,8 +336,8 @@ def test_reference_open_cabinet_drawer(reference):
     env = gym.make("OpenCabinetDrawer-v1", num_envs=n, obs_mode="state", sim_backend="physx_cuda")
     obs, _ = env.reset(seed=0)
     e = env.unwrapped
-    assert obs.shape == (n, 44) and e.agent.robot.max_dof == 15 and e.cabinet.max_dof == 2 and len({c.name for c in e._cabinets}) == n
-    assert e.get_state().shape == (n, 13 + 13 + 2 * 2 + 13 + 15 * 2)
+    assert obs.shape == (n, 44) and e.agent.robot.max_dof == 15 and e.cabinet.max_dof == 3 and len({c.name for c in e._cabinets}) == n
+    assert e.get_state().shape == (n, 13 + 13 + 2 * 3 + 13 + 15 * 2) and set(e.handle_link.joint.type) == {"prismatic"}
     ql = e.cabinet.get_qlimits()
     assert torch.allclose(e.cabinet.qpos, ql[..., 0], atol=2e-3)
     assert float((e.handle_link_goal.pose.p - e.handle_link_positions()).abs().max()) < 1e-5
@@ -350,4 +352,24 @@ def test_reference_open_cabinet_drawer(reference):
     ev = e.evaluate()
     assert ev["open_enough"].all() and float((ev["handle_link_pos"][:, 0] - (-0.28 - 0.35)).abs().max()) < 5e-3
     assert int(e.scene.px._world.overflow_flag.item()) == 0
+    env.close()
+
+
+def test_reference_open_cabinet_door(reference):
+    """OpenCabinetDoor-v1: the same module's subclass that targets revolute handles (every stand-in cabinet carries one door above its two drawers)."""
+    gym = reference
+    n = 4
+    env = gym.make("OpenCabinetDoor-v1", num_envs=n, obs_mode="state", sim_backend="physx_cuda")
+    env.reset(seed=0)
+    e = env.unwrapped
+    assert set(e.handle_link.joint.type) == {"revolute"}
+    closed = e.handle_link_positions().clone()
+    e.cabinet.set_qpos(e.cabinet.get_qlimits()[..., 1])
+    e.scene._gpu_apply_all()
+    e.scene.px.gpu_update_articulation_kinematics()
+    e.scene._gpu_fetch_all()
+    ev = e.evaluate()
+    # the handle sits 0.69 m from the hinge: a quarter turn about the vertical hinge moves it out (-x) and across (+y), the height stays
+    assert ev["open_enough"].all() and float((ev["handle_link_pos"][:, 2] - closed[:, 2]).abs().max()) < 1e-4
+    assert float((ev["handle_link_pos"][:, 0] - closed[:, 0]).max()) < -0.5 and float((ev["handle_link_pos"][:, 1] - closed[:, 1]).min()) > 0.5
     env.close()

@@ -238,7 +238,7 @@ def test_peg_insertion_side_rgbd_and_open_cabinet_drawer(gym):
     env = gym.make("OpenCabinetDrawer-v1", num_envs=n, obs_mode="state")
     obs, _ = env.reset(seed=0)
     e = env.unwrapped
-    assert obs.shape == (n, 44) and e.cabinet.max_dof == 2 and e.get_state().shape == (n, 13 + 13 + 2 * 2 + 13 + 15 * 2)
+    assert obs.shape == (n, 44) and e.cabinet.max_dof == 3 and e.get_state().shape == (n, 13 + 13 + 2 * 3 + 13 + 15 * 2)
     for _ in range(2):
         obs, r, _, _, info = env.step(torch.as_tensor(env.action_space.sample(), device=DEV))
     assert torch.isfinite(obs).all() and torch.isfinite(r).all() and not info["open_enough"].any()
