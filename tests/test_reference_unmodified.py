@@ -373,3 +373,12 @@ def test_reference_open_cabinet_door(reference):
     assert ev["open_enough"].all() and float((ev["handle_link_pos"][:, 2] - closed[:, 2]).abs().max()) < 1e-4
     assert float((ev["handle_link_pos"][:, 0] - closed[:, 0]).max()) < -0.5 and float((ev["handle_link_pos"][:, 1] - closed[:, 1]).min()) > 0.5
     env.close()
+
+
+def test_reference_benchmark_script(reference, capsys):
+    """mani_skill/examples/benchmarking/gpu_sim.py -- the script that defines BASELINE.json's metric (reset(seed=2022), 1000 steps of uniform actions, then 1000 steps
+    with a reset every 200) -- `main(Args(...))` unmodified on the backend (examples/run_reference_benchmark.py is the launcher for a B200)."""
+    from mani_skill.examples.benchmarking.gpu_sim import Args, main
+    main(Args(env_id="PickCube-v1", obs_mode="state", num_envs=4, sim_freq=100, control_freq=20))
+    out = capsys.readouterr().out
+    assert "env.step:" in out and "env.step+env.reset:" in out and "4 parallel environments, sim_backend=physx_cuda" in out

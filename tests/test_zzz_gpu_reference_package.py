@@ -269,3 +269,15 @@ def test_reference_benchmark_protocol_throughput(gym):
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
     print(f"\nREFERENCE_PYTHON_ON_SHIM PickCube-v1 state num_envs={n}: {n * steps / dt:.0f} env-steps/s ({1e3 * dt / steps:.2f} ms/step)")
     env.close()
+
+
+@_first_gpu_run
+def test_reference_benchmark_script_itself(gym, capsys):
+    """the reference's own mani_skill/examples/benchmarking/gpu_sim.py `main`, unmodified (what examples/run_reference_benchmark.py launches): 1000 steps + 1000 steps
+    with resets of PickCube-v1 at 1024 sub-scenes; its report is echoed into the test log"""
+    from mani_skill.examples.benchmarking.gpu_sim import Args, main
+    main(Args(env_id="PickCube-v1", obs_mode="state", num_envs=4 if EMU else 1024, sim_freq=100, control_freq=20))
+    out = capsys.readouterr().out
+    assert "env.step:" in out and "env.step+env.reset:" in out
+    with capsys.disabled():
+        print("\nREFERENCE gpu_sim.py ON THE SHIM:\n" + "\n".join(l for l in out.splitlines() if "steps/s" in l or "Task ID" in l))
