@@ -679,6 +679,16 @@ class PhysxArticulationLinkComponent(PhysxRigidBodyComponent):
         if self.parent is None:
             self.articulation._root_pose = pose
 
+    @property
+    def pose(self):
+        return self._pose
+
+    @pose.setter
+    def pose(self, pose):   # the root link's pose IS the articulation's root pose (mani_skill/utils/structs/articulation.py:857-859 sets it through the link)
+        PhysxRigidBaseComponent.pose.fset(self, pose)
+        if self.parent is None:
+            self.articulation._root_pose = pose
+
 
 class PhysxArticulationLink(PhysxArticulationLinkComponent):
     pass

@@ -159,10 +159,11 @@ def installed(precision="f32"):
         return s if isinstance(s, OracleCpuSystem) else None
 
     Link, Art = physx.PhysxArticulationLinkComponent, physx.PhysxArticulation
-    saved = {(cls, k): cls.__dict__[k] for cls, k in [(physx, "PhysxCpuSystem"), (Art, "qvel"), (Art, "qf"), (Art, "qacc"), (Art, "get_qvel"), (Art, "set_qvel"),
-                                                         (Art, "get_qf"), (Art, "set_qf"), (Art, "get_qacc"), (Art, "compute_passive_force")]}
-    added = [(Link, "_body_pose"), (Link, "pose"), (Link, "linear_velocity"), (Link, "angular_velocity"), (Link, "entity_pose"),
-             (physx.PhysxRigidBaseComponent, "entity_pose")]
+    _MISSING = object()
+    patched = [(physx, "PhysxCpuSystem"), (Art, "qvel"), (Art, "qf"), (Art, "qacc"), (Art, "get_qvel"), (Art, "set_qvel"), (Art, "get_qf"), (Art, "set_qf"), (Art, "get_qacc"),
+               (Art, "compute_passive_force"), (Link, "_body_pose"), (Link, "pose"), (Link, "linear_velocity"), (Link, "angular_velocity"),
+               (physx.PhysxRigidBaseComponent, "entity_pose")]
+    saved = {(cls, k): cls.__dict__.get(k, _MISSING) for cls, k in patched}
 
     # ---- articulation: generalized velocities / forces are stored (the GPU objects return zeros: live values are in the cuda buffers)
     def _stored(name):
@@ -181,7 +182,7 @@ def installed(precision="f32"):
     Art.compute_passive_force = lambda self, gravity=True, coriolis_and_centrifugal=True: np.zeros(self.dof, dtype=np.float32)
 
     # ---- links: pose / velocity follow (root pose, qpos, qvel)
-    base_pose = physx.PhysxRigidBaseComponent.pose
+    link_pose_setter = Link.__dict__["pose"].fset
 
     def link_body_pose(self):
         s = _live(self)
@@ -201,7 +202,7 @@ def installed(precision="f32"):
         return property(get, put)
 
     Link._body_pose = link_body_pose
-    Link.pose = property(lambda self: link_body_pose(self), base_pose.fset)
+    Link.pose = property(lambda self: link_body_pose(self), link_pose_setter)
     Link.linear_velocity, Link.angular_velocity = link_velocity("linear_velocity"), link_velocity("angular_velocity")
     physx.PhysxRigidBaseComponent.entity_pose = property(lambda self: self.entity.pose if self.entity is not None else self.pose)
     physx.PhysxCpuSystem = OracleCpuSystem
@@ -209,7 +210,8 @@ def installed(precision="f32"):
         yield OracleCpuSystem
     finally:
         for (cls, k), v in saved.items():
-            setattr(cls, k, v)
-        for cls, k in added:
-            if k in cls.__dict__:
-                delattr(cls, k)
+            if v is _MISSING:
+                if k in cls.__dict__:
+                    delattr(cls, k)
+            else:
+                setattr(cls, k, v)

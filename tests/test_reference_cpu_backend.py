@@ -27,26 +27,31 @@ def test_the_product_has_no_cpu_system(reference):  # noqa: F811
         physx.PhysxCpuSystem()
 
 
-def test_configs0_cpu_rollout_equals_the_gpu_path(cpu_backend):
-    """BASELINE.json configs[0] (PickCube-v1, num_envs=1, CPU simulation, state observations) against sub-scene 2 of the same task on the GPU path, both
-    through the reference's own env code, from the same state and with the same actions: observations (q, qdot, tcp / cube / goal poses) and rewards within
-    1e-4 after 20 control steps = 100 substeps (north_star's tolerance; measured 1e-6)."""
+@pytest.mark.parametrize("task", ["PickCube-v1", "PegInsertionSide-v1", "OpenCabinetDrawer-v1", "StackCube-v1", "PushCube-v1"])
+def test_cpu_rollout_equals_the_gpu_path(cpu_backend, task):
+    """BASELINE.json configs[0] (PickCube-v1, num_envs=1, CPU simulation, state observations) -- and the same for the other two tasks north_star names and two more --
+    against a sub-scene of the same task on the GPU path, both through the reference's own env code, from the same state and with the same actions: observations
+    (q, qdot, tcp / object / goal poses) and rewards within 1e-4 after 20 control steps = 100 substeps (north_star's tolerance; measured 1e-6 ... 4e-5).
+    `reconfiguration_freq=0`: the reference rebuilds a single-env CPU scene on every reset by default (sapien_env.py), which would draw new peg / cabinet geometry."""
     gym = cpu_backend
-    cpu = gym.make("PickCube-v1", num_envs=1, obs_mode="state", sim_backend="physx_cpu")
-    gpu = gym.make("PickCube-v1", num_envs=4, obs_mode="state", sim_backend="physx_cuda")
+    k = 2 if task == "PickCube-v1" else 0     # per-sub-scene geometry (peg, cabinet id) is drawn from seed 2022 + i: sub-scene 0 is the one a single env builds
+    cpu = gym.make(task, num_envs=1, obs_mode="state", sim_backend="physx_cpu", reconfiguration_freq=0)
+    gpu = gym.make(task, num_envs=4, obs_mode="state", sim_backend="physx_cuda")
     assert not cpu.unwrapped.gpu_sim_enabled and gpu.unwrapped.gpu_sim_enabled
     cpu.reset(seed=3)
     gpu.reset(seed=3)
-    one = lambda d, i: {k: one(v, i) for k, v in d.items()} if isinstance(d, dict) else d[i:i + 1]
-    cpu.unwrapped.set_state_dict(one(gpu.unwrapped.get_state_dict(), 2))
-    assert float((cpu.unwrapped.get_obs()[0] - gpu.unwrapped.get_obs()[2]).abs().max()) < 1e-6
+    one = lambda d, i: {kk: one(v, i) for kk, v in d.items()} if isinstance(d, dict) else d[i:i + 1]
+    cpu.unwrapped.set_state_dict(one(gpu.unwrapped.get_state_dict(), k))
+    assert float((cpu.unwrapped.get_obs()[0] - gpu.unwrapped.get_obs()[k]).abs().max()) < 1e-6
     g = torch.Generator().manual_seed(0)
+    A = cpu.action_space.shape[-1]
     for i in range(20):
-        a = 2 * torch.rand((4, 8), generator=g) - 1
+        a = 2 * torch.rand((4, A), generator=g) - 1
         og, rg, _, _, ig = gpu.step(a)
-        oc, rc, _, _, ic = cpu.step(a[2])
-        assert float((oc[0] - og[2]).abs().max()) < 1e-4 and float((rc[0] - rg[2]).abs()) < 1e-4, i
-        assert bool(ic["is_grasped"][0]) == bool(ig["is_grasped"][2])
+        oc, rc, _, _, ic = cpu.step(a[k])
+        assert float((oc[0] - og[k]).abs().max()) < 1e-4 and float((rc[0] - rg[k]).abs()) < 1e-4, i
+        if "is_grasped" in ic:
+            assert bool(ic["is_grasped"][0]) == bool(ig["is_grasped"][k])
     cpu.close()
     gpu.close()
 
