@@ -21,6 +21,30 @@ def cpu_backend(reference):  # noqa: F811
         yield reference
 
 
+def test_float64_cpu_backend_against_the_float32_gpu_path(reference):  # noqa: F811
+    """the same rollout with the FLOAT64 build of the oracle behind the CPU path: the float32 device code stays within north_star's 1e-4 of a double-precision
+    restatement over 100 substeps of random actions (PickCube-v1)"""
+    from cpu_sim_double import installed
+    gym = reference
+    with installed("f64"):
+        cpu = gym.make("PickCube-v1", num_envs=1, obs_mode="state", sim_backend="physx_cpu")
+        gpu = gym.make("PickCube-v1", num_envs=2, obs_mode="state", sim_backend="physx_cuda")
+        cpu.reset(seed=4)
+        gpu.reset(seed=4)
+        one = lambda d, i: {kk: one(v, i) for kk, v in d.items()} if isinstance(d, dict) else d[i:i + 1]
+        cpu.unwrapped.set_state_dict(one(gpu.unwrapped.get_state_dict(), 1))
+        g = torch.Generator().manual_seed(1)
+        worst = 0.0
+        for _ in range(20):
+            a = 2 * torch.rand((2, 8), generator=g) - 1
+            og = gpu.step(a)[0]
+            oc = cpu.step(a[1])[0]
+            worst = max(worst, float((oc[0] - og[1]).abs().max()))
+        assert worst < 1e-4, worst
+        cpu.close()
+        gpu.close()
+
+
 def test_the_product_has_no_cpu_system(reference):  # noqa: F811
     from sapien import physx
     with pytest.raises(RuntimeError, match="no CPU simulation"):
