@@ -27,6 +27,26 @@ from .model import (SHAPE_BOX, SHAPE_CAPSULE, SHAPE_CONVEX, SHAPE_PLANE, SHAPE_S
                     cylinder_shape, pose7, pose_inv, pose_mul, qmat, qrot, sym6)
 
 
+class Device:
+    """`sapien.Device("cuda" | "cuda:n" | "cpu")` (mani_skill/envs/utils/system/backend.py:60-91)."""
+
+    def __init__(self, name: str):
+        self.name = name
+        kind, _, idx = name.partition(":")
+        if kind not in ("cpu", "cuda"):
+            raise ValueError(f"unknown device {name!r}")
+        self.type, self.cuda_id = kind, (int(idx) if idx else 0)
+
+    def is_cuda(self) -> bool:
+        return self.type == "cuda"
+
+    def is_cpu(self) -> bool:
+        return self.type == "cpu"
+
+    def __repr__(self):
+        return f"Device({self.name!r})"
+
+
 class Pose:
     """`sapien.Pose`: one rigid transform, numpy float32, quaternion wxyz (`.p .q`, `*`, `.inv()`,
     `.to_transformation_matrix()`, `Pose(4x4)`, `set_p/set_q`, `.rpy`)."""

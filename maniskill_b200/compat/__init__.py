@@ -27,14 +27,11 @@ def install(force_sapien: bool = False) -> str:
     """Make `import sapien`, `import gymnasium`, ... resolvable.  Returns the directory that was added to sys.path."""
     if SITE not in sys.path:
         sys.path.append(SITE)   # last: real packages take precedence
-    if force_sapien or importlib.util.find_spec("sapien") is None or not _is_ours("sapien"):
-        pass
-    # a `sapien` stub registered by an earlier maniskill_b200.sapien_shim.install() must not shadow the package
+    # a stub registered as `sapien` (a module object without a file: a test's mock) must not shadow the package; a really installed sapien is left alone
     mod = sys.modules.get("sapien")
-    if mod is not None and not getattr(mod, "__file__", "").startswith(SITE):
-        if getattr(mod, "__name__", "") == "maniskill_b200.sapien_shim":
-            for k in [k for k in sys.modules if k == "sapien" or k.startswith("sapien.")]:
-                del sys.modules[k]
+    if mod is not None and not isinstance(getattr(mod, "__file__", None), str):
+        for k in [k for k in sys.modules if k == "sapien" or k.startswith("sapien.")]:
+            del sys.modules[k]
     return SITE
 
 

@@ -20,7 +20,7 @@ import sys as _sys
 import numpy as _np
 
 from maniskill_b200.building import Pose as _BPose
-from maniskill_b200.sapien_shim import Device  # noqa: F401
+from maniskill_b200.building import Device  # noqa: F401
 
 __version__ = "3.0.0.b200sim"
 

@@ -22,7 +22,7 @@ from ..backend import (BUF_ALL, BUF_APPLY_ALL, BUF_QF, BUF_QPOS, BUF_QVEL, BUF_R
                        BUF_TARGET_QVEL)
 from ..model import CompiledModel, SceneDesc, SimParams
 from ..observations import parse_obs_mode, sensor_data_to_pointcloud
-from ..sapien_shim import Device
+from ..building import Device
 from ..visualization import camera_observations_to_images, tile_images
 from ..structs import Actor, Articulation, Pose
 

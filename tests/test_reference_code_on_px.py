@@ -202,21 +202,32 @@ def test_reference_texture_transforms_on_our_render_targets(reference_module):
             assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), (cam["uid"], k)
 
 
+def _install_sapien():
+    """`import sapien` = the shim package (maniskill_b200/compat/site/sapien), also where an earlier test left MagicMock modules under that name"""
+    import maniskill_b200.compat as compat
+    compat.install()
+    for k in [k for k in sys.modules if k == "sapien" or k.startswith("sapien.")]:
+        f = getattr(sys.modules[k], "__file__", None)
+        if not (isinstance(f, str) and f.startswith(compat.SITE)):
+            del sys.modules[k]
+    import sapien
+    return sapien
+
+
 def test_reference_pose_struct_over_the_sapien_shim():
-    """`install()` makes `import sapien` resolve to maniskill_b200/sapien_shim.py; the reference's REAL batched `Pose`
+    """`compat.install()` makes `import sapien` resolve to maniskill_b200/compat/site/sapien; the reference's REAL batched `Pose`
     (mani_skill/utils/structs/pose.py, loaded with only its non-sapien imports stubbed) then accepts the shim's `sapien.Pose` objects:
     `Pose.create(sapien.Pose)`, `.sp` round trip, products against our own batched Pose."""
     saved = dict(sys.modules)
     try:
-        from maniskill_b200 import sapien_shim
-        assert sapien_shim.install(force=True)
-        import sapien
+        sapien = _install_sapien()
         import sapien.physx as physx
-        assert sapien.Pose is sapien_shim.Pose and physx.PhysxGpuSystem.__name__ == "PhysxGpuSystem" and not physx.is_gpu_enabled()
+        from maniskill_b200 import building
+        assert issubclass(sapien.Pose, building.Pose) and physx.PhysxGpuSystem.__name__ == "PhysxGpuSystem"
         physx.enable_gpu()
         assert physx.is_gpu_enabled() and sapien.Device("cuda:1").is_cuda() and sapien.Device("cuda:1").cuda_id == 1 and sapien.Device("cpu").is_cpu()
-        with pytest.raises(AttributeError):
-            sapien.Entity            # not part of the shim: fails loudly rather than pretending
+        with pytest.raises(RuntimeError, match="no CPU simulation"):
+            physx.PhysxCpuSystem()   # not part of the product: fails loudly rather than pretending
         rot = _load_reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
         common = MagicMock()
         common.to_tensor = lambda x, device=None: torch.as_tensor(x, device=device).float() if not isinstance(x, torch.Tensor) else x.to(device)
@@ -254,9 +265,9 @@ def test_reference_task_logic_on_our_live_env(reference_module, task):
     """The reference's own task class -- `evaluate`, `_get_obs_extra`, `compute_dense_reward` of mani_skill/envs/tasks/tabletop/<task>.py --
     called with `self` = OUR running env (same attribute names: actors, agent, tcp, obs_mode_struct, device ...) at every step of a random
     rollout on the emulated backend; each result must equal what the mirror's own methods return on the same state."""
-    from maniskill_b200 import sapien_shim, structs
+    from maniskill_b200 import structs
     fname, cls_name = TASK_FILES[task]
-    sapien_shim.install(force=True)          # `sapien.Pose(...)` inside the task code is the shim's Pose, not a mock
+    _install_sapien()          # `sapien.Pose(...)` inside the task code is the shim's Pose, not a mock
     rot = reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
     for name, attrs in (("mani_skill.envs.sapien_env", dict(BaseEnv=object)),
                         ("mani_skill.utils.registration", dict(register_env=lambda *a, **k: (lambda cls: cls))),
@@ -306,9 +317,9 @@ def test_reference_episode_initialisation_on_our_env(reference_module, task):
     `UniformPlacementSampler` run against our env object (actors' `set_pose`, `agent.reset`, the episode RNG, `sapien.Pose` from the shim).
     The resulting simulation state must equal the state after the mirror's own reset with the same seed: same random streams, same
     layout, same robot configuration."""
-    from maniskill_b200 import sapien_shim, structs, utils as U
+    from maniskill_b200 import structs, utils as U
     fname, cls_name = TASK_FILES[task]
-    sapien_shim.install(force=True)
+    _install_sapien()
     rot = reference_module("/root/reference/mani_skill/utils/geometry/rotation_conversions.py", as_name="mani_skill.utils.geometry.rotation_conversions")
     stubs = dict([("mani_skill.envs.sapien_env", dict(BaseEnv=object)), ("mani_skill.utils.registration", dict(register_env=lambda *a, **k: (lambda cls: cls))),
                   ("mani_skill.utils.structs.pose", dict(Pose=structs.Pose)), ("mani_skill.utils.structs", dict(Pose=structs.Pose)),
@@ -352,8 +363,7 @@ def test_reference_panda_grasp_checks_on_our_agent_during_a_scripted_grasp(refer
     """mani_skill/agents/robots/panda/panda.py `is_grasping` / `is_static` (with the real `common.compute_angle_between`) called with `self` =
     our agent while a scripted pick closes the gripper on the cube and lifts it: the reference's verdict follows ours through approach,
     grasp and lift (contact forces come from the px-level queries of the emulated device code)."""
-    from maniskill_b200 import sapien_shim
-    sapien_shim.install(force=True)
+    _install_sapien()
     for name, attrs in (("mani_skill.agents.base_agent", dict(BaseAgent=object, Keyframe=lambda **k: None)),
                         ("mani_skill.agents.registration", dict(register_agent=lambda *a, **k: (lambda cls: cls)))):
         m = MagicMock(name=name, **attrs)
@@ -633,8 +643,7 @@ def test_reference_flatten_wrappers_on_our_live_observations(reference_module):
 def test_reference_fetch_checks_on_our_agent(reference_module):
     """mani_skill/agents/robots/fetch/fetch.py `is_static` / `is_grasping` with `self` = our Fetch while it drives around and moves its arm
     (OpenCabinetDrawer-v1): same verdicts as the mirror, including the base-velocity threshold."""
-    from maniskill_b200 import sapien_shim
-    sapien_shim.install(force=True)
+    _install_sapien()
     for name, attrs in (("mani_skill.agents.base_agent", dict(BaseAgent=object, Keyframe=lambda **k: None, DictControllerConfig=dict)),
                         ("mani_skill.agents.registration", dict(register_agent=lambda *a, **k: (lambda cls: cls)))):
         m = MagicMock(name=name, **attrs)
