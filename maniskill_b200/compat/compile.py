@@ -380,8 +380,10 @@ def compile_system(system, config) -> Compiled:
             body_type = "static"
         else:
             body_type = "kinematic" if b.kinematic else "dynamic"
-            if any(b.locked_motion_axes):
-                raise NotImplementedError("locked motion axes are not supported by the b200sim backend")
+            if all(b.locked_motion_axes):
+                body_type = "kinematic"      # all six axes locked (base.py:343-354): the body only moves when its pose is set -- a kinematic body
+            elif any(b.locked_motion_axes):
+                raise NotImplementedError("partially locked motion axes are not supported by the b200sim backend (all six locked = kinematic is)")
         shapes = _body_shapes(b, others, N)
         pose0 = _p7(b.pose)
         if body_type == "static" and others:
