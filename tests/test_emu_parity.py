@@ -117,10 +117,21 @@ class _EmuAsOracle:
     def pair_impulse(self, a, b):
         return self.w.pair_impulse(a, b).astype(np.float64)
 
+    def set_joint(self, name, arr):
+        buf = getattr(self.w, name)
+        a = np.asarray(arr, dtype=np.float32).reshape(buf.shape[0], -1)
+        buf[:, :a.shape[1]] = a
+        self.w.apply()
+
+    def get_joint(self, name):
+        self.w.fetch()
+        return getattr(self.w, name).astype(np.float64).copy()
+
 
 def test_device_code_reproduces_the_analytic_answers_directly(monkeypatch):
-    """Three of the known-answer tests of tests/test_oracle_kat.py run on the emulated DEVICE code instead of the oracle: the ball
-    that ends up rolling at 5/7 v0, the stack of three boxes carrying 3 m g, the cooked cylinder resting on a box."""
+    """Known-answer tests of tests/test_oracle_kat.py run on the emulated DEVICE code instead of the oracle: the ball that ends up rolling at
+    5/7 v0, the stack of three boxes carrying 3 m g, the cooked cylinder resting on a box, the spinning box, and the two articulated chains against their
+    Lagrangian equations (double pendulum; spatial chain with a prismatic joint)."""
     import test_oracle_kat as K
     monkeypatch.setattr(K, "OracleWorld", lambda cm, precision="f64": _EmuAsOracle(cm))
     K.test_sliding_ball_ends_up_rolling_at_five_sevenths_of_its_speed("box")
@@ -128,3 +139,6 @@ def test_device_code_reproduces_the_analytic_answers_directly(monkeypatch):
     K.test_stack_of_three_boxes_stays_put()
     K.test_cooked_cylinder_rests_on_a_facet_and_weighs_mg("box", True)
     K.test_torsional_friction_of_a_spinning_box()
+    # the articulated-body recursion of the DEVICE code (float32) against the independently integrated equations of motion
+    K.test_double_pendulum_follows_the_lagrangian_equations()
+    K.test_spatial_chain_follows_its_numerical_lagrangian()
