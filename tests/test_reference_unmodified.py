@@ -382,3 +382,19 @@ def test_reference_benchmark_script(reference, capsys):
     main(Args(env_id="PickCube-v1", obs_mode="state", num_envs=4, sim_freq=100, control_freq=20))
     out = capsys.readouterr().out
     assert "env.step:" in out and "env.step+env.reset:" in out and "4 parallel environments, sim_backend=physx_cuda" in out
+
+
+def test_reference_reconfigure_rebuilds_the_world(reference):
+    """`reset(options={"reconfigure": True})` (sapien_env.py:725-760; what tests/test_gpu_envs.py::test_env_reconfiguration exercises with YCB assets): the reference
+    clears its scene and builds a new one -- a new batched world with newly drawn per-sub-scene peg geometry, which then steps."""
+    gym = reference
+    env = gym.make("PegInsertionSide-v1", num_envs=4, obs_mode="state", sim_backend="physx_cuda")
+    env.reset(seed=1)
+    e = env.unwrapped
+    w1, h1 = e.scene.px._world, e.peg_half_sizes.clone()
+    env.reset(seed=5, options=dict(reconfigure=True))
+    assert e.scene.px._world is not w1 and float((h1 - e.peg_half_sizes).abs().max()) > 1e-3
+    for _ in range(2):
+        obs, r, _, _, _ = env.step(torch.as_tensor(env.action_space.sample()))
+    assert obs.shape == (4, 43) and torch.isfinite(obs).all() and int(e.scene.px._world.overflow_flag.item()) == 0
+    env.close()
