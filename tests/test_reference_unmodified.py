@@ -398,3 +398,28 @@ def test_reference_reconfigure_rebuilds_the_world(reference):
         obs, r, _, _, _ = env.step(torch.as_tensor(env.action_space.sample()))
     assert obs.shape == (4, 43) and torch.isfinite(obs).all() and int(e.scene.px._world.overflow_flag.item()) == 0
     env.close()
+
+
+def test_reference_wrappers_and_reward_modes(reference):
+    """The reference's own `FlattenRGBDObservationWrapper` (mani_skill/utils/wrappers/flatten.py -- what its PPO-RGB baselines wrap), `ManiSkillVectorEnv` with
+    `record_metrics` over the time limit (final_info / episode statistics at step 50, auto-reset), and the four reward modes, on the backend."""
+    gym = reference
+    from mani_skill.utils.wrappers.flatten import FlattenRGBDObservationWrapper
+    from mani_skill.vector.wrappers.gymnasium import ManiSkillVectorEnv
+    rewards = {}
+    for mode in ("dense", "normalized_dense", "sparse", "none"):
+        env = gym.make("PickCube-v1", num_envs=4, obs_mode="state", reward_mode=mode)
+        env.reset(seed=0)
+        rewards[mode] = env.step(torch.zeros(4, 8))[1].float()
+        env.close()
+    assert torch.allclose(rewards["normalized_dense"], rewards["dense"] / 5.0, atol=1e-6) and (rewards["sparse"] == 0).all() and (rewards["none"] == 0).all()
+    env = FlattenRGBDObservationWrapper(gym.make("PickCube-v1", num_envs=4, obs_mode="rgbd"), rgb=True, depth=True, state=True)
+    env = ManiSkillVectorEnv(env, auto_reset=True, ignore_terminations=True, record_metrics=True)
+    obs, _ = env.reset(seed=0)
+    assert obs["state"].shape == (4, 29) and obs["rgb"].shape == (4, 128, 128, 3) and obs["rgb"].dtype == torch.uint8 and obs["depth"].shape == (4, 128, 128, 1)
+    for i in range(50):
+        obs, r, te, tr, info = env.step(torch.as_tensor(env.action_space.sample()))
+        assert ("final_info" in info) == (i == 49)
+    assert tr.all() and not te.any() and (info["final_info"]["episode"]["episode_len"] == 50).all() and info["final_info"]["episode"]["return"].shape == (4,)
+    assert (env.base_env.elapsed_steps == 0).all() and obs["rgb"].shape == (4, 128, 128, 3)     # already the first observation of the next episode
+    env.close()
