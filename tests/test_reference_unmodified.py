@@ -423,3 +423,10 @@ def test_reference_wrappers_and_reward_modes(reference):
     assert tr.all() and not te.any() and (info["final_info"]["episode"]["episode_len"] == 50).all() and info["final_info"]["episode"]["return"].shape == (4,)
     assert (env.base_env.elapsed_steps == 0).all() and obs["rgb"].shape == (4, 128, 128, 3)     # already the first observation of the next episode
     env.close()
+    # `env.render()` of the three render modes (sapien_env.py:1373-1440): the human camera, the tiled sensor pictures, both
+    for mode, shape in (("rgb_array", (2, 512, 512, 3)), ("sensors", (2, 128, 256, 3)), ("all", (2, 512, 640, 3))):
+        env = gym.make("PickCube-v1", num_envs=2, obs_mode="rgbd", render_mode=mode)
+        env.reset(seed=0)
+        img = env.render()
+        assert tuple(img.shape) == shape and img.dtype == torch.uint8 and float(img.float().std()) > 5
+        env.close()
