@@ -116,7 +116,8 @@ def test_grasp_detection_agrees_between_the_contact_apis(cpu_backend):
     ("test_envs.py:test_env_seeded_sequence_reset", ()), ("test_envs.py:test_states", ("PickCube-v1",)), ("test_envs.py:test_env_control_modes", ("PickCube-v1", "pd_joint_delta_pos")),
     ("test_envs.py:test_env_control_modes", ("PickCube-v1", "pd_ee_delta_pose")), ("test_envs.py:test_robots", ("PickCube-v1", "panda")),
     ("test_envs.py:test_env_raise_value_error_for_nan_actions", ()), ("test_envs.py:test_envs_obs_modes", ("PickCube-v1", "state_dict")),
-    ("test_envs.py:test_envs_obs_modes", ("PickCube-v1", "state")),
+    ("test_envs.py:test_envs_obs_modes", ("PickCube-v1", "state")), ("test_envs.py:test_states", ("StackCube-v1",)), ("test_envs.py:test_states", ("PegInsertionSide-v1",)),
+    ("test_examples.py:test_demo_random_action", ()),
 ], ids=lambda v: "-".join(v) if isinstance(v, tuple) else str(v))
 def test_reference_own_cpu_tests(cpu_backend, fn, args):
     """/root/reference/tests executed as they are.  tests/test_ik_controller.py is the reference's one numeric CPU-vs-GPU test (end-effector pose after 5 / 20
