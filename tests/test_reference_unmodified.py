@@ -430,3 +430,18 @@ def test_reference_wrappers_and_reward_modes(reference):
         img = env.render()
         assert tuple(img.shape) == shape and img.dtype == torch.uint8 and float(img.float().std()) > 5
         env.close()
+
+
+@pytest.mark.parametrize("env_id", ["FrankaPickCubeBenchmark-v1", "FrankaMoveBenchmark-v1", "CartpoleBalanceBenchmark-v1"])
+def test_reference_benchmark_environments(reference, env_id):
+    """mani_skill/examples/benchmarking/envs: the environments the reference publishes its simulator comparisons with (gpu_sim.py's BENCHMARK_ENVS, configurable
+    camera count / resolution) build, reset, step and render unchanged."""
+    gym = reference
+    import mani_skill.examples.benchmarking.envs  # noqa: F401
+    env = gym.make(env_id, num_envs=4, obs_mode="rgb", num_cameras=2, camera_width=64, camera_height=48)
+    obs, _ = env.reset(seed=0)
+    obs, r, _, _, _ = env.step(torch.as_tensor(env.action_space.sample()))
+    cams = obs["sensor_data"]
+    assert len(cams) == 2 and all(c["rgb"].shape == (4, 48, 64, 3) and c["rgb"].dtype == torch.uint8 for c in cams.values())
+    assert torch.isfinite(r).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
+    env.close()
