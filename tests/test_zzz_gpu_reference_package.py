@@ -286,3 +286,18 @@ def test_reference_benchmark_script_itself(gym, capsys):
     assert "env.step:" in out and "env.step+env.reset:" in out
     with capsys.disabled():
         print("\nREFERENCE gpu_sim.py ON THE SHIM:\n" + "\n".join(l for l in out.splitlines() if "steps/s" in l or "Task ID" in l))
+
+
+@_first_gpu_run
+@pytest.mark.parametrize("env_id,obs_mode", [("CartpoleBalanceBenchmark-v1", "state"), ("FrankaPickCubeBenchmark-v1", "rgb")])
+def test_reference_published_benchmark_configurations(gym, capsys, env_id, obs_mode):
+    """the configurations of the reference's published simulator comparison (docs/source/user_guide/additional_resources/performance_benchmarking.md:
+    `gpu_sim.py -e <benchmark env> -n N -o state | rgb --num-cams 1 --cam-width 128 --cam-height 128`, its default sim_freq 120 / control_freq 60), through its own
+    script; the report is echoed into the test log"""
+    import mani_skill.examples.benchmarking.envs  # noqa: F401
+    from mani_skill.examples.benchmarking.gpu_sim import Args, main
+    main(Args(env_id=env_id, obs_mode=obs_mode, num_envs=4 if EMU else 1024, num_cams=1, cam_width=128, cam_height=128))
+    out = capsys.readouterr().out
+    assert "env.step:" in out and "env.step+env.reset:" in out
+    with capsys.disabled():
+        print("\nREFERENCE gpu_sim.py ON THE SHIM:\n" + "\n".join(l for l in out.splitlines() if "steps/s" in l or "Task ID" in l or "obs_mode" in l))

@@ -32,6 +32,15 @@ def install(reference="/root/reference", force=False) -> str:
         shutil.copytree(reference, src, ignore=shutil.ignore_patterns(".git", "docs", "figures"))
         subprocess.check_call([sys.executable, "-m", "pip", "install", "-q", "--no-index", "--no-build-isolation", "--no-deps", "--find-links", "/opt/wheelhouse",
                                "--target", TARGET, src], cwd=tmp)
+    # small data files the wheel leaves out (its package_data globs miss e.g. examples/benchmarking/envs/maniskill/assets/cartpole.xml): copied as they are
+    src_pkg, dst_pkg = os.path.join(reference, "mani_skill"), os.path.join(TARGET, "mani_skill")
+    for r, _, fs in os.walk(src_pkg):
+        for f in fs:
+            a = os.path.join(r, f)
+            b = os.path.join(dst_pkg, os.path.relpath(a, src_pkg))
+            if not os.path.exists(b) and not f.endswith((".pyc",)) and os.path.getsize(a) < (1 << 20) and "__pycache__" not in a:
+                os.makedirs(os.path.dirname(b), exist_ok=True)
+                shutil.copyfile(a, b)
     assets = os.path.join(TARGET, "mani_skill", "assets")
     shutil.rmtree(os.path.join(assets, "environment_maps"), ignore_errors=True)
     robots = os.path.join(assets, "robots")
