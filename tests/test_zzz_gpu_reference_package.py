@@ -253,7 +253,7 @@ def test_open_cabinet_drawer(gym):
 
 
 @_first_gpu_run
-def test_reference_benchmark_protocol_throughput(gym):
+def test_reference_benchmark_protocol_throughput(gym, capsys):
     """mani_skill/examples/benchmarking/gpu_sim.py:91-108 on the reference's own env object: reset(seed=2022), a warm-up step, reset, then random actions in
     [-1, 1] with a device synchronisation either side; prints env-steps/s of the UNMODIFIED reference python on this backend (python-bound: ~100 torch launches
     per step come from the reference's own obs / reward code -- bench.py times the fused mirror path).  No threshold beyond 'it runs and stays finite'."""
@@ -272,7 +272,8 @@ def test_reference_benchmark_protocol_throughput(gym):
         torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
-    print(f"\nREFERENCE_PYTHON_ON_SHIM PickCube-v1 state num_envs={n}: {n * steps / dt:.0f} env-steps/s ({1e3 * dt / steps:.2f} ms/step)")
+    with capsys.disabled():
+        print(f"\nREFERENCE_PYTHON_ON_SHIM PickCube-v1 state num_envs={n}: {n * steps / dt:.0f} env-steps/s ({1e3 * dt / steps:.2f} ms/step)")
     env.close()
 
 
