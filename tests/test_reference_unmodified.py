@@ -445,3 +445,26 @@ def test_reference_benchmark_environments(reference, env_id):
     assert len(cams) == 2 and all(c["rgb"].shape == (4, 48, 64, 3) and c["rgb"].dtype == torch.uint8 for c in cams.values())
     assert torch.isfinite(r).all() and int(env.unwrapped.scene.px._world.overflow_flag.item()) == 0
     env.close()
+
+
+def test_reference_reset_to_env_states(reference):
+    """`reset(options={"reset_to_env_states": {"env_states": ...}})` (sapien_env.py:935-944; SURVEY 8(c): how a cross-backend parity run copies states instead of
+    relying on seeds), full and partial, with a state dictionary and with the flat state."""
+    gym = reference
+    env = gym.make("PickCube-v1", num_envs=4, obs_mode="state", sim_backend="physx_cuda")
+    env.reset(seed=0)
+    for _ in range(3):
+        env.step(torch.as_tensor(env.action_space.sample()))
+    e = env.unwrapped
+    sd, flat, obs_then = e.get_state_dict(), e.get_state().clone(), e.get_obs().clone()
+    for _ in range(3):
+        env.step(torch.as_tensor(env.action_space.sample()))
+    obs, _ = env.reset(options=dict(reset_to_env_states=dict(env_states=sd)))
+    assert float((e.get_state() - flat).abs().max()) < 1e-6 and float((obs - obs_then).abs().max()) < 1e-4 and (e.elapsed_steps == 0).all()
+    env.step(torch.as_tensor(env.action_space.sample()))
+    moved = e.get_state().clone()
+    idx = torch.tensor([1, 2])
+    env.reset(options=dict(env_idx=idx, reset_to_env_states=dict(env_states=flat[idx])))
+    now = e.get_state()
+    assert float((now[idx] - flat[idx]).abs().max()) < 1e-6 and float((now[[0, 3]] - moved[[0, 3]]).abs().max()) < 1e-6
+    env.close()
