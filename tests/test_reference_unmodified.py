@@ -468,3 +468,26 @@ def test_reference_reset_to_env_states(reference):
     now = e.get_state()
     assert float((now[idx] - flat[idx]).abs().max()) < 1e-6 and float((now[[0, 3]] - moved[[0, 3]]).abs().max()) < 1e-6
     env.close()
+
+
+def test_reference_peg_insertion_rollout_matches_the_mirror(reference):
+    """BASELINE.json configs[2]'s task: this repo's mirror (the path bench.py times for that side key) against the reference's own module on the same backend, same
+    seed -- per-sub-scene peg / hole geometry from the same `_batched_episode_rng` draws, observations and rewards equal over a rollout."""
+    import maniskill_b200 as ms
+    from emu_world import EmuBackendWorld
+    gym = reference
+    n = 4
+    ref = gym.make("PegInsertionSide-v1", num_envs=n, obs_mode="state", sim_backend="physx_cuda")
+    mir = ms.make("PegInsertionSide-v1", num_envs=n, obs_mode="state", world_factory=EmuBackendWorld)
+    o1, _ = ref.reset(seed=5)
+    o2, _ = mir.reset(seed=5)
+    assert o1.shape == (n, 43) and float((o1 - o2).abs().max()) < 1e-5
+    assert float((ref.unwrapped.peg_half_sizes - torch.as_tensor(mir.peg_half_sizes)).abs().max()) < 1e-7
+    g = torch.Generator().manual_seed(0)
+    for i in range(12):
+        a = 2 * torch.rand((n, 8), generator=g) - 1
+        o1, r1, _, _, i1 = ref.step(a)
+        o2, r2, _, _, i2 = mir.step(a)
+        assert float((o1 - o2).abs().max()) < 1e-4 and float((r1 - r2).abs().max()) < 1e-5, i
+        assert torch.equal(i1["success"], i2["success"])
+    ref.close()
