@@ -104,6 +104,7 @@ class OpenCabinetDrawerEnv(BaseEnv):
         cab = ArticulationRec("cabinet", robot, pose7([0, 0, 0]), link_mu={L["name"]: 1.0 for L in robot["links"]}, disable_gravity=False)
         cab.link_groups = {L["name"]: (1, 1, 1 << CABINET_COLLISION_BIT, 0) for L in robot["links"]}
         self.scene_desc.add_articulation(cab)
+        self._batched_episode_rng.choice(25)   # the reference draws the cabinet model first (:131, 25 ids in info_cabinet_drawer_train.json): same generator state afterwards
         self._link_ids = self._batched_episode_rng.randint(0, 2**31)  # which drawer is the target, per env (:132)
         self.scene_desc.add_actor(ActorRec("handle_link_goal", "kinematic",
                                            [ShapeRec(SHAPE_SPHERE, pose7(), np.array([0.02, 0, 0]), color=(0, 1, 0, 1), collide=False)], pose7(), hidden=True))
