@@ -7,7 +7,7 @@ collisions, a visual named `handle_<k>` on every drawer -- whose dimensions are 
 the same 0.8 x 0.5 x 0.9 m cabinet (two drawers and a door; the carcass of the mirror task's stand-in, maniskill_b200/envs/open_cabinet_drawer.py), differing per id
 only in the handle size.  The origin is the centre of the carcass, like the dataset's models (the task lifts the cabinet by minus its lowest collision point).
 
-usage: python tools/make_standin_partnet.py <reference>/mani_skill/assets/partnet_mobility/meta <out_asset_dir>      (then MS_ASSET_DIR=<out_asset_dir>)
+usage: python tools/make_standin_partnet.py <reference>/mani_skill/assets/partnet_mobility/meta <out_asset_dir> [door | mirror]      (then MS_ASSET_DIR=<out_asset_dir>)
 """
 import json
 import os
@@ -87,5 +87,5 @@ def main(meta_dir: str, out_dir: str, layout: str = "door"):
 
 
 if __name__ == "__main__":
-    n = main(sys.argv[1], sys.argv[2])
+    n = main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "door")
     print(f"wrote {n} stand-in cabinets under {sys.argv[2]}/data/partnet_mobility/dataset")
